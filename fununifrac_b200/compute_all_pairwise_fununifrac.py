@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Driver of the all-pairs FunUniFrac path: validate → tree → ingest → push-up → pairwise → save.
+
+Same ``main(args)`` contract, log milestones and output files as the reference's
+``src/compute_all_pairwise_fununifrac.py:20-108``; the compute section (:64-73) is one call into the
+CUDA engine instead of N Python push-ups and N(N-1)/2 numpy pair evaluations.
+"""
+import datetime
+import glob
+import logging
+import os
+import pickle
+from pathlib import Path
+
+import numpy as np
+
+import fununifrac_b200.factory.make_emd_input as make_emd_input
+import fununifrac_b200.factory.make_tree as make_tree
+import fununifrac_b200.utility.constant as constant
+import fununifrac_b200.utility.data_paths as data
+import fununifrac_b200.utility.kegg_db as kegg_db
+from fununifrac_b200 import engine, sparse_npz
+from fununifrac_b200.algorithms.emd_unifrac import EarthMoverDistanceUniFracSolver
+from fununifrac_b200.objects.func_tree import FuncTreeEmduInput
+
+
+def main(args):
+    logging.basicConfig(level=args.loglevel, format='%(asctime)s %(levelname)s: %(message)s')
+    edge_list_file = args.edge_list
+    out_dir = args.out_dir
+    out_id = args.out_id
+    file_dir = args.file_dir
+    file_pattern = args.file_pattern
+    abundance_key = args.abundance_key
+    num_threads = args.threads
+    brite = args.brite
+    make_diffab = args.diffab
+    unweighted = args.unweighted
+    is_L2 = args.L2
+    save_Ppushed = args.Ppushed
+    validate = bool(getattr(args, "validate", False))
+    ##############################################################################
+    # Validations (reference :37-46)
+    ##############################################################################
+    if brite not in kegg_db.instance.brites:
+        raise ValueError(f"{brite} is not a valid BRITE ID. Choices are: {kegg_db.instance.brites}")
+    data.check_data_abspath(edge_list_file)
+    file_pattern = os.path.join(file_dir, file_pattern)
+    data.check_data_abspaths(file_pattern)
+    fun_files = glob.glob(file_pattern)
+    fun_files = sorted(fun_files)  # this order is the basis of the output matrix
+    logging.info(f"Parsing graph")
+    ##############################################################################
+    # Main objects
+    ##############################################################################
+    solver = EarthMoverDistanceUniFracSolver(validate=validate)
+    tree = make_tree.import_graph(edge_list_file, directed=True)
+    logging.info(f"Converting graph into EMDUniFrac format")
+    input: FuncTreeEmduInput = make_emd_input.tree_to_EMDU_input(tree, brite)
+    logging.info(f"Computing pairwise distances in parallel")
+    ##############################################################################
+    # Computations
+    ##############################################################################
+    results = make_emd_input.parallel_functional_profile_to_vector(num_threads, fun_files, input, abundance_key,
+                                                                   unweighted)
+    files, X = make_emd_input.profiles_to_matrix(results, len(input.basis))
+    assert files == fun_files
+    mode = engine.MODE_L2 if is_L2 else engine.MODE_L1
+    logging.info(f"Computing pairwise distances")
+    diffabs_sparse = None
+    Ps_pushed = None
+    if save_Ppushed:
+        pushed = solver.push_up_batch(X, input, is_L2)  # float64, the reference's operation order
+        Ps_pushed = {file: pushed[i] for i, file in enumerate(fun_files)}
+    if not make_diffab:
+        dists = solver.all_pairs(X, input, is_L2)
+    else:
+        torch = engine._torch()
+        ctx = engine.context_for(input)
+        N = len(fun_files)
+        Xd = torch.from_numpy(X).to(f"cuda:{ctx.device}")
+        if validate:
+            PT = ctx.push_up_f64(Xd, mode)
+            dists = ctx.pairwise_f64(PT, N, mode).cpu().numpy()
+        else:
+            PT = ctx.push_up(Xd, mode)
+            dists = ctx.pairwise(PT, N, mode).cpu().numpy()
+        diffabs_sparse = solver.diffab_coo(ctx, PT, N, mode)
+    ##############################################################################
+    # Save Outputs (reference :76-108)
+    ##############################################################################
+    logging.info(f"Saving results")
+    fid = out_id if out_id else datetime.datetime.now().strftime('%Y%m%d-%H%M%S')
+    out_file = Path(out_dir, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format(fid))
+    out_file.parent.mkdir(parents=True, exist_ok=True)
+
+    np.save(out_file, dists)
+    out_basis_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__MAIN_BASIS__FILE_NAME.format(fid))
+    with open(out_basis_file, 'w') as f:
+        for file in fun_files:
+            f.write(f"{file}\n")
+    logging.info(f"Saved distances to {out_file}")
+    if make_diffab:
+        logging.info("Saving diffabs as a sparse npz file")
+        out_diffab_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__DIFFAB_FILE_NAME.format(fid))
+        sparse_npz.save_npz(out_diffab_file, diffabs_sparse)
+        logging.info(f"Saved difference abundance diffabs to {out_file}")
+        out_diffab_node_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__DIFFAB_NODES_FILE_NAME.format(fid))
+        with open(out_diffab_node_file, 'w') as f:
+            for node in input.basis:
+                f.write(f'{input.idx_to_node[node]}\n')
+
+    if save_Ppushed:
+        logging.info(f"Saving pushed profiles")
+        out_pushed_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__PUSH_FILE_NAME.format(fid))
+        with open(out_pushed_file, 'wb') as f:
+            pickle.dump(Ps_pushed, f)
+        logging.info(f"Saved pushed profiles to {out_pushed_file}")

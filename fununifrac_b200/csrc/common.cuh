@@ -1,0 +1,120 @@
+// common.cuh — shared declarations of libfununifrac.so (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fununifrac.h"
+
+namespace fuf {
+
+void set_error(const char *fmt, ...);
+
+#define FUF_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess) {                                                            \
+            fuf::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,                  \
+                           cudaGetErrorString(err__));                                         \
+            return FUF_ECUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define FUF_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            fuf::set_error(__VA_ARGS__);                                                       \
+            return FUF_EINVAL;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+constexpr int kPushChunk = 32;  // nodes per push-up chunk (KT)
+
+// One spanning node = a node whose postorder range [start, k] crosses a push-up chunk boundary.
+struct SpanNode {
+    int32_t k;           // postorder index
+    int32_t chunk_first; // chunk holding `start`
+    int32_t chunk_last;  // chunk holding `k`
+    int32_t slot_start;  // checkpoint slot with the chunk-local prefix sum up to start-1, -1 if start is a chunk start
+    int32_t slot_k;      // checkpoint slot with the chunk-local prefix sum up to k (inclusive)
+};
+
+// Grow-only device buffer owned by a context.
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want);
+    void release();
+};
+
+// Pinned host staging buffer.
+struct PinnedBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t want);
+    void release();
+};
+
+}  // namespace fuf
+
+struct fuf_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int32_t n = 0;
+    int32_t n_leaves = 0, depth = 0, n_zero_len = 0;
+    bool contiguous = true;  // every subtree is a contiguous postorder range (true DFS postorder)
+
+    // host copies
+    std::vector<int32_t> parent;
+    std::vector<int32_t> start;  // first postorder index of the subtree of k
+    std::vector<double> w[2];    // [mode][k]: L1 -> L (0 -> eps), L2 -> sqrt(L); root -> 1
+
+    // device tree data
+    int32_t *d_parent = nullptr;
+    double *d_w[2] = {nullptr, nullptr};
+    int32_t *d_parent_local = nullptr;  // parent index relative to the node's chunk base, -1 if outside
+    int32_t *d_cp_after = nullptr;      // checkpoint slot to store the chunk prefix after node k, -1 if none
+    uint8_t *d_is_span = nullptr;       // 1 if node k is a spanning node (written by the fix-up kernel)
+    fuf::SpanNode *d_span = nullptr;
+    int32_t n_chunks = 0, n_span = 0, n_cp = 0;
+
+    // scratch
+    fuf::DeviceBuffer ws_push;     // T, CT, CP arrays of the push-up
+    fuf::DeviceBuffer ws_pair;     // tile list + split-K partials of the pairwise kernel
+    fuf::DeviceBuffer ws_x;        // X staging blocks (fuf_all_pairs_host)
+    fuf::DeviceBuffer ws_p;        // PT / P64T (fuf_all_pairs_host)
+    fuf::DeviceBuffer ws_d;        // D on device when the host buffer cannot be written in place
+    fuf::PinnedBuffer pin_x;       // pinned staging when X_h is pageable
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev[8] = {};
+    float t_h2d_push = 0.f, t_pair = 0.f, t_total = 0.f;
+
+    int64_t launches = 0;
+};
+
+namespace fuf {
+
+// pushup.cu
+int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, float *PT, int64_t ldp,
+                int64_t col0, cudaStream_t stream);
+int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int mode, double *P64T, int64_t ldp,
+                      int64_t col0, cudaStream_t stream);
+// pairwise.cu
+int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
+                 const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
+                 cudaStream_t stream);
+int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
+                 cudaStream_t stream);
+int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
+             double *D, int64_t ldd, cudaStream_t stream);
+// diffab.cu
+int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
+                 int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);
+
+}  // namespace fuf

@@ -1,0 +1,122 @@
+// diffab.cu — per-pair differential-abundance rows (--diffab).
+//
+// Replaces get_L1_diffab / get_L2_diffab (src/objects/profile_vector.py:13-15,21-23) evaluated for every
+// pair in itertools.combinations order (src/algorithms/emd_unifrac.py:49,56-67):
+//     out[p][k] = P_i[k] - P_j[k]      (L1, signed, already length-weighted)
+//                 (P_i[k] - P_j[k])^2  (L2)
+// The host turns the dense rows into the reference's COO (and its negated transpose).
+//
+// K4 diffab_kernel (bound by the link to wherever `out` lives: HBM, or PCIe for pinned host memory):
+// pairs of one row i with 32 consecutive j form a block; the node-major profiles are read coalesced
+// along j, transposed through shared memory, and written coalesced along k (128 B per warp store).
+#include "common.cuh"
+
+namespace fuf {
+
+struct DiffabBlock {
+    int32_t i, j0, count;   // pairs (i, j0 .. j0+count-1), count <= 32
+    int32_t pad;
+    int64_t out_pair;       // index of the first pair of the block in the output
+};
+
+template <typename TP, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+diffab_kernel(const DiffabBlock *__restrict__ blocks, const TP *__restrict__ P, int64_t ldp, int32_t n,
+              TO *__restrict__ out)
+{
+    __shared__ TP tile[32][33];
+    const DiffabBlock b = blocks[blockIdx.x];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int32_t k0 = blockIdx.y * 32;
+    for (int kk = ly; kk < 32; kk += 8) {
+        const int32_t k = k0 + kk;
+        TP d = TP(0);
+        if (k < n && lx < b.count) {
+            const TP a = P[(int64_t)k * ldp + b.i];
+            const TP q = P[(int64_t)k * ldp + b.j0 + lx];
+            d = a - q;
+            if (MODE == FUF_MODE_L2) d = d * d;
+        }
+        tile[kk][lx] = d;
+    }
+    __syncthreads();
+    const int32_t k = k0 + lx;
+    if (k < n)
+        for (int q = ly; q < b.count; q += 8) out[(b.out_pair + q) * (int64_t)n + k] = (TO)tile[lx][q];
+}
+
+int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
+                 int64_t pair_end, void *out, int out_dtype, cudaStream_t stream)
+{
+    const int64_t total = N * (N - 1) / 2;
+    FUF_REQUIRE(pair_begin >= 0 && pair_begin <= pair_end && pair_end <= total,
+                "fuf_diffab_block: pair range [%lld,%lld) outside [0,%lld)", (long long)pair_begin,
+                (long long)pair_end, (long long)total);
+    if (pair_begin == pair_end) return FUF_OK;
+    // enumerate blocks: row i owns pairs [off(i), off(i+1)), off(i) = i*N - i*(i+1)/2
+    std::vector<DiffabBlock> blocks;
+    int64_t i = 0;
+    {
+        int64_t lo = 0, hi = N - 1;  // largest i with off(i) <= pair_begin
+        while (lo < hi) {
+            int64_t mid = (lo + hi + 1) / 2;
+            if (mid * N - mid * (mid + 1) / 2 <= pair_begin) lo = mid; else hi = mid - 1;
+        }
+        i = lo;
+    }
+    int64_t p = pair_begin;
+    while (p < pair_end) {
+        const int64_t off = i * N - i * (i + 1) / 2, row_end = off + (N - 1 - i);
+        if (p >= row_end) {
+            i++;
+            continue;
+        }
+        const int64_t stop = std::min(row_end, pair_end);
+        while (p < stop) {
+            const int32_t cnt = (int32_t)std::min<int64_t>(32, stop - p);
+            blocks.push_back(DiffabBlock{(int32_t)i, (int32_t)(i + 1 + (p - off)), cnt, 0, p - pair_begin});
+            p += cnt;
+        }
+        i++;
+    }
+    int rc = ctx->ws_pair.reserve(blocks.size() * sizeof(DiffabBlock));
+    if (rc) return rc;
+    DiffabBlock *d_blocks = (DiffabBlock *)ctx->ws_pair.ptr;
+    FUF_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(DiffabBlock), cudaMemcpyHostToDevice,
+                             stream));
+    FUF_CUDA(cudaStreamSynchronize(stream));
+    dim3 grid((unsigned)blocks.size(), (unsigned)((ctx->n + 31) / 32));
+    FUF_REQUIRE(grid.y <= 65535, "fuf_diffab_block: tree too large");
+    const int32_t n = ctx->n;
+#define LAUNCH(TP, TO)                                                                                       \
+    do {                                                                                                     \
+        if (mode == FUF_MODE_L1)                                                                             \
+            diffab_kernel<TP, TO, FUF_MODE_L1><<<grid, 256, 0, stream>>>(d_blocks, (const TP *)PT, ldp, n, (TO *)out); \
+        else                                                                                                 \
+            diffab_kernel<TP, TO, FUF_MODE_L2><<<grid, 256, 0, stream>>>(d_blocks, (const TP *)PT, ldp, n, (TO *)out); \
+    } while (0)
+    if (p_dtype == FUF_F32 && out_dtype == FUF_F32) LAUNCH(float, float);
+    else if (p_dtype == FUF_F32 && out_dtype == FUF_F64) LAUNCH(float, double);
+    else if (p_dtype == FUF_F64 && out_dtype == FUF_F32) LAUNCH(double, float);
+    else LAUNCH(double, double);
+#undef LAUNCH
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+}  // namespace fuf
+
+using namespace fuf;
+
+extern "C" int fuf_diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode,
+                                int64_t pair_begin, int64_t pair_end, void *out, int out_dtype, void *stream)
+{
+    FUF_REQUIRE(ctx && PT && out, "fuf_diffab_block: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_diffab_block: bad mode %d", mode);
+    FUF_REQUIRE((p_dtype == FUF_F32 || p_dtype == FUF_F64) && (out_dtype == FUF_F32 || out_dtype == FUF_F64),
+                "fuf_diffab_block: bad dtype");
+    FUF_REQUIRE(N >= 0 && ldp >= N, "fuf_diffab_block: bad shape");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return diffab_block(ctx, PT, p_dtype, N, ldp, mode, pair_begin, pair_end, out, out_dtype, (cudaStream_t)stream);
+}

@@ -1,0 +1,639 @@
+// pairwise.cu — all-pairs distance kernels over node-major pushed profiles.
+//
+// Replaces the N(N-1)/2 iteration Python loop of pairwise_computation
+// (src/algorithms/emd_unifrac.py:42-54) and its per-pair numpy arithmetic get_L1 / get_L2
+// (src/objects/profile_vector.py:9-11,17-19):
+//     L1: D[i,j] = D[j,i] = sum_k |P_i[k] - P_j[k]|          L2: sum_k (P_i[k] - P_j[k])^2   (no sqrt)
+// over ALL n basis entries including the unscaled root.
+//
+// K2 pairwise_tile_kernel (production, FP32-pipe bound: 2 FP32 lane-ops per (pair, basis entry)):
+//   * persistent CTAs (one per SM) loop over work items = (128x128 tile of D, k-split);
+//   * warp-specialised: warps 0-7 (256 threads, 2 warpgroups) consume, the third warpgroup donates its
+//     registers (setmaxnreg) and one of its lanes is the TMA producer;
+//   * operand tiles A = PT[k0:k0+16][i0:i0+128], B = PT[k0:k0+16][j0:j0+128] are brought in by TMA
+//     (cp.async.bulk.tensor.3d) into a 4-stage shared-memory ring guarded by full/empty mbarriers;
+//     out-of-range rows/columns are zero-filled by the TMA unit, so no edge cases in the inner loop;
+//   * each consumer thread owns an 8x8 block of the tile: per basis entry 4 LDS.128 feed
+//     32 FADD2 (d = a - b, packed pairs along j) + 32 FADD2 (acc += |d|)  [L2: 32 FFMA2 acc += d*d];
+//   * accuracy: fp32 partial sums are folded into double accumulators (shared memory, one private
+//     column per thread) every 256 basis entries, so each fp32 accumulator sees at most 256 adds;
+//   * epilogue: the double tile is written through shared memory with fully coalesced rows, to
+//     D[i,j] and (mirrored) D[j,i]; with k-splits, to a partial buffer that a second kernel reduces
+//     in fixed order (deterministic, no atomics).
+// K5 pairwise_f64_kernel: validation mode, everything in double, no FMA contraction.
+#include "common.cuh"
+
+namespace fuf {
+
+constexpr int TILE = FUF_TILE;    // 128
+constexpr int KC = 16;            // basis entries per pipeline stage
+constexpr int STAGES = 4;
+constexpr int FLUSH_STAGES = 16;  // fold fp32 partials into double every 16 stages = 256 basis entries
+constexpr int NCONS = 256;        // consumer threads (8 warps, 16x16 grid of 8x8 register blocks)
+constexpr int NTHREADS = NCONS + 128;  // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg works per warpgroup)
+constexpr uint32_t STAGE_BYTES = 2u * KC * TILE * sizeof(float);                      // 16 KB
+constexpr uint32_t ACC64_BYTES = 64u * NCONS * sizeof(double);                        // 128 KB
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC64_BYTES + 2 * STAGES * 8;  // + barriers
+
+struct TileDesc {
+    int32_t ti, tj;     // tile coordinates (tj >= ti)
+    int32_t out_row0;   // first row of this tile row in the output buffer
+    int32_t mirror;     // also write the transposed tile to (tj, ti)
+};
+
+struct PairParams {
+    const TileDesc *tiles;
+    int32_t n_items;           // n_tiles * splits
+    int32_t splits;
+    int32_t stages_total;      // ceil(n / KC)
+    int32_t stages_per_split;
+    int32_t shard;             // columns per shard of PT (>= padded N when there is a single block)
+    int64_t N;
+    double *D;
+    int64_t ldd;
+    double *partial;           // [n_items][TILE*TILE] when splits > 1
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a broken pipeline traps (CUDA error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_bar()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory");
+}
+
+// packed fp32x2 math (FADD2 / FFMA2 on sm_100a)
+__device__ __forceinline__ uint64_t pk_sub_bcast(float a, uint64_t b)
+{
+    uint64_t aa, d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(aa), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t pk_add_abs(uint64_t acc, uint64_t d)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+    lo = fabsf(lo);
+    hi = fabsf(hi);
+    uint64_t ad;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ad) : "f"(lo), "f"(hi));
+    asm("add.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(ad));
+    return acc;
+}
+__device__ __forceinline__ uint64_t pk_fma_sq(uint64_t acc, uint64_t d)
+{
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(d));
+    return acc;
+}
+__device__ __forceinline__ void pk_unpack(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: production tile kernel
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool PACKED>
+__global__ void __launch_bounds__(NTHREADS, 1)
+pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float *stage_base = reinterpret_cast<float *>(smem);
+    double *acc64 = reinterpret_cast<double *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + ACC64_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full0 + 8 * s, 1);           // one arrive.expect_tx by the producer + the TMA bytes
+            mbar_init(empty0 + 8 * s, NCONS / 32);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= NCONS / 32) {
+        // ===================== producer warpgroup: gives its registers to the consumers =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == NCONS / 32 && lane == 0) {  // one elected lane issues all TMA loads
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const TileDesc td = p.tiles[item / p.splits];
+                const int split = item % p.splits;
+                const int s_begin = split * p.stages_per_split;
+                const int s_end = min(p.stages_total, s_begin + p.stages_per_split);
+                const int ia = td.ti * TILE, ib = td.tj * TILE;
+                const int a_col = ia % p.shard, a_sh = ia / p.shard;
+                const int b_col = ib % p.shard, b_sh = ib / p.shard;
+                for (int st = s_begin; st < s_end; ++st, ++it) {
+                    const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * slot, phase ^ 1u);
+                    const uint32_t full = full0 + 8 * slot;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    const uint32_t dst = smem_u32(stage_base) + slot * STAGE_BYTES;
+                    tma_load_3d(dst, &tmap, full, a_col, st * KC, a_sh);
+                    tma_load_3d(dst + STAGE_BYTES / 2, &tmap, full, b_col, st * KC, b_sh);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: 256 threads, 8x8 register block each =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int tx = (warp & 1) * 8 + (lane & 7);   // 0..15 along i (rows of the tile)
+    const int ty = (warp >> 1) * 4 + (lane >> 3); // 0..15 along j (columns of the tile)
+    double *my64 = acc64 + tid;                   // slot (m*8+nn) lives at my64[(m*8+nn)*NCONS]
+
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const TileDesc td = p.tiles[item / p.splits];
+        const int split = item % p.splits;
+        const int s_begin = split * p.stages_per_split;
+        const int s_end = min(p.stages_total, s_begin + p.stages_per_split);
+
+        float acc[8][8];
+        uint64_t acc2[8][4];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc[m][q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc2[m][q] = 0ull;
+        }
+#pragma unroll
+        for (int e = 0; e < 64; e++) my64[e * NCONS] = 0.0;
+
+        auto flush = [&]() {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                if (PACKED) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        float lo, hi;
+                        pk_unpack(acc2[m][q], lo, hi);
+                        my64[(m * 8 + 2 * q) * NCONS] += (double)lo;
+                        my64[(m * 8 + 2 * q + 1) * NCONS] += (double)hi;
+                        acc2[m][q] = 0ull;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        my64[(m * 8 + q) * NCONS] += (double)acc[m][q];
+                        acc[m][q] = 0.f;
+                    }
+                }
+            }
+        };
+
+        for (int st = s_begin; st < s_end; ++st, ++it) {
+            const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
+            mbar_wait(full0 + 8 * slot, phase);
+            const float *As = stage_base + slot * (STAGE_BYTES / 4);
+            const float *Bs = As + KC * TILE;
+#pragma unroll
+            for (int k = 0; k < KC; k++) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(As + k * TILE + tx * 4);
+                const float4 a1 = *reinterpret_cast<const float4 *>(As + k * TILE + 64 + tx * 4);
+                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                if (PACKED) {
+                    const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(Bs + k * TILE + ty * 4);
+                    const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(Bs + k * TILE + 64 + ty * 4);
+                    const uint64_t b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint64_t d = pk_sub_bcast(a[m], b[q]);
+                            acc2[m][q] = (MODE == FUF_MODE_L1) ? pk_add_abs(acc2[m][q], d) : pk_fma_sq(acc2[m][q], d);
+                        }
+                    }
+                } else {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(Bs + k * TILE + ty * 4);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(Bs + k * TILE + 64 + ty * 4);
+                    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float d = a[m] - b[q];
+                            if (MODE == FUF_MODE_L1)
+                                acc[m][q] += fabsf(d);
+                            else
+                                acc[m][q] = fmaf(d, d, acc[m][q]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+            if ((st - s_begin + 1) % FLUSH_STAGES == 0) flush();
+        }
+        flush();
+        consumer_bar();  // all double accumulators of the tile are in shared memory
+
+        // ---- epilogue: coalesced rows through shared memory ---------------------------------
+        // element (r, c) of the tile is owned by thread (tx = (r%64)/4, ty = (c%64)/4), register (m, nn)
+        auto slot_of = [](int r, int c) {
+            const int otx = (r & 63) >> 2, m = ((r >> 6) << 2) | (r & 3);
+            const int oty = (c & 63) >> 2, nn = ((c >> 6) << 2) | (c & 3);
+            const int ow = ((oty >> 2) << 1) | (otx >> 3), ol = ((oty & 3) << 3) | (otx & 7);
+            return (m * 8 + nn) * NCONS + ow * 32 + ol;
+        };
+        const int half = tid >> 7, col = tid & 127;
+        if (p.splits > 1) {
+            double *dst = p.partial + (size_t)item * (TILE * TILE);
+            for (int r = half; r < TILE; r += 2) dst[r * TILE + col] = acc64[slot_of(r, col)];
+        } else {
+            const int64_t gi0 = (int64_t)td.ti * TILE, gj0 = (int64_t)td.tj * TILE;
+            if (gj0 + col < p.N) {
+                for (int r = half; r < TILE; r += 2)
+                    if (gi0 + r < p.N) p.D[((int64_t)td.out_row0 + r) * p.ldd + gj0 + col] = acc64[slot_of(r, col)];
+            }
+            if (td.mirror && gi0 + col < p.N) {
+                for (int c = half; c < TILE; c += 2)
+                    if (gj0 + c < p.N) p.D[(gj0 + c) * p.ldd + gi0 + col] = acc64[slot_of(col, c)];
+            }
+        }
+        consumer_bar();  // the next item re-zeroes the accumulators
+    }
+}
+
+// Sum the k-split partial tiles in fixed order and write D (+ mirror).
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restrict__ partial, int splits, int64_t N,
+                       double *__restrict__ D, int64_t ldd)
+{
+    const TileDesc td = tiles[blockIdx.x];
+    const double *src = partial + (size_t)blockIdx.x * splits * (TILE * TILE);
+    const int64_t gi0 = (int64_t)td.ti * TILE, gj0 = (int64_t)td.tj * TILE;
+    __shared__ double tile[32][33];
+    // 4x4 sub-blocks of 32x32 so that both the direct and the mirrored write are coalesced
+    for (int sb = 0; sb < 16; sb++) {
+        const int r0 = (sb >> 2) * 32, c0 = (sb & 3) * 32;
+        const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+        for (int rr = ly; rr < 32; rr += 8) {
+            double v = 0.0;
+            for (int s = 0; s < splits; s++) v += src[(size_t)s * (TILE * TILE) + (r0 + rr) * TILE + c0 + lx];
+            tile[rr][lx] = v;
+            const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
+            if (gi < N && gj < N) D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
+        }
+        __syncthreads();
+        if (td.mirror) {
+            for (int cc = ly; cc < 32; cc += 8) {
+                const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;
+                if (gi < N && gj < N) D[gj * ldd + gi] = tile[lx][cc];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: validation kernel, all double, 64x64 tiles, 4x4 per thread; separate mul/add (no FMA) so the
+// squares match numpy's (P-Q)**2 followed by a sum.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+pairwise_f64_kernel(const double *__restrict__ P, int64_t ldp, int64_t N, int32_t n, double *__restrict__ D, int64_t ldd)
+{
+    constexpr int T = 64, KB = 16;
+    __shared__ double As[KB][T], Bs[KB][T];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t i0 = (int64_t)ti * T, j0 = (int64_t)tj * T;
+    double acc[4][4] = {};
+    for (int32_t k0 = 0; k0 < n; k0 += KB) {
+        for (int e = tid; e < KB * T; e += 256) {
+            const int kk = e / T, c = e % T;
+            const int32_t k = k0 + kk;
+            As[kk][c] = (k < n && i0 + c < N) ? P[(int64_t)k * ldp + i0 + c] : 0.0;
+            Bs[kk][c] = (k < n && j0 + c < N) ? P[(int64_t)k * ldp + j0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < KB; kk++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) a[m] = As[kk][tx * 4 + m];
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[q] = Bs[kk][ty * 4 + q];
+#pragma unroll
+            for (int m = 0; m < 4; m++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double d = fabs(__dsub_rn(a[m], b[q]));
+                    acc[m][q] = __dadd_rn(acc[m][q], MODE == FUF_MODE_L1 ? d : __dmul_rn(d, d));
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int64_t i = i0 + tx * 4 + m, j = j0 + ty * 4 + q;
+            if (i < N && j < N) {
+                D[i * ldd + j] = acc[m][q];
+                D[j * ldd + i] = acc[m][q];
+            }
+        }
+}
+
+// Compact row blocks (one per tile row, upper part valid) -> full symmetric matrix.
+__global__ void __launch_bounds__(256)
+assemble_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ tile_rows, int64_t N, int64_t ldb,
+                double *__restrict__ D, int64_t ldd)
+{
+    const int c = blockIdx.y;            // compact block
+    const int t = tile_rows[c];          // its tile row
+    const int tj = t + blockIdx.x;       // tile column (only tj >= t carry data)
+    const int64_t gi0 = (int64_t)t * TILE, gj0 = (int64_t)tj * TILE;
+    if (gj0 >= N) return;
+    __shared__ double tile[32][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int sb = 0; sb < 16; sb++) {
+        const int r0 = (sb >> 2) * 32, c0 = (sb & 3) * 32;
+        for (int rr = ly; rr < 32; rr += 8) {
+            const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
+            double v = 0.0;
+            if (gi < N && gj < N) {
+                v = blocks[((int64_t)c * TILE + r0 + rr) * ldb + gj];
+                D[gi * ldd + gj] = v;
+            }
+            tile[rr][lx] = v;
+        }
+        __syncthreads();
+        if (tj != t) {
+            for (int cc = ly; cc < 32; cc += 8) {
+                const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;
+                if (gi < N && gj < N) D[gj * ldd + gi] = tile[lx][cc];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
+                 const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
+                 cudaStream_t stream)
+{
+    if (N == 0) return FUF_OK;
+    const int32_t n = ctx->n;
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise: PT must be 16-byte aligned");
+    FUF_REQUIRE(tiles_per_dim < (1 << 20), "fuf_pairwise: N too large");
+
+    // ---- TMA descriptor over PT: dims (sample-in-shard, node, shard) -------------------------
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) {
+        set_error("fuf_pairwise: cuTensorMapEncodeTiled is not available from this driver");
+        return FUF_ECUDA;
+    }
+    cuuint64_t gdim[3], gstride[2];
+    int32_t shard_cols;
+    if (shard == 0) {
+        FUF_REQUIRE(ldp % 4 == 0 && ldp >= N, "fuf_pairwise: ldp=%lld must be a multiple of 4 and >= N=%lld",
+                    (long long)ldp, (long long)N);
+        gdim[0] = (cuuint64_t)N;  // columns beyond N are zero-filled by the TMA unit
+        gdim[1] = (cuuint64_t)n;
+        gdim[2] = 1;
+        gstride[0] = (cuuint64_t)ldp * sizeof(float);
+        gstride[1] = (cuuint64_t)ldp * sizeof(float) * (cuuint64_t)n;
+        shard_cols = (int32_t)(tiles_per_dim * TILE);
+    } else {
+        FUF_REQUIRE(shard % TILE == 0 && shard > 0, "fuf_pairwise: shard=%lld must be a positive multiple of %d",
+                    (long long)shard, TILE);
+        FUF_REQUIRE(shard_stride % 4 == 0 && shard_stride >= shard * (int64_t)n,
+                    "fuf_pairwise: shard_stride=%lld too small or not a multiple of 4", (long long)shard_stride);
+        const int64_t n_shards = (N + shard - 1) / shard;
+        gdim[0] = (cuuint64_t)shard;
+        gdim[1] = (cuuint64_t)n;
+        gdim[2] = (cuuint64_t)n_shards;
+        gstride[0] = (cuuint64_t)shard * sizeof(float);
+        gstride[1] = (cuuint64_t)shard_stride * sizeof(float);
+        shard_cols = (int32_t)shard;
+    }
+    const cuuint32_t box[3] = {TILE, KC, 1}, estr[3] = {1, 1, 1};
+    CUtensorMap tmap;
+    CUresult cres = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)PT, gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cres != CUDA_SUCCESS) {
+        set_error("fuf_pairwise: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld n=%d ldp=%lld shard=%lld)",
+                  (int)cres, (long long)N, n, (long long)ldp, (long long)shard);
+        return FUF_ECUDA;
+    }
+
+    // ---- tile list ------------------------------------------------------------------------------
+    std::vector<TileDesc> tiles;
+    const bool full = (tile_rows_h == nullptr);
+    const int32_t n_rows = full ? (int32_t)tiles_per_dim : n_tile_rows;
+    for (int32_t c = 0; c < n_rows; c++) {
+        const int32_t t = full ? c : tile_rows_h[c];
+        FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise: tile row %d out of range [0,%lld)", t,
+                    (long long)tiles_per_dim);
+        for (int32_t tj = t; tj < tiles_per_dim; tj++)
+            tiles.push_back(TileDesc{t, tj, full ? t * TILE : c * TILE, (full && tj != t) ? 1 : 0});
+    }
+    const int32_t n_tiles = (int32_t)tiles.size();
+    if (n_tiles == 0) return FUF_OK;
+
+    // ---- k-splits: minimise the makespan over the SMs ------------------------------------------------
+    const int32_t stages_total = (n + KC - 1) / KC;
+    int32_t best_s = 1;
+    {
+        int64_t best_cost = INT64_MAX;
+        const int32_t max_s = std::max(1, std::min(64, stages_total / (2 * FLUSH_STAGES)));
+        for (int32_t s = 1; s <= max_s; s++) {
+            const int64_t per = (stages_total + s - 1) / s;
+            const int64_t waves = ((int64_t)n_tiles * s + ctx->sm_count - 1) / ctx->sm_count;
+            const int64_t cost = waves * (per + 40);  // +40 stages ~ per-item prologue/epilogue
+            if (cost < best_cost) {
+                best_cost = cost;
+                best_s = s;
+            }
+        }
+    }
+    int32_t per_split = (stages_total + best_s - 1) / best_s;
+    const int32_t splits = (stages_total + per_split - 1) / per_split;  // no empty split
+
+    size_t tiles_bytes = ((size_t)n_tiles * sizeof(TileDesc) + 255) & ~(size_t)255;
+    size_t partial_bytes = splits > 1 ? (size_t)n_tiles * splits * TILE * TILE * sizeof(double) : 0;
+    int rc = ctx->ws_pair.reserve(tiles_bytes + partial_bytes);
+    if (rc) return rc;
+    TileDesc *d_tiles = (TileDesc *)ctx->ws_pair.ptr;
+    double *d_partial = splits > 1 ? (double *)((char *)ctx->ws_pair.ptr + tiles_bytes) : nullptr;
+    FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, stream));
+    // the tile list lives in pageable host memory: make sure the copy has read it before `tiles` dies
+    FUF_CUDA(cudaStreamSynchronize(stream));
+
+    PairParams p;
+    p.tiles = d_tiles;
+    p.n_items = n_tiles * splits;
+    p.splits = splits;
+    p.stages_total = stages_total;
+    p.stages_per_split = per_split;
+    p.shard = shard_cols;
+    p.N = N;
+    p.D = D;
+    p.ldd = ldd;
+    p.partial = d_partial;
+
+    const bool packed = !(flags & FUF_PW_SCALAR_MATH);
+    void (*kern)(const CUtensorMap, const PairParams) = nullptr;
+    if (mode == FUF_MODE_L1)
+        kern = packed ? pairwise_tile_kernel<FUF_MODE_L1, true> : pairwise_tile_kernel<FUF_MODE_L1, false>;
+    else
+        kern = packed ? pairwise_tile_kernel<FUF_MODE_L2, true> : pairwise_tile_kernel<FUF_MODE_L2, false>;
+    FUF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int grid = std::min<int64_t>(p.n_items, ctx->sm_count);
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmap, p);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    if (splits > 1) {
+        reduce_partials_kernel<<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd);
+        FUF_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return FUF_OK;
+}
+
+int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
+                 cudaStream_t stream)
+{
+    if (N == 0) return FUF_OK;
+    const unsigned t = (unsigned)((N + 63) / 64);
+    dim3 grid(t, t);
+    if (mode == FUF_MODE_L1)
+        pairwise_f64_kernel<FUF_MODE_L1><<<grid, 256, 0, stream>>>(P64T, ldp, N, ctx->n, D, ldd);
+    else
+        pairwise_f64_kernel<FUF_MODE_L2><<<grid, 256, 0, stream>>>(P64T, ldp, N, ctx->n, D, ldd);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
+             double *D, int64_t ldd, cudaStream_t stream)
+{
+    if (n_blocks == 0 || N == 0) return FUF_OK;
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    for (int32_t c = 0; c < n_blocks; c++)
+        FUF_REQUIRE(tile_rows_h[c] >= 0 && tile_rows_h[c] < tiles_per_dim, "fuf_assemble: tile row %d out of range",
+                    tile_rows_h[c]);
+    int rc = ctx->ws_pair.reserve((size_t)n_blocks * sizeof(int32_t));
+    if (rc) return rc;
+    int32_t *d_rows = (int32_t *)ctx->ws_pair.ptr;
+    FUF_CUDA(cudaMemcpyAsync(d_rows, tile_rows_h, (size_t)n_blocks * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaStreamSynchronize(stream));
+    dim3 grid((unsigned)tiles_per_dim, (unsigned)n_blocks);
+    assemble_kernel<<<grid, 256, 0, stream>>>(blocks, d_rows, N, ldb, D, ldd);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+}  // namespace fuf
+
+using namespace fuf;
+
+extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
+                            int mode, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd,
+                            int flags, void *stream)
+{
+    FUF_REQUIRE(ctx && PT && D, "fuf_pairwise: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_pairwise: bad mode %d", mode);
+    FUF_REQUIRE(N >= 0 && ldd >= N, "fuf_pairwise: bad shape N=%lld ldd=%lld", (long long)N, (long long)ldd);
+    FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise: n_tile_rows without tile_rows_h");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return pairwise_f32(ctx, PT, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd, flags,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D,
+                                int64_t ldd, void *stream)
+{
+    FUF_REQUIRE(ctx && P64T && D, "fuf_pairwise_f64: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_pairwise_f64: bad mode %d", mode);
+    FUF_REQUIRE(N >= 0 && ldd >= N && ldp >= N, "fuf_pairwise_f64: bad shape N=%lld ldp=%lld ldd=%lld", (long long)N,
+                (long long)ldp, (long long)ldd);
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return pairwise_f64(ctx, P64T, N, ldp, mode, D, ldd, (cudaStream_t)stream);
+}
+
+extern "C" int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
+                            int64_t ldb, double *D, int64_t ldd, void *stream)
+{
+    FUF_REQUIRE(ctx && blocks && tile_rows_h && D, "fuf_assemble: null argument");
+    FUF_REQUIRE(N >= 0 && ldd >= N && ldb >= N, "fuf_assemble: bad shape");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return assemble(ctx, blocks, tile_rows_h, n_blocks, N, ldb, D, ldd, (cudaStream_t)stream);
+}

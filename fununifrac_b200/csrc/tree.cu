@@ -1,0 +1,338 @@
+// tree.cu — context lifetime and tree preprocessing (host side) for libfununifrac.so.
+//
+// Replaces the dict-based tree view of the reference (Tint / lint of tree_to_EMDU_input,
+// src/factory/make_emd_input.py:10-54) with dense postorder arrays on the device, plus the
+// metadata the chunked push-up kernel needs (see pushup.cu).
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "common.cuh"
+
+namespace fuf {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int DeviceBuffer::reserve(size_t want)
+{
+    if (want <= bytes) return FUF_OK;
+    if (ptr) {
+        cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    size_t rounded = (want + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    cudaError_t err = cudaMalloc(&ptr, rounded);
+    if (err != cudaSuccess) {
+        ptr = nullptr;
+        set_error("cudaMalloc(%zu bytes) failed: %s", rounded, cudaGetErrorString(err));
+        cudaGetLastError();
+        return FUF_ENOMEM;
+    }
+    bytes = rounded;
+    return FUF_OK;
+}
+
+void DeviceBuffer::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+}
+
+int PinnedBuffer::reserve(size_t want)
+{
+    if (want <= bytes) return FUF_OK;
+    if (ptr) {
+        cudaFreeHost(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    cudaError_t err = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+    if (err != cudaSuccess) {
+        ptr = nullptr;
+        set_error("cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(err));
+        cudaGetLastError();
+        return FUF_ENOMEM;
+    }
+    bytes = want;
+    return FUF_OK;
+}
+
+void PinnedBuffer::release()
+{
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+}
+
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src)
+{
+    size_t bytes = src.size() * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    FUF_CUDA(cudaMalloc((void **)dst, bytes));
+    if (!src.empty()) FUF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return FUF_OK;
+}
+
+// Host-only planning of the chunked push-up (no device work): subtree ranges, which nodes span a chunk
+// boundary, and where chunk-local prefix sums must be checkpointed.  Shared by fuf_tree_create and the
+// test hook fuf_debug_tree_plan.
+struct TreePlan {
+    std::vector<int32_t> start, parent_local, cp_after;
+    std::vector<uint8_t> is_span;
+    std::vector<SpanNode> span;
+    int32_t n_leaves = 0, depth = 0, n_cp = 0;
+    bool contiguous = true;
+};
+
+static void build_tree_plan(const int32_t *parent_h, int32_t n, TreePlan &plan)
+{
+    const int32_t KT = kPushChunk;
+    std::vector<int32_t> size(n, 1), depth(n, 0);
+    std::vector<uint8_t> has_child(n, 0);
+    for (int32_t i = 0; i < n - 1; i++) {
+        size[parent_h[i]] += size[i];
+        has_child[parent_h[i]] = 1;
+    }
+    for (int32_t i = n - 2; i >= 0; i--) depth[i] = depth[parent_h[i]] + 1;
+    plan.start.resize(n);
+    for (int32_t i = 0; i < n; i++) {
+        plan.start[i] = i - size[i] + 1;
+        if (!has_child[i]) plan.n_leaves++;
+        if (depth[i] > plan.depth) plan.depth = depth[i];
+    }
+    // every subtree is the contiguous range [start, k] iff each child's range nests in its parent's
+    plan.contiguous = true;
+    for (int32_t i = 0; i < n - 1; i++)
+        if (plan.start[parent_h[i]] > plan.start[i] || plan.start[i] < 0) {
+            plan.contiguous = false;
+            break;
+        }
+    plan.parent_local.assign(n, -1);
+    plan.cp_after.assign(n, -1);
+    plan.is_span.assign(n, 0);
+    plan.span.clear();
+    plan.n_cp = 0;
+    if (!plan.contiguous) return;
+    std::map<int32_t, int32_t> slot_of_pos;  // node position -> checkpoint slot
+    auto slot_for = [&](int32_t pos) {
+        auto it = slot_of_pos.find(pos);
+        if (it != slot_of_pos.end()) return it->second;
+        int32_t s = (int32_t)slot_of_pos.size();
+        slot_of_pos[pos] = s;
+        plan.cp_after[pos] = s;
+        return s;
+    };
+    for (int32_t k = 0; k < n; k++) {
+        if (k < n - 1 && parent_h[k] / KT == k / KT) plan.parent_local[k] = parent_h[k] % KT;
+        const int32_t st = plan.start[k];
+        if (st / KT != k / KT) {
+            SpanNode s;
+            s.k = k;
+            s.chunk_first = st / KT;
+            s.chunk_last = k / KT;
+            s.slot_start = (st % KT == 0) ? -1 : slot_for(st - 1);
+            s.slot_k = slot_for(k);
+            plan.span.push_back(s);
+            plan.is_span[k] = 1;
+        }
+    }
+    plan.n_cp = (int32_t)slot_of_pos.size();
+}
+
+}  // namespace fuf
+
+using namespace fuf;
+
+// Test hook (host only, no device needed): the push-up plan for a postorder parent array.
+// span_out receives 5 ints per spanning node (k, chunk_first, chunk_last, slot_start, slot_k); capacity n nodes.
+extern "C" int fuf_debug_tree_plan(const int32_t *parent_h, int32_t n, int32_t *parent_local, int32_t *cp_after,
+                                   uint8_t *is_span, int32_t *span_out, int32_t *n_span, int32_t *n_cp,
+                                   int32_t *contiguous, int32_t *chunk)
+{
+    FUF_REQUIRE(parent_h && parent_local && cp_after && is_span && span_out && n_span && n_cp && contiguous && chunk,
+                "fuf_debug_tree_plan: null argument");
+    FUF_REQUIRE(n >= 1 && parent_h[n - 1] == -1, "fuf_debug_tree_plan: root must be last");
+    for (int32_t i = 0; i < n - 1; i++)
+        FUF_REQUIRE(parent_h[i] > i && parent_h[i] < n, "fuf_debug_tree_plan: parent[%d] = %d is not a postorder", i,
+                    parent_h[i]);
+    TreePlan plan;
+    build_tree_plan(parent_h, n, plan);
+    for (int32_t i = 0; i < n; i++) {
+        parent_local[i] = plan.parent_local[i];
+        cp_after[i] = plan.cp_after[i];
+        is_span[i] = plan.is_span[i];
+    }
+    for (size_t q = 0; q < plan.span.size(); q++) {
+        span_out[5 * q + 0] = plan.span[q].k;
+        span_out[5 * q + 1] = plan.span[q].chunk_first;
+        span_out[5 * q + 2] = plan.span[q].chunk_last;
+        span_out[5 * q + 3] = plan.span[q].slot_start;
+        span_out[5 * q + 4] = plan.span[q].slot_k;
+    }
+    *n_span = (int32_t)plan.span.size();
+    *n_cp = plan.n_cp;
+    *contiguous = plan.contiguous ? 1 : 0;
+    *chunk = kPushChunk;
+    return FUF_OK;
+}
+
+extern "C" int fuf_version(void) { return FUF_ABI_VERSION; }
+
+extern "C" const char *fuf_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int64_t fuf_padded_samples(int64_t N)
+{
+    if (N <= 0) return FUF_TILE;
+    return (N + FUF_TILE - 1) / FUF_TILE * FUF_TILE;
+}
+
+extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_h, const double *length_h, int32_t n)
+{
+    FUF_REQUIRE(out != nullptr && parent_h != nullptr && length_h != nullptr, "fuf_tree_create: null argument");
+    FUF_REQUIRE(n >= 1, "fuf_tree_create: n must be >= 1 (got %d)", n);
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("fuf_tree_create: no CUDA device available (this library has no CPU fallback)");
+        return FUF_ENODEV;
+    }
+    if (device < 0) FUF_CUDA(cudaGetDevice(&device));
+    FUF_REQUIRE(device < ndev, "fuf_tree_create: device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    FUF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("fuf_tree_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return FUF_ENODEV;
+    }
+    // ---- validate the postorder contract --------------------------------------------------
+    FUF_REQUIRE(parent_h[n - 1] == -1, "fuf_tree_create: parent[n-1] must be -1 (root last), got %d", parent_h[n - 1]);
+    for (int32_t i = 0; i < n - 1; i++) {
+        FUF_REQUIRE(parent_h[i] > i && parent_h[i] < n,
+                    "fuf_tree_create: parent[%d] = %d violates child < parent < n (postorder)", i, parent_h[i]);
+        FUF_REQUIRE(std::isfinite(length_h[i]), "fuf_tree_create: edge length of node %d is not finite", i);
+    }
+    fuf_ctx *ctx = new (std::nothrow) fuf_ctx();
+    if (!ctx) {
+        set_error("fuf_tree_create: out of host memory");
+        return FUF_ENOMEM;
+    }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->n = n;
+    ctx->parent.assign(parent_h, parent_h + n);
+
+    // weights: zero -> DBL_EPSILON (emd_unifrac.py:24-25,35-36), L2 takes the square root (:28); the root is unscaled
+    ctx->w[0].resize(n);
+    ctx->w[1].resize(n);
+    for (int32_t i = 0; i < n - 1; i++) {
+        double l = length_h[i];
+        if (l == 0.0) {
+            l = DBL_EPSILON;
+            ctx->n_zero_len++;
+        }
+        ctx->w[0][i] = l;
+        ctx->w[1][i] = std::sqrt(l);
+    }
+    ctx->w[0][n - 1] = 1.0;
+    ctx->w[1][n - 1] = 1.0;
+
+    TreePlan plan;
+    build_tree_plan(parent_h, n, plan);
+    ctx->start = plan.start;
+    ctx->n_leaves = plan.n_leaves;
+    ctx->depth = plan.depth;
+    ctx->contiguous = plan.contiguous;
+    ctx->n_chunks = (n + kPushChunk - 1) / kPushChunk;
+    ctx->n_cp = plan.n_cp;
+    ctx->n_span = (int32_t)plan.span.size();
+    std::vector<int32_t> &parent_local = plan.parent_local, &cp_after = plan.cp_after;
+    std::vector<uint8_t> &is_span = plan.is_span;
+    std::vector<SpanNode> &span = plan.span;
+
+    int rc = FUF_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+        delete ctx;
+        return FUF_ECUDA;
+    }
+    if ((rc = upload(&ctx->d_parent, ctx->parent)) || (rc = upload(&ctx->d_w[0], ctx->w[0])) ||
+        (rc = upload(&ctx->d_w[1], ctx->w[1])) || (rc = upload(&ctx->d_parent_local, parent_local)) ||
+        (rc = upload(&ctx->d_cp_after, cp_after)) || (rc = upload(&ctx->d_is_span, is_span)) ||
+        (rc = upload(&ctx->d_span, span))) {
+        fuf_tree_destroy(ctx);
+        return rc;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("fuf_tree_create: cudaStreamCreate failed");
+        fuf_tree_destroy(ctx);
+        return FUF_ECUDA;
+    }
+    for (auto &ev : ctx->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) {
+            set_error("fuf_tree_create: cudaEventCreate failed");
+            fuf_tree_destroy(ctx);
+            return FUF_ECUDA;
+        }
+    *out = ctx;
+    return FUF_OK;
+}
+
+extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
+{
+    if (!ctx) return FUF_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_parent);
+    cudaFree(ctx->d_w[0]);
+    cudaFree(ctx->d_w[1]);
+    cudaFree(ctx->d_parent_local);
+    cudaFree(ctx->d_cp_after);
+    cudaFree(ctx->d_is_span);
+    cudaFree(ctx->d_span);
+    ctx->ws_push.release();
+    ctx->ws_pair.release();
+    ctx->ws_x.release();
+    ctx->ws_p.release();
+    ctx->ws_d.release();
+    ctx->pin_x.release();
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaGetLastError();
+    delete ctx;
+    return FUF_OK;
+}
+
+extern "C" int fuf_tree_get_info(const fuf_ctx *ctx, fuf_tree_info *info)
+{
+    FUF_REQUIRE(ctx != nullptr && info != nullptr, "fuf_tree_get_info: null argument");
+    info->n = ctx->n;
+    info->n_leaves = ctx->n_leaves;
+    info->depth = ctx->depth;
+    info->chunk = kPushChunk;
+    info->n_chunks = ctx->n_chunks;
+    info->n_spanning = ctx->contiguous ? ctx->n_span : -1;
+    info->n_zero_len = ctx->n_zero_len;
+    info->device = ctx->device;
+    return FUF_OK;
+}
+
+extern "C" int64_t fuf_launch_count(const fuf_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,365 @@
+"""Thin Python host over the C ABI (``include/fununifrac.h`` → ``csrc/libfununifrac.so``).
+
+PyTorch is used only for device buffers and streams: every tensor crosses the boundary as a raw
+``data_ptr()``.  There is no CPU fallback — if the shared library is missing or there is no sm_100
+device, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Iterator, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfununifrac.so")
+
+MODE_L1, MODE_L2 = 0, 1
+F32, F64 = 0, 1
+TILE = 128
+PW_SCALAR_MATH = 1
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class FunUniFracError(RuntimeError):
+    """A C-ABI call failed; the message is ``fuf_last_error()``."""
+
+
+class TreeInfo(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("n_leaves", ctypes.c_int32), ("depth", ctypes.c_int32),
+                ("chunk", ctypes.c_int32), ("n_chunks", ctypes.c_int32), ("n_spanning", ctypes.c_int32),
+                ("n_zero_len", ctypes.c_int32), ("device", ctypes.c_int32)]
+
+
+def load_library() -> ctypes.CDLL:
+    """Load ``libfununifrac.so`` (built in-tree by ``__graft_entry__.build()`` / ``make -C fununifrac_b200/csrc``)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise FunUniFracError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                f"g.build()' or make -C fununifrac_b200/csrc). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, ci = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int
+        L.fuf_version.restype = ci
+        L.fuf_last_error.restype = ctypes.c_char_p
+        L.fuf_padded_samples.restype = i64
+        L.fuf_padded_samples.argtypes = [i64]
+        L.fuf_tree_create.argtypes = [ctypes.POINTER(vp), ci, vp, vp, i32]
+        L.fuf_tree_destroy.argtypes = [vp]
+        L.fuf_tree_get_info.argtypes = [vp, ctypes.POINTER(TreeInfo)]
+        L.fuf_push_up.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, i64, vp]
+        L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
+        L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
+        L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
+        L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, vp]
+        L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
+        L.fuf_diffab_block.argtypes = [vp, vp, ci, i64, i64, ci, i64, i64, vp, ci, vp]
+        L.fuf_all_pairs_host.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, ci]
+        L.fuf_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                      ctypes.POINTER(ctypes.c_float)]
+        L.fuf_launch_count.argtypes = [vp]
+        L.fuf_launch_count.restype = i64
+        for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
+                     "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
+                     "fuf_all_pairs_host", "fuf_last_timing"):
+            getattr(L, name).restype = ci
+        _lib = L
+        return L
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().fuf_last_error().decode("utf-8", "replace")
+        raise FunUniFracError(f"{what} failed (code {rc}): {msg}")
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise FunUniFracError("no CUDA device: the FunUniFrac engine runs on sm_100a GPUs only (no CPU fallback)")
+    return torch
+
+
+def _stream_ptr(torch) -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def padded_samples(N: int) -> int:
+    return max(TILE, (N + TILE - 1) // TILE * TILE)
+
+
+def _dtype_code(t) -> int:
+    torch = _torch()
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f"expected a float32 or float64 tensor, got {t.dtype}")
+
+
+class TreeContext:
+    """Device-resident tree (``fuf_tree_create``): parent / weights in postorder, root last."""
+
+    def __init__(self, parent: np.ndarray, edge_length: np.ndarray, device: Optional[int] = None):
+        torch = _torch()
+        L = load_library()
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        edge_length = np.ascontiguousarray(edge_length, dtype=np.float64)
+        if parent.ndim != 1 or parent.shape != edge_length.shape:
+            raise ValueError("parent and edge_length must be 1-D arrays of the same length")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.n = int(parent.shape[0])
+        self._h = ctypes.c_void_p()
+        self._lib = L
+        _check(L.fuf_tree_create(ctypes.byref(self._h), self.device, parent.ctypes.data, edge_length.ctypes.data,
+                                 self.n), "fuf_tree_create")
+        self.parent = parent
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.fuf_tree_destroy(h)
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise FunUniFracError("tree context is closed")
+        return self._h
+
+    def info(self) -> TreeInfo:
+        ti = TreeInfo()
+        _check(self._lib.fuf_tree_get_info(self.handle, ctypes.byref(ti)), "fuf_tree_get_info")
+        return ti
+
+    def launch_count(self) -> int:
+        return int(self._lib.fuf_launch_count(self.handle))
+
+    # -- device-buffer entry points -------------------------------------------------------------
+    def new_profile_buffer(self, N: int, dtype=None, ldp: Optional[int] = None):
+        """Zeroed node-major buffer PT[n, ldp] (float32 by default)."""
+        torch = _torch()
+        ldp = padded_samples(N) if ldp is None else ldp
+        return torch.zeros((self.n, ldp), dtype=dtype or torch.float32, device=f"cuda:{self.device}")
+
+    def push_up(self, X, mode: int, PT=None, col0: int = 0):
+        """X: device tensor [N, ldx>=n] float32/float64, sample-major → PT float32 [n, ldp] (columns col0..col0+N)."""
+        torch = _torch()
+        N = int(X.shape[0])
+        assert X.dim() == 2 and X.stride(1) == 1 and X.shape[1] >= self.n
+        if PT is None:
+            PT = self.new_profile_buffer(N + col0)
+        assert PT.dtype == torch.float32 and PT.stride(1) == 1
+        _check(self._lib.fuf_push_up(self.handle, X.data_ptr(), _dtype_code(X), N, X.stride(0), mode, PT.data_ptr(),
+                                     PT.stride(0), col0, _stream_ptr(torch)), "fuf_push_up")
+        return PT
+
+    def push_up_f64(self, X, mode: int, P64T=None, col0: int = 0):
+        """Validation path: X float64 [N, ldx] → P64T float64 [n, ldp], reference operation order."""
+        torch = _torch()
+        N = int(X.shape[0])
+        assert X.dtype == torch.float64 and X.dim() == 2 and X.stride(1) == 1 and X.shape[1] >= self.n
+        if P64T is None:
+            P64T = self.new_profile_buffer(N + col0, dtype=torch.float64)
+        assert P64T.dtype == torch.float64 and P64T.stride(1) == 1
+        _check(self._lib.fuf_push_up_f64(self.handle, X.data_ptr(), N, X.stride(0), mode, P64T.data_ptr(),
+                                         P64T.stride(0), col0, _stream_ptr(torch)), "fuf_push_up_f64")
+        return P64T
+
+    def load_pushed(self, P_rows, PT=None, col0: int = 0, out_dtype=None):
+        """Already pushed sample-major rows [N, n] → node-major PT (float32 unless out_dtype says float64)."""
+        torch = _torch()
+        N = int(P_rows.shape[0])
+        assert P_rows.dim() == 2 and P_rows.stride(1) == 1 and P_rows.shape[1] >= self.n
+        if PT is None:
+            PT = self.new_profile_buffer(N + col0, dtype=out_dtype or torch.float32)
+        _check(self._lib.fuf_load_pushed(self.handle, P_rows.data_ptr(), _dtype_code(P_rows), N, P_rows.stride(0),
+                                         PT.data_ptr(), _dtype_code(PT), PT.stride(0), col0, _stream_ptr(torch)),
+               "fuf_load_pushed")
+        return PT
+
+    def pairwise(self, PT, N: int, mode: int, D=None, tile_rows: Optional[Sequence[int]] = None, flags: int = 0,
+                 shard: int = 0, shard_stride: int = 0):
+        """All-pairs distances from node-major float32 PT.
+
+        ``tile_rows is None`` → full symmetric D[N, N]; otherwise compact row blocks [len(tile_rows)*128, N]
+        (upper part only, see ``fuf_pairwise``).  ``PT`` may be [n, ldp] or, with ``shard``, [G, n, shard].
+        """
+        torch = _torch()
+        assert PT.dtype == torch.float32 and PT.is_contiguous() or PT.stride(-1) == 1
+        rows_arr = None
+        if tile_rows is not None:
+            rows_arr = np.ascontiguousarray(tile_rows, dtype=np.int32)
+        if D is None:
+            nrows = N if rows_arr is None else len(rows_arr) * TILE
+            D = torch.zeros((nrows, N), dtype=torch.float64, device=PT.device)
+        assert D.dtype == torch.float64 and D.stride(1) == 1
+        ldp = PT.stride(0) if shard == 0 else 0
+        _check(self._lib.fuf_pairwise(self.handle, PT.data_ptr(), N, ldp, shard, shard_stride, mode,
+                                      rows_arr.ctypes.data if rows_arr is not None else None,
+                                      0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0), flags,
+                                      _stream_ptr(torch)), "fuf_pairwise")
+        return D
+
+    def pairwise_f64(self, P64T, N: int, mode: int, D=None):
+        torch = _torch()
+        assert P64T.dtype == torch.float64 and P64T.stride(1) == 1
+        if D is None:
+            D = torch.zeros((N, N), dtype=torch.float64, device=P64T.device)
+        _check(self._lib.fuf_pairwise_f64(self.handle, P64T.data_ptr(), N, P64T.stride(0), mode, D.data_ptr(),
+                                          D.stride(0), _stream_ptr(torch)), "fuf_pairwise_f64")
+        return D
+
+    def assemble(self, blocks, tile_rows: Sequence[int], N: int, D=None):
+        """Compact row blocks (possibly gathered from several ranks) → full symmetric D."""
+        torch = _torch()
+        rows_arr = np.ascontiguousarray(tile_rows, dtype=np.int32)
+        assert blocks.dtype == torch.float64 and blocks.stride(-1) == 1
+        blocks2 = blocks.reshape(-1, blocks.shape[-1])
+        assert blocks2.shape[0] >= len(rows_arr) * TILE
+        if D is None:
+            D = torch.zeros((N, N), dtype=torch.float64, device=blocks.device)
+        _check(self._lib.fuf_assemble(self.handle, blocks2.data_ptr(), rows_arr.ctypes.data, len(rows_arr), N,
+                                      blocks2.stride(0), D.data_ptr(), D.stride(0), _stream_ptr(torch)),
+               "fuf_assemble")
+        return D
+
+    def diffab_block(self, PT, N: int, mode: int, pair_begin: int, pair_end: int, out):
+        """Dense diffab rows of pairs [pair_begin, pair_end) (combinations order) into ``out`` [pairs, n]
+        (a device tensor or a pinned host tensor)."""
+        torch = _torch()
+        assert out.stride(-1) == 1 and out.shape[-1] == self.n and out.is_contiguous()
+        assert out.shape[0] >= pair_end - pair_begin
+        _check(self._lib.fuf_diffab_block(self.handle, PT.data_ptr(), _dtype_code(PT), N, PT.stride(0), mode,
+                                          pair_begin, pair_end, out.data_ptr(), _dtype_code(out),
+                                          _stream_ptr(torch)), "fuf_diffab_block")
+        return out
+
+    # -- host-buffer entry point ------------------------------------------------------------------
+    def all_pairs_host(self, X: np.ndarray, mode: int, D: Optional[np.ndarray] = None, validate: bool = False
+                       ) -> np.ndarray:
+        """``fuf_all_pairs_host``: host profiles X[N, n] (float32/float64, C-order) → host D[N, N] float64."""
+        _torch()
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        if X.ndim != 2 or X.shape[1] < self.n or X.strides[1] != X.itemsize:
+            raise ValueError(f"X must be a C-ordered [N, >={self.n}] array")
+        N = X.shape[0]
+        if D is None:
+            D = np.zeros((N, N), dtype=np.float64)
+        if D.dtype != np.float64 or D.shape != (N, N) or D.strides[1] != 8:
+            raise ValueError("D must be a C-ordered float64 [N, N] array")
+        _check(self._lib.fuf_all_pairs_host(self.handle, X.ctypes.data, F32 if X.dtype == np.float32 else F64, N,
+                                            X.strides[0] // X.itemsize, mode, D.ctypes.data, D.strides[0] // 8,
+                                            int(validate)), "fuf_all_pairs_host")
+        return D
+
+    def last_timing(self) -> Tuple[float, float, float]:
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        _check(self._lib.fuf_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+               "fuf_last_timing")
+        return a.value, b.value, c.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers on top of the ABI
+# ---------------------------------------------------------------------------------------------------
+
+def context_for(input, device: Optional[int] = None) -> TreeContext:
+    """Tree context cached on a ``FuncTreeEmduInput`` (rebuilt if its dicts were changed in size)."""
+    key = (len(input.basis), len(input.lint), device)
+    cached = input.__dict__.get("_fuf_ctx")
+    if cached is not None and cached[0] == key and cached[1]._h:
+        return cached[1]
+    parent, length = input.dense_arrays()
+    ctx = TreeContext(parent, length, device)
+    input.__dict__["_fuf_ctx"] = (key, ctx)
+    return ctx
+
+
+def pinned_empty(shape, dtype):
+    """Pinned host tensor (+ its numpy view) for zero-copy / async transfers."""
+    torch = _torch()
+    t = torch.empty(shape, dtype=dtype, pin_memory=True)
+    return t, t.numpy()
+
+
+def pair_primitive(P: np.ndarray, Q: np.ndarray, is_l2: bool, diffab: bool):
+    """``get_L1`` / ``get_L2`` / ``get_L*_diffab`` for one pair on the device (float64 kernels).
+
+    The vectors are already pushed, so only their length matters: a star tree of the right size
+    provides the context.
+    """
+    torch = _torch()
+    n = int(P.shape[0])
+    if Q.shape != P.shape:
+        raise ValueError("P and Q must have the same shape")
+    ctx = _star_context(n)
+    rows = torch.from_numpy(np.stack([P, Q])).cuda()
+    P64T = ctx.load_pushed(rows, out_dtype=torch.float64)
+    mode = MODE_L2 if is_l2 else MODE_L1
+    if diffab:
+        out = torch.empty((1, n), dtype=torch.float64, device=rows.device)
+        ctx.diffab_block(P64T, 2, mode, 0, 1, out)
+        return out[0].cpu().numpy()
+    D = ctx.pairwise_f64(P64T, 2, mode)
+    return float(D[0, 1].item())
+
+
+_STAR = {}
+
+
+def _star_context(n: int) -> TreeContext:
+    ctx = _STAR.get(n)
+    if ctx is None or not ctx._h:
+        parent = np.full(n, n - 1, dtype=np.int32)
+        parent[-1] = -1
+        ctx = TreeContext(parent, np.ones(n))
+        _STAR[n] = ctx
+    return ctx
+
+
+def combinations_offset(i: int, N: int) -> int:
+    """Index of pair (i, i+1) in ``itertools.combinations(range(N), 2)`` order."""
+    return i * N - i * (i + 1) // 2
+
+
+def iter_diffab_blocks(ctx: TreeContext, PT, N: int, mode: int, pairs_per_block: int = 1024, out_dtype=None
+                       ) -> Iterator[Tuple[int, int, np.ndarray]]:
+    """Stream dense diffab rows to pinned host memory, double-buffered.
+
+    Yields ``(pair_begin, pair_end, rows)`` with ``rows`` a numpy view [pairs, n] that is valid until the
+    next iteration.  The kernel writes straight into pinned host memory (PCIe-bound, K4).
+    """
+    torch = _torch()
+    total = N * (N - 1) // 2
+    if total == 0:
+        return
+    dt = out_dtype or PT.dtype
+    bufs = [torch.empty((pairs_per_block, ctx.n), dtype=dt, pin_memory=True) for _ in range(2)]
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+    starts = list(range(0, total, pairs_per_block))
+
+    def launch(bi):
+        b, e = starts[bi], min(total, starts[bi] + pairs_per_block)
+        ctx.diffab_block(PT, N, mode, b, e, bufs[bi & 1])
+        events[bi & 1].record()
+        return b, e
+
+    pending = launch(0)
+    for bi in range(len(starts)):
+        nxt = launch(bi + 1) if bi + 1 < len(starts) else None
+        events[bi & 1].synchronize()
+        b, e = pending
+        yield b, e, bufs[bi & 1].numpy()[: e - b]
+        pending = nxt

@@ -1,0 +1,168 @@
+/*
+ * fununifrac.h — C ABI of the B200-native all-pairs FunUniFrac engine (libfununifrac.so).
+ *
+ * The reference (KoslickiLab/FunUniFrac) is pure Python and has no FFI of its own; these entry
+ * points are what a binding for its hot path would call, one per reference function they replace
+ * (paths relative to the reference repository):
+ *
+ *   fuf_tree_create      <- the arrays tree_to_EMDU_input builds        src/factory/make_emd_input.py:10-54
+ *                           (Tint -> parent[], lint -> edge_length[], postorder, root last)
+ *   fuf_push_up          <- push_up_L1 / push_up_L2 over all samples    src/algorithms/emd_unifrac.py:20-39
+ *   fuf_push_up_f64      <- same, float64, reference operation order    src/algorithms/emd_unifrac.py:20-39
+ *   fuf_load_pushed      <- the dict of pushed vectors handed to        src/algorithms/emd_unifrac.py:42
+ *                           pairwise_computation (layout change only)
+ *   fuf_pairwise         <- pairwise_computation (no diffab) =          src/algorithms/emd_unifrac.py:42-54
+ *                           get_L1 / get_L2 over all i<j                src/objects/profile_vector.py:9-19
+ *   fuf_pairwise_f64     <- same, float64 validation mode
+ *   fuf_assemble         <- dists[i,j] = dists[j,i] = Z                 src/algorithms/emd_unifrac.py:51-54
+ *                           (joins row-block shards computed on several GPUs)
+ *   fuf_diffab_block     <- get_L1_diffab / get_L2_diffab per pair in   src/objects/profile_vector.py:13-23
+ *                           itertools.combinations order                src/algorithms/emd_unifrac.py:49,56-67
+ *   fuf_all_pairs_host   <- the compute section of the driver           src/compute_all_pairwise_fununifrac.py:64-73
+ *                           (host float64 profiles in, host float64 distance matrix out)
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every function returns 0 on success or a negative FUF_E* code
+ *     and never throws; fuf_last_error() returns a thread-local message for the last failure.
+ *   - "device" pointers are CUDA device pointers on the context's device (any allocator; the Python
+ *     host uses torch tensors purely as buffers).  "host" pointers are ordinary process memory.
+ *   - stream is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - one context per device and tree; contexts are independent; a context is not thread-safe.
+ *
+ * Layouts
+ *   X   : un-pushed profiles, sample-major  X[s * ldx + k],  s in [0,N), k in [0,n)  (float or double)
+ *   PT  : pushed profiles, NODE-major (transposed)  PT[k * ldp + s], float; ldp % 4 == 0 and ldp >= N.
+ *         Padding columns (s >= N) are never read into a result.
+ *   P64T: same layout in double (validation mode).
+ *   D   : distance matrix, row-major D[i * ldd + j], double.
+ */
+#ifndef FUNUNIFRAC_H
+#define FUNUNIFRAC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUF_ABI_VERSION 1
+
+/* error codes */
+#define FUF_OK 0
+#define FUF_EINVAL (-1)  /* bad argument (shape, alignment, mode, tree not in postorder ...) */
+#define FUF_ECUDA (-2)   /* a CUDA runtime / driver call failed */
+#define FUF_ENOMEM (-3)  /* device or host allocation failed */
+#define FUF_ENODEV (-4)  /* no usable sm_100 device */
+
+/* modes */
+#define FUF_MODE_L1 0 /* weights L_e   ; distance sum |a-b|   */
+#define FUF_MODE_L2 1 /* weights sqrt L; distance sum (a-b)^2 (squared, no root: reference quirk) */
+
+/* dtypes for void* operands */
+#define FUF_F32 0
+#define FUF_F64 1
+
+/* fuf_pairwise flags */
+#define FUF_PW_SCALAR_MATH 1 /* use scalar FADD instead of packed FADD2/FFMA2 (A/B switch for profiling) */
+
+#define FUF_TILE 128 /* edge of a distance-matrix tile; shard boundaries must be multiples of it */
+
+typedef struct fuf_ctx fuf_ctx;
+
+typedef struct fuf_tree_info {
+    int32_t n;           /* nodes incl. root */
+    int32_t n_leaves;    /* nodes without children */
+    int32_t depth;       /* edges on the longest root-to-leaf path */
+    int32_t chunk;       /* push-up chunk length (nodes) */
+    int32_t n_chunks;    /* ceil(n / chunk) */
+    int32_t n_spanning;  /* nodes whose subtree crosses a chunk boundary */
+    int32_t n_zero_len;  /* edges of length exactly 0 (replaced by DBL_EPSILON, emd_unifrac.py:24-25) */
+    int32_t device;
+} fuf_tree_info;
+
+int fuf_version(void);
+const char *fuf_last_error(void);
+
+/* Tree context.  parent_h[i] > i for i < n-1, parent_h[n-1] == -1 (postorder, root last);
+ * length_h[i] = length of edge (i, parent[i]) (length_h[n-1] ignored).  Zero lengths are replaced by
+ * DBL_EPSILON exactly as push_up_L1/L2 do.  device < 0 = current device. */
+int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_h, const double *length_h, int32_t n);
+int fuf_tree_destroy(fuf_ctx *ctx);
+int fuf_tree_get_info(const fuf_ctx *ctx, fuf_tree_info *info);
+
+/* Smallest legal ldp for N samples (N rounded up to a multiple of FUF_TILE). */
+int64_t fuf_padded_samples(int64_t N);
+
+/* Push-up, production path.  X (device, x_dtype, sample-major, leading dimension ldx >= n) holds N
+ * samples; columns [col0, col0+N) of PT (device, float, ld ldp) receive
+ *   PT[k][col0+s] = (float)( w_k * sum_{k' in subtree(k)} X[s][k'] ),  w = L (L1) or sqrt(L) (L2), w_root = 1.
+ * Subtree sums are accumulated in double. */
+int fuf_push_up(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, float *PT, int64_t ldp,
+                int64_t col0, void *stream);
+
+/* Push-up, validation path: float64 in/out, additions in the reference's order (bit-identical to
+ * push_up_L1 / push_up_L2 for finite inputs).  P64T: device double, node-major, ld ldp. */
+int fuf_push_up_f64(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int mode, double *P64T, int64_t ldp,
+                    int64_t col0, void *stream);
+
+/* Load ALREADY pushed profiles (what pairwise_computation receives, src/algorithms/emd_unifrac.py:42):
+ * P_rows (device, p_dtype, sample-major N x n, ld >= n) -> node-major PT of dtype out_dtype, columns [col0, col0+N). */
+int fuf_load_pushed(fuf_ctx *ctx, const void *P_rows, int p_dtype, int64_t N, int64_t ld, void *PT, int out_dtype,
+                    int64_t ldp, int64_t col0, void *stream);
+
+/* All-pairs distances from pushed profiles.
+ *   PT          device float, node-major.  The samples may be split in equal shards of `shard` columns
+ *               laid out one after the other: sample s lives at PT[(s / shard) * shard_stride + k * shard + s % shard]
+ *               (what an all-gather of per-rank [n][shard] blocks produces).  shard == 0: a single block with
+ *               leading dimension ldp (shard_stride ignored).  shard must be a multiple of FUF_TILE.
+ *   tile_rows_h host array of the 128-row tile rows to compute, NULL = all of them.
+ *   D           device (or pinned, device-accessible host) double.
+ *                 tile_rows_h == NULL : full N x N matrix, ld ldd, both triangles and the zero diagonal written.
+ *                 tile_rows_h != NULL : compact row blocks; block c (rows c*128 .. c*128+127) holds the rows of
+ *                                       tile row tile_rows_h[c]; only columns j >= tile_rows_h[c]*128 are written.
+ *   Accumulation: fp32 partial sums over 256 basis entries, combined in double. */
+int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
+                 const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags, void *stream);
+
+/* Validation mode: everything in double. Full matrix only. */
+int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
+                     void *stream);
+
+/* Join compact row blocks (as written by fuf_pairwise with tile_rows_h, possibly gathered from several
+ * devices and concatenated: blocks[c] for c in [0, n_blocks)) into the full symmetric N x N matrix. */
+int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
+                 int64_t ldb, double *D, int64_t ldd, void *stream);
+
+/* Differential-abundance rows for pairs [pair_begin, pair_end) in itertools.combinations(range(N), 2) order:
+ *   out[(p - pair_begin) * n + k] = P_i[k] - P_j[k]          (L1)
+ *                                   (P_i[k] - P_j[k])^2      (L2)
+ * PT: node-major profiles of dtype p_dtype; out: device or pinned host memory of dtype out_dtype. */
+int fuf_diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
+                     int64_t pair_end, void *out, int out_dtype, void *stream);
+
+/* Whole path with HOST buffers (the call a reference-side binding makes):
+ *   X_h  host, x_dtype, sample-major N x n (ldx >= n), un-pushed normalised profiles;
+ *   D_h  host double N x N (ldd >= N).
+ * Copies X to the device in row blocks, pushes up, computes all pairs and returns D in D_h.
+ * Pinned (cudaHostAlloc / cudaHostRegister) buffers are used in place; pageable ones are staged.
+ * validate != 0 runs the float64 validation kernels instead of the fp32 production path. */
+int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, int64_t N, int64_t ldx, int mode, double *D_h,
+                       int64_t ldd, int validate);
+
+/* Timing of the phases of the last fuf_all_pairs_host call on this context, milliseconds (CUDA events). */
+int fuf_last_timing(const fuf_ctx *ctx, float *h2d_pushup_ms, float *pairwise_ms, float *total_ms);
+
+/* Number of kernel launches issued by this library since the context was created (bench bookkeeping). */
+int64_t fuf_launch_count(const fuf_ctx *ctx);
+
+/* Test hook, host only (needs no device): the plan of the chunked push-up for a postorder parent array.
+ * Arrays of length n; span_out gets 5 ints per spanning node (k, chunk_first, chunk_last, slot_start, slot_k). */
+int fuf_debug_tree_plan(const int32_t *parent_h, int32_t n, int32_t *parent_local, int32_t *cp_after,
+                        uint8_t *is_span, int32_t *span_out, int32_t *n_span, int32_t *n_cp, int32_t *contiguous,
+                        int32_t *chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUNUNIFRAC_H */

@@ -1,0 +1,98 @@
+"""numpy models of the CUDA kernels' index math and summation order (TEST CODE).
+
+They restate, step by step, what ``csrc/pushup.cu`` and ``csrc/pairwise.cu`` do on the device so that the
+host-side planning (``fuf_debug_tree_plan``) and the numerical scheme (fp32 partial sums over 256 basis
+entries folded into double) can be checked against the oracle on a box without a GPU.  The GPU tests check
+the real kernels against the same oracle.
+"""
+import ctypes
+
+import numpy as np
+
+from fununifrac_b200 import engine
+
+
+def tree_plan(parent):
+    L = engine.load_library()
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    n = len(parent)
+    pl, cp = np.empty(n, np.int32), np.empty(n, np.int32)
+    sp, span = np.empty(n, np.uint8), np.empty(5 * n, np.int32)
+    ns, ncp, contig, chunk = (ctypes.c_int32() for _ in range(4))
+    L.fuf_debug_tree_plan.restype = ctypes.c_int
+    rc = L.fuf_debug_tree_plan(parent.ctypes.data_as(ctypes.c_void_p), n, pl.ctypes.data_as(ctypes.c_void_p),
+                               cp.ctypes.data_as(ctypes.c_void_p), sp.ctypes.data_as(ctypes.c_void_p),
+                               span.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ns), ctypes.byref(ncp),
+                               ctypes.byref(contig), ctypes.byref(chunk))
+    if rc != 0:
+        raise RuntimeError(L.fuf_last_error().decode())
+    return dict(parent_local=pl, cp_after=cp, is_span=sp.astype(bool), span=span[:5 * ns.value].reshape(-1, 5),
+                n_cp=ncp.value, contiguous=bool(contig.value), chunk=chunk.value)
+
+
+def pushup_model(parent, length, X, is_l2, plan=None, x_dtype=np.float64):
+    """K1a/K1b/K1c of pushup.cu on the host: returns PT-like float32 [N, n]."""
+    parent = np.asarray(parent)
+    n = len(parent)
+    plan = plan or tree_plan(parent)
+    assert plan["contiguous"]
+    KT = plan["chunk"]
+    w = np.array(length, dtype=np.float64)
+    w[:-1][w[:-1] == 0] = np.finfo(np.float64).eps
+    if is_l2:
+        w = np.sqrt(w)
+    w[-1] = 1.0
+    X = np.asarray(X).astype(x_dtype)
+    N = X.shape[0]
+    n_chunks = (n + KT - 1) // KT
+    out = np.full((N, n), np.nan, dtype=np.float32)
+    T = np.zeros((n_chunks, N))
+    CP = np.zeros((max(1, plan["n_cp"]), N))
+    for c in range(n_chunks):                       # K1a: one CTA per chunk (and 128-sample block)
+        k0 = c * KT
+        kt = min(KT, n - k0)
+        acc = np.zeros((KT, N))
+        r = np.zeros(N)
+        for kk in range(kt):
+            k = k0 + kk
+            x = X[:, k].astype(np.float64)
+            S = x + acc[kk]
+            r = r + x
+            pl = plan["parent_local"][k]
+            if pl >= 0:
+                acc[pl] += S
+            if not plan["is_span"][k]:
+                out[:, k] = (w[k] * S).astype(np.float32)
+            cp = plan["cp_after"][k]
+            if cp >= 0:
+                CP[cp] = r
+        T[c] = r
+    CT = np.zeros_like(T)                            # K1b: exclusive scan over chunks
+    run = np.zeros(N)
+    for c in range(n_chunks):
+        CT[c] = run
+        run = run + T[c]
+    for k, cf, cl, s_start, s_k in plan["span"]:     # K1c: spanning nodes from prefix differences
+        hi = CT[cl] + CP[s_k]
+        lo = CT[cf] + (CP[s_start] if s_start >= 0 else 0.0)
+        out[:, k] = (w[k] * (hi - lo)).astype(np.float32)
+    assert not np.isnan(out).any()
+    return out
+
+
+def pairwise_model(P32, is_l2, flush=256):
+    """K2's numerical scheme: fp32 subtraction and accumulation over chunks of `flush` basis entries,
+    chunk sums combined in double.  P32: float32 [N, n]."""
+    P32 = np.asarray(P32, dtype=np.float32)
+    N, n = P32.shape
+    D = np.zeros((N, N))
+    for k0 in range(0, n, flush):
+        blk = P32[:, k0:k0 + flush]
+        d = blk[:, None, :] - blk[None, :, :]
+        d = np.abs(d) if not is_l2 else d * d
+        part = np.zeros((N, N), dtype=np.float32)
+        for kk in range(d.shape[2]):                 # sequential fp32 adds, like one register accumulator
+            part = part + d[:, :, kk]
+        D += part.astype(np.float64)
+    np.fill_diagonal(D, 0.0)
+    return D
