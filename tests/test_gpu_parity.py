@@ -1,0 +1,416 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): the CUDA path, called through the C ABI, against
+(1) vectors produced by the unmodified reference (tests/golden), (2) the CPU oracle on seeded inputs, and
+(3) size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star): tree/postorder/basis bit-exact (CPU tests); float64 validation
+kernels: push-up bit-identical, distances within 1e-12 relative; production fp32 path: within 1e-6 relative
+of the reference's float64 output (pairs whose distance is tiny relative to the operands: 1e-6 of that scale).
+"""
+import glob
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import torch  # noqa: E402
+
+from fununifrac_b200 import engine, sparse_npz, synth  # noqa: E402
+from fununifrac_b200.algorithms.emd_unifrac import EarthMoverDistanceUniFracSolver  # noqa: E402
+from fununifrac_b200.factory import make_emd_input, make_tree  # noqa: E402
+from oracle import oracle_c  # noqa: E402
+
+REL = 1e-6
+
+
+def rel_err(D, ref, scale=None):
+    iu = np.triu_indices(len(ref), 1)
+    den = np.maximum(ref[iu], 1e-300) if scale is None else np.maximum(ref[iu], scale[iu])
+    return (np.abs(D[iu] - ref[iu]) / den).max() if len(iu[0]) else 0.0
+
+
+def pair_scale(P, l2):
+    """Operand scale of each pair: ||P_i||_1 + ||P_j||_1 (L1) or ||P_i||² + ||P_j||² (L2)."""
+    s = (P ** 2).sum(1) if l2 else np.abs(P).sum(1)
+    return s[:, None] + s[None, :]
+
+
+def run_all(ctx, X, l2, check_scalar=True):
+    """Every device route for the same input: validation, production (packed / scalar), host-buffer call."""
+    mode = engine.MODE_L2 if l2 else engine.MODE_L1
+    N = X.shape[0]
+    Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    P64T = ctx.push_up_f64(Xd, mode)
+    D64 = ctx.pairwise_f64(P64T, N, mode).cpu().numpy()
+    PT = ctx.push_up(Xd, mode)
+    D32 = ctx.pairwise(PT, N, mode).cpu().numpy()
+    if check_scalar:
+        D32s = ctx.pairwise(PT, N, mode, flags=engine.PW_SCALAR_MATH).cpu().numpy()
+        assert np.array_equal(D32, D32s)      # FADD2/FFMA2 are IEEE per lane: identical to scalar FADD/FFMA
+    Dh = ctx.all_pairs_host(X, mode)
+    assert np.array_equal(Dh, D32)
+    Dhv = ctx.all_pairs_host(X, mode, validate=True)
+    assert np.array_equal(Dhv, D64)
+    return P64T[:, :N].t().cpu().numpy(), PT[:, :N].t().cpu().numpy(), D64, D32
+
+
+def check_matrix(D):
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0) and np.all(D >= 0)
+
+
+# --------------------------------------------------------------------------------------------------
+# (1) reference-generated goldens
+# --------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def toy(data_dir, golden_dir):
+    tree = make_tree.import_graph(os.path.join(data_dir, "small_edge_list_with_lengths.txt"))
+    inp = make_emd_input.tree_to_EMDU_input(tree, "ko00001")
+    return inp, engine.TreeContext(inp.parent, inp.edge_length), np.load(os.path.join(golden_dir, "toy_config1.npz"))
+
+
+@pytest.mark.parametrize("tag,l2", [("l1_median", False), ("l2_median", True), ("l1_median_unweighted", False),
+                                    ("l2_median_unweighted", True), ("l1_default", False)])
+def test_config1_toy(tag, l2, toy):
+    inp, ctx, z = toy
+    P64, P32, D64, D32 = run_all(ctx, z[f"{tag}.X"], l2)
+    assert np.array_equal(P64, z[f"{tag}.P"])                      # bit-identical push-up
+    assert np.allclose(P32, z[f"{tag}.P"], rtol=2e-7, atol=0)
+    ref = z[f"{tag}.D"]
+    for D in (D64, D32):
+        check_matrix(D)
+    assert rel_err(D64, ref) < 1e-12 and rel_err(D32, ref, 1e-3 * pair_scale(z[f"{tag}.P"], l2)) < REL
+    assert np.all(D32[ref == 0] == 0)                              # identical samples → exactly 0
+    if tag == "l1_median":   # hand values of tests/scripts/test_make_all_pw_fununifrac.py:32-33
+        assert np.allclose(D32, [[0.0, 13 / 14, 10 / 21], [13 / 14, 0.0, 4 / 3], [10 / 21, 4 / 3, 0.0]], atol=1e-3)
+    if tag == "l2_median":   # :173-175
+        k = np.array([[0.0, np.sqrt(37) / 14, np.sqrt(22) / 21], [np.sqrt(37) / 14, 0.0, np.sqrt(13) / 6],
+                      [np.sqrt(22) / 21, np.sqrt(13) / 6, 0.0]]) ** 2
+        assert np.allclose(D32, k, atol=1e-3)
+
+
+@pytest.mark.parametrize("tag,l2,unw", [("l1", False, False), ("l2", True, False), ("l1_unweighted", False, True)])
+def test_synth_mid_golden(tag, l2, unw, golden_dir):
+    z = np.load(os.path.join(golden_dir, "synth_mid.npz"))
+    ctx = engine.TreeContext(z["parent"], z["length"])
+    assert ctx.info().n_zero_len > 0 and ctx.info().n_spanning > 0
+    X = z["X"].copy()
+    if unw:
+        X[X > 0] = 1
+    P64, P32, D64, D32 = run_all(ctx, X, l2)
+    assert np.array_equal(P64, z[f"{tag}.P"])
+    assert np.allclose(P32, z[f"{tag}.P"], rtol=2e-7, atol=0)
+    ref = z[f"{tag}.D"]
+    check_matrix(D32)
+    assert rel_err(D64, ref) < 1e-12
+    # ordinary pairs: plain 1e-6 relative; near-duplicates (0,20): 1e-6 of the operand scale; (1,21): exactly 0
+    assert rel_err(D32, ref, 1e-3 * pair_scale(z[f"{tag}.P"], l2)) < REL
+    iu = np.triu_indices(len(ref), 1)
+    ordinary = ref[iu] > 1e-2 * np.median(ref[iu])
+    assert (np.abs(D32[iu] - ref[iu]) / np.maximum(ref[iu], 1e-300))[ordinary].max() < REL
+    assert D32[1, 21] == 0.0 and D64[1, 21] == 0.0
+
+
+def test_real_tree_golden(golden_dir, real_trees):
+    z = np.load(os.path.join(golden_dir, "real_tree_rows.npz"))
+    inp = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(
+        real_trees["kegg_ko_edge_df_br_ko00001.txt_AAI_lengths_n_50_f_10_r_100.txt"]), "ko00001")
+    ctx = engine.TreeContext(inp.parent, inp.edge_length)
+    n, N = len(inp.basis), len(z["indptr"]) - 1
+    X = np.zeros((N, n))
+    for i in range(N):
+        s, e = z["indptr"][i], z["indptr"][i + 1]
+        X[i, z["indices"][s:e]] = z["values"][s:e]
+    internal = np.setdiff1d(np.arange(n), synth.leaves_of(inp.parent))
+    for tag, l2 in (("l1", False), ("l2", True)):
+        P64, P32, D64, D32 = run_all(ctx, X, l2)
+        assert np.array_equal(P64[0][internal], z[f"{tag}.P0_internal"])
+        assert rel_err(D64, z[f"{tag}.D"]) < 1e-12 and rel_err(D32, z[f"{tag}.D"]) < REL
+
+
+# --------------------------------------------------------------------------------------------------
+# (2) the oracle on seeded inputs, full-size synthetic KO tree
+# --------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_tree(tmp_path_factory):
+    path = synth.synth_ko_tree(str(tmp_path_factory.mktemp("synth") / "ko_tree.txt"), seed=0)
+    inp = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(path), "ko00001")
+    assert len(inp.basis) == 30002
+    return inp, engine.TreeContext(inp.parent, inp.edge_length), synth.leaves_of(inp.parent)
+
+
+@pytest.mark.parametrize("l2", [False, True])
+def test_full_tree_vs_oracle(l2, full_tree):
+    inp, ctx, leaves = full_tree
+    N = 300                                  # 3 tile rows, edge tile 44 wide, k-split path (few tiles)
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=1)
+    Pref = oracle_c.push_up(inp.parent, inp.edge_length, X, l2)
+    Dref = oracle_c.pairwise(Pref, l2)
+    P64, P32, D64, D32 = run_all(ctx, X, l2, check_scalar=False)
+    assert np.array_equal(P64, Pref)
+    assert np.allclose(P32, Pref, rtol=2e-7, atol=0)
+    check_matrix(D32)
+    assert rel_err(D64, Dref) < 1e-12
+    assert rel_err(D32, Dref) < REL
+    # float32 resident input (the benchmark's device format) obeys the same bound
+    PT = ctx.push_up(torch.from_numpy(X.astype(np.float32)).cuda(), engine.MODE_L2 if l2 else engine.MODE_L1)
+    D = ctx.pairwise(PT, N, engine.MODE_L2 if l2 else engine.MODE_L1).cpu().numpy()
+    assert rel_err(D, Dref) < 2e-6
+
+
+def test_unweighted_full_tree(full_tree):
+    inp, ctx, leaves = full_tree
+    X = synth.synth_profiles_dense(leaves, ctx.n, 40, seed=2)
+    X[X > 0] = 1                              # --unweighted: after normalisation, not renormalised
+    Pref = oracle_c.push_up(inp.parent, inp.edge_length, X, False)
+    assert Pref[:, -1].min() > 1000           # the unscaled root entry carries the node count
+    Dref = oracle_c.pairwise(Pref, False)
+    D = ctx.all_pairs_host(X, engine.MODE_L1)
+    assert rel_err(D, Dref) < REL
+
+
+# --------------------------------------------------------------------------------------------------
+# sharding primitives: compact tile rows + assemble, sharded profile layout
+# --------------------------------------------------------------------------------------------------
+def test_tile_rows_assemble_and_shards(full_tree):
+    inp, ctx, leaves = full_tree
+    N = 700                                   # 6 tile rows
+    X = torch.from_numpy(synth.synth_profiles_dense(leaves, ctx.n, N, seed=3, dtype=np.float32)).cuda()
+    PT = ctx.push_up(X, engine.MODE_L1)
+    D = ctx.pairwise(PT, N, engine.MODE_L1)
+    T = (N + 127) // 128
+    # 3 "ranks", boustrophedon tile rows, each computing compact upper row blocks
+    owners = [[t for t in range(T) if (t % 6 if t % 6 < 3 else 5 - t % 6) == r] for r in range(3)]
+    blocks, rows = [], []
+    for own in owners:
+        blk = ctx.pairwise(PT, N, engine.MODE_L1, tile_rows=own)
+        assert blk.shape == (len(own) * 128, N)
+        blocks.append(blk)
+        rows += own
+    D2 = ctx.assemble(torch.cat(blocks, 0), rows, N)
+    assert torch.equal(D, D2)
+    # sharded layout [G, n, shard]: what an all-gather of per-rank push-up outputs looks like
+    shard = 256
+    G = (N + shard - 1) // shard
+    PS = torch.zeros((G, ctx.n, shard), dtype=torch.float32, device="cuda")
+    for g in range(G):
+        w = min(shard, N - g * shard)
+        ctx.push_up(X[g * shard:g * shard + w], engine.MODE_L1, PS[g], 0)
+    D3 = ctx.pairwise(PS, N, engine.MODE_L1, shard=shard, shard_stride=ctx.n * shard)
+    assert torch.equal(D, D3)
+
+
+# --------------------------------------------------------------------------------------------------
+# (3) size-independent properties at a larger size + edge cases
+# --------------------------------------------------------------------------------------------------
+def test_properties_large(full_tree):
+    inp, ctx, leaves = full_tree
+    N = 1500
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=4, dtype=np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    PT = ctx.push_up(Xd, engine.MODE_L1)
+    D = ctx.pairwise(PT, N, engine.MODE_L1).cpu().numpy()
+    check_matrix(D)
+    # homogeneity: scaling every profile by 2 is exact in binary floating point
+    D2 = ctx.pairwise(ctx.push_up(Xd * 2, engine.MODE_L1), N, engine.MODE_L1).cpu().numpy()
+    assert np.array_equal(D2, 2 * D)
+    # permutation equivariance, bit for bit (a pair's k-order does not depend on its tile position)
+    perm = np.random.default_rng(0).permutation(N)
+    Dp = ctx.pairwise(ctx.push_up(Xd[torch.from_numpy(perm).cuda()], engine.MODE_L1), N, engine.MODE_L1).cpu().numpy()
+    assert np.array_equal(Dp, D[np.ix_(perm, perm)])
+    # L1 on pushed vectors is a metric: triangle inequality on random triples
+    rng = np.random.default_rng(1)
+    i, j, k = rng.integers(0, N, (3, 20000))
+    assert np.all(D[i, k] <= D[i, j] + D[j, k] + 1e-9)
+    # a random sample of pairs against the oracle
+    sub = np.sort(rng.choice(N, 64, replace=False))
+    Pref = oracle_c.push_up(inp.parent, inp.edge_length, X[sub].astype(np.float64), False)
+    assert rel_err(D[np.ix_(sub, sub)], oracle_c.pairwise(Pref, False)) < 2e-6
+    # mass conservation of the push-up: the root entry is the total mass
+    assert np.allclose(PT[-1, :N].cpu().numpy(), X.astype(np.float64).sum(1), rtol=1e-6)
+
+
+@pytest.mark.parametrize("N", [1, 2, 127, 128, 129])
+def test_edge_sizes(N, full_tree):
+    inp, ctx, leaves = full_tree
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=6)
+    for l2 in (False, True):
+        Pref = oracle_c.push_up(inp.parent, inp.edge_length, X, l2)
+        D = ctx.all_pairs_host(X, engine.MODE_L2 if l2 else engine.MODE_L1)
+        assert D.shape == (N, N) and rel_err(D, oracle_c.pairwise(Pref, l2)) < REL
+        check_matrix(D)
+
+
+def test_degenerate_trees():
+    # single node (root only), chain (every node spans chunks), star; with zero-length edges
+    rng = np.random.default_rng(0)
+    chain = np.arange(1, 101, dtype=np.int32)
+    chain[-1] = -1
+    star = np.full(100, 99, dtype=np.int32)
+    star[-1] = -1
+    for parent in (np.array([-1], np.int32), chain, star):
+        n = len(parent)
+        length = rng.random(n) * (rng.random(n) > 0.2)
+        ctx = engine.TreeContext(parent, length)
+        X = rng.random((5, n))
+        for l2 in (False, True):
+            Pref = oracle_c.push_up(parent, length, X, l2)
+            P64, P32, D64, D32 = run_all(ctx, X, l2)
+            assert np.array_equal(P64, Pref)
+            assert rel_err(D32, oracle_c.pairwise(Pref, l2)) < REL
+    # empty input is a no-op, bad arguments are errors (never a crash)
+    ctx = engine.TreeContext(chain, np.ones(100))
+    assert ctx.all_pairs_host(np.zeros((0, 100)), engine.MODE_L1).shape == (0, 0)
+    with pytest.raises(engine.FunUniFracError):
+        engine.TreeContext(np.array([0, -1], np.int32), np.ones(2))       # parent[i] <= i
+    with pytest.raises(ValueError):
+        ctx.all_pairs_host(np.zeros((3, 99)), engine.MODE_L1)
+
+
+def test_non_dfs_order_falls_back_to_exact_kernel():
+    parent = np.array([3, 2, 4, 4, -1], np.int32)       # valid child<parent order, subtrees interleaved
+    length = np.array([0.5, 0.25, 1.0, 2.0, 0.0])
+    ctx = engine.TreeContext(parent, length)
+    assert ctx.info().n_spanning == -1
+    X = np.random.default_rng(0).random((4, 5))
+    D = ctx.all_pairs_host(X, engine.MODE_L1)
+    assert rel_err(D, oracle_c.pairwise(oracle_c.push_up(parent, length, X, False), False)) < REL
+
+
+# --------------------------------------------------------------------------------------------------
+# diffab, solver API, CLI
+# --------------------------------------------------------------------------------------------------
+def test_diffab_blocks_vs_oracle(golden_dir):
+    z = np.load(os.path.join(golden_dir, "synth_mid.npz"))
+    ctx = engine.TreeContext(z["parent"], z["length"])
+    N, n = z["X"].shape
+    Xd = torch.from_numpy(z["X"]).cuda()
+    for tag, l2 in (("l1", False), ("l2", True)):
+        mode = engine.MODE_L2 if l2 else engine.MODE_L1
+        want = oracle_c.diffab_dense(z[f"{tag}.P"], l2)
+        P64T = ctx.push_up_f64(Xd, mode)
+        got = np.zeros((N, N, n))
+        seen = 0
+        for b, e, rows in engine.iter_diffab_blocks(ctx, P64T, N, mode, pairs_per_block=37):
+            for p in range(b, e):
+                i = int(np.searchsorted([engine.combinations_offset(r, N) for r in range(N)], p, side="right")) - 1
+                j = p - engine.combinations_offset(i, N) + i + 1
+                got[i, j] = rows[p - b]
+                got[j, i] = -rows[p - b]
+            seen += e - b
+        assert seen == N * (N - 1) // 2
+        assert np.array_equal(got, want)                 # float64 rows are bit-identical to P_i - P_j
+        PT = ctx.push_up(Xd, mode)
+        out = torch.empty((N - 1, n), dtype=torch.float32, device="cuda")
+        ctx.diffab_block(PT, N, mode, 0, N - 1, out)     # pairs (0, 1..N-1), fp32 production rows
+        scale = np.abs(z[f"{tag}.P"]).max()
+        assert np.abs(out.cpu().numpy() - want[0, 1:]).max() < 1e-6 * max(scale, scale ** 2)
+
+
+def test_solver_api_matches_reference_semantics(toy, golden_dir):
+    inp, ctx, z = toy
+    solver = EarthMoverDistanceUniFracSolver()
+    files = list(z["files"])
+    for tag, l2 in (("l1_median", False), ("l2_median", True)):
+        X, Pg, Dg, diffab_g = z[f"{tag}.X"], z[f"{tag}.P"], z[f"{tag}.D"], z[f"{tag}.diffab"]
+        Ps = {}
+        for f, x in zip(files, X):
+            x0 = x.copy()
+            Ps[f] = solver.push_up_L2(x, inp) if l2 else solver.push_up_L1(x, inp)
+            assert np.array_equal(x, x0)                # the input vector is not modified
+        assert np.array_equal(np.array([Ps[f] for f in files]), Pg)
+        dists, none = solver.pairwise_computation(Ps, files, inp, False, l2)
+        assert none is None and rel_err(dists, Dg) < REL and dists.dtype == np.float64
+        dists, coo = solver.pairwise_computation(Ps, files, inp, True, l2)
+        assert rel_err(dists, Dg) < REL
+        assert np.allclose(coo.todense(), diffab_g, rtol=0, atol=2e-7)
+        assert np.allclose(coo[2, 0, :].todense(), -coo[0, 2, :].todense())
+        v = EarthMoverDistanceUniFracSolver(validate=True)
+        dists, coo = v.pairwise_computation(Ps, files, inp, True, l2)
+        assert rel_err(dists, Dg) < 1e-12 and np.array_equal(coo.todense(), diffab_g)
+    # known diffab answers: tests/scripts/test_make_all_pw_fununifrac.py:78-88
+    Ps = {f: solver.push_up_L1(x, inp) for f, x in zip(files, z["l1_median.X"])}
+    _, coo = solver.pairwise_computation(Ps, files, inp, True, False)
+    assert np.allclose(coo[0, 2, :].todense(), [-1 / 14, -1 / 21, -5 / 42, 5 / 42, 0, 5 / 42, 0], atol=1e-3)
+    assert np.allclose(coo[0, 0, :].todense(), 0)
+    # get_L1 & co
+    from fununifrac_b200.objects import profile_vector as pv
+    P, Q = Ps[files[0]], Ps[files[1]]
+    assert np.isclose(pv.get_L1(P, Q), np.sum(np.abs(P - Q)), rtol=1e-14)
+    assert np.isclose(pv.get_L2(P, Q), np.sum((P - Q) ** 2), rtol=1e-14)
+    assert np.array_equal(pv.get_L1_diffab(P, Q), P - Q) and np.array_equal(pv.get_L2_diffab(P, Q), (P - Q) ** 2)
+
+
+def test_push_up_side_effect_on_lint():
+    from fununifrac_b200.objects.func_tree import FuncTreeEmduInput
+    inp = FuncTreeEmduInput({0: 2, 1: 2}, {(0, 2): 0, (2, 0): 0, (1, 2): 1.0, (2, 1): 1.0}, [0, 1, 2],
+                            {0: 'a', 1: 'b', 2: 'r'})
+    out = EarthMoverDistanceUniFracSolver().push_up_L1(np.array([0.5, 0.5, 0.0]), inp)
+    assert out.tolist() == [0.5 * 2.220446049250313e-16, 0.5, 1.0]
+    assert inp.lint[(0, 2)] == 2.220446049250313e-16 and inp.lint[(2, 0)] == 0   # one direction only
+
+
+def test_legacy_solve_entry_points(data_dir, golden_dir):
+    import json
+    with open(os.path.join(golden_dir, "solve.json")) as f:
+        g = json.load(f)
+    solver = EarthMoverDistanceUniFracSolver()
+    inp4 = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(
+        os.path.join(data_dir, "small_edge_list_with_lengths_emdu.txt")))
+    for weighted in (True, False):
+        c = g[f"emdu4:weighted={weighted}"]
+        Z, diffab = solver.solve(inp4, np.array(c["P"]), np.array(c["Q"]), weighted)
+        assert Z == c["Z"] and {f"{a},{b}": v for (a, b), v in diffab.items()} == c["diffab"]
+        Z, F, diffab = solver.solve_with_flow(inp4, np.array(c["P"]), np.array(c["Q"]), weighted)
+        assert Z == c["Z_flow"] and {f"{a},{b}": float(v) for (a, b), v in F.items()} == c["F"]
+        assert set(f"{a},{b}" for a, b in diffab) == set(c["diffab_flow"])
+        for (a, b), v in diffab.items():
+            assert np.isclose(v, c["diffab_flow"][f"{a},{b}"])
+    inp7 = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(
+        os.path.join(data_dir, "small_edge_list_with_lengths.txt")))
+    for c in g["small7:dirichlet"]:
+        Z, diffab = solver.solve(inp7, np.array(c["P"]), np.array(c["Q"]), True)
+        assert Z == c["Z"] and {f"{a},{b}": v for (a, b), v in diffab.items()} == c["diffab"]
+
+
+def test_cli_end_to_end(data_dir, golden_dir, tmp_path):
+    """BASELINE config 1 through the CLI: same flags, same files, same contents as the reference run."""
+    from fununifrac_b200 import compute_fununifrac
+    from fununifrac_b200.utility import constant
+    z = np.load(os.path.join(golden_dir, "toy_config1.npz"))
+    edge = os.path.join(data_dir, "small_edge_list_with_lengths.txt")
+    out = str(tmp_path / "out")
+    base = ["-e", edge, "-fd", data_dir, "-o", out, "-i", "testing", "--force", "-b", "ko00001", "-a", "median_abund",
+            "-t", "2"]
+    compute_fununifrac.main(base)
+    D = np.load(os.path.join(out, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format("testing")))
+    assert D.dtype == np.float64 and rel_err(D, z["l1_median.D"]) < REL
+    with open(os.path.join(out, constant.FUNUNIFRAC_OUT__MAIN_BASIS__FILE_NAME.format("testing"))) as f:
+        basis = [os.path.basename(l.strip()) for l in f]
+    assert basis == ["small_sim2_10_KOs_gather.csv", "small_sim3_10_KOs_gather.csv", "small_sim_10_KOs_gather.csv"]
+    # --L2 --diffab --Ppushed
+    compute_fununifrac.main(base + ["--L2", "--diffab", "--Ppushed"])
+    D = np.load(os.path.join(out, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format("testing")))
+    assert rel_err(D, z["l2_median.D"]) < REL
+    coo = sparse_npz.load_npz(os.path.join(out, constant.FUNUNIFRAC_OUT__DIFFAB_FILE_NAME.format("testing")) + ".npz")
+    assert coo.shape == (3, 3, 7) and np.allclose(coo.todense(), z["l2_median.diffab"], atol=2e-7)
+    assert np.allclose(coo[0, 2, :].todense(), [1 / 196, 1 / 441, 25 / 1764, 25 / 1764, 0, 25 / 1764, 0], atol=1e-3)
+    with open(os.path.join(out, constant.FUNUNIFRAC_OUT__DIFFAB_NODES_FILE_NAME.format("testing"))) as f:
+        assert [l.strip() for l in f] == ['d', 'e', 'b', 'f', 'g', 'c', 'ko00001']
+    with open(os.path.join(out, constant.FUNUNIFRAC_OUT__PUSH_FILE_NAME.format("testing")), "rb") as f:
+        pushed = pickle.load(f)
+    files = sorted(glob.glob(os.path.join(data_dir, "*_gather.csv")))
+    assert list(pushed) == files and np.array_equal(np.array([pushed[f] for f in files]), z["l2_median.P"])
+    # --unweighted and the default abundance key
+    compute_fununifrac.main(base + ["--unweighted"])
+    D = np.load(os.path.join(out, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format("testing")))
+    assert rel_err(D, z["l1_median_unweighted.D"], np.full((3, 3), 1e-3)) < REL
+    compute_fununifrac.main([a for a in base if a not in ("-a", "median_abund")] + ["--validate"])
+    D = np.load(os.path.join(out, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format("testing")))
+    assert rel_err(D, z["l1_default.D"], np.full((3, 3), 1e-9)) < 1e-12
+    # validation errors of the driver
+    with pytest.raises(ValueError):
+        compute_fununifrac.main(base[:8] + ["-b", "not_a_brite", "-a", "median_abund"])
+    with pytest.raises(Exception):
+        compute_fununifrac.main(["-e", edge, "-fd", str(tmp_path), "-o", out])     # no matching files
