@@ -4,8 +4,9 @@
 
 * ``push_up_L1/L2``: one vector, float64 in → float64 out through the validation kernel, which replays the
   reference loop in its operation order, so the returned vector is bit-identical to the reference's.
-* ``pairwise_computation``: all pairs.  Default = production path (float32 operands, fp32 partial sums over
-  256 basis entries combined in float64; ≤1e-6 relative to the reference).  ``validate=True`` = float64 kernels.
+* ``pairwise_computation``: all pairs.  Default = production path (centred float32 operands, fp32 partial sums
+  over 256 basis entries combined in float64, then a float64 refinement pass over the pairs the fp32 operands
+  cannot certify; ≤1e-6 relative to the reference).  ``validate=True`` = float64 kernels throughout.
 * batch entry points used by the driver: ``push_up_batch`` and ``all_pairs`` (host matrix in, host D out).
 
 There is no CPU fallback; without the built extension or a GPU every method raises ``FunUniFracError``.
@@ -99,16 +100,20 @@ class EarthMoverDistanceUniFracSolver:
         dev = f"cuda:{ctx.device}"
         if N == 0:
             return np.zeros((0, 0)), (COO(np.zeros((3, 0)), np.zeros(0), (0, 0, n)) if make_diffab else None)
-        want64 = bool(self.validate)
-        dt = torch.float64 if want64 else torch.float32
-        PT = ctx.new_profile_buffer(N, dtype=dt)
+        P64T = ctx.new_profile_buffer(N, dtype=torch.float64)
         block = max(1, min(N, (256 << 20) // (8 * n)))
         for b in range(0, N, block):
             rows = np.stack([np.asarray(Ps[nm], dtype=np.float64) for nm in names[b:b + block]])
             if rows.shape[1] != n:
                 raise ValueError(f"pushed vectors must have length {n}")
-            ctx.load_pushed(torch.from_numpy(rows).to(dev), PT, col0=b)
-        D = ctx.pairwise_f64(PT, N, mode) if want64 else ctx.pairwise(PT, N, mode)
+            ctx.load_pushed(torch.from_numpy(rows).to(dev), P64T, col0=b)
+        if self.validate:
+            PT = P64T
+            D = ctx.pairwise_f64(P64T, N, mode)
+        else:
+            job = ctx.round_pushed(P64T, N, mode)
+            PT = job.PT
+            D = ctx.distances(job, mode)
         dists = D.cpu().numpy()
         if not make_diffab:
             return dists, None

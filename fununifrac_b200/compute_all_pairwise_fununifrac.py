@@ -83,8 +83,9 @@ def main(args):
             PT = ctx.push_up_f64(Xd, mode)
             dists = ctx.pairwise_f64(PT, N, mode).cpu().numpy()
         else:
-            PT = ctx.push_up(Xd, mode)
-            dists = ctx.pairwise(PT, N, mode).cpu().numpy()
+            job = ctx.push_up_job(Xd, mode)
+            PT = job.PT     # centred: per-pair differences are unchanged by the common offset
+            dists = ctx.distances(job, mode).cpu().numpy()
         diffabs_sparse = solver.diffab_coo(ctx, PT, N, mode)
     ##############################################################################
     # Save Outputs (reference :76-108)

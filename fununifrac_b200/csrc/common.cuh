@@ -81,6 +81,7 @@ struct fuf_ctx {
     int32_t *d_parent_local = nullptr;  // parent index relative to the node's chunk base, -1 if outside
     int32_t *d_cp_after = nullptr;      // checkpoint slot to store the chunk prefix after node k, -1 if none
     uint8_t *d_is_span = nullptr;       // 1 if node k is a spanning node (written by the fix-up kernel)
+    uint8_t *d_has_child = nullptr;     // 1 for internal nodes (the centre is zero on leaves)
     fuf::SpanNode *d_span = nullptr;
     int32_t n_chunks = 0, n_span = 0, n_cp = 0;
 
@@ -90,6 +91,11 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_x;        // X staging blocks (fuf_all_pairs_host)
     fuf::DeviceBuffer ws_p;        // PT / P64T (fuf_all_pairs_host)
     fuf::DeviceBuffer ws_d;        // D on device when the host buffer cannot be written in place
+    fuf::DeviceBuffer ws_center;   // column mean scratch of fuf_push_up_center
+    fuf::DeviceBuffer ws_rows;     // tile-row list of fuf_refine
+    fuf::DeviceBuffer ws_p64;      // P64T + centre + error statistics (fuf_all_pairs_host)
+    unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine
+    int64_t last_refined = 0;
     fuf::PinnedBuffer pin_x;       // pinned staging when X_h is pageable
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev[8] = {};
@@ -101,18 +107,25 @@ struct fuf_ctx {
 namespace fuf {
 
 // pushup.cu
-int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, float *PT, int64_t ldp,
-                int64_t col0, cudaStream_t stream);
+int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, const double *center,
+                float *PT, int64_t ldp, double *P64T, int64_t ldp64, double *err_stat, int64_t col0,
+                cudaStream_t stream);
+int push_up_center(fuf_ctx *ctx, const void *X, int x_dtype, int64_t m, int64_t ldx, int mode, double *center_out,
+                   cudaStream_t stream);
 int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int mode, double *P64T, int64_t ldp,
                       int64_t col0, cudaStream_t stream);
 // pairwise.cu
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream);
+                 cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0);
 int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
                  cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
              double *D, int64_t ldd, cudaStream_t stream);
+// refine.cu
+int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
+           const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
+           int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0);
 // diffab.cu
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                  int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);

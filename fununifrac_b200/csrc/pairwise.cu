@@ -51,6 +51,8 @@ struct PairParams {
     int64_t N;
     double *D;
     int64_t ldd;
+    double *D2;                // optional second destination (zero-copy host mirror of D), same indexing
+    int64_t ldd2;
     double *partial;           // [n_items][TILE*TILE] when splits > 1
 };
 
@@ -290,11 +292,19 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
             const int64_t gi0 = (int64_t)td.ti * TILE, gj0 = (int64_t)td.tj * TILE;
             if (gj0 + col < p.N) {
                 for (int r = half; r < TILE; r += 2)
-                    if (gi0 + r < p.N) p.D[((int64_t)td.out_row0 + r) * p.ldd + gj0 + col] = acc64[slot_of(r, col)];
+                    if (gi0 + r < p.N) {
+                        const double v = acc64[slot_of(r, col)];
+                        p.D[((int64_t)td.out_row0 + r) * p.ldd + gj0 + col] = v;
+                        if (p.D2) p.D2[((int64_t)td.out_row0 + r) * p.ldd2 + gj0 + col] = v;
+                    }
             }
             if (td.mirror && gi0 + col < p.N) {
                 for (int c = half; c < TILE; c += 2)
-                    if (gj0 + c < p.N) p.D[(gj0 + c) * p.ldd + gi0 + col] = acc64[slot_of(col, c)];
+                    if (gj0 + c < p.N) {
+                        const double v = acc64[slot_of(col, c)];
+                        p.D[(gj0 + c) * p.ldd + gi0 + col] = v;
+                        if (p.D2) p.D2[(gj0 + c) * p.ldd2 + gi0 + col] = v;
+                    }
             }
         }
         consumer_bar();  // the next item re-zeroes the accumulators
@@ -304,7 +314,7 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
 // Sum the k-split partial tiles in fixed order and write D (+ mirror).
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restrict__ partial, int splits, int64_t N,
-                       double *__restrict__ D, int64_t ldd)
+                       double *__restrict__ D, int64_t ldd, double *__restrict__ D2, int64_t ldd2)
 {
     const TileDesc td = tiles[blockIdx.x];
     const double *src = partial + (size_t)blockIdx.x * splits * (TILE * TILE);
@@ -319,13 +329,19 @@ reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restr
             for (int s = 0; s < splits; s++) v += src[(size_t)s * (TILE * TILE) + (r0 + rr) * TILE + c0 + lx];
             tile[rr][lx] = v;
             const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
-            if (gi < N && gj < N) D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
+            if (gi < N && gj < N) {
+                D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
+                if (D2) D2[((int64_t)td.out_row0 + r0 + rr) * ldd2 + gj] = v;
+            }
         }
         __syncthreads();
         if (td.mirror) {
             for (int cc = ly; cc < 32; cc += 8) {
                 const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;
-                if (gi < N && gj < N) D[gj * ldd + gi] = tile[lx][cc];
+                if (gi < N && gj < N) {
+                    D[gj * ldd + gi] = tile[lx][cc];
+                    if (D2) D2[gj * ldd2 + gi] = tile[lx][cc];
+                }
             }
         }
         __syncthreads();
@@ -390,7 +406,8 @@ assemble_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ t
                 double *__restrict__ D, int64_t ldd)
 {
     const int c = blockIdx.y;            // compact block
-    const int t = tile_rows[c];          // its tile row
+    const int t = tile_rows[c];          // its tile row (-1: padding slot of a gathered buffer)
+    if (t < 0) return;
     const int tj = t + blockIdx.x;       // tile column (only tj >= t carry data)
     const int64_t gi0 = (int64_t)t * TILE, gj0 = (int64_t)tj * TILE;
     if (gj0 >= N) return;
@@ -402,7 +419,11 @@ assemble_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ t
             const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
             double v = 0.0;
             if (gi < N && gj < N) {
-                v = blocks[((int64_t)c * TILE + r0 + rr) * ldb + gj];
+                // diagonal tile: the lower triangle is the mirror of the upper one (fuf_refine corrects only i < j)
+                if (tj == t && r0 + rr > c0 + lx)
+                    v = blocks[((int64_t)c * TILE + c0 + lx) * ldb + gi0 + r0 + rr];
+                else
+                    v = blocks[((int64_t)c * TILE + r0 + rr) * ldb + gj];
                 D[gi * ldd + gj] = v;
             }
             tile[rr][lx] = v;
@@ -443,7 +464,7 @@ static EncodeTiledFn get_encode_fn()
 
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream)
+                 cudaStream_t stream, double *D2, int64_t ldd2)
 {
     if (N == 0) return FUF_OK;
     const int32_t n = ctx->n;
@@ -522,7 +543,10 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
             }
         }
     }
+    // split boundaries fall on fp32 flush boundaries, so the set of 256-entry fp32 partial sums of a pair does
+    // not depend on the number of splits (only the order of the final double additions does)
     int32_t per_split = (stages_total + best_s - 1) / best_s;
+    per_split = (per_split + FLUSH_STAGES - 1) / FLUSH_STAGES * FLUSH_STAGES;
     const int32_t splits = (stages_total + per_split - 1) / per_split;  // no empty split
 
     size_t tiles_bytes = ((size_t)n_tiles * sizeof(TileDesc) + 255) & ~(size_t)255;
@@ -545,6 +569,8 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     p.N = N;
     p.D = D;
     p.ldd = ldd;
+    p.D2 = D2;
+    p.ldd2 = ldd2;
     p.partial = d_partial;
 
     const bool packed = !(flags & FUF_PW_SCALAR_MATH);
@@ -559,7 +585,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
     if (splits > 1) {
-        reduce_partials_kernel<<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd);
+        reduce_partials_kernel<<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd, D2, ldd2);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -587,7 +613,7 @@ int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int
     if (n_blocks == 0 || N == 0) return FUF_OK;
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
     for (int32_t c = 0; c < n_blocks; c++)
-        FUF_REQUIRE(tile_rows_h[c] >= 0 && tile_rows_h[c] < tiles_per_dim, "fuf_assemble: tile row %d out of range",
+        FUF_REQUIRE(tile_rows_h[c] >= -1 && tile_rows_h[c] < tiles_per_dim, "fuf_assemble: tile row %d out of range",
                     tile_rows_h[c]);
     int rc = ctx->ws_pair.reserve((size_t)n_blocks * sizeof(int32_t));
     if (rc) return rc;
@@ -615,7 +641,7 @@ extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ld
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_f32(ctx, PT, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd, flags,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, nullptr, 0);
 }
 
 extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D,

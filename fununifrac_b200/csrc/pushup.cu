@@ -12,9 +12,19 @@
 //                             the chunk with double accumulators in shared memory.  Nodes whose subtree lies
 //                             inside the chunk are final and written (coalesced along samples) as float.
 //                             For the rest ("spanning" nodes, a few hundred of 30K) the chunk leaves behind
-//                             its total mass T[chunk] and chunk-local prefix sums at checkpoint positions.
-//   K1b pushup_scan_kernel    exclusive scan of T over chunks (per sample) -> global prefix at chunk starts.
-//   K1c pushup_span_kernel    spanning node k: S = prefix(k) - prefix(start_k - 1); writes w_k * S.
+//                             its total mass T[chunk] and chunk-local prefix sums CP at checkpoint positions.
+//   K1b pushup_span_kernel    spanning node k: S = tail of its first chunk + totals of the chunks in between
+//                             + head of its last chunk (same-sign terms only); writes w_k * S.
+//   K1c pushup_stat_kernel    sums the per-chunk rounding-error statistics of the fp32 outputs per sample.
+//
+// Production outputs per entry (all optional):
+//   PT    float, CENTRED:  (float)(w_k * S_k - c_k).  Distances are invariant under subtracting one fixed vector c
+//         from every profile; with c = the pushed mean of a few samples on the internal nodes (fuf_push_up_center)
+//         the large, nearly sample-independent upper-level entries shrink to their sample-to-sample variation, so
+//         rounding them to fp32 costs 2^-24 of that variation instead of 2^-24 of their magnitude.
+//   P64T  double, uncentred w_k * S_k: the operands of the float64 refinement pass (refine.cu).
+//   err   per sample: sum_k |rounding error of PT| (L1) or sum_k (rounding error)^2 (L2), the input to the
+//         refinement criterion.
 //
 // Validation path (fuf_push_up_f64): transpose to node-major double, then one thread per sample replays the
 // reference loop verbatim -> bit-identical to the reference's float64 result.
@@ -25,18 +35,19 @@ namespace fuf {
 constexpr int KT = kPushChunk;  // nodes per chunk
 constexpr int TI = 128;         // samples per CTA
 
-template <typename TX>
+template <typename TX, int MODE>
 __global__ void __launch_bounds__(TI)
 pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n, const double *__restrict__ w,
                     const int32_t *__restrict__ parent_local, const int32_t *__restrict__ cp_after,
-                    const uint8_t *__restrict__ is_span, float *__restrict__ PT, int64_t ldp, int64_t col0,
-                    double *__restrict__ T, double *__restrict__ CP, int64_t ldt)
+                    const uint8_t *__restrict__ is_span, const double *__restrict__ center, float *__restrict__ PT,
+                    int64_t ldp, double *__restrict__ P64T, int64_t ldp64, int64_t col0, double *__restrict__ T,
+                    double *__restrict__ CP, double *__restrict__ R, int64_t ldt)
 {
     // dynamic shared memory: acc[KT][TI] double | xs[KT][TI+1] TX   (48.5 KB float, 65 KB double)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double(*acc)[TI] = reinterpret_cast<double(*)[TI]>(smem_raw);
     TX(*xs)[TI + 1] = reinterpret_cast<TX(*)[TI + 1]>(smem_raw + sizeof(double) * KT * TI);
-    __shared__ double s_w[KT];
+    __shared__ double s_w[KT], s_c[KT];
     __shared__ int32_t s_pl[KT], s_cp[KT];
     __shared__ uint8_t s_span[KT];
 
@@ -49,6 +60,7 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
         int32_t k = k0 + tid;
         bool ok = tid < kt;
         s_w[tid] = ok ? w[k] : 0.0;
+        s_c[tid] = (ok && center) ? center[k] : 0.0;
         s_pl[tid] = ok ? parent_local[k] : -1;
         s_cp[tid] = ok ? cp_after[k] : -1;
         s_span[tid] = ok ? is_span[k] : 1;
@@ -68,58 +80,117 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
 
     const int64_t s = i0 + tid;
     if (s >= N) return;
-    double r = 0.0;  // running sum of X over the chunk (chunk-local prefix)
-    float *out = PT + col0 + s;
+    double r = 0.0;    // running sum of X over the chunk (chunk-local prefix)
+    double err = 0.0;  // rounding-error statistic of the float outputs of this chunk
     for (int kk = 0; kk < kt; kk++) {
         double x = (double)xs[kk][tid];
         double S = x + acc[kk][tid];
         r += x;
         int pl = s_pl[kk];
         if (pl >= 0) acc[pl][tid] += S;
-        if (!s_span[kk]) out[(int64_t)(k0 + kk) * ldp] = (float)(s_w[kk] * S);
+        if (!s_span[kk]) {
+            const double v = s_w[kk] * S;
+            if (P64T) P64T[(int64_t)(k0 + kk) * ldp64 + col0 + s] = v;
+            if (PT) {
+                const double c = v - s_c[kk];
+                const float f = (float)c;
+                PT[(int64_t)(k0 + kk) * ldp + col0 + s] = f;
+                const double e = c - (double)f;
+                err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
+            }
+        }
         int cp = s_cp[kk];
         if (cp >= 0) CP[(int64_t)cp * ldt + s] = r;
     }
     if (T) T[(int64_t)blockIdx.x * ldt + s] = r;
+    if (R) R[(int64_t)blockIdx.x * ldt + s] = err;
 }
 
-// T[c][s] (chunk totals) -> exclusive prefix over chunks, in place.
-__global__ void pushup_scan_kernel(double *__restrict__ T, int32_t n_chunks, int64_t N, int64_t ldt)
+// R[c][s] (per-chunk error statistics) -> their sum in err_stat[col0 + s] (overwritten; the span kernel adds its
+// own share afterwards).
+__global__ void pushup_stat_kernel(const double *__restrict__ R, int32_t n_chunks, int64_t N, int64_t ldt,
+                                   double *__restrict__ err_stat, int64_t col0)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    double run = 0.0;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
     int c = 0;
-    for (; c + 8 <= n_chunks; c += 8) {
-        double v[8];
+    for (; c + 4 <= n_chunks; c += 4) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = T[(int64_t)(c + u) * ldt + s];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            T[(int64_t)(c + u) * ldt + s] = run;
-            run += v[u];
-        }
+        for (int u = 0; u < 4; u++) e[u] += R[(int64_t)(c + u) * ldt + s];
     }
-    for (; c < n_chunks; c++) {
-        double v = T[(int64_t)c * ldt + s];
-        T[(int64_t)c * ldt + s] = run;
-        run += v;
-    }
+    for (; c < n_chunks; c++) e[0] += R[(int64_t)c * ldt + s];
+    err_stat[col0 + s] = (e[0] + e[1]) + (e[2] + e[3]);
 }
 
+template <int MODE>
 __global__ void pushup_span_kernel(const SpanNode *__restrict__ span, int32_t n_span, const double *__restrict__ w,
-                                   const double *__restrict__ CT, const double *__restrict__ CP, int64_t ldt,
-                                   int64_t N, float *__restrict__ PT, int64_t ldp, int64_t col0)
+                                   const double *__restrict__ center, const double *__restrict__ T,
+                                   const double *__restrict__ CP, int64_t ldt, int64_t N, float *__restrict__ PT,
+                                   int64_t ldp, double *__restrict__ P64T, int64_t ldp64, int64_t col0,
+                                   double *__restrict__ err_stat)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
+    double err = 0.0;
     for (int q = blockIdx.y; q < n_span; q += gridDim.y) {
         SpanNode sn = span[q];
-        double hi = CT[(int64_t)sn.chunk_last * ldt + s] + CP[(int64_t)sn.slot_k * ldt + s];
-        double lo = CT[(int64_t)sn.chunk_first * ldt + s];
-        if (sn.slot_start >= 0) lo += CP[(int64_t)sn.slot_start * ldt + s];
-        PT[(int64_t)sn.k * ldp + col0 + s] = (float)(w[sn.k] * (hi - lo));
+        // subtree sum = tail of the first chunk + whole chunks in between + head of the last chunk: only
+        // same-sign terms are added (no difference of long prefix sums), so the result is accurate relative
+        // to the subtree's own mass
+        double head = T[(int64_t)sn.chunk_first * ldt + s];
+        if (sn.slot_start >= 0) head -= CP[(int64_t)sn.slot_start * ldt + s];
+        double mid[4] = {0.0, 0.0, 0.0, 0.0};
+        int c = sn.chunk_first + 1;
+        for (; c + 4 <= sn.chunk_last; c += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) mid[u] += T[(int64_t)(c + u) * ldt + s];
+        }
+        for (; c < sn.chunk_last; c++) mid[0] += T[(int64_t)c * ldt + s];
+        const double tail = CP[(int64_t)sn.slot_k * ldt + s];
+        const double S = (head + tail) + ((mid[0] + mid[1]) + (mid[2] + mid[3]));
+        const double v = w[sn.k] * S;
+        if (P64T) P64T[(int64_t)sn.k * ldp64 + col0 + s] = v;
+        if (PT) {
+            const double c = v - (center ? center[sn.k] : 0.0);
+            const float f = (float)c;
+            PT[(int64_t)sn.k * ldp + col0 + s] = f;
+            const double e = c - (double)f;
+            err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
+        }
     }
+    if (err_stat && PT && err != 0.0) atomicAdd(&err_stat[col0 + s], err);
+}
+
+// Centre support: column mean of the first m rows (double), and the leaf mask.
+template <typename TX>
+__global__ void column_mean_kernel(const TX *__restrict__ X, int64_t ldx, int64_t m, int32_t n, double *__restrict__ out)
+{
+    int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double acc = 0.0;
+    for (int64_t s = 0; s < m; s++) acc += (double)X[s * ldx + k];
+    out[k] = acc / (double)m;
+}
+
+// centre of ALREADY pushed node-major profiles: mean over the first m columns, zero on the leaves
+__global__ void center_of_pushed_kernel(const double *__restrict__ P64T, int64_t ldp64, int64_t m, int32_t n,
+                                        const uint8_t *__restrict__ has_child, double *__restrict__ out)
+{
+    int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double acc = 0.0;
+    if (has_child[k]) {
+        for (int64_t s = 0; s < m; s++) acc += P64T[(int64_t)k * ldp64 + s];
+        acc /= (double)m;
+    }
+    out[k] = acc;
+}
+
+__global__ void mask_leaves_kernel(double *__restrict__ center, const uint8_t *__restrict__ has_child, int32_t n)
+{
+    int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && !has_child[k]) center[k] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,12 +250,31 @@ __global__ void pushup_exact_kernel(double *__restrict__ PT, int64_t ldp, int64_
     }
 }
 
-__global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, int64_t ld_src,
-                                  int64_t ld_dst, int64_t col0, int64_t N, int32_t n)
+// Non-DFS fallback: double node-major result -> centred float + error statistic (one thread per sample).
+template <int MODE>
+__global__ void f64_to_f32_kernel(const double *__restrict__ src, const double *__restrict__ center,
+                                  float *__restrict__ dst, int64_t ld_src, int64_t ld_dst, int64_t col0, int64_t N,
+                                  int32_t n, double *__restrict__ err_stat)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    double err = 0.0;
+    for (int32_t k = 0; k < n; k++) {
+        const double c = src[(int64_t)k * ld_src + s] - (center ? center[k] : 0.0);
+        const float f = (float)c;
+        dst[(int64_t)k * ld_dst + col0 + s] = f;
+        const double e = c - (double)f;
+        err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
+    }
+    if (err_stat) err_stat[col0 + s] = err;
+}
+
+__global__ void copy_cols_f64_kernel(const double *__restrict__ src, int64_t ld_src, double *__restrict__ dst,
+                                     int64_t ld_dst, int64_t col0, int64_t N, int32_t n)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int32_t k = blockIdx.y;
-    if (s < N && k < n) dst[(int64_t)k * ld_dst + col0 + s] = (float)src[(int64_t)k * ld_src + s];
+    if (s < N && k < n) dst[(int64_t)k * ld_dst + col0 + s] = src[(int64_t)k * ld_src + s];
 }
 
 int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int mode, double *P64T, int64_t ldp,
@@ -201,8 +291,9 @@ int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int
     return FUF_OK;
 }
 
-int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, float *PT, int64_t ldp,
-                int64_t col0, cudaStream_t stream)
+int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, const double *center,
+                float *PT, int64_t ldp, double *P64T, int64_t ldp64, double *err_stat, int64_t col0,
+                cudaStream_t stream)
 {
     if (N == 0) return FUF_OK;
     const int32_t n = ctx->n;
@@ -215,20 +306,41 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
         double *tmp = (double *)ctx->ws_push.ptr;
         rc = push_up_f64_exact(ctx, (const double *)X, N, ldx, mode, tmp, N, 0, stream);
         if (rc) return rc;
-        dim3 g((unsigned)((N + 255) / 256), n);
-        f64_to_f32_kernel<<<g, 256, 0, stream>>>(tmp, PT, N, ldp, col0, N, n);
-        FUF_CUDA(cudaGetLastError());
-        ctx->launches += 1;
+        if (PT) {
+            const unsigned g = (unsigned)((N + 127) / 128);
+            if (mode == FUF_MODE_L1)
+                f64_to_f32_kernel<FUF_MODE_L1><<<g, 128, 0, stream>>>(tmp, center, PT, N, ldp, col0, N, n, err_stat);
+            else
+                f64_to_f32_kernel<FUF_MODE_L2><<<g, 128, 0, stream>>>(tmp, center, PT, N, ldp, col0, N, n, err_stat);
+            FUF_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+        }
+        if (P64T) {
+            dim3 g((unsigned)((N + 255) / 256), n);
+            copy_cols_f64_kernel<<<g, 256, 0, stream>>>(tmp, N, P64T, ldp64, col0, N, n);
+            FUF_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+        }
         return FUF_OK;
     }
     const int64_t ldt = (N + 31) / 32 * 32;
-    double *T = nullptr, *CP = nullptr;
-    if (ctx->n_span > 0) {
-        size_t need = ((size_t)ctx->n_chunks + (size_t)ctx->n_cp) * (size_t)ldt * sizeof(double);
-        int rc = ctx->ws_push.reserve(need);
-        if (rc) return rc;
-        T = (double *)ctx->ws_push.ptr;
-        CP = T + (size_t)ctx->n_chunks * ldt;
+    const bool want_err = (err_stat != nullptr && PT != nullptr);
+    double *T = nullptr, *CP = nullptr, *R = nullptr;
+    {
+        size_t need = 0;
+        if (ctx->n_span > 0) need += ((size_t)ctx->n_chunks + (size_t)ctx->n_cp) * (size_t)ldt * sizeof(double);
+        if (want_err) need += (size_t)ctx->n_chunks * (size_t)ldt * sizeof(double);
+        if (need) {
+            int rc = ctx->ws_push.reserve(need);
+            if (rc) return rc;
+            double *base = (double *)ctx->ws_push.ptr;
+            if (ctx->n_span > 0) {
+                T = base;
+                CP = T + (size_t)ctx->n_chunks * ldt;
+                base = CP + (size_t)ctx->n_cp * ldt;
+            }
+            if (want_err) R = base;
+        }
     }
     FUF_REQUIRE((N + TI - 1) / TI <= 65535, "fuf_push_up: N = %lld too large for one call (max %d)", (long long)N,
                 65535 * TI);
@@ -237,31 +349,65 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
     const size_t smem_d = sizeof(double) * KT * TI + sizeof(double) * KT * (TI + 1);
     static bool attr_set = false;
     if (!attr_set) {
-        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_f));
-        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem_d));
+        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
         attr_set = true;
     }
-    if (x_dtype == FUF_F32)
-        pushup_chunk_kernel<float><<<grid, TI, smem_f, stream>>>((const float *)X, ldx, N, n, ctx->d_w[mode],
-                                                            ctx->d_parent_local, ctx->d_cp_after, ctx->d_is_span, PT,
-                                                            ldp, col0, T, CP, ldt);
-    else
-        pushup_chunk_kernel<double><<<grid, TI, smem_d, stream>>>((const double *)X, ldx, N, n, ctx->d_w[mode],
-                                                             ctx->d_parent_local, ctx->d_cp_after, ctx->d_is_span, PT,
-                                                             ldp, col0, T, CP, ldt);
+#define FUF_CHUNK(TX, MODE_, SMEM)                                                                                  \
+    pushup_chunk_kernel<TX, MODE_><<<grid, TI, SMEM, stream>>>((const TX *)X, ldx, N, n, ctx->d_w[mode],            \
+                                                              ctx->d_parent_local, ctx->d_cp_after, ctx->d_is_span, \
+                                                              center, PT, ldp, P64T, ldp64, col0, T, CP, R, ldt)
+    if (x_dtype == FUF_F32) {
+        if (mode == FUF_MODE_L1) FUF_CHUNK(float, 0, smem_f); else FUF_CHUNK(float, 1, smem_f);
+    } else {
+        if (mode == FUF_MODE_L1) FUF_CHUNK(double, 0, smem_d); else FUF_CHUNK(double, 1, smem_d);
+    }
+#undef FUF_CHUNK
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    if (ctx->n_span > 0) {
-        pushup_scan_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(T, ctx->n_chunks, N, ldt);
+    if (want_err) {
+        pushup_stat_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(R, ctx->n_chunks, N, ldt, err_stat, col0);
         FUF_CUDA(cudaGetLastError());
-        dim3 g2((unsigned)((N + 127) / 128), (unsigned)min(ctx->n_span, 1024));
-        pushup_span_kernel<<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], T, CP, ldt, N, PT, ldp,
-                                                   col0);
-        FUF_CUDA(cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches += 1;
     }
+    if (ctx->n_span > 0) {
+        dim3 g2((unsigned)((N + 127) / 128), (unsigned)min(ctx->n_span, 64));
+        if (mode == FUF_MODE_L1)
+            pushup_span_kernel<FUF_MODE_L1><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
+                                                                    ldt, N, PT, ldp, P64T, ldp64, col0,
+                                                                    want_err ? err_stat : nullptr);
+        else
+            pushup_span_kernel<FUF_MODE_L2><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
+                                                                    ldt, N, PT, ldp, P64T, ldp64, col0,
+                                                                    want_err ? err_stat : nullptr);
+        FUF_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return FUF_OK;
+}
+
+// centre = pushed column mean of the first m rows, zero on the leaves (see the header comment)
+int push_up_center(fuf_ctx *ctx, const void *X, int x_dtype, int64_t m, int64_t ldx, int mode, double *center_out,
+                   cudaStream_t stream)
+{
+    const int32_t n = ctx->n;
+    int rc = ctx->ws_center.reserve((size_t)n * sizeof(double));
+    if (rc) return rc;
+    double *mean = (double *)ctx->ws_center.ptr;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (x_dtype == FUF_F32)
+        column_mean_kernel<float><<<g, 256, 0, stream>>>((const float *)X, ldx, m, n, mean);
+    else
+        column_mean_kernel<double><<<g, 256, 0, stream>>>((const double *)X, ldx, m, n, mean);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    rc = push_up_f32(ctx, mean, FUF_F64, 1, n, mode, nullptr, nullptr, 0, center_out, 1, nullptr, 0, stream);
+    if (rc) return rc;
+    mask_leaves_kernel<<<g, 256, 0, stream>>>(center_out, ctx->d_has_child, n);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return FUF_OK;
 }
 
@@ -269,17 +415,69 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
 
 using namespace fuf;
 
-extern "C" int fuf_push_up(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, float *PT,
-                           int64_t ldp, int64_t col0, void *stream)
+extern "C" int fuf_push_up(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode,
+                           const double *center, float *PT, int64_t ldp, double *P64T, int64_t ldp64,
+                           double *err_stat, int64_t col0, void *stream)
 {
-    FUF_REQUIRE(ctx && X && PT, "fuf_push_up: null argument");
+    FUF_REQUIRE(ctx && X && (PT || P64T), "fuf_push_up: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_push_up: bad mode %d", mode);
     FUF_REQUIRE(x_dtype == FUF_F32 || x_dtype == FUF_F64, "fuf_push_up: bad x_dtype %d", x_dtype);
-    FUF_REQUIRE(N >= 0 && ldx >= ctx->n && col0 >= 0 && col0 + N <= ldp,
-                "fuf_push_up: bad shape N=%lld ldx=%lld ldp=%lld col0=%lld n=%d", (long long)N, (long long)ldx,
-                (long long)ldp, (long long)col0, ctx->n);
+    FUF_REQUIRE(N >= 0 && ldx >= ctx->n && col0 >= 0 && (!PT || col0 + N <= ldp) && (!P64T || col0 + N <= ldp64),
+                "fuf_push_up: bad shape N=%lld ldx=%lld ldp=%lld ldp64=%lld col0=%lld n=%d", (long long)N,
+                (long long)ldx, (long long)ldp, (long long)ldp64, (long long)col0, ctx->n);
     FUF_CUDA(cudaSetDevice(ctx->device));
-    return push_up_f32(ctx, X, x_dtype, N, ldx, mode, PT, ldp, col0, (cudaStream_t)stream);
+    return push_up_f32(ctx, X, x_dtype, N, ldx, mode, center, PT, ldp, P64T, ldp64, err_stat, col0,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int fuf_push_up_center(fuf_ctx *ctx, const void *X, int x_dtype, int64_t m, int64_t ldx, int mode,
+                                  double *center_out, void *stream)
+{
+    FUF_REQUIRE(ctx && X && center_out, "fuf_push_up_center: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_push_up_center: bad mode %d", mode);
+    FUF_REQUIRE(x_dtype == FUF_F32 || x_dtype == FUF_F64, "fuf_push_up_center: bad x_dtype %d", x_dtype);
+    FUF_REQUIRE(m >= 1 && ldx >= ctx->n, "fuf_push_up_center: bad shape m=%lld ldx=%lld", (long long)m, (long long)ldx);
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->contiguous) {  // hand-built non-DFS order: no centring (the exact fallback handles it)
+        FUF_CUDA(cudaMemsetAsync(center_out, 0, (size_t)ctx->n * sizeof(double), (cudaStream_t)stream));
+        return FUF_OK;
+    }
+    return push_up_center(ctx, X, x_dtype, m, ldx, mode, center_out, (cudaStream_t)stream);
+}
+
+extern "C" int fuf_center_of_pushed(fuf_ctx *ctx, const double *P64T, int64_t m, int64_t ldp64, double *center_out,
+                                    void *stream)
+{
+    FUF_REQUIRE(ctx && P64T && center_out, "fuf_center_of_pushed: null argument");
+    FUF_REQUIRE(m >= 1 && ldp64 >= m, "fuf_center_of_pushed: bad shape m=%lld ldp64=%lld", (long long)m, (long long)ldp64);
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    center_of_pushed_kernel<<<(unsigned)((ctx->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        P64T, ldp64, m, ctx->n, ctx->d_has_child, center_out);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+extern "C" int fuf_round_pushed(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int mode,
+                                const double *center, float *PT, int64_t ldp, double *err_stat, int64_t col0,
+                                void *stream)
+{
+    FUF_REQUIRE(ctx && P64T && PT, "fuf_round_pushed: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_round_pushed: bad mode %d", mode);
+    FUF_REQUIRE(N >= 0 && col0 >= 0 && col0 + N <= ldp && col0 + N <= ldp64, "fuf_round_pushed: bad shape");
+    if (N == 0) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    const unsigned g = (unsigned)((N + 127) / 128);
+    // source and destination use the same column offset
+    if (mode == FUF_MODE_L1)
+        f64_to_f32_kernel<FUF_MODE_L1><<<g, 128, 0, (cudaStream_t)stream>>>(P64T + col0, center, PT, ldp64, ldp, col0, N,
+                                                                           ctx->n, err_stat);
+    else
+        f64_to_f32_kernel<FUF_MODE_L2><<<g, 128, 0, (cudaStream_t)stream>>>(P64T + col0, center, PT, ldp64, ldp, col0, N,
+                                                                           ctx->n, err_stat);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
 }
 
 extern "C" int fuf_push_up_f64(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int mode, double *P64T,

@@ -1,0 +1,194 @@
+// refine.cu — float64 refinement of the pairs the fp32 production path cannot certify to 1e-6 relative.
+//
+// The production kernel (pairwise.cu) evaluates get_L1 / get_L2 (src/objects/profile_vector.py:9-19) on pushed
+// profiles that were rounded to fp32.  For a pair (i, j) that rounding perturbs the distance by at most
+//     L1:  rho_i + rho_j                      rho_s = sum_k |P_s[k] - fl32(P_s[k])|      (triangle inequality)
+//     L2:  2 sqrt(D) (r_i + r_j) + (r_i+r_j)^2   r_s  = sqrt(sum_k (P_s[k] - fl32(P_s[k]))^2)  (Cauchy-Schwarz)
+// (rho, r^2 are the per-sample statistics the push-up kernel emits).  The bound is only a problem for
+// near-duplicate samples, whose distance is tiny compared with their mass.  K6 refine_kernel scans the distance
+// matrix once, and wherever the bound exceeds 0.5e-6 of the computed distance,
+//     L1:  D < kappa (rho_i + rho_j),   kappa = 2e6        L2:  D < kappa (r_i + r_j)^2,   kappa = 1.6e13
+// it recomputes the pair from the float64 pushed profiles P64T (sum over all n entries in double) and overwrites
+// D[i,j] (and D[j,i]).  Cost: one pass over the upper triangle of D plus ~2 n sector reads per refined pair.
+#include "common.cuh"
+
+namespace fuf {
+
+constexpr int RSEG = 256;  // columns of one row a warp examines per work item
+
+struct RefineParams {
+    const double *P64T;
+    int64_t ldp64, shard, shard_stride;
+    int32_t n;
+    int64_t N;
+    const double *stat;
+    double kappa;
+    const int32_t *tile_rows;  // nullptr: full matrix; else compact row blocks
+    int32_t n_rows_total;      // rows to scan (N, or n_tile_rows * 128)
+    double *D;
+    int64_t ldd;
+    double *D2;                // optional second destination (zero-copy host mirror), write-only
+    int64_t ldd2;
+    int mirror;                // also write D[j,i]
+    unsigned long long *counter;
+};
+
+__device__ __forceinline__ const double *col_ptr(const RefineParams &p, int64_t s)
+{
+    if (p.shard == 0) return p.P64T + s;
+    return p.P64T + (s / p.shard) * p.shard_stride + (s % p.shard);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+refine_kernel(const RefineParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t segs_per_row = (p.N + RSEG - 1) / RSEG;
+    const int64_t n_items = (int64_t)p.n_rows_total * segs_per_row;
+    const int64_t kstride = p.shard == 0 ? p.ldp64 : p.shard;
+    unsigned long long refined = 0;
+    for (int64_t item = warp; item < n_items; item += n_warps) {
+        const int64_t row = item / segs_per_row, seg = item % segs_per_row;
+        int64_t gi = row;
+        if (p.tile_rows) {
+            const int32_t t = p.tile_rows[row / FUF_TILE];
+            if (t < 0) continue;
+            gi = (int64_t)t * FUF_TILE + row % FUF_TILE;
+        }
+        if (gi >= p.N) continue;
+        const int64_t j0 = seg * RSEG;
+        if (j0 + RSEG <= gi + 1) continue;  // entirely on or below the diagonal
+        const double si = MODE == FUF_MODE_L2 ? sqrt(p.stat[gi]) : p.stat[gi];
+        double *drow = p.D + row * p.ldd;
+#pragma unroll 1
+        for (int u = 0; u < RSEG / 32; u++) {
+            const int64_t gj = j0 + u * 32 + lane;
+            bool flag = false;
+            if (gj > gi && gj < p.N) {
+                const double d = drow[gj];
+                const double sj = MODE == FUF_MODE_L2 ? sqrt(p.stat[gj]) : p.stat[gj];
+                const double b = si + sj;
+                flag = MODE == FUF_MODE_L2 ? !(d >= p.kappa * b * b) : !(d >= p.kappa * b);
+                if (b == 0.0) flag = false;  // both samples exactly representable in fp32: nothing to gain
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, flag);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int64_t j = j0 + u * 32 + src;
+                const double *a = col_ptr(p, gi), *b = col_ptr(p, j);
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                int32_t k = lane;
+                for (; k + 96 < p.n; k += 128) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double x = a[(int64_t)(k + 32 * q) * kstride], y = b[(int64_t)(k + 32 * q) * kstride];
+                        const double d = fabs(__dsub_rn(x, y));
+                        acc[q] = __dadd_rn(acc[q], MODE == FUF_MODE_L2 ? __dmul_rn(d, d) : d);
+                    }
+                }
+                for (; k < p.n; k += 32) {
+                    const double d = fabs(__dsub_rn(a[(int64_t)k * kstride], b[(int64_t)k * kstride]));
+                    acc[0] = __dadd_rn(acc[0], MODE == FUF_MODE_L2 ? __dmul_rn(d, d) : d);
+                }
+                double v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) {
+                    drow[j] = v;
+                    if (p.mirror) p.D[j * p.ldd + gi] = v;
+                    if (p.D2) {
+                        p.D2[row * p.ldd2 + j] = v;
+                        if (p.mirror) p.D2[j * p.ldd2 + gi] = v;
+                    }
+                    refined++;
+                }
+            }
+        }
+    }
+    if (lane == 0 && refined) atomicAdd(p.counter, refined);
+}
+
+int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
+           const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
+           int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2)
+{
+    if (N < 2) return FUF_OK;
+    if (!ctx->d_refined) FUF_CUDA(cudaMalloc((void **)&ctx->d_refined, sizeof(unsigned long long)));
+    FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
+    RefineParams p;
+    p.P64T = P64T;
+    p.ldp64 = ldp64;
+    p.shard = shard;
+    p.shard_stride = shard_stride;
+    p.n = ctx->n;
+    p.N = N;
+    p.stat = err_stat;
+    p.kappa = kappa > 0 ? kappa : (mode == FUF_MODE_L2 ? 1.6e13 : 2e6);
+    p.D = D;
+    p.ldd = ldd;
+    p.D2 = D2;
+    p.ldd2 = ldd2;
+    p.counter = ctx->d_refined;
+    if (tile_rows_h) {
+        if (n_tile_rows == 0) return FUF_OK;
+        int rc = ctx->ws_rows.reserve((size_t)n_tile_rows * sizeof(int32_t));
+        if (rc) return rc;
+        FUF_CUDA(cudaMemcpyAsync(ctx->ws_rows.ptr, tile_rows_h, (size_t)n_tile_rows * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, stream));
+        FUF_CUDA(cudaStreamSynchronize(stream));  // tile_rows_h may be pageable and short-lived
+        p.tile_rows = (const int32_t *)ctx->ws_rows.ptr;
+        p.n_rows_total = n_tile_rows * FUF_TILE;
+        p.mirror = 0;
+    } else {
+        p.tile_rows = nullptr;
+        p.n_rows_total = (int32_t)N;
+        p.mirror = 1;
+    }
+    const int grid = ctx->sm_count * 8;
+    if (mode == FUF_MODE_L1)
+        refine_kernel<FUF_MODE_L1><<<grid, 256, 0, stream>>>(p);
+    else
+        refine_kernel<FUF_MODE_L2><<<grid, 256, 0, stream>>>(p);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+}  // namespace fuf
+
+using namespace fuf;
+
+extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard,
+                          int64_t shard_stride, int mode, const double *err_stat, double kappa,
+                          const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream)
+{
+    FUF_REQUIRE(ctx && P64T && err_stat && D, "fuf_refine: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_refine: bad mode %d", mode);
+    FUF_REQUIRE(N >= 0 && ldd >= N && N < ((int64_t)1 << 31), "fuf_refine: bad shape N=%lld ldd=%lld", (long long)N,
+                (long long)ldd);
+    FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_refine: n_tile_rows without tile_rows_h");
+    if (shard == 0)
+        FUF_REQUIRE(ldp64 >= N, "fuf_refine: ldp64=%lld < N=%lld", (long long)ldp64, (long long)N);
+    else
+        FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
+                  (cudaStream_t)stream, nullptr, 0);
+}
+
+extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)
+{
+    FUF_REQUIRE(ctx && refined, "fuf_refine_count: null argument");
+    *refined = 0;
+    if (!ctx->d_refined) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long v = 0;
+    FUF_CUDA(cudaMemcpyAsync(&v, ctx->d_refined, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FUF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *refined = (int64_t)v;
+    return FUF_OK;
+}

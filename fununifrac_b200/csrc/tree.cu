@@ -92,7 +92,7 @@ static int upload(T **dst, const std::vector<T> &src)
 // test hook fuf_debug_tree_plan.
 struct TreePlan {
     std::vector<int32_t> start, parent_local, cp_after;
-    std::vector<uint8_t> is_span;
+    std::vector<uint8_t> is_span, has_child;
     std::vector<SpanNode> span;
     int32_t n_leaves = 0, depth = 0, n_cp = 0;
     bool contiguous = true;
@@ -109,6 +109,7 @@ static void build_tree_plan(const int32_t *parent_h, int32_t n, TreePlan &plan)
     }
     for (int32_t i = n - 2; i >= 0; i--) depth[i] = depth[parent_h[i]] + 1;
     plan.start.resize(n);
+    plan.has_child = has_child;
     for (int32_t i = 0; i < n; i++) {
         plan.start[i] = i - size[i] + 1;
         if (!has_child[i]) plan.n_leaves++;
@@ -275,7 +276,7 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
     if ((rc = upload(&ctx->d_parent, ctx->parent)) || (rc = upload(&ctx->d_w[0], ctx->w[0])) ||
         (rc = upload(&ctx->d_w[1], ctx->w[1])) || (rc = upload(&ctx->d_parent_local, parent_local)) ||
         (rc = upload(&ctx->d_cp_after, cp_after)) || (rc = upload(&ctx->d_is_span, is_span)) ||
-        (rc = upload(&ctx->d_span, span))) {
+        (rc = upload(&ctx->d_span, span)) || (rc = upload(&ctx->d_has_child, plan.has_child))) {
         fuf_tree_destroy(ctx);
         return rc;
     }
@@ -306,6 +307,11 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     cudaFree(ctx->d_cp_after);
     cudaFree(ctx->d_is_span);
     cudaFree(ctx->d_span);
+    cudaFree(ctx->d_has_child);
+    cudaFree(ctx->d_refined);
+    ctx->ws_center.release();
+    ctx->ws_rows.release();
+    ctx->ws_p64.release();
     ctx->ws_push.release();
     ctx->ws_pair.release();
     ctx->ws_x.release();

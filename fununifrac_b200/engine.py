@@ -20,6 +20,9 @@ MODE_L1, MODE_L2 = 0, 1
 F32, F64 = 0, 1
 TILE = 128
 PW_SCALAR_MATH = 1
+AP_VALIDATE, AP_NO_REFINE = 1, 2
+CENTER_SAMPLES = 32
+ABI_VERSION = 2
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -54,7 +57,12 @@ def load_library() -> ctypes.CDLL:
         L.fuf_tree_create.argtypes = [ctypes.POINTER(vp), ci, vp, vp, i32]
         L.fuf_tree_destroy.argtypes = [vp]
         L.fuf_tree_get_info.argtypes = [vp, ctypes.POINTER(TreeInfo)]
-        L.fuf_push_up.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, i64, vp]
+        L.fuf_push_up.argtypes = [vp, vp, ci, i64, i64, ci, vp, vp, i64, vp, i64, vp, i64, vp]
+        L.fuf_push_up_center.argtypes = [vp, vp, ci, i64, i64, ci, vp, vp]
+        L.fuf_center_of_pushed.argtypes = [vp, vp, i64, i64, vp, vp]
+        L.fuf_round_pushed.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64, vp, i64, vp]
+        L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, vp, i32, vp, i64, vp]
+        L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
@@ -67,9 +75,13 @@ def load_library() -> ctypes.CDLL:
         L.fuf_launch_count.argtypes = [vp]
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
+                     "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci
+        if L.fuf_version() != ABI_VERSION:
+            raise FunUniFracError(f"{LIB_PATH} has ABI version {L.fuf_version()}, this package needs {ABI_VERSION}: "
+                                  f"rebuild it (make -C fununifrac_b200/csrc)")
         _lib = L
         return L
 
@@ -152,17 +164,90 @@ class TreeContext:
         ldp = padded_samples(N) if ldp is None else ldp
         return torch.zeros((self.n, ldp), dtype=dtype or torch.float32, device=f"cuda:{self.device}")
 
-    def push_up(self, X, mode: int, PT=None, col0: int = 0):
-        """X: device tensor [N, ldx>=n] float32/float64, sample-major → PT float32 [n, ldp] (columns col0..col0+N)."""
+    def push_up_center(self, X, mode: int, m: Optional[int] = None):
+        """Centre of a job (``fuf_push_up_center``): pushed mean of the first ``m`` rows of X, zero on leaves."""
+        torch = _torch()
+        m = min(int(X.shape[0]), CENTER_SAMPLES) if m is None else int(m)
+        center = torch.zeros(self.n, dtype=torch.float64, device=X.device)
+        if m > 0:
+            _check(self._lib.fuf_push_up_center(self.handle, X.data_ptr(), _dtype_code(X), m, X.stride(0), mode,
+                                                center.data_ptr(), _stream_ptr(torch)), "fuf_push_up_center")
+        return center
+
+    def push_up(self, X, mode: int, PT=None, col0: int = 0, center=None, P64T=None, err_stat=None):
+        """X: device tensor [N, ldx>=n] float32/float64, sample-major → PT float32 [n, ldp] (columns col0..col0+N),
+        centred on ``center`` when given; optionally also P64T (float64, uncentred) and the per-sample
+        rounding-error statistic ``err_stat`` (see ``fuf_push_up``)."""
         torch = _torch()
         N = int(X.shape[0])
         assert X.dim() == 2 and X.stride(1) == 1 and X.shape[1] >= self.n
         if PT is None:
             PT = self.new_profile_buffer(N + col0)
         assert PT.dtype == torch.float32 and PT.stride(1) == 1
-        _check(self._lib.fuf_push_up(self.handle, X.data_ptr(), _dtype_code(X), N, X.stride(0), mode, PT.data_ptr(),
-                                     PT.stride(0), col0, _stream_ptr(torch)), "fuf_push_up")
+        assert center is None or (center.dtype == torch.float64 and center.numel() >= self.n)
+        assert P64T is None or (P64T.dtype == torch.float64 and P64T.stride(1) == 1)
+        assert err_stat is None or (err_stat.dtype == torch.float64 and err_stat.numel() >= col0 + N)
+        _check(self._lib.fuf_push_up(self.handle, X.data_ptr(), _dtype_code(X), N, X.stride(0), mode,
+                                     None if center is None else center.data_ptr(), PT.data_ptr(), PT.stride(0),
+                                     None if P64T is None else P64T.data_ptr(),
+                                     0 if P64T is None else P64T.stride(0),
+                                     None if err_stat is None else err_stat.data_ptr(), col0, _stream_ptr(torch)),
+               "fuf_push_up")
         return PT
+
+    def push_up_job(self, X, mode: int, refine: bool = True) -> "Pushed":
+        """The production push-up of a whole job: centre from the first samples, centred fp32 profiles, and
+        (``refine``) the float64 profiles + error statistics the refinement pass needs."""
+        job = Pushed(self, int(X.shape[0]), refine)
+        if job.N:
+            job.center = self.push_up_center(X, mode)
+            self.push_up(X, mode, job.PT, 0, job.center, job.P64T, job.err_stat)
+        return job
+
+    def round_pushed(self, P64T, N: int, mode: int, refine: bool = True) -> "Pushed":
+        """Same as ``push_up_job`` for profiles that are already pushed (node-major float64 P64T)."""
+        torch = _torch()
+        job = Pushed(self, N, False)
+        if N:
+            job.center = torch.zeros(self.n, dtype=torch.float64, device=P64T.device)
+            st = _stream_ptr(torch)
+            _check(self._lib.fuf_center_of_pushed(self.handle, P64T.data_ptr(), min(N, CENTER_SAMPLES), P64T.stride(0),
+                                                  job.center.data_ptr(), st), "fuf_center_of_pushed")
+            _check(self._lib.fuf_round_pushed(self.handle, P64T.data_ptr(), N, P64T.stride(0), mode,
+                                              job.center.data_ptr(), job.PT.data_ptr(), job.PT.stride(0),
+                                              job.err_stat.data_ptr(), 0, st), "fuf_round_pushed")
+        if refine:
+            job.P64T = P64T
+        return job
+
+    def distances(self, job: "Pushed", mode: int, D=None):
+        """Full symmetric D of a pushed job: fp32 tile kernel, then the float64 refinement pass when the job
+        carries float64 profiles."""
+        D = self.pairwise(job.PT, job.N, mode, D=D)
+        if job.P64T is not None and job.N > 1:
+            self.refine(job.P64T, job.N, mode, job.err_stat, D)
+        return D
+
+    def refine(self, P64T, N: int, mode: int, err_stat, D, tile_rows: Optional[Sequence[int]] = None,
+               shard: int = 0, shard_stride: int = 0, kappa: float = 0.0):
+        """``fuf_refine``: recompute in float64 the pairs of D the fp32 operands cannot certify (in place)."""
+        torch = _torch()
+        assert P64T.dtype == torch.float64 and err_stat.dtype == torch.float64 and D.dtype == torch.float64
+        rows_arr = None if tile_rows is None else np.ascontiguousarray(tile_rows, dtype=np.int32)
+        ldp = P64T.stride(0) if shard == 0 else 0
+        _check(self._lib.fuf_refine(self.handle, P64T.data_ptr(), N, ldp, shard, shard_stride, mode,
+                                    err_stat.data_ptr(), float(kappa),
+                                    rows_arr.ctypes.data if rows_arr is not None else None,
+                                    0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),
+                                    _stream_ptr(torch)), "fuf_refine")
+        return D
+
+    def refine_count(self) -> int:
+        """Pairs recomputed by the last refinement (synchronises the current stream)."""
+        torch = _torch()
+        v = ctypes.c_int64()
+        _check(self._lib.fuf_refine_count(self.handle, ctypes.byref(v), _stream_ptr(torch)), "fuf_refine_count")
+        return int(v.value)
 
     def push_up_f64(self, X, mode: int, P64T=None, col0: int = 0):
         """Validation path: X float64 [N, ldx] → P64T float64 [n, ldp], reference operation order."""
@@ -246,22 +331,25 @@ class TreeContext:
         return out
 
     # -- host-buffer entry point ------------------------------------------------------------------
-    def all_pairs_host(self, X: np.ndarray, mode: int, D: Optional[np.ndarray] = None, validate: bool = False
-                       ) -> np.ndarray:
+    def all_pairs_host(self, X: np.ndarray, mode: int, D: Optional[np.ndarray] = None, validate: bool = False,
+                       refine: bool = True) -> np.ndarray:
         """``fuf_all_pairs_host``: host profiles X[N, n] (float32/float64, C-order) → host D[N, N] float64."""
         _torch()
         if X.dtype not in (np.float32, np.float64):
             X = X.astype(np.float64)
-        if X.ndim != 2 or X.shape[1] < self.n or X.strides[1] != X.itemsize:
+        if X.ndim != 2 or X.shape[1] < self.n or (X.shape[0] > 0 and X.strides[1] != X.itemsize):
             raise ValueError(f"X must be a C-ordered [N, >={self.n}] array")
         N = X.shape[0]
+        if N == 0:
+            return np.zeros((0, 0), dtype=np.float64) if D is None else D
         if D is None:
             D = np.zeros((N, N), dtype=np.float64)
         if D.dtype != np.float64 or D.shape != (N, N) or D.strides[1] != 8:
             raise ValueError("D must be a C-ordered float64 [N, N] array")
         _check(self._lib.fuf_all_pairs_host(self.handle, X.ctypes.data, F32 if X.dtype == np.float32 else F64, N,
                                             X.strides[0] // X.itemsize, mode, D.ctypes.data, D.strides[0] // 8,
-                                            int(validate)), "fuf_all_pairs_host")
+                                            (AP_VALIDATE if validate else 0) | (0 if refine else AP_NO_REFINE)),
+               "fuf_all_pairs_host")
         return D
 
     def last_timing(self) -> Tuple[float, float, float]:
@@ -269,6 +357,19 @@ class TreeContext:
         _check(self._lib.fuf_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
                "fuf_last_timing")
         return a.value, b.value, c.value
+
+
+class Pushed:
+    """Device buffers of one pushed job: centred fp32 profiles ``PT`` [n, ldp], and for the refinement pass the
+    float64 profiles ``P64T`` [n, ldp] and per-sample rounding-error statistics ``err_stat`` [ldp]."""
+
+    def __init__(self, ctx: TreeContext, N: int, refine: bool = True):
+        torch = _torch()
+        self.N = N
+        self.PT = ctx.new_profile_buffer(N)
+        self.err_stat = torch.zeros(self.PT.shape[1], dtype=torch.float64, device=self.PT.device)
+        self.P64T = ctx.new_profile_buffer(N, dtype=torch.float64) if refine else None
+        self.center = None
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,151 @@
+"""Multi-GPU all-pairs: one process per GPU, samples and tile rows sharded, two exchanges per job.
+
+The distance matrix has no cross-pair dependence (every ``dists[i, j]`` of the reference loop,
+``src/algorithms/emd_unifrac.py:49-54``, needs only rows i and j of the pushed profiles), so the job shards
+without any collective inside the kernels:
+
+1. rank r pushes up its own block of ``shard`` samples              (``fuf_push_up``  → ``[n, shard]`` node-major)
+2. one all-gather of the pushed blocks over NCCL / NVLink            (→ ``[G, n, shard]``, the layout ``fuf_pairwise``
+   reads directly through its ``shard`` / ``shard_stride`` arguments)
+3. rank r computes the 128-row tile rows it owns, upper triangle    (``fuf_pairwise`` with ``tile_rows``)
+4. one gather of the compact row blocks to rank 0, which mirrors    (``fuf_assemble``)
+   them into the full symmetric matrix.
+
+The compute calls are injected (``ops``) so that the partition / exchange logic is testable on CPU with the
+``gloo`` backend; the product always injects ``engine.TreeContext`` (CUDA).  ``world == 1`` needs no process group.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+TILE = 128
+
+
+def shard_size(N: int, world: int) -> int:
+    """Samples per rank: ceil(N / world) rounded up to a multiple of the 128-sample tile."""
+    per = (N + world - 1) // world
+    return max(TILE, (per + TILE - 1) // TILE * TILE)
+
+
+def sample_range(N: int, world: int, rank: int):
+    s = shard_size(N, world)
+    return min(N, rank * s), min(N, (rank + 1) * s)
+
+
+def tile_row_owner(t: int, world: int) -> int:
+    """Boustrophedon deal of tile rows: row t of the upper triangle holds T - t tiles, so dealing
+    0,1,..,G-1,G-1,..,1,0,0,1,.. keeps every rank within one tile row of the mean tile count."""
+    q = t % (2 * world)
+    return q if q < world else 2 * world - 1 - q
+
+
+def owned_tile_rows(N: int, world: int, rank: int) -> List[int]:
+    T = (N + TILE - 1) // TILE
+    return [t for t in range(T) if tile_row_owner(t, world) == rank]
+
+
+def tiles_of(rows: Sequence[int], N: int) -> int:
+    T = (N + TILE - 1) // TILE
+    return sum(T - t for t in rows)
+
+
+class ShardedAllPairs:
+    """One rank's part of an all-pairs job over ``N`` samples.
+
+    ``ops`` provides ``n``, ``empty(shape, dtype)``, ``push_up_center``, ``push_up``, ``pairwise``, ``refine`` and
+    ``assemble`` with the semantics of the C ABI; ``dist`` is ``torch.distributed`` (None when world == 1).
+    ``refine=True`` also exchanges the float64 profiles and runs the float64 refinement pass on this rank's rows.
+    """
+
+    def __init__(self, ops, N: int, mode: int, world: int = 1, rank: int = 0, dist=None, refine: bool = True):
+        self.ops, self.N, self.mode, self.world, self.rank, self.dist = ops, N, mode, world, rank, dist
+        self.do_refine = refine
+        self.shard = shard_size(N, world)
+        self.lo, self.hi = sample_range(N, world, rank)
+        self.all_rows = [owned_tile_rows(N, world, r) for r in range(world)]
+        self.rows = self.all_rows[rank]
+        self.max_rows = max(len(r) for r in self.all_rows)
+        if world > 1 and dist is None:
+            raise ValueError("world > 1 needs a torch.distributed process group")
+        n = ops.n
+        self.PS = ops.empty((world, n, self.shard), "float32")          # pushed blocks of all ranks (zero-padded)
+        self.P64S = ops.empty((world, n, self.shard), "float64") if refine else None
+        self.stat = ops.empty((world * self.shard,), "float64")
+        self.center = ops.empty((n,), "float64")
+        self.D = ops.empty((N, N), "float64") if rank == 0 else None
+        self.blocks = self.gathered = None
+        if world > 1:
+            self.blocks = ops.empty((self.max_rows * TILE, N), "float64")
+            if rank == 0:   # one buffer, one slot of max_rows row blocks per rank (unused slots are skipped)
+                self.gathered = ops.empty((world, self.max_rows * TILE, N), "float64")
+                self.slot_rows = []
+                for r in range(world):
+                    self.slot_rows += self.all_rows[r] + [-1] * (self.max_rows - len(self.all_rows[r]))
+
+    def step(self, X_local, mark=None):
+        """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
+        ``mark(name)`` is called at the phase boundaries (bench.py records CUDA events there)."""
+        ops, N, mode, r, sh, n = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n
+        mark = mark or (lambda name: None)
+        stride = n * sh
+        mark("start")
+        if r == 0:
+            ops.push_up_center(X_local, mode, self.center)
+        if self.world > 1:
+            self.dist.broadcast(self.center, src=0)
+        mark("push_begin")
+        if self.hi > self.lo:
+            ops.push_up(X_local, mode, self.PS[r], 0, self.center, self.P64S[r] if self.do_refine else None,
+                        self.stat[r * sh:(r + 1) * sh])
+        mark("push_end")
+        if self.world == 1:
+            mark("pair_begin")
+            ops.pairwise(self.PS, N, mode, None, sh, stride, self.D)
+            mark("pair_end")
+            if self.do_refine:
+                ops.refine(self.P64S, N, mode, self.stat, self.D, None, sh, stride)
+            mark("end")
+            return self.D
+        self.dist.all_gather_into_tensor(self.PS.view(-1), self.PS[r].reshape(-1))
+        self.dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
+        if self.do_refine:
+            self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
+        mark("pair_begin")
+        if self.rows:
+            ops.pairwise(self.PS, N, mode, self.rows, sh, stride, self.blocks)
+        mark("pair_end")
+        if self.rows and self.do_refine:
+            ops.refine(self.P64S, N, mode, self.stat, self.blocks, self.rows, sh, stride)
+        self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
+        if r == 0:
+            ops.assemble(self.gathered, self.slot_rows, N, self.D)
+        mark("end")
+        return self.D
+
+
+class CudaOps:
+    """``ops`` over ``engine.TreeContext`` (the only implementation the product uses)."""
+
+    def __init__(self, ctx):
+        import torch
+
+        self.ctx, self.n, self.torch = ctx, ctx.n, torch
+        self.device = f"cuda:{ctx.device}"
+
+    def empty(self, shape, dtype):
+        return self.torch.zeros(shape, dtype=getattr(self.torch, dtype), device=self.device)
+
+    def push_up_center(self, X, mode, out):
+        out.copy_(self.ctx.push_up_center(X, mode))
+
+    def push_up(self, X, mode, PT, col0, center, P64T, err_stat):
+        return self.ctx.push_up(X, mode, PT, col0, center, P64T, err_stat)
+
+    def pairwise(self, PT, N, mode, tile_rows, shard, shard_stride, D):
+        return self.ctx.pairwise(PT, N, mode, D=D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)
+
+    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride):
+        return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)
+
+    def assemble(self, blocks, rows, N, D):
+        return self.ctx.assemble(blocks, rows, N, D=D)

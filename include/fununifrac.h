@@ -8,12 +8,16 @@
  *   fuf_tree_create      <- the arrays tree_to_EMDU_input builds        src/factory/make_emd_input.py:10-54
  *                           (Tint -> parent[], lint -> edge_length[], postorder, root last)
  *   fuf_push_up          <- push_up_L1 / push_up_L2 over all samples    src/algorithms/emd_unifrac.py:20-39
+ *   fuf_push_up_center   <- (no counterpart) the common vector subtracted from every pushed profile before it
+ *                           is rounded to fp32; distances are invariant under it
  *   fuf_push_up_f64      <- same, float64, reference operation order    src/algorithms/emd_unifrac.py:20-39
  *   fuf_load_pushed      <- the dict of pushed vectors handed to        src/algorithms/emd_unifrac.py:42
  *                           pairwise_computation (layout change only)
  *   fuf_pairwise         <- pairwise_computation (no diffab) =          src/algorithms/emd_unifrac.py:42-54
  *                           get_L1 / get_L2 over all i<j                src/objects/profile_vector.py:9-19
  *   fuf_pairwise_f64     <- same, float64 validation mode
+ *   fuf_refine           <- get_L1 / get_L2 in float64 for the pairs    src/objects/profile_vector.py:9-19
+ *                           the fp32 operands cannot certify to 1e-6
  *   fuf_assemble         <- dists[i,j] = dists[j,i] = Z                 src/algorithms/emd_unifrac.py:51-54
  *                           (joins row-block shards computed on several GPUs)
  *   fuf_diffab_block     <- get_L1_diffab / get_L2_diffab per pair in   src/objects/profile_vector.py:13-23
@@ -46,7 +50,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 1
+#define FUF_ABI_VERSION 2
 
 /* error codes */
 #define FUF_OK 0
@@ -62,6 +66,12 @@ extern "C" {
 /* dtypes for void* operands */
 #define FUF_F32 0
 #define FUF_F64 1
+
+/* fuf_all_pairs_host flags */
+#define FUF_AP_VALIDATE 1  /* float64 validation kernels instead of the fp32 production path */
+#define FUF_AP_NO_REFINE 2 /* production path without the float64 refinement pass */
+
+#define FUF_CENTER_SAMPLES 32 /* fuf_all_pairs_host centres on the pushed mean of the first min(N, 32) samples */
 
 /* fuf_pairwise flags */
 #define FUF_PW_SCALAR_MATH 1 /* use scalar FADD instead of packed FADD2/FFMA2 (A/B switch for profiling) */
@@ -94,12 +104,21 @@ int fuf_tree_get_info(const fuf_ctx *ctx, fuf_tree_info *info);
 /* Smallest legal ldp for N samples (N rounded up to a multiple of FUF_TILE). */
 int64_t fuf_padded_samples(int64_t N);
 
-/* Push-up, production path.  X (device, x_dtype, sample-major, leading dimension ldx >= n) holds N
- * samples; columns [col0, col0+N) of PT (device, float, ld ldp) receive
- *   PT[k][col0+s] = (float)( w_k * sum_{k' in subtree(k)} X[s][k'] ),  w = L (L1) or sqrt(L) (L2), w_root = 1.
- * Subtree sums are accumulated in double. */
-int fuf_push_up(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, float *PT, int64_t ldp,
-                int64_t col0, void *stream);
+/* Centre of a job: center_out (device, n doubles) = the pushed (mode weights) mean of the first m rows of X,
+ * set to zero on the leaves.  Every fuf_push_up call of one job must be given the same centre (on several
+ * GPUs: compute it on one rank and broadcast it).  Distances do not depend on it; accuracy does. */
+int fuf_push_up_center(fuf_ctx *ctx, const void *X, int x_dtype, int64_t m, int64_t ldx, int mode, double *center_out,
+                       void *stream);
+
+/* Push-up, production path.  X (device, x_dtype, sample-major, leading dimension ldx >= n) holds N samples.
+ * With S_k(s) = sum of X[s] over the subtree of k (accumulated in double), w = L (L1) or sqrt(L) (L2), w_root = 1:
+ *   PT   (device float, node-major, ld ldp; may be NULL):    PT[k][col0+s]   = (float)(w_k S_k(s) - center[k])
+ *   P64T (device double, node-major, ld ldp64; may be NULL): P64T[k][col0+s] = w_k S_k(s)
+ *   err_stat (device double, may be NULL): err_stat[col0+s] = sum_k |rounding error of PT[k][col0+s]|   (L1)
+ *                                                             sum_k (rounding error of PT[k][col0+s])^2 (L2)
+ * center: device, n doubles, or NULL for no centring. */
+int fuf_push_up(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, const double *center,
+                float *PT, int64_t ldp, double *P64T, int64_t ldp64, double *err_stat, int64_t col0, void *stream);
 
 /* Push-up, validation path: float64 in/out, additions in the reference's order (bit-identical to
  * push_up_L1 / push_up_L2 for finite inputs).  P64T: device double, node-major, ld ldp. */
@@ -110,6 +129,13 @@ int fuf_push_up_f64(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int m
  * P_rows (device, p_dtype, sample-major N x n, ld >= n) -> node-major PT of dtype out_dtype, columns [col0, col0+N). */
 int fuf_load_pushed(fuf_ctx *ctx, const void *P_rows, int p_dtype, int64_t N, int64_t ld, void *PT, int out_dtype,
                     int64_t ldp, int64_t col0, void *stream);
+
+/* The same centring / rounding for profiles that are ALREADY pushed (P64T from fuf_load_pushed with out_dtype
+ * FUF_F64): centre = mean of the first m columns on internal nodes, then PT = (float)(P64T - centre) and the
+ * per-sample rounding-error statistic (columns [col0, col0+N) of both buffers). */
+int fuf_center_of_pushed(fuf_ctx *ctx, const double *P64T, int64_t m, int64_t ldp64, double *center_out, void *stream);
+int fuf_round_pushed(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int mode, const double *center,
+                     float *PT, int64_t ldp, double *err_stat, int64_t col0, void *stream);
 
 /* All-pairs distances from pushed profiles.
  *   PT          device float, node-major.  The samples may be split in equal shards of `shard` columns
@@ -129,8 +155,20 @@ int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
 int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
                      void *stream);
 
+/* Float64 refinement of what fuf_pairwise wrote into D (same D / tile_rows_h / shard conventions; P64T laid out
+ * like PT): every pair i<j with
+ *     L1: D[i,j] < kappa (err_stat[i] + err_stat[j])          L2: D[i,j] < kappa (sqrt err_stat[i] + sqrt err_stat[j])^2
+ * is recomputed from P64T in double and overwritten (with its mirror when tile_rows_h == NULL).
+ * kappa <= 0 selects the default (2e6 / 1.6e13: rounding of the fp32 operands may cost at most 0.5e-6 relative).
+ * fuf_refine_count synchronises the stream and returns how many pairs the last fuf_refine recomputed. */
+int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
+               const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
+               int64_t ldd, void *stream);
+int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
+
 /* Join compact row blocks (as written by fuf_pairwise with tile_rows_h, possibly gathered from several
- * devices and concatenated: blocks[c] for c in [0, n_blocks)) into the full symmetric N x N matrix. */
+ * devices and concatenated: blocks[c] for c in [0, n_blocks)) into the full symmetric N x N matrix.
+ * tile_rows_h[c] == -1 marks a padding block that is skipped. */
 int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
                  int64_t ldb, double *D, int64_t ldd, void *stream);
 
@@ -144,11 +182,11 @@ int fuf_diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64
 /* Whole path with HOST buffers (the call a reference-side binding makes):
  *   X_h  host, x_dtype, sample-major N x n (ldx >= n), un-pushed normalised profiles;
  *   D_h  host double N x N (ldd >= N).
- * Copies X to the device in row blocks, pushes up, computes all pairs and returns D in D_h.
- * Pinned (cudaHostAlloc / cudaHostRegister) buffers are used in place; pageable ones are staged.
- * validate != 0 runs the float64 validation kernels instead of the fp32 production path. */
+ * Copies X to the device in row blocks, pushes up (centred, see fuf_push_up_center), computes all pairs,
+ * refines (fuf_refine) and returns D in D_h.  Pinned (cudaHostAlloc / cudaHostRegister) buffers are used in
+ * place; pageable ones are staged.  flags: FUF_AP_VALIDATE, FUF_AP_NO_REFINE. */
 int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, int64_t N, int64_t ldx, int mode, double *D_h,
-                       int64_t ldd, int validate);
+                       int64_t ldd, int flags);
 
 /* Timing of the phases of the last fuf_all_pairs_host call on this context, milliseconds (CUDA events). */
 int fuf_last_timing(const fuf_ctx *ctx, float *h2d_pushup_ms, float *pairwise_ms, float *total_ms);

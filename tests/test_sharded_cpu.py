@@ -1,0 +1,146 @@
+"""Host-side logic of the multi-GPU path (fununifrac_b200/sharded.py) on CPU: the partition helpers, and the
+whole exchange sequence with world_size 2 and 3 over the ``gloo`` backend.  The compute calls are replaced by a
+test-only stand-in built on the CPU oracle (the product always injects the CUDA context); what is under test is
+the sharding, the layouts that cross ranks, and the assembly of the full matrix on rank 0."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fununifrac_b200 import sharded
+
+TILE = 128
+
+
+def test_partition_helpers():
+    for N, world in ((1, 1), (127, 2), (128, 2), (700, 3), (10000, 8), (10000, 1), (300, 8)):
+        sh = sharded.shard_size(N, world)
+        assert sh % TILE == 0 and sh * world >= N
+        ranges = [sharded.sample_range(N, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == N
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        T = (N + TILE - 1) // TILE
+        rows = [sharded.owned_tile_rows(N, world, r) for r in range(world)]
+        assert sorted(sum(rows, [])) == list(range(T))
+        tiles = [sharded.tiles_of(r, N) for r in rows]
+        assert sum(tiles) == T * (T + 1) // 2
+        if T >= 4 * world:          # balanced to within ~one tile row
+            assert max(tiles) - min(tiles) <= T
+    # 10K samples over 8 GPUs: every rank within 2% of the mean tile count
+    t = [sharded.tiles_of(sharded.owned_tile_rows(10000, 8, r), 10000) for r in range(8)]
+    assert max(t) / (sum(t) / 8) < 1.02
+
+
+class OracleOps:
+    """Test-only stand-in for ``sharded.CudaOps``: same calls, computed by the CPU oracle on torch CPU tensors."""
+
+    def __init__(self, parent, length, l2):
+        from oracle import oracle_c
+        self.o, self.parent, self.length, self.l2, self.n = oracle_c, parent, length, l2, len(parent)
+        self.refine_calls = 0
+
+    def empty(self, shape, dtype):
+        return torch.zeros(shape, dtype=getattr(torch, dtype))
+
+    def push_up_center(self, X, mode, out):
+        m = min(X.shape[0], 32)
+        c = self.o.push_up(self.parent, self.length, X[:m].numpy().mean(0), self.l2)
+        has_child = np.zeros(self.n, bool)
+        has_child[self.parent[self.parent >= 0]] = True
+        out.copy_(torch.from_numpy(np.where(has_child, c, 0.0)))
+
+    def push_up(self, X, mode, PT, col0, center, P64T, err_stat):
+        P = self.o.push_up(self.parent, self.length, X.numpy(), self.l2)            # [N, n]
+        N = P.shape[0]
+        c = P - center.numpy()[None, :]
+        f = c.astype(np.float32)
+        PT[:, col0:col0 + N] = torch.from_numpy(f.T.copy())
+        if P64T is not None:
+            P64T[:, col0:col0 + N] = torch.from_numpy(P.T.copy())
+        e = np.abs(c - f.astype(np.float64))
+        err_stat[col0:col0 + N] = torch.from_numpy((e ** 2).sum(1) if self.l2 else e.sum(1))
+
+    def _samples(self, PS, N, shard):
+        G, n, sh = PS.shape
+        return PS.permute(0, 2, 1).reshape(G * sh, n)[:N].double().numpy()
+
+    def pairwise(self, PT, N, mode, tile_rows, shard, shard_stride, D):
+        P = self._samples(PT, N, shard)
+        if tile_rows is None:
+            D.copy_(torch.from_numpy(self.o.pairwise(P, self.l2)))
+            return D
+        D.fill_(float("nan"))       # everything the contract does not promise is poisoned
+        for c, t in enumerate(tile_rows):
+            r0, r1 = t * TILE, min(N, (t + 1) * TILE)
+            blk = self.o.pairwise_rows(P, r0, r1, self.l2)
+            D[c * TILE:c * TILE + (r1 - r0), r0:] = torch.from_numpy(blk[:, r0:])
+        return D
+
+    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride):
+        self.refine_calls += 1
+        assert P64T.shape[0] * P64T.shape[2] >= N and err_stat.numel() >= N
+        return D
+
+    def assemble(self, blocks, rows, N, D):
+        blocks = blocks.reshape(-1, blocks.shape[-1])
+        for c, t in enumerate(rows):
+            if t < 0:
+                continue
+            r0, r1 = t * TILE, min(N, (t + 1) * TILE)
+            blk = blocks[c * TILE:c * TILE + (r1 - r0)]
+            D[r0:r1, r0:] = blk[:, r0:]
+            D[r0:, r0:r1] = blk[:, r0:].T
+        return D
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, N, l2, out_path):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        n = 300
+        parent = np.minimum(np.arange(n) + 1 + rng.integers(0, 6, n), n - 1).astype(np.int32)
+        parent[-1] = -1
+        length = rng.random(n) * (rng.random(n) > 0.1)
+        X = rng.random((N, n)) * (rng.random((N, n)) < 0.3)
+        X[:, -1] = 0
+        X /= X.sum(1, keepdims=True)
+        ops = OracleOps(parent, length, l2)
+        job = sharded.ShardedAllPairs(ops, N, int(l2), world, rank, dist)
+        marks = []
+        D = job.step(torch.from_numpy(X[job.lo:job.hi]), marks.append)
+        assert marks[0] == "start" and marks[-1] == "end" and "pair_begin" in marks
+        assert ops.refine_calls == (1 if job.rows else 0)
+        if rank == 0:
+            from oracle import oracle_c
+            ref = oracle_c.pairwise(oracle_c.push_up(parent, length, X, l2), l2)
+            got = D.numpy()
+            assert not np.isnan(got).any()
+            iu = np.triu_indices(N, 1)
+            err = np.abs(got[iu] - ref[iu]) / ref[iu]
+            assert err.max() < 1e-5, err.max()          # fp32-rounded operands, float64 arithmetic
+            assert np.array_equal(got, got.T) and not np.diag(got).any()
+            np.save(out_path, got)
+        else:
+            assert D is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N,l2", [(2, 300, False), (3, 700, False), (2, 129, True)])
+def test_sharded_exchange_gloo(world, N, l2, tmp_path):
+    out = str(tmp_path / "D.npy")
+    mp.spawn(_worker, args=(world, _free_port(), N, l2, out), nprocs=world, join=True)
+    assert np.load(out).shape == (N, N)
