@@ -75,6 +75,10 @@ refine_kernel(const RefineParams p)
                 if (b == 0.0) flag = false;  // both samples exactly representable in fp32: nothing to gain
             }
             unsigned mask = __ballot_sync(0xffffffffu, flag);
+            if (p.P64T == nullptr) {  // count-only mode
+                if (lane == 0) refined += __popc(mask);
+                continue;
+            }
             while (mask) {
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -166,12 +170,13 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
                           int64_t shard_stride, int mode, const double *err_stat, double kappa,
                           const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream)
 {
-    FUF_REQUIRE(ctx && P64T && err_stat && D, "fuf_refine: null argument");
+    FUF_REQUIRE(ctx && err_stat && D, "fuf_refine: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_refine: bad mode %d", mode);
     FUF_REQUIRE(N >= 0 && ldd >= N && N < ((int64_t)1 << 31), "fuf_refine: bad shape N=%lld ldd=%lld", (long long)N,
                 (long long)ldd);
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_refine: n_tile_rows without tile_rows_h");
-    if (shard == 0)
+    if (!P64T) {
+    } else if (shard == 0)
         FUF_REQUIRE(ldp64 >= N, "fuf_refine: ldp64=%lld < N=%lld", (long long)ldp64, (long long)N);
     else
         FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");

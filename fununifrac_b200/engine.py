@@ -232,10 +232,12 @@ class TreeContext:
                shard: int = 0, shard_stride: int = 0, kappa: float = 0.0):
         """``fuf_refine``: recompute in float64 the pairs of D the fp32 operands cannot certify (in place)."""
         torch = _torch()
-        assert P64T.dtype == torch.float64 and err_stat.dtype == torch.float64 and D.dtype == torch.float64
+        assert err_stat.dtype == torch.float64 and D.dtype == torch.float64
+        assert P64T is None or P64T.dtype == torch.float64      # None: count-only mode
         rows_arr = None if tile_rows is None else np.ascontiguousarray(tile_rows, dtype=np.int32)
-        ldp = P64T.stride(0) if shard == 0 else 0
-        _check(self._lib.fuf_refine(self.handle, P64T.data_ptr(), N, ldp, shard, shard_stride, mode,
+        ldp = P64T.stride(0) if (shard == 0 and P64T is not None) else 0
+        _check(self._lib.fuf_refine(self.handle, None if P64T is None else P64T.data_ptr(), N, ldp, shard,
+                                    shard_stride, mode,
                                     err_stat.data_ptr(), float(kappa),
                                     rows_arr.ctypes.data if rows_arr is not None else None,
                                     0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),

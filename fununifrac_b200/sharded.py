@@ -74,7 +74,9 @@ class ShardedAllPairs:
         self.center = ops.empty((n,), "float64")
         self.D = ops.empty((N, N), "float64") if rank == 0 else None
         self.blocks = self.gathered = None
+        self.last_flagged = 0
         if world > 1:
+            self.flagged = ops.empty((1,), "int64")
             self.blocks = ops.empty((self.max_rows * TILE, N), "float64")
             if rank == 0:   # one buffer, one slot of max_rows row blocks per rank (unused slots are skipped)
                 self.gathered = ops.empty((world, self.max_rows * TILE, N), "float64")
@@ -108,14 +110,20 @@ class ShardedAllPairs:
             return self.D
         self.dist.all_gather_into_tensor(self.PS.view(-1), self.PS[r].reshape(-1))
         self.dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
-        if self.do_refine:
-            self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
         mark("pair_begin")
         if self.rows:
             ops.pairwise(self.PS, N, mode, self.rows, sh, stride, self.blocks)
         mark("pair_end")
-        if self.rows and self.do_refine:
-            ops.refine(self.P64S, N, mode, self.stat, self.blocks, self.rows, sh, stride)
+        if self.do_refine:
+            # the float64 profiles (2x the fp32 volume) cross NVLink only if some rank has a pair to refine
+            mine = ops.count_uncertified(N, mode, self.stat, self.blocks, self.rows) if self.rows else 0
+            self.flagged[0] = mine
+            self.dist.all_reduce(self.flagged)
+            self.last_flagged = int(self.flagged.item())
+            if self.last_flagged > 0:
+                self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
+                if self.rows:
+                    ops.refine(self.P64S, N, mode, self.stat, self.blocks, self.rows, sh, stride)
         self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
         if r == 0:
             ops.assemble(self.gathered, self.slot_rows, N, self.D)
@@ -146,6 +154,10 @@ class CudaOps:
 
     def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride):
         return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)
+
+    def count_uncertified(self, N, mode, err_stat, D, tile_rows):
+        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows)
+        return self.ctx.refine_count()
 
     def assemble(self, blocks, rows, N, D):
         return self.ctx.assemble(blocks, rows, N, D=D)

@@ -160,6 +160,8 @@ int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, i
  *     L1: D[i,j] < kappa (err_stat[i] + err_stat[j])          L2: D[i,j] < kappa (sqrt err_stat[i] + sqrt err_stat[j])^2
  * is recomputed from P64T in double and overwritten (with its mirror when tile_rows_h == NULL).
  * kappa <= 0 selects the default (2e6 / 1.6e13: rounding of the fp32 operands may cost at most 0.5e-6 relative).
+ * P64T == NULL: count-only mode (D is not modified) — lets several GPUs agree on whether the float64 profiles
+ * have to be exchanged at all.
  * fuf_refine_count synchronises the stream and returns how many pairs the last fuf_refine recomputed. */
 int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
                const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,

@@ -163,6 +163,15 @@ double oracle_solve(const int32_t *parent, const double *length, int32_t n, cons
     return Z;
 }
 
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -37,6 +37,7 @@ def lib():
         L.oracle_np_sum.argtypes = [f64p, ctypes.c_int64]
         L.oracle_np_sum.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
 
@@ -108,3 +109,8 @@ def np_sum(a):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_threads(n):
+    """Use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1, which would otherwise cap the baseline)."""
+    lib().oracle_set_threads(int(n))
