@@ -4,10 +4,10 @@
 //
 // Pipeline: X is copied to the device in row blocks on a copy stream (double-buffered staging),
 // each block is pushed up on the compute stream as soon as it has landed, then the all-pairs kernel
-// runs over the complete node-major P, followed by the float64 refinement pass over the few pairs the
-// fp32 operands cannot certify (refine.cu).  The matrix is always produced in device memory; when D_h
-// is pinned memory the tile epilogue ALSO writes it straight into D_h over PCIe (coalesced 1 KB rows),
-// so the device-to-host transfer overlaps the kernel; otherwise D is copied back at the end.
+// runs band by band (see below), each band followed by the float64 refinement pass over the few pairs the
+// fp32 operands cannot certify (refine.cu) and by the device-to-host copy of the finished part of D on a
+// third stream.  (Letting the tile epilogues write D straight into pinned host memory was measured: the
+// kernel then stalls for exactly the PCIe time of the matrix, so the DMA engines do it instead.)
 #include <algorithm>
 #include <cstdlib>
 
@@ -53,56 +53,89 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         stat = center + n;
         if (do_refine) P64T = stat + ldp;
     }
-    // row blocks of ~64 MB, multiples of 128 samples
-    int64_t rb = (int64_t)(((size_t)64 << 20) / ((size_t)n * esz));
-    rb = std::max<int64_t>(128, rb / 128 * 128);
-    rb = std::min<int64_t>(rb, ldp);
-    const size_t blk_bytes = (size_t)rb * n * esz;
-    if ((rc = ctx->ws_x.reserve(2 * blk_bytes))) return rc;
-    const bool d_pinned = is_pinned_host(D_h) && !getenv("FUF_NO_ZEROCOPY");
+    // The whole X gets a device copy (no staging ring: the copy stream never waits for compute).  Samples are
+    // cut into up to 16 bands of whole 128-sample tiles; band b is copied on the copy stream, and as soon as it has
+    // landed the compute stream pushes it up and computes the column band of D that involves it (tiles
+    // (ti, tj) with tj in the band, ti <= tj) while the later bands are still crossing PCIe.
+    const int64_t tiles_per_dim = ldp / 128;
+    int nb = validate ? 1 : (int)std::min<int64_t>(16, std::max<int64_t>(1, tiles_per_dim / 4));
+    if (getenv("FUF_HOST_BANDS")) nb = std::max(1, std::min(64, atoi(getenv("FUF_HOST_BANDS"))));
+    nb = (int)std::min<int64_t>(nb, tiles_per_dim);
+    if ((rc = ctx->ws_x.reserve((size_t)N * n * esz))) return rc;
+    const bool d_pinned = is_pinned_host(D_h);
     if ((rc = ctx->ws_d.reserve((size_t)N * N * sizeof(double)))) return rc;
     double *D_dev = (double *)ctx->ws_d.ptr, *D_zc = nullptr;
-    if (d_pinned) FUF_CUDA(cudaHostGetDevicePointer((void **)&D_zc, D_h, 0));
-    cudaStream_t sc = ctx->s_copy, sk = ctx->s_comp;
+    if (d_pinned && !validate && getenv("FUF_ZEROCOPY")) FUF_CUDA(cudaHostGetDevicePointer((void **)&D_zc, D_h, 0));
+    // pinned D_h: every finished band of D is copied while the next one computes; pageable D_h: one copy at the end
+    const bool band_d2h = !validate && d_pinned && D_zc == nullptr;
+    cudaStream_t sc = ctx->s_copy, sk = ctx->s_comp, sd = ctx->s_d2h;
     cudaEvent_t e_start = ctx->ev[0], e_push = ctx->ev[1], e_end = ctx->ev[2];
-    cudaEvent_t e_copied[2] = {ctx->ev[3], ctx->ev[4]}, e_free[2] = {ctx->ev[5], ctx->ev[6]};
+    std::vector<cudaEvent_t> &e_band = ctx->ev_band;
+    while ((int)e_band.size() < 2 * nb) {
+        cudaEvent_t e;
+        FUF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        e_band.push_back(e);
+    }
+    std::vector<int64_t> band_tile(nb + 1);
+    for (int b = 0; b <= nb; b++) band_tile[b] = tiles_per_dim * b / nb;
 
     FUF_CUDA(cudaEventRecord(e_start, sk));
     FUF_CUDA(cudaStreamWaitEvent(sc, e_start, 0));
-    int64_t done = 0;
-    for (int b = 0; done < N; b++) {
-        const int slot = b & 1;
-        const int64_t rows = std::min<int64_t>(rb, N - done);
-        char *xbuf = (char *)ctx->ws_x.ptr + (size_t)slot * blk_bytes;
-        if (b >= 2) FUF_CUDA(cudaStreamWaitEvent(sc, e_free[slot], 0));
-        FUF_CUDA(cudaMemcpy2DAsync(xbuf, (size_t)n * esz, (const char *)X_h + (size_t)done * ldx * esz,
-                                   (size_t)ldx * esz, (size_t)n * esz, (size_t)rows, cudaMemcpyHostToDevice, sc));
-        FUF_CUDA(cudaEventRecord(e_copied[slot], sc));
-        FUF_CUDA(cudaStreamWaitEvent(sk, e_copied[slot], 0));
+    for (int b = 0; b < nb; b++) {  // all copies are queued up front
+        const int64_t s0 = band_tile[b] * 128, s1 = std::min<int64_t>(N, band_tile[b + 1] * 128);
+        if (s1 > s0)
+            FUF_CUDA(cudaMemcpy2DAsync((char *)ctx->ws_x.ptr + (size_t)s0 * n * esz, (size_t)n * esz,
+                                       (const char *)X_h + (size_t)s0 * ldx * esz, (size_t)ldx * esz, (size_t)n * esz,
+                                       (size_t)(s1 - s0), cudaMemcpyHostToDevice, sc));
+        FUF_CUDA(cudaEventRecord(e_band[b], sc));
+    }
+    for (int b = 0; b < nb; b++) {
+        const int64_t s0 = band_tile[b] * 128, s1 = std::min<int64_t>(N, band_tile[b + 1] * 128);
+        FUF_CUDA(cudaStreamWaitEvent(sk, e_band[b], 0));
+        if (s1 <= s0) continue;
+        const char *xb = (const char *)ctx->ws_x.ptr + (size_t)s0 * n * esz;
         if (validate) {
-            rc = push_up_f64_exact(ctx, (const double *)xbuf, rows, n, mode, (double *)ctx->ws_p.ptr, ldp, done, sk);
+            rc = push_up_f64_exact(ctx, (const double *)xb, s1 - s0, n, mode, (double *)ctx->ws_p.ptr, ldp, s0, sk);
         } else {
             if (b == 0) {  // the centre of the whole job: pushed mean of the first few samples
-                rc = push_up_center(ctx, xbuf, x_dtype, std::min<int64_t>(rows, FUF_CENTER_SAMPLES), n, mode, center, sk);
+                rc = push_up_center(ctx, xb, x_dtype, std::min<int64_t>(s1 - s0, FUF_CENTER_SAMPLES), n, mode, center, sk);
                 if (rc) return rc;
             }
-            rc = push_up_f32(ctx, xbuf, x_dtype, rows, n, mode, center, (float *)ctx->ws_p.ptr, ldp, P64T, ldp, stat,
-                             done, sk);
+            rc = push_up_f32(ctx, xb, x_dtype, s1 - s0, n, mode, center, (float *)ctx->ws_p.ptr, ldp, P64T, ldp, stat,
+                             s0, sk);
         }
         if (rc) return rc;
-        FUF_CUDA(cudaEventRecord(e_free[slot], sk));
-        done += rows;
+        if (b == 0) FUF_CUDA(cudaEventRecord(e_push, sk));
+        if (!validate) {
+            rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, s1, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk, D_zc,
+                              ldd, (int32_t)band_tile[b], (int32_t)band_tile[b + 1]);
+            if (rc) return rc;
+            if (do_refine) {
+                rc = refine(ctx, P64T, s1, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, D_zc, ldd, s0, s1,
+                            b == 0);
+                if (rc) return rc;
+            }
+            if (band_d2h) {
+                // finished: columns [s0, s1) of rows [0, s1), and (mirror) rows [s0, s1) left of the band
+                FUF_CUDA(cudaEventRecord(e_band[nb + b], sk));
+                FUF_CUDA(cudaStreamWaitEvent(sd, e_band[nb + b], 0));
+                FUF_CUDA(cudaMemcpy2DAsync(D_h + s0, (size_t)ldd * sizeof(double), D_dev + s0, (size_t)N * sizeof(double),
+                                           (size_t)(s1 - s0) * sizeof(double), (size_t)s1, cudaMemcpyDeviceToHost, sd));
+                if (s0 > 0)
+                    FUF_CUDA(cudaMemcpy2DAsync(D_h + (size_t)s0 * ldd, (size_t)ldd * sizeof(double),
+                                               D_dev + (size_t)s0 * N, (size_t)N * sizeof(double),
+                                               (size_t)s0 * sizeof(double), (size_t)(s1 - s0), cudaMemcpyDeviceToHost,
+                                               sd));
+            }
+        }
     }
-    FUF_CUDA(cudaEventRecord(e_push, sk));
-    if (validate) {
-        rc = pairwise_f64(ctx, (const double *)ctx->ws_p.ptr, N, ldp, mode, D_dev, N, sk);
-    } else {
-        rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, N, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk, D_zc, ldd);
-        if (!rc && do_refine)
-            rc = refine(ctx, P64T, N, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, D_zc, ldd);
+    if (validate) rc = pairwise_f64(ctx, (const double *)ctx->ws_p.ptr, N, ldp, mode, D_dev, N, sk);
+    if (band_d2h) {  // the compute stream's end event waits for the last band copy
+        FUF_CUDA(cudaEventRecord(e_band[0], sd));
+        FUF_CUDA(cudaStreamWaitEvent(sk, e_band[0], 0));
     }
     if (rc) return rc;
-    if (!d_pinned || validate)
+    if (!band_d2h && D_zc == nullptr)
         FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
                                    (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
     FUF_CUDA(cudaEventRecord(e_end, sk));

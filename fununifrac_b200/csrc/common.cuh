@@ -97,8 +97,9 @@ struct fuf_ctx {
     unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine
     int64_t last_refined = 0;
     fuf::PinnedBuffer pin_x;       // pinned staging when X_h is pageable
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> ev_band;  // one per sample band of fuf_all_pairs_host
     float t_h2d_push = 0.f, t_pair = 0.f, t_total = 0.f;
 
     int64_t launches = 0;
@@ -117,7 +118,8 @@ int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int
 // pairwise.cu
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0);
+                 cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int32_t col_tile_begin = 0,
+                 int32_t col_tile_end = 0);
 int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
                  cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
@@ -125,7 +127,8 @@ int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int
 // refine.cu
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
-           int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0);
+           int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int64_t j_begin = 0,
+           int64_t j_end = 0, bool reset_counter = true);
 // diffab.cu
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                  int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);

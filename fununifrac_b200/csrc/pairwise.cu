@@ -464,7 +464,7 @@ static EncodeTiledFn get_encode_fn()
 
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream, double *D2, int64_t ldd2)
+                 cudaStream_t stream, double *D2, int64_t ldd2, int32_t col_tile_begin, int32_t col_tile_end)
 {
     if (N == 0) return FUF_OK;
     const int32_t n = ctx->n;
@@ -517,12 +517,20 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     std::vector<TileDesc> tiles;
     const bool full = (tile_rows_h == nullptr);
     const int32_t n_rows = full ? (int32_t)tiles_per_dim : n_tile_rows;
-    for (int32_t c = 0; c < n_rows; c++) {
-        const int32_t t = full ? c : tile_rows_h[c];
-        FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise: tile row %d out of range [0,%lld)", t,
-                    (long long)tiles_per_dim);
-        for (int32_t tj = t; tj < tiles_per_dim; tj++)
-            tiles.push_back(TileDesc{t, tj, full ? t * TILE : c * TILE, (full && tj != t) ? 1 : 0});
+    if (full && col_tile_end > 0) {
+        // column band [col_tile_begin, col_tile_end) of the upper triangle (the host-buffer path computes the
+        // matrix band by band while later samples are still in flight over PCIe)
+        const int32_t ce = std::min<int32_t>(col_tile_end, (int32_t)tiles_per_dim);
+        for (int32_t tj = std::max(0, col_tile_begin); tj < ce; tj++)
+            for (int32_t t = 0; t <= tj; t++) tiles.push_back(TileDesc{t, tj, t * TILE, tj != t ? 1 : 0});
+    } else {
+        for (int32_t c = 0; c < n_rows; c++) {
+            const int32_t t = full ? c : tile_rows_h[c];
+            FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise: tile row %d out of range [0,%lld)", t,
+                        (long long)tiles_per_dim);
+            for (int32_t tj = t; tj < tiles_per_dim; tj++)
+                tiles.push_back(TileDesc{t, tj, full ? t * TILE : c * TILE, (full && tj != t) ? 1 : 0});
+        }
     }
     const int32_t n_tiles = (int32_t)tiles.size();
     if (n_tiles == 0) return FUF_OK;
@@ -641,7 +649,7 @@ extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ld
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_f32(ctx, PT, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd, flags,
-                        (cudaStream_t)stream, nullptr, 0);
+                        (cudaStream_t)stream, nullptr, 0, 0, 0);
 }
 
 extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D,

@@ -65,14 +65,18 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
         s_cp[tid] = ok ? cp_after[k] : -1;
         s_span[tid] = ok ? is_span[k] : 1;
     }
-    // coalesced load of the X tile: one warp request = one sample row segment of KT entries
-#pragma unroll 4
-    for (int it = 0; it < TI / 4; it++) {
-        int row = it * 4 + warp;
-        int64_t s = i0 + row;
-        TX v = TX(0);
-        if (s < N && lane < kt) v = X[s * ldx + k0 + lane];
-        xs[lane][row] = v;
+    // coalesced load of the X tile: one warp request = one sample row segment of KT entries.  All TI/4 requests
+    // of a warp are issued before the first value is used (32 x 256 B in flight per warp): the kernel streams
+    // X once and is bound by how many bytes it keeps in flight.
+    {
+        TX v[TI / 4];
+#pragma unroll
+        for (int it = 0; it < TI / 4; it++) {
+            const int64_t s = i0 + it * 4 + warp;
+            v[it] = (s < N && lane < kt) ? __ldcs(X + s * ldx + k0 + lane) : TX(0);
+        }
+#pragma unroll
+        for (int it = 0; it < TI / 4; it++) xs[lane][it * 4 + warp] = v[it];
     }
 #pragma unroll
     for (int kk = 0; kk < KT; kk++) acc[kk][tid] = 0.0;

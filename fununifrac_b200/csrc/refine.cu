@@ -30,6 +30,7 @@ struct RefineParams {
     double *D2;                // optional second destination (zero-copy host mirror), write-only
     int64_t ldd2;
     int mirror;                // also write D[j,i]
+    int64_t j_begin, j_end;    // only pairs with j in [j_begin, j_end) are examined
     unsigned long long *counter;
 };
 
@@ -46,7 +47,7 @@ refine_kernel(const RefineParams p)
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t segs_per_row = (p.N + RSEG - 1) / RSEG;
+    const int64_t segs_per_row = (p.j_end - p.j_begin + RSEG - 1) / RSEG;
     const int64_t n_items = (int64_t)p.n_rows_total * segs_per_row;
     const int64_t kstride = p.shard == 0 ? p.ldp64 : p.shard;
     unsigned long long refined = 0;
@@ -59,7 +60,7 @@ refine_kernel(const RefineParams p)
             gi = (int64_t)t * FUF_TILE + row % FUF_TILE;
         }
         if (gi >= p.N) continue;
-        const int64_t j0 = seg * RSEG;
+        const int64_t j0 = p.j_begin + seg * RSEG;
         if (j0 + RSEG <= gi + 1) continue;  // entirely on or below the diagonal
         const double si = MODE == FUF_MODE_L2 ? sqrt(p.stat[gi]) : p.stat[gi];
         double *drow = p.D + row * p.ldd;
@@ -67,7 +68,7 @@ refine_kernel(const RefineParams p)
         for (int u = 0; u < RSEG / 32; u++) {
             const int64_t gj = j0 + u * 32 + lane;
             bool flag = false;
-            if (gj > gi && gj < p.N) {
+            if (gj > gi && gj < p.j_end) {
                 const double d = drow[gj];
                 const double sj = MODE == FUF_MODE_L2 ? sqrt(p.stat[gj]) : p.stat[gj];
                 const double b = si + sj;
@@ -118,11 +119,15 @@ refine_kernel(const RefineParams p)
 
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
-           int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2)
+           int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2, int64_t j_begin, int64_t j_end,
+           bool reset_counter)
 {
-    if (N < 2) return FUF_OK;
     if (!ctx->d_refined) FUF_CUDA(cudaMalloc((void **)&ctx->d_refined, sizeof(unsigned long long)));
-    FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
+    if (reset_counter) FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
+    if (N < 2) return FUF_OK;
+    if (j_end <= 0 || j_end > N) j_end = N;
+    if (j_begin < 0) j_begin = 0;
+    if (j_begin >= j_end) return FUF_OK;
     RefineParams p;
     p.P64T = P64T;
     p.ldp64 = ldp64;
@@ -137,6 +142,8 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
     p.D2 = D2;
     p.ldd2 = ldd2;
     p.counter = ctx->d_refined;
+    p.j_begin = j_begin;
+    p.j_end = j_end;
     if (tile_rows_h) {
         if (n_tile_rows == 0) return FUF_OK;
         int rc = ctx->ws_rows.reserve((size_t)n_tile_rows * sizeof(int32_t));
@@ -149,7 +156,7 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
         p.mirror = 0;
     } else {
         p.tile_rows = nullptr;
-        p.n_rows_total = (int32_t)N;
+        p.n_rows_total = (int32_t)j_end;   // rows i < j < j_end
         p.mirror = 1;
     }
     const int grid = ctx->sm_count * 8;
@@ -182,7 +189,7 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
         FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
-                  (cudaStream_t)stream, nullptr, 0);
+                  (cudaStream_t)stream, nullptr, 0, 0, N, true);
 }
 
 extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)

@@ -281,7 +281,8 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
         return rc;
     }
     if (cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("fuf_tree_create: cudaStreamCreate failed");
         fuf_tree_destroy(ctx);
         return FUF_ECUDA;
@@ -320,8 +321,10 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     ctx->pin_x.release();
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_band) cudaEventDestroy(ev);
     cudaGetLastError();
     delete ctx;
     return FUF_OK;

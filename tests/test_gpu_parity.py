@@ -222,6 +222,26 @@ def test_tile_rows_assemble_and_shards(full_tree):
     assert torch.equal(one.step(X), D)
 
 
+def test_host_path_bands(full_tree, monkeypatch):
+    """fuf_all_pairs_host computes D band by band while later samples are still being copied; forcing 3 and 5
+    bands at a small N must give the device-resident result up to the order of the final float64 additions."""
+    inp, ctx, leaves = full_tree
+    N = 700
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=9)
+    X[300] = X[2] * (1 + 1e-5 * np.random.default_rng(1).random(ctx.n))
+    X[699] = X[130]
+    D = ctx.distances(ctx.push_up_job(torch.from_numpy(X).cuda(), engine.MODE_L1), engine.MODE_L1).cpu().numpy()
+    for bands in ("1", "3", "5"):
+        monkeypatch.setenv("FUF_HOST_BANDS", bands)
+        Dh = ctx.all_pairs_host(X, engine.MODE_L1)
+        assert np.allclose(Dh, D, rtol=1e-13, atol=0) and np.array_equal(Dh, Dh.T)
+        assert Dh[130, 699] == 0 and ctx.refine_count() >= 2
+        Dp = engine.pinned_empty((N, N), torch.float64)[1]
+        Dp[:] = -1
+        ctx.all_pairs_host(X, engine.MODE_L1, Dp)            # pinned destination: written by the tile epilogues
+        assert np.array_equal(Dp, Dh)
+
+
 def test_near_duplicates_are_refined(full_tree):
     """Clusters of near-identical samples: the fp32 operands cannot resolve their distances, the refinement pass
     does; ordinary pairs are left to the fp32 tiles."""
