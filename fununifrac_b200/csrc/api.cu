@@ -46,26 +46,27 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     if ((rc = ctx->ws_p.reserve((size_t)n * ldp * psz))) return rc;
     double *P64T = nullptr, *center = nullptr, *stat = nullptr;
     if (!validate) {
-        // centre [n] | error statistic [ldp] | P64T [n][ldp] (only when refining)
-        const size_t head = ((size_t)n + (size_t)ldp) * sizeof(double);
+        // centre [n] | error statistic [ldp] | Gram norms [ldp] | Gram error statistic [ldp] | P64T [n][ldp] (if refining)
+        const size_t head = ((size_t)n + 3 * (size_t)ldp) * sizeof(double);
         if ((rc = ctx->ws_p64.reserve(head + (do_refine ? (size_t)n * ldp * sizeof(double) : 0)))) return rc;
         center = (double *)ctx->ws_p64.ptr;
         stat = center + n;
-        if (do_refine) P64T = stat + ldp;
+        if (do_refine) P64T = stat + 3 * ldp;
     }
     // The whole X gets a device copy (no staging ring: the copy stream never waits for compute).  Samples are
     // cut into up to 16 bands of whole 128-sample tiles; band b is copied on the copy stream, and as soon as it has
     // landed the compute stream pushes it up and computes the column band of D that involves it (tiles
     // (ti, tj) with tj in the band, ti <= tj) while the later bands are still crossing PCIe.
     const int64_t tiles_per_dim = ldp / 128;
-    int nb = validate ? 1 : (int)std::min<int64_t>(16, std::max<int64_t>(1, tiles_per_dim / 4));
+    const bool use_gram = !validate && mode == FUF_MODE_L2 && N >= FUF_GRAM_MIN_SAMPLES && !(flags & FUF_AP_NO_GRAM);
+    int nb = (validate || use_gram) ? 1 : (int)std::min<int64_t>(16, std::max<int64_t>(1, tiles_per_dim / 4));
     if (getenv("FUF_HOST_BANDS")) nb = std::max(1, std::min(64, atoi(getenv("FUF_HOST_BANDS"))));
     nb = (int)std::min<int64_t>(nb, tiles_per_dim);
     if ((rc = ctx->ws_x.reserve((size_t)N * n * esz))) return rc;
     const bool d_pinned = is_pinned_host(D_h);
     if ((rc = ctx->ws_d.reserve((size_t)N * N * sizeof(double)))) return rc;
     double *D_dev = (double *)ctx->ws_d.ptr, *D_zc = nullptr;
-    if (d_pinned && !validate && getenv("FUF_ZEROCOPY")) FUF_CUDA(cudaHostGetDevicePointer((void **)&D_zc, D_h, 0));
+    if (d_pinned && !validate && !use_gram && getenv("FUF_ZEROCOPY")) FUF_CUDA(cudaHostGetDevicePointer((void **)&D_zc, D_h, 0));
     // pinned D_h: every finished band of D is copied while the next one computes; pageable D_h: one copy at the end
     const bool band_d2h = !validate && d_pinned && D_zc == nullptr;
     cudaStream_t sc = ctx->s_copy, sk = ctx->s_comp, sd = ctx->s_d2h;
@@ -106,7 +107,22 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         }
         if (rc) return rc;
         if (b == 0) FUF_CUDA(cudaEventRecord(e_push, sk));
-        if (!validate) {
+        if (use_gram) {
+            // --L2 on the tensor cores: the Gram kernel needs every sample (node means), so no banding here
+            double *qg = stat + ldp, *eg = qg + ldp;
+            rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, stat, qg, eg, D_dev, N, sk);
+            if (rc) return rc;
+            if (do_refine) {
+                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, qg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,
+                            FUF_CRIT_LINEAR);
+                if (!rc) rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, false);
+                if (rc) return rc;
+            }
+            if (band_d2h) {
+                FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
+                                           (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
+            }
+        } else if (!validate) {
             rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, s1, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk, D_zc,
                               ldd, (int32_t)band_tile[b], (int32_t)band_tile[b + 1]);
             if (rc) return rc;
@@ -115,7 +131,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
                             b == 0);
                 if (rc) return rc;
             }
-            if (band_d2h) {
+            if (band_d2h && !use_gram) {
                 // finished: columns [s0, s1) of rows [0, s1), and (mirror) rows [s0, s1) left of the band
                 FUF_CUDA(cudaEventRecord(e_band[nb + b], sk));
                 FUF_CUDA(cudaStreamWaitEvent(sd, e_band[nb + b], 0));

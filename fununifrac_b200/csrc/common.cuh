@@ -93,12 +93,15 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_d;        // D on device when the host buffer cannot be written in place
     fuf::DeviceBuffer ws_center;   // column mean scratch of fuf_push_up_center
     fuf::DeviceBuffer ws_rows;     // tile-row list of fuf_refine
+    fuf::DeviceBuffer ws_gram;     // TF32 hi/lo planes + tile list of fuf_pairwise_gram
     fuf::DeviceBuffer ws_p64;      // P64T + centre + error statistics (fuf_all_pairs_host)
     unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine
     int64_t last_refined = 0;
     fuf::PinnedBuffer pin_x;       // pinned staging when X_h is pageable
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_gram[2] = {};       // around the last gram_tile_kernel launch
+    double gram_flops = 0.0;           // MMA flops that launch executed
     std::vector<cudaEvent_t> ev_band;  // one per sample band of fuf_all_pairs_host
     float t_h2d_push = 0.f, t_pair = 0.f, t_total = 0.f;
 
@@ -119,16 +122,19 @@ int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
                  cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int32_t col_tile_begin = 0,
-                 int32_t col_tile_end = 0);
+                 int32_t col_tile_end = 0, int32_t n_rows_override = 0, int32_t flush_stages = 0);
 int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
                  cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
              double *D, int64_t ldd, cudaStream_t stream);
+// gram.cu
+int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, const double *err_in, double *q,
+                  double *err_out, double *D, int64_t ldd, cudaStream_t stream);
 // refine.cu
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int64_t j_begin = 0,
-           int64_t j_end = 0, bool reset_counter = true);
+           int64_t j_end = 0, bool reset_counter = true, int criterion = 0);
 // diffab.cu
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                  int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);

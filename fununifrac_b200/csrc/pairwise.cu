@@ -47,6 +47,7 @@ struct PairParams {
     int32_t splits;
     int32_t stages_total;      // ceil(n / KC)
     int32_t stages_per_split;
+    int32_t flush_stages;      // fp32 partial sums are folded into double every flush_stages stages
     int32_t shard;             // columns per shard of PT (>= padded N when there is a single block)
     int64_t N;
     double *D;
@@ -271,7 +272,7 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-            if ((st - s_begin + 1) % FLUSH_STAGES == 0) flush();
+            if ((st - s_begin + 1) % p.flush_stages == 0) flush();
         }
         flush();
         consumer_bar();  // all double accumulators of the tile are in shared memory
@@ -464,10 +465,12 @@ static EncodeTiledFn get_encode_fn()
 
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream, double *D2, int64_t ldd2, int32_t col_tile_begin, int32_t col_tile_end)
+                 cudaStream_t stream, double *D2, int64_t ldd2, int32_t col_tile_begin, int32_t col_tile_end,
+                 int32_t n_rows_override, int32_t flush_stages)
 {
     if (N == 0) return FUF_OK;
-    const int32_t n = ctx->n;
+    if (flush_stages <= 0) flush_stages = FLUSH_STAGES;
+    const int32_t n = n_rows_override > 0 ? n_rows_override : ctx->n;
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
     FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise: PT must be 16-byte aligned");
     FUF_REQUIRE(tiles_per_dim < (1 << 20), "fuf_pairwise: N too large");
@@ -540,7 +543,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     int32_t best_s = 1;
     {
         int64_t best_cost = INT64_MAX;
-        const int32_t max_s = std::max(1, std::min(64, stages_total / (2 * FLUSH_STAGES)));
+        const int32_t max_s = std::max(1, std::min(64, stages_total / (2 * flush_stages)));
         for (int32_t s = 1; s <= max_s; s++) {
             const int64_t per = (stages_total + s - 1) / s;
             const int64_t waves = ((int64_t)n_tiles * s + ctx->sm_count - 1) / ctx->sm_count;
@@ -554,7 +557,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     // split boundaries fall on fp32 flush boundaries, so the set of 256-entry fp32 partial sums of a pair does
     // not depend on the number of splits (only the order of the final double additions does)
     int32_t per_split = (stages_total + best_s - 1) / best_s;
-    per_split = (per_split + FLUSH_STAGES - 1) / FLUSH_STAGES * FLUSH_STAGES;
+    per_split = (per_split + flush_stages - 1) / flush_stages * flush_stages;
     const int32_t splits = (stages_total + per_split - 1) / per_split;  // no empty split
 
     size_t tiles_bytes = ((size_t)n_tiles * sizeof(TileDesc) + 255) & ~(size_t)255;
@@ -573,6 +576,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     p.splits = splits;
     p.stages_total = stages_total;
     p.stages_per_split = per_split;
+    p.flush_stages = flush_stages;
     p.shard = shard_cols;
     p.N = N;
     p.D = D;
@@ -649,7 +653,7 @@ extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ld
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_f32(ctx, PT, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd, flags,
-                        (cudaStream_t)stream, nullptr, 0, 0, 0);
+                        (cudaStream_t)stream, nullptr, 0, 0, 0, 0, 0);
 }
 
 extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D,

@@ -31,6 +31,7 @@ struct RefineParams {
     int64_t ldd2;
     int mirror;                // also write D[j,i]
     int64_t j_begin, j_end;    // only pairs with j in [j_begin, j_end) are examined
+    int linear;                // criterion D < kappa (s_i + s_j) on the raw statistic, whatever the mode
     unsigned long long *counter;
 };
 
@@ -62,7 +63,8 @@ refine_kernel(const RefineParams p)
         if (gi >= p.N) continue;
         const int64_t j0 = p.j_begin + seg * RSEG;
         if (j0 + RSEG <= gi + 1) continue;  // entirely on or below the diagonal
-        const double si = MODE == FUF_MODE_L2 ? sqrt(p.stat[gi]) : p.stat[gi];
+        const bool square = (MODE == FUF_MODE_L2) && !p.linear;
+        const double si = square ? sqrt(p.stat[gi]) : p.stat[gi];
         double *drow = p.D + row * p.ldd;
 #pragma unroll 1
         for (int u = 0; u < RSEG / 32; u++) {
@@ -70,9 +72,9 @@ refine_kernel(const RefineParams p)
             bool flag = false;
             if (gj > gi && gj < p.j_end) {
                 const double d = drow[gj];
-                const double sj = MODE == FUF_MODE_L2 ? sqrt(p.stat[gj]) : p.stat[gj];
+                const double sj = square ? sqrt(p.stat[gj]) : p.stat[gj];
                 const double b = si + sj;
-                flag = MODE == FUF_MODE_L2 ? !(d >= p.kappa * b * b) : !(d >= p.kappa * b);
+                flag = square ? !(d >= p.kappa * b * b) : !(d >= p.kappa * b);
                 if (b == 0.0) flag = false;  // both samples exactly representable in fp32: nothing to gain
             }
             unsigned mask = __ballot_sync(0xffffffffu, flag);
@@ -120,7 +122,7 @@ refine_kernel(const RefineParams p)
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2, int64_t j_begin, int64_t j_end,
-           bool reset_counter)
+           bool reset_counter, int criterion)
 {
     if (!ctx->d_refined) FUF_CUDA(cudaMalloc((void **)&ctx->d_refined, sizeof(unsigned long long)));
     if (reset_counter) FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
@@ -136,7 +138,8 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
     p.n = ctx->n;
     p.N = N;
     p.stat = err_stat;
-    p.kappa = kappa > 0 ? kappa : (mode == FUF_MODE_L2 ? 1.6e13 : 2e6);
+    p.linear = (criterion == FUF_CRIT_LINEAR);
+    p.kappa = kappa > 0 ? kappa : (p.linear ? 0.02 : (mode == FUF_MODE_L2 ? 1.6e13 : 2e6));
     p.D = D;
     p.ldd = ldd;
     p.D2 = D2;
@@ -174,11 +177,12 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
 using namespace fuf;
 
 extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard,
-                          int64_t shard_stride, int mode, const double *err_stat, double kappa,
+                          int64_t shard_stride, int mode, const double *err_stat, double kappa, int criterion,
                           const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream)
 {
     FUF_REQUIRE(ctx && err_stat && D, "fuf_refine: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_refine: bad mode %d", mode);
+    FUF_REQUIRE(criterion == FUF_CRIT_ROUNDING || criterion == FUF_CRIT_LINEAR, "fuf_refine: bad criterion %d", criterion);
     FUF_REQUIRE(N >= 0 && ldd >= N && N < ((int64_t)1 << 31), "fuf_refine: bad shape N=%lld ldd=%lld", (long long)N,
                 (long long)ldd);
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_refine: n_tile_rows without tile_rows_h");
@@ -189,7 +193,7 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
         FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
-                  (cudaStream_t)stream, nullptr, 0, 0, N, true);
+                  (cudaStream_t)stream, nullptr, 0, 0, N, true, criterion);
 }
 
 extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)

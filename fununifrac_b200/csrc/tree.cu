@@ -312,6 +312,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     cudaFree(ctx->d_refined);
     ctx->ws_center.release();
     ctx->ws_rows.release();
+    ctx->ws_gram.release();
     ctx->ws_p64.release();
     ctx->ws_push.release();
     ctx->ws_pair.release();
@@ -325,6 +326,8 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto &ev : ctx->ev_band) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_gram)
+        if (ev) cudaEventDestroy(ev);
     cudaGetLastError();
     delete ctx;
     return FUF_OK;

@@ -20,9 +20,11 @@ MODE_L1, MODE_L2 = 0, 1
 F32, F64 = 0, 1
 TILE = 128
 PW_SCALAR_MATH = 1
-AP_VALIDATE, AP_NO_REFINE = 1, 2
+AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
+GRAM_MIN_SAMPLES = 512
 CENTER_SAMPLES = 32
-ABI_VERSION = 2
+ABI_VERSION = 3
+CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -61,7 +63,9 @@ def load_library() -> ctypes.CDLL:
         L.fuf_push_up_center.argtypes = [vp, vp, ci, i64, i64, ci, vp, vp]
         L.fuf_center_of_pushed.argtypes = [vp, vp, i64, i64, vp, vp]
         L.fuf_round_pushed.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64, vp, i64, vp]
-        L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, vp, i32, vp, i64, vp]
+        L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, ci, vp, i32, vp, i64, vp]
+        L.fuf_pairwise_gram.argtypes = [vp, vp, i64, i64, ci, vp, vp, vp, vp, i64, vp]
+        L.fuf_gram_last_kernel.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
         L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
@@ -76,6 +80,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
                      "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count",
+                     "fuf_pairwise_gram", "fuf_gram_last_kernel",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci
@@ -220,16 +225,51 @@ class TreeContext:
             job.P64T = P64T
         return job
 
-    def distances(self, job: "Pushed", mode: int, D=None):
-        """Full symmetric D of a pushed job: fp32 tile kernel, then the float64 refinement pass when the job
-        carries float64 profiles."""
+    def distances(self, job: "Pushed", mode: int, D=None, gram: Optional[bool] = None):
+        """Full symmetric D of a pushed job: fp32 tile kernel (or, for --L2 from 512 samples on, the tensor-core
+        Gram kernel), then the float64 refinement pass when the job carries float64 profiles."""
+        if gram is None:
+            gram = mode == MODE_L2 and job.N >= GRAM_MIN_SAMPLES and job.P64T is not None
+        if gram:
+            return self.distances_gram(job, D=D)
         D = self.pairwise(job.PT, job.N, mode, D=D)
         if job.P64T is not None and job.N > 1:
             self.refine(job.P64T, job.N, mode, job.err_stat, D)
         return D
 
+    def pairwise_gram(self, PT, N: int, D=None, err_stat=None):
+        """``fuf_pairwise_gram``: --L2 distances on the tcgen05 tensor cores.  Returns (D, q, err_out): q = squared
+        norms of the re-centred operands (statistic of the linear refinement), err_out = their rounding statistic."""
+        torch = _torch()
+        assert PT.dtype == torch.float32 and PT.dim() == 2 and PT.stride(1) == 1
+        if D is None:
+            D = torch.zeros((N, N), dtype=torch.float64, device=PT.device)
+        q = torch.zeros(max(N, 1), dtype=torch.float64, device=PT.device)
+        err_out = torch.zeros(max(N, 1), dtype=torch.float64, device=PT.device)
+        _check(self._lib.fuf_pairwise_gram(self.handle, PT.data_ptr(), N, PT.stride(0), MODE_L2,
+                                           None if err_stat is None else err_stat.data_ptr(), q.data_ptr(),
+                                           err_out.data_ptr(), D.data_ptr(), D.stride(0), _stream_ptr(torch)),
+               "fuf_pairwise_gram")
+        return D, q, err_out
+
+    def gram_last_kernel(self) -> Tuple[float, float]:
+        """(milliseconds, executed MMA flops) of the last tcgen05 tile kernel launch."""
+        ms, fl = ctypes.c_float(), ctypes.c_double()
+        _check(self._lib.fuf_gram_last_kernel(self.handle, ctypes.byref(ms), ctypes.byref(fl)), "fuf_gram_last_kernel")
+        return ms.value, fl.value
+
+    def distances_gram(self, job: "Pushed", D=None):
+        """--L2 through the Gram kernel + both refinement passes (needs a job pushed with refine=True)."""
+        assert job.P64T is not None, "the Gram path needs the float64 profiles for its refinement pass"
+        D, q, err = self.pairwise_gram(job.PT, job.N, D=D, err_stat=job.err_stat)
+        if job.N > 1:
+            self.refine(job.P64T, job.N, MODE_L2, q, D, criterion=CRIT_LINEAR)
+            self.gram_refined = self.refine_count()
+            self.refine(job.P64T, job.N, MODE_L2, err, D)
+        return D
+
     def refine(self, P64T, N: int, mode: int, err_stat, D, tile_rows: Optional[Sequence[int]] = None,
-               shard: int = 0, shard_stride: int = 0, kappa: float = 0.0):
+               shard: int = 0, shard_stride: int = 0, kappa: float = 0.0, criterion: int = 0):
         """``fuf_refine``: recompute in float64 the pairs of D the fp32 operands cannot certify (in place)."""
         torch = _torch()
         assert err_stat.dtype == torch.float64 and D.dtype == torch.float64
@@ -238,7 +278,7 @@ class TreeContext:
         ldp = P64T.stride(0) if (shard == 0 and P64T is not None) else 0
         _check(self._lib.fuf_refine(self.handle, None if P64T is None else P64T.data_ptr(), N, ldp, shard,
                                     shard_stride, mode,
-                                    err_stat.data_ptr(), float(kappa),
+                                    err_stat.data_ptr(), float(kappa), int(criterion),
                                     rows_arr.ctypes.data if rows_arr is not None else None,
                                     0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),
                                     _stream_ptr(torch)), "fuf_refine")
@@ -334,7 +374,7 @@ class TreeContext:
 
     # -- host-buffer entry point ------------------------------------------------------------------
     def all_pairs_host(self, X: np.ndarray, mode: int, D: Optional[np.ndarray] = None, validate: bool = False,
-                       refine: bool = True) -> np.ndarray:
+                       refine: bool = True, gram: bool = True) -> np.ndarray:
         """``fuf_all_pairs_host``: host profiles X[N, n] (float32/float64, C-order) → host D[N, N] float64."""
         _torch()
         if X.dtype not in (np.float32, np.float64):
@@ -350,7 +390,8 @@ class TreeContext:
             raise ValueError("D must be a C-ordered float64 [N, N] array")
         _check(self._lib.fuf_all_pairs_host(self.handle, X.ctypes.data, F32 if X.dtype == np.float32 else F64, N,
                                             X.strides[0] // X.itemsize, mode, D.ctypes.data, D.strides[0] // 8,
-                                            (AP_VALIDATE if validate else 0) | (0 if refine else AP_NO_REFINE)),
+                                            (AP_VALIDATE if validate else 0) | (0 if refine else AP_NO_REFINE) |
+                                            (0 if gram else AP_NO_GRAM)),
                "fuf_all_pairs_host")
         return D
 

@@ -15,6 +15,7 @@
  *                           pairwise_computation (layout change only)
  *   fuf_pairwise         <- pairwise_computation (no diffab) =          src/algorithms/emd_unifrac.py:42-54
  *                           get_L1 / get_L2 over all i<j                src/objects/profile_vector.py:9-19
+ *   fuf_pairwise_gram    <- same for is_L2, as a Gram matrix on the tcgen05 tensor cores
  *   fuf_pairwise_f64     <- same, float64 validation mode
  *   fuf_refine           <- get_L1 / get_L2 in float64 for the pairs    src/objects/profile_vector.py:9-19
  *                           the fp32 operands cannot certify to 1e-6
@@ -50,7 +51,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 2
+#define FUF_ABI_VERSION 3
 
 /* error codes */
 #define FUF_OK 0
@@ -71,7 +72,14 @@ extern "C" {
 #define FUF_AP_VALIDATE 1  /* float64 validation kernels instead of the fp32 production path */
 #define FUF_AP_NO_REFINE 2 /* production path without the float64 refinement pass */
 
+#define FUF_GRAM_MIN_SAMPLES 512 /* fuf_all_pairs_host uses the tensor-core Gram path for FUF_MODE_L2 from this N on */
+#define FUF_AP_NO_GRAM 4   /* FUF_MODE_L2 through the direct (a-b)^2 kernel whatever N */
+
 #define FUF_CENTER_SAMPLES 32 /* fuf_all_pairs_host centres on the pushed mean of the first min(N, 32) samples */
+
+/* fuf_refine criteria */
+#define FUF_CRIT_ROUNDING 0 /* err_stat = rounding statistics of fuf_push_up; L1: D < kappa (s_i+s_j), L2: D < kappa (sqrt s_i + sqrt s_j)^2 */
+#define FUF_CRIT_LINEAR 1   /* D < kappa (s_i + s_j) on any per-sample statistic (the Gram path passes squared norms) */
 
 /* fuf_pairwise flags */
 #define FUF_PW_SCALAR_MATH 1 /* use scalar FADD instead of packed FADD2/FFMA2 (A/B switch for profiling) */
@@ -151,6 +159,24 @@ int fuf_round_pushed(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64,
 int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags, void *stream);
 
+/* --L2 on the tensor cores: D[i,j] = q_i + q_j - 2 (A A^T)[i,j], A = PT minus its node-wise mean over the samples,
+ * with the Gram matrix computed by tcgen05.mma (kind::tf32, three products per term on hi/lo TF32 splits of the
+ * fp32 operands, fp32 accumulation in tensor memory over 256 basis entries, float64 across); the 512 node columns of largest
+ * energy go through the direct fp32 kernel instead (their products are where 3xTF32 is not accurate enough).
+ *   PT       device float, node-major, ld ldp (any centre; centred profiles lose less in the second rounding)
+ *   err_in   device, N doubles or NULL: the L2 rounding statistic of PT from fuf_push_up
+ *   q        device, N doubles, out: squared norms of A (the statistic of the follow-up linear refinement)
+ *   err_out  device, N doubles or NULL, out: rounding statistic of A = (sqrt err_in + sqrt(own rounding))^2
+ *   D        full symmetric N x N, zero diagonal.
+ * Follow with fuf_refine(err_stat = q, criterion = FUF_CRIT_LINEAR) and fuf_refine(err_stat = err_out).
+ * mode must be FUF_MODE_L2. */
+int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int mode, const double *err_in, double *q,
+                      double *err_out, double *D, int64_t ldd, void *stream);
+
+/* Device time of the tcgen05 tile kernel of the last fuf_pairwise_gram call (CUDA events on its stream; waits for
+ * it) and the MMA flops it executed (3 products x 2 x 128 x 128 x padded n per tile) — for the tensor-pipe roofline. */
+int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_flops);
+
 /* Validation mode: everything in double. Full matrix only. */
 int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
                      void *stream);
@@ -159,13 +185,14 @@ int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, i
  * like PT): every pair i<j with
  *     L1: D[i,j] < kappa (err_stat[i] + err_stat[j])          L2: D[i,j] < kappa (sqrt err_stat[i] + sqrt err_stat[j])^2
  * is recomputed from P64T in double and overwritten (with its mirror when tile_rows_h == NULL).
- * kappa <= 0 selects the default (2e6 / 1.6e13: rounding of the fp32 operands may cost at most 0.5e-6 relative).
+ * kappa <= 0 selects the default (2e6 / 1.6e13: rounding of the fp32 operands may cost at most 0.5e-6 relative;
+ * 0.02 for FUF_CRIT_LINEAR).
  * P64T == NULL: count-only mode (D is not modified) — lets several GPUs agree on whether the float64 profiles
  * have to be exchanged at all.
  * fuf_refine_count synchronises the stream and returns how many pairs the last fuf_refine recomputed. */
 int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
-               const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
-               int64_t ldd, void *stream);
+               const double *err_stat, double kappa, int criterion, const int32_t *tile_rows_h, int32_t n_tile_rows,
+               double *D, int64_t ldd, void *stream);
 int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
 
 /* Join compact row blocks (as written by fuf_pairwise with tile_rows_h, possibly gathered from several

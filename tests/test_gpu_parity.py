@@ -271,6 +271,61 @@ def test_near_duplicates_are_refined(full_tree):
 
 
 # --------------------------------------------------------------------------------------------------
+# --L2 on the tensor cores (tcgen05 Gram kernel + direct part + refinement)
+# --------------------------------------------------------------------------------------------------
+def test_gram_exact_on_small_integers():
+    """Rank-1 integer profiles: every product and sum is exact in TF32/fp32, so D must be exactly (i - j)^2 —
+    pins the shared-memory / instruction descriptors, the swizzle and the TMEM read-out, for nodes in different
+    swizzle rows and pipeline stages."""
+    n, N = 70, 300
+    parent = np.full(n, n - 1, np.int32)
+    parent[-1] = -1
+    ctx = engine.TreeContext(parent, np.ones(n))
+    idx = np.arange(N, dtype=np.float64)
+    for k0 in (0, 1, 9, 33, 69):
+        PT = torch.zeros((n, engine.padded_samples(N)), dtype=torch.float32, device="cuda")
+        PT[k0, :N] = torch.arange(1, N + 1, dtype=torch.float32, device="cuda")
+        D, q, err = ctx.pairwise_gram(PT, N)
+        assert np.array_equal(D.cpu().numpy(), (idx[:, None] - idx[None, :]) ** 2), k0
+        assert float(err.abs().max()) == 0.0     # nothing was rounded
+
+
+def test_gram_vs_oracle(full_tree):
+    inp, ctx, leaves = full_tree
+    N = 640                                   # 5 tile rows, the last one 128 wide; above the Gram threshold
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=12)
+    rng = np.random.default_rng(12)
+    for base, copies, jitter in ((0, 4, 1e-3), (300, 3, 1e-5), (500, 3, 0.0)):
+        for c in range(1, copies):
+            X[base + c] = X[base] * (1 + jitter * rng.random(ctx.n))
+            X[base + c] /= X[base + c].sum()
+    Dref = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, X, True), True)
+    job = ctx.push_up_job(torch.from_numpy(X).cuda(), engine.MODE_L2)
+    raw = ctx.pairwise_gram(job.PT, N, err_stat=job.err_stat)[0].cpu().numpy()
+    D = ctx.distances(job, engine.MODE_L2)                      # N >= 512: routed to the Gram path
+    assert ctx.gram_refined >= 7
+    D = D.cpu().numpy()
+    check_matrix(D)
+    assert rel_err(D, Dref) < REL
+    ordinary = Dref > 1e-2 * np.median(Dref)
+    assert (np.abs(raw - Dref)[ordinary] / Dref[ordinary]).max() < REL     # the tensor-core result itself
+    assert rel_err(raw, Dref) > REL                                        # near-duplicates need the refinement
+    assert D[500, 501] == 0 and D[501, 502] == 0
+    Dd = ctx.distances(job, engine.MODE_L2, gram=False).cpu().numpy()      # direct (a-b)^2 kernel
+    assert rel_err(Dd, Dref) < REL
+    Dh = ctx.all_pairs_host(X, engine.MODE_L2)                             # host path takes the Gram route too
+    assert np.array_equal(Dh, D)
+    Dh2 = ctx.all_pairs_host(X, engine.MODE_L2, gram=False)
+    assert np.array_equal(Dh2, Dd)
+    # unweighted profiles: counts in the thousands on the upper levels
+    Xu = X.copy()
+    Xu[Xu > 0] = 1
+    Dref = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, Xu, True), True)
+    D = ctx.distances(ctx.push_up_job(torch.from_numpy(Xu).cuda(), engine.MODE_L2), engine.MODE_L2).cpu().numpy()
+    assert rel_err(D, Dref) < REL
+
+
+# --------------------------------------------------------------------------------------------------
 # (3) size-independent properties at a larger size + edge cases
 # --------------------------------------------------------------------------------------------------
 def test_properties_large(full_tree):
