@@ -15,7 +15,8 @@
 //                             its total mass T[chunk] and chunk-local prefix sums CP at checkpoint positions.
 //   K1b pushup_span_kernel    spanning node k: S = tail of its first chunk + totals of the chunks in between
 //                             + head of its last chunk (same-sign terms only); writes w_k * S.
-//   K1c pushup_stat_kernel    sums the per-chunk rounding-error statistics of the fp32 outputs per sample.
+//   K1c pushup_stat_kernel    sums the per-chunk (and per-span-block) rounding-error statistics of the fp32 outputs per
+//                             sample, in fixed order.
 //
 // Production outputs per entry (all optional):
 //   PT    float, CENTRED:  (float)(w_k * S_k - c_k).  Distances are invariant under subtracting one fixed vector c
@@ -43,13 +44,13 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
                     int64_t ldp, double *__restrict__ P64T, int64_t ldp64, int64_t col0, double *__restrict__ T,
                     double *__restrict__ CP, double *__restrict__ R, int64_t ldt)
 {
-    // dynamic shared memory: acc[KT][TI] double | xs[KT][TI+1] TX   (48.5 KB float, 65 KB double)
+    // dynamic shared memory: one array S[KT][TI+1] of doubles (33 KB -> 6 CTAs per SM).  It first receives the X tile,
+    // transposed (coalesced global reads, conflict-free padded stores); each thread then lifts ITS sample's KT values
+    // into registers and reuses its own column of S as the accumulators of the replayed loop.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double(*acc)[TI] = reinterpret_cast<double(*)[TI]>(smem_raw);
-    TX(*xs)[TI + 1] = reinterpret_cast<TX(*)[TI + 1]>(smem_raw + sizeof(double) * KT * TI);
+    double(*S)[TI + 1] = reinterpret_cast<double(*)[TI + 1]>(smem_raw);
     __shared__ double s_w[KT], s_c[KT];
-    __shared__ int32_t s_pl[KT], s_cp[KT];
-    __shared__ uint8_t s_span[KT];
+    __shared__ int32_t s_meta[KT];  // (cp + 1) << 8 | span << 7 | (parent_local + 1); span = 1 beyond the tree
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t k0 = blockIdx.x * KT;
@@ -61,9 +62,7 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
         bool ok = tid < kt;
         s_w[tid] = ok ? w[k] : 0.0;
         s_c[tid] = (ok && center) ? center[k] : 0.0;
-        s_pl[tid] = ok ? parent_local[k] : -1;
-        s_cp[tid] = ok ? cp_after[k] : -1;
-        s_span[tid] = ok ? is_span[k] : 1;
+        s_meta[tid] = ok ? (((cp_after[k] + 1) << 8) | ((int32_t)is_span[k] << 7) | (parent_local[k] + 1)) : (1 << 7);
     }
     // coalesced load of the X tile: one warp request = one sample row segment of KT entries.  All TI/4 requests
     // of a warp are issued before the first value is used (32 x 256 B in flight per warp): the kernel streams
@@ -76,55 +75,80 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
             v[it] = (s < N && lane < kt) ? __ldcs(X + s * ldx + k0 + lane) : TX(0);
         }
 #pragma unroll
-        for (int it = 0; it < TI / 4; it++) xs[lane][it * 4 + warp] = v[it];
+        for (int it = 0; it < TI / 4; it++) S[lane][it * 4 + warp] = (double)v[it];
     }
-#pragma unroll
-    for (int kk = 0; kk < KT; kk++) acc[kk][tid] = 0.0;
     __syncthreads();
 
     const int64_t s = i0 + tid;
     if (s >= N) return;
+    double x[KT];
+#pragma unroll
+    for (int kk = 0; kk < KT; kk++) {
+        x[kk] = S[kk][tid];
+        S[kk][tid] = 0.0;  // from here on: sum of the already processed children of node kk
+    }
     double r = 0.0;    // running sum of X over the chunk (chunk-local prefix)
     double err = 0.0;  // rounding-error statistic of the float outputs of this chunk
-    for (int kk = 0; kk < kt; kk++) {
-        double x = (double)xs[kk][tid];
-        double S = x + acc[kk][tid];
-        r += x;
-        int pl = s_pl[kk];
-        if (pl >= 0) acc[pl][tid] += S;
-        if (!s_span[kk]) {
-            const double v = s_w[kk] * S;
-            if (P64T) P64T[(int64_t)(k0 + kk) * ldp64 + col0 + s] = v;
-            if (PT) {
+    float *pt = PT ? PT + (int64_t)k0 * ldp + col0 + s : nullptr;          // walks down the node rows
+    double *p64 = P64T ? P64T + (int64_t)k0 * ldp64 + col0 + s : nullptr;
+    double *cps = CP + s;
+    double *mine = &S[0][tid];
+#pragma unroll
+    for (int kk = 0; kk < KT; kk++) {
+        const int32_t meta = s_meta[kk];
+        const double Sk = x[kk] + mine[kk * (TI + 1)];
+        r += x[kk];
+        const int pl = (meta & 0x7f) - 1;
+        if (pl >= 0) mine[pl * (TI + 1)] += Sk;
+        if (!(meta & 0x80)) {
+            const double v = s_w[kk] * Sk;
+            if (p64) *p64 = v;
+            if (pt) {
                 const double c = v - s_c[kk];
                 const float f = (float)c;
-                PT[(int64_t)(k0 + kk) * ldp + col0 + s] = f;
+                *pt = f;
                 const double e = c - (double)f;
                 err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
             }
         }
-        int cp = s_cp[kk];
-        if (cp >= 0) CP[(int64_t)cp * ldt + s] = r;
+        const int cp = (meta >> 8) - 1;
+        if (cp >= 0) cps[(int64_t)cp * ldt] = r;
+        if (pt) pt += ldp;
+        if (p64) p64 += ldp64;
     }
     if (T) T[(int64_t)blockIdx.x * ldt + s] = r;
     if (R) R[(int64_t)blockIdx.x * ldt + s] = err;
 }
 
-// R[c][s] (per-chunk error statistics) -> their sum in err_stat[col0 + s] (overwritten; the span kernel adds its
-// own share afterwards).
-__global__ void pushup_stat_kernel(const double *__restrict__ R, int32_t n_chunks, int64_t N, int64_t ldt,
-                                   double *__restrict__ err_stat, int64_t col0)
+// err_stat[col0 + s] = sum of the per-chunk error statistics R[c][s] and of the span kernel's per-block partials
+// R2[b][s].  32 samples x 8 chunk ranges per block, combined in fixed order: bit-reproducible.
+__global__ void __launch_bounds__(256)
+pushup_stat_kernel(const double *__restrict__ R, int32_t n_chunks, const double *__restrict__ R2, int32_t n_span_blocks,
+                   int64_t N, int64_t ldt, double *__restrict__ err_stat, int64_t col0)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= N) return;
+    __shared__ double part[8][33];
+    const int sx = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * 32 + sx;
     double e[4] = {0.0, 0.0, 0.0, 0.0};
-    int c = 0;
-    for (; c + 4 <= n_chunks; c += 4) {
+    if (s < N) {
+        const int per = (n_chunks + 7) / 8;
+        const int c0 = py * per, c1 = min(n_chunks, c0 + per);
+        int c = c0;
+        for (; c + 4 <= c1; c += 4) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) e[u] += R[(int64_t)(c + u) * ldt + s];
+            for (int u = 0; u < 4; u++) e[u] += R[(int64_t)(c + u) * ldt + s];
+        }
+        for (; c < c1; c++) e[0] += R[(int64_t)c * ldt + s];
     }
-    for (; c < n_chunks; c++) e[0] += R[(int64_t)c * ldt + s];
-    err_stat[col0 + s] = (e[0] + e[1]) + (e[2] + e[3]);
+    part[py][sx] = (e[0] + e[1]) + (e[2] + e[3]);
+    __syncthreads();
+    if (py == 0 && s < N) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += part[q][sx];
+        for (int b = 0; b < n_span_blocks; b++) t += R2[(int64_t)b * ldt + s];
+        err_stat[col0 + s] = t;
+    }
 }
 
 template <int MODE>
@@ -132,7 +156,7 @@ __global__ void pushup_span_kernel(const SpanNode *__restrict__ span, int32_t n_
                                    const double *__restrict__ center, const double *__restrict__ T,
                                    const double *__restrict__ CP, int64_t ldt, int64_t N, float *__restrict__ PT,
                                    int64_t ldp, double *__restrict__ P64T, int64_t ldp64, int64_t col0,
-                                   double *__restrict__ err_stat)
+                                   double *__restrict__ R2)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
@@ -163,7 +187,7 @@ __global__ void pushup_span_kernel(const SpanNode *__restrict__ span, int32_t n_
             err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
         }
     }
-    if (err_stat && PT && err != 0.0) atomicAdd(&err_stat[col0 + s], err);
+    if (R2) R2[(int64_t)blockIdx.y * ldt + s] = err;
 }
 
 // Centre support: column mean of the first m rows (double), and the leaf mask.
@@ -329,11 +353,12 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
     }
     const int64_t ldt = (N + 31) / 32 * 32;
     const bool want_err = (err_stat != nullptr && PT != nullptr);
-    double *T = nullptr, *CP = nullptr, *R = nullptr;
+    const int span_blocks = ctx->n_span > 0 ? min(ctx->n_span, 64) : 0;
+    double *T = nullptr, *CP = nullptr, *R = nullptr, *R2 = nullptr;
     {
         size_t need = 0;
         if (ctx->n_span > 0) need += ((size_t)ctx->n_chunks + (size_t)ctx->n_cp) * (size_t)ldt * sizeof(double);
-        if (want_err) need += (size_t)ctx->n_chunks * (size_t)ldt * sizeof(double);
+        if (want_err) need += ((size_t)ctx->n_chunks + (size_t)span_blocks) * (size_t)ldt * sizeof(double);
         if (need) {
             int rc = ctx->ws_push.reserve(need);
             if (rc) return rc;
@@ -343,14 +368,16 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
                 CP = T + (size_t)ctx->n_chunks * ldt;
                 base = CP + (size_t)ctx->n_cp * ldt;
             }
-            if (want_err) R = base;
+            if (want_err) {
+                R = base;
+                R2 = R + (size_t)ctx->n_chunks * ldt;
+            }
         }
     }
     FUF_REQUIRE((N + TI - 1) / TI <= 65535, "fuf_push_up: N = %lld too large for one call (max %d)", (long long)N,
                 65535 * TI);
     dim3 grid(ctx->n_chunks, (unsigned)((N + TI - 1) / TI));
-    const size_t smem_f = sizeof(double) * KT * TI + sizeof(float) * KT * (TI + 1);
-    const size_t smem_d = sizeof(double) * KT * TI + sizeof(double) * KT * (TI + 1);
+    const size_t smem_f = sizeof(double) * KT * (TI + 1), smem_d = smem_f;
     static bool attr_set = false;
     if (!attr_set) {
         FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
@@ -371,21 +398,20 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
 #undef FUF_CHUNK
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    if (want_err) {
-        pushup_stat_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(R, ctx->n_chunks, N, ldt, err_stat, col0);
+    if (ctx->n_span > 0) {
+        dim3 g2((unsigned)((N + 127) / 128), (unsigned)span_blocks);
+        if (mode == FUF_MODE_L1)
+            pushup_span_kernel<FUF_MODE_L1><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
+                                                                    ldt, N, PT, ldp, P64T, ldp64, col0, R2);
+        else
+            pushup_span_kernel<FUF_MODE_L2><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
+                                                                    ldt, N, PT, ldp, P64T, ldp64, col0, R2);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
-    if (ctx->n_span > 0) {
-        dim3 g2((unsigned)((N + 127) / 128), (unsigned)min(ctx->n_span, 64));
-        if (mode == FUF_MODE_L1)
-            pushup_span_kernel<FUF_MODE_L1><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
-                                                                    ldt, N, PT, ldp, P64T, ldp64, col0,
-                                                                    want_err ? err_stat : nullptr);
-        else
-            pushup_span_kernel<FUF_MODE_L2><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
-                                                                    ldt, N, PT, ldp, P64T, ldp64, col0,
-                                                                    want_err ? err_stat : nullptr);
+    if (want_err) {
+        pushup_stat_kernel<<<(unsigned)((N + 31) / 32), 256, 0, stream>>>(R, ctx->n_chunks, R2, span_blocks, N, ldt,
+                                                                         err_stat, col0);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
