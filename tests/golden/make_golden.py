@@ -310,8 +310,46 @@ def golden_errors():
     shutil.rmtree(tmp)
 
 
+def golden_combined():
+    """fununifrac/compute_fununifrac_combined.py: one KO x sample table instead of gather files.  The table is built
+    from the three toy gather CSVs (median_abund) plus a KO that is not in the tree and an internal-node row; the
+    reference's own make_fununifrac_inputs / push_up_L1 / pairwise_computation produce the expected matrices —
+    including its quirk of pushing with L1 weights even when --L2 is given (:57-67)."""
+    sys.path.insert(0, os.path.join(REF, "fununifrac"))
+    import compute_fununifrac_combined as ref_comb
+    edge = os.path.join(REF, "data/small_edge_list_with_lengths.txt")
+    files = sorted(glob.glob(os.path.join(REF, "data", "*_gather.csv")))
+    cols = {}
+    for f in files:
+        df = pd.read_csv(f)
+        cols[os.path.basename(f).replace("_10_KOs_gather.csv", "")] = {
+            str(nm).split(":")[-1]: float(v) for nm, v in zip(df["name"], df["median_abund"])}
+    kos = sorted(set().union(*[set(c) for c in cols.values()])) + ["K99999_not_in_tree", "b"]
+    table = pd.DataFrame({c: [cols[c].get(k, 0.0) for k in kos] for c in cols}, index=pd.Index(kos, name="name"))
+    table.loc["K99999_not_in_tree"] = [1.0, 0.0, 2.0]      # counts in the normalisation, then skipped with a warning
+    table.loc["b"] = [0.0, 3.0, 0.0]                        # mass placed on an internal node
+    table.to_csv(os.path.join(DATA, "small_combined_table.csv"))
+    solver = EarthMoverDistanceUniFracSolver()
+    tree = ref_make_tree.import_graph(edge, directed=True)
+    inp = ref_make_emd_input.tree_to_EMDU_input(tree, "ko00001")
+    sample_df = pd.read_csv(os.path.join(DATA, "small_combined_table.csv"), index_col="name")
+    X, PP = [], {}
+    for col in sample_df.columns:
+        with contextlib.redirect_stdout(io.StringIO()):
+            P = ref_comb.make_fununifrac_inputs(sample_df[col], inp)
+            assert np.array_equal(P, ref_make_emd_input.extend_vector(sample_df[col], inp))
+        X.append(P.copy())
+        PP[col] = solver.push_up_L1(P, inp)
+    out = {"columns": np.array(list(sample_df.columns)), "X": np.array(X),
+           "P": np.array([PP[c] for c in sample_df.columns])}
+    out["D_l1"], _ = solver.pairwise_computation(PP, sample_df.columns, inp, False, False)
+    out["D_l2_quirk"], _ = solver.pairwise_computation(PP, sample_df.columns, inp, False, True)
+    np.savez(os.path.join(HERE, "combined.npz"), **out)
+
+
 if __name__ == "__main__":
     copy_fixtures()
+    golden_combined()
     golden_trees()
     golden_toy()
     golden_synth_mid()

@@ -545,3 +545,22 @@ def test_cli_end_to_end(data_dir, golden_dir, tmp_path):
         compute_fununifrac.main(base[:8] + ["-b", "not_a_brite", "-a", "median_abund"])
     with pytest.raises(Exception):
         compute_fununifrac.main(["-e", edge, "-fd", str(tmp_path), "-o", out])     # no matching files
+
+
+def test_combined_table_cli(data_dir, golden_dir, tmp_path):
+    """Second caller of the path (reference fununifrac/compute_fununifrac_combined.py): one KO x sample table.
+    Expected matrices come from the reference itself, including its L1-push-up-with---L2 quirk."""
+    from fununifrac_b200 import compute_fununifrac_combined as comb
+    z = np.load(os.path.join(golden_dir, "combined.npz"))
+    edge = os.path.join(data_dir, "small_edge_list_with_lengths.txt")
+    table = os.path.join(data_dir, "small_combined_table.csv")
+    out = str(tmp_path)
+    comb.main(["-e", edge, "-f", table, "-o", out, "-b", "ko00001"])
+    D = np.load(os.path.join(out, "fununifrac_out.npy"))
+    assert D.dtype == np.float64 and rel_err(D, z["D_l1"]) < REL
+    with open(os.path.join(out, "fununifrac_out.basis.npy")) as f:
+        assert [l.strip() for l in f] == list(z["columns"])
+    comb.main(["-e", edge, "-f", table, "-o", out, "-i", "t2", "--L2", "--diffab", "--unweighted", "--Ppushed"])
+    assert rel_err(np.load(os.path.join(out, "t2.npy")), z["D_l2_quirk"]) < REL
+    comb.main(["-e", edge, "-f", table, "-o", out, "-i", "t3", "--L2", "--validate"])
+    assert rel_err(np.load(os.path.join(out, "t3.npy")), z["D_l2_quirk"]) < 1e-12

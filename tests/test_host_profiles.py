@@ -84,3 +84,22 @@ def test_extend_vector(toy):
     P = make_emd_input.extend_vector(s, toy)
     idx = toy.node_to_idx()
     assert P[idx["d"]] == 2.0 / 9.0 and P[idx["f"]] == 6.0 / 9.0 and P.sum() == pytest.approx(8 / 9)
+
+
+def test_combined_table_to_matrix(data_dir, golden_dir, capsys):
+    """Combined KO x sample table (fununifrac/compute_fununifrac_combined.py:13-27, make_emd_input.extend_vector):
+    the vectorised table reader and the per-column function against vectors produced by the reference."""
+    import pandas as pd
+    from fununifrac_b200 import compute_fununifrac_combined as comb
+    z = np.load(os.path.join(golden_dir, "combined.npz"))
+    tree = make_tree.import_graph(os.path.join(data_dir, "small_edge_list_with_lengths.txt"))
+    inp = make_emd_input.tree_to_EMDU_input(tree, "ko00001")
+    df = pd.read_csv(os.path.join(data_dir, "small_combined_table.csv"), index_col="name")
+    assert list(df.columns) == list(z["columns"])
+    X = comb.table_to_matrix(df, inp)
+    assert "K99999_not_in_tree not found in EMDU index" in capsys.readouterr().out
+    assert np.array_equal(X, z["X"])
+    for i, col in enumerate(df.columns):
+        assert np.array_equal(comb.make_fununifrac_inputs(df[col], inp), z["X"][i])
+        assert np.array_equal(make_emd_input.extend_vector(df[col], inp), z["X"][i])
+    assert not np.isclose(X.sum(1), 1).all()      # the KO outside the tree took part in the normalisation
