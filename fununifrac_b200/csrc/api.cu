@@ -110,7 +110,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         if (use_gram) {
             // --L2 on the tensor cores: the Gram kernel needs every sample (node means), so no banding here
             double *qg = stat + ldp, *eg = qg + ldp;
-            rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, stat, qg, eg, D_dev, N, sk);
+            rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, 0, 0, stat, qg, eg, nullptr, 0, D_dev, N, sk);
             if (rc) return rc;
             if (do_refine) {
                 rc = refine(ctx, P64T, N, ldp, 0, 0, mode, qg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,

@@ -59,6 +59,15 @@ constexpr int GRAM_DIRECT_ROWS = 512;       // node columns routed through the d
 
 struct Tile {
     int32_t ti, tj;
+    int32_t out_row0;  // first row of this tile row in the output buffer
+    int32_t pad;
+};
+
+// Where sample s of a node-major operand lives: element (k, s) at base[(s / S) * SS + k * LD + s % S].
+// Single block: S = padded sample count, SS = 0, LD = ldp.  All-gathered shards [G][n][S]: SS = shard stride, LD = S.
+struct Lay {
+    int64_t S, SS, LD;
+    __host__ __device__ int64_t at(int64_t k, int64_t s) const { return (s / S) * SS + k * LD + s % S; }
 };
 
 struct Params {
@@ -66,6 +75,7 @@ struct Params {
     int32_t n_tiles;
     int32_t stages_total;  // ceil(n / KC)
     int32_t flush_stages;  // fp32 accumulation length in tensor memory, in stages
+    int32_t S;             // samples per operand shard (a multiple of 128)
     int64_t N;
     const double *q;
     double *D;
@@ -100,11 +110,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         if (spin > (1u << 26)) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor).  MN-major 32-bit operands have exactly one legal
@@ -199,7 +209,8 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             uint32_t it = 0;
             for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
                 const Tile tl = p.tiles[t];
-                const int ia = tl.ti * TILE, ib = tl.tj * TILE;
+                const int ia = (tl.ti * TILE) % p.S, ga = (tl.ti * TILE) / p.S;
+                const int ib = (tl.tj * TILE) % p.S, gb = (tl.tj * TILE) / p.S;
                 for (int st = 0; st < p.stages_total; ++st, ++it) {
                     const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * slot, phase ^ 1u);
@@ -208,10 +219,10 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                     const uint32_t dst = base + slot * STAGE_BYTES;
 #pragma unroll
                     for (int b = 0; b < TILE / BOX_W; b++) {
-                        tma_load_2d(dst + 0 * OPER_BYTES + b * BOX_BYTES, &map_hi, full, ia + b * BOX_W, st * KC);
-                        tma_load_2d(dst + 1 * OPER_BYTES + b * BOX_BYTES, &map_lo, full, ia + b * BOX_W, st * KC);
-                        tma_load_2d(dst + 2 * OPER_BYTES + b * BOX_BYTES, &map_hi, full, ib + b * BOX_W, st * KC);
-                        tma_load_2d(dst + 3 * OPER_BYTES + b * BOX_BYTES, &map_lo, full, ib + b * BOX_W, st * KC);
+                        tma_load_3d(dst + 0 * OPER_BYTES + b * BOX_BYTES, &map_hi, full, ia + b * BOX_W, st * KC, ga);
+                        tma_load_3d(dst + 1 * OPER_BYTES + b * BOX_BYTES, &map_lo, full, ia + b * BOX_W, st * KC, ga);
+                        tma_load_3d(dst + 2 * OPER_BYTES + b * BOX_BYTES, &map_hi, full, ib + b * BOX_W, st * KC, gb);
+                        tma_load_3d(dst + 3 * OPER_BYTES + b * BOX_BYTES, &map_lo, full, ib + b * BOX_W, st * KC, gb);
                     }
                 }
             }
@@ -280,7 +291,7 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             const int64_t gi = (int64_t)tl.ti * TILE + row, gj0 = (int64_t)tl.tj * TILE + half * 64;
             if (gi < p.N) {
                 const double qi = p.q[gi];
-                double *drow = p.D + gi * p.ldd + gj0;
+                double *drow = p.D + ((int64_t)tl.out_row0 + row) * p.ldd + gj0;
 #pragma unroll
                 for (int e = 0; e < 64; e++) {
                     const int64_t gj = gj0 + e;
@@ -299,20 +310,20 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 
 // mean[k] = (1/N) sum_s PT[k][s] and energy[k] = sum_s (PT[k][s] - mean[k])^2, in double, one warp per node row.
 __global__ void __launch_bounds__(256)
-gram_mean_kernel(const float *__restrict__ PT, int64_t ldp, int64_t N, int32_t n, float *__restrict__ mean,
+gram_mean_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32_t n, float *__restrict__ mean,
                  float *__restrict__ energy)
 {
     const int32_t k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= n) return;
     const int lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int64_t s = lane; s < N; s += 32) acc += (double)PT[(int64_t)k * ldp + s];
+    for (int64_t s = lane; s < N; s += 32) acc += (double)PT[lay.at(k, s)];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const float m = (float)(acc / (double)N);
     double e = 0.0;
     for (int64_t s = lane; s < N; s += 32) {
-        const double d = (double)PT[(int64_t)k * ldp + s] - (double)m;
+        const double d = (double)PT[lay.at(k, s)] - (double)m;
         e = fma(d, d, e);
     }
 #pragma unroll
@@ -326,35 +337,38 @@ gram_mean_kernel(const float *__restrict__ PT, int64_t ldp, int64_t N, int32_t n
 // a = fl32(PT - mean) = hi + lo with hi, lo representable in TF32 (10 explicit mantissa bits);
 // q[block][s] = sum_k a^2 (Gram columns only) and r2[block][s] = sum_k (rounding error of a)^2 over the block's nodes.
 __global__ void __launch_bounds__(256)
-gram_prep_kernel(const float *__restrict__ PT, int64_t ldp, int64_t N, int32_t n, int32_t k_per_block,
-                 const float *__restrict__ mean, const int32_t *__restrict__ direct_slot, float *__restrict__ HI,
-                 float *__restrict__ LO, float *__restrict__ SUB, double *__restrict__ q, double *__restrict__ r2)
+gram_prep_kernel(const float *__restrict__ PT, const Lay lay, const Lay ws, const Lay sub, int64_t n_cols, int64_t N,
+                 int32_t n, int32_t k_per_block, const float *__restrict__ mean, const int32_t *__restrict__ direct_slot,
+                 float *__restrict__ HI, float *__restrict__ LO, float *__restrict__ SUB, double *__restrict__ q,
+                 double *__restrict__ r2)
 {
+    // s runs over every sample slot of the workspace planes (padding slots are written as zeros)
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= ldp) return;
+    if (s >= n_cols) return;
+    const int64_t ldp = n_cols;  // row length of the partial-statistics arrays
     const int32_t k0 = blockIdx.y * k_per_block, k1 = min(n, k0 + k_per_block);
     double acc = 0.0, err = 0.0;
     for (int32_t k = k0; k < k1; k++) {
         float a = 0.f;
         if (s < N) {
-            const double c = (double)PT[(int64_t)k * ldp + s] - (double)mean[k];
+            const double c = (double)PT[lay.at(k, s)] - (double)mean[k];
             a = (float)c;
             const double e = c - (double)a;
             err = fma(e, e, err);
         }
         const int32_t slot = direct_slot[k];
         if (slot >= 0) {  // this node column goes through the direct fp32 kernel
-            SUB[(int64_t)slot * ldp + s] = a;
-            HI[(int64_t)k * ldp + s] = 0.f;
-            LO[(int64_t)k * ldp + s] = 0.f;
+            SUB[sub.at(slot, s)] = a;
+            HI[ws.at(k, s)] = 0.f;
+            LO[ws.at(k, s)] = 0.f;
             continue;
         }
         uint32_t hb, lb;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
         const float hi = __uint_as_float(hb);
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
-        HI[(int64_t)k * ldp + s] = hi;
-        LO[(int64_t)k * ldp + s] = __uint_as_float(lb);
+        HI[ws.at(k, s)] = hi;
+        LO[ws.at(k, s)] = __uint_as_float(lb);
         acc = fma((double)a, (double)a, acc);
     }
     // per-(node block) partials, summed in fixed order by gram_stat_kernel: bit-reproducible norms
@@ -422,22 +436,25 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const float *ptr, int64_t N, int32_t n, int64_t ldp)
+static int make_map(CUtensorMap *map, const float *ptr, int64_t N, int32_t n, const Lay &ws)
 {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) {
         set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled is not available from this driver");
         return FUF_ECUDA;
     }
-    const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)n};  // samples beyond N / nodes beyond n read as zero
-    const cuuint64_t gstride[1] = {(cuuint64_t)ldp * sizeof(float)};
-    const cuuint32_t box[2] = {BOX_W, KC}, estr[2] = {1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, gdim, gstride, box, estr,
+    // dims (sample in shard, node, shard); samples beyond N / nodes beyond n read as zero (the planes are zero there)
+    const int64_t n_shards = ws.SS ? (N + ws.S - 1) / ws.S : 1;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(ws.SS ? ws.S : N), (cuuint64_t)n, (cuuint64_t)n_shards};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ws.LD * sizeof(float),
+                                   (cuuint64_t)(ws.SS ? ws.SS : ws.LD * (int64_t)n) * sizeof(float)};
+    const cuuint32_t box[3] = {BOX_W, KC, 1}, estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)ptr, gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld n=%d ldp=%lld)", (int)r,
-                  (long long)N, n, (long long)ldp);
+        set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld n=%d S=%lld)", (int)r,
+                  (long long)N, n, (long long)ws.S);
         return FUF_ECUDA;
     }
     return FUF_OK;
@@ -445,38 +462,64 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t N, int32_t n, in
 
 }  // namespace gram
 
-int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, const double *err_in, double *q,
-                  double *err_out, double *D, int64_t ldd, cudaStream_t stream)
+int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
+                  const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
+                  double *D, int64_t ldd, cudaStream_t stream)
 {
     using namespace gram;
     if (N == 0) return FUF_OK;
     const int32_t n = ctx->n;
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
-    FUF_REQUIRE(((uintptr_t)PT & 15) == 0 && ldp % 4 == 0 && ldp >= N,
-                "fuf_pairwise_gram: PT must be 16-byte aligned with ldp %% 4 == 0 and ldp >= N");
-    // workspace: HI | LO (n x ldp floats each) | SUB (n_direct x ldp) | mean, energy (n floats) | slot (n ints)
-    //            | r2 (N doubles) | tile list
+    FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise_gram: PT must be 16-byte aligned");
+    Lay lay, ws, sub;
     const int32_t n_direct = std::min<int32_t>(n, GRAM_DIRECT_ROWS);
     const int32_t n_direct_pad = (n_direct + 15) / 16 * 16;
+    int64_t n_cols;  // sample slots of the workspace planes
+    if (shard == 0) {
+        FUF_REQUIRE(ldp % 4 == 0 && ldp >= N, "fuf_pairwise_gram: ldp=%lld must be a multiple of 4 and >= N=%lld",
+                    (long long)ldp, (long long)N);
+        n_cols = tiles_per_dim * TILE;
+        lay = Lay{ldp, 0, ldp};
+        ws = Lay{n_cols, 0, n_cols};
+        sub = Lay{n_cols, 0, n_cols};
+    } else {
+        FUF_REQUIRE(shard % TILE == 0 && shard > 0 && shard_stride >= shard * (int64_t)n,
+                    "fuf_pairwise_gram: bad shard layout (shard=%lld stride=%lld)", (long long)shard,
+                    (long long)shard_stride);
+        const int64_t n_shards = (N + shard - 1) / shard;
+        n_cols = n_shards * shard;
+        lay = Lay{shard, shard_stride, shard};
+        ws = Lay{shard, (int64_t)n * shard, shard};
+        sub = Lay{shard, (int64_t)n_direct_pad * shard, shard};
+    }
+    // workspace: HI | LO (n x n_cols floats each) | SUB (n_direct x n_cols) | mean, energy (n floats) | slot (n ints)
+    //            | partial norms and rounding statistics | tile list
     auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
-    const size_t plane = up((size_t)n * ldp * sizeof(float)), sub_bytes = up((size_t)n_direct_pad * ldp * sizeof(float));
+    const size_t plane = up((size_t)n * n_cols * sizeof(float)), sub_bytes = up((size_t)n_direct_pad * n_cols * sizeof(float));
     const int32_t k_per_block = 512, n_parts = (n + k_per_block - 1) / k_per_block;
-    const size_t vec_bytes = up((size_t)n * sizeof(float)), part_bytes = up((size_t)n_parts * ldp * sizeof(double));
+    const size_t vec_bytes = up((size_t)n * sizeof(float)), part_bytes = up((size_t)n_parts * n_cols * sizeof(double));
     std::vector<Tile> tiles;
-    for (int32_t ti = 0; ti < tiles_per_dim; ti++)
-        for (int32_t tj = ti; tj < tiles_per_dim; tj++) tiles.push_back(Tile{ti, tj});
+    const bool full = (tile_rows_h == nullptr);
+    const int32_t n_rows = full ? (int32_t)tiles_per_dim : n_tile_rows;
+    for (int32_t c = 0; c < n_rows; c++) {
+        const int32_t t = full ? c : tile_rows_h[c];
+        FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise_gram: tile row %d out of range [0,%lld)", t,
+                    (long long)tiles_per_dim);
+        for (int32_t tj = t; tj < tiles_per_dim; tj++) tiles.push_back(Tile{t, tj, full ? t * TILE : c * TILE, 0});
+    }
+    if (tiles.empty()) return FUF_OK;
     const size_t tiles_bytes = tiles.size() * sizeof(Tile);
     int rc = ctx->ws_gram.reserve(2 * plane + sub_bytes + 3 * vec_bytes + 2 * part_bytes + tiles_bytes);
     if (rc) return rc;
-    char *ws = (char *)ctx->ws_gram.ptr;
-    float *HI = (float *)ws, *LO = (float *)(ws + plane), *SUB = (float *)(ws + 2 * plane);
-    float *mean = (float *)(ws + 2 * plane + sub_bytes), *energy = (float *)((char *)mean + vec_bytes);
+    char *wsp = (char *)ctx->ws_gram.ptr;
+    float *HI = (float *)wsp, *LO = (float *)(wsp + plane), *SUB = (float *)(wsp + 2 * plane);
+    float *mean = (float *)(wsp + 2 * plane + sub_bytes), *energy = (float *)((char *)mean + vec_bytes);
     int32_t *d_slot = (int32_t *)((char *)mean + 2 * vec_bytes);
     double *qpart = (double *)((char *)mean + 3 * vec_bytes), *r2part = (double *)((char *)qpart + part_bytes);
     Tile *d_tiles = (Tile *)((char *)r2part + part_bytes);
     FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles_bytes, cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemsetAsync(SUB, 0, sub_bytes, stream));
-    gram_mean_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, ldp, N, n, mean, energy);
+    gram_mean_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, mean, energy);
     FUF_CUDA(cudaGetLastError());
     // the n_direct node columns of largest energy -> direct kernel (host selection: n floats, once per call)
     std::vector<float> h_energy(n);
@@ -492,25 +535,28 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, const d
     FUF_CUDA(cudaMemcpyAsync(d_slot, h_slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaStreamSynchronize(stream));
     {
-        dim3 g((unsigned)((ldp + 255) / 256), (unsigned)n_parts);
-        gram_prep_kernel<<<g, 256, 0, stream>>>(PT, ldp, N, n, k_per_block, mean, d_slot, HI, LO, SUB, qpart, r2part);
+        dim3 g((unsigned)((n_cols + 255) / 256), (unsigned)n_parts);
+        gram_prep_kernel<<<g, 256, 0, stream>>>(PT, lay, ws, sub, n_cols, N, n, k_per_block, mean, d_slot, HI, LO, SUB,
+                                                qpart, r2part);
         FUF_CUDA(cudaGetLastError());
-        gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(qpart, r2part, n_parts, ldp, err_in, N, q, err_out);
+        gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(qpart, r2part, n_parts, n_cols, err_in, N, q, err_out);
         FUF_CUDA(cudaGetLastError());
     }
-    // direct part first: D = sum over the selected node columns of (a_i - a_j)^2, both triangles
+    // direct part first: D = sum over the selected node columns of (a_i - a_j)^2
     // (fp32 partial sums over 16 entries only: these columns carry most of the magnitude)
-    rc = pairwise_f32(ctx, SUB, N, ldp, 0, 0, FUF_MODE_L2, nullptr, 0, D, ldd, 0, stream, nullptr, 0, 0, 0, n_direct_pad, 1);
+    rc = pairwise_f32(ctx, SUB, N, n_cols, shard ? shard : 0, shard ? sub.SS : 0, FUF_MODE_L2, tile_rows_h, n_tile_rows, D,
+                      ldd, 0, stream, nullptr, 0, 0, 0, n_direct_pad, 1);
     if (rc) return rc;
     ctx->launches += 3;
     CUtensorMap map_hi, map_lo;
-    if ((rc = make_map(&map_hi, HI, N, n, ldp)) || (rc = make_map(&map_lo, LO, N, n, ldp))) return rc;
+    if ((rc = make_map(&map_hi, HI, N, n, ws)) || (rc = make_map(&map_lo, LO, N, n, ws))) return rc;
     Params p;
     p.tiles = d_tiles;
     p.n_tiles = (int32_t)tiles.size();
     p.stages_total = (n + KC - 1) / KC;
     p.flush_stages = FLUSH_STAGES;
     if (getenv("FUF_GRAM_FLUSH")) p.flush_stages = std::max(1, atoi(getenv("FUF_GRAM_FLUSH")));
+    p.S = (int32_t)ws.S;
     p.N = N;
     p.q = q;
     p.D = D;
@@ -527,7 +573,7 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, const d
     FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], stream));
     ctx->gram_flops = 3.0 * 2.0 * TILE * TILE * (double)p.stages_total * KC * (double)p.n_tiles;
     ctx->launches += 1;
-    {
+    if (full) {
         const unsigned b = (unsigned)((N + 31) / 32);
         mirror_kernel<<<dim3(b, b), 256, 0, stream>>>(D, N, ldd);
         FUF_CUDA(cudaGetLastError());
@@ -552,12 +598,15 @@ extern "C" int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_fl
     return FUF_OK;
 }
 
-extern "C" int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int mode, const double *err_in,
-                                 double *q, double *err_out, double *D, int64_t ldd, void *stream)
+extern "C" int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard,
+                                 int64_t shard_stride, int mode, const double *err_in, double *q, double *err_out,
+                                 const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream)
 {
     FUF_REQUIRE(ctx && PT && q && D, "fuf_pairwise_gram: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L2, "fuf_pairwise_gram: only FUF_MODE_L2 has a Gram form (got mode %d)", mode);
     FUF_REQUIRE(N >= 0 && ldd >= N, "fuf_pairwise_gram: bad shape N=%lld ldd=%lld", (long long)N, (long long)ldd);
     FUF_CUDA(cudaSetDevice(ctx->device));
-    return pairwise_gram(ctx, PT, N, ldp, err_in, q, err_out, D, ldd, (cudaStream_t)stream);
+    FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise_gram: n_tile_rows without tile_rows_h");
+    return pairwise_gram(ctx, PT, N, ldp, shard, shard_stride, err_in, q, err_out, tile_rows_h, n_tile_rows, D, ldd,
+                         (cudaStream_t)stream);
 }

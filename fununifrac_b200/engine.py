@@ -64,7 +64,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_center_of_pushed.argtypes = [vp, vp, i64, i64, vp, vp]
         L.fuf_round_pushed.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64, vp, i64, vp]
         L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, ci, vp, i32, vp, i64, vp]
-        L.fuf_pairwise_gram.argtypes = [vp, vp, i64, i64, ci, vp, vp, vp, vp, i64, vp]
+        L.fuf_pairwise_gram.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, vp, vp, vp, i32, vp, i64, vp]
         L.fuf_gram_last_kernel.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
         L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
@@ -237,19 +237,26 @@ class TreeContext:
             self.refine(job.P64T, job.N, mode, job.err_stat, D)
         return D
 
-    def pairwise_gram(self, PT, N: int, D=None, err_stat=None):
+    def pairwise_gram(self, PT, N: int, D=None, err_stat=None, tile_rows: Optional[Sequence[int]] = None,
+                      shard: int = 0, shard_stride: int = 0):
         """``fuf_pairwise_gram``: --L2 distances on the tcgen05 tensor cores.  Returns (D, q, err_out): q = squared
-        norms of the re-centred operands (statistic of the linear refinement), err_out = their rounding statistic."""
+        norms of the re-centred operands (statistic of the linear refinement), err_out = their rounding statistic.
+        ``tile_rows`` / ``shard`` as in ``pairwise``."""
         torch = _torch()
-        assert PT.dtype == torch.float32 and PT.dim() == 2 and PT.stride(1) == 1
+        assert PT.dtype == torch.float32 and PT.stride(-1) == 1
+        rows_arr = None if tile_rows is None else np.ascontiguousarray(tile_rows, dtype=np.int32)
         if D is None:
-            D = torch.zeros((N, N), dtype=torch.float64, device=PT.device)
+            nrows = N if rows_arr is None else len(rows_arr) * TILE
+            D = torch.zeros((nrows, N), dtype=torch.float64, device=PT.device)
         q = torch.zeros(max(N, 1), dtype=torch.float64, device=PT.device)
         err_out = torch.zeros(max(N, 1), dtype=torch.float64, device=PT.device)
-        _check(self._lib.fuf_pairwise_gram(self.handle, PT.data_ptr(), N, PT.stride(0), MODE_L2,
+        ldp = PT.stride(0) if shard == 0 else 0
+        _check(self._lib.fuf_pairwise_gram(self.handle, PT.data_ptr(), N, ldp, shard, shard_stride, MODE_L2,
                                            None if err_stat is None else err_stat.data_ptr(), q.data_ptr(),
-                                           err_out.data_ptr(), D.data_ptr(), D.stride(0), _stream_ptr(torch)),
-               "fuf_pairwise_gram")
+                                           err_out.data_ptr(),
+                                           rows_arr.ctypes.data if rows_arr is not None else None,
+                                           0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),
+                                           _stream_ptr(torch)), "fuf_pairwise_gram")
         return D, q, err_out
 
     def gram_last_kernel(self) -> Tuple[float, float]:

@@ -16,7 +16,7 @@ The compute calls are injected (``ops``) so that the partition / exchange logic 
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence  # noqa: F401
 
 TILE = 128
 
@@ -57,9 +57,12 @@ class ShardedAllPairs:
     ``refine=True`` also exchanges the float64 profiles and runs the float64 refinement pass on this rank's rows.
     """
 
-    def __init__(self, ops, N: int, mode: int, world: int = 1, rank: int = 0, dist=None, refine: bool = True):
+    def __init__(self, ops, N: int, mode: int, world: int = 1, rank: int = 0, dist=None, refine: bool = True,
+                 gram: Optional[bool] = None):
         self.ops, self.N, self.mode, self.world, self.rank, self.dist = ops, N, mode, world, rank, dist
         self.do_refine = refine
+        # --L2 from 512 samples on: tensor-core Gram kernel (its refinement needs the float64 profiles)
+        self.use_gram = (mode == 1 and N >= 512 and refine) if gram is None else bool(gram)
         self.shard = shard_size(N, world)
         self.lo, self.hi = sample_range(N, world, rank)
         self.all_rows = [owned_tile_rows(N, world, r) for r in range(world)]
@@ -84,6 +87,16 @@ class ShardedAllPairs:
                 for r in range(world):
                     self.slot_rows += self.all_rows[r] + [-1] * (self.max_rows - len(self.all_rows[r]))
 
+    def _pairwise(self, rows, D):
+        """Distances of this rank's tile rows (all rows when ``rows`` is None) into D; returns the refinement
+        criteria to apply afterwards as (statistic, criterion) pairs."""
+        ops, N, sh, stride = self.ops, self.N, self.shard, self.ops.n * self.shard
+        if self.use_gram:
+            q, err = ops.pairwise_gram(self.PS, N, self.stat, rows, sh, stride, D)
+            return [(q, 1), (err, 0)]            # linear criterion on the Gram norms, then the rounding criterion
+        ops.pairwise(self.PS, N, self.mode, rows, sh, stride, D)
+        return [(self.stat, 0)]
+
     def step(self, X_local, mark=None):
         """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
         ``mark(name)`` is called at the phase boundaries (bench.py records CUDA events there)."""
@@ -102,33 +115,34 @@ class ShardedAllPairs:
         mark("push_end")
         if self.world == 1:
             mark("pair_begin")
-            ops.pairwise(self.PS, N, mode, None, sh, stride, self.D)
+            crit = self._pairwise(None, self.D)
             mark("pair_end")
             if self.do_refine:
-                ops.refine(self.P64S, N, mode, self.stat, self.D, None, sh, stride)
+                for stat, criterion in crit:
+                    ops.refine(self.P64S, N, mode, stat, self.D, None, sh, stride, criterion)
             mark("end")
             return self.D
         self.dist.all_gather_into_tensor(self.PS.view(-1), self.PS[r].reshape(-1))
         self.dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
         mark("pair_begin")
-        if self.rows:
-            ops.pairwise(self.PS, N, mode, self.rows, sh, stride, self.blocks)
+        crit = self._pairwise(self.rows, self.blocks) if self.rows else []
         mark("pair_end")
         if self.do_refine:
             # the float64 profiles (2x the fp32 volume) cross NVLink only if some rank has a pair to refine
-            mine = ops.count_uncertified(N, mode, self.stat, self.blocks, self.rows) if self.rows else 0
+            mine = sum(ops.count_uncertified(N, mode, stat, self.blocks, self.rows, criterion) for stat, criterion in crit)
             self.flagged[0] = mine
             self.dist.all_reduce(self.flagged)
             self.last_flagged = int(self.flagged.item())
             if self.last_flagged > 0:
                 self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
-                if self.rows:
-                    ops.refine(self.P64S, N, mode, self.stat, self.blocks, self.rows, sh, stride)
+                for stat, criterion in crit:
+                    ops.refine(self.P64S, N, mode, stat, self.blocks, self.rows, sh, stride, criterion)
         self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
         if r == 0:
             ops.assemble(self.gathered, self.slot_rows, N, self.D)
         mark("end")
         return self.D
+
 
 
 class CudaOps:
@@ -152,11 +166,17 @@ class CudaOps:
     def pairwise(self, PT, N, mode, tile_rows, shard, shard_stride, D):
         return self.ctx.pairwise(PT, N, mode, D=D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)
 
-    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride):
-        return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)
+    def pairwise_gram(self, PT, N, err_stat, tile_rows, shard, shard_stride, D):
+        _, q, err = self.ctx.pairwise_gram(PT, N, D=D, err_stat=err_stat, tile_rows=tile_rows, shard=shard,
+                                           shard_stride=shard_stride)
+        return q, err
 
-    def count_uncertified(self, N, mode, err_stat, D, tile_rows):
-        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows)
+    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, criterion=0):
+        return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride,
+                               criterion=criterion)
+
+    def count_uncertified(self, N, mode, err_stat, D, tile_rows, criterion=0):
+        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, criterion=criterion)
         return self.ctx.refine_count()
 
     def assemble(self, blocks, rows, N, D):

@@ -167,11 +167,13 @@ int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
  *   err_in   device, N doubles or NULL: the L2 rounding statistic of PT from fuf_push_up
  *   q        device, N doubles, out: squared norms of A (the statistic of the follow-up linear refinement)
  *   err_out  device, N doubles or NULL, out: rounding statistic of A = (sqrt err_in + sqrt(own rounding))^2
- *   D        full symmetric N x N, zero diagonal.
+ *   shard, shard_stride, tile_rows_h, n_tile_rows: as in fuf_pairwise (all-gathered shards; compact row blocks)
+ *   D        full symmetric N x N with zero diagonal, or compact upper row blocks when tile_rows_h != NULL.
  * Follow with fuf_refine(err_stat = q, criterion = FUF_CRIT_LINEAR) and fuf_refine(err_stat = err_out).
  * mode must be FUF_MODE_L2. */
-int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int mode, const double *err_in, double *q,
-                      double *err_out, double *D, int64_t ldd, void *stream);
+int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
+                      const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
+                      double *D, int64_t ldd, void *stream);
 
 /* Device time of the tcgen05 tile kernel of the last fuf_pairwise_gram call (CUDA events on its stream; waits for
  * it) and the MMA flops it executed (3 products x 2 x 128 x 128 x padded n per tile) — for the tensor-pipe roofline. */

@@ -317,6 +317,29 @@ def test_gram_vs_oracle(full_tree):
     assert np.array_equal(Dh, D)
     Dh2 = ctx.all_pairs_host(X, engine.MODE_L2, gram=False)
     assert np.array_equal(Dh2, Dd)
+    # compact tile rows on the all-gathered shard layout (the multi-GPU form), then assembled
+    shard, G, T = 256, 3, 5
+    PS = torch.zeros((G, ctx.n, shard), dtype=torch.float32, device="cuda")
+    P64S = torch.zeros((G, ctx.n, shard), dtype=torch.float64, device="cuda")
+    stat = torch.zeros(G * shard, dtype=torch.float64, device="cuda")
+    Xd = torch.from_numpy(X).cuda()
+    for g in range(G):
+        w = min(shard, N - g * shard)
+        ctx.push_up(Xd[g * shard:g * shard + w], engine.MODE_L2, PS[g], 0, job.center, P64S[g],
+                    stat[g * shard:(g + 1) * shard])
+    blocks, rows = [], []
+    for own in ([0, 3, 4], [1, 2]):
+        blk, q, err = ctx.pairwise_gram(PS, N, err_stat=stat, tile_rows=own, shard=shard, shard_stride=ctx.n * shard)
+        ctx.refine(P64S, N, engine.MODE_L2, q, blk, tile_rows=own, shard=shard, shard_stride=ctx.n * shard,
+                   criterion=engine.CRIT_LINEAR)
+        ctx.refine(P64S, N, engine.MODE_L2, err, blk, tile_rows=own, shard=shard, shard_stride=ctx.n * shard)
+        blocks.append(blk)
+        rows += own
+    Ds = ctx.assemble(torch.cat(blocks, 0), rows, N).cpu().numpy()
+    assert np.allclose(Ds, D, rtol=1e-12, atol=0) and rel_err(Ds, Dref) < REL
+    from fununifrac_b200 import sharded
+    one = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, engine.MODE_L2)
+    assert one.use_gram and np.allclose(one.step(Xd).cpu().numpy(), D, rtol=1e-12, atol=0)
     # unweighted profiles: counts in the thousands on the upper levels
     Xu = X.copy()
     Xu[Xu > 0] = 1
