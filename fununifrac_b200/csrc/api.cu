@@ -113,9 +113,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, 0, 0, stat, qg, eg, nullptr, 0, D_dev, N, sk);
             if (rc) return rc;
             if (do_refine) {
-                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, qg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,
-                            FUF_CRIT_LINEAR);
-                if (!rc) rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, false);
+                // one scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
+                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,
+                            FUF_CRIT_ROUNDING, qg, 0.0);
                 if (rc) return rc;
             }
             if (band_d2h) {

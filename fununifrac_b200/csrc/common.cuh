@@ -135,7 +135,8 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int64_t j_begin = 0,
-           int64_t j_end = 0, bool reset_counter = true, int criterion = 0);
+           int64_t j_end = 0, bool reset_counter = true, int criterion = 0, const double *lin_stat = nullptr,
+           double lin_kappa = 0.0);
 // diffab.cu
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                  int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);

@@ -472,7 +472,9 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
     FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise_gram: PT must be 16-byte aligned");
     Lay lay, ws, sub;
-    const int32_t n_direct = std::min<int32_t>(n, GRAM_DIRECT_ROWS);
+    int32_t n_direct = GRAM_DIRECT_ROWS;
+    if (getenv("FUF_GRAM_DIRECT")) n_direct = std::max(16, atoi(getenv("FUF_GRAM_DIRECT")));
+    n_direct = std::min<int32_t>(n, n_direct);
     const int32_t n_direct_pad = (n_direct + 15) / 16 * 16;
     int64_t n_cols;  // sample slots of the workspace planes
     if (shard == 0) {

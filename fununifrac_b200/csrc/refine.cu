@@ -32,6 +32,8 @@ struct RefineParams {
     int mirror;                // also write D[j,i]
     int64_t j_begin, j_end;    // only pairs with j in [j_begin, j_end) are examined
     int linear;                // criterion D < kappa (s_i + s_j) on the raw statistic, whatever the mode
+    const double *stat2;       // optional second statistic: additional linear criterion D < kappa2 (t_i + t_j)
+    double kappa2;
     unsigned long long *counter;
 };
 
@@ -65,6 +67,7 @@ refine_kernel(const RefineParams p)
         if (j0 + RSEG <= gi + 1) continue;  // entirely on or below the diagonal
         const bool square = (MODE == FUF_MODE_L2) && !p.linear;
         const double si = square ? sqrt(p.stat[gi]) : p.stat[gi];
+        const double ti = p.stat2 ? p.stat2[gi] : 0.0;
         double *drow = p.D + row * p.ldd;
 #pragma unroll 1
         for (int u = 0; u < RSEG / 32; u++) {
@@ -76,6 +79,7 @@ refine_kernel(const RefineParams p)
                 const double b = si + sj;
                 flag = square ? !(d >= p.kappa * b * b) : !(d >= p.kappa * b);
                 if (b == 0.0) flag = false;  // both samples exactly representable in fp32: nothing to gain
+                if (p.stat2) flag = flag || !(d >= p.kappa2 * (ti + p.stat2[gj]));
             }
             unsigned mask = __ballot_sync(0xffffffffu, flag);
             if (p.P64T == nullptr) {  // count-only mode
@@ -122,7 +126,7 @@ refine_kernel(const RefineParams p)
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2, int64_t j_begin, int64_t j_end,
-           bool reset_counter, int criterion)
+           bool reset_counter, int criterion, const double *lin_stat, double lin_kappa)
 {
     if (!ctx->d_refined) FUF_CUDA(cudaMalloc((void **)&ctx->d_refined, sizeof(unsigned long long)));
     if (reset_counter) FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
@@ -138,6 +142,8 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
     p.n = ctx->n;
     p.N = N;
     p.stat = err_stat;
+    p.stat2 = lin_stat;
+    p.kappa2 = lin_kappa > 0 ? lin_kappa : 0.02;
     p.linear = (criterion == FUF_CRIT_LINEAR);
     p.kappa = kappa > 0 ? kappa : (p.linear ? 0.02 : (mode == FUF_MODE_L2 ? 1.6e13 : 2e6));
     p.D = D;
@@ -178,7 +184,8 @@ using namespace fuf;
 
 extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard,
                           int64_t shard_stride, int mode, const double *err_stat, double kappa, int criterion,
-                          const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream)
+                          const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd,
+                          const double *lin_stat, double lin_kappa, void *stream)
 {
     FUF_REQUIRE(ctx && err_stat && D, "fuf_refine: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_refine: bad mode %d", mode);
@@ -193,7 +200,7 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
         FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
-                  (cudaStream_t)stream, nullptr, 0, 0, N, true, criterion);
+                  (cudaStream_t)stream, nullptr, 0, 0, N, true, criterion, lin_stat, lin_kappa);
 }
 
 extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)

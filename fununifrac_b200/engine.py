@@ -23,7 +23,7 @@ PW_SCALAR_MATH = 1
 AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 CENTER_SAMPLES = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -63,7 +63,8 @@ def load_library() -> ctypes.CDLL:
         L.fuf_push_up_center.argtypes = [vp, vp, ci, i64, i64, ci, vp, vp]
         L.fuf_center_of_pushed.argtypes = [vp, vp, i64, i64, vp, vp]
         L.fuf_round_pushed.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64, vp, i64, vp]
-        L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, ci, vp, i32, vp, i64, vp]
+        L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, ci, vp, i32, vp, i64, vp,
+                                 ctypes.c_double, vp]
         L.fuf_pairwise_gram.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, vp, vp, vp, i32, vp, i64, vp]
         L.fuf_gram_last_kernel.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
         L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
@@ -269,14 +270,14 @@ class TreeContext:
         """--L2 through the Gram kernel + both refinement passes (needs a job pushed with refine=True)."""
         assert job.P64T is not None, "the Gram path needs the float64 profiles for its refinement pass"
         D, q, err = self.pairwise_gram(job.PT, job.N, D=D, err_stat=job.err_stat)
-        if job.N > 1:
-            self.refine(job.P64T, job.N, MODE_L2, q, D, criterion=CRIT_LINEAR)
+        if job.N > 1:    # one scan: rounding criterion on err, linear criterion on the Gram norms q
+            self.refine(job.P64T, job.N, MODE_L2, err, D, lin_stat=q)
             self.gram_refined = self.refine_count()
-            self.refine(job.P64T, job.N, MODE_L2, err, D)
         return D
 
     def refine(self, P64T, N: int, mode: int, err_stat, D, tile_rows: Optional[Sequence[int]] = None,
-               shard: int = 0, shard_stride: int = 0, kappa: float = 0.0, criterion: int = 0):
+               shard: int = 0, shard_stride: int = 0, kappa: float = 0.0, criterion: int = 0, lin_stat=None,
+               lin_kappa: float = 0.0):
         """``fuf_refine``: recompute in float64 the pairs of D the fp32 operands cannot certify (in place)."""
         torch = _torch()
         assert err_stat.dtype == torch.float64 and D.dtype == torch.float64
@@ -288,6 +289,7 @@ class TreeContext:
                                     err_stat.data_ptr(), float(kappa), int(criterion),
                                     rows_arr.ctypes.data if rows_arr is not None else None,
                                     0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),
+                                    None if lin_stat is None else lin_stat.data_ptr(), float(lin_kappa),
                                     _stream_ptr(torch)), "fuf_refine")
         return D
 

@@ -89,13 +89,13 @@ class ShardedAllPairs:
 
     def _pairwise(self, rows, D):
         """Distances of this rank's tile rows (all rows when ``rows`` is None) into D; returns the refinement
-        criteria to apply afterwards as (statistic, criterion) pairs."""
+        statistics of the refinement scan to run afterwards: (rounding statistic, linear statistic or None)."""
         ops, N, sh, stride = self.ops, self.N, self.shard, self.ops.n * self.shard
         if self.use_gram:
             q, err = ops.pairwise_gram(self.PS, N, self.stat, rows, sh, stride, D)
-            return [(q, 1), (err, 0)]            # linear criterion on the Gram norms, then the rounding criterion
+            return err, q                        # rounding criterion + linear criterion on the Gram norms
         ops.pairwise(self.PS, N, self.mode, rows, sh, stride, D)
-        return [(self.stat, 0)]
+        return self.stat, None
 
     def step(self, X_local, mark=None):
         """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
@@ -115,28 +115,27 @@ class ShardedAllPairs:
         mark("push_end")
         if self.world == 1:
             mark("pair_begin")
-            crit = self._pairwise(None, self.D)
+            stat, lin = self._pairwise(None, self.D)
             mark("pair_end")
             if self.do_refine:
-                for stat, criterion in crit:
-                    ops.refine(self.P64S, N, mode, stat, self.D, None, sh, stride, criterion)
+                ops.refine(self.P64S, N, mode, stat, self.D, None, sh, stride, lin)
             mark("end")
             return self.D
         self.dist.all_gather_into_tensor(self.PS.view(-1), self.PS[r].reshape(-1))
         self.dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
         mark("pair_begin")
-        crit = self._pairwise(self.rows, self.blocks) if self.rows else []
+        stat, lin = self._pairwise(self.rows, self.blocks) if self.rows else (None, None)
         mark("pair_end")
         if self.do_refine:
             # the float64 profiles (2x the fp32 volume) cross NVLink only if some rank has a pair to refine
-            mine = sum(ops.count_uncertified(N, mode, stat, self.blocks, self.rows, criterion) for stat, criterion in crit)
+            mine = ops.count_uncertified(N, mode, stat, self.blocks, self.rows, lin) if self.rows else 0
             self.flagged[0] = mine
             self.dist.all_reduce(self.flagged)
             self.last_flagged = int(self.flagged.item())
             if self.last_flagged > 0:
                 self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
-                for stat, criterion in crit:
-                    ops.refine(self.P64S, N, mode, stat, self.blocks, self.rows, sh, stride, criterion)
+                if self.rows:
+                    ops.refine(self.P64S, N, mode, stat, self.blocks, self.rows, sh, stride, lin)
         self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
         if r == 0:
             ops.assemble(self.gathered, self.slot_rows, N, self.D)
@@ -171,12 +170,12 @@ class CudaOps:
                                            shard_stride=shard_stride)
         return q, err
 
-    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, criterion=0):
+    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, lin_stat=None):
         return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride,
-                               criterion=criterion)
+                               lin_stat=lin_stat)
 
-    def count_uncertified(self, N, mode, err_stat, D, tile_rows, criterion=0):
-        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, criterion=criterion)
+    def count_uncertified(self, N, mode, err_stat, D, tile_rows, lin_stat=None):
+        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, lin_stat=lin_stat)
         return self.ctx.refine_count()
 
     def assemble(self, blocks, rows, N, D):

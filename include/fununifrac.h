@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 3
+#define FUF_ABI_VERSION 4
 
 /* error codes */
 #define FUF_OK 0
@@ -169,7 +169,7 @@ int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
  *   err_out  device, N doubles or NULL, out: rounding statistic of A = (sqrt err_in + sqrt(own rounding))^2
  *   shard, shard_stride, tile_rows_h, n_tile_rows: as in fuf_pairwise (all-gathered shards; compact row blocks)
  *   D        full symmetric N x N with zero diagonal, or compact upper row blocks when tile_rows_h != NULL.
- * Follow with fuf_refine(err_stat = q, criterion = FUF_CRIT_LINEAR) and fuf_refine(err_stat = err_out).
+ * Follow with fuf_refine(err_stat = err_out, lin_stat = q).
  * mode must be FUF_MODE_L2. */
 int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                       const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
@@ -189,12 +189,14 @@ int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, i
  * is recomputed from P64T in double and overwritten (with its mirror when tile_rows_h == NULL).
  * kappa <= 0 selects the default (2e6 / 1.6e13: rounding of the fp32 operands may cost at most 0.5e-6 relative;
  * 0.02 for FUF_CRIT_LINEAR).
+ * lin_stat != NULL adds, in the same scan, the linear criterion D[i,j] < lin_kappa (lin_stat[i] + lin_stat[j])
+ * (lin_kappa <= 0: 0.02) — what the Gram path needs on top of the rounding criterion.
  * P64T == NULL: count-only mode (D is not modified) — lets several GPUs agree on whether the float64 profiles
  * have to be exchanged at all.
  * fuf_refine_count synchronises the stream and returns how many pairs the last fuf_refine recomputed. */
 int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
                const double *err_stat, double kappa, int criterion, const int32_t *tile_rows_h, int32_t n_tile_rows,
-               double *D, int64_t ldd, void *stream);
+               double *D, int64_t ldd, const double *lin_stat, double lin_kappa, void *stream);
 int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
 
 /* Join compact row blocks (as written by fuf_pairwise with tile_rows_h, possibly gathered from several

@@ -330,9 +330,8 @@ def test_gram_vs_oracle(full_tree):
     blocks, rows = [], []
     for own in ([0, 3, 4], [1, 2]):
         blk, q, err = ctx.pairwise_gram(PS, N, err_stat=stat, tile_rows=own, shard=shard, shard_stride=ctx.n * shard)
-        ctx.refine(P64S, N, engine.MODE_L2, q, blk, tile_rows=own, shard=shard, shard_stride=ctx.n * shard,
-                   criterion=engine.CRIT_LINEAR)
-        ctx.refine(P64S, N, engine.MODE_L2, err, blk, tile_rows=own, shard=shard, shard_stride=ctx.n * shard)
+        ctx.refine(P64S, N, engine.MODE_L2, err, blk, tile_rows=own, shard=shard, shard_stride=ctx.n * shard,
+                   lin_stat=q)
         blocks.append(blk)
         rows += own
     Ds = ctx.assemble(torch.cat(blocks, 0), rows, N).cpu().numpy()

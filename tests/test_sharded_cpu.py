@@ -81,11 +81,11 @@ class OracleOps:
             D[c * TILE:c * TILE + (r1 - r0), r0:] = torch.from_numpy(blk[:, r0:])
         return D
 
-    def count_uncertified(self, N, mode, err_stat, D, tile_rows, criterion=0):
+    def count_uncertified(self, N, mode, err_stat, D, tile_rows, lin_stat=None):
         assert err_stat.numel() >= N
         return 1 if 0 in tile_rows else 0          # pretend the rank that owns tile row 0 found one pair
 
-    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, criterion=0):
+    def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, lin_stat=None):
         self.refine_calls += 1
         assert P64T.shape[0] * P64T.shape[2] >= N and err_stat.numel() >= N
         return D
