@@ -115,7 +115,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             if (do_refine) {
                 // one scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
                 rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,
-                            FUF_CRIT_ROUNDING, qg, 0.0);
+                            FUF_CRIT_ROUNDING, qg, 2.9e-3);
                 if (rc) return rc;
             }
             if (band_d2h) {

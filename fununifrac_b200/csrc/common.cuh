@@ -93,7 +93,8 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_d;        // D on device when the host buffer cannot be written in place
     fuf::DeviceBuffer ws_center;   // column mean scratch of fuf_push_up_center
     fuf::DeviceBuffer ws_rows;     // tile-row list of fuf_refine
-    fuf::DeviceBuffer ws_gram;     // TF32 hi/lo planes + tile list of fuf_pairwise_gram
+    fuf::DeviceBuffer ws_gram;     // int8 digit planes + tables of fuf_pairwise_gram
+    fuf::DeviceBuffer ws_gram_small;  // column maxima
     fuf::DeviceBuffer ws_p64;      // P64T + centre + error statistics (fuf_all_pairs_host)
     unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine
     int64_t last_refined = 0;
@@ -102,6 +103,7 @@ struct fuf_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_gram[2] = {};       // around the last gram_tile_kernel launch
     double gram_flops = 0.0;           // MMA flops that launch executed
+    int gram_groups = 0;               // exponent buckets of the last Gram call
     std::vector<cudaEvent_t> ev_band;  // one per sample band of fuf_all_pairs_host
     float t_h2d_push = 0.f, t_pair = 0.f, t_total = 0.f;
 

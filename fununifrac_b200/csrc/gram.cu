@@ -1,39 +1,50 @@
-// gram.cu — --L2 all-pairs distances as a length-weighted Gram matrix on the tcgen05 tensor cores.
+// gram.cu — --L2 all-pairs distances as an ERROR-FREE integer Gram matrix on the tcgen05 tensor cores.
 //
 // Replaces, for is_L2, the pair loop of pairwise_computation (src/algorithms/emd_unifrac.py:49-54) with
 // get_L2 = sum_k (P_i[k] - P_j[k])^2 (src/objects/profile_vector.py:17-19) rewritten as
-//     D[i,j] = q_i + q_j - 2 G[i,j],     G = P' P'^T,     q_i = sum_k P'_i[k]^2,
-// where P' are the centred fp32 pushed profiles (sqrt(L) weights are already inside P, see pushup.cu; centring
-// is what keeps q_i + q_j - 2G from cancelling: for centred profiles G is small against q).
+//     D[i,j] = q_i + q_j - 2 G[i,j],     G = A A^T,     q_i = sum_k A_i[k]^2.
+// A Gram form cancels: for similar samples G ~ q and every relative error of G is amplified by q / D.  A first
+// version of this file used 3xTF32 floating-point MMAs; it measured 1e-7 on independent samples and 1e-5 on
+// correlated ones, because the tensor core's fp32 accumulation truncates (errors add up linearly with G).  The cure
+// is to make the arithmetic exact:
 //
-// K3c gram_mean_kernel   column (node) means of the operand over the samples: the Gram path centres EVERY node,
-//                        leaves included, so that the products a_k b_k have no common sign and the fp32 partial
-//                        sums in tensor memory stay small against q (distances do not depend on the centre).
-// K3p gram_prep_kernel   a = fl32(PT - mean); splits it into two TF32 numbers, a = hi + lo (hi = tf32(a),
-//                        lo = tf32(a-hi)); accumulates q_i and the extra rounding statistic in double.  HBM-bound.
-// K3  gram_tile_kernel   persistent, warp-specialised, one CTA per SM, 128x128 tiles of the upper triangle:
-//       warp 0   TMA producer: per stage (32 nodes) 16 boxes of 32 samples x 32 nodes, SWIZZLE_128B_ATOM_32B, into a
-//                3-stage 64 KB ring (A_hi, A_lo, B_hi, B_lo), full/empty mbarriers;
-//       warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::tf32, M = N = 128, K = 8,
-//                MN-major shared-memory descriptors; three products per k-block (hi*hi + hi*lo + lo*hi =
-//                "3xTF32", products exact in fp32, dropped lo*lo ~ 2^-22); accumulators in TMEM (2 x 128 columns,
-//                double-buffered), tcgen05.commit releases smem stages and hands accumulators to the epilogue;
-//       warps 4-11 epilogue (two warpgroups, setmaxnreg 232): every 256 nodes the fp32 accumulator tile is read
-//                with tcgen05.ld (32x32b.x32), widened and added to float64 accumulators held in REGISTERS
-//                (each thread owns one row x 64 columns = 64 doubles), so no fp32 sum ever sees more than 96
-//                tensor-core additions; at the end of the tile the thread writes q_i + q_j - 2G (512 B contiguous).
-// K3m mirror_kernel      lower triangle := transpose of the upper one, zero diagonal.
-// Hybrid split.  The few nodes near the root carry large, strongly correlated entries: for them the products
-// a_k b_k are of the order of q while their contribution to D is small, and the 2^-22 relative error of a 3xTF32
-// product shows (measured: 1.3e-6 on 1.8 %% of the nodes, 1.2e-7 on the rest).  The host therefore picks the
-// GRAM_DIRECT_ROWS node columns of largest energy sum_s a_k[s]^2; they are excluded from the Gram operands and go
-// through the direct fp32 tile kernel (pairwise.cu, K2) on a gathered copy — 1.7 %% of its full cost — whose
-// result the Gram epilogue adds.
-// The pairs the Gram form cannot certify (D small against q_i + q_j: near-duplicates) are recomputed by the
-// float64 refinement pass (refine.cu) with the linear criterion D < tau (q_i + q_j).
+//   * block fixed point along the basis.  Node columns are bucketed by the power of two of their largest entry and
+//     permuted so that a bucket is a contiguous range of basis rows (D does not depend on the order of the basis);
+//     within a bucket with scale S every entry is a / S in [-1, 1], written with four signed 8-bit digits
+//         a / S = (d0 + d1 / 254 + d2 / 254^2 + d3 / 254^3) / 127,      |d_p| <= 127      (32.6 bits below S;
+//     three digits were tried first: 24.6 bits below a scale that can exceed a typical entry by 16-64x left the
+//     refinement criterion flagging every pair, and the truncated product expansion showed at 1e-6)
+//   * integer MMAs.  tcgen05.mma kind::i8 (int8 x int8 -> int32 in tensor memory) computes the digit products by
+//     order,  c0 = d0 d0',  c1 = d0 d1' + d1 d0',  c2 = d1 d1' + d0 d2' + d2 d0',
+//             c3 = d0 d3' + d3 d0' + d1 d2' + d2 d1'      (10 MMAs per 32 basis rows)
+//     in four int32 accumulators; sums of at most 32K x 4 products of magnitude < 2^14 cannot overflow, so the
+//     accumulation is EXACT and needs no periodic flush; the dropped orders are below 3 x 254^-4 = 7e-10 of S^2.
+//   * per bucket, the epilogue adds S^2 (c0 + c1/254 + c2/254^2 + c3/254^3) / 127^2 into float64 accumulators in
+//     registers.
+// q_i is the same truncated digit form evaluated on (i, i) with the same operations in the same order
+// (gram_selfnorm_kernel), so D[i,j] = B(delta, delta) for the digit difference delta of the two samples: identical
+// samples give exactly 0, nothing cancels, and |D - exact squared distance of the quantised profiles| is at most
+// 2.9e-9 S^2 per column in which the two samples differ.  What is left is the quantisation of the inputs, which is
+// the same kind of error as rounding them to fp32 and is covered by the same refinement criterion (refine.cu) through
+// the per-sample statistic sum_k (a - a_quantised)^2 this file emits.
 //
-// Tensor-pipe accounting: executed MMA flops = 3 passes x 2 x 128 x 128 x n per tile; algorithmic flops = 2 n per pair.
+// K3c gram_colmax_kernel  largest |entry| of every node column (one warp per row).
+// K3p gram_digits_kernel  fp32 operand -> four int8 digit planes in permuted row order; the quantisation and scale
+//                         statistics in double.  HBM-bound, one pass.
+// K3q gram_selfnorm_kernel  q_i = the Gram form of sample i with itself, from the digit planes, bucket by bucket.
+// K3  gram_tile_kernel    persistent, warp-specialised, one CTA per SM, 128x128 tiles of the upper triangle:
+//       warp 0   TMA producer: per stage (64 basis rows) 8 boxes of 128 samples x 64 rows (A and B, four digit
+//                planes each; 1 byte per entry, SWIZZLE_128B), 3-stage 64 KB ring, full/empty mbarriers;
+//       warp 1   MMA issuer: one elected lane, M = N = 128, K = 32, MN-major descriptors, ten MMAs per 32 rows;
+//                tcgen05.commit frees smem stages and, at the end of a bucket, publishes the accumulators;
+//       warps 4-11 (two warpgroups, setmaxnreg 232) epilogue: tcgen05.ld of the four int32 accumulators, weighted
+//                into 64 float64 registers per thread; each accumulator is released as soon as it has been read, so
+//                the next bucket's MMAs stall only until the first one is drained.
+// K3m mirror_kernel       lower triangle := transpose of the upper one.
+//
+// Tensor-pipe accounting: executed int8 MACs = 10 x 128 x 128 x (padded n) per tile; algorithmic flops = 2 n per pair.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -43,19 +54,18 @@ namespace fuf {
 namespace gram {
 
 constexpr int TILE = FUF_TILE;              // 128 = UMMA M = UMMA N
-constexpr int KC = 32;                      // nodes per pipeline stage
-constexpr int KB = 8;                       // nodes per tcgen05.mma (kind::tf32: 32 bytes of K)
+constexpr int KC = 64;                      // basis rows per pipeline stage
+constexpr int KB = 32;                      // basis rows per tcgen05.mma (kind::i8: 32 bytes of K)
 constexpr int STAGES = 3;
-constexpr int FLUSH_STAGES = 8;             // fp32 accumulation length in TMEM: 8 stages = 256 nodes (96 MMA adds)
-constexpr int BOX_W = 32;                   // samples per TMA box (128 bytes: the swizzle span)
-constexpr uint32_t BOX_BYTES = BOX_W * KC * 4;              // 4 KB
-constexpr uint32_t OPER_BYTES = (TILE / BOX_W) * BOX_BYTES;  // 16 KB: one operand tile (128 samples x 32 nodes)
-constexpr uint32_t STAGE_BYTES = 4 * OPER_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int NDIG = 4;                     // digits per entry = accumulators (product orders 0..3)
+constexpr uint32_t PLANE_BYTES = TILE * KC;                 // 8 KB: one digit plane of one operand tile
+constexpr uint32_t STAGE_BYTES = 2 * NDIG * PLANE_BYTES;    // A d0..d3 | B d0..d3
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers + tmem ptr */;
 constexpr int NTHREADS = 384;               // warpgroup 0: warp 0 TMA, warp 1 MMA (2 idle); warpgroups 1-2: epilogue
 constexpr int NEPI_WARPS = 8;
-constexpr uint32_t TMEM_COLS = 256;         // two 128-column fp32 accumulators
-constexpr int GRAM_DIRECT_ROWS = 512;       // node columns routed through the direct fp32 kernel
+constexpr uint32_t TMEM_COLS = 512;         // four 128-column int32 accumulators: all of tensor memory
+constexpr double DIGIT0 = 127.0, DIGIT = 254.0;
+constexpr int GRAM_DIRECT_ROWS = 256;       // node columns of largest scale computed in float64 instead
 
 struct Tile {
     int32_t ti, tj;
@@ -70,12 +80,17 @@ struct Lay {
     __host__ __device__ int64_t at(int64_t k, int64_t s) const { return (s / S) * SS + k * LD + s % S; }
 };
 
+struct Group {
+    int32_t stage_end;  // one past the last stage of this bucket
+    int32_t pad;
+    double w0;          // S^2 / 127^2: weight of the class-0 accumulator (class p: w0 / 254^p)
+};
+
 struct Params {
     const Tile *tiles;
-    int32_t n_tiles;
-    int32_t stages_total;  // ceil(n / KC)
-    int32_t flush_stages;  // fp32 accumulation length in tensor memory, in stages
-    int32_t S;             // samples per operand shard (a multiple of 128)
+    const Group *groups;
+    int32_t n_tiles, n_groups;
+    int32_t S;  // samples per operand shard (a multiple of 128)
     int64_t N;
     const double *q;
     double *D;
@@ -117,26 +132,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor).  MN-major 32-bit operands have exactly one legal
-// layout: SWIZZLE_128B_BASE32B = rows of 128 B (32 samples) along MN, atoms of 4 node-rows (512 B), the 32-byte chunk
-// index XORed with (row % 4) — what the TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.
-//   [0,14) start >> 4 | [16,30) LBO >> 4 (between 32-sample blocks) | [32,46) SBO >> 4 (between 4-node atoms)
-//   | [46,48) version = 1 | [61,64) layout = 1 (SWIZZLE_128B_BASE32B)
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), MN-major 8-bit operand, SWIZZLE_128B: a row of the
+// plane is 128 samples = 128 bytes = the whole M (or N) extent; 8 basis rows form a 1 KB swizzle atom.
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (between 128-sample blocks: unused, M = 128) | [32,46) SBO >> 4 (between
+//   8-row atoms = 1 KB) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
 {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(BOX_BYTES >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-           (1ull << 46) | (1ull << 61);
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(PLANE_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c = F32, a = b = TF32, both MN-major, N = 128, M = 128.
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TILE >> 3) << 17) |
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c = S32 (2), a = b = signed INT8 (1), both MN-major,
+// N = 128, M = 128.
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TILE >> 3) << 17) |
                            ((uint32_t)(TILE >> 4) << 24);
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
         : "memory");
 }
@@ -160,14 +175,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p)
+gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                 const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3, const Params p)
 {
     extern __shared__ unsigned char smem_raw[];
-    // swizzle atoms must sit on their own size boundaries; 1,024 bytes covers every mode
+    // swizzle atoms must sit on their own size boundaries (1 KB)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + STAGES * STAGE_BYTES;
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
-    const uint32_t tmem_slot = tempty0 + 16;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tempty0 = tfull + 8;
+    const uint32_t tmem_slot = tempty0 + 8 * NDIG;
     volatile uint32_t *tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -177,10 +193,8 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             mbar_init(full0 + 8 * s, 1);   // producer's arrive.expect_tx (+ the TMA bytes)
             mbar_init(empty0 + 8 * s, 1);  // tcgen05.commit of the MMA warp
         }
-        for (int b = 0; b < 2; b++) {
-            mbar_init(tfull0 + 8 * b, 1);   // tcgen05.commit after the last MMA of a flush chunk
-            mbar_init(tempty0 + 8 * b, NEPI_WARPS);  // one arrive per epilogue warp
-        }
+        mbar_init(tfull, 1);                                                  // tcgen05.commit after a bucket's last MMA
+        for (int c = 0; c < NDIG; c++) mbar_init(tempty0 + 8 * c, NEPI_WARPS);  // accumulator c has been read
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -193,100 +207,112 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
-
-    const int FS = p.flush_stages;
-    const int n_chunks = (p.stages_total + FS - 1) / FS;
+    const int stages_total = p.groups[p.n_groups - 1].stage_end;
 
     if (warp < 4) {
         // warpgroup 0 gives its registers to the epilogue warpgroups (the register re-allocation has to sit inside
         // the role branches: ptxas budgets each branch by the setmaxnreg that dominates it)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-                const Tile tl = p.tiles[t];
-                const int ia = (tl.ti * TILE) % p.S, ga = (tl.ti * TILE) / p.S;
-                const int ib = (tl.tj * TILE) % p.S, gb = (tl.tj * TILE) / p.S;
-                for (int st = 0; st < p.stages_total; ++st, ++it) {
-                    const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
-                    mbar_wait(empty0 + 8 * slot, phase ^ 1u);
-                    const uint32_t full = full0 + 8 * slot;
-                    mbar_expect_tx(full, STAGE_BYTES);
-                    const uint32_t dst = base + slot * STAGE_BYTES;
-#pragma unroll
-                    for (int b = 0; b < TILE / BOX_W; b++) {
-                        tma_load_3d(dst + 0 * OPER_BYTES + b * BOX_BYTES, &map_hi, full, ia + b * BOX_W, st * KC, ga);
-                        tma_load_3d(dst + 1 * OPER_BYTES + b * BOX_BYTES, &map_lo, full, ia + b * BOX_W, st * KC, ga);
-                        tma_load_3d(dst + 2 * OPER_BYTES + b * BOX_BYTES, &map_hi, full, ib + b * BOX_W, st * KC, gb);
-                        tma_load_3d(dst + 3 * OPER_BYTES + b * BOX_BYTES, &map_lo, full, ib + b * BOX_W, st * KC, gb);
+        if (warp == 0) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map0) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map1) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map2) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&map3) : "memory");
+                uint32_t it = 0;
+                for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                    const Tile tl = p.tiles[t];
+                    const int ia = (tl.ti * TILE) % p.S, ga = (tl.ti * TILE) / p.S;
+                    const int ib = (tl.tj * TILE) % p.S, gb = (tl.tj * TILE) / p.S;
+                    for (int st = 0; st < stages_total; ++st, ++it) {
+                        const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
+                        mbar_wait(empty0 + 8 * slot, phase ^ 1u);
+                        const uint32_t full = full0 + 8 * slot;
+                        mbar_expect_tx(full, STAGE_BYTES);
+                        const uint32_t dst = base + slot * STAGE_BYTES;
+                        tma_load_3d(dst + 0 * PLANE_BYTES, &map0, full, ia, st * KC, ga);
+                        tma_load_3d(dst + 1 * PLANE_BYTES, &map1, full, ia, st * KC, ga);
+                        tma_load_3d(dst + 2 * PLANE_BYTES, &map2, full, ia, st * KC, ga);
+                        tma_load_3d(dst + 3 * PLANE_BYTES, &map3, full, ia, st * KC, ga);
+                        tma_load_3d(dst + 4 * PLANE_BYTES, &map0, full, ib, st * KC, gb);
+                        tma_load_3d(dst + 5 * PLANE_BYTES, &map1, full, ib, st * KC, gb);
+                        tma_load_3d(dst + 6 * PLANE_BYTES, &map2, full, ib, st * KC, gb);
+                        tma_load_3d(dst + 7 * PLANE_BYTES, &map3, full, ib, st * KC, gb);
                     }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one elected lane) =====================
-        uint32_t it = 0, chunk_it = 0;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-            for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
-                const uint32_t buf = chunk_it & 1u, bphase = (chunk_it >> 1) & 1u;
-                mbar_wait(tempty0 + 8 * buf, bphase ^ 1u);  // the epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + buf * TILE;
-                const int s_end = min(p.stages_total, (c + 1) * FS);
-                for (int st = c * FS; st < s_end; ++st, ++it) {
-                    const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
-                    mbar_wait(full0 + 8 * slot, phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (lane == 0) {
-                        const uint32_t a_hi = base + slot * STAGE_BYTES, a_lo = a_hi + OPER_BYTES;
-                        const uint32_t b_hi = a_hi + 2 * OPER_BYTES, b_lo = a_hi + 3 * OPER_BYTES;
+        } else if (warp == 1) {
+            // ===================== MMA issuer (one elected lane) =====================
+            uint32_t it = 0, grp_it = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                int st = 0;
+                for (int g = 0; g < p.n_groups; ++g, ++grp_it) {
+                    const int s_end = p.groups[g].stage_end;
+                    const uint32_t eph = (grp_it & 1u) ^ 1u;  // parity of "the previous bucket has been read"
+                    bool fresh = true;                        // the first MMA of a class overwrites its accumulator
+                    for (; st < s_end; ++st, ++it) {
+                        const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
+                        mbar_wait(full0 + 8 * slot, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t A = base + slot * STAGE_BYTES, B = A + NDIG * PLANE_BYTES;
 #pragma unroll
                         for (int kb = 0; kb < KC / KB; kb++) {
-                            const uint32_t off = kb * 1024;  // 8 nodes x 128 B
-                            const uint32_t first = (st == c * FS && kb == 0) ? 0u : 1u;
-                            umma_tf32(d_tmem, umma_desc(a_lo + off), umma_desc(b_hi + off), first);
-                            umma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
-                            umma_tf32(d_tmem, umma_desc(a_hi + off), umma_desc(b_hi + off), 1u);
+                            const uint32_t off = kb * KB * TILE;  // 32 rows x 128 B
+                            // order c: all products d_x d'_y with x + y = c go to accumulator c
+#pragma unroll
+                            for (int c = 0; c < NDIG; c++) {
+                                if (fresh) {  // accumulator c must have been drained by the epilogue
+                                    mbar_wait(tempty0 + 8 * c, eph);
+                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                }
+                                if (lane == 0) {
+#pragma unroll
+                                    for (int x = 0; x <= c; x++)
+                                        umma_i8(tmem_base + c * TILE, umma_desc(A + x * PLANE_BYTES + off),
+                                                umma_desc(B + (c - x) * PLANE_BYTES + off), (fresh && x == 0) ? 0u : 1u);
+                                }
+                            }
+                            fresh = false;
                         }
-                        umma_commit(empty0 + 8 * slot);  // frees the smem stage when these MMAs have read it
+                        if (lane == 0) umma_commit(empty0 + 8 * slot);  // frees the smem stage when the MMAs have read it
+                        __syncwarp();
                     }
+                    if (lane == 0) umma_commit(tfull);  // the accumulators of this bucket are complete
                     __syncwarp();
                 }
-                if (lane == 0) umma_commit(tfull0 + 8 * buf);  // accumulator complete
-                __syncwarp();
             }
         }
-    }
     } else {
-        // ===================== epilogue warps: TMEM -> float64 accumulators in registers =====================
+        // ===================== epilogue warps: int32 TMEM accumulators -> float64 registers =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int quarter = warp & 3;         // tcgen05.ld: a warp may touch TMEM lanes 32 (warp % 4) .. + 31
         const int half = (warp >> 2) - 1;     // columns [64 half, 64 half + 64)
         const int row = quarter * 32 + lane;
-        uint32_t chunk_it = 0;
+        uint32_t grp_it = 0;
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             const Tile tl = p.tiles[t];
             double acc[64];
 #pragma unroll
             for (int e = 0; e < 64; e++) acc[e] = 0.0;
-            for (int c = 0; c < n_chunks; ++c, ++chunk_it) {
-                const uint32_t buf = chunk_it & 1u, bphase = (chunk_it >> 1) & 1u;
-                mbar_wait(tfull0 + 8 * buf, bphase);
+            for (int g = 0; g < p.n_groups; ++g, ++grp_it) {
+                double w = p.groups[g].w0;
+                mbar_wait(tfull, grp_it & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int cb = 0; cb < 2; cb++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TILE + half * 64 + cb * 32, v);
+                for (int c = 0; c < NDIG; c++) {
 #pragma unroll
-                    for (int e = 0; e < 32; e++) acc[cb * 32 + e] += (double)__uint_as_float(v[e]);
+                    for (int cb = 0; cb < 2; cb++) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64 + cb * 32, v);
+#pragma unroll
+                        for (int e = 0; e < 32; e++) acc[cb * 32 + e] = fma((double)(int32_t)v[e], w, acc[cb * 32 + e]);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * c);  // accumulator c may be overwritten
+                    w *= (1.0 / DIGIT);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
             }
             const int64_t gi = (int64_t)tl.ti * TILE + row, gj0 = (int64_t)tl.tj * TILE + half * 64;
             if (gi < p.N) {
@@ -308,92 +334,182 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
 }
 
-// mean[k] = (1/N) sum_s PT[k][s] and energy[k] = sum_s (PT[k][s] - mean[k])^2, in double, one warp per node row.
+// cmax[k] = max_s |PT[k][s]|, one warp per node row.
 __global__ void __launch_bounds__(256)
-gram_mean_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32_t n, float *__restrict__ mean,
-                 float *__restrict__ energy)
+gram_colmax_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32_t n, float *__restrict__ cmax)
 {
     const int32_t k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= n) return;
     const int lane = threadIdx.x & 31;
-    double acc = 0.0;
-    for (int64_t s = lane; s < N; s += 32) acc += (double)PT[lay.at(k, s)];
+    float m = 0.f;
+    for (int64_t s = lane; s < N; s += 32) m = fmaxf(m, fabsf(PT[lay.at(k, s)]));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const float m = (float)(acc / (double)N);
-    double e = 0.0;
-    for (int64_t s = lane; s < N; s += 32) {
-        const double d = (double)PT[lay.at(k, s)] - (double)m;
-        e = fma(d, d, e);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    if (lane == 0) {
-        mean[k] = m;
-        energy[k] = (float)e;
-    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) cmax[k] = m;
 }
 
-// a = fl32(PT - mean) = hi + lo with hi, lo representable in TF32 (10 explicit mantissa bits);
-// q[block][s] = sum_k a^2 (Gram columns only) and r2[block][s] = sum_k (rounding error of a)^2 over the block's nodes.
+// Permuted row r (node row_map[r], bucket scale 1 / inv_scale[r]) of every sample -> three int8 digits;
+// r2[part][s] = sum over the part's rows of (quantisation error)^2, h2[part][s] = sum of S^2 over its non-zero entries.
+// Padding rows (row_map < 0) and padding samples (s >= N) get zero digits.
 __global__ void __launch_bounds__(256)
-gram_prep_kernel(const float *__restrict__ PT, const Lay lay, const Lay ws, const Lay sub, int64_t n_cols, int64_t N,
-                 int32_t n, int32_t k_per_block, const float *__restrict__ mean, const int32_t *__restrict__ direct_slot,
-                 float *__restrict__ HI, float *__restrict__ LO, float *__restrict__ SUB, double *__restrict__ q,
-                 double *__restrict__ r2)
+gram_digits_kernel(const float *__restrict__ PT, const Lay lay, const Lay ws, int64_t n_cols, int64_t N, int32_t n_rows,
+                   int32_t rows_per_part, const int32_t *__restrict__ row_map, const float *__restrict__ inv_scale,
+                   int8_t *__restrict__ D0, int8_t *__restrict__ D1, int8_t *__restrict__ D2, int8_t *__restrict__ D3,
+                   double *__restrict__ r2, double *__restrict__ h2)
 {
-    // s runs over every sample slot of the workspace planes (padding slots are written as zeros)
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_cols) return;
-    const int64_t ldp = n_cols;  // row length of the partial-statistics arrays
-    const int32_t k0 = blockIdx.y * k_per_block, k1 = min(n, k0 + k_per_block);
-    double acc = 0.0, err = 0.0;
-    for (int32_t k = k0; k < k1; k++) {
-        float a = 0.f;
-        if (s < N) {
-            const double c = (double)PT[lay.at(k, s)] - (double)mean[k];
-            a = (float)c;
-            const double e = c - (double)a;
-            err = fma(e, e, err);
+    const int32_t r0 = blockIdx.y * rows_per_part, r1 = min(n_rows, r0 + rows_per_part);
+    double err = 0.0, hh = 0.0;
+    for (int32_t r = r0; r < r1; r++) {
+        const int32_t k = row_map[r];
+        int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (k >= 0 && s < N) {
+            const float a = PT[lay.at(k, s)];
+            if (a != 0.f) {
+                const double is = (double)inv_scale[r];         // a power of two: a * is is exact and in [-1, 1]
+                double t = (double)a * is * DIGIT0;
+                const double f0 = rint(t);
+                t = (t - f0) * DIGIT;
+                const double f1 = rint(t);
+                t = (t - f1) * DIGIT;
+                const double f2 = rint(t);
+                t = (t - f2) * DIGIT;
+                const double f3 = rint(t);
+                d0 = (int)f0, d1 = (int)f1, d2 = (int)f2, d3 = (int)f3;
+                const double unit = 1.0 / (is * DIGIT0);        // value of one step of d0
+                const double e = (t - f3) * unit * (1.0 / (DIGIT * DIGIT * DIGIT));
+                err = fma(e, e, err);
+                hh += 1.0 / (is * is);                          // S^2 of every non-zero entry
+            }
         }
-        const int32_t slot = direct_slot[k];
-        if (slot >= 0) {  // this node column goes through the direct fp32 kernel
-            SUB[sub.at(slot, s)] = a;
-            HI[ws.at(k, s)] = 0.f;
-            LO[ws.at(k, s)] = 0.f;
-            continue;
-        }
-        uint32_t hb, lb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
-        const float hi = __uint_as_float(hb);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(a - hi));
-        HI[ws.at(k, s)] = hi;
-        LO[ws.at(k, s)] = __uint_as_float(lb);
-        acc = fma((double)a, (double)a, acc);
+        const int64_t o = ws.at(r, s);
+        D0[o] = (int8_t)d0;
+        D1[o] = (int8_t)d1;
+        D2[o] = (int8_t)d2;
+        D3[o] = (int8_t)d3;
     }
-    // per-(node block) partials, summed in fixed order by gram_stat_kernel: bit-reproducible norms
-    q[(int64_t)blockIdx.y * ldp + s] = acc;
-    r2[(int64_t)blockIdx.y * ldp + s] = err;
+    r2[(int64_t)blockIdx.y * n_cols + s] = err;
+    h2[(int64_t)blockIdx.y * n_cols + s] = hh;
 }
 
-// q[s] = sum of the partial norms in block order; err_out[s] = (sqrt(err_in[s]) + sqrt(sum r2))^2: the rounding
-// statistics of two successive roundings add in norm.
-__global__ void gram_stat_kernel(const double *__restrict__ qpart, const double *__restrict__ r2part, int32_t n_parts,
-                                 int64_t ldp, const double *__restrict__ err_in, int64_t N, double *__restrict__ q,
+// Gather of the node rows that bypass the integer Gram (largest scales): SUB[slot][s] = (double) PT[node][s].
+__global__ void __launch_bounds__(256)
+gram_gather_kernel(const float *__restrict__ PT, const Lay lay, const Lay sub, int64_t n_cols, int64_t N,
+                   const int32_t *__restrict__ direct_nodes, double *__restrict__ SUB)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_cols) return;
+    const int32_t k = direct_nodes[blockIdx.y];
+    SUB[sub.at(blockIdx.y, s)] = (k >= 0 && s < N) ? (double)PT[lay.at(k, s)] : 0.0;
+}
+
+// Bypass part in float64: D[tile] = sum over the bypassed rows of (a_i - a_j)^2 (plain stores; the Gram epilogue adds
+// its part afterwards).  One block = one 64x64 quarter of a 128x128 tile, 4x4 entries per thread.
+__global__ void __launch_bounds__(256)
+gram_bypass_kernel(const Tile *__restrict__ tiles, const double *__restrict__ SUB, const Lay sub, int32_t n_direct,
+                   int64_t N, double *__restrict__ D, int64_t ldd)
+{
+    constexpr int T = 64, KBK = 16;
+    __shared__ double As[KBK][T], Bs[KBK][T];
+    const Tile tl = tiles[blockIdx.x];
+    const int si = blockIdx.y >> 1, sj = blockIdx.y & 1;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t i0 = (int64_t)tl.ti * TILE + si * T, j0 = (int64_t)tl.tj * TILE + sj * T;
+    if (i0 >= N || j0 >= N) return;
+    double acc[4][4] = {};
+    for (int32_t k0 = 0; k0 < n_direct; k0 += KBK) {
+        for (int e = tid; e < KBK * T; e += 256) {
+            const int kk = e / T, c = e % T;
+            const int32_t k = k0 + kk;
+            As[kk][c] = (k < n_direct && i0 + c < N) ? SUB[sub.at(k, i0 + c)] : 0.0;
+            Bs[kk][c] = (k < n_direct && j0 + c < N) ? SUB[sub.at(k, j0 + c)] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < KBK; kk++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) a[m] = As[kk][ty * 4 + m];
+#pragma unroll
+            for (int u = 0; u < 4; u++) b[u] = Bs[kk][tx * 4 + u];
+#pragma unroll
+            for (int m = 0; m < 4; m++)
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double d = a[m] - b[u];
+                    acc[m][u] = fma(d, d, acc[m][u]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int64_t gi = i0 + ty * 4 + m;
+        if (gi >= N) continue;
+        double *drow = D + ((int64_t)tl.out_row0 + si * T + ty * 4 + m) * ldd;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t gj = j0 + tx * 4 + u;
+            if (gj < N) drow[gj] = acc[m][u];
+        }
+    }
+}
+
+// err_out[s] = (sqrt(err_in[s]) + sqrt(sum r2))^2: the statistics of
+// two successive roundings (fp32 rounding in the push-up, digit quantisation here) add in norm; h2[s] = sum of S^2 over
+// the sample's non-zero entries (bounds what the dropped product orders can contribute, see fuf_pairwise_gram).
+__global__ void gram_stat_kernel(const double *__restrict__ r2part, const double *__restrict__ h2part, int32_t n_parts,
+                                 int64_t ldp, const double *__restrict__ err_in, int64_t N, double *__restrict__ h2,
                                  double *__restrict__ err_out)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    double qs = 0.0, rs = 0.0;
+    double rs = 0.0, hs = 0.0;
     for (int32_t b = 0; b < n_parts; b++) {
-        qs += qpart[(int64_t)b * ldp + s];
         rs += r2part[(int64_t)b * ldp + s];
+        hs += h2part[(int64_t)b * ldp + s];
     }
-    q[s] = qs;
+    if (h2) h2[s] = hs;
     if (err_out) {
         const double a = sqrt(err_in ? err_in[s] : 0.0) + sqrt(rs);
         err_out[s] = a * a;
     }
+}
+
+// q[s] = the truncated digit form of sample s with itself: per bucket the integer sums c_p = sum_k sum_{x+y=p} d_x d_y
+// (exact, int64), combined with the SAME floating-point operations in the same order as the tile epilogue uses for
+// G[i,j] — so that q_i + q_j - 2 G[i,j] is exactly 0 when the digit rows of i and j coincide.
+__global__ void __launch_bounds__(128)
+gram_selfnorm_kernel(const int8_t *__restrict__ D0, const int8_t *__restrict__ D1, const int8_t *__restrict__ D2,
+                     const int8_t *__restrict__ D3, const Lay ws, int64_t N, const Group *__restrict__ groups,
+                     int32_t n_groups, double *__restrict__ q)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    double acc = 0.0;
+    int32_t r = 0;
+    for (int32_t g = 0; g < n_groups; g++) {
+        const int32_t r_end = groups[g].stage_end * KC;
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        for (; r < r_end; r++) {
+            const int64_t o = ws.at(r, s);
+            const int x0 = D0[o], x1 = D1[o], x2 = D2[o], x3 = D3[o];
+            c0 += x0 * x0;
+            c1 += 2 * x0 * x1;
+            c2 += x1 * x1 + 2 * x0 * x2;
+            c3 += 2 * x0 * x3 + 2 * x1 * x2;
+        }
+        double w = groups[g].w0;
+        acc = fma((double)(int32_t)c0, w, acc);
+        w *= (1.0 / DIGIT);
+        acc = fma((double)(int32_t)c1, w, acc);
+        w *= (1.0 / DIGIT);
+        acc = fma((double)(int32_t)c2, w, acc);
+        w *= (1.0 / DIGIT);
+        acc = fma((double)(int32_t)c3, w, acc);
+    }
+    q[s] = acc;
 }
 
 // lower triangle := transpose of the upper triangle (tiles tj > ti and the diagonal tiles), 32x32 sub-blocks.
@@ -436,25 +552,24 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const float *ptr, int64_t N, int32_t n, const Lay &ws)
+static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_rows, const Lay &ws)
 {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) {
         set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled is not available from this driver");
         return FUF_ECUDA;
     }
-    // dims (sample in shard, node, shard); samples beyond N / nodes beyond n read as zero (the planes are zero there)
+    // dims (sample in shard, permuted basis row, shard), one byte per entry
     const int64_t n_shards = ws.SS ? (N + ws.S - 1) / ws.S : 1;
-    const cuuint64_t gdim[3] = {(cuuint64_t)(ws.SS ? ws.S : N), (cuuint64_t)n, (cuuint64_t)n_shards};
-    const cuuint64_t gstride[2] = {(cuuint64_t)ws.LD * sizeof(float),
-                                   (cuuint64_t)(ws.SS ? ws.SS : ws.LD * (int64_t)n) * sizeof(float)};
-    const cuuint32_t box[3] = {BOX_W, KC, 1}, estr[3] = {1, 1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)ptr, gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const cuuint64_t gdim[3] = {(cuuint64_t)ws.S, (cuuint64_t)n_rows, (cuuint64_t)n_shards};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ws.LD, (cuuint64_t)(ws.SS ? ws.SS : ws.LD * (int64_t)n_rows)};
+    const cuuint32_t box[3] = {TILE, KC, 1}, estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)ptr, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld n=%d S=%lld)", (int)r,
-                  (long long)N, n, (long long)ws.S);
+        set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld rows=%d S=%lld)", (int)r,
+                  (long long)N, n_rows, (long long)ws.S);
         return FUF_ECUDA;
     }
     return FUF_OK;
@@ -463,7 +578,7 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t N, int32_t n, co
 }  // namespace gram
 
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
-                  const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
+                  const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
                   double *D, int64_t ldd, cudaStream_t stream)
 {
     using namespace gram;
@@ -471,93 +586,145 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     const int32_t n = ctx->n;
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
     FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise_gram: PT must be 16-byte aligned");
-    Lay lay, ws, sub;
-    int32_t n_direct = GRAM_DIRECT_ROWS;
-    if (getenv("FUF_GRAM_DIRECT")) n_direct = std::max(16, atoi(getenv("FUF_GRAM_DIRECT")));
-    n_direct = std::min<int32_t>(n, n_direct);
-    const int32_t n_direct_pad = (n_direct + 15) / 16 * 16;
-    int64_t n_cols;  // sample slots of the workspace planes
+    Lay lay;
+    int64_t n_cols;  // sample slots of the digit planes
     if (shard == 0) {
         FUF_REQUIRE(ldp % 4 == 0 && ldp >= N, "fuf_pairwise_gram: ldp=%lld must be a multiple of 4 and >= N=%lld",
                     (long long)ldp, (long long)N);
         n_cols = tiles_per_dim * TILE;
         lay = Lay{ldp, 0, ldp};
-        ws = Lay{n_cols, 0, n_cols};
-        sub = Lay{n_cols, 0, n_cols};
     } else {
         FUF_REQUIRE(shard % TILE == 0 && shard > 0 && shard_stride >= shard * (int64_t)n,
                     "fuf_pairwise_gram: bad shard layout (shard=%lld stride=%lld)", (long long)shard,
                     (long long)shard_stride);
-        const int64_t n_shards = (N + shard - 1) / shard;
-        n_cols = n_shards * shard;
+        n_cols = (N + shard - 1) / shard * shard;
         lay = Lay{shard, shard_stride, shard};
-        ws = Lay{shard, (int64_t)n * shard, shard};
-        sub = Lay{shard, (int64_t)n_direct_pad * shard, shard};
     }
-    // workspace: HI | LO (n x n_cols floats each) | SUB (n_direct x n_cols) | mean, energy (n floats) | slot (n ints)
-    //            | partial norms and rounding statistics | tile list
-    auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
-    const size_t plane = up((size_t)n * n_cols * sizeof(float)), sub_bytes = up((size_t)n_direct_pad * n_cols * sizeof(float));
-    const int32_t k_per_block = 512, n_parts = (n + k_per_block - 1) / k_per_block;
-    const size_t vec_bytes = up((size_t)n * sizeof(float)), part_bytes = up((size_t)n_parts * n_cols * sizeof(double));
     std::vector<Tile> tiles;
     const bool full = (tile_rows_h == nullptr);
-    const int32_t n_rows = full ? (int32_t)tiles_per_dim : n_tile_rows;
-    for (int32_t c = 0; c < n_rows; c++) {
+    const int32_t n_trows = full ? (int32_t)tiles_per_dim : n_tile_rows;
+    for (int32_t c = 0; c < n_trows; c++) {
         const int32_t t = full ? c : tile_rows_h[c];
         FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise_gram: tile row %d out of range [0,%lld)", t,
                     (long long)tiles_per_dim);
         for (int32_t tj = t; tj < tiles_per_dim; tj++) tiles.push_back(Tile{t, tj, full ? t * TILE : c * TILE, 0});
     }
     if (tiles.empty()) return FUF_OK;
-    const size_t tiles_bytes = tiles.size() * sizeof(Tile);
-    int rc = ctx->ws_gram.reserve(2 * plane + sub_bytes + 3 * vec_bytes + 2 * part_bytes + tiles_bytes);
+
+    // ---- column maxima -> buckets (powers of four), permutation, stage table --------------------------------
+    int rc = ctx->ws_gram_small.reserve((size_t)n * sizeof(float));
     if (rc) return rc;
-    char *wsp = (char *)ctx->ws_gram.ptr;
-    float *HI = (float *)wsp, *LO = (float *)(wsp + plane), *SUB = (float *)(wsp + 2 * plane);
-    float *mean = (float *)(wsp + 2 * plane + sub_bytes), *energy = (float *)((char *)mean + vec_bytes);
-    int32_t *d_slot = (int32_t *)((char *)mean + 2 * vec_bytes);
-    double *qpart = (double *)((char *)mean + 3 * vec_bytes), *r2part = (double *)((char *)qpart + part_bytes);
-    Tile *d_tiles = (Tile *)((char *)r2part + part_bytes);
-    FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles_bytes, cudaMemcpyHostToDevice, stream));
-    FUF_CUDA(cudaMemsetAsync(SUB, 0, sub_bytes, stream));
-    gram_mean_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, mean, energy);
+    float *d_cmax = (float *)ctx->ws_gram_small.ptr;
+    gram_colmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, d_cmax);
     FUF_CUDA(cudaGetLastError());
-    // the n_direct node columns of largest energy -> direct kernel (host selection: n floats, once per call)
-    std::vector<float> h_energy(n);
-    FUF_CUDA(cudaMemcpyAsync(h_energy.data(), energy, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    FUF_CUDA(cudaStreamSynchronize(stream));  // also: `tiles` is pageable and dies with this call
-    std::vector<int32_t> order(n), h_slot(n, -1);
-    for (int32_t k = 0; k < n; k++) order[k] = k;
-    std::nth_element(order.begin(), order.begin() + (n_direct - 1), order.end(), [&](int32_t a, int32_t b) {
-        return h_energy[a] > h_energy[b] || (h_energy[a] == h_energy[b] && a < b);
-    });
-    std::sort(order.begin(), order.begin() + n_direct);
-    for (int32_t i = 0; i < n_direct; i++) h_slot[order[i]] = i;
-    FUF_CUDA(cudaMemcpyAsync(d_slot, h_slot.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    std::vector<float> cmax(n);
+    FUF_CUDA(cudaMemcpyAsync(cmax.data(), d_cmax, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
     FUF_CUDA(cudaStreamSynchronize(stream));
+    std::vector<std::pair<int32_t, int32_t>> keyed;  // (bucket exponent, node), all-zero columns dropped
+    keyed.reserve(n);
+    for (int32_t k = 0; k < n; k++) {
+        FUF_REQUIRE(std::isfinite(cmax[k]), "fuf_pairwise_gram: profile column %d holds a non-finite value", k);
+        if (cmax[k] > 0.f) {
+            int e;
+            std::frexp(cmax[k], &e);                    // cmax = m 2^e, m in [0.5, 1): cmax < 2^e = the bucket scale
+            keyed.emplace_back(e, k);
+        }
+    }
+    std::sort(keyed.begin(), keyed.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) {
+        return a.first > b.first || (a.first == b.first && a.second < b.second);
+    });
+    // the columns of largest scale bypass the integer Gram: their S^2 is what the dropped product orders are relative
+    // to, and the direct (a-b)^2 kernel has no such term.  `keyed` is sorted by decreasing scale.
+    int32_t n_direct = GRAM_DIRECT_ROWS;
+    if (getenv("FUF_GRAM_DIRECT")) n_direct = std::max(0, atoi(getenv("FUF_GRAM_DIRECT")));
+    n_direct = std::min<int32_t>(n_direct, (int32_t)keyed.size());
+    const int32_t n_direct_pad = std::max(16, (n_direct + 15) / 16 * 16);
+    std::vector<int32_t> direct_nodes(n_direct_pad, -1);
+    for (int32_t i = 0; i < n_direct; i++) direct_nodes[i] = keyed[i].second;
+    keyed.erase(keyed.begin(), keyed.begin() + n_direct);
+    std::vector<int32_t> row_map;
+    std::vector<float> inv_scale;
+    std::vector<Group> groups;
+    for (size_t i = 0; i < keyed.size();) {
+        size_t j = i;
+        // one bucket; at most 32,768 rows per group so that 4 x 127^2 x rows stays below 2^31 in accumulator 3
+        while (j < keyed.size() && keyed[j].first == keyed[i].first && j - i < 32768) j++;
+        const double S = std::ldexp(1.0, keyed[i].first);
+        for (size_t u = i; u < j; u++) {
+            row_map.push_back(keyed[u].second);
+            inv_scale.push_back((float)(1.0 / S));
+        }
+        while (row_map.size() % KC) {  // pad the bucket to whole stages with zero rows
+            row_map.push_back(-1);
+            inv_scale.push_back(0.f);
+        }
+        groups.push_back(Group{(int32_t)(row_map.size() / KC), 0, S * S / (DIGIT0 * DIGIT0)});
+        i = j;
+    }
+    if (groups.empty()) {  // every profile is identically zero: one all-zero stage
+        row_map.assign(KC, -1);
+        inv_scale.assign(KC, 0.f);
+        groups.push_back(Group{1, 0, 0.0});
+    }
+    const int32_t n_rows = (int32_t)row_map.size();
+    Lay ws = shard == 0 ? Lay{n_cols, 0, n_cols} : Lay{shard, (int64_t)n_rows * shard, shard};
+
+    // ---- workspace: four digit planes | partial statistics | row map, scales, groups, tiles -----------------
+    auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
+    const size_t plane = up((size_t)n_rows * n_cols);
+    const int32_t rows_per_part = 512, n_parts = (n_rows + rows_per_part - 1) / rows_per_part;
+    const size_t part_bytes = up((size_t)n_parts * n_cols * sizeof(double));
+    const size_t map_bytes = up((size_t)n_rows * sizeof(int32_t)), scl_bytes = up((size_t)n_rows * sizeof(float));
+    const size_t grp_bytes = up(groups.size() * sizeof(Group)), tiles_bytes = up(tiles.size() * sizeof(Tile));
+    const size_t sub_bytes = up((size_t)n_direct_pad * n_cols * sizeof(double)), dn_bytes = up((size_t)n_direct_pad * sizeof(int32_t));
+    const size_t q_bytes = up((size_t)n_cols * sizeof(double));
+    if ((rc = ctx->ws_gram.reserve(NDIG * plane + 2 * part_bytes + map_bytes + scl_bytes + grp_bytes + tiles_bytes + sub_bytes +
+                                   dn_bytes + q_bytes)))
+        return rc;
+    char *wsp = (char *)ctx->ws_gram.ptr;
+    int8_t *D0 = (int8_t *)wsp, *D1 = D0 + plane, *D2 = D1 + plane, *D3 = D2 + plane;
+    double *r2part = (double *)(wsp + NDIG * plane), *h2part = (double *)((char *)r2part + part_bytes);
+    int32_t *d_map = (int32_t *)((char *)h2part + part_bytes);
+    float *d_scl = (float *)((char *)d_map + map_bytes);
+    Group *d_groups = (Group *)((char *)d_scl + scl_bytes);
+    Tile *d_tiles = (Tile *)((char *)d_groups + grp_bytes);
+    double *SUB = (double *)((char *)d_tiles + tiles_bytes);
+    int32_t *d_dn = (int32_t *)((char *)SUB + sub_bytes);
+    double *q = (double *)((char *)d_dn + dn_bytes);  // squared norms of the quantised Gram part (kernel-internal)
+    FUF_CUDA(cudaMemcpyAsync(d_dn, direct_nodes.data(), (size_t)n_direct_pad * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaMemcpyAsync(d_map, row_map.data(), (size_t)n_rows * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaMemcpyAsync(d_scl, inv_scale.data(), (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(Group), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaStreamSynchronize(stream));  // the host vectors are pageable and die with this call
     {
         dim3 g((unsigned)((n_cols + 255) / 256), (unsigned)n_parts);
-        gram_prep_kernel<<<g, 256, 0, stream>>>(PT, lay, ws, sub, n_cols, N, n, k_per_block, mean, d_slot, HI, LO, SUB,
-                                                qpart, r2part);
+        gram_digits_kernel<<<g, 256, 0, stream>>>(PT, lay, ws, n_cols, N, n_rows, rows_per_part, d_map, d_scl, D0, D1, D2,
+                                                  D3, r2part, h2part);
         FUF_CUDA(cudaGetLastError());
-        gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(qpart, r2part, n_parts, n_cols, err_in, N, q, err_out);
+        gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(r2part, h2part, n_parts, n_cols, err_in, N, h2, err_out);
+        FUF_CUDA(cudaGetLastError());
+        gram_selfnorm_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(D0, D1, D2, D3, ws, N, d_groups,
+                                                                              (int32_t)groups.size(), q);
+        FUF_CUDA(cudaGetLastError());
+        dim3 gg((unsigned)((n_cols + 255) / 256), (unsigned)n_direct_pad);
+        const Lay sub = shard == 0 ? Lay{n_cols, 0, n_cols} : Lay{shard, (int64_t)n_direct_pad * shard, shard};
+        gram_gather_kernel<<<gg, 256, 0, stream>>>(PT, lay, sub, n_cols, N, d_dn, SUB);
+        FUF_CUDA(cudaGetLastError());
+        // bypass part first, in float64: D = sum over the bypassed node columns of (a_i - a_j)^2
+        gram_bypass_kernel<<<dim3((unsigned)tiles.size(), 4), 256, 0, stream>>>(d_tiles, SUB, sub, n_direct_pad, N, D, ldd);
         FUF_CUDA(cudaGetLastError());
     }
-    // direct part first: D = sum over the selected node columns of (a_i - a_j)^2
-    // (fp32 partial sums over 16 entries only: these columns carry most of the magnitude)
-    rc = pairwise_f32(ctx, SUB, N, n_cols, shard ? shard : 0, shard ? sub.SS : 0, FUF_MODE_L2, tile_rows_h, n_tile_rows, D,
-                      ldd, 0, stream, nullptr, 0, 0, 0, n_direct_pad, 1);
-    if (rc) return rc;
-    ctx->launches += 3;
-    CUtensorMap map_hi, map_lo;
-    if ((rc = make_map(&map_hi, HI, N, n, ws)) || (rc = make_map(&map_lo, LO, N, n, ws))) return rc;
+    ctx->launches += 5;
+    CUtensorMap map0, map1, map2, map3;
+    if ((rc = make_map(&map0, D0, N, n_rows, ws)) || (rc = make_map(&map1, D1, N, n_rows, ws)) ||
+        (rc = make_map(&map2, D2, N, n_rows, ws)) || (rc = make_map(&map3, D3, N, n_rows, ws)))
+        return rc;
     Params p;
     p.tiles = d_tiles;
+    p.groups = d_groups;
     p.n_tiles = (int32_t)tiles.size();
-    p.stages_total = (n + KC - 1) / KC;
-    p.flush_stages = FLUSH_STAGES;
-    if (getenv("FUF_GRAM_FLUSH")) p.flush_stages = std::max(1, atoi(getenv("FUF_GRAM_FLUSH")));
+    p.n_groups = (int32_t)groups.size();
     p.S = (int32_t)ws.S;
     p.N = N;
     p.q = q;
@@ -570,10 +737,11 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
     }
     FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
-    gram_tile_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map_hi, map_lo, p);
+    gram_tile_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map0, map1, map2, map3, p);
     FUF_CUDA(cudaGetLastError());
     FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], stream));
-    ctx->gram_flops = 3.0 * 2.0 * TILE * TILE * (double)p.stages_total * KC * (double)p.n_tiles;
+    ctx->gram_flops = 10.0 * 2.0 * TILE * TILE * (double)n_rows * (double)p.n_tiles;  // int8 multiply-adds x 2
+    ctx->gram_groups = p.n_groups;
     ctx->launches += 1;
     if (full) {
         const unsigned b = (unsigned)((N + 31) / 32);
@@ -601,14 +769,14 @@ extern "C" int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_fl
 }
 
 extern "C" int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard,
-                                 int64_t shard_stride, int mode, const double *err_in, double *q, double *err_out,
+                                 int64_t shard_stride, int mode, const double *err_in, double *h2, double *err_out,
                                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream)
 {
-    FUF_REQUIRE(ctx && PT && q && D, "fuf_pairwise_gram: null argument");
+    FUF_REQUIRE(ctx && PT && h2 && D, "fuf_pairwise_gram: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L2, "fuf_pairwise_gram: only FUF_MODE_L2 has a Gram form (got mode %d)", mode);
     FUF_REQUIRE(N >= 0 && ldd >= N, "fuf_pairwise_gram: bad shape N=%lld ldd=%lld", (long long)N, (long long)ldd);
-    FUF_CUDA(cudaSetDevice(ctx->device));
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise_gram: n_tile_rows without tile_rows_h");
-    return pairwise_gram(ctx, PT, N, ldp, shard, shard_stride, err_in, q, err_out, tile_rows_h, n_tile_rows, D, ldd,
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return pairwise_gram(ctx, PT, N, ldp, shard, shard_stride, err_in, h2, err_out, tile_rows_h, n_tile_rows, D, ldd,
                          (cudaStream_t)stream);
 }

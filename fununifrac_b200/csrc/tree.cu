@@ -313,6 +313,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     ctx->ws_center.release();
     ctx->ws_rows.release();
     ctx->ws_gram.release();
+    ctx->ws_gram_small.release();
     ctx->ws_p64.release();
     ctx->ws_push.release();
     ctx->ws_pair.release();

@@ -22,6 +22,7 @@ TILE = 128
 PW_SCALAR_MATH = 1
 AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
+GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
 ABI_VERSION = 4
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
@@ -270,8 +271,8 @@ class TreeContext:
         """--L2 through the Gram kernel + both refinement passes (needs a job pushed with refine=True)."""
         assert job.P64T is not None, "the Gram path needs the float64 profiles for its refinement pass"
         D, q, err = self.pairwise_gram(job.PT, job.N, D=D, err_stat=job.err_stat)
-        if job.N > 1:    # one scan: rounding criterion on err, linear criterion on the Gram norms q
-            self.refine(job.P64T, job.N, MODE_L2, err, D, lin_stat=q)
+        if job.N > 1:    # one scan: rounding criterion on err, truncation criterion on the scale statistic h2
+            self.refine(job.P64T, job.N, MODE_L2, err, D, lin_stat=q, lin_kappa=GRAM_KAPPA)
             self.gram_refined = self.refine_count()
         return D
 

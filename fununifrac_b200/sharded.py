@@ -172,10 +172,10 @@ class CudaOps:
 
     def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, lin_stat=None):
         return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride,
-                               lin_stat=lin_stat)
+                               lin_stat=lin_stat, lin_kappa=2.9e-3)
 
     def count_uncertified(self, N, mode, err_stat, D, tile_rows, lin_stat=None):
-        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, lin_stat=lin_stat)
+        self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, lin_stat=lin_stat, lin_kappa=2.9e-3)
         return self.ctx.refine_count()
 
     def assemble(self, blocks, rows, N, D):

@@ -159,24 +159,27 @@ int fuf_round_pushed(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64,
 int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags, void *stream);
 
-/* --L2 on the tensor cores: D[i,j] = q_i + q_j - 2 (A A^T)[i,j], A = PT minus its node-wise mean over the samples,
- * with the Gram matrix computed by tcgen05.mma (kind::tf32, three products per term on hi/lo TF32 splits of the
- * fp32 operands, fp32 accumulation in tensor memory over 256 basis entries, float64 across); the 512 node columns of largest
- * energy go through the direct fp32 kernel instead (their products are where 3xTF32 is not accurate enough).
- *   PT       device float, node-major, ld ldp (any centre; centred profiles lose less in the second rounding)
+/* --L2 on the tensor cores: D[i,j] = q_i + q_j - 2 (A A^T)[i,j] as an ERROR-FREE integer Gram matrix.
+ * Node columns are bucketed by the power of two of their largest entry (bucket scale S); every entry becomes four
+ * signed 8-bit digits, a / S = (d0 + d1/254 + d2/254^2 + d3/254^3) / 127; tcgen05.mma kind::i8 accumulates the digit
+ * products of order 0..3 exactly in int32 tensor memory (10 MMAs per 32 basis rows); the 256 columns of largest scale
+ * are computed in float64 instead.  D is then the exact squared distance of the quantised profiles up to the dropped
+ * product orders, |error| <= 1.44e-9 (h2_i + h2_j), and exactly 0 for identical samples.
+ *   PT       device float, node-major, ld ldp (centred profiles quantise better)
  *   err_in   device, N doubles or NULL: the L2 rounding statistic of PT from fuf_push_up
- *   q        device, N doubles, out: squared norms of A (the statistic of the follow-up linear refinement)
- *   err_out  device, N doubles or NULL, out: rounding statistic of A = (sqrt err_in + sqrt(own rounding))^2
+ *   h2       device, N doubles, out: sum of S^2 over the sample's non-zero Gram entries (statistic of the
+ *            linear refinement criterion, lin_kappa = 2.9e-3)
+ *   err_out  device, N doubles or NULL, out: rounding statistic incl. the quantisation = (sqrt err_in + sqrt(own))^2
  *   shard, shard_stride, tile_rows_h, n_tile_rows: as in fuf_pairwise (all-gathered shards; compact row blocks)
  *   D        full symmetric N x N with zero diagonal, or compact upper row blocks when tile_rows_h != NULL.
- * Follow with fuf_refine(err_stat = err_out, lin_stat = q).
- * mode must be FUF_MODE_L2. */
+ * Follow with fuf_refine(err_stat = err_out, lin_stat = h2, lin_kappa = 2.9e-3).  mode must be FUF_MODE_L2. */
 int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
-                      const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
+                      const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
                       double *D, int64_t ldd, void *stream);
 
 /* Device time of the tcgen05 tile kernel of the last fuf_pairwise_gram call (CUDA events on its stream; waits for
- * it) and the MMA flops it executed (3 products x 2 x 128 x 128 x padded n per tile) — for the tensor-pipe roofline. */
+ * it) and the int8 operations it executed (10 products x 2 x 128 x 128 x padded n per tile) — for the tensor-pipe
+ * roofline. */
 int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_flops);
 
 /* Validation mode: everything in double. Full matrix only. */

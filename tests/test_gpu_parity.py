@@ -273,21 +273,39 @@ def test_near_duplicates_are_refined(full_tree):
 # --------------------------------------------------------------------------------------------------
 # --L2 on the tensor cores (tcgen05 Gram kernel + direct part + refinement)
 # --------------------------------------------------------------------------------------------------
-def test_gram_exact_on_small_integers():
-    """Rank-1 integer profiles: every product and sum is exact in TF32/fp32, so D must be exactly (i - j)^2 —
-    pins the shared-memory / instruction descriptors, the swizzle and the TMEM read-out, for nodes in different
-    swizzle rows and pipeline stages."""
-    n, N = 70, 300
+def test_gram_kernel_layouts(monkeypatch):
+    """Pins the shared-memory / instruction descriptors, the swizzle, the digit planes and the TMEM read-out of the
+    integer Gram kernel: dense random profiles with column scales over six decades, (a) every column through the
+    int8 path, (b) the default split with the largest-scale columns in float64.  A wrong layout gives O(1) errors;
+    the arithmetic itself is exact up to 1.44e-9 of the scale statistic."""
+    n, N = 200, 300
     parent = np.full(n, n - 1, np.int32)
     parent[-1] = -1
     ctx = engine.TreeContext(parent, np.ones(n))
-    idx = np.arange(N, dtype=np.float64)
-    for k0 in (0, 1, 9, 33, 69):
-        PT = torch.zeros((n, engine.padded_samples(N)), dtype=torch.float32, device="cuda")
-        PT[k0, :N] = torch.arange(1, N + 1, dtype=torch.float32, device="cuda")
-        D, q, err = ctx.pairwise_gram(PT, N)
-        assert np.array_equal(D.cpu().numpy(), (idx[:, None] - idx[None, :]) ** 2), k0
-        assert float(err.abs().max()) == 0.0     # nothing was rounded
+    rng = np.random.default_rng(0)
+    P = (rng.random((n, N)) * (rng.random((n, N)) < 0.4)).astype(np.float32)
+    P *= (10.0 ** rng.integers(-6, 1, (n, 1))).astype(np.float32)
+    P[:, 7] = P[:, 3]                                                     # an identical pair
+    P64 = P.astype(np.float64)
+    exact = ((P64[:, :, None] - P64[:, None, :]) ** 2).sum(0)
+    PT = torch.zeros((n, engine.padded_samples(N)), dtype=torch.float32, device="cuda")
+    PT[:, :N] = torch.from_numpy(P)
+    for direct in ("0", "16", None):
+        if direct is None:
+            monkeypatch.delenv("FUF_GRAM_DIRECT", raising=False)
+        else:
+            monkeypatch.setenv("FUF_GRAM_DIRECT", direct)
+        D, h2, err = ctx.pairwise_gram(PT, N)
+        D, h2, err = D.cpu().numpy(), h2.cpu().numpy()[:N], err.cpu().numpy()[:N]
+        check_matrix(D)
+        r = np.sqrt(err)[:, None] + np.sqrt(err)[None, :]
+        qq = (P64 ** 2).sum(0)
+        bound = (2 * np.sqrt(exact) * r + r ** 2 + 1.44e-9 * (h2[:, None] + h2[None, :])
+                 + 1e-13 * (qq[:, None] + qq[None, :]))               # + float64 rounding of the sums themselves
+        assert np.all(np.abs(D - exact) <= bound), direct                # the certified error model holds pairwise
+        assert D[3, 7] == 0.0
+        if direct == "0":
+            assert np.abs(D - exact).max() / exact.max() < 1e-8 and h2.min() > 0
 
 
 def test_gram_vs_oracle(full_tree):
@@ -303,14 +321,23 @@ def test_gram_vs_oracle(full_tree):
     job = ctx.push_up_job(torch.from_numpy(X).cuda(), engine.MODE_L2)
     raw = ctx.pairwise_gram(job.PT, N, err_stat=job.err_stat)[0].cpu().numpy()
     D = ctx.distances(job, engine.MODE_L2)                      # N >= 512: routed to the Gram path
-    assert ctx.gram_refined >= 7
+    assert 7 <= ctx.gram_refined <= 200
     D = D.cpu().numpy()
     check_matrix(D)
     assert rel_err(D, Dref) < REL
     ordinary = Dref > 1e-2 * np.median(Dref)
     assert (np.abs(raw - Dref)[ordinary] / Dref[ordinary]).max() < REL     # the tensor-core result itself
     assert rel_err(raw, Dref) > REL                                        # near-duplicates need the refinement
+    assert raw[500, 501] == 0 and raw[501, 502] == 0                       # exact arithmetic: identical samples -> 0
     assert D[500, 501] == 0 and D[501, 502] == 0
+    # correlated samples (mixtures): the floating-point Gram forms lose digits here, the integer one does not
+    Xm = X.copy()
+    for i in range(0, 200, 2):
+        lam = 10 ** rng.uniform(-3, 0)
+        Xm[i + 1] = (1 - lam) * Xm[i] + lam * Xm[i + 1]
+    Drefm = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, Xm, True), True)
+    Dm = ctx.distances(ctx.push_up_job(torch.from_numpy(Xm).cuda(), engine.MODE_L2), engine.MODE_L2).cpu().numpy()
+    assert rel_err(Dm, Drefm) < REL and ctx.gram_refined < 400
     Dd = ctx.distances(job, engine.MODE_L2, gram=False).cpu().numpy()      # direct (a-b)^2 kernel
     assert rel_err(Dd, Dref) < REL
     Dh = ctx.all_pairs_host(X, engine.MODE_L2)                             # host path takes the Gram route too
@@ -329,9 +356,9 @@ def test_gram_vs_oracle(full_tree):
                     stat[g * shard:(g + 1) * shard])
     blocks, rows = [], []
     for own in ([0, 3, 4], [1, 2]):
-        blk, q, err = ctx.pairwise_gram(PS, N, err_stat=stat, tile_rows=own, shard=shard, shard_stride=ctx.n * shard)
+        blk, h2, err = ctx.pairwise_gram(PS, N, err_stat=stat, tile_rows=own, shard=shard, shard_stride=ctx.n * shard)
         ctx.refine(P64S, N, engine.MODE_L2, err, blk, tile_rows=own, shard=shard, shard_stride=ctx.n * shard,
-                   lin_stat=q)
+                   lin_stat=h2, lin_kappa=engine.GRAM_KAPPA)
         blocks.append(blk)
         rows += own
     Ds = ctx.assemble(torch.cat(blocks, 0), rows, N).cpu().numpy()
