@@ -70,6 +70,8 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     // pinned D_h: every finished band of D is copied while the next one computes; pageable D_h: one copy at the end
     const bool band_d2h = !validate && d_pinned && D_zc == nullptr;
     cudaStream_t sc = ctx->s_copy, sk = ctx->s_comp, sd = ctx->s_d2h;
+    // per-pair refinement budget: 0.1 % of the pairs (beyond it the float64 tile kernel redoes the whole matrix)
+    const int64_t refine_budget = std::max<int64_t>(1024, N * (N - 1) / 2 / 1000);
     cudaEvent_t e_start = ctx->ev[0], e_push = ctx->ev[1], e_end = ctx->ev[2];
     std::vector<cudaEvent_t> &e_band = ctx->ev_band;
     while ((int)e_band.size() < 2 * nb) {
@@ -115,7 +117,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             if (do_refine) {
                 // one scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
                 rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,
-                            FUF_CRIT_ROUNDING, qg, 2.9e-3);
+                            FUF_CRIT_ROUNDING, qg, 2.9e-3, refine_budget);
                 if (rc) return rc;
             }
             if (band_d2h) {
@@ -128,7 +130,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             if (rc) return rc;
             if (do_refine) {
                 rc = refine(ctx, P64T, s1, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, D_zc, ldd, s0, s1,
-                            b == 0);
+                            b == 0, FUF_CRIT_ROUNDING, nullptr, 0.0, refine_budget);
                 if (rc) return rc;
             }
             if (band_d2h && !use_gram) {
@@ -165,6 +167,15 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         unsigned long long v = 0;
         FUF_CUDA(cudaMemcpy(&v, ctx->d_refined, sizeof(v), cudaMemcpyDeviceToHost));
         ctx->last_refined = (int64_t)v;
+        if ((int64_t)v > refine_budget) {
+            // too many pairs for per-pair recomputation (e.g. --unweighted --L2, or a data set of near-duplicates):
+            // the float64 tile kernel over the float64 profiles gives every pair at validation accuracy
+            rc = pairwise_f64(ctx, P64T, N, ldp, mode, D_dev, N, sk);
+            if (rc) return rc;
+            FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
+                                       (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
+            FUF_CUDA(cudaStreamSynchronize(sk));
+        }
     }
     return FUF_OK;
 }

@@ -104,6 +104,7 @@ struct fuf_ctx {
     cudaEvent_t ev_gram[2] = {};       // around the last gram_tile_kernel launch
     double gram_flops = 0.0;           // MMA flops that launch executed
     int gram_groups = 0;               // exponent buckets of the last Gram call
+    int gram_bypassed = 0;             // node columns the last Gram call computed in float64
     std::vector<cudaEvent_t> ev_band;  // one per sample band of fuf_all_pairs_host
     float t_h2d_push = 0.f, t_pair = 0.f, t_total = 0.f;
 
@@ -138,7 +139,7 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int64_t j_begin = 0,
            int64_t j_end = 0, bool reset_counter = true, int criterion = 0, const double *lin_stat = nullptr,
-           double lin_kappa = 0.0);
+           double lin_kappa = 0.0, int64_t max_pairs = 0);
 // diffab.cu
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                  int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);

@@ -334,18 +334,34 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     }
 }
 
-// cmax[k] = max_s |PT[k][s]|, one warp per node row.
+// Per node column (one warp per row): cmax[k] = max_s |PT[k][s]|, nnz[k] = number of non-zero entries,
+// energy[k] = sum_s PT[k][s]^2.
 __global__ void __launch_bounds__(256)
-gram_colmax_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32_t n, float *__restrict__ cmax)
+gram_colmax_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32_t n, float *__restrict__ cmax,
+                   float *__restrict__ nnz, float *__restrict__ energy)
 {
     const int32_t k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= n) return;
     const int lane = threadIdx.x & 31;
-    float m = 0.f;
-    for (int64_t s = lane; s < N; s += 32) m = fmaxf(m, fabsf(PT[lay.at(k, s)]));
+    float m = 0.f, c = 0.f;
+    double e = 0.0;
+    for (int64_t s = lane; s < N; s += 32) {
+        const float a = PT[lay.at(k, s)];
+        m = fmaxf(m, fabsf(a));
+        c += (a != 0.f) ? 1.f : 0.f;
+        e = fma((double)a, (double)a, e);
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) cmax[k] = m;
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    if (lane == 0) {
+        cmax[k] = m;
+        nnz[k] = c;
+        energy[k] = (float)e;
+    }
 }
 
 // Permuted row r (node row_map[r], bucket scale 1 / inv_scale[r]) of every sample -> three int8 digits;
@@ -480,36 +496,53 @@ __global__ void gram_stat_kernel(const double *__restrict__ r2part, const double
 // q[s] = the truncated digit form of sample s with itself: per bucket the integer sums c_p = sum_k sum_{x+y=p} d_x d_y
 // (exact, int64), combined with the SAME floating-point operations in the same order as the tile epilogue uses for
 // G[i,j] — so that q_i + q_j - 2 G[i,j] is exactly 0 when the digit rows of i and j coincide.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 gram_selfnorm_kernel(const int8_t *__restrict__ D0, const int8_t *__restrict__ D1, const int8_t *__restrict__ D2,
                      const int8_t *__restrict__ D3, const Lay ws, int64_t N, const Group *__restrict__ groups,
                      int32_t n_groups, double *__restrict__ q)
 {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= N) return;
+    // 32 samples x 16 row slices per block; integer partial sums are combined exactly through shared memory
+    __shared__ long long part[4][16][33];
+    const int sx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int64_t s = (int64_t)blockIdx.x * 32 + sx;
+    const bool ok = s < N;
     double acc = 0.0;
-    int32_t r = 0;
+    int32_t r0 = 0;
     for (int32_t g = 0; g < n_groups; g++) {
         const int32_t r_end = groups[g].stage_end * KC;
         long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        for (; r < r_end; r++) {
-            const int64_t o = ws.at(r, s);
-            const int x0 = D0[o], x1 = D1[o], x2 = D2[o], x3 = D3[o];
-            c0 += x0 * x0;
-            c1 += 2 * x0 * x1;
-            c2 += x1 * x1 + 2 * x0 * x2;
-            c3 += 2 * x0 * x3 + 2 * x1 * x2;
+        if (ok) {
+            for (int32_t r = r0 + sl; r < r_end; r += 16) {
+                const int64_t o = ws.at(r, s);
+                const int x0 = D0[o], x1 = D1[o], x2 = D2[o], x3 = D3[o];
+                c0 += x0 * x0;
+                c1 += 2 * x0 * x1;
+                c2 += x1 * x1 + 2 * x0 * x2;
+                c3 += 2 * x0 * x3 + 2 * x1 * x2;
+            }
         }
-        double w = groups[g].w0;
-        acc = fma((double)(int32_t)c0, w, acc);
-        w *= (1.0 / DIGIT);
-        acc = fma((double)(int32_t)c1, w, acc);
-        w *= (1.0 / DIGIT);
-        acc = fma((double)(int32_t)c2, w, acc);
-        w *= (1.0 / DIGIT);
-        acc = fma((double)(int32_t)c3, w, acc);
+        part[0][sl][sx] = c0;
+        part[1][sl][sx] = c1;
+        part[2][sl][sx] = c2;
+        part[3][sl][sx] = c3;
+        __syncthreads();
+        if (sl == 0 && ok) {
+            long long t[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int u = 0; u < 16; u++) t[c] += part[c][u][sx];
+            double w = groups[g].w0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {   // the epilogue's operations, in the epilogue's order
+                acc = fma((double)(int32_t)t[c], w, acc);
+                w *= (1.0 / DIGIT);
+            }
+        }
+        __syncthreads();
+        r0 = r_end;
     }
-    q[s] = acc;
+    if (sl == 0 && ok) q[s] = acc;
 }
 
 // lower triangle := transpose of the upper triangle (tiles tj > ti and the diagonal tiles), 32x32 sub-blocks.
@@ -612,15 +645,16 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     if (tiles.empty()) return FUF_OK;
 
     // ---- column maxima -> buckets (powers of four), permutation, stage table --------------------------------
-    int rc = ctx->ws_gram_small.reserve((size_t)n * sizeof(float));
+    int rc = ctx->ws_gram_small.reserve(3 * (size_t)n * sizeof(float));
     if (rc) return rc;
     float *d_cmax = (float *)ctx->ws_gram_small.ptr;
-    gram_colmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, d_cmax);
+    gram_colmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, d_cmax, d_cmax + n, d_cmax + 2 * n);
     FUF_CUDA(cudaGetLastError());
-    std::vector<float> cmax(n);
-    FUF_CUDA(cudaMemcpyAsync(cmax.data(), d_cmax, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    std::vector<float> cstat(3 * (size_t)n);
+    FUF_CUDA(cudaMemcpyAsync(cstat.data(), d_cmax, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
     FUF_CUDA(cudaStreamSynchronize(stream));
-    std::vector<std::pair<int32_t, int32_t>> keyed;  // (bucket exponent, node), all-zero columns dropped
+    const float *cmax = cstat.data(), *nnz = cmax + n, *energy = nnz + n;
+    std::vector<std::pair<int32_t, int32_t>> keyed, direct_keyed;  // (bucket exponent, node), all-zero columns dropped
     keyed.reserve(n);
     for (int32_t k = 0; k < n; k++) {
         FUF_REQUIRE(std::isfinite(cmax[k]), "fuf_pairwise_gram: profile column %d holds a non-finite value", k);
@@ -633,15 +667,47 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     std::sort(keyed.begin(), keyed.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) {
         return a.first > b.first || (a.first == b.first && a.second < b.second);
     });
-    // the columns of largest scale bypass the integer Gram: their S^2 is what the dropped product orders are relative
-    // to, and the direct (a-b)^2 kernel has no such term.  `keyed` is sorted by decreasing scale.
-    int32_t n_direct = GRAM_DIRECT_ROWS;
-    if (getenv("FUF_GRAM_DIRECT")) n_direct = std::max(0, atoi(getenv("FUF_GRAM_DIRECT")));
-    n_direct = std::min<int32_t>(n_direct, (int32_t)keyed.size());
+    // Bypass.  What the dropped product orders can cost a pair is bounded by 1.44e-9 (h2_i + h2_j), h2_s = sum of S_k^2
+    // over the sample's non-zero Gram columns; the refinement flags pairs with D < 2.9e-3 (h2_i + h2_j).  To keep
+    // ordinary pairs (D ~ q_i + q_j) a factor ~10 clear of that line, the columns contributing most to sum_s h2_s
+    // (S_k^2 nnz_k) are computed in float64 instead, until the mean h2 is below 30 x the mean squared norm, at most
+    // GRAM_DIRECT_ROWS of them.  `keyed` is sorted by decreasing scale.
+    {
+        double sum_h = 0.0, sum_e = 0.0;
+        std::vector<std::pair<double, size_t>> contrib;
+        contrib.reserve(keyed.size());
+        for (size_t i = 0; i < keyed.size(); i++) {
+            const int32_t k = keyed[i].second;
+            const double S = std::ldexp(1.0, keyed[i].first), h = S * S * (double)nnz[k];
+            contrib.emplace_back(h, i);
+            sum_h += h;
+            sum_e += (double)energy[k];
+        }
+        std::sort(contrib.begin(), contrib.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &b) {
+            return a.first > b.first || (a.first == b.first && a.second < b.second);
+        });
+        int32_t max_direct = GRAM_DIRECT_ROWS;
+        if (getenv("FUF_GRAM_DIRECT")) max_direct = std::max(0, atoi(getenv("FUF_GRAM_DIRECT")));
+        std::vector<uint8_t> bypass(keyed.size(), 0);
+        int32_t n_sel = 0;
+        for (size_t u = 0; u < contrib.size() && n_sel < max_direct && sum_h > 30.0 * sum_e; u++) {
+            bypass[contrib[u].second] = 1;   // (its energy stays in sum_e: D does not shrink when a column is bypassed)
+            sum_h -= contrib[u].first;
+            n_sel++;
+        }
+        if (getenv("FUF_GRAM_DIRECT") && max_direct > 0 && getenv("FUF_GRAM_DIRECT_FORCE"))  // test hook: exactly max_direct
+            for (size_t u = 0; u < contrib.size() && n_sel < max_direct; u++)
+                if (!bypass[contrib[u].second]) bypass[contrib[u].second] = 1, n_sel++;
+        std::vector<std::pair<int32_t, int32_t>> rest;
+        rest.reserve(keyed.size());
+        for (size_t i = 0; i < keyed.size(); i++) (bypass[i] ? direct_keyed : rest).push_back(keyed[i]);
+        keyed.swap(rest);
+    }
+    const int32_t n_direct = (int32_t)direct_keyed.size();
     const int32_t n_direct_pad = std::max(16, (n_direct + 15) / 16 * 16);
     std::vector<int32_t> direct_nodes(n_direct_pad, -1);
-    for (int32_t i = 0; i < n_direct; i++) direct_nodes[i] = keyed[i].second;
-    keyed.erase(keyed.begin(), keyed.begin() + n_direct);
+    for (int32_t i = 0; i < n_direct; i++) direct_nodes[i] = direct_keyed[i].second;
+    ctx->gram_bypassed = n_direct;
     std::vector<int32_t> row_map;
     std::vector<float> inv_scale;
     std::vector<Group> groups;
@@ -704,7 +770,7 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         FUF_CUDA(cudaGetLastError());
         gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(r2part, h2part, n_parts, n_cols, err_in, N, h2, err_out);
         FUF_CUDA(cudaGetLastError());
-        gram_selfnorm_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(D0, D1, D2, D3, ws, N, d_groups,
+        gram_selfnorm_kernel<<<(unsigned)((N + 31) / 32), 512, 0, stream>>>(D0, D1, D2, D3, ws, N, d_groups,
                                                                               (int32_t)groups.size(), q);
         FUF_CUDA(cudaGetLastError());
         dim3 gg((unsigned)((n_cols + 255) / 256), (unsigned)n_direct_pad);
@@ -712,7 +778,9 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         gram_gather_kernel<<<gg, 256, 0, stream>>>(PT, lay, sub, n_cols, N, d_dn, SUB);
         FUF_CUDA(cudaGetLastError());
         // bypass part first, in float64: D = sum over the bypassed node columns of (a_i - a_j)^2
-        gram_bypass_kernel<<<dim3((unsigned)tiles.size(), 4), 256, 0, stream>>>(d_tiles, SUB, sub, n_direct_pad, N, D, ldd);
+        // (with no bypassed column this just zeroes the tiles the Gram epilogue adds to)
+        gram_bypass_kernel<<<dim3((unsigned)tiles.size(), 4), 256, 0, stream>>>(d_tiles, SUB, sub, n_direct > 0 ? n_direct_pad : 0,
+                                                                               N, D, ldd);
         FUF_CUDA(cudaGetLastError());
     }
     ctx->launches += 5;
@@ -765,6 +833,14 @@ extern "C" int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_fl
     FUF_CUDA(cudaSetDevice(ctx->device));
     FUF_CUDA(cudaEventSynchronize(ctx->ev_gram[1]));
     FUF_CUDA(cudaEventElapsedTime(ms, ctx->ev_gram[0], ctx->ev_gram[1]));
+    return FUF_OK;
+}
+
+extern "C" int fuf_gram_last_info(const fuf_ctx *ctx, int32_t *n_buckets, int32_t *n_bypassed)
+{
+    FUF_REQUIRE(ctx && n_buckets && n_bypassed, "fuf_gram_last_info: null argument");
+    *n_buckets = ctx->gram_groups;
+    *n_bypassed = ctx->gram_bypassed;
     return FUF_OK;
 }
 

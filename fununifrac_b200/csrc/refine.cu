@@ -9,7 +9,9 @@
 // matrix once, and wherever the bound exceeds 0.5e-6 of the computed distance,
 //     L1:  D < kappa (rho_i + rho_j),   kappa = 2e6        L2:  D < kappa (r_i + r_j)^2,   kappa = 1.6e13
 // it recomputes the pair from the float64 pushed profiles P64T (sum over all n entries in double) and overwrites
-// D[i,j] (and D[j,i]).  Cost: one pass over the upper triangle of D plus ~2 n sector reads per refined pair.
+// D[i,j] (and D[j,i]).  Cost: one pass over the upper triangle of D plus ~2 n sector reads per refined pair
+// (~1 us): beyond `max_pairs` flagged pairs the kernel only counts, and the caller recomputes the whole matrix with
+// the float64 tile kernel (3 ns per pair) instead.
 #include "common.cuh"
 
 namespace fuf {
@@ -34,6 +36,7 @@ struct RefineParams {
     int linear;                // criterion D < kappa (s_i + s_j) on the raw statistic, whatever the mode
     const double *stat2;       // optional second statistic: additional linear criterion D < kappa2 (t_i + t_j)
     double kappa2;
+    unsigned long long budget; // pairs beyond this many flagged ones are counted but not recomputed
     unsigned long long *counter;
 };
 
@@ -53,7 +56,6 @@ refine_kernel(const RefineParams p)
     const int64_t segs_per_row = (p.j_end - p.j_begin + RSEG - 1) / RSEG;
     const int64_t n_items = (int64_t)p.n_rows_total * segs_per_row;
     const int64_t kstride = p.shard == 0 ? p.ldp64 : p.shard;
-    unsigned long long refined = 0;
     for (int64_t item = warp; item < n_items; item += n_warps) {
         const int64_t row = item / segs_per_row, seg = item % segs_per_row;
         int64_t gi = row;
@@ -82,13 +84,17 @@ refine_kernel(const RefineParams p)
                 if (p.stat2) flag = flag || !(d >= p.kappa2 * (ti + p.stat2[gj]));
             }
             unsigned mask = __ballot_sync(0xffffffffu, flag);
-            if (p.P64T == nullptr) {  // count-only mode
-                if (lane == 0) refined += __popc(mask);
-                continue;
-            }
+            if (mask == 0) continue;
+            // the counter counts FLAGGED pairs; only the first `budget` of them are recomputed here (beyond that the
+            // caller is better off recomputing everything with the float64 tile kernel)
+            unsigned long long first = 0;
+            if (lane == 0) first = atomicAdd(p.counter, (unsigned long long)__popc(mask));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (p.P64T == nullptr) continue;  // count-only mode
             while (mask) {
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
+                if (first++ >= p.budget) break;
                 const int64_t j = j0 + u * 32 + src;
                 const double *a = col_ptr(p, gi), *b = col_ptr(p, j);
                 double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -115,18 +121,16 @@ refine_kernel(const RefineParams p)
                         p.D2[row * p.ldd2 + j] = v;
                         if (p.mirror) p.D2[j * p.ldd2 + gi] = v;
                     }
-                    refined++;
                 }
             }
         }
     }
-    if (lane == 0 && refined) atomicAdd(p.counter, refined);
 }
 
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2, int64_t j_begin, int64_t j_end,
-           bool reset_counter, int criterion, const double *lin_stat, double lin_kappa)
+           bool reset_counter, int criterion, const double *lin_stat, double lin_kappa, int64_t max_pairs)
 {
     if (!ctx->d_refined) FUF_CUDA(cudaMalloc((void **)&ctx->d_refined, sizeof(unsigned long long)));
     if (reset_counter) FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
@@ -142,6 +146,7 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
     p.n = ctx->n;
     p.N = N;
     p.stat = err_stat;
+    p.budget = max_pairs > 0 ? (unsigned long long)max_pairs : ~0ull;
     p.stat2 = lin_stat;
     p.kappa2 = lin_kappa > 0 ? lin_kappa : 0.02;
     p.linear = (criterion == FUF_CRIT_LINEAR);
@@ -185,7 +190,7 @@ using namespace fuf;
 extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard,
                           int64_t shard_stride, int mode, const double *err_stat, double kappa, int criterion,
                           const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd,
-                          const double *lin_stat, double lin_kappa, void *stream)
+                          const double *lin_stat, double lin_kappa, int64_t max_pairs, void *stream)
 {
     FUF_REQUIRE(ctx && err_stat && D, "fuf_refine: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_refine: bad mode %d", mode);
@@ -200,7 +205,7 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
         FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
-                  (cudaStream_t)stream, nullptr, 0, 0, N, true, criterion, lin_stat, lin_kappa);
+                  (cudaStream_t)stream, nullptr, 0, 0, N, true, criterion, lin_stat, lin_kappa, max_pairs);
 }
 
 extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)

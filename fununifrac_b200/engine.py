@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -65,9 +65,10 @@ def load_library() -> ctypes.CDLL:
         L.fuf_center_of_pushed.argtypes = [vp, vp, i64, i64, vp, vp]
         L.fuf_round_pushed.argtypes = [vp, vp, i64, i64, ci, vp, vp, i64, vp, i64, vp]
         L.fuf_refine.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, ctypes.c_double, ci, vp, i32, vp, i64, vp,
-                                 ctypes.c_double, vp]
+                                 ctypes.c_double, i64, vp]
         L.fuf_pairwise_gram.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, vp, vp, vp, i32, vp, i64, vp]
         L.fuf_gram_last_kernel.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
+        L.fuf_gram_last_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
@@ -82,7 +83,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
                      "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count",
-                     "fuf_pairwise_gram", "fuf_gram_last_kernel",
+                     "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci
@@ -236,7 +237,17 @@ class TreeContext:
             return self.distances_gram(job, D=D)
         D = self.pairwise(job.PT, job.N, mode, D=D)
         if job.P64T is not None and job.N > 1:
-            self.refine(job.P64T, job.N, mode, job.err_stat, D)
+            D = self._refine_or_redo(job, mode, job.err_stat, D)
+        return D
+
+    def _refine_or_redo(self, job: "Pushed", mode: int, err_stat, D, lin_stat=None, lin_kappa: float = 0.0):
+        """Per-pair float64 refinement of up to 0.1 % of the pairs (~1 us each); when more are flagged the float64
+        tile kernel (~3 ns per pair) recomputes the whole matrix instead.  Returns D."""
+        budget = max(1024, job.N * (job.N - 1) // 2 // 1000)
+        self.refine(job.P64T, job.N, mode, err_stat, D, lin_stat=lin_stat, lin_kappa=lin_kappa, max_pairs=budget)
+        self.last_flagged = self.refine_count()
+        if self.last_flagged > budget:
+            D = self.pairwise_f64(job.P64T, job.N, mode, D=D)
         return D
 
     def pairwise_gram(self, PT, N: int, D=None, err_stat=None, tile_rows: Optional[Sequence[int]] = None,
@@ -267,18 +278,25 @@ class TreeContext:
         _check(self._lib.fuf_gram_last_kernel(self.handle, ctypes.byref(ms), ctypes.byref(fl)), "fuf_gram_last_kernel")
         return ms.value, fl.value
 
+    def gram_last_info(self) -> Tuple[int, int]:
+        """(scale buckets, float64-bypassed node columns) of the last Gram call."""
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        _check(self._lib.fuf_gram_last_info(self.handle, ctypes.byref(a), ctypes.byref(b)), "fuf_gram_last_info")
+        return a.value, b.value
+
     def distances_gram(self, job: "Pushed", D=None):
         """--L2 through the Gram kernel + both refinement passes (needs a job pushed with refine=True)."""
         assert job.P64T is not None, "the Gram path needs the float64 profiles for its refinement pass"
         D, q, err = self.pairwise_gram(job.PT, job.N, D=D, err_stat=job.err_stat)
+        self.gram_refined = 0
         if job.N > 1:    # one scan: rounding criterion on err, truncation criterion on the scale statistic h2
-            self.refine(job.P64T, job.N, MODE_L2, err, D, lin_stat=q, lin_kappa=GRAM_KAPPA)
-            self.gram_refined = self.refine_count()
+            D = self._refine_or_redo(job, MODE_L2, err, D, lin_stat=q, lin_kappa=GRAM_KAPPA)
+            self.gram_refined = self.last_flagged
         return D
 
     def refine(self, P64T, N: int, mode: int, err_stat, D, tile_rows: Optional[Sequence[int]] = None,
                shard: int = 0, shard_stride: int = 0, kappa: float = 0.0, criterion: int = 0, lin_stat=None,
-               lin_kappa: float = 0.0):
+               lin_kappa: float = 0.0, max_pairs: int = 0):
         """``fuf_refine``: recompute in float64 the pairs of D the fp32 operands cannot certify (in place)."""
         torch = _torch()
         assert err_stat.dtype == torch.float64 and D.dtype == torch.float64
@@ -291,7 +309,7 @@ class TreeContext:
                                     rows_arr.ctypes.data if rows_arr is not None else None,
                                     0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),
                                     None if lin_stat is None else lin_stat.data_ptr(), float(lin_kappa),
-                                    _stream_ptr(torch)), "fuf_refine")
+                                    int(max_pairs), _stream_ptr(torch)), "fuf_refine")
         return D
 
     def refine_count(self) -> int:

@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 4
+#define FUF_ABI_VERSION 5
 
 /* error codes */
 #define FUF_OK 0
@@ -162,8 +162,8 @@ int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
 /* --L2 on the tensor cores: D[i,j] = q_i + q_j - 2 (A A^T)[i,j] as an ERROR-FREE integer Gram matrix.
  * Node columns are bucketed by the power of two of their largest entry (bucket scale S); every entry becomes four
  * signed 8-bit digits, a / S = (d0 + d1/254 + d2/254^2 + d3/254^3) / 127; tcgen05.mma kind::i8 accumulates the digit
- * products of order 0..3 exactly in int32 tensor memory (10 MMAs per 32 basis rows); the 256 columns of largest scale
- * are computed in float64 instead.  D is then the exact squared distance of the quantised profiles up to the dropped
+ * products of order 0..3 exactly in int32 tensor memory (10 MMAs per 32 basis rows); the columns that dominate the
+ * scale statistic h2 (at most 256) are computed in float64 instead.  D is then the exact squared distance of the quantised profiles up to the dropped
  * product orders, |error| <= 1.44e-9 (h2_i + h2_j), and exactly 0 for identical samples.
  *   PT       device float, node-major, ld ldp (centred profiles quantise better)
  *   err_in   device, N doubles or NULL: the L2 rounding statistic of PT from fuf_push_up
@@ -181,6 +181,8 @@ int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int
  * it) and the int8 operations it executed (10 products x 2 x 128 x 128 x padded n per tile) — for the tensor-pipe
  * roofline. */
 int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_flops);
+/* Scale buckets and float64-bypassed node columns of the last fuf_pairwise_gram call. */
+int fuf_gram_last_info(const fuf_ctx *ctx, int32_t *n_buckets, int32_t *n_bypassed);
 
 /* Validation mode: everything in double. Full matrix only. */
 int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
@@ -194,12 +196,16 @@ int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, i
  * 0.02 for FUF_CRIT_LINEAR).
  * lin_stat != NULL adds, in the same scan, the linear criterion D[i,j] < lin_kappa (lin_stat[i] + lin_stat[j])
  * (lin_kappa <= 0: 0.02) — what the Gram path needs on top of the rounding criterion.
+ * max_pairs > 0: only the first max_pairs flagged pairs are recomputed, the rest are just counted — a per-pair
+ * recomputation costs ~1 us, the float64 tile kernel (fuf_pairwise_f64) ~3 ns per pair, so when more than ~0.3 %
+ * of the pairs are flagged the caller should recompute everything with fuf_pairwise_f64 (fuf_all_pairs_host does).
+ * fuf_refine_count returns the number of FLAGGED pairs.
  * P64T == NULL: count-only mode (D is not modified) — lets several GPUs agree on whether the float64 profiles
  * have to be exchanged at all.
  * fuf_refine_count synchronises the stream and returns how many pairs the last fuf_refine recomputed. */
 int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
                const double *err_stat, double kappa, int criterion, const int32_t *tile_rows_h, int32_t n_tile_rows,
-               double *D, int64_t ldd, const double *lin_stat, double lin_kappa, void *stream);
+               double *D, int64_t ldd, const double *lin_stat, double lin_kappa, int64_t max_pairs, void *stream);
 int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
 
 /* Join compact row blocks (as written by fuf_pairwise with tile_rows_h, possibly gathered from several

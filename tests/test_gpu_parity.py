@@ -613,3 +613,23 @@ def test_combined_table_cli(data_dir, golden_dir, tmp_path):
     assert rel_err(np.load(os.path.join(out, "t2.npy")), z["D_l2_quirk"]) < REL
     comb.main(["-e", edge, "-f", table, "-o", out, "-i", "t3", "--L2", "--validate"])
     assert rel_err(np.load(os.path.join(out, "t3.npy")), z["D_l2_quirk"]) < 1e-12
+
+
+def test_many_uncertified_pairs_fall_back_to_float64(full_tree):
+    """A data set dominated by near-duplicates: more pairs are flagged than per-pair refinement should handle
+    (budget: 0.1 % of the pairs, at least 1,024), so the float64 tile kernel redoes the whole matrix."""
+    inp, ctx, leaves = full_tree
+    N = 520
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=13)
+    rng = np.random.default_rng(13)
+    for c in range(1, 70):                                   # 70 jittered copies of sample 0: 2,415 tiny distances
+        X[c] = X[0] * (1 + 1e-4 * rng.random(ctx.n))
+        X[c] /= X[c].sum()
+    for l2 in (False, True):
+        mode = engine.MODE_L2 if l2 else engine.MODE_L1
+        Dref = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, X, l2), l2)
+        job = ctx.push_up_job(torch.from_numpy(X).cuda(), mode)
+        D = ctx.distances(job, mode).cpu().numpy()
+        assert ctx.last_flagged > 2000 and rel_err(D, Dref) < 1e-8       # float64 arithmetic on the float64 profiles
+        Dh = ctx.all_pairs_host(X, mode)
+        assert rel_err(Dh, Dref) < 1e-8
