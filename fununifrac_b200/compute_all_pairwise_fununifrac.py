@@ -61,9 +61,15 @@ def main(args):
     ##############################################################################
     # Computations
     ##############################################################################
-    results = make_emd_input.parallel_functional_profile_to_vector(num_threads, fun_files, input, abundance_key,
-                                                                   unweighted)
-    files, X = make_emd_input.profiles_to_matrix(results, len(input.basis))
+    if getattr(args, "python_ingest", False):
+        # the reference's own route: pandas.read_csv + a process pool (src/factory/make_emd_input.py:58-122)
+        results = make_emd_input.parallel_functional_profile_to_vector(num_threads, fun_files, input, abundance_key,
+                                                                       unweighted)
+        files, X = make_emd_input.profiles_to_matrix(results, len(input.basis))
+    else:
+        # native ingest (csrc/ingest.cu): C++ thread pool, only the two columns the path uses are tokenised;
+        # rows are bit-identical to the route above
+        files, X = make_emd_input.native_profiles_to_matrix(fun_files, input, abundance_key, unweighted, num_threads)
     assert files == fun_files
     mode = engine.MODE_L2 if is_L2 else engine.MODE_L1
     logging.info(f"Computing pairwise distances")

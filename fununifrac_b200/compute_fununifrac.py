@@ -40,6 +40,9 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument('--Ppushed', help="Flag indicating you want the pushed vectors to be saved.", action="store_true")
     parser.add_argument('--validate', help="Run the float64 validation kernels instead of the fp32 production path.",
                         action="store_true")
+    parser.add_argument('--python-ingest', dest="python_ingest", action="store_true",
+                        help="Read the gather CSVs with pandas and a process pool (the reference's route) instead of "
+                             "the native C++ ingest; the profiles are bit-identical either way.")
     return parser
 
 

@@ -1,0 +1,428 @@
+// ingest.cu — native ingest of sourmash `gather` CSV profiles (host code; no device work).
+//
+// Replaces the per-file work of the reference's ingest pool — pd.read_csv of all 29 columns followed by a Python
+// iterrows() loop (functional_profile_to_vector, src/factory/make_emd_input.py:82-122; pool :58-79) — with one pass
+// over the file bytes that tokenises only the two columns the path uses (`name` and the abundance key), looks the KO
+// up in a hash of the tree's node names and scatters into the dense profile row.  A thread pool runs over the files.
+//
+// Parity contract (pinned in tests/test_ingest_native.py against pandas + the Python mirror of the reference):
+//   * fields: RFC-4180 quoting as pandas' C tokenizer does it (delimiter ',', quote '"', doubled quotes, \r\n or \n,
+//     blank lines skipped, first non-blank line = header, short rows padded with NA, long rows = error);
+//   * numbers: pandas' default float parser for the C engine (`precise_xstrtod`: up to 17 significant digits
+//     accumulated in a double, one multiplication or division by an exact power of ten), its NA strings -> NaN;
+//     anything else in the abundance column is "not a number" (the reference raises ValueError, :99-103);
+//   * KO id: name.split(':')[-1] if the name starts with 'ko:' else name.split('|')[-1].split(':')[-1] (:105-109);
+//     unknown ids are reported back (the reference prints a warning and skips, :110-111); duplicate ids: the last
+//     row wins (plain assignment, :113);
+//   * P.sum() == 0 -> "empty profile" error (:117-119); P / P.sum() with numpy's pairwise summation (:120-121);
+//     --unweighted: P[P > 0] = 1 after the normalisation (:62-64).
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+struct fuf_name_index {
+    std::unordered_map<std::string, int32_t> map;
+    int32_t n = 0;
+};
+
+namespace fuf {
+namespace ingest {
+
+// numpy's float64 add-reduce over a contiguous vector: pairwise summation, 8-way unrolled 128-element base case.
+static double np_pairwise_sum(const double *a, ptrdiff_t n)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (ptrdiff_t i = 0; i < n; i++) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8], res;
+        ptrdiff_t i;
+        for (i = 0; i < 8; i++) r[i] = a[i];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int u = 0; u < 8; u++) r[u] += a[i + u];
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    ptrdiff_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+static const double *pow10_table()
+{
+    static double e[309];
+    static bool init = false;
+    if (!init) {
+        char buf[16];
+        for (int i = 0; i <= 308; i++) {
+            snprintf(buf, sizeof(buf), "1e%d", i);
+            e[i] = strtod(buf, nullptr);  // correctly rounded literals, as the compiler makes of pandas' table
+        }
+        init = true;
+    }
+    return e;
+}
+
+// pandas/_libs/src/parser/tokenizer.c: precise_xstrtod with decimal '.', sci 'E', no thousands separator, trailing
+// whitespace skipped.  Returns false if [s, s+len) is not entirely one number.
+static bool parse_double(const char *s, size_t len, double *out)
+{
+    const double *e = pow10_table();
+    const char *p = s, *end = s + len;
+    auto digit = [&](const char *q) { return q < end && *q >= '0' && *q <= '9'; };
+    while (p < end && (*p == ' ' || (*p >= '\t' && *p <= '\r'))) p++;
+    bool negative = false;
+    if (p < end && (*p == '-' || *p == '+')) negative = (*p++ == '-');
+    double number = 0.;
+    int exponent = 0, num_digits = 0, num_decimals = 0;
+    const int max_digits = 17;
+    while (digit(p)) {
+        if (num_digits < max_digits) {
+            number = number * 10. + (*p - '0');
+            num_digits++;
+        } else {
+            ++exponent;
+        }
+        p++;
+    }
+    if (p < end && *p == '.') {
+        p++;
+        while (num_digits < max_digits && digit(p)) {
+            number = number * 10. + (*p - '0');
+            p++;
+            num_digits++;
+            num_decimals++;
+        }
+        if (num_digits >= max_digits)
+            while (digit(p)) ++p;
+        exponent -= num_decimals;
+    }
+    if (num_digits == 0) return false;
+    if (negative) number = -number;
+    if (p < end && (*p == 'E' || *p == 'e')) {
+        const char *q = p + 1;
+        bool eneg = false;
+        if (q < end && (*q == '-' || *q == '+')) eneg = (*q++ == '-');
+        int n = 0, nd = 0;
+        while (digit(q) && nd < max_digits) {
+            n = n * 10 + (*q - '0');
+            nd++;
+            q++;
+        }
+        if (nd > 0) {  // pandas leaves p on the 'E' (and then fails the whole-field check) when no digits follow
+            exponent += eneg ? -n : n;
+            p = q;
+        }
+    }
+    if (exponent > 308) return false;  // pandas: ERANGE -> the column is not numeric
+    if (exponent > 0) {
+        number *= e[exponent];
+    } else if (exponent < -308) {
+        if (exponent < -616) {
+            number = 0.;
+        } else {
+            number /= e[-308 - exponent];
+            number /= e[308];
+        }
+    } else {
+        number /= e[-exponent];
+    }
+    if (number == HUGE_VAL || number == -HUGE_VAL) return false;
+    while (p < end && (*p == ' ' || (*p >= '\t' && *p <= '\r'))) p++;
+    if (p != end) return false;
+    *out = number;
+    return true;
+}
+
+static bool is_na(const char *s, size_t len)
+{
+    static const char *na[] = {"", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN",
+                               "<NA>", "N/A", "NA", "NULL", "NaN", "None", "n/a", "nan", "null"};
+    for (const char *w : na)
+        if (strlen(w) == len && memcmp(w, s, len) == 0) return true;
+    return false;
+}
+
+// Non-NA text pandas' float conversion accepts besides plain numbers: infinities, any case.
+static bool parse_special(const char *s, size_t len, double *out)
+{
+    std::string t(s, len);
+    bool neg = false;
+    size_t i = 0;
+    if (i < t.size() && (t[i] == '-' || t[i] == '+')) neg = (t[i++] == '-');
+    std::string r = t.substr(i);
+    for (auto &c : r) c = (char)tolower((unsigned char)c);
+    if (r == "inf" || r == "infinity") {
+        *out = neg ? -INFINITY : INFINITY;
+        return true;
+    }
+    return false;
+}
+
+struct Field {
+    const char *p;
+    size_t len;
+    bool quoted;
+};
+
+// One record starting at *cur: fields appended to `fields` (unescaped text lives in `scratch` when a quoted field
+// contains doubled quotes).  Returns false at end of input.
+static bool next_record(const char *&cur, const char *end, std::vector<Field> &fields, std::vector<std::string> &scratch)
+{
+    fields.clear();
+    scratch.clear();
+    if (cur >= end) return false;
+    for (;;) {
+        Field f{cur, 0, false};
+        if (cur < end && *cur == '"') {
+            f.quoted = true;
+            const char *q = cur + 1;
+            bool escaped = false;
+            const char *start = q;
+            while (q < end) {
+                if (*q == '"') {
+                    if (q + 1 < end && q[1] == '"') {
+                        escaped = true;
+                        q += 2;
+                        continue;
+                    }
+                    break;
+                }
+                q++;
+            }
+            const char *close = q;
+            if (escaped) {
+                std::string s;
+                for (const char *r = start; r < close; r++) {
+                    s.push_back(*r);
+                    if (*r == '"') r++;
+                }
+                scratch.push_back(std::move(s));
+                f.p = nullptr;  // resolved below (scratch may reallocate)
+                f.len = scratch.size() - 1;
+            } else {
+                f.p = start;
+                f.len = (size_t)(close - start);
+            }
+            cur = close < end ? close + 1 : end;
+            // pandas appends whatever follows the closing quote up to the delimiter
+            const char *tail = cur;
+            while (cur < end && *cur != ',' && *cur != '\n' && *cur != '\r') cur++;
+            if (cur > tail) {
+                std::string s = (f.p ? std::string(f.p, f.len) : scratch[f.len]) + std::string(tail, cur - tail);
+                scratch.push_back(std::move(s));
+                f.p = nullptr;
+                f.len = scratch.size() - 1;
+            }
+        } else {
+            while (cur < end && *cur != ',' && *cur != '\n' && *cur != '\r') cur++;
+            f.len = (size_t)(cur - f.p);
+        }
+        fields.push_back(f);
+        if (cur >= end) break;
+        if (*cur == ',') {
+            cur++;
+            if (cur >= end) {  // trailing delimiter: one more empty field
+                fields.push_back(Field{cur, 0, false});
+                break;
+            }
+            continue;
+        }
+        if (*cur == '\r') {
+            cur++;
+            if (cur < end && *cur == '\n') cur++;
+        } else {
+            cur++;  // '\n'
+        }
+        break;
+    }
+    for (auto &f : fields)
+        if (!f.p) {
+            const std::string &s = scratch[f.len];
+            f.p = s.data();
+            f.len = s.size();
+        }
+    return true;
+}
+
+struct FileResult {
+    int rc = 0;  // 0 ok; 1 not a number; 2 empty profile; 3 io / malformed; 4 bad name
+    std::string message, warnings;
+};
+
+static void set_msg(FileResult &r, int rc, const std::string &m)
+{
+    r.rc = rc;
+    r.message = m;
+}
+
+static void parse_file(const fuf_name_index *index, const char *path, const std::string &key, bool normalize, bool unweighted,
+                       double *P, FileResult &res)
+{
+    const int32_t n = index->n;
+    for (int32_t k = 0; k < n; k++) P[k] = 0.0;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return set_msg(res, 3, std::string("cannot open ") + path + ": " + strerror(errno));
+    std::string buf;
+    {
+        char chunk[1 << 16];
+        size_t got;
+        while ((got = fread(chunk, 1, sizeof(chunk), fp)) > 0) buf.append(chunk, got);
+        fclose(fp);
+    }
+    const char *cur = buf.data(), *end = cur + buf.size();
+    if (buf.size() >= 3 && (unsigned char)cur[0] == 0xEF && (unsigned char)cur[1] == 0xBB && (unsigned char)cur[2] == 0xBF) cur += 3;
+    std::vector<Field> fields;
+    std::vector<std::string> scratch;
+    auto blank = [&](const std::vector<Field> &f) { return f.size() == 1 && f[0].len == 0 && !f[0].quoted; };
+    // header
+    do {
+        if (!next_record(cur, end, fields, scratch)) return set_msg(res, 3, std::string("No columns to parse from file ") + path);
+    } while (blank(fields));
+    int name_col = -1, key_col = -1;
+    const size_t n_cols = fields.size();
+    for (size_t c = 0; c < n_cols; c++) {
+        std::string h(fields[c].p, fields[c].len);
+        if (h == "name" && name_col < 0) name_col = (int)c;
+        if (h == key && key_col < 0) key_col = (int)c;
+    }
+    if (key_col < 0) return set_msg(res, 5, key);          // KeyError(abundance_key) in the reference
+    if (name_col < 0) return set_msg(res, 5, "name");
+    long long line = 1;
+    while (next_record(cur, end, fields, scratch)) {
+        line++;
+        if (blank(fields)) continue;
+        if (fields.size() > n_cols)
+            return set_msg(res, 3, "Error tokenizing data. C error: Expected " + std::to_string(n_cols) + " fields in line " +
+                                       std::to_string(line) + ", saw " + std::to_string(fields.size()));
+        // abundance
+        double value = NAN;
+        if ((size_t)key_col < fields.size()) {
+            const Field &f = fields[key_col];
+            if (!(is_na(f.p, f.len) && !(f.quoted && f.len == 0 && false))) {
+                if (!parse_double(f.p, f.len, &value) && !parse_special(f.p, f.len, &value))
+                    return set_msg(res, 1, std::string(f.p, f.len));
+            }
+        }
+        // name -> KO id
+        if ((size_t)name_col >= fields.size() || is_na(fields[name_col].p, fields[name_col].len))
+            return set_msg(res, 4, "nan");
+        const Field &nf = fields[name_col];
+        const char *b = nf.p, *e = nf.p + nf.len;
+        if (!(nf.len >= 3 && memcmp(b, "ko:", 3) == 0)) {
+            for (const char *q = e; q > b; q--)
+                if (q[-1] == '|') {
+                    b = q;
+                    break;
+                }
+        }
+        for (const char *q = e; q > b; q--)
+            if (q[-1] == ':') {
+                b = q;
+                break;
+            }
+        std::string ko(b, e - b);
+        auto it = index->map.find(ko);
+        if (it == index->map.end()) {
+            res.warnings += ko;
+            res.warnings.push_back('\n');
+        } else {
+            P[it->second] = value;
+        }
+    }
+    const double total = np_pairwise_sum(P, n);
+    if (total == 0) return set_msg(res, 2, "");
+    if (normalize)
+        for (int32_t k = 0; k < n; k++) P[k] = P[k] / total;
+    if (unweighted)
+        for (int32_t k = 0; k < n; k++)
+            if (P[k] > 0) P[k] = 1;
+}
+
+}  // namespace ingest
+}  // namespace fuf
+
+using namespace fuf;
+
+extern "C" int fuf_name_index_create(fuf_name_index **out, const char *const *names, int32_t n)
+{
+    FUF_REQUIRE(out && names && n >= 0, "fuf_name_index_create: bad argument");
+    fuf_name_index *ix = new (std::nothrow) fuf_name_index();
+    if (!ix) {
+        set_error("fuf_name_index_create: out of host memory");
+        return FUF_ENOMEM;
+    }
+    ix->n = n;
+    ix->map.reserve((size_t)n * 2);
+    for (int32_t k = 0; k < n; k++) ix->map[std::string(names[k])] = k;  // a repeated name keeps its last index (dict semantics)
+    *out = ix;
+    return FUF_OK;
+}
+
+extern "C" int fuf_name_index_destroy(fuf_name_index *ix)
+{
+    delete ix;
+    return FUF_OK;
+}
+
+extern "C" int fuf_ingest_gather_csv(const fuf_name_index *index, const char *const *paths, int32_t n_files,
+                                     const char *abundance_key, int normalize, int unweighted, int n_threads, double *X,
+                                     int64_t ldx, int32_t *status, char *messages, int64_t message_stride, char *warnings,
+                                     int64_t warnings_cap)
+{
+    FUF_REQUIRE(index && paths && abundance_key && X && status && n_files >= 0 && ldx >= index->n,
+                "fuf_ingest_gather_csv: bad argument");
+    FUF_REQUIRE(!messages || message_stride > 0, "fuf_ingest_gather_csv: message_stride must be positive");
+    ingest::pow10_table();  // initialise before the threads start
+    std::vector<ingest::FileResult> results((size_t)n_files);
+    const std::string key(abundance_key);
+    std::atomic<int32_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int32_t f = next.fetch_add(1);
+            if (f >= n_files) break;
+            ingest::parse_file(index, paths[f], key, normalize != 0, unweighted != 0, X + (size_t)f * ldx, results[f]);
+        }
+    };
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::max(1, (int)n_files)));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+    worker();
+    for (auto &th : pool) th.join();
+    int64_t wpos = 0;
+    int n_failed = 0;
+    for (int32_t f = 0; f < n_files; f++) {
+        status[f] = results[f].rc;
+        if (results[f].rc) n_failed++;
+        if (messages) {
+            snprintf(messages + (size_t)f * message_stride, (size_t)message_stride, "%s", results[f].message.c_str());
+        }
+        if (warnings && !results[f].warnings.empty()) {  // "<file index>\t<ko>\n" per unknown id, in file and row order
+            size_t start = 0;
+            const std::string &w = results[f].warnings;
+            while (start < w.size()) {
+                size_t nl = w.find('\n', start);
+                std::string line = std::to_string(f) + "\t" + w.substr(start, nl - start) + "\n";
+                if (wpos + (int64_t)line.size() < warnings_cap) {
+                    memcpy(warnings + wpos, line.data(), line.size());
+                    wpos += (int64_t)line.size();
+                }
+                start = nl + 1;
+            }
+        }
+    }
+    if (warnings && warnings_cap > 0) warnings[std::min(wpos, warnings_cap - 1)] = '\0';
+    return n_failed ? 1 : FUF_OK;
+}

@@ -79,11 +79,16 @@ def load_library() -> ctypes.CDLL:
         L.fuf_all_pairs_host.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, ci]
         L.fuf_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                                       ctypes.POINTER(ctypes.c_float)]
+        L.fuf_name_index_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_char_p), i32]
+        L.fuf_name_index_destroy.argtypes = [vp]
+        L.fuf_ingest_gather_csv.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), i32, ctypes.c_char_p, ci, ci, ci, vp, i64,
+                                            vp, ctypes.c_char_p, i64, ctypes.c_char_p, i64]
         L.fuf_launch_count.argtypes = [vp]
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
                      "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count",
-                     "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info",
+                     "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_name_index_create",
+                     "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci

@@ -14,6 +14,7 @@ path that keeps the reference's error order for malformed inputs.
 from __future__ import annotations
 
 import multiprocessing
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -215,6 +216,59 @@ def parallel_functional_profile_to_vector(num_threads, fun_files, input: FuncTre
                            [(f, abundance_key, unweighted) for f in fun_files],
                            chunksize=max(2, len(fun_files) // num_threads))
     return results
+
+
+def native_profiles_to_matrix(fun_files, input: FuncTreeEmduInput, abundance_key, unweighted, num_threads=0,
+                              normalize=True, out: Optional[np.ndarray] = None) -> Tuple[List[str], np.ndarray]:
+    """All gather CSVs → dense X[N, n] through the native ingest (``fuf_ingest_gather_csv``, csrc/ingest.cu): a C++
+    thread pool that tokenises only the ``name`` and abundance columns of each file.  Row f is bit-for-bit what
+    ``functional_profile_to_vector(pd.read_csv(fun_files[f]), input, abundance_key)`` returns; warnings are printed
+    and errors raised as the reference does, for the first failing file in ``fun_files`` order."""
+    import ctypes
+
+    from fununifrac_b200 import engine
+
+    L = engine.load_library()
+    fun_files = list(fun_files)
+    n = len(input.idx_to_node)
+    names = [str(input.idx_to_node[k]).encode() for k in range(n)]
+    arr = (ctypes.c_char_p * n)(*names)
+    ix = ctypes.c_void_p()
+    engine._check(L.fuf_name_index_create(ctypes.byref(ix), arr, n), "fuf_name_index_create")
+    try:
+        N = len(fun_files)
+        X = out if out is not None else np.zeros((N, n), dtype=np.float64)
+        if X.dtype != np.float64 or X.shape[0] < N or X.shape[1] < n or X.strides[1] != 8:
+            raise ValueError("out must be a C-ordered float64 [>=N, >=n] array")
+        paths = (ctypes.c_char_p * max(N, 1))(*[os.fsencode(f) for f in fun_files])
+        status = np.zeros(max(N, 1), dtype=np.int32)
+        stride = 512
+        messages = ctypes.create_string_buffer(stride * max(N, 1))
+        wcap = 1 << 20
+        warnings = ctypes.create_string_buffer(wcap)
+        rc = L.fuf_ingest_gather_csv(ix, paths, N, str(abundance_key).encode(), int(bool(normalize)),
+                                     int(bool(unweighted)), int(num_threads or 0), X.ctypes.data,
+                                     X.strides[0] // 8 if N else n, status.ctypes.data, messages, stride, warnings, wcap)
+        if rc < 0:
+            engine._check(rc, "fuf_ingest_gather_csv")
+        for line in warnings.value.decode("utf-8", "replace").splitlines():
+            print(f"Warning: {line.split(chr(9), 1)[1]} not found in EMDU index, skipping.")
+        for f in range(N):
+            if status[f]:
+                msg = messages.raw[f * stride:(f + 1) * stride].split(b"\0", 1)[0].decode("utf-8", "replace")
+                if status[f] == 1:
+                    raise ValueError(f"The abundance key {abundance_key} gives a value that is not a number: {msg}")
+                if status[f] == 2:
+                    raise Exception(f"Functional profile is empty! Perhaps try a different abundance key? "
+                                    f"You used {abundance_key}.")
+                if status[f] == 4:
+                    raise Exception(f"Could not parse the name {msg} in the functional profile")
+                if status[f] == 5:
+                    raise KeyError(msg)
+                raise Exception(f"{fun_files[f]}: {msg}")
+        return fun_files, X[:N]
+    finally:
+        L.fuf_name_index_destroy(ix)
 
 
 def profiles_to_matrix(results, n: int) -> Tuple[List[str], np.ndarray]:

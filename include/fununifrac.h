@@ -7,6 +7,7 @@
  *
  *   fuf_tree_create      <- the arrays tree_to_EMDU_input builds        src/factory/make_emd_input.py:10-54
  *                           (Tint -> parent[], lint -> edge_length[], postorder, root last)
+ *   fuf_ingest_gather_csv <- functional_profile_to_vector + ingest pool  src/factory/make_emd_input.py:58-122
  *   fuf_push_up          <- push_up_L1 / push_up_L2 over all samples    src/algorithms/emd_unifrac.py:20-39
  *   fuf_push_up_center   <- (no counterpart) the common vector subtracted from every pushed profile before it
  *                           is rounded to fp32; distances are invariant under it
@@ -87,6 +88,7 @@ extern "C" {
 #define FUF_TILE 128 /* edge of a distance-matrix tile; shard boundaries must be multiples of it */
 
 typedef struct fuf_ctx fuf_ctx;
+typedef struct fuf_name_index fuf_name_index; /* node name -> basis index (host) */
 
 typedef struct fuf_tree_info {
     int32_t n;           /* nodes incl. root */
@@ -235,6 +237,24 @@ int fuf_last_timing(const fuf_ctx *ctx, float *h2d_pushup_ms, float *pairwise_ms
 
 /* Number of kernel launches issued by this library since the context was created (bench bookkeeping). */
 int64_t fuf_launch_count(const fuf_ctx *ctx);
+
+/* Native ingest of sourmash gather CSVs (host only; replaces pd.read_csv + functional_profile_to_vector per file and
+ * the ingest pool, src/factory/make_emd_input.py:58-122).
+ *   fuf_name_index_create: names[k] = name of basis node k (idx_to_node of tree_to_EMDU_input), n of them.
+ *   fuf_ingest_gather_csv: file f -> row f of X (host double, row-major, ld ldx >= n): the un-pushed profile exactly as
+ *     functional_profile_to_vector(pd.read_csv(path), input, abundance_key, normalize) returns it (then P[P>0] = 1
+ *     when `unweighted`), parsed by n_threads threads (<= 0: all cores).
+ *     status[f]: 0 ok, 1 abundance not a number (messages: the offending text; reference: ValueError), 2 empty profile
+ *     (reference: Exception "Functional profile is empty!"), 3 unreadable / malformed file (messages: why), 4 name
+ *     missing (reference: Exception "Could not parse the name"), 5 column missing (messages: its name; KeyError).
+ *     messages: n_files slots of message_stride bytes (may be NULL); warnings: "<file index>\t<id>\n" for every id
+ *     that is not in the tree, in file and row order (the reference prints a warning and skips the row), truncated
+ *     at warnings_cap.  Returns 0, or 1 if any file failed (see status). */
+int fuf_name_index_create(fuf_name_index **out, const char *const *names, int32_t n);
+int fuf_name_index_destroy(fuf_name_index *index);
+int fuf_ingest_gather_csv(const fuf_name_index *index, const char *const *paths, int32_t n_files, const char *abundance_key,
+                          int normalize, int unweighted, int n_threads, double *X, int64_t ldx, int32_t *status,
+                          char *messages, int64_t message_stride, char *warnings, int64_t warnings_cap);
 
 /* Test hook, host only (needs no device): the plan of the chunked push-up for a postorder parent array.
  * Arrays of length n; span_out gets 5 ints per spanning node (k, chunk_first, chunk_last, slot_start, slot_k). */
