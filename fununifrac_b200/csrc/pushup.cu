@@ -36,7 +36,7 @@ namespace fuf {
 constexpr int KT = kPushChunk;  // nodes per chunk
 constexpr int TI = 128;         // samples per CTA
 
-template <typename TX, int MODE>
+template <typename TX, int MODE, bool HAS_PT, bool HAS_P64>
 __global__ void __launch_bounds__(TI)
 pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n, const double *__restrict__ w,
                     const int32_t *__restrict__ parent_local, const int32_t *__restrict__ cp_after,
@@ -89,8 +89,8 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
     }
     double r = 0.0;    // running sum of X over the chunk (chunk-local prefix)
     double err = 0.0;  // rounding-error statistic of the float outputs of this chunk
-    float *pt = PT ? PT + (int64_t)k0 * ldp + col0 + s : nullptr;          // walks down the node rows
-    double *p64 = P64T ? P64T + (int64_t)k0 * ldp64 + col0 + s : nullptr;
+    float *pt = HAS_PT ? PT + (int64_t)k0 * ldp + col0 + s : nullptr;          // walks down the node rows
+    double *p64 = HAS_P64 ? P64T + (int64_t)k0 * ldp64 + col0 + s : nullptr;
     double *cps = CP + s;
     double *mine = &S[0][tid];
 #pragma unroll
@@ -102,8 +102,8 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
         if (pl >= 0) mine[pl * (TI + 1)] += Sk;
         if (!(meta & 0x80)) {
             const double v = s_w[kk] * Sk;
-            if (p64) *p64 = v;
-            if (pt) {
+            if (HAS_P64) *p64 = v;
+            if (HAS_PT) {
                 const double c = v - s_c[kk];
                 const float f = (float)c;
                 *pt = f;
@@ -113,8 +113,8 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
         }
         const int cp = (meta >> 8) - 1;
         if (cp >= 0) cps[(int64_t)cp * ldt] = r;
-        if (pt) pt += ldp;
-        if (p64) p64 += ldp64;
+        if (HAS_PT) pt += ldp;
+        if (HAS_P64) p64 += ldp64;
     }
     if (T) T[(int64_t)blockIdx.x * ldt + s] = r;
     if (R) R[(int64_t)blockIdx.x * ldt + s] = err;
@@ -378,23 +378,27 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
                 65535 * TI);
     dim3 grid(ctx->n_chunks, (unsigned)((N + TI - 1) / TI));
     const size_t smem_f = sizeof(double) * KT * (TI + 1), smem_d = smem_f;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
-        FUF_CUDA(cudaFuncSetAttribute(pushup_chunk_kernel<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
-        attr_set = true;
-    }
-#define FUF_CHUNK(TX, MODE_, SMEM)                                                                                  \
-    pushup_chunk_kernel<TX, MODE_><<<grid, TI, SMEM, stream>>>((const TX *)X, ldx, N, n, ctx->d_w[mode],            \
-                                                              ctx->d_parent_local, ctx->d_cp_after, ctx->d_is_span, \
-                                                              center, PT, ldp, P64T, ldp64, col0, T, CP, R, ldt)
+    // one instantiation per (input type, mode, which outputs exist): no pointer tests in the per-node loop
+#define FUF_CHUNK(TX, MODE_, HP, H6)                                                                                  \
+    do {                                                                                                              \
+        auto kern = pushup_chunk_kernel<TX, MODE_, HP, H6>;                                                           \
+        FUF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));               \
+        kern<<<grid, TI, smem_f, stream>>>((const TX *)X, ldx, N, n, ctx->d_w[mode], ctx->d_parent_local,             \
+                                           ctx->d_cp_after, ctx->d_is_span, center, PT, ldp, P64T, ldp64, col0, T, CP, \
+                                           R, ldt);                                                                   \
+    } while (0)
+#define FUF_CHUNK_OUT(TX, MODE_)                                                                                      \
+    do {                                                                                                              \
+        if (PT && P64T) FUF_CHUNK(TX, MODE_, true, true);                                                             \
+        else if (PT) FUF_CHUNK(TX, MODE_, true, false);                                                               \
+        else FUF_CHUNK(TX, MODE_, false, true);                                                                       \
+    } while (0)
     if (x_dtype == FUF_F32) {
-        if (mode == FUF_MODE_L1) FUF_CHUNK(float, 0, smem_f); else FUF_CHUNK(float, 1, smem_f);
+        if (mode == FUF_MODE_L1) FUF_CHUNK_OUT(float, 0); else FUF_CHUNK_OUT(float, 1);
     } else {
-        if (mode == FUF_MODE_L1) FUF_CHUNK(double, 0, smem_d); else FUF_CHUNK(double, 1, smem_d);
+        if (mode == FUF_MODE_L1) FUF_CHUNK_OUT(double, 0); else FUF_CHUNK_OUT(double, 1);
     }
+#undef FUF_CHUNK_OUT
 #undef FUF_CHUNK
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
