@@ -105,6 +105,65 @@ int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t l
     return FUF_OK;
 }
 
+// K4b diffab_gather_kernel: the sub-block T[rows_i, rows_j, nodes] of the antisymmetric diffab tensor the reference
+// materialises as COO minus its transpose (src/algorithms/emd_unifrac.py:56-72) and slices through
+// DiffabArrayIndexer.get_diffab / get_diffab_for_node (src/utility/differential_abundance.py:18-55).  The store is the
+// pushed matrix itself (N x n instead of N x N x n); same transpose-through-shared-memory tile as K4.
+template <typename TP, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+diffab_gather_kernel(const TP *__restrict__ P, int64_t ldp, const int32_t *__restrict__ rows_i,
+                     const int32_t *__restrict__ rows_j, int32_t nb, const int32_t *__restrict__ nodes, int32_t nk,
+                     TO *__restrict__ out)
+{
+    __shared__ TP tile[32][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int32_t c0 = blockIdx.x * 32, b0 = blockIdx.y * 32, a = blockIdx.z;
+    const int32_t i = rows_i[a];
+    const int32_t b = b0 + lx;
+    const int32_t j = b < nb ? rows_j[b] : -1;
+    for (int cc = ly; cc < 32; cc += 8) {
+        const int32_t c = c0 + cc;
+        TP d = TP(0);
+        if (c < nk && j >= 0) {
+            const int64_t k = nodes ? nodes[c] : c;
+            d = P[k * ldp + i] - P[k * ldp + j];
+            if (MODE == FUF_MODE_L2) d = (j > i) ? d * d : -(d * d);   // i == j: d == 0 either way
+        }
+        tile[cc][lx] = d;
+    }
+    __syncthreads();
+    const int32_t c = c0 + lx;
+    const int32_t cnt = min(32, nb - b0);
+    if (c < nk)
+        for (int q = ly; q < cnt; q += 8) out[((int64_t)a * nb + b0 + q) * nk + c] = (TO)tile[lx][q];
+}
+
+int diffab_gather(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t ldp, int mode, const int32_t *rows_i, int64_t na,
+                  const int32_t *rows_j, int64_t nb, const int32_t *nodes, int64_t nk, void *out, int out_dtype,
+                  cudaStream_t stream)
+{
+    if (na == 0 || nb == 0 || nk == 0) return FUF_OK;
+    dim3 grid((unsigned)((nk + 31) / 32), (unsigned)((nb + 31) / 32), (unsigned)na);
+    FUF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "fuf_diffab_gather: more than 65535 rows_i or 2097120 rows_j");
+#define LAUNCH(TP, TO)                                                                                       \
+    do {                                                                                                     \
+        if (mode == FUF_MODE_L1)                                                                             \
+            diffab_gather_kernel<TP, TO, FUF_MODE_L1><<<grid, 256, 0, stream>>>(                             \
+                (const TP *)PT, ldp, rows_i, rows_j, (int32_t)nb, nodes, (int32_t)nk, (TO *)out);            \
+        else                                                                                                 \
+            diffab_gather_kernel<TP, TO, FUF_MODE_L2><<<grid, 256, 0, stream>>>(                             \
+                (const TP *)PT, ldp, rows_i, rows_j, (int32_t)nb, nodes, (int32_t)nk, (TO *)out);            \
+    } while (0)
+    if (p_dtype == FUF_F32 && out_dtype == FUF_F32) LAUNCH(float, float);
+    else if (p_dtype == FUF_F32 && out_dtype == FUF_F64) LAUNCH(float, double);
+    else if (p_dtype == FUF_F64 && out_dtype == FUF_F32) LAUNCH(double, float);
+    else LAUNCH(double, double);
+#undef LAUNCH
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
 }  // namespace fuf
 
 using namespace fuf;
@@ -119,4 +178,22 @@ extern "C" int fuf_diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64
     FUF_REQUIRE(N >= 0 && ldp >= N, "fuf_diffab_block: bad shape");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return diffab_block(ctx, PT, p_dtype, N, ldp, mode, pair_begin, pair_end, out, out_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int fuf_diffab_gather(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode,
+                                 const int32_t *rows_i, int64_t na, const int32_t *rows_j, int64_t nb,
+                                 const int32_t *nodes, int64_t nk, void *out, int out_dtype, void *stream)
+{
+    FUF_REQUIRE(ctx, "fuf_diffab_gather: null context");
+    if (na == 0 || nb == 0 || nk == 0) return FUF_OK;
+    FUF_REQUIRE(PT && out && rows_i && rows_j, "fuf_diffab_gather: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_diffab_gather: bad mode %d", mode);
+    FUF_REQUIRE((p_dtype == FUF_F32 || p_dtype == FUF_F64) && (out_dtype == FUF_F32 || out_dtype == FUF_F64),
+                "fuf_diffab_gather: bad dtype");
+    FUF_REQUIRE(N >= 0 && ldp >= N && na >= 0 && nb >= 0 && nk >= 0, "fuf_diffab_gather: bad shape");
+    FUF_REQUIRE(nodes || nk == ctx->n, "fuf_diffab_gather: nodes == NULL needs nk == n (%d), got %lld", ctx->n,
+                (long long)nk);
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return diffab_gather(ctx, PT, p_dtype, ldp, mode, rows_i, na, rows_j, nb, nodes, nk, out, out_dtype,
+                         (cudaStream_t)stream);
 }

@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 5
+ABI_VERSION = 6
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, vp]
         L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
         L.fuf_diffab_block.argtypes = [vp, vp, ci, i64, i64, ci, i64, i64, vp, ci, vp]
+        L.fuf_diffab_gather.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, vp, i64, vp, i64, vp, ci, vp]
         L.fuf_all_pairs_host.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, ci]
         L.fuf_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                                       ctypes.POINTER(ctypes.c_float)]
@@ -90,6 +91,7 @@ def load_library() -> ctypes.CDLL:
                      "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_name_index_create",
                      "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
+                     "fuf_diffab_gather",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
@@ -403,6 +405,35 @@ class TreeContext:
         _check(self._lib.fuf_diffab_block(self.handle, PT.data_ptr(), _dtype_code(PT), N, PT.stride(0), mode,
                                           pair_begin, pair_end, out.data_ptr(), _dtype_code(out),
                                           _stream_ptr(torch)), "fuf_diffab_block")
+        return out
+
+    def diffab_gather(self, PT, N: int, mode: int, rows_i, rows_j, nodes=None, out=None):
+        """``out[a, b, c] = T[rows_i[a], rows_j[b], nodes[c]]`` of the antisymmetric diffab tensor (see
+        ``fuf_diffab_gather``); index arguments are integer sequences / arrays, checked here."""
+        torch = _torch()
+
+        def dev_index(v, limit, what):
+            a = np.asarray(v, dtype=np.int64).reshape(-1)
+            if a.size and (a.min() < -limit or a.max() >= limit):
+                raise IndexError(f"{what} index out of range for size {limit}")
+            a = np.where(a < 0, a + limit, a).astype(np.int32)
+            return torch.from_numpy(a).to(PT.device)
+
+        ri, rj = dev_index(rows_i, N, "sample"), dev_index(rows_j, N, "sample")
+        nk = self.n if nodes is None else None
+        nd = None
+        if nodes is not None:
+            nd = dev_index(nodes, self.n, "node")
+            nk = nd.numel()
+        if out is None:
+            out = torch.empty((ri.numel(), rj.numel(), nk), dtype=torch.float64, device=PT.device)
+        assert out.is_contiguous() and tuple(out.shape) == (ri.numel(), rj.numel(), nk)
+        if out.numel() == 0:
+            return out
+        _check(self._lib.fuf_diffab_gather(self.handle, PT.data_ptr(), _dtype_code(PT), N, PT.stride(0), mode,
+                                           ri.data_ptr(), ri.numel(), rj.data_ptr(), rj.numel(),
+                                           nd.data_ptr() if nd is not None else None, nk, out.data_ptr(),
+                                           _dtype_code(out), _stream_ptr(torch)), "fuf_diffab_gather")
         return out
 
     # -- host-buffer entry point ------------------------------------------------------------------

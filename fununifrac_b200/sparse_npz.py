@@ -90,6 +90,29 @@ class COO:
             return self.data[mask][0] if mask.any() else self.fill_value
         return COO(self.coords[keep_axes][:, mask], self.data[mask], new_shape, self.fill_value, sorted_=True)
 
+    def take(self, *indices) -> np.ndarray:
+        """Dense ``self.todense()[np.ix_(*indices)]`` without densifying the whole array (one integer index list per
+        axis; negative and repeated indices allowed) — what ``DiffabArrayIndexer`` needs from a loaded diffab file."""
+        if len(indices) != self.ndim:
+            raise IndexError(f"take needs {self.ndim} index lists")
+        uniq, inv, pos = [], [], []
+        for ax, ind in enumerate(indices):
+            ind = np.asarray(ind, dtype=np.int64).reshape(-1)
+            size = self.shape[ax]
+            if ind.size and (ind.min() < -size or ind.max() >= size):
+                raise IndexError(f"index out of bounds for axis {ax} with size {size}")
+            u, iv = np.unique(np.where(ind < 0, ind + size, ind), return_inverse=True)
+            lut = np.full(size, -1, dtype=np.int64)
+            lut[u] = np.arange(len(u))
+            uniq.append(u)
+            inv.append(iv.reshape(-1))
+            pos.append(lut[self.coords[ax]])
+        block = np.full([len(u) for u in uniq], self.fill_value, dtype=self.data.dtype if self.data.size else np.float64)
+        if self.nnz:
+            hit = np.all(np.stack(pos) >= 0, axis=0)
+            block[tuple(p[hit] for p in pos)] = self.data[hit]
+        return block[np.ix_(*inv)]
+
 
 def save_npz(filename, matrix: COO, compressed=True):
     """Same arrays and names as ``sparse.save_npz`` (numpy appends ``.npz`` when missing)."""

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 5
+#define FUF_ABI_VERSION 6
 
 /* error codes */
 #define FUF_OK 0
@@ -222,6 +222,17 @@ int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h,
  * PT: node-major profiles of dtype p_dtype; out: device or pinned host memory of dtype out_dtype. */
 int fuf_diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                      int64_t pair_end, void *out, int out_dtype, void *stream);
+
+/* Sub-block of the antisymmetric diffab tensor T (N x N x n) that pairwise_computation returns as COO minus its
+ * transpose (src/algorithms/emd_unifrac.py:56-72) and that DiffabArrayIndexer.get_diffab / get_diffab_for_node slice
+ * (src/utility/differential_abundance.py:18-55), computed from the pushed matrix instead of being stored:
+ *   out[(a * nb + b) * nk + c] = T[rows_i[a]][rows_j[b]][nodes[c]]
+ *   T[i][j][k] = P_i[k] - P_j[k]  (L1);   sign(j - i) * (P_i[k] - P_j[k])^2  (L2).
+ * rows_i (na), rows_j (nb), nodes (nk) are DEVICE int32 arrays of sample / node indices, each in range (not checked on
+ * the device); nodes == NULL selects all n nodes in order (nk must be n).  out: device or pinned host, dense. */
+int fuf_diffab_gather(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, const int32_t *rows_i,
+                      int64_t na, const int32_t *rows_j, int64_t nb, const int32_t *nodes, int64_t nk, void *out,
+                      int out_dtype, void *stream);
 
 /* Whole path with HOST buffers (the call a reference-side binding makes):
  *   X_h  host, x_dtype, sample-major N x n (ldx >= n), un-pushed normalised profiles;

@@ -633,3 +633,59 @@ def test_many_uncertified_pairs_fall_back_to_float64(full_tree):
         assert ctx.last_flagged > 2000 and rel_err(D, Dref) < 1e-8       # float64 arithmetic on the float64 profiles
         Dh = ctx.all_pairs_host(X, mode)
         assert rel_err(Dh, Dref) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------------
+# diffab consumers on the GPU-resident store
+# ------------------------------------------------------------------------------------------------------
+def test_diffab_store_indexer_vs_reference_golden(toy):
+    """The reference's test_diffab_indexer (tests/algorithms/test_emd_unifrac.py:142-184) against the store that keeps
+    only the pushed matrix in HBM; values are those of the diffab tensor the unmodified reference produced."""
+    from fununifrac_b200.utility import differential_abundance as da
+    from test_diffab_consumers import check_indexer
+    inp, ctx, z = toy
+    files = [str(f) for f in z["files"]]
+    for tag, l2 in (("l1_median", False), ("l2_median", True), ("l2_median_unweighted", True)):
+        Ps = {f: p for f, p in zip(files, z[f"{tag}.P"])}
+        store = da.PushedDiffabStore.from_pushed(Ps, files, inp, l2)
+        golden = z[f"{tag}.diffab"]
+        assert store.shape == golden.shape
+        assert np.array_equal(store.todense(), golden)               # float64 differences of the same pushed vectors
+        check_indexer(da.DiffabArrayIndexer(store, inp.basis, files, inp.idx_to_node), golden, files, atol=0)
+        assert np.array_equal(store[0, 2], golden[0, 2]) and np.array_equal(store[2, 0, :], golden[2, 0, :])
+        assert store[1, 2, 3] == golden[1, 2, 3] and np.array_equal(store[-1], golden[-1])
+        assert np.array_equal(store[0:2, [2, 0], 1:5], golden[0:2][:, [2, 0]][:, :, 1:5])
+        with pytest.raises(IndexError):
+            store[3, 0]
+        df = da.convert_diffab_array_to_df(store, [inp.idx_to_node[i] for i in inp.basis], files)
+        assert df[files[0]][files[2]]["d"] == golden[0, 2, 0]
+
+
+@pytest.mark.parametrize("l2", [False, True])
+def test_diffab_gather_vs_oracle_blocks(l2, full_tree):
+    """Ragged index lists on the 30,002-node tree: every block equals the dense definition built from the oracle's
+    pushed vectors (antisymmetric; L2 squared with the sign of j - i)."""
+    inp, ctx, leaves = full_tree
+    N = 70
+    mode = engine.MODE_L2 if l2 else engine.MODE_L1
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=11)
+    P = oracle_c.push_up(inp.parent, inp.edge_length, X, l2)
+    P64T = ctx.push_up_f64(torch.from_numpy(X).cuda(), mode)
+    assert np.array_equal(P64T[:, :N].cpu().numpy().T, P)
+    rng = np.random.default_rng(4)
+    for na, nb, nk in ((1, 1, None), (3, 70, None), (33, 65, 100), (70, 2, 1), (5, 40, 4097)):
+        ri, rj = rng.integers(0, N, na), rng.integers(-N, N, nb)
+        nodes = None if nk is None else rng.integers(0, ctx.n, nk)
+        got = ctx.diffab_gather(P64T, N, mode, ri, rj, nodes).cpu().numpy()
+        d = P[ri][:, None, :] - P[rj % N][None, :, :]
+        if l2:
+            d = np.sign((rj % N)[None, :] - ri[:, None])[:, :, None] * d * d
+        want = d if nodes is None else d[:, :, nodes]
+        assert got.shape == want.shape and np.array_equal(got, want)
+    out32 = torch.empty((2, 3, ctx.n), dtype=torch.float32, device="cuda")
+    ctx.diffab_gather(P64T, N, mode, [0, 1], [2, 3, 4], None, out=out32)
+    d = P[[0, 1]][:, None, :] - P[[2, 3, 4]][None, :, :]
+    assert np.array_equal(out32.cpu().numpy(), (d * d if l2 else d).astype(np.float32))
+    with pytest.raises(IndexError):
+        ctx.diffab_gather(P64T, N, mode, [N], [0])
+    assert ctx.diffab_gather(P64T, N, mode, [], [0, 1]).shape == (0, 2, ctx.n)
