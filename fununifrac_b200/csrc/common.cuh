@@ -93,6 +93,7 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_d;        // D on device when the host buffer cannot be written in place
     fuf::DeviceBuffer ws_center;   // column mean scratch of fuf_push_up_center
     fuf::DeviceBuffer ws_rows;     // tile-row list of fuf_refine
+    fuf::DeviceBuffer ws_panel;    // transposed tile panels of fuf_store_tile_rows_host
     fuf::DeviceBuffer ws_gram;     // int8 digit planes + tables of fuf_pairwise_gram
     fuf::DeviceBuffer ws_gram_small;  // column maxima
     fuf::DeviceBuffer ws_p64;      // P64T + centre + error statistics (fuf_all_pairs_host)
@@ -130,6 +131,8 @@ int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int m
                  cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
              double *D, int64_t ldd, cudaStream_t stream);
+int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
+                         int64_t ldb, double *D_h, int64_t ldd, cudaStream_t stream);
 // gram.cu
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
                   const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,

@@ -619,6 +619,51 @@ int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int m
     return FUF_OK;
 }
 
+// Prepares compact row blocks for the direct store into a host matrix shared by all ranks of one node
+// (fuf_store_tile_rows_host): the diagonal tile is made symmetric in place, every other upper tile is written
+// transposed into a [N - 128 (t + 1)] x 128 panel so that the mirror half leaves as one pitched DMA copy per tile row.
+struct PanelSlot {
+    int32_t t, pad;
+    int64_t offset;   // of the slot's panel in the panel buffer, doubles
+};
+
+__global__ void __launch_bounds__(256)
+mirror_panels_kernel(double *__restrict__ blocks, const PanelSlot *__restrict__ slots, int64_t N, int64_t ldb,
+                     double *__restrict__ panels)
+{
+    const int c = blockIdx.y;
+    const PanelSlot slot = slots[c];
+    const int t = slot.t;
+    if (t < 0) return;
+    const int tj = t + blockIdx.x;
+    const int64_t gi0 = (int64_t)t * TILE, gj0 = (int64_t)tj * TILE;
+    if (gj0 >= N) return;
+    __shared__ double tile[32][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    double *brow = blocks + (int64_t)c * TILE * ldb;
+    double *panel = panels + slot.offset;
+    for (int sb = 0; sb < 16; sb++) {
+        const int r0 = (sb >> 2) * 32, c0 = (sb & 3) * 32;
+        if (tj == t && r0 > c0) continue;            // diagonal tile: only sub-tiles on or above the diagonal are sources
+        for (int rr = ly; rr < 32; rr += 8) {
+            const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
+            tile[rr][lx] = (gi < N && gj < N) ? brow[(int64_t)(r0 + rr) * ldb + gj] : 0.0;
+        }
+        __syncthreads();
+        for (int cc = ly; cc < 32; cc += 8) {
+            const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;   // destination (row gj, column gi)
+            if (gi < N && gj < N) {
+                if (tj == t) {
+                    if (gj > gi) brow[(int64_t)(c0 + cc) * ldb + gi] = tile[lx][cc];
+                } else {
+                    panel[(gj - gi0 - TILE) * TILE + r0 + lx] = tile[lx][cc];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
              double *D, int64_t ldd, cudaStream_t stream)
 {
@@ -636,6 +681,48 @@ int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int
     assemble_kernel<<<grid, 256, 0, stream>>>(blocks, d_rows, N, ldb, D, ldd);
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    return FUF_OK;
+}
+
+int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
+                         int64_t ldb, double *D_h, int64_t ldd, cudaStream_t stream)
+{
+    if (n_blocks == 0 || N == 0) return FUF_OK;
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    std::vector<PanelSlot> slots((size_t)n_blocks);
+    int64_t total = 0;
+    for (int32_t c = 0; c < n_blocks; c++) {
+        const int32_t t = tile_rows_h[c];
+        FUF_REQUIRE(t >= -1 && t < tiles_per_dim, "fuf_store_tile_rows_host: tile row %d out of range", t);
+        slots[c] = PanelSlot{t, 0, total};
+        if (t >= 0) total += std::max<int64_t>(0, N - (int64_t)(t + 1) * TILE) * TILE;
+    }
+    int rc = ctx->ws_rows.reserve(slots.size() * sizeof(PanelSlot));
+    if (rc) return rc;
+    rc = ctx->ws_panel.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double));
+    if (rc) return rc;
+    PanelSlot *d_slots = (PanelSlot *)ctx->ws_rows.ptr;
+    double *panels = (double *)ctx->ws_panel.ptr;
+    FUF_CUDA(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(PanelSlot), cudaMemcpyHostToDevice, stream));
+    FUF_CUDA(cudaStreamSynchronize(stream));
+    dim3 grid((unsigned)tiles_per_dim, (unsigned)n_blocks);
+    mirror_panels_kernel<<<grid, 256, 0, stream>>>(blocks, d_slots, N, ldb, panels);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    for (int32_t c = 0; c < n_blocks; c++) {
+        const int64_t t = slots[c].t;
+        if (t < 0) continue;
+        const int64_t row0 = t * TILE, rows = std::min<int64_t>(TILE, N - row0), below = N - row0 - rows;
+        // rows [row0, row0 + rows), columns >= row0 (the diagonal tile is symmetric by now)
+        FUF_CUDA(cudaMemcpy2DAsync(D_h + row0 * ldd + row0, (size_t)ldd * sizeof(double),
+                                   blocks + (int64_t)c * TILE * ldb + row0, (size_t)ldb * sizeof(double),
+                                   (size_t)(N - row0) * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, stream));
+        // the mirror: rows below the diagonal tile, columns [row0, row0 + rows)
+        if (below > 0)
+            FUF_CUDA(cudaMemcpy2DAsync(D_h + (row0 + rows) * ldd + row0, (size_t)ldd * sizeof(double),
+                                       panels + slots[c].offset, (size_t)TILE * sizeof(double),
+                                       (size_t)rows * sizeof(double), (size_t)below, cudaMemcpyDeviceToHost, stream));
+    }
     return FUF_OK;
 }
 
@@ -674,4 +761,13 @@ extern "C" int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *t
     FUF_REQUIRE(N >= 0 && ldd >= N && ldb >= N, "fuf_assemble: bad shape");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return assemble(ctx, blocks, tile_rows_h, n_blocks, N, ldb, D, ldd, (cudaStream_t)stream);
+}
+
+extern "C" int fuf_store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks,
+                                        int64_t N, int64_t ldb, double *D_h, int64_t ldd, void *stream)
+{
+    FUF_REQUIRE(ctx && blocks && tile_rows_h && D_h, "fuf_store_tile_rows_host: null argument");
+    FUF_REQUIRE(N >= 0 && ldd >= N && ldb >= N, "fuf_store_tile_rows_host: bad shape");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return store_tile_rows_host(ctx, blocks, tile_rows_h, n_blocks, N, ldb, D_h, ldd, (cudaStream_t)stream);
 }

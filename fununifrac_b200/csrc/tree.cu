@@ -312,6 +312,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     cudaFree(ctx->d_refined);
     ctx->ws_center.release();
     ctx->ws_rows.release();
+    ctx->ws_panel.release();
     ctx->ws_gram.release();
     ctx->ws_gram_small.release();
     ctx->ws_p64.release();

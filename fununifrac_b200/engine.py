@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 6
+ABI_VERSION = 7
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -75,6 +75,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
         L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, vp]
         L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
+        L.fuf_store_tile_rows_host.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
         L.fuf_diffab_block.argtypes = [vp, vp, ci, i64, i64, ci, i64, i64, vp, ci, vp]
         L.fuf_diffab_gather.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, vp, i64, vp, i64, vp, ci, vp]
         L.fuf_all_pairs_host.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, ci]
@@ -91,7 +92,7 @@ def load_library() -> ctypes.CDLL:
                      "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_name_index_create",
                      "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
-                     "fuf_diffab_gather",
+                     "fuf_diffab_gather", "fuf_store_tile_rows_host",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
@@ -395,6 +396,18 @@ class TreeContext:
                                       blocks2.stride(0), D.data_ptr(), D.stride(0), _stream_ptr(torch)),
                "fuf_assemble")
         return D
+
+    def store_tile_rows_host(self, blocks, tile_rows: Sequence[int], N: int, D_host: np.ndarray):
+        """Store this device's row blocks (and their mirror) into the host matrix ``D_host`` [N, N] float64 — usually a
+        :class:`fununifrac_b200.sharded.SharedHostMatrix` every rank of the node writes its part of.  Asynchronous on
+        the current stream when ``D_host`` is pinned or registered."""
+        torch = _torch()
+        rows = np.ascontiguousarray(tile_rows, dtype=np.int32)
+        assert blocks.dtype == torch.float64 and blocks.stride(1) == 1 and blocks.shape[0] >= len(rows) * 128
+        assert D_host.dtype == np.float64 and D_host.shape == (N, N) and D_host.strides[1] == 8
+        _check(self._lib.fuf_store_tile_rows_host(self.handle, blocks.data_ptr(), rows.ctypes.data, len(rows), N,
+                                                  blocks.stride(0), D_host.ctypes.data, D_host.strides[0] // 8,
+                                                  _stream_ptr(torch)), "fuf_store_tile_rows_host")
 
     def diffab_block(self, PT, N: int, mode: int, pair_begin: int, pair_end: int, out):
         """Dense diffab rows of pairs [pair_begin, pair_end) (combinations order) into ``out`` [pairs, n]

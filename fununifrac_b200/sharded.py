@@ -9,7 +9,10 @@ without any collective inside the kernels:
    reads directly through its ``shard`` / ``shard_stride`` arguments)
 3. rank r computes the 128-row tile rows it owns, upper triangle    (``fuf_pairwise`` with ``tile_rows``)
 4. one gather of the compact row blocks to rank 0, which mirrors    (``fuf_assemble``)
-   them into the full symmetric matrix.
+   them into the full symmetric matrix (``step``: matrix resident on GPU 0), or — with host buffers, ``step_host`` —
+   every rank stores its tile rows and their mirror straight into ONE host matrix shared by the ranks of the node
+   (``SharedHostMatrix`` + ``fuf_store_tile_rows_host``): the device-to-host traffic then runs over all PCIe links at
+   once and nothing funnels through rank 0.
 
 The compute calls are injected (``ops``) so that the partition / exchange logic is testable on CPU with the
 ``gloo`` backend; the product always injects ``engine.TreeContext`` (CUDA).  ``world == 1`` needs no process group.
@@ -75,17 +78,17 @@ class ShardedAllPairs:
         self.P64S = ops.empty((world, n, self.shard), "float64") if refine else None
         self.stat = ops.empty((world * self.shard,), "float64")
         self.center = ops.empty((n,), "float64")
-        self.D = ops.empty((N, N), "float64") if rank == 0 else None
+        # full matrix on GPU 0: needed by step(); step_host() with several ranks never touches it (allocated lazily)
+        self.D = ops.empty((N, N), "float64") if world == 1 else None
         self.blocks = self.gathered = None
         self.last_flagged = 0
+        self._x_stage = None
         if world > 1:
             self.flagged = ops.empty((1,), "int64")
             self.blocks = ops.empty((self.max_rows * TILE, N), "float64")
-            if rank == 0:   # one buffer, one slot of max_rows row blocks per rank (unused slots are skipped)
-                self.gathered = ops.empty((world, self.max_rows * TILE, N), "float64")
-                self.slot_rows = []
-                for r in range(world):
-                    self.slot_rows += self.all_rows[r] + [-1] * (self.max_rows - len(self.all_rows[r]))
+            self.slot_rows = []     # rank 0's gather buffer: one slot of max_rows row blocks per rank
+            for r in range(world):
+                self.slot_rows += self.all_rows[r] + [-1] * (self.max_rows - len(self.all_rows[r]))
 
     def _pairwise(self, rows, D):
         """Distances of this rank's tile rows (all rows when ``rows`` is None) into D; returns the refinement
@@ -97,11 +100,10 @@ class ShardedAllPairs:
         ops.pairwise(self.PS, N, self.mode, rows, sh, stride, D)
         return self.stat, None
 
-    def step(self, X_local, mark=None):
-        """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
-        ``mark(name)`` is called at the phase boundaries (bench.py records CUDA events there)."""
+    def _compute(self, X_local, mark):
+        """Phases 1-3 (+ refinement).  Afterwards ``self.D`` (world == 1) or ``self.blocks`` (this rank's tile rows, upper
+        part) hold the final distances."""
         ops, N, mode, r, sh, n = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n
-        mark = mark or (lambda name: None)
         stride = n * sh
         mark("start")
         if r == 0:
@@ -119,8 +121,7 @@ class ShardedAllPairs:
             mark("pair_end")
             if self.do_refine:
                 ops.refine(self.P64S, N, mode, stat, self.D, None, sh, stride, lin)
-            mark("end")
-            return self.D
+            return
         self.dist.all_gather_into_tensor(self.PS.view(-1), self.PS[r].reshape(-1))
         self.dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
         mark("pair_begin")
@@ -136,12 +137,100 @@ class ShardedAllPairs:
                 self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
                 if self.rows:
                     ops.refine(self.P64S, N, mode, stat, self.blocks, self.rows, sh, stride, lin)
-        self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
-        if r == 0:
-            ops.assemble(self.gathered, self.slot_rows, N, self.D)
+
+    def step(self, X_local, mark=None):
+        """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
+        ``mark(name)`` is called at the phase boundaries (bench.py records CUDA events there)."""
+        mark = mark or (lambda name: None)
+        self._compute(X_local, mark)
+        if self.world > 1:
+            r = self.rank
+            if r == 0 and self.gathered is None:
+                self.D = self.ops.empty((self.N, self.N), "float64")
+                self.gathered = self.ops.empty((self.world, self.max_rows * TILE, self.N), "float64")
+            self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
+            if r == 0:
+                self.ops.assemble(self.gathered, self.slot_rows, self.N, self.D)
         mark("end")
         return self.D
 
+    def step_host(self, X_local_host, D_host: "SharedHostMatrix", mark=None):
+        """Host buffers on both sides: ``X_local_host`` is this rank's un-pushed samples in (pinned) host memory,
+        ``D_host`` the node-wide shared matrix.  Every rank copies its samples in, computes its tile rows and stores
+        them and their mirror image into ``D_host``; when the call returns (after a barrier) the full symmetric
+        matrix is in ``D_host.array`` on EVERY rank."""
+        mark = mark or (lambda name: None)
+        if D_host.array.shape != (self.N, self.N):
+            raise ValueError(f"shared matrix is {D_host.array.shape}, job needs {(self.N, self.N)}")
+        if self._x_stage is None:
+            self._x_stage = self.ops.empty((max(self.hi - self.lo, 1), self.ops.n), "float64")
+        X = self.ops.to_device(X_local_host, self._x_stage)
+        self._compute(X, mark)
+        if self.world == 1:
+            self.ops.copy_to_host(self.D, D_host.array)
+        elif self.rows:
+            self.ops.store_tile_rows_host(self.blocks, self.rows, self.N, D_host.array)
+        self.ops.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        mark("end")
+        return D_host.array
+
+
+class SharedHostMatrix:
+    """N x N float64 host matrix shared by the ranks of ONE node, page-locked for every rank's GPU.
+
+    Rank 0 creates an anonymous memory file (``memfd_create``: no name, no ``/dev/shm`` size limit, freed when the last
+    process closes it); the other ranks open it through ``/proc/<pid>/fd/<fd>`` and map the same pages.  Each rank
+    registers its mapping with CUDA (``cudaHostRegister``), so ``fuf_store_tile_rows_host`` DMA-writes into it over
+    that rank's own PCIe link.  This is the array the driver then hands to ``np.save``
+    (``src/compute_all_pairwise_fununifrac.py:88-89``)."""
+
+    def __init__(self, N: int, world: int = 1, rank: int = 0, dist=None, register: Optional[bool] = None):
+        import mmap
+        import os
+
+        import numpy as np
+
+        self.N, self.nbytes = N, max(8, N * N * 8)
+        self._registered = False
+        if rank == 0:
+            self._fd = os.memfd_create("fununifrac_D")
+            os.ftruncate(self._fd, self.nbytes)
+        if world > 1:
+            where = [(os.getpid(), self._fd) if rank == 0 else None]
+            dist.broadcast_object_list(where, src=0)
+            if rank != 0:
+                self._fd = os.open(f"/proc/{where[0][0]}/fd/{where[0][1]}", os.O_RDWR)
+            dist.barrier()           # rank 0 keeps its descriptor open until everybody has opened the file
+        self._map = mmap.mmap(self._fd, self.nbytes)
+        self.array = np.frombuffer(self._map, dtype=np.float64, count=N * N).reshape(N, N)
+        if register is None:
+            import torch
+            register = torch.cuda.is_available()
+        if register and N:
+            import torch
+            rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared {N} x {N} matrix failed: {rc}")
+            self._registered = True
+
+    def close(self):
+        import os
+        if self._registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self._registered = False
+        self.array = None
+        if self._map is not None:
+            try:
+                self._map.close()
+            except BufferError:      # a view of the array is still alive somewhere: the pages go when it does
+                pass
+            self._map = None
+        if self._fd is not None:
+            os.close(self._fd)
+            self._fd = None
 
 
 class CudaOps:
@@ -180,3 +269,18 @@ class CudaOps:
 
     def assemble(self, blocks, rows, N, D):
         return self.ctx.assemble(blocks, rows, N, D=D)
+
+    def to_device(self, X_host, stage):
+        src = X_host if self.torch.is_tensor(X_host) else self.torch.from_numpy(X_host)
+        out = stage[:src.shape[0]]
+        out.copy_(src, non_blocking=True)
+        return out
+
+    def store_tile_rows_host(self, blocks, rows, N, D_host):
+        self.ctx.store_tile_rows_host(blocks, rows, N, D_host)
+
+    def copy_to_host(self, D, D_host):
+        self.torch.from_numpy(D_host).copy_(D, non_blocking=True)
+
+    def synchronize(self):
+        self.torch.cuda.synchronize()

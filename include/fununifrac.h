@@ -21,6 +21,7 @@
  *   fuf_refine           <- get_L1 / get_L2 in float64 for the pairs    src/objects/profile_vector.py:9-19
  *                           the fp32 operands cannot certify to 1e-6
  *   fuf_assemble         <- dists[i,j] = dists[j,i] = Z                 src/algorithms/emd_unifrac.py:51-54
+ *   fuf_store_tile_rows_host <- same, into the host matrix np.save writes src/compute_all_pairwise_fununifrac.py:88-89
  *                           (joins row-block shards computed on several GPUs)
  *   fuf_diffab_block     <- get_L1_diffab / get_L2_diffab per pair in   src/objects/profile_vector.py:13-23
  *                           itertools.combinations order                src/algorithms/emd_unifrac.py:49,56-67
@@ -52,7 +53,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 6
+#define FUF_ABI_VERSION 7
 
 /* error codes */
 #define FUF_OK 0
@@ -215,6 +216,17 @@ int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
  * tile_rows_h[c] == -1 marks a padding block that is skipped. */
 int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
                  int64_t ldb, double *D, int64_t ldd, void *stream);
+
+/* Same join, but straight into a HOST matrix: each GPU of a node stores the tile rows it owns (and their mirror image)
+ * into one N x N host matrix shared by all ranks (shared memory registered with cudaHostRegister in every process), so
+ * the device-to-host traffic runs over every GPU's own PCIe link at once instead of through rank 0.
+ *   blocks  device double [n_blocks * 128, ldb], as written by fuf_pairwise / fuf_pairwise_gram / fuf_refine with
+ *           tile_rows_h; its diagonal tiles are made symmetric in place;
+ *   D_h     host double N x N (ldd >= N); slot c writes D_h[128 t : 128 t + 128, 128 t :] and
+ *           D_h[128 (t + 1) :, 128 t : 128 t + 128] for t = tile_rows_h[c]  (-1 = padding slot, skipped).
+ * Asynchronous on `stream` when D_h is pinned / registered; the union over all tile rows covers D_h exactly once. */
+int fuf_store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
+                             int64_t ldb, double *D_h, int64_t ldd, void *stream);
 
 /* Differential-abundance rows for pairs [pair_begin, pair_end) in itertools.combinations(range(N), 2) order:
  *   out[(p - pair_begin) * n + k] = P_i[k] - P_j[k]          (L1)

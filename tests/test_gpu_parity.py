@@ -202,6 +202,19 @@ def test_tile_rows_assemble_and_shards(full_tree):
     D2b = ctx.assemble(torch.cat(blocks + [torch.full((128, N), 7.0, dtype=torch.float64, device="cuda")], 0),
                        rows + [-1], N)
     assert torch.equal(D2, D2b)
+    # the same join straight into one host matrix (what every rank of a node does in ShardedAllPairs.step_host):
+    # pinned, page-locked-by-registration (SharedHostMatrix) and plain pageable destinations, N not a multiple of 128
+    from fununifrac_b200 import sharded
+    shared = sharded.SharedHostMatrix(N)
+    pinned = torch.full((N, N), float("nan"), dtype=torch.float64, pin_memory=True).numpy()
+    pageable = np.full((N, N + 3), np.nan)[:, :N]
+    for dst in (shared.array, pinned, pageable):
+        dst[...] = np.nan
+        for own, blk in zip(owners, blocks):
+            ctx.store_tile_rows_host(blk.clone(), own, N, dst)
+        torch.cuda.synchronize()
+        assert np.array_equal(dst, D2.cpu().numpy())
+    shared.close()
     # sharded layout [G, n, shard]: what an all-gather of per-rank push-up outputs looks like
     shard = 256
     G = (N + shard - 1) // shard
@@ -217,9 +230,11 @@ def test_tile_rows_assemble_and_shards(full_tree):
     ctx.refine(P64S, N, engine.MODE_L1, stat, D3, shard=shard, shard_stride=ctx.n * shard)
     assert torch.equal(D, D3)
     # the same through the sharded driver at world size 1
-    from fununifrac_b200 import sharded
     one = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, engine.MODE_L1)
     assert torch.equal(one.step(X), D)
+    shared = sharded.SharedHostMatrix(N)
+    assert np.array_equal(one.step_host(X.double().cpu().numpy(), shared), D.cpu().numpy())
+    shared.close()
 
 
 def test_host_path_bands(full_tree, monkeypatch):

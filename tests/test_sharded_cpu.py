@@ -79,6 +79,8 @@ class OracleOps:
             r0, r1 = t * TILE, min(N, (t + 1) * TILE)
             blk = self.o.pairwise_rows(P, r0, r1, self.l2)
             D[c * TILE:c * TILE + (r1 - r0), r0:] = torch.from_numpy(blk[:, r0:])
+            lower = np.tril_indices(r1 - r0, -1)      # the kernels only promise i <= j inside the diagonal tile
+            D[c * TILE + lower[0], r0 + lower[1]] = float("nan")
         return D
 
     def count_uncertified(self, N, mode, err_stat, D, tile_rows, lin_stat=None):
@@ -97,9 +99,25 @@ class OracleOps:
                 continue
             r0, r1 = t * TILE, min(N, (t + 1) * TILE)
             blk = blocks[c * TILE:c * TILE + (r1 - r0)]
-            D[r0:r1, r0:] = blk[:, r0:]
             D[r0:, r0:r1] = blk[:, r0:].T
+            D[r0:r1, r1:] = blk[:, r1:]
+            D[r0:r1, r0:r1] = torch.triu(blk[:, r0:r1]) + torch.triu(blk[:, r0:r1], 1).T
         return D
+
+    # host-buffer variant (step_host)
+    def to_device(self, X_host, stage):
+        src = X_host if torch.is_tensor(X_host) else torch.from_numpy(X_host)
+        stage[:src.shape[0]].copy_(src)
+        return stage[:src.shape[0]]
+
+    def store_tile_rows_host(self, blocks, rows, N, D_host):
+        self.assemble(blocks, rows, N, torch.from_numpy(D_host))
+
+    def copy_to_host(self, D, D_host):
+        D_host[...] = D.numpy()
+
+    def synchronize(self):
+        pass
 
 
 def _free_port():
@@ -139,6 +157,20 @@ def _worker(rank, world, port, N, l2, out_path):
             np.save(out_path, got)
         else:
             assert D is None
+        # host-buffer variant: every rank stores its rows into one shared host matrix; all ranks see the full result
+        shared = sharded.SharedHostMatrix(N, world, rank, dist, register=False)
+        shared.array.fill(np.nan)
+        dist.barrier()
+        Dh = job.step_host(X[job.lo:job.hi], shared)
+        want = torch.zeros(1, dtype=torch.float64)
+        if rank == 0:
+            want[0] = float(np.abs(got).sum())
+            assert np.array_equal(Dh, got)
+        dist.broadcast(want, src=0)
+        assert not np.isnan(Dh).any() and float(np.abs(Dh).sum()) == float(want[0])      # same pages on every rank
+        dist.barrier()
+        del Dh
+        shared.close()
     finally:
         dist.destroy_process_group()
 
