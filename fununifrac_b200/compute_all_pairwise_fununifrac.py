@@ -24,6 +24,54 @@ from fununifrac_b200.algorithms.emd_unifrac import EarthMoverDistanceUniFracSolv
 from fununifrac_b200.objects.func_tree import FuncTreeEmduInput
 
 
+def _ingest(files, input, abundance_key, unweighted, num_threads, python_ingest):
+    """Un-pushed profile matrix [len(files), n] of gather CSVs, in file order."""
+    if not files:
+        return np.zeros((0, len(input.basis)))
+    if python_ingest:
+        # the reference's own route: pandas.read_csv + a process pool (src/factory/make_emd_input.py:58-122)
+        results = make_emd_input.parallel_functional_profile_to_vector(num_threads, files, input, abundance_key,
+                                                                       unweighted)
+        got, X = make_emd_input.profiles_to_matrix(results, len(input.basis))
+    else:
+        # native ingest (csrc/ingest.cu): C++ thread pool, only the two columns the path uses are tokenised;
+        # rows are bit-identical to the route above
+        got, X = make_emd_input.native_profiles_to_matrix(files, input, abundance_key, unweighted, num_threads)
+    assert got == list(files)
+    return X
+
+
+def _all_pairs_multi_gpu(fun_files, input, abundance_key, unweighted, num_threads, is_L2, python_ingest):
+    """The compute section under ``torchrun`` (one process per GPU of one node): every rank ingests and pushes up its
+    own block of files, the pushed profiles are all-gathered over NVLink, every rank computes its tile rows and stores
+    them into one shared host matrix (``sharded.ShardedAllPairs.step_host``).  Returns the matrix on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    from fununifrac_b200 import sharded
+
+    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        N = len(fun_files)
+        ctx = engine.context_for(input, local_rank)
+        job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, engine.MODE_L2 if is_L2 else engine.MODE_L1, world, rank,
+                                      dist)
+        X = _ingest(fun_files[job.lo:job.hi], input, abundance_key, unweighted, num_threads, python_ingest)
+        shared = sharded.SharedHostMatrix(N, world, rank, dist)
+        dists = job.step_host(X, shared).copy()
+        dist.barrier()
+        shared.close()
+        return dists
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+
+
 def main(args):
     logging.basicConfig(level=args.loglevel, format='%(asctime)s %(levelname)s: %(message)s')
     edge_list_file = args.edge_list
@@ -61,16 +109,20 @@ def main(args):
     ##############################################################################
     # Computations
     ##############################################################################
-    if getattr(args, "python_ingest", False):
-        # the reference's own route: pandas.read_csv + a process pool (src/factory/make_emd_input.py:58-122)
-        results = make_emd_input.parallel_functional_profile_to_vector(num_threads, fun_files, input, abundance_key,
-                                                                       unweighted)
-        files, X = make_emd_input.profiles_to_matrix(results, len(input.basis))
+    python_ingest = bool(getattr(args, "python_ingest", False))
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1 and not (make_diffab or save_Ppushed or validate):
+        # launched with torchrun: shard over the GPUs of the node; rank 0 writes the output files
+        dists = _all_pairs_multi_gpu(fun_files, input, abundance_key, unweighted, num_threads, is_L2, python_ingest)
+        if rank != 0:
+            return
+        X = None
+    elif rank != 0:
+        logging.info("--diffab / --Ppushed / --validate run on one GPU: this rank has nothing to do")
+        return
     else:
-        # native ingest (csrc/ingest.cu): C++ thread pool, only the two columns the path uses are tokenised;
-        # rows are bit-identical to the route above
-        files, X = make_emd_input.native_profiles_to_matrix(fun_files, input, abundance_key, unweighted, num_threads)
-    assert files == fun_files
+        X = _ingest(fun_files, input, abundance_key, unweighted, num_threads, python_ingest)
+        dists = None
     mode = engine.MODE_L2 if is_L2 else engine.MODE_L1
     logging.info(f"Computing pairwise distances")
     diffabs_sparse = None
@@ -78,7 +130,9 @@ def main(args):
     if save_Ppushed:
         pushed = solver.push_up_batch(X, input, is_L2)  # float64, the reference's operation order
         Ps_pushed = {file: pushed[i] for i, file in enumerate(fun_files)}
-    if not make_diffab:
+    if dists is not None:
+        pass
+    elif not make_diffab:
         dists = solver.all_pairs(X, input, is_L2)
     else:
         torch = engine._torch()

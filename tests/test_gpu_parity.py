@@ -704,3 +704,46 @@ def test_diffab_gather_vs_oracle_blocks(l2, full_tree):
     with pytest.raises(IndexError):
         ctx.diffab_gather(P64T, N, mode, [N], [0])
     assert ctx.diffab_gather(P64T, N, mode, [], [0, 1]).shape == (0, 2, ctx.n)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("l2", [False, True])
+def test_cli_under_torchrun_two_gpus(l2, tmp_path):
+    """The drop-in CLI launched with torchrun: every rank ingests its block of files, tile rows are sharded, the ranks
+    store into one shared host matrix, rank 0 writes the reference's output files — same matrix as the 1-GPU run."""
+    import subprocess
+    import sys
+    from fununifrac_b200 import compute_fununifrac
+    from fununifrac_b200.utility import constant
+    tree = synth.synth_ko_tree(str(tmp_path / "tree.txt"), seed=3, widths=(1, 1, 4, 12, 40, 160, 900))
+    inp = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(tree), "ko00001")
+    n = len(inp.basis)
+    leaves = synth.leaves_of(inp.parent)
+    names = [inp.idx_to_node[k] for k in range(n)]
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    N = 600 if l2 else 300                 # --L2 from 512 samples on: the tensor-core Gram route
+    rng = np.random.default_rng(8)
+    for i in range(N):
+        indptr, indices, values = synth.synth_profile_rows(leaves, n, [i], seed=21)
+        synth.write_gather_csv(str(prof / f"s{i:04d}_gather.csv"), [names[j] for j in indices],
+                               rng.geometric(0.2, len(indices)))
+    base = ["-e", tree, "-fd", str(prof), "-b", "ko00001", "-a", "median_abund", "-t", "4"] + (["--L2"] if l2 else [])
+    compute_fununifrac.main(base + ["-o", str(tmp_path / "one"), "-i", "x"])
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=repo + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", "-m", "fununifrac_b200.compute_fununifrac"] + base + \
+          ["-o", str(tmp_path / "two"), "-i", "x"]
+    res = subprocess.run(cmd, env=env, cwd=repo, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    name = constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format("x")
+    D1, D2 = np.load(tmp_path / "one" / name), np.load(tmp_path / "two" / name)
+    assert D2.shape == (N, N) and np.array_equal(D2, D2.T) and not np.diag(D2).any()
+    assert rel_err(D2, D1) < 1e-9          # same kernels; only the order of a few float64 additions differs
+    P = oracle_c.push_up(inp.parent, inp.edge_length,
+                         make_emd_input.native_profiles_to_matrix(sorted(glob.glob(str(prof / "*_gather.csv"))), inp,
+                                                                  "median_abund", False, 4)[1], l2)
+    assert rel_err(D2, oracle_c.pairwise(P, l2)) < REL
+    bn = constant.FUNUNIFRAC_OUT__MAIN_BASIS__FILE_NAME.format("x")
+    assert open(tmp_path / "one" / bn).read() == open(tmp_path / "two" / bn).read()
