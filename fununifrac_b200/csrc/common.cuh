@@ -131,6 +131,10 @@ int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int m
                  cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
              double *D, int64_t ldd, cudaStream_t stream);
+int pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_t *tile_rows_h, const int64_t *offsets_h,
+                   int32_t n_blocks, int64_t N, double *packed, cudaStream_t stream);
+int assemble_packed(fuf_ctx *ctx, const double *packed, const int32_t *tile_rows_h, const int64_t *offsets_h,
+                    int32_t n_blocks, int64_t N, double *D, int64_t ldd, cudaStream_t stream);
 int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
                          int64_t ldb, double *D_h, int64_t ldd, cudaStream_t stream);
 // gram.cu

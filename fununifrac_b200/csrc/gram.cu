@@ -40,7 +40,7 @@
 //       warps 4-11 (two warpgroups, setmaxnreg 232) epilogue: tcgen05.ld of the four int32 accumulators, weighted
 //                into 64 float64 registers per thread; each accumulator is released as soon as it has been read, so
 //                the next bucket's MMAs stall only until the first one is drained.
-// K3m mirror_kernel       lower triangle := transpose of the upper one.
+//       With the full matrix as output the epilogue also stores the transposed tile (no separate mirror pass).
 //
 // Tensor-pipe accounting: executed int8 MACs = 10 x 128 x 128 x (padded n) per tile; algorithmic flops = 2 n per pair.
 #include <algorithm>
@@ -95,6 +95,10 @@ struct Params {
     const double *q;
     double *D;
     int64_t ldd;
+    int32_t mirror;      // 1: D is the full matrix (out_row0 = 128 ti): also store the transposed tile
+    int32_t n_direct;    // node columns kept out of the integer Gram (largest scales): added here in float64
+    const double *SUB;   // their values, [n_direct][samples] in layout `sub`
+    Lay sub;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -315,13 +319,31 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 }
             }
             const int64_t gi = (int64_t)tl.ti * TILE + row, gj0 = (int64_t)tl.tj * TILE + half * 64;
+            const bool mirror = p.mirror != 0 && tl.ti != tl.tj;
+            // bypass columns in float64: D += sum_k (a_i - a_j)^2, folded into acc as -(a_i - a_j)^2 / 2 (exact scaling);
+            // all lanes of a warp read the same a_j (one broadcast transaction), a_i is coalesced along the lanes
+            if (p.n_direct > 0 && gi < p.N) {
+                for (int32_t k = 0; k < p.n_direct; k++) {
+                    const double ai = p.SUB[p.sub.at(k, gi)];
+                    const double *bj = p.SUB + p.sub.at(k, gj0);
+#pragma unroll
+                    for (int e = 0; e < 64; e++) {
+                        const double d = ai - bj[e];            // columns >= N hold zeros and are never stored
+                        acc[e] = fma(-0.5 * d, d, acc[e]);
+                    }
+                }
+            }
             if (gi < p.N) {
                 const double qi = p.q[gi];
                 double *drow = p.D + ((int64_t)tl.out_row0 + row) * p.ldd + gj0;
 #pragma unroll
                 for (int e = 0; e < 64; e++) {
                     const int64_t gj = gj0 + e;
-                    if (gj < p.N) drow[e] = (gi == gj) ? 0.0 : drow[e] + ((qi + p.q[gj]) - 2.0 * acc[e]);
+                    if (gj < p.N) {
+                        const double v = (gi == gj) ? 0.0 : (qi + p.q[gj]) - 2.0 * acc[e];
+                        drow[e] = v;
+                        if (mirror) p.D[gj * p.ldd + gi] = v;    // lanes = consecutive gi: one 256-byte store per warp
+                    }
                 }
             }
         }
@@ -335,7 +357,8 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 }
 
 // Per node column (one warp per row): cmax[k] = max_s |PT[k][s]|, nnz[k] = number of non-zero entries,
-// energy[k] = sum_s PT[k][s]^2.
+// energy[k] = sum_s PT[k][s]^2 (fp32: it only steers the bypass heuristic).  Shard by shard, 16-byte loads, four of
+// them in flight per lane.
 __global__ void __launch_bounds__(256)
 gram_colmax_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32_t n, float *__restrict__ cmax,
                    float *__restrict__ nnz, float *__restrict__ energy)
@@ -343,13 +366,29 @@ gram_colmax_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32
     const int32_t k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= n) return;
     const int lane = threadIdx.x & 31;
-    float m = 0.f, c = 0.f;
-    double e = 0.0;
-    for (int64_t s = lane; s < N; s += 32) {
-        const float a = PT[lay.at(k, s)];
+    float m = 0.f, c = 0.f, e = 0.f;
+    auto take = [&](float a) {
         m = fmaxf(m, fabsf(a));
         c += (a != 0.f) ? 1.f : 0.f;
-        e = fma((double)a, (double)a, e);
+        e = fmaf(a, a, e);
+    };
+    for (int64_t s0 = 0; s0 < N; s0 += lay.S) {
+        const float *row = PT + lay.at(k, s0);               // 16-byte aligned: S, LD and SS are multiples of 4
+        const int64_t len = min(lay.S, N - s0), len4 = len >> 2;
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        int64_t i = lane;
+        for (; i + 96 < len4; i += 128) {
+            const float4 v0 = row4[i], v1 = row4[i + 32], v2 = row4[i + 64], v3 = row4[i + 96];
+            take(v0.x), take(v0.y), take(v0.z), take(v0.w);
+            take(v1.x), take(v1.y), take(v1.z), take(v1.w);
+            take(v2.x), take(v2.y), take(v2.z), take(v2.w);
+            take(v3.x), take(v3.y), take(v3.z), take(v3.w);
+        }
+        for (; i < len4; i += 32) {
+            const float4 v = row4[i];
+            take(v.x), take(v.y), take(v.z), take(v.w);
+        }
+        for (int64_t j = (len4 << 2) + lane; j < len; j += 32) take(row[j]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -360,53 +399,82 @@ gram_colmax_kernel(const float *__restrict__ PT, const Lay lay, int64_t N, int32
     if (lane == 0) {
         cmax[k] = m;
         nnz[k] = c;
-        energy[k] = (float)e;
+        energy[k] = e;
     }
 }
 
-// Permuted row r (node row_map[r], bucket scale 1 / inv_scale[r]) of every sample -> three int8 digits;
-// r2[part][s] = sum over the part's rows of (quantisation error)^2, h2[part][s] = sum of S^2 over its non-zero entries.
+// One part = up to 512 permuted rows of ONE bucket.
+struct Part {
+    int32_t row0, row1;   // permuted rows [row0, row1)
+    int32_t group, pad;
+};
+
+// Permuted row r (node row_map[r], bucket scale 1 / inv_scale[r]) of every sample -> four int8 digits, four samples per
+// thread (one 16-byte load, one 4-byte store per digit plane).  Per (part, sample) it also emits
+//   r2 = sum of (quantisation error)^2,  h2 = sum of S^2 over the non-zero entries,
+//   c_p = sum over the rows of sum_{x+y=p} d_x d_y  (p = 0..3, exact integers: the sample's digit form with itself).
 // Padding rows (row_map < 0) and padding samples (s >= N) get zero digits.
-__global__ void __launch_bounds__(256)
-gram_digits_kernel(const float *__restrict__ PT, const Lay lay, const Lay ws, int64_t n_cols, int64_t N, int32_t n_rows,
-                   int32_t rows_per_part, const int32_t *__restrict__ row_map, const float *__restrict__ inv_scale,
-                   int8_t *__restrict__ D0, int8_t *__restrict__ D1, int8_t *__restrict__ D2, int8_t *__restrict__ D3,
-                   double *__restrict__ r2, double *__restrict__ h2)
+__global__ void __launch_bounds__(128)
+gram_digits_kernel(const float *__restrict__ PT, const Lay lay, const Lay ws, int64_t n_cols, int64_t N,
+                   const Part *__restrict__ parts, const int32_t *__restrict__ row_map,
+                   const float *__restrict__ inv_scale, int8_t *__restrict__ D0, int8_t *__restrict__ D1,
+                   int8_t *__restrict__ D2, int8_t *__restrict__ D3, double *__restrict__ r2, double *__restrict__ h2,
+                   int32_t *__restrict__ cself)
 {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (s >= n_cols) return;
-    const int32_t r0 = blockIdx.y * rows_per_part, r1 = min(n_rows, r0 + rows_per_part);
-    double err = 0.0, hh = 0.0;
-    for (int32_t r = r0; r < r1; r++) {
+    const Part part = parts[blockIdx.y];
+    double err[4] = {0.0, 0.0, 0.0, 0.0}, hh[4] = {0.0, 0.0, 0.0, 0.0};
+    int32_t c[4][4] = {};
+    const bool any = s < N;
+    for (int32_t r = part.row0; r < part.row1; r++) {
         const int32_t k = row_map[r];
-        int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        if (k >= 0 && s < N) {
-            const float a = PT[lay.at(k, s)];
-            if (a != 0.f) {
-                const double is = (double)inv_scale[r];         // a power of two: a * is is exact and in [-1, 1]
-                double t = (double)a * is * DIGIT0;
-                const double f0 = rint(t);
-                t = (t - f0) * DIGIT;
-                const double f1 = rint(t);
-                t = (t - f1) * DIGIT;
-                const double f2 = rint(t);
-                t = (t - f2) * DIGIT;
-                const double f3 = rint(t);
-                d0 = (int)f0, d1 = (int)f1, d2 = (int)f2, d3 = (int)f3;
-                const double unit = 1.0 / (is * DIGIT0);        // value of one step of d0
-                const double e = (t - f3) * unit * (1.0 / (DIGIT * DIGIT * DIGIT));
-                err = fma(e, e, err);
-                hh += 1.0 / (is * is);                          // S^2 of every non-zero entry
+        int d[4][4] = {};                 // [sample][digit]
+        if (k >= 0 && any) {
+            const float4 v = *reinterpret_cast<const float4 *>(PT + lay.at(k, s));
+            const double is = (double)inv_scale[r];             // a power of two: a * is is exact and in [-1, 1]
+            const double unit = 1.0 / (is * DIGIT0) * (1.0 / (DIGIT * DIGIT * DIGIT));   // value of one step of d3
+            const double S2 = 1.0 / (is * is);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float a = u == 0 ? v.x : u == 1 ? v.y : u == 2 ? v.z : v.w;
+                if (a != 0.f && s + u < N) {
+                    double t = (double)a * is * DIGIT0;
+                    const double f0 = rint(t);
+                    t = (t - f0) * DIGIT;
+                    const double f1 = rint(t);
+                    t = (t - f1) * DIGIT;
+                    const double f2 = rint(t);
+                    t = (t - f2) * DIGIT;
+                    const double f3 = rint(t);
+                    d[u][0] = (int)f0, d[u][1] = (int)f1, d[u][2] = (int)f2, d[u][3] = (int)f3;
+                    const double e = (t - f3) * unit;
+                    err[u] = fma(e, e, err[u]);
+                    hh[u] += S2;                                // S^2 of every non-zero entry
+                    c[u][0] += d[u][0] * d[u][0];
+                    c[u][1] += 2 * d[u][0] * d[u][1];
+                    c[u][2] += d[u][1] * d[u][1] + 2 * d[u][0] * d[u][2];
+                    c[u][3] += 2 * d[u][0] * d[u][3] + 2 * d[u][1] * d[u][2];
+                }
             }
         }
         const int64_t o = ws.at(r, s);
-        D0[o] = (int8_t)d0;
-        D1[o] = (int8_t)d1;
-        D2[o] = (int8_t)d2;
-        D3[o] = (int8_t)d3;
+        auto pack = [&](int p) {
+            return (uint32_t)(uint8_t)d[0][p] | ((uint32_t)(uint8_t)d[1][p] << 8) | ((uint32_t)(uint8_t)d[2][p] << 16) |
+                   ((uint32_t)(uint8_t)d[3][p] << 24);
+        };
+        *reinterpret_cast<uint32_t *>(D0 + o) = pack(0);
+        *reinterpret_cast<uint32_t *>(D1 + o) = pack(1);
+        *reinterpret_cast<uint32_t *>(D2 + o) = pack(2);
+        *reinterpret_cast<uint32_t *>(D3 + o) = pack(3);
     }
-    r2[(int64_t)blockIdx.y * n_cols + s] = err;
-    h2[(int64_t)blockIdx.y * n_cols + s] = hh;
+    const int64_t base = (int64_t)blockIdx.y * n_cols + s;
+    *reinterpret_cast<double4 *>(r2 + base) = make_double4(err[0], err[1], err[2], err[3]);
+    *reinterpret_cast<double4 *>(h2 + base) = make_double4(hh[0], hh[1], hh[2], hh[3]);
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+        *reinterpret_cast<int4 *>(cself + ((int64_t)blockIdx.y * 4 + p) * n_cols + s) =
+            make_int4(c[0][p], c[1][p], c[2][p], c[3][p]);
 }
 
 // Gather of the node rows that bypass the integer Gram (largest scales): SUB[slot][s] = (double) PT[node][s].
@@ -420,148 +488,43 @@ gram_gather_kernel(const float *__restrict__ PT, const Lay lay, const Lay sub, i
     SUB[sub.at(blockIdx.y, s)] = (k >= 0 && s < N) ? (double)PT[lay.at(k, s)] : 0.0;
 }
 
-// Bypass part in float64: D[tile] = sum over the bypassed rows of (a_i - a_j)^2 (plain stores; the Gram epilogue adds
-// its part afterwards).  One block = one 64x64 quarter of a 128x128 tile, 4x4 entries per thread.
-__global__ void __launch_bounds__(256)
-gram_bypass_kernel(const Tile *__restrict__ tiles, const double *__restrict__ SUB, const Lay sub, int32_t n_direct,
-                   int64_t N, double *__restrict__ D, int64_t ldd)
-{
-    constexpr int T = 64, KBK = 16;
-    __shared__ double As[KBK][T], Bs[KBK][T];
-    const Tile tl = tiles[blockIdx.x];
-    const int si = blockIdx.y >> 1, sj = blockIdx.y & 1;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t i0 = (int64_t)tl.ti * TILE + si * T, j0 = (int64_t)tl.tj * TILE + sj * T;
-    if (i0 >= N || j0 >= N) return;
-    double acc[4][4] = {};
-    for (int32_t k0 = 0; k0 < n_direct; k0 += KBK) {
-        for (int e = tid; e < KBK * T; e += 256) {
-            const int kk = e / T, c = e % T;
-            const int32_t k = k0 + kk;
-            As[kk][c] = (k < n_direct && i0 + c < N) ? SUB[sub.at(k, i0 + c)] : 0.0;
-            Bs[kk][c] = (k < n_direct && j0 + c < N) ? SUB[sub.at(k, j0 + c)] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int kk = 0; kk < KBK; kk++) {
-            double a[4], b[4];
-#pragma unroll
-            for (int m = 0; m < 4; m++) a[m] = As[kk][ty * 4 + m];
-#pragma unroll
-            for (int u = 0; u < 4; u++) b[u] = Bs[kk][tx * 4 + u];
-#pragma unroll
-            for (int m = 0; m < 4; m++)
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const double d = a[m] - b[u];
-                    acc[m][u] = fma(d, d, acc[m][u]);
-                }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const int64_t gi = i0 + ty * 4 + m;
-        if (gi >= N) continue;
-        double *drow = D + ((int64_t)tl.out_row0 + si * T + ty * 4 + m) * ldd;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int64_t gj = j0 + tx * 4 + u;
-            if (gj < N) drow[gj] = acc[m][u];
-        }
-    }
-}
-
-// err_out[s] = (sqrt(err_in[s]) + sqrt(sum r2))^2: the statistics of
-// two successive roundings (fp32 rounding in the push-up, digit quantisation here) add in norm; h2[s] = sum of S^2 over
-// the sample's non-zero entries (bounds what the dropped product orders can contribute, see fuf_pairwise_gram).
-__global__ void gram_stat_kernel(const double *__restrict__ r2part, const double *__restrict__ h2part, int32_t n_parts,
-                                 int64_t ldp, const double *__restrict__ err_in, int64_t N, double *__restrict__ h2,
-                                 double *__restrict__ err_out)
+// Per sample, from the per-part outputs of gram_digits_kernel:
+//   err_out[s] = (sqrt(err_in[s]) + sqrt(sum r2))^2: the statistics of two successive roundings (fp32 rounding in the
+//     push-up, digit quantisation here) add in norm;
+//   h2[s] = sum of S^2 over the sample's non-zero entries (bounds what the dropped product orders can contribute, see
+//     fuf_pairwise_gram);
+//   q[s] = the truncated digit form of sample s with itself: per bucket the integer sums c_p (exact), combined with
+//     the SAME floating-point operations in the same order as the tile epilogue uses for G[i,j] — so that
+//     q_i + q_j - 2 G[i,j] is exactly 0 when the digit rows of i and j coincide.
+__global__ void gram_stat_kernel(const double *__restrict__ r2part, const double *__restrict__ h2part,
+                                 const int32_t *__restrict__ cself, const Part *__restrict__ parts, int32_t n_parts,
+                                 const Group *__restrict__ groups, int64_t ldp, const double *__restrict__ err_in,
+                                 int64_t N, double *__restrict__ h2, double *__restrict__ err_out, double *__restrict__ q)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
-    double rs = 0.0, hs = 0.0;
-    for (int32_t b = 0; b < n_parts; b++) {
-        rs += r2part[(int64_t)b * ldp + s];
-        hs += h2part[(int64_t)b * ldp + s];
+    double rs = 0.0, hs = 0.0, acc = 0.0;
+    for (int32_t b = 0; b < n_parts;) {
+        const int32_t g = parts[b].group;
+        long long t[4] = {0, 0, 0, 0};
+        for (; b < n_parts && parts[b].group == g; b++) {
+            rs += r2part[(int64_t)b * ldp + s];
+            hs += h2part[(int64_t)b * ldp + s];
+#pragma unroll
+            for (int p = 0; p < 4; p++) t[p] += cself[((int64_t)b * 4 + p) * ldp + s];
+        }
+        double w = groups[g].w0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {   // the epilogue's operations, in the epilogue's order
+            acc = fma((double)(int32_t)t[p], w, acc);
+            w *= (1.0 / DIGIT);
+        }
     }
+    q[s] = acc;
     if (h2) h2[s] = hs;
     if (err_out) {
         const double a = sqrt(err_in ? err_in[s] : 0.0) + sqrt(rs);
         err_out[s] = a * a;
-    }
-}
-
-// q[s] = the truncated digit form of sample s with itself: per bucket the integer sums c_p = sum_k sum_{x+y=p} d_x d_y
-// (exact, int64), combined with the SAME floating-point operations in the same order as the tile epilogue uses for
-// G[i,j] — so that q_i + q_j - 2 G[i,j] is exactly 0 when the digit rows of i and j coincide.
-__global__ void __launch_bounds__(512)
-gram_selfnorm_kernel(const int8_t *__restrict__ D0, const int8_t *__restrict__ D1, const int8_t *__restrict__ D2,
-                     const int8_t *__restrict__ D3, const Lay ws, int64_t N, const Group *__restrict__ groups,
-                     int32_t n_groups, double *__restrict__ q)
-{
-    // 32 samples x 16 row slices per block; integer partial sums are combined exactly through shared memory
-    __shared__ long long part[4][16][33];
-    const int sx = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int64_t s = (int64_t)blockIdx.x * 32 + sx;
-    const bool ok = s < N;
-    double acc = 0.0;
-    int32_t r0 = 0;
-    for (int32_t g = 0; g < n_groups; g++) {
-        const int32_t r_end = groups[g].stage_end * KC;
-        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (ok) {
-            for (int32_t r = r0 + sl; r < r_end; r += 16) {
-                const int64_t o = ws.at(r, s);
-                const int x0 = D0[o], x1 = D1[o], x2 = D2[o], x3 = D3[o];
-                c0 += x0 * x0;
-                c1 += 2 * x0 * x1;
-                c2 += x1 * x1 + 2 * x0 * x2;
-                c3 += 2 * x0 * x3 + 2 * x1 * x2;
-            }
-        }
-        part[0][sl][sx] = c0;
-        part[1][sl][sx] = c1;
-        part[2][sl][sx] = c2;
-        part[3][sl][sx] = c3;
-        __syncthreads();
-        if (sl == 0 && ok) {
-            long long t[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-#pragma unroll
-                for (int u = 0; u < 16; u++) t[c] += part[c][u][sx];
-            double w = groups[g].w0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {   // the epilogue's operations, in the epilogue's order
-                acc = fma((double)(int32_t)t[c], w, acc);
-                w *= (1.0 / DIGIT);
-            }
-        }
-        __syncthreads();
-        r0 = r_end;
-    }
-    if (sl == 0 && ok) q[s] = acc;
-}
-
-// lower triangle := transpose of the upper triangle (tiles tj > ti and the diagonal tiles), 32x32 sub-blocks.
-__global__ void __launch_bounds__(256)
-mirror_kernel(double *__restrict__ D, int64_t N, int64_t ldd)
-{
-    const int bi = blockIdx.y, bj = blockIdx.x;  // 32x32 block coordinates, bj >= bi
-    if (bj < bi) return;
-    __shared__ double tile[32][33];
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int64_t i0 = (int64_t)bi * 32, j0 = (int64_t)bj * 32;
-    for (int r = ly; r < 32; r += 8) {
-        const int64_t gi = i0 + r, gj = j0 + lx;
-        tile[r][lx] = (gi < N && gj < N) ? D[gi * ldd + gj] : 0.0;
-    }
-    __syncthreads();
-    for (int r = ly; r < 32; r += 8) {
-        const int64_t gj = j0 + r, gi = i0 + lx;  // writes D[gj][gi] = upper[gi][gj]
-        if (gi < N && gj < N && gj > gi) D[gj * ldd + gi] = tile[lx][r];
     }
 }
 
@@ -738,14 +701,25 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     // ---- workspace: four digit planes | partial statistics | row map, scales, groups, tiles -----------------
     auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
     const size_t plane = up((size_t)n_rows * n_cols);
-    const int32_t rows_per_part = 512, n_parts = (n_rows + rows_per_part - 1) / rows_per_part;
+    std::vector<Part> parts;          // <= 512 rows each, never across a bucket boundary
+    {
+        int32_t r0 = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            const int32_t r_end = groups[g].stage_end * KC;
+            for (int32_t r = r0; r < r_end; r += 512) parts.push_back(Part{r, std::min(r_end, r + 512), (int32_t)g, 0});
+            r0 = r_end;
+        }
+    }
+    const int32_t n_parts = (int32_t)parts.size();
     const size_t part_bytes = up((size_t)n_parts * n_cols * sizeof(double));
+    const size_t cself_bytes = up((size_t)n_parts * 4 * n_cols * sizeof(int32_t));
+    const size_t parts_bytes = up(parts.size() * sizeof(Part));
     const size_t map_bytes = up((size_t)n_rows * sizeof(int32_t)), scl_bytes = up((size_t)n_rows * sizeof(float));
     const size_t grp_bytes = up(groups.size() * sizeof(Group)), tiles_bytes = up(tiles.size() * sizeof(Tile));
     const size_t sub_bytes = up((size_t)n_direct_pad * n_cols * sizeof(double)), dn_bytes = up((size_t)n_direct_pad * sizeof(int32_t));
     const size_t q_bytes = up((size_t)n_cols * sizeof(double));
     if ((rc = ctx->ws_gram.reserve(NDIG * plane + 2 * part_bytes + map_bytes + scl_bytes + grp_bytes + tiles_bytes + sub_bytes +
-                                   dn_bytes + q_bytes)))
+                                   dn_bytes + q_bytes + cself_bytes + parts_bytes)))
         return rc;
     char *wsp = (char *)ctx->ws_gram.ptr;
     int8_t *D0 = (int8_t *)wsp, *D1 = D0 + plane, *D2 = D1 + plane, *D3 = D2 + plane;
@@ -757,33 +731,32 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     double *SUB = (double *)((char *)d_tiles + tiles_bytes);
     int32_t *d_dn = (int32_t *)((char *)SUB + sub_bytes);
     double *q = (double *)((char *)d_dn + dn_bytes);  // squared norms of the quantised Gram part (kernel-internal)
+    int32_t *cself = (int32_t *)((char *)q + q_bytes);
+    Part *d_parts = (Part *)((char *)cself + cself_bytes);
+    FUF_CUDA(cudaMemcpyAsync(d_parts, parts.data(), parts.size() * sizeof(Part), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemcpyAsync(d_dn, direct_nodes.data(), (size_t)n_direct_pad * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemcpyAsync(d_map, row_map.data(), (size_t)n_rows * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemcpyAsync(d_scl, inv_scale.data(), (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(Group), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaStreamSynchronize(stream));  // the host vectors are pageable and die with this call
+    const Lay sub = shard == 0 ? Lay{n_cols, 0, n_cols} : Lay{shard, (int64_t)n_direct_pad * shard, shard};
     {
-        dim3 g((unsigned)((n_cols + 255) / 256), (unsigned)n_parts);
-        gram_digits_kernel<<<g, 256, 0, stream>>>(PT, lay, ws, n_cols, N, n_rows, rows_per_part, d_map, d_scl, D0, D1, D2,
-                                                  D3, r2part, h2part);
+        dim3 g((unsigned)((n_cols / 4 + 127) / 128), (unsigned)n_parts);
+        gram_digits_kernel<<<g, 128, 0, stream>>>(PT, lay, ws, n_cols, N, d_parts, d_map, d_scl, D0, D1, D2, D3, r2part,
+                                                  h2part, cself);
         FUF_CUDA(cudaGetLastError());
-        gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(r2part, h2part, n_parts, n_cols, err_in, N, h2, err_out);
-        FUF_CUDA(cudaGetLastError());
-        gram_selfnorm_kernel<<<(unsigned)((N + 31) / 32), 512, 0, stream>>>(D0, D1, D2, D3, ws, N, d_groups,
-                                                                              (int32_t)groups.size(), q);
+        gram_stat_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(r2part, h2part, cself, d_parts, n_parts, d_groups,
+                                                                          n_cols, err_in, N, h2, err_out, q);
         FUF_CUDA(cudaGetLastError());
         dim3 gg((unsigned)((n_cols + 255) / 256), (unsigned)n_direct_pad);
-        const Lay sub = shard == 0 ? Lay{n_cols, 0, n_cols} : Lay{shard, (int64_t)n_direct_pad * shard, shard};
-        gram_gather_kernel<<<gg, 256, 0, stream>>>(PT, lay, sub, n_cols, N, d_dn, SUB);
-        FUF_CUDA(cudaGetLastError());
-        // bypass part first, in float64: D = sum over the bypassed node columns of (a_i - a_j)^2
-        // (with no bypassed column this just zeroes the tiles the Gram epilogue adds to)
-        gram_bypass_kernel<<<dim3((unsigned)tiles.size(), 4), 256, 0, stream>>>(d_tiles, SUB, sub, n_direct > 0 ? n_direct_pad : 0,
-                                                                               N, D, ldd);
-        FUF_CUDA(cudaGetLastError());
+        if (n_direct > 0) {
+            gram_gather_kernel<<<gg, 256, 0, stream>>>(PT, lay, sub, n_cols, N, d_dn, SUB);
+            FUF_CUDA(cudaGetLastError());
+            ctx->launches += 1;
+        }
     }
-    ctx->launches += 5;
+    ctx->launches += 3;   // colmax, digits, stat
     CUtensorMap map0, map1, map2, map3;
     if ((rc = make_map(&map0, D0, N, n_rows, ws)) || (rc = make_map(&map1, D1, N, n_rows, ws)) ||
         (rc = make_map(&map2, D2, N, n_rows, ws)) || (rc = make_map(&map3, D3, N, n_rows, ws)))
@@ -798,6 +771,10 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     p.q = q;
     p.D = D;
     p.ldd = ldd;
+    p.mirror = full;
+    p.n_direct = n_direct;
+    p.SUB = SUB;
+    p.sub = sub;
     FUF_CUDA(cudaFuncSetAttribute(gram_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     const int grid = std::min<int64_t>(p.n_tiles, ctx->sm_count);
     if (!ctx->ev_gram[0]) {
@@ -811,12 +788,6 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     ctx->gram_flops = 10.0 * 2.0 * TILE * TILE * (double)n_rows * (double)p.n_tiles;  // int8 multiply-adds x 2
     ctx->gram_groups = p.n_groups;
     ctx->launches += 1;
-    if (full) {
-        const unsigned b = (unsigned)((N + 31) / 32);
-        mirror_kernel<<<dim3(b, b), 256, 0, stream>>>(D, N, ldd);
-        FUF_CUDA(cudaGetLastError());
-        ctx->launches += 1;
-    }
     return FUF_OK;
 }
 

@@ -619,6 +619,70 @@ int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int m
     return FUF_OK;
 }
 
+// Packed row blocks: slot c keeps only the columns its tile row owns, [128, N - 128 t] contiguous at offset[c] — what
+// crosses NVLink to the rank that joins the matrix (half the volume of the [128, N] blocks).
+struct PackedSlot {
+    int32_t t, pad;
+    int64_t offset;   // doubles
+};
+
+__global__ void __launch_bounds__(256)
+pack_tile_rows_kernel(const double *__restrict__ blocks, const PackedSlot *__restrict__ slots, int64_t N, int64_t ldb,
+                      double *__restrict__ packed)
+{
+    const int c = blockIdx.y;
+    const PackedSlot slot = slots[c];
+    if (slot.t < 0) return;
+    const int64_t col0 = (int64_t)slot.t * TILE, gj0 = col0 + (int64_t)blockIdx.x * TILE, ld = N - col0;
+    if (gj0 >= N) return;
+    const int64_t rows = min((int64_t)TILE, N - col0);
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int r = ly; r < rows; r += 8)
+        for (int q = lx; q < TILE; q += 32) {
+            const int64_t gj = gj0 + q;
+            if (gj < N) packed[slot.offset + r * ld + (gj - col0)] = blocks[((int64_t)c * TILE + r) * ldb + gj];
+        }
+}
+
+__global__ void __launch_bounds__(256)
+assemble_packed_kernel(const double *__restrict__ packed, const PackedSlot *__restrict__ slots, int64_t N,
+                       double *__restrict__ D, int64_t ldd)
+{
+    const int c = blockIdx.y;
+    const PackedSlot slot = slots[c];
+    const int t = slot.t;
+    if (t < 0) return;
+    const int tj = t + blockIdx.x;
+    const int64_t gi0 = (int64_t)t * TILE, gj0 = (int64_t)tj * TILE, ld = N - gi0;
+    if (gj0 >= N) return;
+    const double *src = packed + slot.offset;          // src[r * ld + (gj - gi0)]
+    __shared__ double tile[32][33];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int sb = 0; sb < 16; sb++) {
+        const int r0 = (sb >> 2) * 32, c0 = (sb & 3) * 32;
+        for (int rr = ly; rr < 32; rr += 8) {
+            const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
+            double v = 0.0;
+            if (gi < N && gj < N) {
+                if (tj == t && r0 + rr > c0 + lx)       // diagonal tile: lower triangle = mirror of the upper one
+                    v = src[(int64_t)(c0 + lx) * ld + r0 + rr];
+                else
+                    v = src[(int64_t)(r0 + rr) * ld + (gj - gi0)];
+                D[gi * ldd + gj] = v;
+            }
+            tile[rr][lx] = v;
+        }
+        __syncthreads();
+        if (tj != t) {
+            for (int cc = ly; cc < 32; cc += 8) {
+                const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;
+                if (gi < N && gj < N) D[gj * ldd + gi] = tile[lx][cc];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Prepares compact row blocks for the direct store into a host matrix shared by all ranks of one node
 // (fuf_store_tile_rows_host): the diagonal tile is made symmetric in place, every other upper tile is written
 // transposed into a [N - 128 (t + 1)] x 128 panel so that the mirror half leaves as one pitched DMA copy per tile row.
@@ -684,6 +748,54 @@ int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int
     return FUF_OK;
 }
 
+static int upload_packed_slots(fuf_ctx *ctx, const char *who, const int32_t *tile_rows_h, const int64_t *offsets_h,
+                               int32_t n_blocks, int64_t N, cudaStream_t stream, PackedSlot **d_slots)
+{
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    std::vector<PackedSlot> slots((size_t)n_blocks);
+    for (int32_t c = 0; c < n_blocks; c++) {
+        FUF_REQUIRE(tile_rows_h[c] >= -1 && tile_rows_h[c] < tiles_per_dim, "%s: tile row %d out of range", who,
+                    tile_rows_h[c]);
+        FUF_REQUIRE(tile_rows_h[c] < 0 || offsets_h[c] >= 0, "%s: negative offset", who);
+        slots[c] = PackedSlot{tile_rows_h[c], 0, offsets_h[c]};
+    }
+    int rc = ctx->ws_rows.reserve(slots.size() * sizeof(PackedSlot));
+    if (rc) return rc;
+    FUF_CUDA(cudaMemcpyAsync(ctx->ws_rows.ptr, slots.data(), slots.size() * sizeof(PackedSlot), cudaMemcpyHostToDevice,
+                             stream));
+    FUF_CUDA(cudaStreamSynchronize(stream));
+    *d_slots = (PackedSlot *)ctx->ws_rows.ptr;
+    return FUF_OK;
+}
+
+int pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_t *tile_rows_h, const int64_t *offsets_h,
+                   int32_t n_blocks, int64_t N, double *packed, cudaStream_t stream)
+{
+    if (n_blocks == 0 || N == 0) return FUF_OK;
+    PackedSlot *d_slots = nullptr;
+    int rc = upload_packed_slots(ctx, "fuf_pack_tile_rows", tile_rows_h, offsets_h, n_blocks, N, stream, &d_slots);
+    if (rc) return rc;
+    dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)n_blocks);
+    pack_tile_rows_kernel<<<grid, 256, 0, stream>>>(blocks, d_slots, N, ldb, packed);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+int assemble_packed(fuf_ctx *ctx, const double *packed, const int32_t *tile_rows_h, const int64_t *offsets_h,
+                    int32_t n_blocks, int64_t N, double *D, int64_t ldd, cudaStream_t stream)
+{
+    if (n_blocks == 0 || N == 0) return FUF_OK;
+    PackedSlot *d_slots = nullptr;
+    int rc = upload_packed_slots(ctx, "fuf_assemble_packed", tile_rows_h, offsets_h, n_blocks, N, stream, &d_slots);
+    if (rc) return rc;
+    dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)n_blocks);
+    assemble_packed_kernel<<<grid, 256, 0, stream>>>(packed, d_slots, N, D, ldd);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
 int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
                          int64_t ldb, double *D_h, int64_t ldd, cudaStream_t stream)
 {
@@ -709,16 +821,19 @@ int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_
     mirror_panels_kernel<<<grid, 256, 0, stream>>>(blocks, d_slots, N, ldb, panels);
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    const char *part_env = getenv("FUF_STORE_PART");      // diagnosis only: 1 = upper part only, 2 = mirror only
+    const int part = part_env ? atoi(part_env) : 0;
     for (int32_t c = 0; c < n_blocks; c++) {
         const int64_t t = slots[c].t;
         if (t < 0) continue;
         const int64_t row0 = t * TILE, rows = std::min<int64_t>(TILE, N - row0), below = N - row0 - rows;
         // rows [row0, row0 + rows), columns >= row0 (the diagonal tile is symmetric by now)
+        if (part != 2)
         FUF_CUDA(cudaMemcpy2DAsync(D_h + row0 * ldd + row0, (size_t)ldd * sizeof(double),
                                    blocks + (int64_t)c * TILE * ldb + row0, (size_t)ldb * sizeof(double),
                                    (size_t)(N - row0) * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, stream));
         // the mirror: rows below the diagonal tile, columns [row0, row0 + rows)
-        if (below > 0)
+        if (below > 0 && part != 1)
             FUF_CUDA(cudaMemcpy2DAsync(D_h + (row0 + rows) * ldd + row0, (size_t)ldd * sizeof(double),
                                        panels + slots[c].offset, (size_t)TILE * sizeof(double),
                                        (size_t)rows * sizeof(double), (size_t)below, cudaMemcpyDeviceToHost, stream));
@@ -770,4 +885,23 @@ extern "C" int fuf_store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int3
     FUF_REQUIRE(N >= 0 && ldd >= N && ldb >= N, "fuf_store_tile_rows_host: bad shape");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return store_tile_rows_host(ctx, blocks, tile_rows_h, n_blocks, N, ldb, D_h, ldd, (cudaStream_t)stream);
+}
+
+extern "C" int fuf_pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_t *tile_rows_h,
+                                  const int64_t *offsets_h, int32_t n_blocks, int64_t N, double *packed, void *stream)
+{
+    FUF_REQUIRE(ctx && blocks && tile_rows_h && offsets_h && packed, "fuf_pack_tile_rows: null argument");
+    FUF_REQUIRE(N >= 0 && ldb >= N, "fuf_pack_tile_rows: bad shape");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return pack_tile_rows(ctx, blocks, ldb, tile_rows_h, offsets_h, n_blocks, N, packed, (cudaStream_t)stream);
+}
+
+extern "C" int fuf_assemble_packed(fuf_ctx *ctx, const double *packed, const int32_t *tile_rows_h,
+                                   const int64_t *offsets_h, int32_t n_blocks, int64_t N, double *D, int64_t ldd,
+                                   void *stream)
+{
+    FUF_REQUIRE(ctx && packed && tile_rows_h && offsets_h && D, "fuf_assemble_packed: null argument");
+    FUF_REQUIRE(N >= 0 && ldd >= N, "fuf_assemble_packed: bad shape");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return assemble_packed(ctx, packed, tile_rows_h, offsets_h, n_blocks, N, D, ldd, (cudaStream_t)stream);
 }

@@ -71,18 +71,35 @@ refine_kernel(const RefineParams p)
         const double si = square ? sqrt(p.stat[gi]) : p.stat[gi];
         const double ti = p.stat2 ? p.stat2[gi] : 0.0;
         double *drow = p.D + row * p.ldd;
-#pragma unroll 1
+        // all the loads of the segment first (8 independent 256-byte requests per warp in flight), then the tests
+        double dv[RSEG / 32], sv[RSEG / 32], tv[RSEG / 32];
+#pragma unroll
+        for (int u = 0; u < RSEG / 32; u++) {
+            const int64_t gj = j0 + u * 32 + lane;
+            const bool in = gj > gi && gj < p.j_end;
+            dv[u] = in ? drow[gj] : 0.0;
+            sv[u] = in ? p.stat[gj] : 0.0;
+            tv[u] = (in && p.stat2) ? p.stat2[gj] : 0.0;
+        }
+        unsigned flags = 0;
+#pragma unroll
         for (int u = 0; u < RSEG / 32; u++) {
             const int64_t gj = j0 + u * 32 + lane;
             bool flag = false;
             if (gj > gi && gj < p.j_end) {
-                const double d = drow[gj];
-                const double sj = square ? sqrt(p.stat[gj]) : p.stat[gj];
+                const double d = dv[u];
+                const double sj = square ? sqrt(sv[u]) : sv[u];
                 const double b = si + sj;
                 flag = square ? !(d >= p.kappa * b * b) : !(d >= p.kappa * b);
                 if (b == 0.0) flag = false;  // both samples exactly representable in fp32: nothing to gain
-                if (p.stat2) flag = flag || !(d >= p.kappa2 * (ti + p.stat2[gj]));
+                if (p.stat2) flag = flag || !(d >= p.kappa2 * (ti + tv[u]));
             }
+            flags |= (flag ? 1u : 0u) << u;
+        }
+        if (__ballot_sync(0xffffffffu, flags != 0) == 0) continue;
+#pragma unroll 1
+        for (int u = 0; u < RSEG / 32; u++) {
+            const bool flag = (flags >> u) & 1u;
             unsigned mask = __ballot_sync(0xffffffffu, flag);
             if (mask == 0) continue;
             // the counter counts FLAGGED pairs; only the first `budget` of them are recomputed here (beyond that the

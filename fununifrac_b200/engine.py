@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 7
+ABI_VERSION = 8
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -75,6 +75,8 @@ def load_library() -> ctypes.CDLL:
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
         L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, vp]
         L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
+        L.fuf_pack_tile_rows.argtypes = [vp, vp, i64, vp, vp, i32, i64, vp, vp]
+        L.fuf_assemble_packed.argtypes = [vp, vp, vp, vp, i32, i64, vp, i64, vp]
         L.fuf_store_tile_rows_host.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
         L.fuf_diffab_block.argtypes = [vp, vp, ci, i64, i64, ci, i64, i64, vp, ci, vp]
         L.fuf_diffab_gather.argtypes = [vp, vp, ci, i64, i64, ci, vp, i64, vp, i64, vp, i64, vp, ci, vp]
@@ -92,7 +94,7 @@ def load_library() -> ctypes.CDLL:
                      "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_name_index_create",
                      "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
-                     "fuf_diffab_gather", "fuf_store_tile_rows_host",
+                     "fuf_diffab_gather", "fuf_store_tile_rows_host", "fuf_pack_tile_rows", "fuf_assemble_packed",
                      "fuf_all_pairs_host", "fuf_last_timing"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
@@ -395,6 +397,29 @@ class TreeContext:
         _check(self._lib.fuf_assemble(self.handle, blocks2.data_ptr(), rows_arr.ctypes.data, len(rows_arr), N,
                                       blocks2.stride(0), D.data_ptr(), D.stride(0), _stream_ptr(torch)),
                "fuf_assemble")
+        return D
+
+    def pack_tile_rows(self, blocks, tile_rows: Sequence[int], offsets: Sequence[int], N: int, packed):
+        """Copy the owned part of every row block (columns >= 128 t) to ``packed[offsets[c]:]`` (see sharded.py)."""
+        rows = np.ascontiguousarray(tile_rows, dtype=np.int32)
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert len(rows) == len(offs) and blocks.stride(1) == 1 and packed.is_contiguous()
+        _check(self._lib.fuf_pack_tile_rows(self.handle, blocks.data_ptr(), blocks.stride(0), rows.ctypes.data,
+                                            offs.ctypes.data, len(rows), N, packed.data_ptr(),
+                                            _stream_ptr(_torch())), "fuf_pack_tile_rows")
+        return packed
+
+    def assemble_packed(self, packed, tile_rows: Sequence[int], offsets: Sequence[int], N: int, D=None):
+        """Join packed row blocks (possibly gathered from several devices) into the symmetric N x N matrix."""
+        torch = _torch()
+        rows = np.ascontiguousarray(tile_rows, dtype=np.int32)
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert len(rows) == len(offs) and packed.is_contiguous()
+        if D is None:
+            D = torch.empty((N, N), dtype=torch.float64, device=packed.device)
+        _check(self._lib.fuf_assemble_packed(self.handle, packed.data_ptr(), rows.ctypes.data, offs.ctypes.data,
+                                             len(rows), N, D.data_ptr(), D.stride(0), _stream_ptr(torch)),
+               "fuf_assemble_packed")
         return D
 
     def store_tile_rows_host(self, blocks, tile_rows: Sequence[int], N: int, D_host: np.ndarray):

@@ -8,8 +8,8 @@ without any collective inside the kernels:
 2. one all-gather of the pushed blocks over NCCL / NVLink            (→ ``[G, n, shard]``, the layout ``fuf_pairwise``
    reads directly through its ``shard`` / ``shard_stride`` arguments)
 3. rank r computes the 128-row tile rows it owns, upper triangle    (``fuf_pairwise`` with ``tile_rows``)
-4. one gather of the compact row blocks to rank 0, which mirrors    (``fuf_assemble``)
-   them into the full symmetric matrix (``step``: matrix resident on GPU 0), or — with host buffers, ``step_host`` —
+4. one gather of the row blocks, packed to the columns each tile   (``fuf_pack_tile_rows``, ``fuf_assemble_packed``)
+   row owns, to rank 0, which mirrors them into the full symmetric matrix (``step``: matrix resident on GPU 0), or — with host buffers, ``step_host`` —
    every rank stores its tile rows and their mirror straight into ONE host matrix shared by the ranks of the node
    (``SharedHostMatrix`` + ``fuf_store_tile_rows_host``): the device-to-host traffic then runs over all PCIe links at
    once and nothing funnels through rank 0.
@@ -47,6 +47,17 @@ def owned_tile_rows(N: int, world: int, rank: int) -> List[int]:
     return [t for t in range(T) if tile_row_owner(t, world) == rank]
 
 
+def packed_offsets(rows: Sequence[int], N: int):
+    """Packed layout of a rank's row blocks: slot c keeps [128, N - 128 t] (the columns its tile row owns), contiguous,
+    at offsets[c] doubles.  Returns (offsets, total); -1 rows are padding slots and take no room."""
+    offsets, total = [], 0
+    for t in rows:
+        offsets.append(total)
+        if t >= 0:
+            total += TILE * (N - TILE * t)
+    return offsets, total
+
+
 def tiles_of(rows: Sequence[int], N: int) -> int:
     T = (N + TILE - 1) // TILE
     return sum(T - t for t in rows)
@@ -55,8 +66,8 @@ def tiles_of(rows: Sequence[int], N: int) -> int:
 class ShardedAllPairs:
     """One rank's part of an all-pairs job over ``N`` samples.
 
-    ``ops`` provides ``n``, ``empty(shape, dtype)``, ``push_up_center``, ``push_up``, ``pairwise``, ``refine`` and
-    ``assemble`` with the semantics of the C ABI; ``dist`` is ``torch.distributed`` (None when world == 1).
+    ``ops`` provides ``n``, ``empty(shape, dtype)``, ``push_up_center``, ``push_up``, ``pairwise``, ``refine``,
+    ``pack_tile_rows``, ``assemble_packed`` (and the host-buffer calls) with the semantics of the C ABI; ``dist`` is ``torch.distributed`` (None when world == 1).
     ``refine=True`` also exchanges the float64 profiles and runs the float64 refinement pass on this rank's rows.
     """
 
@@ -86,9 +97,14 @@ class ShardedAllPairs:
         if world > 1:
             self.flagged = ops.empty((1,), "int64")
             self.blocks = ops.empty((self.max_rows * TILE, N), "float64")
-            self.slot_rows = []     # rank 0's gather buffer: one slot of max_rows row blocks per rank
+            # what crosses NVLink to rank 0: each rank's row blocks packed to the columns they own (half the volume)
+            self.offs, _ = packed_offsets(self.rows, N)
+            self.max_packed = max(1, max(packed_offsets(r, N)[1] for r in self.all_rows))
+            self.packed = None
+            self.slot_rows, self.slot_offs = [], []
             for r in range(world):
-                self.slot_rows += self.all_rows[r] + [-1] * (self.max_rows - len(self.all_rows[r]))
+                self.slot_rows += self.all_rows[r]
+                self.slot_offs += [r * self.max_packed + o for o in packed_offsets(self.all_rows[r], N)[0]]
 
     def _pairwise(self, rows, D):
         """Distances of this rank's tile rows (all rows when ``rows`` is None) into D; returns the refinement
@@ -145,12 +161,16 @@ class ShardedAllPairs:
         self._compute(X_local, mark)
         if self.world > 1:
             r = self.rank
-            if r == 0 and self.gathered is None:
-                self.D = self.ops.empty((self.N, self.N), "float64")
-                self.gathered = self.ops.empty((self.world, self.max_rows * TILE, self.N), "float64")
-            self.dist.gather(self.blocks, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
+            if self.packed is None:
+                self.packed = self.ops.empty((self.max_packed,), "float64")
+                if r == 0:
+                    self.D = self.ops.empty((self.N, self.N), "float64")
+                    self.gathered = self.ops.empty((self.world, self.max_packed), "float64")
+            if self.rows:
+                self.ops.pack_tile_rows(self.blocks, self.rows, self.offs, self.N, self.packed)
+            self.dist.gather(self.packed, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
             if r == 0:
-                self.ops.assemble(self.gathered, self.slot_rows, self.N, self.D)
+                self.ops.assemble_packed(self.gathered, self.slot_rows, self.slot_offs, self.N, self.D)
         mark("end")
         return self.D
 
@@ -269,6 +289,12 @@ class CudaOps:
 
     def assemble(self, blocks, rows, N, D):
         return self.ctx.assemble(blocks, rows, N, D=D)
+
+    def pack_tile_rows(self, blocks, rows, offsets, N, packed):
+        return self.ctx.pack_tile_rows(blocks, rows, offsets, N, packed)
+
+    def assemble_packed(self, packed, rows, offsets, N, D):
+        return self.ctx.assemble_packed(packed.view(-1), rows, offsets, N, D=D)
 
     def to_device(self, X_host, stage):
         src = X_host if self.torch.is_tensor(X_host) else self.torch.from_numpy(X_host)

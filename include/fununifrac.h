@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 7
+#define FUF_ABI_VERSION 8
 
 /* error codes */
 #define FUF_OK 0
@@ -216,6 +216,15 @@ int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
  * tile_rows_h[c] == -1 marks a padding block that is skipped. */
 int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
                  int64_t ldb, double *D, int64_t ldd, void *stream);
+
+/* The same join with half the traffic between devices: fuf_pack_tile_rows copies the part of each row block its tile
+ * row owns (rows x columns >= 128 t, row-major with leading dimension N - 128 t) to packed + offsets_h[c] (doubles);
+ * the packed buffers of several devices, gathered and concatenated, are joined by fuf_assemble_packed, which reads
+ * slot c at packed + offsets_h[c].  tile_rows_h[c] == -1: padding slot (its offset is ignored). */
+int fuf_pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_t *tile_rows_h,
+                       const int64_t *offsets_h, int32_t n_blocks, int64_t N, double *packed, void *stream);
+int fuf_assemble_packed(fuf_ctx *ctx, const double *packed, const int32_t *tile_rows_h, const int64_t *offsets_h,
+                        int32_t n_blocks, int64_t N, double *D, int64_t ldd, void *stream);
 
 /* Same join, but straight into a HOST matrix: each GPU of a node stores the tile rows it owns (and their mirror image)
  * into one N x N host matrix shared by all ranks (shared memory registered with cudaHostRegister in every process), so

@@ -205,6 +205,19 @@ def test_tile_rows_assemble_and_shards(full_tree):
     # the same join straight into one host matrix (what every rank of a node does in ShardedAllPairs.step_host):
     # pinned, page-locked-by-registration (SharedHostMatrix) and plain pageable destinations, N not a multiple of 128
     from fununifrac_b200 import sharded
+    # packed row blocks (what crosses NVLink in ShardedAllPairs.step): same matrix, bit for bit
+    offs_all, packs, base = [], [], 0
+    for own, blk in zip(owners, blocks):
+        offs, total = sharded.packed_offsets(own, N)
+        assert total == sum(128 * (N - 128 * t) for t in own)
+        pk = torch.full((total + 5,), float("nan"), dtype=torch.float64, device="cuda")
+        ctx.pack_tile_rows(blk, own, offs, N, pk)
+        assert bool(pk[total:].isnan().all())            # nothing beyond the slots is touched
+        packs.append(pk)
+        offs_all += [base + o for o in offs]
+        base += total + 5
+    D2c = ctx.assemble_packed(torch.cat(packs), rows + [-1], offs_all + [0], N)
+    assert torch.equal(D2, D2c)
     shared = sharded.SharedHostMatrix(N)
     pinned = torch.full((N, N), float("nan"), dtype=torch.float64, pin_memory=True).numpy()
     pageable = np.full((N, N + 3), np.nan)[:, :N]

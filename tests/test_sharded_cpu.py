@@ -31,6 +31,8 @@ def test_partition_helpers():
         assert sum(tiles) == T * (T + 1) // 2
         if T >= 4 * world:          # balanced to within ~one tile row
             assert max(tiles) - min(tiles) <= T
+    offs, total = sharded.packed_offsets([0, 5, -1, 2], 700)
+    assert offs == [0, 128 * 700, 128 * 700 + 128 * 60, 128 * 700 + 128 * 60] and total == offs[-1] + 128 * (700 - 256)
     # 10K samples over 8 GPUs: every rank within 2% of the mean tile count
     t = [sharded.tiles_of(sharded.owned_tile_rows(10000, 8, r), 10000) for r in range(8)]
     assert max(t) / (sum(t) / 8) < 1.02
@@ -102,6 +104,25 @@ class OracleOps:
             D[r0:, r0:r1] = blk[:, r0:].T
             D[r0:r1, r1:] = blk[:, r1:]
             D[r0:r1, r0:r1] = torch.triu(blk[:, r0:r1]) + torch.triu(blk[:, r0:r1], 1).T
+        return D
+
+    def pack_tile_rows(self, blocks, rows, offsets, N, packed):
+        packed.fill_(float("nan"))
+        for c, (t, off) in enumerate(zip(rows, offsets)):
+            r0, r1 = t * TILE, min(N, (t + 1) * TILE)
+            packed[off:off + (r1 - r0) * (N - r0)] = blocks[c * TILE:c * TILE + (r1 - r0), r0:].reshape(-1)
+        return packed
+
+    def assemble_packed(self, packed, rows, offsets, N, D):
+        packed = packed.reshape(-1)
+        for t, off in zip(rows, offsets):
+            if t < 0:
+                continue
+            r0, r1 = t * TILE, min(N, (t + 1) * TILE)
+            blk = packed[off:off + (r1 - r0) * (N - r0)].reshape(r1 - r0, N - r0)
+            D[r0:, r0:r1] = blk.T
+            D[r0:r1, r1:] = blk[:, r1 - r0:]
+            D[r0:r1, r0:r1] = torch.triu(blk[:, :r1 - r0]) + torch.triu(blk[:, :r1 - r0], 1).T
         return D
 
     # host-buffer variant (step_host)
