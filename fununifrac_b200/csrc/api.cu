@@ -2,9 +2,9 @@
 // (src/compute_all_pairwise_fununifrac.py:64-73: push every profile up, then pairwise_computation)
 // behind one C call with HOST pointers.
 //
-// Pipeline: X is copied to the device in row blocks on a copy stream (double-buffered staging),
-// each block is pushed up on the compute stream as soon as it has landed, then the all-pairs kernel
-// runs band by band (see below), each band followed by the float64 refinement pass over the few pairs the
+// Pipeline: X is copied to the device in sample bands on a copy stream (all copies queued up front into a
+// full-size device copy), each band is pushed up on the compute stream as soon as it has landed, then the all-pairs
+// kernel runs band by band (see below), each band followed by the float64 refinement pass over the few pairs the
 // fp32 operands cannot certify (refine.cu) and by the device-to-host copy of the finished part of D on a
 // third stream.  (Letting the tile epilogues write D straight into pinned host memory was measured: the
 // kernel then stalls for exactly the PCIe time of the matrix, so the DMA engines do it instead.)
@@ -14,6 +14,24 @@
 #include "common.cuh"
 
 using namespace fuf;
+
+// Every early return (an error in the middle of the pipeline) must leave no copy in flight that still reads the
+// caller's X_h or writes its D_h: drain the three streams unless the success path has already done so.
+namespace {
+struct StreamDrain {
+    fuf_ctx *ctx;
+    bool armed = true;
+    explicit StreamDrain(fuf_ctx *c) : ctx(c) {}
+    ~StreamDrain()
+    {
+        if (!armed) return;
+        cudaStreamSynchronize(ctx->s_copy);
+        cudaStreamSynchronize(ctx->s_comp);
+        cudaStreamSynchronize(ctx->s_d2h);
+        cudaGetLastError();
+    }
+};
+}  // namespace
 
 static bool is_pinned_host(const void *p)
 {
@@ -82,6 +100,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     std::vector<int64_t> band_tile(nb + 1);
     for (int b = 0; b <= nb; b++) band_tile[b] = tiles_per_dim * b / nb;
 
+    StreamDrain drain(ctx);
     FUF_CUDA(cudaEventRecord(e_start, sk));
     FUF_CUDA(cudaStreamWaitEvent(sc, e_start, 0));
     for (int b = 0; b < nb; b++) {  // all copies are queued up front
@@ -177,6 +196,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             FUF_CUDA(cudaStreamSynchronize(sk));
         }
     }
+    drain.armed = false;   // sk and sc are idle, and sk waited for the last copy on sd
     return FUF_OK;
 }
 

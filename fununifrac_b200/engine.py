@@ -522,8 +522,9 @@ class Pushed:
 # ---------------------------------------------------------------------------------------------------
 
 def context_for(input, device: Optional[int] = None) -> TreeContext:
-    """Tree context cached on a ``FuncTreeEmduInput`` (rebuilt if its dicts were changed in size)."""
-    key = (len(input.basis), len(input.lint), device)
+    """Tree context cached on a ``FuncTreeEmduInput``; rebuilt when its dicts change in size or the edge lengths
+    change in sum (a C-speed checksum: 0.3 ms for the full KO tree, against ~10 ms for re-densifying the dicts)."""
+    key = (len(input.basis), len(input.lint), device, sum(input.lint.values()))
     cached = input.__dict__.get("_fuf_ctx")
     if cached is not None and cached[0] == key and cached[1]._h:
         return cached[1]
