@@ -214,15 +214,39 @@ class SharedHostMatrix:
 
         self.N, self.nbytes = N, max(8, N * N * 8)
         self._registered = False
+        self._fd = self._map = None
         if rank == 0:
             self._fd = os.memfd_create("fununifrac_D")
             os.ftruncate(self._fd, self.nbytes)
         if world > 1:
             where = [(os.getpid(), self._fd) if rank == 0 else None]
             dist.broadcast_object_list(where, src=0)
+            opened = True
             if rank != 0:
-                self._fd = os.open(f"/proc/{where[0][0]}/fd/{where[0][1]}", os.O_RDWR)
-            dist.barrier()           # rank 0 keeps its descriptor open until everybody has opened the file
+                try:
+                    if os.environ.get("FUF_SHARED_NO_PROCFD"):      # test hook: exercise the named-file route
+                        raise OSError("disabled")
+                    self._fd = os.open(f"/proc/{where[0][0]}/fd/{where[0][1]}", os.O_RDWR)
+                except OSError:
+                    opened = False
+            votes = [None] * world
+            dist.all_gather_object(votes, opened)      # rank 0 keeps its descriptor open until everybody has answered
+            if not all(votes):
+                # /proc/<pid>/fd is not reachable from every rank (separate PID namespaces): a named file in shared memory
+                import tempfile
+                for fd in ([self._fd] if self._fd is not None else []):
+                    os.close(fd)
+                path = [None]
+                if rank == 0:
+                    shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+                    self._fd, path[0] = tempfile.mkstemp(prefix="fununifrac_D_", dir=shm_dir)
+                    os.ftruncate(self._fd, self.nbytes)
+                dist.broadcast_object_list(path, src=0)
+                if rank != 0:
+                    self._fd = os.open(path[0], os.O_RDWR)
+                dist.barrier()
+                if rank == 0:
+                    os.unlink(path[0])                 # the pages live until the last mapping goes
         self._map = mmap.mmap(self._fd, self.nbytes)
         self.array = np.frombuffer(self._map, dtype=np.float64, count=N * N).reshape(N, N)
         if register is None:

@@ -197,7 +197,9 @@ def _worker(rank, world, port, N, l2, out_path):
 
 
 @pytest.mark.parametrize("world,N,l2", [(2, 300, False), (3, 700, False), (2, 129, True)])
-def test_sharded_exchange_gloo(world, N, l2, tmp_path):
+def test_sharded_exchange_gloo(world, N, l2, tmp_path, monkeypatch):
+    if world == 3:      # once through the named shared-memory file instead of /proc/<pid>/fd
+        monkeypatch.setenv("FUF_SHARED_NO_PROCFD", "1")
     out = str(tmp_path / "D.npy")
     mp.spawn(_worker, args=(world, _free_port(), N, l2, out), nprocs=world, join=True)
     assert np.load(out).shape == (N, N)
