@@ -581,31 +581,42 @@ def combinations_offset(i: int, N: int) -> int:
     return i * N - i * (i + 1) // 2
 
 
-def iter_diffab_blocks(ctx: TreeContext, PT, N: int, mode: int, pairs_per_block: int = 1024, out_dtype=None
-                       ) -> Iterator[Tuple[int, int, np.ndarray]]:
+def diffab_pair_range(N: int, world: int = 1, rank: int = 0) -> Tuple[int, int]:
+    """Pairs (``itertools.combinations`` order) a rank streams when ``--diffab`` output is sharded over the GPUs of a
+    node: contiguous, equal shares (every pair costs the same n entries)."""
+    total = N * (N - 1) // 2
+    return total * rank // world, total * (rank + 1) // world
+
+
+def iter_diffab_blocks(ctx: TreeContext, PT, N: int, mode: int, pairs_per_block: int = 1024, out_dtype=None,
+                       pair_begin: int = 0, pair_end: Optional[int] = None) -> Iterator[Tuple[int, int, np.ndarray]]:
     """Stream dense diffab rows to pinned host memory.
 
     Yields ``(pair_begin, pair_end, rows)`` with ``rows`` a numpy view [pairs, n] that is valid until the
-    next iteration.  K4 writes each block into one of two device buffers; the copy engine moves it to one of two
+    next iteration; ``pair_begin`` / ``pair_end`` restrict the stream to a range of pairs (one rank's share, see
+    ``diffab_pair_range``).  K4 writes each block into one of two device buffers; the copy engine moves it to one of two
     pinned host buffers on a second stream while K4 fills the other one and the consumer works on the block
     before (letting the kernel store straight into pinned host memory was measured at 60 % of the link rate;
     the DMA engine reaches it).
     """
     torch = _torch()
     total = N * (N - 1) // 2
-    if total == 0:
+    pair_end = total if pair_end is None else pair_end
+    if not 0 <= pair_begin <= pair_end <= total:
+        raise ValueError(f"pair range [{pair_begin}, {pair_end}) outside [0, {total})")
+    if pair_end == pair_begin:
         return
     dt = out_dtype or PT.dtype
-    ppb = min(pairs_per_block, total)
+    ppb = min(pairs_per_block, pair_end - pair_begin)
     dev = [torch.empty((ppb, ctx.n), dtype=dt, device=PT.device) for _ in range(2)]
     host = [torch.empty((ppb, ctx.n), dtype=dt, pin_memory=True) for _ in range(2)]
     ev_kernel = [torch.cuda.Event(), torch.cuda.Event()]
     ev_copy = [torch.cuda.Event(), torch.cuda.Event()]
     copy_stream = torch.cuda.Stream(device=PT.device)
-    starts = list(range(0, total, ppb))
+    starts = list(range(pair_begin, pair_end, ppb))
 
     def launch(bi):
-        b, e = starts[bi], min(total, starts[bi] + ppb)
+        b, e = starts[bi], min(pair_end, starts[bi] + ppb)
         slot = bi & 1
         ctx.diffab_block(PT, N, mode, b, e, dev[slot])      # compute stream; dev[slot]'s previous copy was awaited
         ev_kernel[slot].record()

@@ -509,6 +509,19 @@ def test_diffab_blocks_vs_oracle(golden_dir):
             seen += e - b
         assert seen == N * (N - 1) // 2
         assert np.array_equal(got, want)                 # float64 rows are bit-identical to P_i - P_j
+        # the stream sharded over 3 "ranks": contiguous pair ranges that tile [0, total) and give the same rows
+        whole = np.concatenate([rows.copy() for _, _, rows in engine.iter_diffab_blocks(ctx, P64T, N, mode, 64)])
+        parts, edges = [], []
+        for r in range(3):
+            p0, p1 = engine.diffab_pair_range(N, 3, r)
+            edges.append((p0, p1))
+            for b, e, rows in engine.iter_diffab_blocks(ctx, P64T, N, mode, 50, pair_begin=p0, pair_end=p1):
+                assert p0 <= b < e <= p1
+                parts.append(rows.copy())
+        assert edges[0][0] == 0 and edges[-1][1] == len(whole) and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert np.array_equal(np.concatenate(parts), whole)
+        with pytest.raises(ValueError):
+            next(engine.iter_diffab_blocks(ctx, P64T, N, mode, 50, pair_begin=5, pair_end=len(whole) + 1))
         PT = ctx.push_up(Xd, mode)
         out = torch.empty((N - 1, n), dtype=torch.float32, device="cuda")
         ctx.diffab_block(PT, N, mode, 0, N - 1, out)     # pairs (0, 1..N-1), fp32 production rows
