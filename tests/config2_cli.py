@@ -2,7 +2,7 @@
 """BASELINE config 2 through the drop-in CLI: synthetic full KO tree (30,002 nodes), N gather CSVs on disk
 (29 sourmash columns, 2,000-8,000 KO rows each), weighted L1, median_abund, one B200.
 
-    python tools/config2_cli.py [N=1000]
+    python tests/config2_cli.py [N=1000]
 
 Times the whole user-visible run (argument parsing -> tree -> native ingest -> push-up + all pairs -> np.save) and
 checks the saved matrix against the CPU oracle on the same files.  Prints one JSON line."""
