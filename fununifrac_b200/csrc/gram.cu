@@ -159,9 +159,41 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
         : "memory");
 }
+// The issuing thread is the bottleneck of this kernel if it spends more than the ~68 cycles an MMA takes on building
+// its operands: the descriptors of one stage differ only in the 14-bit start-address field, so the low words are
+// `stage base + constant` (one add each) and the high word (SBO, version, layout) is a constant.
+constexpr uint32_t DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_SW64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) & 0x3FFFu; }
+template <int CTA_GROUP, uint32_t HI_A, uint32_t HI_B, uint32_t IDESC_V, int ACCUMULATE>
+__device__ __forceinline__ void umma_i8_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo)
+{
+    if (CTA_GROUP == 1)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "n"(HI_A), "n"(HI_B), "r"(IDESC_V), "n"(ACCUMULATE)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "n"(HI_A), "n"(HI_B), "r"(IDESC_V), "n"(ACCUMULATE)
+            : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// int32 -> double without the quarter-rate I2F.F64: 2^52 + 2^31 + v is exactly representable, its bit pattern is
+// {0x43300000, v ^ 0x80000000}; one LOP3 and one DADD (exact for every int32).
+__device__ __forceinline__ double i32_to_f64(uint32_t v)
+{
+    return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
@@ -259,25 +291,43 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
                         mbar_wait(full0 + 8 * slot, phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t A = base + slot * STAGE_BYTES, B = A + NDIG * PLANE_BYTES;
-#pragma unroll
-                        for (int kb = 0; kb < KC / KB; kb++) {
-                            const uint32_t off = kb * KB * TILE;  // 32 rows x 128 B
-                            // order c: all products d_x d'_y with x + y = c go to accumulator c
+                        const uint32_t a_lo = desc_lo(base + slot * STAGE_BYTES), b_lo = a_lo + ((NDIG * PLANE_BYTES) >> 4);
+                        if (fresh) {
+                            // first 32 rows of a bucket: accumulator c must have been drained by the epilogue, and the
+                            // first product of every order overwrites it
 #pragma unroll
                             for (int c = 0; c < NDIG; c++) {
-                                if (fresh) {  // accumulator c must have been drained by the epilogue
-                                    mbar_wait(tempty0 + 8 * c, eph);
-                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                }
+                                mbar_wait(tempty0 + 8 * c, eph);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                                 if (lane == 0) {
+                                    umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 0>(
+                                        tmem_base + c * TILE, a_lo, b_lo + ((c * PLANE_BYTES) >> 4));
 #pragma unroll
-                                    for (int x = 0; x <= c; x++)
-                                        umma_i8(tmem_base + c * TILE, umma_desc(A + x * PLANE_BYTES + off),
-                                                umma_desc(B + (c - x) * PLANE_BYTES + off), (fresh && x == 0) ? 0u : 1u);
+                                    for (int x = 1; x <= c; x++)
+                                        umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 1>(
+                                            tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
+                                            b_lo + (((c - x) * PLANE_BYTES) >> 4));
                                 }
                             }
                             fresh = false;
+                        } else if (lane == 0) {
+#pragma unroll
+                            for (int c = 0; c < NDIG; c++)
+#pragma unroll
+                                for (int x = 0; x <= c; x++)
+                                    umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 1>(
+                                        tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
+                                        b_lo + (((c - x) * PLANE_BYTES) >> 4));
+                        }
+                        if (lane == 0) {   // second 32 rows of the stage: order c = all products d_x d'_y with x + y = c
+                            constexpr uint32_t off = (KB * TILE) >> 4;
+#pragma unroll
+                            for (int c = 0; c < NDIG; c++)
+#pragma unroll
+                                for (int x = 0; x <= c; x++)
+                                    umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 1>(
+                                        tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4) + off,
+                                        b_lo + (((c - x) * PLANE_BYTES) >> 4) + off);
                         }
                         if (lane == 0) umma_commit(empty0 + 8 * slot);  // frees the smem stage when the MMAs have read it
                         __syncwarp();
@@ -310,7 +360,7 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         uint32_t v[32];
                         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64 + cb * 32, v);
 #pragma unroll
-                        for (int e = 0; e < 32; e++) acc[cb * 32 + e] = fma((double)(int32_t)v[e], w, acc[cb * 32 + e]);
+                        for (int e = 0; e < 32; e++) acc[cb * 32 + e] = fma(i32_to_f64(v[e]), w, acc[cb * 32 + e]);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
@@ -353,6 +403,288 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3x2 gram_pair_kernel: the same computation on CTA PAIRS (thread-block clusters of 2, tcgen05 cta_group::2).
+// With one CTA per tile the tensor pipe is held back by shared-memory bandwidth: an int8 MMA (M = N = 128, K = 32)
+// reads 8 KB of operands per 68 cycles (120 B/clk) while TMA writes another 48 B/clk into the same banks.  A pair
+// computes a 256 x 128 tile: M = 256 are the samples of TWO column tiles (2b, 2b+1), one per CTA, N = 128 the samples
+// of row tile ti, split in halves of 64 between the two CTAs.  Per CTA and MMA that is 4 KB (A) + 2 KB (half of B):
+// 90 B/clk of reads + 36 B/clk of TMA writes, and a stage shrinks from 64 KB to 48 KB (4 stages).
+//   * both CTAs run a TMA producer for their own operands; every byte is accounted on CTA 0's `full` barrier
+//     (cp.async.bulk.tensor ... .cta_group::2 with the barrier address of the even CTA);
+//   * CTA 0's MMA warp issues tcgen05.mma.cta_group::2; its commits are multicast to the `empty` / `tfull` barriers
+//     of both CTAs;
+//   * each CTA's accumulators (TMEM lanes = its 128 column-tile samples, columns = the 128 row-tile samples) hold the
+//     TRANSPOSED tile: the epilogue's stores into D[row][column] run along the lanes (coalesced);
+//   * the epilogue warps of both CTAs release accumulator c on CTA 0's `tempty[c]` (remote mbarrier arrive).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 4;
+constexpr uint32_t PLANE_B2 = 64 * KC;                                   // 4 KB: half of B, one digit plane
+constexpr uint32_t STAGE2_BYTES = NDIG * PLANE_BYTES + NDIG * PLANE_B2;  // 48 KB per CTA
+constexpr uint32_t SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                              // shared::cluster address of the even CTA
+
+struct PairTile {
+    int32_t ti, b;       // row tile, column-tile pair (2b, 2b + 1)
+    int32_t out_row0, pad;
+};
+
+struct Params2 {
+    const PairTile *tiles;
+    const Group *groups;
+    int32_t n_tiles, n_groups;
+    int32_t S;
+    int32_t tiles_per_dim;
+    int64_t N;
+    const double *q;
+    double *D;
+    int64_t ldd;
+    int32_t mirror, n_direct;
+    const double *SUB;
+    Lay sub;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar_cta0, int c0, int c1,
+                                                int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cta0), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+// half of B: 64 samples = 64-byte rows, SWIZZLE_64B (layout type 4), 8-row atoms of 512 bytes
+__device__ __forceinline__ uint64_t umma_desc_b64(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(PLANE_B2 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           (1ull << 46) | (4ull << 61);
+}
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TILE >> 3) << 17) |
+                            ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair, N = 128
+__device__ __forceinline__ void umma_i8_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC2), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                 const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+                 const __grid_constant__ CUtensorMap mapB2, const __grid_constant__ CUtensorMap mapB3, const Params2 p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
+    const uint32_t bars = base + STAGES2 * STAGE2_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES2, tfull = bars + 16 * STAGES2, tempty0 = tfull + 8;
+    const uint32_t tmem_slot = tempty0 + 8 * NDIG;
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; s++) {
+            mbar_init(full0 + 8 * s, 1);   // CTA 0: its producer's arrive.expect_tx (+ the TMA bytes of both CTAs)
+            mbar_init(empty0 + 8 * s, 1);  // both: multicast tcgen05.commit of the MMA warp
+        }
+        mbar_init(tfull, 1);                                                        // both: multicast commit
+        for (int c = 0; c < NDIG; c++) mbar_init(tempty0 + 8 * c, 2 * NEPI_WARPS);  // CTA 0: epilogue warps of the pair
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // warp 1 of BOTH CTAs: paired tensor-memory allocation
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything can signal them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int stages_total = p.groups[p.n_groups - 1].stage_end;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0) {
+            // ===================== TMA producer (both CTAs, each for its own operands) =====================
+            if (lane == 0) {
+                uint32_t it = 0;
+                for (int t = pair; t < p.n_tiles; t += n_pairs) {
+                    const PairTile tl = p.tiles[t];
+                    const int sa = (2 * tl.b + (int)rank) * TILE;          // first sample of this CTA's column tile
+                    const int sb = tl.ti * TILE + 64 * (int)rank;          // its half of the row tile
+                    const int ia = sa % p.S, ga = sa / p.S, ib = sb % p.S, gb = sb / p.S;
+                    for (int st = 0; st < stages_total; ++st, ++it) {
+                        const uint32_t slot = it % STAGES2, phase = (it / STAGES2) & 1u;
+                        mbar_wait(empty0 + 8 * slot, phase ^ 1u);
+                        const uint32_t full = (full0 + 8 * slot) & PEER_MASK;   // CTA 0's barrier
+                        if (rank == 0) mbar_expect_tx(full0 + 8 * slot, 2 * STAGE2_BYTES);
+                        const uint32_t dst = base + slot * STAGE2_BYTES, dstB = dst + NDIG * PLANE_BYTES;
+                        tma_load_3d_2sm(dst + 0 * PLANE_BYTES, &mapA0, full, ia, st * KC, ga);
+                        tma_load_3d_2sm(dst + 1 * PLANE_BYTES, &mapA1, full, ia, st * KC, ga);
+                        tma_load_3d_2sm(dst + 2 * PLANE_BYTES, &mapA2, full, ia, st * KC, ga);
+                        tma_load_3d_2sm(dst + 3 * PLANE_BYTES, &mapA3, full, ia, st * KC, ga);
+                        tma_load_3d_2sm(dstB + 0 * PLANE_B2, &mapB0, full, ib, st * KC, gb);
+                        tma_load_3d_2sm(dstB + 1 * PLANE_B2, &mapB1, full, ib, st * KC, gb);
+                        tma_load_3d_2sm(dstB + 2 * PLANE_B2, &mapB2, full, ib, st * KC, gb);
+                        tma_load_3d_2sm(dstB + 3 * PLANE_B2, &mapB3, full, ib, st * KC, gb);
+                    }
+                }
+            }
+        } else if (warp == 1 && rank == 0) {
+            // ===================== MMA issuer: one elected lane of the even CTA, for the pair =====================
+            uint32_t it = 0, grp_it = 0;
+            for (int t = pair; t < p.n_tiles; t += n_pairs) {
+                int st = 0;
+                for (int g = 0; g < p.n_groups; ++g, ++grp_it) {
+                    const int s_end = p.groups[g].stage_end;
+                    const uint32_t eph = (grp_it & 1u) ^ 1u;
+                    bool fresh = true;
+                    for (; st < s_end; ++st, ++it) {
+                        const uint32_t slot = it % STAGES2, phase = (it / STAGES2) & 1u;
+                        mbar_wait(full0 + 8 * slot, phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_lo = desc_lo(base + slot * STAGE2_BYTES), b_lo = a_lo + ((NDIG * PLANE_BYTES) >> 4);
+                        if (fresh) {
+#pragma unroll
+                            for (int c = 0; c < NDIG; c++) {
+                                mbar_wait(tempty0 + 8 * c, eph);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                if (lane == 0) {
+                                    umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 0>(
+                                        tmem_base + c * TILE, a_lo, b_lo + ((c * PLANE_B2) >> 4));
+#pragma unroll
+                                    for (int x = 1; x <= c; x++)
+                                        umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 1>(
+                                            tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
+                                            b_lo + (((c - x) * PLANE_B2) >> 4));
+                                }
+                            }
+                            fresh = false;
+                        } else if (lane == 0) {
+#pragma unroll
+                            for (int c = 0; c < NDIG; c++)
+#pragma unroll
+                                for (int x = 0; x <= c; x++)
+                                    umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 1>(
+                                        tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
+                                        b_lo + (((c - x) * PLANE_B2) >> 4));
+                        }
+                        if (lane == 0) {
+                            constexpr uint32_t offA = (KB * TILE) >> 4, offB = (KB * 64) >> 4;
+#pragma unroll
+                            for (int c = 0; c < NDIG; c++)
+#pragma unroll
+                                for (int x = 0; x <= c; x++)
+                                    umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 1>(
+                                        tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4) + offA,
+                                        b_lo + (((c - x) * PLANE_B2) >> 4) + offB);
+                        }
+                        if (lane == 0) umma_commit_2sm(empty0 + 8 * slot);
+                        __syncwarp();
+                    }
+                    if (lane == 0) umma_commit_2sm(tfull);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs): transposed tile, lanes = column samples =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int quarter = warp & 3;
+        const int half = (warp >> 2) - 1;     // row-tile samples [64 half, 64 half + 64) = TMEM columns
+        uint32_t grp_it = 0;
+        for (int t = pair; t < p.n_tiles; t += n_pairs) {
+            const PairTile tl = p.tiles[t];
+            double acc[64];
+#pragma unroll
+            for (int e = 0; e < 64; e++) acc[e] = 0.0;
+            for (int g = 0; g < p.n_groups; ++g, ++grp_it) {
+                double w = p.groups[g].w0;
+                mbar_wait(tfull, grp_it & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < NDIG; c++) {
+#pragma unroll
+                    for (int cb = 0; cb < 2; cb++) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64 + cb * 32, v);
+#pragma unroll
+                        for (int e = 0; e < 32; e++) acc[cb * 32 + e] = fma(i32_to_f64(v[e]), w, acc[cb * 32 + e]);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta0(tempty0 + 8 * c);
+                    w *= (1.0 / DIGIT);
+                }
+            }
+            const int tj = 2 * tl.b + (int)rank;
+            if (tj < tl.ti || tj >= p.tiles_per_dim) continue;   // the lower-triangle / out-of-range half of a pair
+            const int64_t gj = (int64_t)tj * TILE + quarter * 32 + lane, gi0 = (int64_t)tl.ti * TILE + half * 64;
+            const bool mirror = p.mirror != 0 && tl.ti != tj;
+            if (p.n_direct > 0 && gj < p.N) {
+                for (int32_t k = 0; k < p.n_direct; k++) {
+                    const double aj = p.SUB[p.sub.at(k, gj)];
+                    const double *bi = p.SUB + p.sub.at(k, gi0);
+#pragma unroll
+                    for (int e = 0; e < 64; e++) {
+                        const double d = bi[e] - aj;
+                        acc[e] = fma(-0.5 * d, d, acc[e]);
+                    }
+                }
+            }
+            if (gj < p.N) {
+                const double qj = p.q[gj];
+                double *dcol = p.D + ((int64_t)tl.out_row0 + half * 64) * p.ldd + gj;   // walks down the rows
+                double *mrow = p.D + gj * p.ldd + gi0;
+#pragma unroll
+                for (int e = 0; e < 64; e++) {
+                    const int64_t gi = gi0 + e;
+                    if (gi < p.N) {
+                        const double v = (gi == gj) ? 0.0 : (p.q[gi] + qj) - 2.0 * acc[e];
+                        dcol[(int64_t)e * p.ldd] = v;         // lanes = consecutive gj: one 256-byte store per warp
+                        if (mirror) mrow[e] = v;
+                    }
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();   // both CTAs are done with both tensor memories
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -548,7 +880,7 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_rows, const Lay &ws)
+static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_rows, const Lay &ws, uint32_t box_samples = TILE)
 {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) {
@@ -559,10 +891,11 @@ static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_ro
     const int64_t n_shards = ws.SS ? (N + ws.S - 1) / ws.S : 1;
     const cuuint64_t gdim[3] = {(cuuint64_t)ws.S, (cuuint64_t)n_rows, (cuuint64_t)n_shards};
     const cuuint64_t gstride[2] = {(cuuint64_t)ws.LD, (cuuint64_t)(ws.SS ? ws.SS : ws.LD * (int64_t)n_rows)};
-    const cuuint32_t box[3] = {TILE, KC, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {box_samples, KC, 1}, estr[3] = {1, 1, 1};   // 128-byte rows: SWIZZLE_128B, 64-byte: 64B
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)ptr, gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        box_samples == TILE ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld rows=%d S=%lld)", (int)r,
                   (long long)N, n_rows, (long long)ws.S);
@@ -590,7 +923,7 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         n_cols = tiles_per_dim * TILE;
         lay = Lay{ldp, 0, ldp};
     } else {
-        FUF_REQUIRE(shard % TILE == 0 && shard > 0 && shard_stride >= shard * (int64_t)n,
+        FUF_REQUIRE(shard % TILE == 0 && shard > 0 && shard_stride >= shard * (int64_t)n && shard_stride % 4 == 0,
                     "fuf_pairwise_gram: bad shard layout (shard=%lld stride=%lld)", (long long)shard,
                     (long long)shard_stride);
         n_cols = (N + shard - 1) / shard * shard;
@@ -775,17 +1108,59 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     p.n_direct = n_direct;
     p.SUB = SUB;
     p.sub = sub;
-    FUF_CUDA(cudaFuncSetAttribute(gram_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    const int grid = std::min<int64_t>(p.n_tiles, ctx->sm_count);
     if (!ctx->ev_gram[0]) {
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[0]));
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
     }
-    FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
-    gram_tile_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map0, map1, map2, map3, p);
-    FUF_CUDA(cudaGetLastError());
-    FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], stream));
-    ctx->gram_flops = 10.0 * 2.0 * TILE * TILE * (double)n_rows * (double)p.n_tiles;  // int8 multiply-adds x 2
+    const char *pair_env = getenv("FUF_GRAM_2CTA");
+    const bool use_pairs = pair_env ? atoi(pair_env) != 0 : false;
+    if (use_pairs) {
+        // CTA pairs: work item = row tile x two column tiles (2b, 2b+1); the half below the diagonal is computed and dropped
+        std::vector<PairTile> ptiles;
+        for (int32_t c = 0; c < n_trows; c++) {
+            const int32_t t = full ? c : tile_rows_h[c];
+            for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, full ? t * TILE : c * TILE, 0});
+        }
+        static_assert(KC == 2 * KB, "the issue loops are written for two 32-row MMA blocks per stage");
+        static_assert(sizeof(PairTile) == sizeof(Tile), "the pair tiles reuse the tile table's room");
+        FUF_REQUIRE(ptiles.size() <= tiles.size(), "fuf_pairwise_gram: pair-tile table larger than the tile table");
+        FUF_CUDA(cudaMemcpyAsync(d_tiles, ptiles.data(), ptiles.size() * sizeof(PairTile), cudaMemcpyHostToDevice, stream));
+        FUF_CUDA(cudaStreamSynchronize(stream));
+        CUtensorMap mb0, mb1, mb2, mb3;
+        if ((rc = make_map(&mb0, D0, N, n_rows, ws, 64)) || (rc = make_map(&mb1, D1, N, n_rows, ws, 64)) ||
+            (rc = make_map(&mb2, D2, N, n_rows, ws, 64)) || (rc = make_map(&mb3, D3, N, n_rows, ws, 64)))
+            return rc;
+        Params2 p2;
+        p2.tiles = (const PairTile *)d_tiles;
+        p2.groups = d_groups;
+        p2.n_tiles = (int32_t)ptiles.size();
+        p2.n_groups = p.n_groups;
+        p2.S = p.S;
+        p2.tiles_per_dim = (int32_t)tiles_per_dim;
+        p2.N = N;
+        p2.q = q;
+        p2.D = D;
+        p2.ldd = ldd;
+        p2.mirror = full;
+        p2.n_direct = n_direct;
+        p2.SUB = SUB;
+        p2.sub = sub;
+        FUF_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
+        const int n_pairs = (int)std::min<int64_t>(p2.n_tiles, ctx->sm_count / 2);
+        FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
+        gram_pair_kernel<<<2 * n_pairs, NTHREADS, SMEM2_BYTES, stream>>>(map0, map1, map2, map3, mb0, mb1, mb2, mb3, p2);
+        FUF_CUDA(cudaGetLastError());
+        FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], stream));
+        ctx->gram_flops = 10.0 * 2.0 * (2.0 * TILE) * TILE * (double)n_rows * (double)p2.n_tiles;
+    } else {
+        FUF_CUDA(cudaFuncSetAttribute(gram_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        const int grid = std::min<int64_t>(p.n_tiles, ctx->sm_count);
+        FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
+        gram_tile_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(map0, map1, map2, map3, p);
+        FUF_CUDA(cudaGetLastError());
+        FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], stream));
+        ctx->gram_flops = 10.0 * 2.0 * TILE * TILE * (double)n_rows * (double)p.n_tiles;  // int8 multiply-adds x 2
+    }
     ctx->gram_groups = p.n_groups;
     ctx->launches += 1;
     return FUF_OK;

@@ -54,8 +54,8 @@ if "host" in a.what:
     import time
     Xh = torch.empty((N, n), dtype=torch.float64, pin_memory=True); Xh.copy_(X); Xn = Xh.numpy()
     Dp = torch.zeros((N, N), dtype=torch.float64, pin_memory=True); Dn = Dp.numpy()
-    for zc in ("", "1"):
-        for bands in ("1", "6", "10", "16"):
+    for zc in ("",) if os.environ.get("KB_BANDS") else ("", "1"):
+        for bands in (os.environ["KB_BANDS"].split(",") if os.environ.get("KB_BANDS") else ("1", "6", "10", "16")):
             os.environ["FUF_HOST_BANDS"] = bands
             if zc: os.environ["FUF_ZEROCOPY"] = "1"
             else: os.environ.pop("FUF_ZEROCOPY", None)
