@@ -45,6 +45,7 @@
 // Tensor-pipe accounting: executed int8 MACs = 10 x 128 x 128 x (padded n) per tile; algorithmic flops = 2 n per pair.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -210,6 +211,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 64 consecutive TMEM columns of this warp's lane quarter in one go (two x32 loads in flight, one wait): the
+// accumulator can be handed back to the MMA warp as soon as its raw int32 values sit in registers.
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr), "r"(taddr + 32)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                  const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3, const Params p)
@@ -355,16 +380,13 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int c = 0; c < NDIG; c++) {
-#pragma unroll
-                    for (int cb = 0; cb < 2; cb++) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64 + cb * 32, v);
-#pragma unroll
-                        for (int e = 0; e < 32; e++) acc[cb * 32 + e] = fma(i32_to_f64(v[e]), w, acc[cb * 32 + e]);
-                    }
+                    uint32_t v[64];
+                    tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64, v);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty0 + 8 * c);  // accumulator c may be overwritten
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * c);  // accumulator c may be overwritten: the raw values
+#pragma unroll                                                    // are in registers, the arithmetic comes after
+                    for (int e = 0; e < 64; e++) acc[e] = fma(i32_to_f64(v[e]), w, acc[e]);
                     w *= (1.0 / DIGIT);
                 }
             }
@@ -635,16 +657,13 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int c = 0; c < NDIG; c++) {
-#pragma unroll
-                    for (int cb = 0; cb < 2; cb++) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64 + cb * 32, v);
-#pragma unroll
-                        for (int e = 0; e < 32; e++) acc[cb * 32 + e] = fma(i32_to_f64(v[e]), w, acc[cb * 32 + e]);
-                    }
+                    uint32_t v[64];
+                    tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + c * TILE + half * 64, v);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cta0(tempty0 + 8 * c);
+#pragma unroll
+                    for (int e = 0; e < 64; e++) acc[e] = fma(i32_to_f64(v[e]), w, acc[e]);
                     w *= (1.0 / DIGIT);
                 }
             }
@@ -999,6 +1018,37 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         for (size_t i = 0; i < keyed.size(); i++) (bypass[i] ? direct_keyed : rest).push_back(keyed[i]);
         keyed.swap(rest);
     }
+    // Small buckets are expensive: every bucket ends with a drain of the four accumulators during which the tensor
+    // pipe idles (~3 us, the time of 250 rows of MMAs), and a bucket is padded to whole 64-row stages.  A bucket with
+    // fewer than 1,024 columns therefore joins the next LARGER scale (coarser digits for its columns, still covered by
+    // the h2 bound, which is computed from the scale a column is actually quantised with) whenever that raises
+    // sum_s h2_s by less than 1 % — in practice the tail of tiny-scale columns (zero-length edges), never the few
+    // large upper-level columns.  `keyed` is sorted by decreasing exponent.
+    if (!getenv("FUF_GRAM_NO_MERGE")) {
+        double total_h = 0.0;
+        for (const auto &kv : keyed) total_h += std::ldexp(1.0, 2 * kv.first) * (double)nnz[kv.second];
+        const double allowance = 0.01 * total_h;
+        double spent = 0.0;
+        size_t end = keyed.size();
+        while (end > 0) {
+            size_t begin = end;
+            const int32_t e = keyed[end - 1].first;
+            while (begin > 0 && keyed[begin - 1].first == e) begin--;
+            if (begin == 0) break;                                  // the largest scale has nowhere to go
+            const int32_t e_up = keyed[begin - 1].first;            // next larger exponent present
+            if (end - begin < 1024) {
+                double cost = 0.0;
+                for (size_t i = begin; i < end; i++)
+                    cost += (std::ldexp(1.0, 2 * e_up) - std::ldexp(1.0, 2 * e)) * (double)nnz[keyed[i].second];
+                if (spent + cost <= allowance) {
+                    spent += cost;
+                    for (size_t i = begin; i < end; i++) keyed[i].first = e_up;   // stays sorted: joins the bucket above
+                    continue;                                       // re-examine the enlarged bucket [.., end)
+                }
+            }
+            end = begin;
+        }
+    }
     const int32_t n_direct = (int32_t)direct_keyed.size();
     const int32_t n_direct_pad = std::max(16, (n_direct + 15) / 16 * 16);
     std::vector<int32_t> direct_nodes(n_direct_pad, -1);
@@ -1022,6 +1072,14 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         }
         groups.push_back(Group{(int32_t)(row_map.size() / KC), 0, S * S / (DIGIT0 * DIGIT0)});
         i = j;
+    }
+    if (getenv("FUF_GRAM_DEBUG")) {
+        int32_t prev = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            fprintf(stderr, "gram bucket %zu: %d rows (w0 %.3g)\n", g, (groups[g].stage_end - prev) * KC, groups[g].w0);
+            prev = groups[g].stage_end;
+        }
+        fprintf(stderr, "gram: %d float64 columns\n", n_direct);
     }
     if (groups.empty()) {  // every profile is identically zero: one all-zero stage
         row_map.assign(KC, -1);
