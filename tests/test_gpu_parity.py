@@ -780,3 +780,84 @@ def test_cli_under_torchrun_two_gpus(l2, tmp_path):
     assert rel_err(D2, oracle_c.pairwise(P, l2)) < REL
     bn = constant.FUNUNIFRAC_OUT__MAIN_BASIS__FILE_NAME.format("x")
     assert open(tmp_path / "one" / bn).read() == open(tmp_path / "two" / bn).read()
+
+
+# ------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes (configs 3 and 4) through size-independent properties
+# ------------------------------------------------------------------------------------------------------
+def _full_size_profiles(leaves, n, N, seed):
+    """Uniform abundances on a random 20 % of the leaves, normalised, generated on the device (bench.py's generator)."""
+    import bench
+    return bench.device_profiles(leaves, n, N, seed=seed)
+
+
+def test_full_size_config3_l1_10k(full_tree):
+    """10,000 samples x 30,002 nodes, weighted L1 (the headline workload): structure of the whole matrix, planted
+    identical / near-duplicate samples, and a random 320-sample block against the oracle."""
+    inp, ctx, leaves = full_tree
+    N = 10000
+    X = _full_size_profiles(leaves, ctx.n, N, seed=31)
+    X[7777] = X[12]                                                   # identical pair, far apart
+    X[4242] = X[13] * (1 + 1e-7 * torch.rand(ctx.n, device="cuda", dtype=torch.float64))   # near-duplicate: must be refined
+    job = ctx.push_up_job(X, engine.MODE_L1)
+    D = ctx.distances(job, engine.MODE_L1)
+    assert ctx.refine_count() >= 2
+    assert torch.equal(D, D.T) and not bool(torch.diagonal(D).any()) and bool(torch.isfinite(D).all())
+    assert float(D[12, 7777]) == 0.0
+    off = D + torch.eye(N, device="cuda", dtype=torch.float64)
+    off[12, 7777] = off[7777, 12] = 1.0
+    assert float(off.min()) > 0.0                                     # every other pair is strictly apart
+    # mass conservation: the root entry of every pushed profile is its total mass (1 up to rounding)
+    assert torch.allclose(job.P64T[-1, :N], X.sum(1), rtol=1e-14)
+    rng = np.random.default_rng(2)
+    sub = np.sort(np.concatenate([rng.choice(N, 316, replace=False), [12, 13, 4242, 7777]]))
+    sub = np.unique(sub)
+    Pref = oracle_c.push_up(inp.parent, inp.edge_length, X[torch.from_numpy(sub).cuda()].cpu().numpy(), False)
+    Dref = oracle_c.pairwise(Pref, False)
+    got = D[torch.from_numpy(sub).cuda()][:, torch.from_numpy(sub).cuda()].cpu().numpy()
+    i12, i7777 = int(np.searchsorted(sub, 12)), int(np.searchsorted(sub, 7777))
+    scale = np.full_like(Dref, 1e-300)
+    scale[i12, i7777] = scale[i7777, i12] = 1.0                       # the identical pair: 0 against the oracle's 0
+    assert rel_err(got, Dref, scale) < REL                            # includes the near-duplicate pair (13, 4242)
+    # triangle inequality on random triples of the full matrix
+    i, j, k = (torch.from_numpy(rng.integers(0, N, 200000)).cuda() for _ in range(3))
+    assert bool((D[i, k] <= D[i, j] + D[j, k] + 1e-9).all())
+
+
+def test_full_size_config4_l2_50k(full_tree):
+    """50,000 samples, --L2 on the tensor cores: every one of the 1.25e9 distances enters a row-sum identity that
+    float64 can evaluate in O(N n):  sum_j ||a_i - a_j||^2 = N q_i + sum_j q_j - 2 a_i . (sum_j a_j)."""
+    inp, ctx, leaves = full_tree
+    N = 50000
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90 * (1 << 30):
+        pytest.skip("needs ~80 GB of free device memory")
+    X = _full_size_profiles(leaves, ctx.n, N, seed=32)
+    X[31000] = X[5]
+    job = ctx.push_up_job(X, engine.MODE_L2)
+    del X
+    D = ctx.distances(job, engine.MODE_L2)
+    assert float(D[5, 31000]) == 0.0 and float(D[31000, 5]) == 0.0
+    assert not bool(torch.diagonal(D).any())
+    rows = D.sum(1)
+    A = job.P64T[:, :N]
+    q = (A * A).sum(0)
+    s = A.sum(1)
+    want = N * q + q.sum() - 2.0 * (s @ A)
+    assert float(((rows - want).abs() / want).max()) < 1e-7
+    cols = D.sum(0)
+    assert torch.equal(rows, cols) or float(((rows - cols).abs() / rows).max()) < 1e-14     # symmetric (sum order)
+    # a block against the oracle, rows and columns far apart in the matrix
+    rng = np.random.default_rng(3)
+    sub = np.unique(np.concatenate([rng.choice(N, 256, replace=False), [5, 31000]]))
+    idx = torch.from_numpy(sub).cuda()
+    P = A[:, idx].T.contiguous().cpu().numpy()                        # float64 pushed profiles (bit-exact vs the oracle's)
+    Dref = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    got = D[idx][:, idx].cpu().numpy()
+    i5, i31 = int(np.searchsorted(sub, 5)), int(np.searchsorted(sub, 31000))
+    scale = np.full_like(Dref, 1e-300)
+    scale[i5, i31] = scale[i31, i5] = 1.0
+    assert rel_err(got, Dref, scale) < REL
+    del D, job, A
+    torch.cuda.empty_cache()
