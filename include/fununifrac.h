@@ -20,11 +20,14 @@
  *   fuf_pairwise_f64     <- same, float64 validation mode
  *   fuf_refine           <- get_L1 / get_L2 in float64 for the pairs    src/objects/profile_vector.py:9-19
  *                           the fp32 operands cannot certify to 1e-6
- *   fuf_assemble         <- dists[i,j] = dists[j,i] = Z                 src/algorithms/emd_unifrac.py:51-54
- *   fuf_store_tile_rows_host <- same, into the host matrix np.save writes src/compute_all_pairwise_fununifrac.py:88-89
+ *   fuf_assemble, fuf_pack_tile_rows, fuf_assemble_packed
+ *                        <- dists[i,j] = dists[j,i] = Z                 src/algorithms/emd_unifrac.py:51-54
  *                           (joins row-block shards computed on several GPUs)
+ *   fuf_store_tile_rows_host <- same, into the host matrix np.save writes src/compute_all_pairwise_fununifrac.py:88-89
  *   fuf_diffab_block     <- get_L1_diffab / get_L2_diffab per pair in   src/objects/profile_vector.py:13-23
  *                           itertools.combinations order                src/algorithms/emd_unifrac.py:49,56-67
+ *   fuf_diffab_gather    <- diffabs[np.ix_(files1, files2, nodes)] of   src/utility/differential_abundance.py:18-55
+ *                           DiffabArrayIndexer, from the pushed matrix
  *   fuf_all_pairs_host   <- the compute section of the driver           src/compute_all_pairwise_fununifrac.py:64-73
  *                           (host float64 profiles in, host float64 distance matrix out)
  *
