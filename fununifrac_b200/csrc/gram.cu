@@ -45,6 +45,8 @@
 // Tensor-pipe accounting: executed int8 MACs = 10 x 128 x 128 x (padded n) per tile; algorithmic flops = 2 n per pair.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 
@@ -968,6 +970,7 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     std::vector<float> cstat(3 * (size_t)n);
     FUF_CUDA(cudaMemcpyAsync(cstat.data(), d_cmax, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
     FUF_CUDA(cudaStreamSynchronize(stream));
+    const auto t_plan0 = std::chrono::steady_clock::now();
     const float *cmax = cstat.data(), *nnz = cmax + n, *energy = nnz + n;
     std::vector<std::pair<int32_t, int32_t>> keyed, direct_keyed;  // (bucket exponent, node), all-zero columns dropped
     keyed.reserve(n);
@@ -979,9 +982,19 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
             keyed.emplace_back(e, k);
         }
     }
-    std::sort(keyed.begin(), keyed.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) {
-        return a.first > b.first || (a.first == b.first && a.second < b.second);
-    });
+    {   // order: decreasing exponent, then node index — a counting sort (float exponents span < 300 values, the nodes
+        // arrive in increasing order); this runs on the host while the GPU waits for the plan
+        int32_t e_min = INT32_MAX, e_max = INT32_MIN;
+        for (const auto &kv : keyed) e_min = std::min(e_min, kv.first), e_max = std::max(e_max, kv.first);
+        if (!keyed.empty()) {
+            std::vector<size_t> start((size_t)(e_max - e_min) + 2, 0);
+            for (const auto &kv : keyed) start[(size_t)(e_max - kv.first) + 1]++;
+            for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+            std::vector<std::pair<int32_t, int32_t>> sorted(keyed.size());
+            for (const auto &kv : keyed) sorted[start[(size_t)(e_max - kv.first)]++] = kv;
+            keyed.swap(sorted);
+        }
+    }
     // Bypass.  What the dropped product orders can cost a pair is bounded by 1.44e-9 (h2_i + h2_j), h2_s = sum of S_k^2
     // over the sample's non-zero Gram columns; the refinement flags pairs with D < 2.9e-3 (h2_i + h2_j).  To keep
     // ordinary pairs (D ~ q_i + q_j) a factor ~10 clear of that line, the columns contributing most to sum_s h2_s
@@ -998,9 +1011,13 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
             sum_h += h;
             sum_e += (double)energy[k];
         }
-        std::sort(contrib.begin(), contrib.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &b) {
-            return a.first > b.first || (a.first == b.first && a.second < b.second);
-        });
+        // only the largest GRAM_DIRECT_ROWS (or the test hook's count) contributions can be selected
+        const size_t top = std::min<size_t>(contrib.size(), (size_t)std::max(GRAM_DIRECT_ROWS,
+                                                getenv("FUF_GRAM_DIRECT") ? atoi(getenv("FUF_GRAM_DIRECT")) : 0));
+        std::partial_sort(contrib.begin(), contrib.begin() + top, contrib.end(),
+                          [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &b) {
+                              return a.first > b.first || (a.first == b.first && a.second < b.second);
+                          });
         int32_t max_direct = GRAM_DIRECT_ROWS;
         if (getenv("FUF_GRAM_DIRECT")) max_direct = std::max(0, atoi(getenv("FUF_GRAM_DIRECT")));
         std::vector<uint8_t> bypass(keyed.size(), 0);
@@ -1131,6 +1148,9 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     FUF_CUDA(cudaMemcpyAsync(d_groups, groups.data(), groups.size() * sizeof(Group), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, stream));
     FUF_CUDA(cudaStreamSynchronize(stream));  // the host vectors are pageable and die with this call
+    if (getenv("FUF_GRAM_DEBUG"))
+        fprintf(stderr, "gram: host planning + table upload %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count());
     const Lay sub = shard == 0 ? Lay{n_cols, 0, n_cols} : Lay{shard, (int64_t)n_direct_pad * shard, shard};
     {
         dim3 g((unsigned)((n_cols / 4 + 127) / 128), (unsigned)n_parts);
