@@ -237,3 +237,15 @@ extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)
     *refined = (int64_t)v;
     return FUF_OK;
 }
+
+extern "C" int fuf_refine_count_device(fuf_ctx *ctx, int64_t *count_dev, void *stream)
+{
+    FUF_REQUIRE(ctx && count_dev, "fuf_refine_count_device: null argument");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->d_refined) {
+        FUF_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int64_t), (cudaStream_t)stream));
+        return FUF_OK;
+    }
+    FUF_CUDA(cudaMemcpyAsync(count_dev, ctx->d_refined, sizeof(int64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FUF_OK;
+}

@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 8
+ABI_VERSION = 9
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -70,6 +70,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_gram_last_kernel.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
         L.fuf_gram_last_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
+        L.fuf_refine_count_device.argtypes = [vp, vp, vp]
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
@@ -90,7 +91,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_launch_count.argtypes = [vp]
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
-                     "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count",
+                     "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count", "fuf_refine_count_device",
                      "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_name_index_create",
                      "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
@@ -328,6 +329,14 @@ class TreeContext:
         v = ctypes.c_int64()
         _check(self._lib.fuf_refine_count(self.handle, ctypes.byref(v), _stream_ptr(torch)), "fuf_refine_count")
         return int(v.value)
+
+    def refine_count_into(self, out):
+        """The same count written into ``out`` (device int64 tensor, one element), stream-ordered, no host sync."""
+        torch = _torch()
+        assert out.dtype == torch.int64 and out.numel() >= 1 and out.is_cuda
+        _check(self._lib.fuf_refine_count_device(self.handle, out.data_ptr(), _stream_ptr(torch)),
+               "fuf_refine_count_device")
+        return out
 
     def push_up_f64(self, X, mode: int, P64T=None, col0: int = 0):
         """Validation path: X float64 [N, ldx] → P64T float64 [n, ldp], reference operation order."""

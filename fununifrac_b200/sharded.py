@@ -94,6 +94,7 @@ class ShardedAllPairs:
         self.blocks = self.gathered = None
         self.last_flagged = 0
         self._x_stage = None
+        self._pending = None
         if world > 1:
             self.flagged = ops.empty((1,), "int64")
             self.blocks = ops.empty((self.max_rows * TILE, N), "float64")
@@ -126,7 +127,7 @@ class ShardedAllPairs:
             ops.push_up_center(X_local, mode, self.center)
         if self.world > 1:
             self.dist.broadcast(self.center, src=0)
-        mark("push_begin")
+        mark("push_begin")      # (after the centre: its kernels and the broadcast)
         if self.hi > self.lo:
             ops.push_up(X_local, mode, self.PS[r], 0, self.center, self.P64S[r] if self.do_refine else None,
                         self.stat[r * sh:(r + 1) * sh])
@@ -143,16 +144,35 @@ class ShardedAllPairs:
         mark("pair_begin")
         stat, lin = self._pairwise(self.rows, self.blocks) if self.rows else (None, None)
         mark("pair_end")
+        self._pending = None
         if self.do_refine:
-            # the float64 profiles (2x the fp32 volume) cross NVLink only if some rank has a pair to refine
-            mine = ops.count_uncertified(N, mode, stat, self.blocks, self.rows, lin) if self.rows else 0
-            self.flagged[0] = mine
+            # The float64 profiles (2x the fp32 volume) cross NVLink only if some rank has a pair to refine.  The count
+            # stays on the device: it is all-reduced in stream order and the caller goes on queueing the collection of
+            # the results; the host looks at the count afterwards (_refine_if_flagged) and, in the rare case, refines
+            # and collects again.
+            if self.rows:
+                ops.count_uncertified_into(N, mode, stat, self.blocks, self.rows, lin, self.flagged)
+            else:
+                self.flagged.zero_()
             self.dist.all_reduce(self.flagged)
-            self.last_flagged = int(self.flagged.item())
-            if self.last_flagged > 0:
-                self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
-                if self.rows:
-                    ops.refine(self.P64S, N, mode, stat, self.blocks, self.rows, sh, stride, lin)
+            self._pending = (stat, lin)
+        mark("refine_end")
+
+    def _refine_if_flagged(self) -> bool:
+        """Second half of the refinement decision (one host synchronisation).  True: rows were refined, collect again."""
+        self.last_flagged = 0
+        if self._pending is None:
+            return False
+        stat, lin = self._pending
+        self._pending = None
+        self.last_flagged = int(self.flagged.item())
+        if self.last_flagged == 0:
+            return False
+        ops, r, sh = self.ops, self.rank, self.shard
+        self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
+        if self.rows:
+            ops.refine(self.P64S, self.N, self.mode, stat, self.blocks, self.rows, sh, ops.n * sh, lin)
+        return True
 
     def step(self, X_local, mark=None):
         """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
@@ -166,11 +186,16 @@ class ShardedAllPairs:
                 if r == 0:
                     self.D = self.ops.empty((self.N, self.N), "float64")
                     self.gathered = self.ops.empty((self.world, self.max_packed), "float64")
-            if self.rows:
-                self.ops.pack_tile_rows(self.blocks, self.rows, self.offs, self.N, self.packed)
-            self.dist.gather(self.packed, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
-            if r == 0:
-                self.ops.assemble_packed(self.gathered, self.slot_rows, self.slot_offs, self.N, self.D)
+            for attempt in range(2):
+                if self.rows:
+                    self.ops.pack_tile_rows(self.blocks, self.rows, self.offs, self.N, self.packed)
+                self.dist.gather(self.packed, [self.gathered[q] for q in range(self.world)] if r == 0 else None, dst=0)
+                if attempt == 0:
+                    mark("gather_end")
+                if r == 0:
+                    self.ops.assemble_packed(self.gathered, self.slot_rows, self.slot_offs, self.N, self.D)
+                if attempt == 1 or not self._refine_if_flagged():
+                    break
         mark("end")
         return self.D
 
@@ -188,8 +213,12 @@ class ShardedAllPairs:
         self._compute(X, mark)
         if self.world == 1:
             self.ops.copy_to_host(self.D, D_host.array)
-        elif self.rows:
-            self.ops.store_tile_rows_host(self.blocks, self.rows, self.N, D_host.array)
+        else:
+            for attempt in range(2):
+                if self.rows:
+                    self.ops.store_tile_rows_host(self.blocks, self.rows, self.N, D_host.array)
+                if attempt == 1 or not self._refine_if_flagged():
+                    break
         self.ops.synchronize()
         if self.world > 1:
             self.dist.barrier()
@@ -307,9 +336,9 @@ class CudaOps:
         return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride,
                                lin_stat=lin_stat, lin_kappa=2.9e-3)
 
-    def count_uncertified(self, N, mode, err_stat, D, tile_rows, lin_stat=None):
+    def count_uncertified_into(self, N, mode, err_stat, D, tile_rows, lin_stat, out):
         self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, lin_stat=lin_stat, lin_kappa=2.9e-3)
-        return self.ctx.refine_count()
+        self.ctx.refine_count_into(out)
 
     def assemble(self, blocks, rows, N, D):
         return self.ctx.assemble(blocks, rows, N, D=D)

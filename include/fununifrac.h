@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 8
+#define FUF_ABI_VERSION 9
 
 /* error codes */
 #define FUF_OK 0
@@ -213,6 +213,9 @@ int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64
                const double *err_stat, double kappa, int criterion, const int32_t *tile_rows_h, int32_t n_tile_rows,
                double *D, int64_t ldd, const double *lin_stat, double lin_kappa, int64_t max_pairs, void *stream);
 int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream);
+/* The same count left on the DEVICE (count_dev: device int64), stream-ordered and without a host synchronisation: several
+ * GPUs can all-reduce it and go on queueing work while the host has not looked at it yet. */
+int fuf_refine_count_device(fuf_ctx *ctx, int64_t *count_dev, void *stream);
 
 /* Join compact row blocks (as written by fuf_pairwise with tile_rows_h, possibly gathered from several
  * devices and concatenated: blocks[c] for c in [0, n_blocks)) into the full symmetric N x N matrix.

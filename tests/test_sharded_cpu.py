@@ -85,9 +85,9 @@ class OracleOps:
             D[c * TILE + lower[0], r0 + lower[1]] = float("nan")
         return D
 
-    def count_uncertified(self, N, mode, err_stat, D, tile_rows, lin_stat=None):
+    def count_uncertified_into(self, N, mode, err_stat, D, tile_rows, lin_stat, out):
         assert err_stat.numel() >= N
-        return 1 if 0 in tile_rows else 0          # pretend the rank that owns tile row 0 found one pair
+        out[0] = 1 if 0 in tile_rows else 0        # pretend the rank that owns tile row 0 found one pair
 
     def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, lin_stat=None):
         self.refine_calls += 1
