@@ -21,26 +21,32 @@
 //     accumulation is EXACT and needs no periodic flush; the dropped orders are below 3 x 254^-4 = 7e-10 of S^2.
 //   * per bucket, the epilogue adds S^2 (c0 + c1/254 + c2/254^2 + c3/254^3) / 127^2 into float64 accumulators in
 //     registers.
-// q_i is the same truncated digit form evaluated on (i, i) with the same operations in the same order
-// (gram_selfnorm_kernel), so D[i,j] = B(delta, delta) for the digit difference delta of the two samples: identical
-// samples give exactly 0, nothing cancels, and |D - exact squared distance of the quantised profiles| is at most
-// 2.9e-9 S^2 per column in which the two samples differ.  What is left is the quantisation of the inputs, which is
-// the same kind of error as rounding them to fp32 and is covered by the same refinement criterion (refine.cu) through
-// the per-sample statistic sum_k (a - a_quantised)^2 this file emits.
+// q_i is the same truncated digit form evaluated on (i, i) with the same operations in the same order (integer
+// self-products from gram_digits_kernel, combined in gram_stat_kernel), so D[i,j] = B(delta, delta) for the digit
+// difference delta of the two samples: identical samples give exactly 0, nothing cancels, and
+// |D - exact squared distance of the quantised profiles| is at most 2.9e-9 S^2 per column in which the two samples
+// differ.  What is left is the quantisation of the inputs, which is the same kind of error as rounding them to fp32 and
+// is covered by the same refinement criterion (refine.cu) through the per-sample statistic sum_k (a - a_quantised)^2
+// this file emits.
 //
-// K3c gram_colmax_kernel  largest |entry| of every node column (one warp per row).
-// K3p gram_digits_kernel  fp32 operand -> four int8 digit planes in permuted row order; the quantisation and scale
-//                         statistics in double.  HBM-bound, one pass.
-// K3q gram_selfnorm_kernel  q_i = the Gram form of sample i with itself, from the digit planes, bucket by bucket.
+// K3c gram_colmax_kernel  largest |entry|, non-zero count and energy of every node column (one warp per row, 16-byte
+//                         loads).  The host turns them into the plan: scale buckets (tiny ones merged into the next
+//                         larger scale under an h2 budget), the columns kept in float64, the permuted row map.
+// K3p gram_digits_kernel  fp32 operand -> four int8 digit planes in permuted row order, four samples per thread; the
+//                         quantisation / scale statistics and the integer self-products of every sample in the same
+//                         pass.  HBM-bound.
+// K3s gram_stat_kernel    per sample: error statistic, h2, and q_i with the epilogue's own floating-point operations.
 // K3  gram_tile_kernel    persistent, warp-specialised, one CTA per SM, 128x128 tiles of the upper triangle:
 //       warp 0   TMA producer: per stage (64 basis rows) 8 boxes of 128 samples x 64 rows (A and B, four digit
 //                planes each; 1 byte per entry, SWIZZLE_128B), 3-stage 64 KB ring, full/empty mbarriers;
-//       warp 1   MMA issuer: one elected lane, M = N = 128, K = 32, MN-major descriptors, ten MMAs per 32 rows;
-//                tcgen05.commit frees smem stages and, at the end of a bucket, publishes the accumulators;
-//       warps 4-11 (two warpgroups, setmaxnreg 232) epilogue: tcgen05.ld of the four int32 accumulators, weighted
-//                into 64 float64 registers per thread; each accumulator is released as soon as it has been read, so
-//                the next bucket's MMAs stall only until the first one is drained.
+//       warp 1   MMA issuer: one lane, M = N = 128, K = 32, MN-major descriptors, ten MMAs per 32 rows, ~6 instructions
+//                per MMA (descriptor low words = stage base + constant); tcgen05.commit frees smem stages and, at the
+//                end of a bucket, publishes the accumulators;
+//       warps 4-11 (two warpgroups, setmaxnreg 232) epilogue: tcgen05.ld of the four int32 accumulators; each one is
+//                handed back to the MMA warp as soon as its raw values are in registers, then weighted into 64 float64
+//                registers per thread (int32 -> double without I2F); the float64 bypass columns are added here too.
 //       With the full matrix as output the epilogue also stores the transposed tile (no separate mirror pass).
+// K3x2 gram_pair_kernel   the same on CTA pairs (cta_group::2), opt-in (FUF_GRAM_2CTA=1): see its own comment.
 //
 // Tensor-pipe accounting: executed int8 MACs = 10 x 128 x 128 x (padded n) per tile; algorithmic flops = 2 n per pair.
 #include <algorithm>
@@ -139,29 +145,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), MN-major 8-bit operand, SWIZZLE_128B: a row of the
-// plane is 128 samples = 128 bytes = the whole M (or N) extent; 8 basis rows form a 1 KB swizzle atom.
-//   [0,14) start >> 4 | [16,30) LBO >> 4 (between 128-sample blocks: unused, M = 128) | [32,46) SBO >> 4 (between
-//   8-row atoms = 1 KB) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(PLANE_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
-}
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), MN-major 8-bit operands.  SWIZZLE_128B: a row of the
+// plane is 128 samples = 128 bytes = the whole M (or N) extent, 8 basis rows form a 1 KB swizzle atom; SWIZZLE_64B (the
+// N-halves of the CTA-pair kernel): 64-byte rows, 512-byte atoms.
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (between blocks along M/N: unused, one block) | [32,46) SBO >> 4 (between
+//   8-row atoms) | [46,48) version = 1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+// The low word is `desc_lo(address)`, the high word one of the DESC_HI_* constants below.
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c = S32 (2), a = b = signed INT8 (1), both MN-major,
 // N = 128, M = 128.
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TILE >> 3) << 17) |
                            ((uint32_t)(TILE >> 4) << 24);
 
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
-        : "memory");
-}
 // The issuing thread is the bottleneck of this kernel if it spends more than the ~68 cycles an MMA takes on building
 // its operands: the descriptors of one stage differ only in the 14-bit start-address field, so the low words are
 // `stage base + constant` (one add each) and the high word (SBO, version, layout) is a constant.
@@ -198,21 +192,6 @@ __device__ __forceinline__ double i32_to_f64(uint32_t v)
 {
     return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // 64 consecutive TMEM columns of this warp's lane quarter in one go (two x32 loads in flight, one wait): the
 // accumulator can be handed back to the MMA warp as soon as its raw int32 values sit in registers.
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64])
@@ -494,23 +473,8 @@ __device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
 }
-// half of B: 64 samples = 64-byte rows, SWIZZLE_64B (layout type 4), 8-row atoms of 512 bytes
-__device__ __forceinline__ uint64_t umma_desc_b64(uint32_t smem_addr)
-{
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(PLANE_B2 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
-           (1ull << 46) | (4ull << 61);
-}
 constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TILE >> 3) << 17) |
                             ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair, N = 128
-__device__ __forceinline__ void umma_i8_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC2), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
