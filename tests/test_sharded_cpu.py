@@ -196,7 +196,7 @@ def _worker(rank, world, port, N, l2, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,N,l2", [(2, 300, False), (3, 700, False), (2, 129, True)])
+@pytest.mark.parametrize("world,N,l2", [(2, 300, False), (3, 700, False), (2, 129, True), (3, 100, False)])
 def test_sharded_exchange_gloo(world, N, l2, tmp_path, monkeypatch):
     if world == 3:      # once through the named shared-memory file instead of /proc/<pid>/fd
         monkeypatch.setenv("FUF_SHARED_NO_PROCFD", "1")
