@@ -72,67 +72,75 @@ def _all_pairs_multi_gpu(fun_files, input, abundance_key, unweighted, num_thread
             dist.destroy_process_group()
 
 
+def _sample_files(args):
+    """Validation of the inputs (reference :37-46: unknown BRITE id -> ValueError, missing edge list or no matching sample
+    file -> Exception) and the sample order: sorted glob, which is the row / column order of the output matrix."""
+    if args.brite not in kegg_db.instance.brites:
+        raise ValueError(f"{args.brite} is not a valid BRITE ID. Choices are: {kegg_db.instance.brites}")
+    data.check_data_abspath(args.edge_list)
+    pattern = os.path.join(args.file_dir, args.file_pattern)
+    data.check_data_abspaths(pattern)
+    return sorted(glob.glob(pattern))
+
+
+def _write_outputs(args, input: FuncTreeEmduInput, fun_files, dists, diffabs_sparse, Ps_pushed):
+    """The files of reference :76-108, same names (utility/constant.py) and contents."""
+    run_id = args.out_id if args.out_id else datetime.datetime.now().strftime('%Y%m%d-%H%M%S')
+    target = Path(args.out_dir)
+    target.mkdir(parents=True, exist_ok=True)
+
+    matrix_path = target / constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format(run_id)
+    np.save(matrix_path, dists)
+    (target / constant.FUNUNIFRAC_OUT__MAIN_BASIS__FILE_NAME.format(run_id)).write_text(
+        "".join(f"{sample}\n" for sample in fun_files))
+    logging.info("distance matrix (%d x %d) written to %s", len(fun_files), len(fun_files), matrix_path)
+    if diffabs_sparse is not None:
+        diffab_path = str(target / constant.FUNUNIFRAC_OUT__DIFFAB_FILE_NAME.format(run_id))
+        sparse_npz.save_npz(diffab_path, diffabs_sparse)
+        (target / constant.FUNUNIFRAC_OUT__DIFFAB_NODES_FILE_NAME.format(run_id)).write_text(
+            "".join(f"{input.idx_to_node[node]}\n" for node in input.basis))
+        logging.info("difference vectors (%d non-zero entries) written to %s.npz", diffabs_sparse.nnz, diffab_path)
+    if Ps_pushed is not None:
+        pushed_path = target / constant.FUNUNIFRAC_OUT__PUSH_FILE_NAME.format(run_id)
+        with open(pushed_path, 'wb') as f:
+            pickle.dump(Ps_pushed, f)
+        logging.info("pushed profiles written to %s", pushed_path)
+
+
 def main(args):
     logging.basicConfig(level=args.loglevel, format='%(asctime)s %(levelname)s: %(message)s')
-    edge_list_file = args.edge_list
-    out_dir = args.out_dir
-    out_id = args.out_id
-    file_dir = args.file_dir
-    file_pattern = args.file_pattern
-    abundance_key = args.abundance_key
-    num_threads = args.threads
-    brite = args.brite
-    make_diffab = args.diffab
-    unweighted = args.unweighted
-    is_L2 = args.L2
-    save_Ppushed = args.Ppushed
+    make_diffab, is_L2, save_Ppushed = args.diffab, args.L2, args.Ppushed
     validate = bool(getattr(args, "validate", False))
-    ##############################################################################
-    # Validations (reference :37-46)
-    ##############################################################################
-    if brite not in kegg_db.instance.brites:
-        raise ValueError(f"{brite} is not a valid BRITE ID. Choices are: {kegg_db.instance.brites}")
-    data.check_data_abspath(edge_list_file)
-    file_pattern = os.path.join(file_dir, file_pattern)
-    data.check_data_abspaths(file_pattern)
-    fun_files = glob.glob(file_pattern)
-    fun_files = sorted(fun_files)  # this order is the basis of the output matrix
-    logging.info(f"Parsing graph")
-    ##############################################################################
-    # Main objects
-    ##############################################################################
-    solver = EarthMoverDistanceUniFracSolver(validate=validate)
-    tree = make_tree.import_graph(edge_list_file, directed=True)
-    logging.info(f"Converting graph into EMDUniFrac format")
-    input: FuncTreeEmduInput = make_emd_input.tree_to_EMDU_input(tree, brite)
-    logging.info(f"Computing pairwise distances in parallel")
-    ##############################################################################
-    # Computations
-    ##############################################################################
     python_ingest = bool(getattr(args, "python_ingest", False))
+    fun_files = _sample_files(args)
+
+    logging.info("reading the tree %s", args.edge_list)
+    solver = EarthMoverDistanceUniFracSolver(validate=validate)
+    tree = make_tree.import_graph(args.edge_list, directed=True)
+    input: FuncTreeEmduInput = make_emd_input.tree_to_EMDU_input(tree, args.brite)
+    logging.info("%d tree nodes below %s, %d samples", len(input.basis), args.brite, len(fun_files))
+
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    ingest = (input, args.abundance_key, args.unweighted, args.threads, python_ingest)
     if world > 1 and not (make_diffab or save_Ppushed or validate):
         # launched with torchrun: shard over the GPUs of the node; rank 0 writes the output files
-        dists = _all_pairs_multi_gpu(fun_files, input, abundance_key, unweighted, num_threads, is_L2, python_ingest)
-        if rank != 0:
-            return
-        X = None
-    elif rank != 0:
+        dists = _all_pairs_multi_gpu(fun_files, input, args.abundance_key, args.unweighted, args.threads, is_L2,
+                                     python_ingest)
+        if rank == 0:
+            _write_outputs(args, input, fun_files, dists, None, None)
+        return
+    if rank != 0:
         logging.info("--diffab / --Ppushed / --validate run on one GPU: this rank has nothing to do")
         return
-    else:
-        X = _ingest(fun_files, input, abundance_key, unweighted, num_threads, python_ingest)
-        dists = None
+
+    X = _ingest(fun_files, *ingest)
+    logging.info("profiles read; computing all pairs on the GPU")
     mode = engine.MODE_L2 if is_L2 else engine.MODE_L1
-    logging.info(f"Computing pairwise distances")
-    diffabs_sparse = None
-    Ps_pushed = None
+    diffabs_sparse = Ps_pushed = None
     if save_Ppushed:
         pushed = solver.push_up_batch(X, input, is_L2)  # float64, the reference's operation order
         Ps_pushed = {file: pushed[i] for i, file in enumerate(fun_files)}
-    if dists is not None:
-        pass
-    elif not make_diffab:
+    if not make_diffab:
         dists = solver.all_pairs(X, input, is_L2)
     else:
         torch = engine._torch()
@@ -147,33 +155,4 @@ def main(args):
             PT = job.PT     # centred: per-pair differences are unchanged by the common offset
             dists = ctx.distances(job, mode).cpu().numpy()
         diffabs_sparse = solver.diffab_coo(ctx, PT, N, mode)
-    ##############################################################################
-    # Save Outputs (reference :76-108)
-    ##############################################################################
-    logging.info(f"Saving results")
-    fid = out_id if out_id else datetime.datetime.now().strftime('%Y%m%d-%H%M%S')
-    out_file = Path(out_dir, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format(fid))
-    out_file.parent.mkdir(parents=True, exist_ok=True)
-
-    np.save(out_file, dists)
-    out_basis_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__MAIN_BASIS__FILE_NAME.format(fid))
-    with open(out_basis_file, 'w') as f:
-        for file in fun_files:
-            f.write(f"{file}\n")
-    logging.info(f"Saved distances to {out_file}")
-    if make_diffab:
-        logging.info("Saving diffabs as a sparse npz file")
-        out_diffab_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__DIFFAB_FILE_NAME.format(fid))
-        sparse_npz.save_npz(out_diffab_file, diffabs_sparse)
-        logging.info(f"Saved difference abundance diffabs to {out_file}")
-        out_diffab_node_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__DIFFAB_NODES_FILE_NAME.format(fid))
-        with open(out_diffab_node_file, 'w') as f:
-            for node in input.basis:
-                f.write(f'{input.idx_to_node[node]}\n')
-
-    if save_Ppushed:
-        logging.info(f"Saving pushed profiles")
-        out_pushed_file = os.path.join(out_dir, constant.FUNUNIFRAC_OUT__PUSH_FILE_NAME.format(fid))
-        with open(out_pushed_file, 'wb') as f:
-            pickle.dump(Ps_pushed, f)
-        logging.info(f"Saved pushed profiles to {out_pushed_file}")
+    _write_outputs(args, input, fun_files, dists, diffabs_sparse, Ps_pushed)

@@ -21,7 +21,7 @@ import numpy as np
 
 import fununifrac_b200.factory.make_emd_input as make_emd_input
 import fununifrac_b200.factory.make_tree as make_tree
-from fununifrac_b200 import engine
+from fununifrac_b200 import cli_flags, engine
 from fununifrac_b200.algorithms.emd_unifrac import EarthMoverDistanceUniFracSolver
 from fununifrac_b200.objects.func_tree import FuncTreeEmduInput
 
@@ -51,33 +51,11 @@ def table_to_matrix(sample_df, input: FuncTreeEmduInput, normalize=True) -> np.n
 
 
 def build_parser() -> argparse.ArgumentParser:
-    parser = argparse.ArgumentParser(description="This script will take a directory of sourmash gather results and "
-                                                 "a weighted edge list representing the KEGG hierarchy and compute "
-                                                 "all pairwise functional unifrac distances.")
-    parser.add_argument('-e', '--edge_list',
-                        help='Input edge list file of the KEGG hierarchy. Must have lengths in the '
-                             'third column.')
-    parser.add_argument('-f', '--file', help="Input file that contains a combined dataframe of all samples with column"
-                                             "names being samples and row names being KOs.")
-    parser.add_argument('-o', '--out_dir', help='Output directory name.')
-    parser.add_argument('-i', '--out_id',
-                        help='Test purpose: give an identifier to the output file so that tester can recognize it')
-    parser.add_argument('-a', '--abundance_key',
-                        help='Key in the gather results to use for abundance. Default is `f_unique_weighted`',
-                        default='f_unique_weighted')
-    parser.add_argument('-b', '--brite', help='Use the subtree of the KEGG hierarchy rooted at the given BRITE ID. '
-                                              'eg. brite:ko00001', default="ko00001", type=str, required=False)
-    parser.add_argument('--diffab', action='store_true', help='Also return the difference abundance vectors.')
-    parser.add_argument('-v', help="Be verbose", action="store_const", dest="loglevel", const=logging.INFO,
-                        default=logging.WARNING)
-    parser.add_argument('--unweighted', help="Compute unweighted unifrac instead of the default weighted version",
-                        action="store_true")
-    parser.add_argument('--L2', help="Use L2 UniFrac instead of L1", action="store_true")
-    parser.add_argument('--Ppushed', help="Flag indicating you want the pushed vectors to be saved.",
-                        action="store_true")
-    parser.add_argument('--validate', help="Run the float64 validation kernels instead of the fp32 production path.",
-                        action="store_true")
-    return parser
+    return cli_flags.build(
+        "All-pairs functional UniFrac between the sample columns of one combined KO x sample table, over a KEGG "
+        "Orthology tree with edge lengths, computed on a B200.",
+        ["edge_list", "file", "out_dir", "out_id", "abundance_key", "brite", "diffab", "verbose", "unweighted", "L2",
+         "Ppushed", "validate"])
 
 
 def compute(sample_df, input: FuncTreeEmduInput, is_L2: bool, make_diffab: bool = False, validate: bool = False):
