@@ -577,6 +577,13 @@ def test_push_up_side_effect_on_lint():
     out = EarthMoverDistanceUniFracSolver().push_up_L1(np.array([0.5, 0.5, 0.0]), inp)
     assert out.tolist() == [0.5 * 2.220446049250313e-16, 0.5, 1.0]
     assert inp.lint[(0, 2)] == 2.220446049250313e-16 and inp.lint[(2, 0)] == 0   # one direction only
+    # the dicts are the caller's: a changed edge length must reach the device (the tree context is cached on the
+    # input object and keyed on a checksum of the lengths)
+    solver = EarthMoverDistanceUniFracSolver()
+    assert solver.push_up_L1(np.array([0.25, 0.75, 0.0]), inp).tolist() == [0.25 * 2.220446049250313e-16, 0.75, 1.0]
+    inp.lint[(1, 2)] = 3.0
+    assert solver.push_up_L1(np.array([0.25, 0.75, 0.0]), inp).tolist() == [0.25 * 2.220446049250313e-16, 2.25, 1.0]
+    assert solver.push_up_L2(np.array([0.0, 1.0, 0.0]), inp).tolist() == [0.0, np.sqrt(3.0), 1.0]
 
 
 def test_legacy_solve_entry_points(data_dir, golden_dir):
