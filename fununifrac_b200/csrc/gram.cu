@@ -46,7 +46,8 @@
 //                handed back to the MMA warp as soon as its raw values are in registers, then weighted into 64 float64
 //                registers per thread (int32 -> double without I2F); the float64 bypass columns are added here too.
 //       With the full matrix as output the epilogue also stores the transposed tile (no separate mirror pass).
-// K3x2 gram_pair_kernel   the same on CTA pairs (cta_group::2), opt-in (FUF_GRAM_2CTA=1): see its own comment.
+// K3x2 gram_pair_kernel   the same on CTA pairs (cta_group::2): the DEFAULT (FUF_GRAM_2CTA=0 selects gram_tile_kernel);
+//                         see its own comment.
 //
 // Tensor-pipe accounting: executed int8 MACs = 10 x 128 x 128 x (padded n) per tile; algorithmic flops = 2 n per pair.
 #include <algorithm>
@@ -156,6 +157,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TILE >> 3) << 17) |
                            ((uint32_t)(TILE >> 4) << 24);
 
+// (Every tcgen05.mma / tcgen05.commit below is executed by the WHOLE MMA warp in converged code and predicated on
+// elect.sync — the same leader every time for the same member mask: an `if (lane == 0)` around the instruction makes
+// ptxas wrap each one in an ELECT / branch loop, in converged code it becomes one predicated UTCIMMA.)
 // The issuing thread is the bottleneck of this kernel if it spends more than the ~68 cycles an MMA takes on building
 // its operands: the descriptors of one stage differ only in the 14-bit start-address field, so the low words are
 // `stage base + constant` (one add each) and the high word (SBO, version, layout) is a constant.
@@ -167,24 +171,51 @@ __device__ __forceinline__ void umma_i8_lo(uint32_t d_tmem, uint32_t a_lo, uint3
 {
     if (CTA_GROUP == 1)
         asm volatile(
-            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p, pe;\n\t"
             "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
             "setp.ne.b32 p, %6, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}"
             ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "n"(HI_A), "n"(HI_B), "r"(IDESC_V), "n"(ACCUMULATE)
             : "memory");
     else
         asm volatile(
-            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p, pe;\n\t"
             "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %4};\n\t"
             "setp.ne.b32 p, %6, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n\t}"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n\t}"
             ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "n"(HI_A), "n"(HI_B), "r"(IDESC_V), "n"(ACCUMULATE)
             : "memory");
 }
+// All ten accumulating MMAs of one 32-row block in ONE asm statement: the compiler wraps every asm that issues a
+// tcgen05 instruction from a single lane into an ELECT / branch sequence, once per statement.  Plane p of A (B) starts
+// 512 descriptor units (8 KB) after plane p - 1; accumulator c is 128 TMEM columns after accumulator c - 1.
+__device__ __forceinline__ void umma_block10(uint32_t tmem, uint32_t a_lo, uint32_t b_lo)
+{
+#define FUF_MMA(C, X, Y)                                                                          \
+    "add.u32 la, %1, " #X "*512;\n\tadd.u32 lb, %2, " #Y "*512;\n\t"                              \
+    "mov.b64 da, {la, %3};\n\tmov.b64 db, {lb, %3};\n\tadd.u32 td, %0, " #C "*128;\n\t"           \
+    "@pe tcgen05.mma.cta_group::1.kind::i8 [td], da, db, %4, p;\n\t"
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .b32 la, lb, td;\n\t.reg .pred p, pe;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        FUF_MMA(0, 0, 0)
+        FUF_MMA(1, 0, 1) FUF_MMA(1, 1, 0)
+        FUF_MMA(2, 0, 2) FUF_MMA(2, 1, 1) FUF_MMA(2, 2, 0)
+        FUF_MMA(3, 0, 3) FUF_MMA(3, 1, 2) FUF_MMA(3, 2, 1) FUF_MMA(3, 3, 0)
+        "}"
+        ::"r"(tmem), "r"(a_lo), "r"(b_lo), "n"(DESC_HI_SW128), "r"(IDESC)
+        : "memory");
+#undef FUF_MMA
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+        : "memory");
 }
 // int32 -> double without the quarter-rate I2F.F64: 2^52 + 2^31 + v is exactly representable, its bit pattern is
 // {0x43300000, v ^ 0x80000000}; one LOP3 and one DADD (exact for every int32).
@@ -305,41 +336,25 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                             for (int c = 0; c < NDIG; c++) {
                                 mbar_wait(tempty0 + 8 * c, eph);
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                if (lane == 0) {
-                                    umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 0>(
-                                        tmem_base + c * TILE, a_lo, b_lo + ((c * PLANE_BYTES) >> 4));
+                                umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 0>(
+                                    tmem_base + c * TILE, a_lo, b_lo + ((c * PLANE_BYTES) >> 4));
 #pragma unroll
-                                    for (int x = 1; x <= c; x++)
-                                        umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 1>(
-                                            tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
-                                            b_lo + (((c - x) * PLANE_BYTES) >> 4));
-                                }
-                            }
-                            fresh = false;
-                        } else if (lane == 0) {
-#pragma unroll
-                            for (int c = 0; c < NDIG; c++)
-#pragma unroll
-                                for (int x = 0; x <= c; x++)
+                                for (int x = 1; x <= c; x++)
                                     umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 1>(
                                         tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
                                         b_lo + (((c - x) * PLANE_BYTES) >> 4));
+                            }
+                            fresh = false;
+                        } else {
+                            umma_block10(tmem_base, a_lo, b_lo);   // whole warp: one elected lane issues
                         }
-                        if (lane == 0) {   // second 32 rows of the stage: order c = all products d_x d'_y with x + y = c
+                        {   // second 32 rows of the stage: order c = all products d_x d'_y with x + y = c
                             constexpr uint32_t off = (KB * TILE) >> 4;
-#pragma unroll
-                            for (int c = 0; c < NDIG; c++)
-#pragma unroll
-                                for (int x = 0; x <= c; x++)
-                                    umma_i8_lo<1, DESC_HI_SW128, DESC_HI_SW128, IDESC, 1>(
-                                        tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4) + off,
-                                        b_lo + (((c - x) * PLANE_BYTES) >> 4) + off);
+                            umma_block10(tmem_base, a_lo + off, b_lo + off);
                         }
-                        if (lane == 0) umma_commit(empty0 + 8 * slot);  // frees the smem stage when the MMAs have read it
-                        __syncwarp();
+                        umma_commit(empty0 + 8 * slot);  // frees the smem stage when the MMAs have read it
                     }
-                    if (lane == 0) umma_commit(tfull);  // the accumulators of this bucket are complete
-                    __syncwarp();
+                    umma_commit(tfull);  // the accumulators of this bucket are complete
                 }
             }
         }
@@ -411,7 +426,7 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K3x2 gram_pair_kernel: the same computation on CTA PAIRS (thread-block clusters of 2, tcgen05 cta_group::2).
-// With one CTA per tile the tensor pipe is held back by shared-memory bandwidth: an int8 MMA (M = N = 128, K = 32)
+// With one CTA per tile every operand byte is fetched and read per CTA: an int8 MMA (M = N = 128, K = 32)
 // reads 8 KB of operands per 68 cycles (120 B/clk) while TMA writes another 48 B/clk into the same banks.  A pair
 // computes a 256 x 128 tile: M = 256 are the samples of TWO column tiles (2b, 2b+1), one per CTA, N = 128 the samples
 // of row tile ti, split in halves of 64 between the two CTAs.  Per CTA and MMA that is 4 KB (A) + 2 KB (half of B):
@@ -477,9 +492,11 @@ constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1
                             ((uint32_t)((2 * TILE) >> 4) << 24);   // M = 256 over the pair, N = 128
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3)
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
@@ -568,18 +585,16 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                             for (int c = 0; c < NDIG; c++) {
                                 mbar_wait(tempty0 + 8 * c, eph);
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                if (lane == 0) {
-                                    umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 0>(
-                                        tmem_base + c * TILE, a_lo, b_lo + ((c * PLANE_B2) >> 4));
+                                umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 0>(
+                                    tmem_base + c * TILE, a_lo, b_lo + ((c * PLANE_B2) >> 4));
 #pragma unroll
-                                    for (int x = 1; x <= c; x++)
-                                        umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 1>(
-                                            tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
-                                            b_lo + (((c - x) * PLANE_B2) >> 4));
-                                }
+                                for (int x = 1; x <= c; x++)
+                                    umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 1>(
+                                        tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
+                                        b_lo + (((c - x) * PLANE_B2) >> 4));
                             }
                             fresh = false;
-                        } else if (lane == 0) {
+                        } else {
 #pragma unroll
                             for (int c = 0; c < NDIG; c++)
 #pragma unroll
@@ -588,7 +603,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                                         tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4),
                                         b_lo + (((c - x) * PLANE_B2) >> 4));
                         }
-                        if (lane == 0) {
+                        {
                             constexpr uint32_t offA = (KB * TILE) >> 4, offB = (KB * 64) >> 4;
 #pragma unroll
                             for (int c = 0; c < NDIG; c++)
@@ -598,11 +613,9 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                                         tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4) + offA,
                                         b_lo + (((c - x) * PLANE_B2) >> 4) + offB);
                         }
-                        if (lane == 0) umma_commit_2sm(empty0 + 8 * slot);
-                        __syncwarp();
+                        umma_commit_2sm(empty0 + 8 * slot);
                     }
-                    if (lane == 0) umma_commit_2sm(tfull);
-                    __syncwarp();
+                    umma_commit_2sm(tfull);
                 }
             }
         }
@@ -1155,7 +1168,7 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
     }
     const char *pair_env = getenv("FUF_GRAM_2CTA");
-    const bool use_pairs = pair_env ? atoi(pair_env) != 0 : false;
+    const bool use_pairs = pair_env ? atoi(pair_env) != 0 : true;   // default: CTA pairs (FUF_GRAM_2CTA=0: one CTA per tile)
     if (use_pairs) {
         // CTA pairs: work item = row tile x two column tiles (2b, 2b+1); the half below the diagonal is computed and dropped
         std::vector<PairTile> ptiles;
@@ -1163,6 +1176,7 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
             const int32_t t = full ? c : tile_rows_h[c];
             for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, full ? t * TILE : c * TILE, 0});
         }
+        static_assert(PLANE_BYTES == 8192 && TILE == 128, "umma_block10 hard-codes the plane and accumulator strides");
         static_assert(KC == 2 * KB, "the issue loops are written for two 32-row MMA blocks per stage");
         static_assert(sizeof(PairTile) == sizeof(Tile), "the pair tiles reuse the tile table's room");
         FUF_REQUIRE(ptiles.size() <= tiles.size(), "fuf_pairwise_gram: pair-tile table larger than the tile table");

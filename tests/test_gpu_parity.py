@@ -303,13 +303,13 @@ def test_near_duplicates_are_refined(full_tree):
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cta_pairs", [False, True])
 def test_gram_kernel_layouts(cta_pairs, monkeypatch):
-    """cta_pairs: the opt-in variant on thread-block clusters of two (tcgen05 cta_group::2, FUF_GRAM_2CTA=1).
+    """cta_pairs: the default kernel on thread-block clusters of two (tcgen05 cta_group::2); False: one CTA per tile
+    (FUF_GRAM_2CTA=0).
     Pins the shared-memory / instruction descriptors, the swizzle, the digit planes and the TMEM read-out of the
     integer Gram kernel: dense random profiles with column scales over six decades, (a) every column through the
     int8 path, (b) the default split with the largest-scale columns in float64.  A wrong layout gives O(1) errors;
     the arithmetic itself is exact up to 1.44e-9 of the scale statistic."""
-    if cta_pairs:
-        monkeypatch.setenv("FUF_GRAM_2CTA", "1")
+    monkeypatch.setenv("FUF_GRAM_2CTA", "1" if cta_pairs else "0")
     n, N = 200, 300
     parent = np.full(n, n - 1, np.int32)
     parent[-1] = -1
@@ -342,8 +342,7 @@ def test_gram_kernel_layouts(cta_pairs, monkeypatch):
 
 @pytest.mark.parametrize("cta_pairs", [False, True])
 def test_gram_vs_oracle(cta_pairs, full_tree, monkeypatch):
-    if cta_pairs:
-        monkeypatch.setenv("FUF_GRAM_2CTA", "1")
+    monkeypatch.setenv("FUF_GRAM_2CTA", "1" if cta_pairs else "0")
     inp, ctx, leaves = full_tree
     N = 640                                   # 5 tile rows, the last one 128 wide; above the Gram threshold
     X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=12)
