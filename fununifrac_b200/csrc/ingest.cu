@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <deque>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -176,15 +177,42 @@ struct Field {
     bool quoted;
 };
 
-// One record starting at *cur: fields appended to `fields` (unescaped text lives in `scratch` when a quoted field
-// contains doubled quotes).  Returns false at end of input.
-static bool next_record(const char *&cur, const char *end, std::vector<Field> &fields, std::vector<std::string> &scratch)
+// First ',', '\n' or '\r' at or after p (end if none): eight bytes at a time.
+static inline const char *skip_plain(const char *p, const char *end)
 {
-    fields.clear();
+    const uint64_t ones = 0x0101010101010101ull, high = 0x8080808080808080ull;
+    while (p + 8 <= end) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        const uint64_t a = w ^ (ones * (uint64_t)','), b = w ^ (ones * (uint64_t)'\n'), c = w ^ (ones * (uint64_t)'\r');
+        const uint64_t m = (((a - ones) & ~a) | ((b - ones) & ~b) | ((c - ones) & ~c)) & high;
+        if (m) return p + (__builtin_ctzll(m) >> 3);   // lowest flagged byte = first delimiter (little endian)
+        p += 8;
+    }
+    while (p < end && *p != ',' && *p != '\n' && *p != '\r') p++;
+    return p;
+}
+
+// One record starting at *cur, tokenised with pandas' C-parser rules; `sink(index, field)` receives every field whose
+// text `want(index)` asks for (the others are only counted).  Unescaped text of a wanted quoted field with doubled
+// quotes lives in `scratch`.  Returns false at end of input; *n_fields = fields in the record, *first_empty = the first
+// field is empty and unquoted (a record with one such field is a blank line).
+template <class Want, class Sink>
+static bool tokenize_record(const char *&cur, const char *end, std::deque<std::string> &scratch, size_t *n_fields,
+                            bool *first_empty, Want want, Sink sink)
+{
     scratch.clear();
+    *n_fields = 0;
+    *first_empty = false;
     if (cur >= end) return false;
+    auto emit = [&](Field f) {
+        const size_t idx = (*n_fields)++;
+        if (idx == 0) *first_empty = f.len == 0 && !f.quoted;
+        if (want(idx)) sink(idx, f);
+    };
     for (;;) {
         Field f{cur, 0, false};
+        const bool keep = want(*n_fields);
         if (cur < end && *cur == '"') {
             f.quoted = true;
             const char *q = cur + 1;
@@ -202,39 +230,43 @@ static bool next_record(const char *&cur, const char *end, std::vector<Field> &f
                 q++;
             }
             const char *close = q;
-            if (escaped) {
+            f.p = start;
+            f.len = (size_t)(close - start);
+            if (escaped && keep) {
                 std::string s;
                 for (const char *r = start; r < close; r++) {
                     s.push_back(*r);
                     if (*r == '"') r++;
                 }
                 scratch.push_back(std::move(s));
-                f.p = nullptr;  // resolved below (scratch may reallocate)
+                f.p = nullptr;  // resolved below
                 f.len = scratch.size() - 1;
-            } else {
-                f.p = start;
-                f.len = (size_t)(close - start);
             }
             cur = close < end ? close + 1 : end;
             // pandas appends whatever follows the closing quote up to the delimiter
             const char *tail = cur;
-            while (cur < end && *cur != ',' && *cur != '\n' && *cur != '\r') cur++;
-            if (cur > tail) {
+            cur = skip_plain(cur, end);
+            if (cur > tail && keep) {
                 std::string s = (f.p ? std::string(f.p, f.len) : scratch[f.len]) + std::string(tail, cur - tail);
                 scratch.push_back(std::move(s));
                 f.p = nullptr;
                 f.len = scratch.size() - 1;
             }
+            if (keep && !f.p) {
+                const std::string &s = scratch[f.len];
+                f.p = s.data();
+                f.len = s.size();
+            }
         } else {
-            while (cur < end && *cur != ',' && *cur != '\n' && *cur != '\r') cur++;
+            cur = skip_plain(cur, end);
             f.len = (size_t)(cur - f.p);
         }
-        fields.push_back(f);
+        emit(f);
         if (cur >= end) break;
         if (*cur == ',') {
             cur++;
             if (cur >= end) {  // trailing delimiter: one more empty field
-                fields.push_back(Field{cur, 0, false});
+                emit(Field{cur, 0, false});
                 break;
             }
             continue;
@@ -247,13 +279,20 @@ static bool next_record(const char *&cur, const char *end, std::vector<Field> &f
         }
         break;
     }
-    for (auto &f : fields)
-        if (!f.p) {
-            const std::string &s = scratch[f.len];
-            f.p = s.data();
-            f.len = s.size();
-        }
     return true;
+}
+
+// All fields of a record (the header).
+static bool next_record(const char *&cur, const char *end, std::vector<Field> &fields, std::deque<std::string> &scratch,
+                        bool *blank)
+{
+    fields.clear();
+    size_t n = 0;
+    bool first_empty = false;
+    const bool ok = tokenize_record(cur, end, scratch, &n, &first_empty, [](size_t) { return true; },
+                                    [&](size_t, const Field &f) { fields.push_back(f); });
+    *blank = ok && n == 1 && first_empty;
+    return ok;
 }
 
 struct FileResult {
@@ -284,12 +323,12 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
     const char *cur = buf.data(), *end = cur + buf.size();
     if (buf.size() >= 3 && (unsigned char)cur[0] == 0xEF && (unsigned char)cur[1] == 0xBB && (unsigned char)cur[2] == 0xBF) cur += 3;
     std::vector<Field> fields;
-    std::vector<std::string> scratch;
-    auto blank = [&](const std::vector<Field> &f) { return f.size() == 1 && f[0].len == 0 && !f[0].quoted; };
+    std::deque<std::string> scratch;   // stable addresses: fields point into its strings
+    bool blank = false;
     // header
     do {
-        if (!next_record(cur, end, fields, scratch)) return set_msg(res, 3, std::string("No columns to parse from file ") + path);
-    } while (blank(fields));
+        if (!next_record(cur, end, fields, scratch, &blank)) return set_msg(res, 3, std::string("No columns to parse from file ") + path);
+    } while (blank);
     int name_col = -1, key_col = -1;
     const size_t n_cols = fields.size();
     for (size_t c = 0; c < n_cols; c++) {
@@ -300,25 +339,37 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
     if (key_col < 0) return set_msg(res, 5, key);          // KeyError(abundance_key) in the reference
     if (name_col < 0) return set_msg(res, 5, "name");
     long long line = 1;
-    while (next_record(cur, end, fields, scratch)) {
+    const size_t c_name = (size_t)name_col, c_key = (size_t)key_col;
+    for (;;) {
+        // data rows: only the two columns the path uses are materialised, the rest is skipped and counted
+        Field f_name{nullptr, 0, false}, f_key{nullptr, 0, false};
+        bool have_name = false, have_key = false, first_empty = false;
+        size_t n_fields = 0;
+        if (!tokenize_record(cur, end, scratch, &n_fields, &first_empty,
+                             [&](size_t i) { return i == c_name || i == c_key; },
+                             [&](size_t i, const Field &f) {
+                                 if (i == c_name) f_name = f, have_name = true;
+                                 if (i == c_key) f_key = f, have_key = true;
+                             }))
+            break;
         line++;
-        if (blank(fields)) continue;
-        if (fields.size() > n_cols)
+        if (n_fields == 1 && first_empty) continue;        // blank line
+        if (n_fields > n_cols)
             return set_msg(res, 3, "Error tokenizing data. C error: Expected " + std::to_string(n_cols) + " fields in line " +
-                                       std::to_string(line) + ", saw " + std::to_string(fields.size()));
+                                       std::to_string(line) + ", saw " + std::to_string(n_fields));
         // abundance
         double value = NAN;
-        if ((size_t)key_col < fields.size()) {
-            const Field &f = fields[key_col];
+        if (have_key) {
+            const Field &f = f_key;
             if (!(is_na(f.p, f.len) && !(f.quoted && f.len == 0 && false))) {
                 if (!parse_double(f.p, f.len, &value) && !parse_special(f.p, f.len, &value))
                     return set_msg(res, 1, std::string(f.p, f.len));
             }
         }
         // name -> KO id
-        if ((size_t)name_col >= fields.size() || is_na(fields[name_col].p, fields[name_col].len))
+        if (!have_name || is_na(f_name.p, f_name.len))
             return set_msg(res, 4, "nan");
-        const Field &nf = fields[name_col];
+        const Field &nf = f_name;
         const char *b = nf.p, *e = nf.p + nf.len;
         if (!(nf.len >= 3 && memcmp(b, "ko:", 3) == 0)) {
             for (const char *q = e; q > b; q--)
