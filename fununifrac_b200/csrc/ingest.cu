@@ -24,6 +24,7 @@
 #include <atomic>
 #include <deque>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -31,7 +32,8 @@
 #include "common.cuh"
 
 struct fuf_name_index {
-    std::unordered_map<std::string, int32_t> map;
+    std::deque<std::string> names;                            // owns the text the views of `map` point into
+    std::unordered_map<std::string_view, int32_t> map;        // looked up with views into the file buffer: no copies
     int32_t n = 0;
 };
 
@@ -314,7 +316,16 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
     FILE *fp = fopen(path, "rb");
     if (!fp) return set_msg(res, 3, std::string("cannot open ") + path + ": " + strerror(errno));
     std::string buf;
-    {
+    {   // one read of the whole file when its size is known, chunks otherwise (pipes)
+        long size = -1;
+        if (fseek(fp, 0, SEEK_END) == 0) {
+            size = ftell(fp);
+            rewind(fp);
+        }
+        if (size > 0) {
+            buf.resize((size_t)size);
+            buf.resize(fread(&buf[0], 1, (size_t)size, fp));
+        }
         char chunk[1 << 16];
         size_t got;
         while ((got = fread(chunk, 1, sizeof(chunk), fp)) > 0) buf.append(chunk, got);
@@ -383,10 +394,10 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
                 b = q;
                 break;
             }
-        std::string ko(b, e - b);
+        const std::string_view ko(b, (size_t)(e - b));
         auto it = index->map.find(ko);
         if (it == index->map.end()) {
-            res.warnings += ko;
+            res.warnings.append(ko.data(), ko.size());
             res.warnings.push_back('\n');
         } else {
             P[it->second] = value;
@@ -416,7 +427,10 @@ extern "C" int fuf_name_index_create(fuf_name_index **out, const char *const *na
     }
     ix->n = n;
     ix->map.reserve((size_t)n * 2);
-    for (int32_t k = 0; k < n; k++) ix->map[std::string(names[k])] = k;  // a repeated name keeps its last index (dict semantics)
+    for (int32_t k = 0; k < n; k++) {   // a repeated name keeps its last index (dict semantics)
+        ix->names.emplace_back(names[k]);
+        ix->map[std::string_view(ix->names.back())] = k;
+    }
     *out = ix;
     return FUF_OK;
 }
