@@ -296,7 +296,10 @@ class FuncTree:
 
     @classmethod
     def infer_edge_len_property(cls, G: TreeDiGraph):
-        edge_properties = list(list(G.edges(data=True))[0][-1].keys())
+        first_edge = next(iter(G.edges(data=True)), None)      # the attribute names of the FIRST edge decide
+        if first_edge is None:
+            raise IndexError("list index out of range")        # what indexing an empty edge list raises
+        edge_properties = list(first_edge[-1].keys())
         if len(edge_properties) > 1:
             raise ValueError(f'I found multiple edge properties: {edge_properties}. I don\'t know which one to use for '
                              f'edge lengths.')
