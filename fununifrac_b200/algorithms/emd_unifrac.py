@@ -108,24 +108,26 @@ class EarthMoverDistanceUniFracSolver:
                 raise ValueError(f"pushed vectors must have length {n}")
             ctx.load_pushed(torch.from_numpy(rows).to(dev), P64T, col0=b)
         if self.validate:
-            PT = P64T
             D = ctx.pairwise_f64(P64T, N, mode)
         else:
-            job = ctx.round_pushed(P64T, N, mode)
-            PT = job.PT
-            D = ctx.distances(job, mode)
+            D = ctx.distances(ctx.round_pushed(P64T, N, mode), mode)
         dists = D.cpu().numpy()
         if not make_diffab:
             return dists, None
-        return dists, self.diffab_coo(ctx, PT, N, mode)
+        # difference vectors always from the float64 profiles: P - Q in double, as get_L1_diffab / get_L2_diffab do
+        return dists, self.diffab_coo(ctx, P64T, N, mode)
 
-    def diffab_coo(self, ctx: engine.TreeContext, PT, N: int, mode: int, pairs_per_block: Optional[int] = None) -> COO:
-        """Stream dense difference rows from the device and build the reference's COO − COOᵀ(1,0,2)."""
+    def diffab_entries(self, ctx: engine.TreeContext, PT, N: int, mode: int, pairs_per_block: Optional[int] = None,
+                       pair_begin: int = 0, pair_end: Optional[int] = None):
+        """Non-zero entries (i, j, k, value) with i < j of the pairs [pair_begin, pair_end) in ``combinations`` order:
+        dense difference rows are streamed from the device and compacted on the host (``np.nonzero``, as the reference
+        does per pair, :58-61)."""
         n = ctx.n
         if pairs_per_block is None:
             pairs_per_block = max(32, min(4096, (128 << 20) // (PT.element_size() * n)))
         ii, jj, kk, vv = [], [], [], []
-        for b, e, rows in engine.iter_diffab_blocks(ctx, PT, N, mode, pairs_per_block):
+        for b, e, rows in engine.iter_diffab_blocks(ctx, PT, N, mode, pairs_per_block, pair_begin=pair_begin,
+                                                    pair_end=pair_end):
             pr, k = np.nonzero(rows)
             if len(pr) == 0:
                 continue
@@ -137,12 +139,21 @@ class EarthMoverDistanceUniFracSolver:
             kk.append(k.astype(np.int64))
             vv.append(rows[pr, k].astype(np.float64))
         if ii:
-            i, j, k, v = map(np.concatenate, (ii, jj, kk, vv))
-        else:
-            i = j = k = np.zeros(0, dtype=np.int64)
-            v = np.zeros(0)
+            return tuple(map(np.concatenate, (ii, jj, kk, vv)))
+        z = np.zeros(0, dtype=np.int64)
+        return z, z, z, np.zeros(0)
+
+    @staticmethod
+    def coo_from_entries(parts, N: int, n: int) -> COO:
+        """The reference's ``COO - COO.transpose((1, 0, 2))`` (:70-72) from the upper-triangle entries of one or more
+        pair ranges (in range order)."""
+        i, j, k, v = (np.concatenate([p[c] for p in parts]) for c in range(4))
         coords = np.stack([np.concatenate([i, j]), np.concatenate([j, i]), np.concatenate([k, k])])
         return COO(coords, np.concatenate([v, -v]), (N, N, n))
+
+    def diffab_coo(self, ctx: engine.TreeContext, PT, N: int, mode: int, pairs_per_block: Optional[int] = None) -> COO:
+        """Stream dense difference rows from the device and build the reference's COO − COOᵀ(1,0,2)."""
+        return self.coo_from_entries([self.diffab_entries(ctx, PT, N, mode, pairs_per_block)], N, ctx.n)
 
     # ------------------------------------------------------------------------------------------
     # legacy per-pair solvers ("Not used. Moved to pushup paradigm", :77-194) kept for API parity

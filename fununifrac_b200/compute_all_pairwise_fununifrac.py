@@ -25,26 +25,35 @@ from fununifrac_b200.objects.func_tree import FuncTreeEmduInput
 
 
 def _ingest(files, input, abundance_key, unweighted, num_threads, python_ingest):
-    """Un-pushed profile matrix [len(files), n] of gather CSVs, in file order."""
+    """Un-pushed profile matrix [len(files), n] of gather CSVs, in file order, in PAGE-LOCKED host memory: the rows are
+    parsed straight into the buffer the GPU then reads by DMA (a pageable matrix would cross PCIe through the driver's
+    staging buffers, serialised with the compute)."""
+    n = len(input.basis)
     if not files:
-        return np.zeros((0, len(input.basis)))
+        return np.zeros((0, n))
+    X = engine.pinned_empty((len(files), n), engine._torch().float64)[1]
     if python_ingest:
         # the reference's own route: pandas.read_csv + a process pool (src/factory/make_emd_input.py:58-122)
         results = make_emd_input.parallel_functional_profile_to_vector(num_threads, files, input, abundance_key,
                                                                        unweighted)
-        got, X = make_emd_input.profiles_to_matrix(results, len(input.basis))
+        got = [f for f, _ in results]
+        for i, (_, P) in enumerate(results):
+            X[i, :] = P
     else:
         # native ingest (csrc/ingest.cu): C++ thread pool, only the two columns the path uses are tokenised;
         # rows are bit-identical to the route above
-        got, X = make_emd_input.native_profiles_to_matrix(files, input, abundance_key, unweighted, num_threads)
+        X[...] = 0
+        got, X = make_emd_input.native_profiles_to_matrix(files, input, abundance_key, unweighted, num_threads, out=X)
     assert got == list(files)
     return X
 
 
-def _all_pairs_multi_gpu(fun_files, input, abundance_key, unweighted, num_threads, is_L2, python_ingest):
-    """The compute section under ``torchrun`` (one process per GPU of one node): every rank ingests and pushes up its
-    own block of files, the pushed profiles are all-gathered over NVLink, every rank computes its tile rows and stores
-    them into one shared host matrix (``sharded.ShardedAllPairs.step_host``).  Returns the matrix on every rank."""
+def _main_multi_gpu(args, input, fun_files, is_L2, make_diffab, save_Ppushed, python_ingest):
+    """The compute section under ``torchrun`` (one process per GPU of ONE node): every rank ingests and pushes up its own
+    block of files, the pushed profiles are exchanged over NVLink, every rank computes its tile rows and stores them into
+    one shared page-locked host matrix (``sharded.ShardedAllPairs.step_host``); rank 0 writes the output files from it.
+    ``--diffab``: every rank streams its own contiguous range of pairs over its own PCIe link and compacts it; the
+    entries are joined on rank 0.  ``--Ppushed``: every rank pushes its own files up in float64 (reference order)."""
     import torch
     import torch.distributed as dist
 
@@ -52,21 +61,52 @@ def _all_pairs_multi_gpu(fun_files, input, abundance_key, unweighted, num_thread
 
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    if local_world != world:
+        # the result matrix is one shared-memory mapping: that exists on one node only.  Fail before any rank waits.
+        raise RuntimeError(f"the multi-GPU driver shards over the GPUs of ONE node (LOCAL_WORLD_SIZE={local_world}, "
+                           f"WORLD_SIZE={world}); launch one job per node")
     torch.cuda.set_device(local_rank)
     own_group = not dist.is_initialized()
     if own_group:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     try:
         N = len(fun_files)
+        mode = engine.MODE_L2 if is_L2 else engine.MODE_L1
         ctx = engine.context_for(input, local_rank)
-        job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, engine.MODE_L2 if is_L2 else engine.MODE_L1, world, rank,
-                                      dist)
-        X = _ingest(fun_files[job.lo:job.hi], input, abundance_key, unweighted, num_threads, python_ingest)
+        solver = EarthMoverDistanceUniFracSolver(device=local_rank)
+        job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, mode, world, rank, dist)
+        X = _ingest(fun_files[job.lo:job.hi], input, args.abundance_key, args.unweighted, args.threads, python_ingest)
         shared = sharded.SharedHostMatrix(N, world, rank, dist)
-        dists = job.step_host(X, shared).copy()
-        dist.barrier()
+        dists = job.step_host(X, shared)              # the shared mapping itself: nobody copies N x N doubles
+        diffabs_sparse = Ps_pushed = None
+        if save_Ppushed:
+            rows = [None] * world
+            dist.gather_object(solver.push_up_batch(X, input, is_L2), rows if rank == 0 else None, dst=0)
+            if rank == 0:
+                pushed = np.concatenate(rows, axis=0)
+                Ps_pushed = {file: pushed[i] for i, file in enumerate(fun_files)}
+        if make_diffab:
+            # every rank needs every sample's float64 profile: all-gather the un-pushed shards (N x n doubles; --diffab
+            # output is N^2 n / 2 entries, so N is small whenever this is feasible at all) and push them up locally
+            dev = f"cuda:{local_rank}"
+            Xs = torch.zeros((job.shard, ctx.n), dtype=torch.float64, device=dev)
+            Xs[:job.hi - job.lo] = torch.from_numpy(X).to(dev)
+            Xall = torch.empty((world * job.shard, ctx.n), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(Xall, Xs)
+            keep = torch.cat([torch.arange(r * job.shard, r * job.shard + hi - lo, device=dev)
+                              for r in range(world) for lo, hi in [sharded.sample_range(N, world, r)]])
+            pushed = ctx.push_up_job(Xall[keep].contiguous(), mode)
+            p0, p1 = engine.diffab_pair_range(N, world, rank)
+            part = solver.diffab_entries(ctx, pushed.P64T, N, mode, pair_begin=p0, pair_end=p1)
+            parts = [None] * world
+            dist.gather_object(part, parts if rank == 0 else None, dst=0)
+            if rank == 0:
+                diffabs_sparse = solver.coo_from_entries(parts, N, ctx.n)
+        if rank == 0:
+            _write_outputs(args, input, fun_files, dists, diffabs_sparse, Ps_pushed)
+        dist.barrier()                                # the other ranks keep their mappings until the file is written
         shared.close()
-        return dists
     finally:
         if own_group:
             dist.destroy_process_group()
@@ -121,38 +161,36 @@ def main(args):
     logging.info("%d tree nodes below %s, %d samples", len(input.basis), args.brite, len(fun_files))
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
-    ingest = (input, args.abundance_key, args.unweighted, args.threads, python_ingest)
-    if world > 1 and not (make_diffab or save_Ppushed or validate):
+    if world > 1 and not validate:
         # launched with torchrun: shard over the GPUs of the node; rank 0 writes the output files
-        dists = _all_pairs_multi_gpu(fun_files, input, args.abundance_key, args.unweighted, args.threads, is_L2,
-                                     python_ingest)
-        if rank == 0:
-            _write_outputs(args, input, fun_files, dists, None, None)
-        return
+        return _main_multi_gpu(args, input, fun_files, is_L2, make_diffab, save_Ppushed, python_ingest)
     if rank != 0:
-        logging.info("--diffab / --Ppushed / --validate run on one GPU: this rank has nothing to do")
+        logging.info("--validate runs on one GPU: this rank has nothing to do")
         return
 
-    X = _ingest(fun_files, *ingest)
+    X = _ingest(fun_files, input, args.abundance_key, args.unweighted, args.threads, python_ingest)
     logging.info("profiles read; computing all pairs on the GPU")
     mode = engine.MODE_L2 if is_L2 else engine.MODE_L1
+    N = len(fun_files)
     diffabs_sparse = Ps_pushed = None
     if save_Ppushed:
         pushed = solver.push_up_batch(X, input, is_L2)  # float64, the reference's operation order
         Ps_pushed = {file: pushed[i] for i, file in enumerate(fun_files)}
     if not make_diffab:
-        dists = solver.all_pairs(X, input, is_L2)
+        # page-locked result: finished bands of the matrix leave the device while later ones are still computed
+        dists = solver.all_pairs(X, input, is_L2, engine.pinned_empty((N, N), engine._torch().float64)[1] if N else None)
     else:
         torch = engine._torch()
         ctx = engine.context_for(input)
-        N = len(fun_files)
         Xd = torch.from_numpy(X).to(f"cuda:{ctx.device}")
         if validate:
             PT = ctx.push_up_f64(Xd, mode)
             dists = ctx.pairwise_f64(PT, N, mode).cpu().numpy()
         else:
             job = ctx.push_up_job(Xd, mode)
-            PT = job.PT     # centred: per-pair differences are unchanged by the common offset
+            # the difference vectors come from the float64 profiles (the reference's P - Q is float64: fp32 operands
+            # would lose near-equal samples' differences altogether); the distances from the fp32 tiles + refinement
+            PT = job.P64T
             dists = ctx.distances(job, mode).cpu().numpy()
         diffabs_sparse = solver.diffab_coo(ctx, PT, N, mode)
     _write_outputs(args, input, fun_files, dists, diffabs_sparse, Ps_pushed)

@@ -32,21 +32,26 @@ def make_fununifrac_inputs(raw_P, input: FuncTreeEmduInput, normalize=True):
 
 
 def table_to_matrix(sample_df, input: FuncTreeEmduInput, normalize=True) -> np.ndarray:
-    """All columns of the table at once: X[N, n] with the arithmetic of ``make_fununifrac_inputs`` per column
-    (column / column.sum(), scattered to the basis; rows whose KO is not in the tree are dropped with one warning
-    each; for a KO listed twice the last row wins, as repeated assignment does)."""
+    """All columns of the table at once: X[N, n] with the arithmetic of ``make_fununifrac_inputs`` per column:
+    ``column / column.sum()`` — ``Series.sum()``: NaN skipped, numpy's pairwise summation over the contiguous column —
+    scattered to the basis; rows whose KO is not in the tree are dropped with one warning each.  A table with a repeated
+    KO id goes column by column through ``make_fununifrac_inputs`` itself, so that it fails the way the reference
+    does (``P[i] = raw_P[ko]`` with a two-element selection)."""
     node_2_idx = input.node_to_idx()
     n = len(input.idx_to_node)
-    vals = sample_df.to_numpy(dtype=np.float64)                 # [rows, N]
+    if not sample_df.index.is_unique:
+        return np.stack([make_fununifrac_inputs(sample_df[c], input, normalize) for c in sample_df.columns])
+    vals_t = np.ascontiguousarray(sample_df.to_numpy(dtype=np.float64).T)        # [N, rows]: one contiguous row per sample
     if normalize:
-        vals = vals / vals.sum(axis=0, keepdims=True)
-    X = np.zeros((vals.shape[1], n), dtype=np.float64)
+        sums = np.where(np.isnan(vals_t), 0.0, vals_t).sum(axis=1)             # pairwise per row, as Series.sum()
+        vals_t = vals_t / sums[:, None]
+    X = np.zeros((vals_t.shape[0], n), dtype=np.float64)
     for r, ko in enumerate(sample_df.index):
         j = node_2_idx.get(ko)
         if j is None:
             print(f"Warning: {ko} not found in EMDU index, skipping.")
         else:
-            X[:, j] = vals[r]
+            X[:, j] = vals_t[:, r]
     return X
 
 
@@ -76,7 +81,7 @@ def compute(sample_df, input: FuncTreeEmduInput, is_L2: bool, make_diffab: bool 
         pushed = ctx.push_up_job(Xd, engine.MODE_L1)                 # always the L1 weights (reference quirk)
         job = ctx.round_pushed(pushed.P64T, N, mode)                 # rounding statistics in the pairwise form's norm
         dists = ctx.distances(job, mode).cpu().numpy()
-        PT = job.PT
+        PT = pushed.P64T                                             # difference vectors in float64, like P - Q
     diffabs = EarthMoverDistanceUniFracSolver(validate=validate).diffab_coo(ctx, PT, N, mode) if make_diffab else None
     return dists, diffabs
 

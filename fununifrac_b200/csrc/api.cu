@@ -83,10 +83,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     if ((rc = ctx->ws_x.reserve((size_t)N * n * esz))) return rc;
     const bool d_pinned = is_pinned_host(D_h);
     if ((rc = ctx->ws_d.reserve((size_t)N * N * sizeof(double)))) return rc;
-    double *D_dev = (double *)ctx->ws_d.ptr, *D_zc = nullptr;
-    if (d_pinned && !validate && !use_gram && getenv("FUF_ZEROCOPY")) FUF_CUDA(cudaHostGetDevicePointer((void **)&D_zc, D_h, 0));
+    double *D_dev = (double *)ctx->ws_d.ptr;
     // pinned D_h: every finished band of D is copied while the next one computes; pageable D_h: one copy at the end
-    const bool band_d2h = !validate && d_pinned && D_zc == nullptr;
+    const bool band_d2h = !validate && d_pinned;
     cudaStream_t sc = ctx->s_copy, sk = ctx->s_comp, sd = ctx->s_d2h;
     // per-pair refinement budget: 0.1 % of the pairs (beyond it the float64 tile kernel redoes the whole matrix)
     const int64_t refine_budget = std::max<int64_t>(1024, N * (N - 1) / 2 / 1000);
@@ -135,7 +134,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             if (rc) return rc;
             if (do_refine) {
                 // one scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
-                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, nullptr, 0, 0, N, true,
+                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, 0, N, true,
                             FUF_CRIT_ROUNDING, qg, 2.9e-3, refine_budget);
                 if (rc) return rc;
             }
@@ -144,12 +143,12 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
                                            (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
             }
         } else if (!validate) {
-            rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, s1, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk, D_zc,
-                              ldd, (int32_t)band_tile[b], (int32_t)band_tile[b + 1]);
+            rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, s1, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk,
+                              (int32_t)band_tile[b], (int32_t)band_tile[b + 1]);
             if (rc) return rc;
             if (do_refine) {
-                rc = refine(ctx, P64T, s1, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, D_zc, ldd, s0, s1,
-                            b == 0, FUF_CRIT_ROUNDING, nullptr, 0.0, refine_budget);
+                rc = refine(ctx, P64T, s1, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, s0, s1, b == 0,
+                            FUF_CRIT_ROUNDING, nullptr, 0.0, refine_budget);
                 if (rc) return rc;
             }
             if (band_d2h && !use_gram) {
@@ -166,13 +165,13 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             }
         }
     }
-    if (validate) rc = pairwise_f64(ctx, (const double *)ctx->ws_p.ptr, N, ldp, mode, D_dev, N, sk);
+    if (validate) rc = pairwise_f64(ctx, (const double *)ctx->ws_p.ptr, N, ldp, 0, 0, mode, nullptr, 0, D_dev, N, sk);
     if (band_d2h) {  // the compute stream's end event waits for the last band copy
         FUF_CUDA(cudaEventRecord(e_band[0], sd));
         FUF_CUDA(cudaStreamWaitEvent(sk, e_band[0], 0));
     }
     if (rc) return rc;
-    if (!band_d2h && D_zc == nullptr)
+    if (!band_d2h)
         FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
                                    (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
     FUF_CUDA(cudaEventRecord(e_end, sk));
@@ -189,7 +188,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         if ((int64_t)v > refine_budget) {
             // too many pairs for per-pair recomputation (e.g. --unweighted --L2, or a data set of near-duplicates):
             // the float64 tile kernel over the float64 profiles gives every pair at validation accuracy
-            rc = pairwise_f64(ctx, P64T, N, ldp, mode, D_dev, N, sk);
+            rc = pairwise_f64(ctx, P64T, N, ldp, 0, 0, mode, nullptr, 0, D_dev, N, sk);
             if (rc) return rc;
             FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
                                        (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));

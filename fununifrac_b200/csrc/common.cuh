@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/fununifrac.h"
@@ -61,6 +62,26 @@ struct PinnedBuffer {
     void release();
 };
 
+// Small read-only device tables (tile lists, tile-row lists, slot tables), keyed by the parameters / content they
+// were built from.  A table is uploaded once with a blocking copy and then reused: the launches that need it never
+// synchronise the stream for a host-to-device copy of pageable planning data.
+struct TableCache {
+    std::unordered_map<std::string, void *> map;
+    size_t bytes = 0;
+    void *find(const std::string &key) const;
+    // uploads `host` under `key` (a miss is assumed); *d_out = device pointer
+    int put(const std::string &key, const void *host, size_t nbytes, void **d_out);
+    // find, else put with the content itself as the key
+    int get_by_content(const char *tag, const void *host, size_t nbytes, void **d_out);
+    void release();
+};
+
+template <typename T>
+inline void key_append(std::string &key, const T &v)
+{
+    key.append(reinterpret_cast<const char *>(&v), sizeof(T));
+}
+
 }  // namespace fuf
 
 struct fuf_ctx {
@@ -99,7 +120,7 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_p64;      // P64T + centre + error statistics (fuf_all_pairs_host)
     unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine
     int64_t last_refined = 0;
-    fuf::PinnedBuffer pin_x;       // pinned staging when X_h is pageable
+    fuf::TableCache tables;        // cached device copies of host-planned tables
     cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_gram[2] = {};       // around the last gram_tile_kernel launch
@@ -125,10 +146,10 @@ int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int
 // pairwise.cu
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int32_t col_tile_begin = 0,
-                 int32_t col_tile_end = 0, int32_t n_rows_override = 0, int32_t flush_stages = 0);
-int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int32_t col_tile_begin = 0, int32_t col_tile_end = 0, int32_t n_rows_override = 0,
+                 int32_t flush_stages = 0);
+int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
+                 const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,
              double *D, int64_t ldd, cudaStream_t stream);
 int pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_t *tile_rows_h, const int64_t *offsets_h,
@@ -144,9 +165,8 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
 // refine.cu
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
-           int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0, int64_t j_begin = 0,
-           int64_t j_end = 0, bool reset_counter = true, int criterion = 0, const double *lin_stat = nullptr,
-           double lin_kappa = 0.0, int64_t max_pairs = 0);
+           int64_t ldd, cudaStream_t stream, int64_t j_begin = 0, int64_t j_end = 0, bool reset_counter = true,
+           int criterion = 0, const double *lin_stat = nullptr, double lin_kappa = 0.0, int64_t max_pairs = 0);
 // diffab.cu
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
                  int64_t pair_end, void *out, int out_dtype, cudaStream_t stream);

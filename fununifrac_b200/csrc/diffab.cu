@@ -7,33 +7,45 @@
 // The host turns the dense rows into the reference's COO (and its negated transpose).
 //
 // K4 diffab_kernel (bound by the link to wherever `out` lives: HBM, or PCIe for pinned host memory):
-// pairs of one row i with 32 consecutive j form a block; the node-major profiles are read coalesced
-// along j, transposed through shared memory, and written coalesced along k (128 B per warp store).
+// 32 consecutive pairs form a block (within a row i the j are consecutive); the node-major profiles are read
+// coalesced along j, transposed through shared memory, and written coalesced along k (128 B per warp store).
+// With float64 profiles and a float32 output the subtraction is done in double and rounded once.
 #include "common.cuh"
 
 namespace fuf {
 
-struct DiffabBlock {
-    int32_t i, j0, count;   // pairs (i, j0 .. j0+count-1), count <= 32
-    int32_t pad;
-    int64_t out_pair;       // index of the first pair of the block in the output
-};
+// pair index (itertools.combinations order) -> (i, j): row i owns pairs [off(i), off(i+1)), off(i) = i N - i (i+1) / 2
+__device__ __forceinline__ void pair_of_index(int64_t p, int64_t N, int32_t &i_out, int32_t &j_out)
+{
+    const double b = 2.0 * (double)N - 1.0;
+    int64_t i = (int64_t)floor((b - sqrt(b * b - 8.0 * (double)p)) * 0.5);
+    i = max((int64_t)0, min(i, N - 2));
+    while (i > 0 && i * N - i * (i + 1) / 2 > p) i--;
+    while ((i + 1) * N - (i + 1) * (i + 2) / 2 <= p) i++;
+    i_out = (int32_t)i;
+    j_out = (int32_t)(p - (i * N - i * (i + 1) / 2) + i + 1);
+}
 
+// One block = 32 consecutive pairs x 32 consecutive nodes; the pair -> (i, j) map is evaluated in the kernel, so the
+// launch needs no host-built table (and no synchronisation to upload one).
 template <typename TP, typename TO, int MODE>
 __global__ void __launch_bounds__(256)
-diffab_kernel(const DiffabBlock *__restrict__ blocks, const TP *__restrict__ P, int64_t ldp, int32_t n,
+diffab_kernel(int64_t pair_begin, int64_t pair_end, int64_t N, const TP *__restrict__ P, int64_t ldp, int32_t n,
               TO *__restrict__ out)
 {
     __shared__ TP tile[32][33];
-    const DiffabBlock b = blocks[blockIdx.x];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int64_t p0 = pair_begin + (int64_t)blockIdx.x * 32;
+    const int count = (int)min((int64_t)32, pair_end - p0);
     const int32_t k0 = blockIdx.y * 32;
+    int32_t i = 0, j = 0;
+    if (lx < count) pair_of_index(p0 + lx, N, i, j);
     for (int kk = ly; kk < 32; kk += 8) {
         const int32_t k = k0 + kk;
         TP d = TP(0);
-        if (k < n && lx < b.count) {
-            const TP a = P[(int64_t)k * ldp + b.i];
-            const TP q = P[(int64_t)k * ldp + b.j0 + lx];
+        if (k < n && lx < count) {
+            const TP a = P[(int64_t)k * ldp + i];
+            const TP q = P[(int64_t)k * ldp + j];
             d = a - q;
             if (MODE == FUF_MODE_L2) d = d * d;
         }
@@ -42,7 +54,7 @@ diffab_kernel(const DiffabBlock *__restrict__ blocks, const TP *__restrict__ P, 
     __syncthreads();
     const int32_t k = k0 + lx;
     if (k < n)
-        for (int q = ly; q < b.count; q += 8) out[(b.out_pair + q) * (int64_t)n + k] = (TO)tile[lx][q];
+        for (int q = ly; q < count; q += 8) out[(p0 - pair_begin + q) * (int64_t)n + k] = (TO)tile[lx][q];
 }
 
 int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t ldp, int mode, int64_t pair_begin,
@@ -53,47 +65,17 @@ int diffab_block(fuf_ctx *ctx, const void *PT, int p_dtype, int64_t N, int64_t l
                 "fuf_diffab_block: pair range [%lld,%lld) outside [0,%lld)", (long long)pair_begin,
                 (long long)pair_end, (long long)total);
     if (pair_begin == pair_end) return FUF_OK;
-    // enumerate blocks: row i owns pairs [off(i), off(i+1)), off(i) = i*N - i*(i+1)/2
-    std::vector<DiffabBlock> blocks;
-    int64_t i = 0;
-    {
-        int64_t lo = 0, hi = N - 1;  // largest i with off(i) <= pair_begin
-        while (lo < hi) {
-            int64_t mid = (lo + hi + 1) / 2;
-            if (mid * N - mid * (mid + 1) / 2 <= pair_begin) lo = mid; else hi = mid - 1;
-        }
-        i = lo;
-    }
-    int64_t p = pair_begin;
-    while (p < pair_end) {
-        const int64_t off = i * N - i * (i + 1) / 2, row_end = off + (N - 1 - i);
-        if (p >= row_end) {
-            i++;
-            continue;
-        }
-        const int64_t stop = std::min(row_end, pair_end);
-        while (p < stop) {
-            const int32_t cnt = (int32_t)std::min<int64_t>(32, stop - p);
-            blocks.push_back(DiffabBlock{(int32_t)i, (int32_t)(i + 1 + (p - off)), cnt, 0, p - pair_begin});
-            p += cnt;
-        }
-        i++;
-    }
-    int rc = ctx->ws_pair.reserve(blocks.size() * sizeof(DiffabBlock));
-    if (rc) return rc;
-    DiffabBlock *d_blocks = (DiffabBlock *)ctx->ws_pair.ptr;
-    FUF_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(DiffabBlock), cudaMemcpyHostToDevice,
-                             stream));
-    FUF_CUDA(cudaStreamSynchronize(stream));
-    dim3 grid((unsigned)blocks.size(), (unsigned)((ctx->n + 31) / 32));
+    const int64_t n_blocks = (pair_end - pair_begin + 31) / 32;
+    FUF_REQUIRE(n_blocks < ((int64_t)1 << 31), "fuf_diffab_block: too many pairs for one call");
+    dim3 grid((unsigned)n_blocks, (unsigned)((ctx->n + 31) / 32));
     FUF_REQUIRE(grid.y <= 65535, "fuf_diffab_block: tree too large");
     const int32_t n = ctx->n;
 #define LAUNCH(TP, TO)                                                                                       \
     do {                                                                                                     \
         if (mode == FUF_MODE_L1)                                                                             \
-            diffab_kernel<TP, TO, FUF_MODE_L1><<<grid, 256, 0, stream>>>(d_blocks, (const TP *)PT, ldp, n, (TO *)out); \
+            diffab_kernel<TP, TO, FUF_MODE_L1><<<grid, 256, 0, stream>>>(pair_begin, pair_end, N, (const TP *)PT, ldp, n, (TO *)out); \
         else                                                                                                 \
-            diffab_kernel<TP, TO, FUF_MODE_L2><<<grid, 256, 0, stream>>>(d_blocks, (const TP *)PT, ldp, n, (TO *)out); \
+            diffab_kernel<TP, TO, FUF_MODE_L2><<<grid, 256, 0, stream>>>(pair_begin, pair_end, N, (const TP *)PT, ldp, n, (TO *)out); \
     } while (0)
     if (p_dtype == FUF_F32 && out_dtype == FUF_F32) LAUNCH(float, float);
     else if (p_dtype == FUF_F32 && out_dtype == FUF_F64) LAUNCH(float, double);

@@ -52,8 +52,6 @@ struct PairParams {
     int64_t N;
     double *D;
     int64_t ldd;
-    double *D2;                // optional second destination (zero-copy host mirror of D), same indexing
-    int64_t ldd2;
     double *partial;           // [n_items][TILE*TILE] when splits > 1
 };
 
@@ -296,7 +294,6 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
                     if (gi0 + r < p.N) {
                         const double v = acc64[slot_of(r, col)];
                         p.D[((int64_t)td.out_row0 + r) * p.ldd + gj0 + col] = v;
-                        if (p.D2) p.D2[((int64_t)td.out_row0 + r) * p.ldd2 + gj0 + col] = v;
                     }
             }
             if (td.mirror && gi0 + col < p.N) {
@@ -304,7 +301,6 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
                     if (gj0 + c < p.N) {
                         const double v = acc64[slot_of(col, c)];
                         p.D[(gj0 + c) * p.ldd + gi0 + col] = v;
-                        if (p.D2) p.D2[(gj0 + c) * p.ldd2 + gi0 + col] = v;
                     }
             }
         }
@@ -315,7 +311,7 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
 // Sum the k-split partial tiles in fixed order and write D (+ mirror).
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restrict__ partial, int splits, int64_t N,
-                       double *__restrict__ D, int64_t ldd, double *__restrict__ D2, int64_t ldd2)
+                       double *__restrict__ D, int64_t ldd)
 {
     const TileDesc td = tiles[blockIdx.x];
     const double *src = partial + (size_t)blockIdx.x * splits * (TILE * TILE);
@@ -330,19 +326,13 @@ reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restr
             for (int s = 0; s < splits; s++) v += src[(size_t)s * (TILE * TILE) + (r0 + rr) * TILE + c0 + lx];
             tile[rr][lx] = v;
             const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
-            if (gi < N && gj < N) {
-                D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
-                if (D2) D2[((int64_t)td.out_row0 + r0 + rr) * ldd2 + gj] = v;
-            }
+            if (gi < N && gj < N) D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
         }
         __syncthreads();
         if (td.mirror) {
             for (int cc = ly; cc < 32; cc += 8) {
                 const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;
-                if (gi < N && gj < N) {
-                    D[gj * ldd + gi] = tile[lx][cc];
-                    if (D2) D2[gj * ldd2 + gi] = tile[lx][cc];
-                }
+                if (gi < N && gj < N) D[gj * ldd + gi] = tile[lx][cc];
             }
         }
         __syncthreads();
@@ -355,21 +345,35 @@ reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restr
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256)
-pairwise_f64_kernel(const double *__restrict__ P, int64_t ldp, int64_t N, int32_t n, double *__restrict__ D, int64_t ldd)
+pairwise_f64_kernel(const double *__restrict__ P, int64_t ldp, int64_t shard, int64_t shard_stride, int64_t N, int32_t n,
+                    const int32_t *__restrict__ tile_rows, double *__restrict__ D, int64_t ldd)
 {
     constexpr int T = 64, KB = 16;
     __shared__ double As[KB][T], Bs[KB][T];
-    const int ti = blockIdx.y, tj = blockIdx.x;
-    if (tj < ti) return;
+    // full matrix: blockIdx.y = 64-row tile, output row = sample row, mirror written too;
+    // tile rows: blockIdx.y = half of a compact 128-row block, output row = compact row, upper part only
+    int64_t i0, out0;
+    if (tile_rows) {
+        const int32_t t = tile_rows[blockIdx.y >> 1];
+        if (t < 0) return;
+        i0 = (int64_t)t * TILE + (blockIdx.y & 1) * T;
+        out0 = (int64_t)blockIdx.y * T;
+    } else {
+        i0 = out0 = (int64_t)blockIdx.y * T;
+    }
+    const int64_t j0 = (int64_t)blockIdx.x * T;
+    if (j0 + T <= i0 || i0 >= N) return;   // entirely below the diagonal / beyond the samples
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t i0 = (int64_t)ti * T, j0 = (int64_t)tj * T;
+    // node-major operand, single block (shard == 0: column s at P[k * ldp + s]) or all-gathered shards [G][n][shard]
+    const int64_t kstride = shard ? shard : ldp;
+    auto col = [&](int64_t s) { return shard ? (s / shard) * shard_stride + s % shard : s; };
     double acc[4][4] = {};
     for (int32_t k0 = 0; k0 < n; k0 += KB) {
         for (int e = tid; e < KB * T; e += 256) {
             const int kk = e / T, c = e % T;
             const int32_t k = k0 + kk;
-            As[kk][c] = (k < n && i0 + c < N) ? P[(int64_t)k * ldp + i0 + c] : 0.0;
-            Bs[kk][c] = (k < n && j0 + c < N) ? P[(int64_t)k * ldp + j0 + c] : 0.0;
+            As[kk][c] = (k < n && i0 + c < N) ? P[(int64_t)k * kstride + col(i0 + c)] : 0.0;
+            Bs[kk][c] = (k < n && j0 + c < N) ? P[(int64_t)k * kstride + col(j0 + c)] : 0.0;
         }
         __syncthreads();
 #pragma unroll 4
@@ -393,10 +397,10 @@ pairwise_f64_kernel(const double *__restrict__ P, int64_t ldp, int64_t N, int32_
     for (int m = 0; m < 4; m++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int64_t i = i0 + tx * 4 + m, j = j0 + ty * 4 + q;
+            const int64_t r = tx * 4 + m, i = i0 + r, j = j0 + ty * 4 + q;
             if (i < N && j < N) {
-                D[i * ldd + j] = acc[m][q];
-                D[j * ldd + i] = acc[m][q];
+                D[(out0 + r) * ldd + j] = acc[m][q];
+                if (!tile_rows) D[j * ldd + i] = acc[m][q];
             }
         }
 }
@@ -465,8 +469,8 @@ static EncodeTiledFn get_encode_fn()
 
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
-                 cudaStream_t stream, double *D2, int64_t ldd2, int32_t col_tile_begin, int32_t col_tile_end,
-                 int32_t n_rows_override, int32_t flush_stages)
+                 cudaStream_t stream, int32_t col_tile_begin, int32_t col_tile_end, int32_t n_rows_override,
+                 int32_t flush_stages)
 {
     if (N == 0) return FUF_OK;
     if (flush_stages <= 0) flush_stages = FLUSH_STAGES;
@@ -516,27 +520,49 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
         return FUF_ECUDA;
     }
 
-    // ---- tile list ------------------------------------------------------------------------------
-    std::vector<TileDesc> tiles;
+    // ---- tile list: built once per (N, rows, column band), kept on the device (ctx->tables) ----------
     const bool full = (tile_rows_h == nullptr);
     const int32_t n_rows = full ? (int32_t)tiles_per_dim : n_tile_rows;
-    if (full && col_tile_end > 0) {
-        // column band [col_tile_begin, col_tile_end) of the upper triangle (the host-buffer path computes the
-        // matrix band by band while later samples are still in flight over PCIe)
-        const int32_t ce = std::min<int32_t>(col_tile_end, (int32_t)tiles_per_dim);
-        for (int32_t tj = std::max(0, col_tile_begin); tj < ce; tj++)
-            for (int32_t t = 0; t <= tj; t++) tiles.push_back(TileDesc{t, tj, t * TILE, tj != t ? 1 : 0});
+    const bool band = full && col_tile_end > 0;
+    const int32_t cb = band ? std::max(0, col_tile_begin) : 0;
+    const int32_t ce = band ? std::min<int32_t>(col_tile_end, (int32_t)tiles_per_dim) : 0;
+    int32_t n_tiles = 0;
+    if (band) {
+        for (int32_t tj = cb; tj < ce; tj++) n_tiles += tj + 1;
     } else {
         for (int32_t c = 0; c < n_rows; c++) {
             const int32_t t = full ? c : tile_rows_h[c];
             FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise: tile row %d out of range [0,%lld)", t,
                         (long long)tiles_per_dim);
-            for (int32_t tj = t; tj < tiles_per_dim; tj++)
-                tiles.push_back(TileDesc{t, tj, full ? t * TILE : c * TILE, (full && tj != t) ? 1 : 0});
+            n_tiles += (int32_t)tiles_per_dim - t;
         }
     }
-    const int32_t n_tiles = (int32_t)tiles.size();
     if (n_tiles == 0) return FUF_OK;
+    std::string key("pw");
+    key_append(key, tiles_per_dim);
+    key_append(key, cb);
+    key_append(key, ce);
+    key_append(key, n_rows);
+    if (!full) key.append((const char *)tile_rows_h, (size_t)n_rows * sizeof(int32_t));
+    TileDesc *d_tiles = (TileDesc *)ctx->tables.find(key);
+    if (!d_tiles) {
+        std::vector<TileDesc> tiles;
+        tiles.reserve(n_tiles);
+        if (band) {
+            // column band [cb, ce) of the upper triangle (the host-buffer path computes the matrix band by band
+            // while later samples are still in flight over PCIe)
+            for (int32_t tj = cb; tj < ce; tj++)
+                for (int32_t t = 0; t <= tj; t++) tiles.push_back(TileDesc{t, tj, t * TILE, tj != t ? 1 : 0});
+        } else {
+            for (int32_t c = 0; c < n_rows; c++) {
+                const int32_t t = full ? c : tile_rows_h[c];
+                for (int32_t tj = t; tj < tiles_per_dim; tj++)
+                    tiles.push_back(TileDesc{t, tj, full ? t * TILE : c * TILE, (full && tj != t) ? 1 : 0});
+            }
+        }
+        int rc = ctx->tables.put(key, tiles.data(), tiles.size() * sizeof(TileDesc), (void **)&d_tiles);
+        if (rc) return rc;
+    }
 
     // ---- k-splits: minimise the makespan over the SMs ------------------------------------------------
     const int32_t stages_total = (n + KC - 1) / KC;
@@ -560,15 +586,12 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     per_split = (per_split + flush_stages - 1) / flush_stages * flush_stages;
     const int32_t splits = (stages_total + per_split - 1) / per_split;  // no empty split
 
-    size_t tiles_bytes = ((size_t)n_tiles * sizeof(TileDesc) + 255) & ~(size_t)255;
-    size_t partial_bytes = splits > 1 ? (size_t)n_tiles * splits * TILE * TILE * sizeof(double) : 0;
-    int rc = ctx->ws_pair.reserve(tiles_bytes + partial_bytes);
-    if (rc) return rc;
-    TileDesc *d_tiles = (TileDesc *)ctx->ws_pair.ptr;
-    double *d_partial = splits > 1 ? (double *)((char *)ctx->ws_pair.ptr + tiles_bytes) : nullptr;
-    FUF_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, stream));
-    // the tile list lives in pageable host memory: make sure the copy has read it before `tiles` dies
-    FUF_CUDA(cudaStreamSynchronize(stream));
+    double *d_partial = nullptr;
+    if (splits > 1) {
+        int rc = ctx->ws_pair.reserve((size_t)n_tiles * splits * TILE * TILE * sizeof(double));
+        if (rc) return rc;
+        d_partial = (double *)ctx->ws_pair.ptr;
+    }
 
     PairParams p;
     p.tiles = d_tiles;
@@ -581,8 +604,6 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     p.N = N;
     p.D = D;
     p.ldd = ldd;
-    p.D2 = D2;
-    p.ldd2 = ldd2;
     p.partial = d_partial;
 
     const bool packed = !(flags & FUF_PW_SCALAR_MATH);
@@ -597,23 +618,29 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
     if (splits > 1) {
-        reduce_partials_kernel<<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd, D2, ldd2);
+        reduce_partials_kernel<<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
     return FUF_OK;
 }
 
-int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
-                 cudaStream_t stream)
+int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
+                 const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, cudaStream_t stream)
 {
     if (N == 0) return FUF_OK;
     const unsigned t = (unsigned)((N + 63) / 64);
-    dim3 grid(t, t);
+    const int32_t *d_rows = nullptr;
+    if (tile_rows_h) {
+        if (n_tile_rows == 0) return FUF_OK;
+        int rc = ctx->tables.get_by_content("rows", tile_rows_h, (size_t)n_tile_rows * sizeof(int32_t), (void **)&d_rows);
+        if (rc) return rc;
+    }
+    dim3 grid(t, tile_rows_h ? 2u * (unsigned)n_tile_rows : t);
     if (mode == FUF_MODE_L1)
-        pairwise_f64_kernel<FUF_MODE_L1><<<grid, 256, 0, stream>>>(P64T, ldp, N, ctx->n, D, ldd);
+        pairwise_f64_kernel<FUF_MODE_L1><<<grid, 256, 0, stream>>>(P64T, ldp, shard, shard_stride, N, ctx->n, d_rows, D, ldd);
     else
-        pairwise_f64_kernel<FUF_MODE_L2><<<grid, 256, 0, stream>>>(P64T, ldp, N, ctx->n, D, ldd);
+        pairwise_f64_kernel<FUF_MODE_L2><<<grid, 256, 0, stream>>>(P64T, ldp, shard, shard_stride, N, ctx->n, d_rows, D, ldd);
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return FUF_OK;
@@ -736,11 +763,9 @@ int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int
     for (int32_t c = 0; c < n_blocks; c++)
         FUF_REQUIRE(tile_rows_h[c] >= -1 && tile_rows_h[c] < tiles_per_dim, "fuf_assemble: tile row %d out of range",
                     tile_rows_h[c]);
-    int rc = ctx->ws_pair.reserve((size_t)n_blocks * sizeof(int32_t));
+    int32_t *d_rows = nullptr;
+    int rc = ctx->tables.get_by_content("rows", tile_rows_h, (size_t)n_blocks * sizeof(int32_t), (void **)&d_rows);
     if (rc) return rc;
-    int32_t *d_rows = (int32_t *)ctx->ws_pair.ptr;
-    FUF_CUDA(cudaMemcpyAsync(d_rows, tile_rows_h, (size_t)n_blocks * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    FUF_CUDA(cudaStreamSynchronize(stream));
     dim3 grid((unsigned)tiles_per_dim, (unsigned)n_blocks);
     assemble_kernel<<<grid, 256, 0, stream>>>(blocks, d_rows, N, ldb, D, ldd);
     FUF_CUDA(cudaGetLastError());
@@ -749,7 +774,7 @@ int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int
 }
 
 static int upload_packed_slots(fuf_ctx *ctx, const char *who, const int32_t *tile_rows_h, const int64_t *offsets_h,
-                               int32_t n_blocks, int64_t N, cudaStream_t stream, PackedSlot **d_slots)
+                               int32_t n_blocks, int64_t N, PackedSlot **d_slots)
 {
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
     std::vector<PackedSlot> slots((size_t)n_blocks);
@@ -759,13 +784,7 @@ static int upload_packed_slots(fuf_ctx *ctx, const char *who, const int32_t *til
         FUF_REQUIRE(tile_rows_h[c] < 0 || offsets_h[c] >= 0, "%s: negative offset", who);
         slots[c] = PackedSlot{tile_rows_h[c], 0, offsets_h[c]};
     }
-    int rc = ctx->ws_rows.reserve(slots.size() * sizeof(PackedSlot));
-    if (rc) return rc;
-    FUF_CUDA(cudaMemcpyAsync(ctx->ws_rows.ptr, slots.data(), slots.size() * sizeof(PackedSlot), cudaMemcpyHostToDevice,
-                             stream));
-    FUF_CUDA(cudaStreamSynchronize(stream));
-    *d_slots = (PackedSlot *)ctx->ws_rows.ptr;
-    return FUF_OK;
+    return ctx->tables.get_by_content("packed", slots.data(), slots.size() * sizeof(PackedSlot), (void **)d_slots);
 }
 
 int pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_t *tile_rows_h, const int64_t *offsets_h,
@@ -773,7 +792,7 @@ int pack_tile_rows(fuf_ctx *ctx, const double *blocks, int64_t ldb, const int32_
 {
     if (n_blocks == 0 || N == 0) return FUF_OK;
     PackedSlot *d_slots = nullptr;
-    int rc = upload_packed_slots(ctx, "fuf_pack_tile_rows", tile_rows_h, offsets_h, n_blocks, N, stream, &d_slots);
+    int rc = upload_packed_slots(ctx, "fuf_pack_tile_rows", tile_rows_h, offsets_h, n_blocks, N, &d_slots);
     if (rc) return rc;
     dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)n_blocks);
     pack_tile_rows_kernel<<<grid, 256, 0, stream>>>(blocks, d_slots, N, ldb, packed);
@@ -787,7 +806,7 @@ int assemble_packed(fuf_ctx *ctx, const double *packed, const int32_t *tile_rows
 {
     if (n_blocks == 0 || N == 0) return FUF_OK;
     PackedSlot *d_slots = nullptr;
-    int rc = upload_packed_slots(ctx, "fuf_assemble_packed", tile_rows_h, offsets_h, n_blocks, N, stream, &d_slots);
+    int rc = upload_packed_slots(ctx, "fuf_assemble_packed", tile_rows_h, offsets_h, n_blocks, N, &d_slots);
     if (rc) return rc;
     dim3 grid((unsigned)((N + TILE - 1) / TILE), (unsigned)n_blocks);
     assemble_packed_kernel<<<grid, 256, 0, stream>>>(packed, d_slots, N, D, ldd);
@@ -809,14 +828,12 @@ int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_
         slots[c] = PanelSlot{t, 0, total};
         if (t >= 0) total += std::max<int64_t>(0, N - (int64_t)(t + 1) * TILE) * TILE;
     }
-    int rc = ctx->ws_rows.reserve(slots.size() * sizeof(PanelSlot));
+    PanelSlot *d_slots = nullptr;
+    int rc = ctx->tables.get_by_content("panel", slots.data(), slots.size() * sizeof(PanelSlot), (void **)&d_slots);
     if (rc) return rc;
     rc = ctx->ws_panel.reserve((size_t)std::max<int64_t>(total, 1) * sizeof(double));
     if (rc) return rc;
-    PanelSlot *d_slots = (PanelSlot *)ctx->ws_rows.ptr;
     double *panels = (double *)ctx->ws_panel.ptr;
-    FUF_CUDA(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(PanelSlot), cudaMemcpyHostToDevice, stream));
-    FUF_CUDA(cudaStreamSynchronize(stream));
     dim3 grid((unsigned)tiles_per_dim, (unsigned)n_blocks);
     mirror_panels_kernel<<<grid, 256, 0, stream>>>(blocks, d_slots, N, ldb, panels);
     FUF_CUDA(cudaGetLastError());
@@ -855,18 +872,28 @@ extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ld
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_f32(ctx, PT, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd, flags,
-                        (cudaStream_t)stream, nullptr, 0, 0, 0, 0, 0);
+                        (cudaStream_t)stream, 0, 0, 0, 0);
 }
 
-extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D,
-                                int64_t ldd, void *stream)
+extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int64_t shard,
+                                int64_t shard_stride, int mode, const int32_t *tile_rows_h, int32_t n_tile_rows,
+                                double *D, int64_t ldd, void *stream)
 {
     FUF_REQUIRE(ctx && P64T && D, "fuf_pairwise_f64: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_pairwise_f64: bad mode %d", mode);
-    FUF_REQUIRE(N >= 0 && ldd >= N && ldp >= N, "fuf_pairwise_f64: bad shape N=%lld ldp=%lld ldd=%lld", (long long)N,
-                (long long)ldp, (long long)ldd);
+    FUF_REQUIRE(N >= 0 && ldd >= N, "fuf_pairwise_f64: bad shape N=%lld ldd=%lld", (long long)N, (long long)ldd);
+    if (shard == 0)
+        FUF_REQUIRE(ldp >= N, "fuf_pairwise_f64: ldp=%lld < N=%lld", (long long)ldp, (long long)N);
+    else
+        FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_pairwise_f64: bad shard layout");
+    FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise_f64: n_tile_rows without tile_rows_h");
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    for (int32_t c = 0; c < n_tile_rows; c++)
+        FUF_REQUIRE(tile_rows_h[c] >= -1 && tile_rows_h[c] < tiles_per_dim, "fuf_pairwise_f64: tile row %d out of range",
+                    tile_rows_h[c]);
     FUF_CUDA(cudaSetDevice(ctx->device));
-    return pairwise_f64(ctx, P64T, N, ldp, mode, D, ldd, (cudaStream_t)stream);
+    return pairwise_f64(ctx, P64T, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd,
+                        (cudaStream_t)stream);
 }
 
 extern "C" int fuf_assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,

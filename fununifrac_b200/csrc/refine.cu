@@ -29,8 +29,6 @@ struct RefineParams {
     int32_t n_rows_total;      // rows to scan (N, or n_tile_rows * 128)
     double *D;
     int64_t ldd;
-    double *D2;                // optional second destination (zero-copy host mirror), write-only
-    int64_t ldd2;
     int mirror;                // also write D[j,i]
     int64_t j_begin, j_end;    // only pairs with j in [j_begin, j_end) are examined
     int linear;                // criterion D < kappa (s_i + s_j) on the raw statistic, whatever the mode
@@ -134,10 +132,6 @@ refine_kernel(const RefineParams p)
                 if (lane == 0) {
                     drow[j] = v;
                     if (p.mirror) p.D[j * p.ldd + gi] = v;
-                    if (p.D2) {
-                        p.D2[row * p.ldd2 + j] = v;
-                        if (p.mirror) p.D2[j * p.ldd2 + gi] = v;
-                    }
                 }
             }
         }
@@ -146,8 +140,8 @@ refine_kernel(const RefineParams p)
 
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
-           int64_t ldd, cudaStream_t stream, double *D2, int64_t ldd2, int64_t j_begin, int64_t j_end,
-           bool reset_counter, int criterion, const double *lin_stat, double lin_kappa, int64_t max_pairs)
+           int64_t ldd, cudaStream_t stream, int64_t j_begin, int64_t j_end, bool reset_counter, int criterion,
+           const double *lin_stat, double lin_kappa, int64_t max_pairs)
 {
     if (!ctx->d_refined) FUF_CUDA(cudaMalloc((void **)&ctx->d_refined, sizeof(unsigned long long)));
     if (reset_counter) FUF_CUDA(cudaMemsetAsync(ctx->d_refined, 0, sizeof(unsigned long long), stream));
@@ -170,19 +164,15 @@ int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t s
     p.kappa = kappa > 0 ? kappa : (p.linear ? 0.02 : (mode == FUF_MODE_L2 ? 1.6e13 : 2e6));
     p.D = D;
     p.ldd = ldd;
-    p.D2 = D2;
-    p.ldd2 = ldd2;
     p.counter = ctx->d_refined;
     p.j_begin = j_begin;
     p.j_end = j_end;
     if (tile_rows_h) {
         if (n_tile_rows == 0) return FUF_OK;
-        int rc = ctx->ws_rows.reserve((size_t)n_tile_rows * sizeof(int32_t));
+        void *d_rows = nullptr;
+        int rc = ctx->tables.get_by_content("rows", tile_rows_h, (size_t)n_tile_rows * sizeof(int32_t), &d_rows);
         if (rc) return rc;
-        FUF_CUDA(cudaMemcpyAsync(ctx->ws_rows.ptr, tile_rows_h, (size_t)n_tile_rows * sizeof(int32_t),
-                                 cudaMemcpyHostToDevice, stream));
-        FUF_CUDA(cudaStreamSynchronize(stream));  // tile_rows_h may be pageable and short-lived
-        p.tile_rows = (const int32_t *)ctx->ws_rows.ptr;
+        p.tile_rows = (const int32_t *)d_rows;
         p.n_rows_total = n_tile_rows * FUF_TILE;
         p.mirror = 0;
     } else {
@@ -222,7 +212,7 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
         FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine: bad shard layout");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
-                  (cudaStream_t)stream, nullptr, 0, 0, N, true, criterion, lin_stat, lin_kappa, max_pairs);
+                  (cudaStream_t)stream, 0, N, true, criterion, lin_stat, lin_kappa, max_pairs);
 }
 
 extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)

@@ -77,6 +77,50 @@ void PinnedBuffer::release()
     bytes = 0;
 }
 
+void *TableCache::find(const std::string &key) const
+{
+    auto it = map.find(key);
+    return it == map.end() ? nullptr : it->second;
+}
+
+int TableCache::put(const std::string &key, const void *host, size_t nbytes, void **d_out)
+{
+    if (map.size() >= 512 || bytes + nbytes > ((size_t)256 << 20)) release();  // cudaFree waits for the device
+    void *d = nullptr;
+    FUF_CUDA(cudaMalloc(&d, nbytes ? nbytes : 1));
+    if (nbytes) {
+        cudaError_t err = cudaMemcpy(d, host, nbytes, cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) {
+            cudaFree(d);
+            set_error("table upload (%zu bytes) failed: %s", nbytes, cudaGetErrorString(err));
+            return FUF_ECUDA;
+        }
+    }
+    map.emplace(key, d);
+    bytes += nbytes;
+    *d_out = d;
+    return FUF_OK;
+}
+
+int TableCache::get_by_content(const char *tag, const void *host, size_t nbytes, void **d_out)
+{
+    std::string key(tag);
+    key.push_back('\0');
+    key.append(static_cast<const char *>(host), nbytes);
+    if (void *d = find(key)) {
+        *d_out = d;
+        return FUF_OK;
+    }
+    return put(key, host, nbytes, d_out);
+}
+
+void TableCache::release()
+{
+    for (auto &kv : map) cudaFree(kv.second);
+    map.clear();
+    bytes = 0;
+}
+
 template <typename T>
 static int upload(T **dst, const std::vector<T> &src)
 {
@@ -321,7 +365,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     ctx->ws_x.release();
     ctx->ws_p.release();
     ctx->ws_d.release();
-    ctx->pin_x.release();
+    ctx->tables.release();
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);

@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 9
+ABI_VERSION = 10
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -74,7 +74,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
-        L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, vp]
+        L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, vp]
         L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
         L.fuf_pack_tile_rows.argtypes = [vp, vp, i64, vp, vp, i32, i64, vp, vp]
         L.fuf_assemble_packed.argtypes = [vp, vp, vp, vp, i32, i64, vp, i64, vp]
@@ -370,7 +370,9 @@ class TreeContext:
         (upper part only, see ``fuf_pairwise``).  ``PT`` may be [n, ldp] or, with ``shard``, [G, n, shard].
         """
         torch = _torch()
-        assert PT.dtype == torch.float32 and PT.is_contiguous() or PT.stride(-1) == 1
+        if PT.dtype != torch.float32 or PT.stride(-1) != 1:
+            raise TypeError(f"fuf_pairwise takes float32 profiles with unit inner stride, got {PT.dtype} "
+                            f"with strides {tuple(PT.stride())} (float64 profiles go to pairwise_f64)")
         rows_arr = None
         if tile_rows is not None:
             rows_arr = np.ascontiguousarray(tile_rows, dtype=np.int32)
@@ -385,13 +387,22 @@ class TreeContext:
                                       _stream_ptr(torch)), "fuf_pairwise")
         return D
 
-    def pairwise_f64(self, P64T, N: int, mode: int, D=None):
+    def pairwise_f64(self, P64T, N: int, mode: int, D=None, tile_rows: Optional[Sequence[int]] = None, shard: int = 0,
+                     shard_stride: int = 0):
+        """``fuf_pairwise_f64``: float64 kernel in the reference's operation order; layouts and ``tile_rows`` as in
+        ``pairwise``."""
         torch = _torch()
-        assert P64T.dtype == torch.float64 and P64T.stride(1) == 1
+        if P64T.dtype != torch.float64 or P64T.stride(-1) != 1:
+            raise TypeError(f"fuf_pairwise_f64 takes float64 profiles with unit inner stride, got {P64T.dtype}")
+        rows_arr = None if tile_rows is None else np.ascontiguousarray(tile_rows, dtype=np.int32)
         if D is None:
-            D = torch.zeros((N, N), dtype=torch.float64, device=P64T.device)
-        _check(self._lib.fuf_pairwise_f64(self.handle, P64T.data_ptr(), N, P64T.stride(0), mode, D.data_ptr(),
-                                          D.stride(0), _stream_ptr(torch)), "fuf_pairwise_f64")
+            nrows = N if rows_arr is None else len(rows_arr) * TILE
+            D = torch.zeros((nrows, N), dtype=torch.float64, device=P64T.device)
+        ldp = P64T.stride(0) if shard == 0 else 0
+        _check(self._lib.fuf_pairwise_f64(self.handle, P64T.data_ptr(), N, ldp, shard, shard_stride, mode,
+                                          rows_arr.ctypes.data if rows_arr is not None else None,
+                                          0 if rows_arr is None else len(rows_arr), D.data_ptr(), D.stride(0),
+                                          _stream_ptr(torch)), "fuf_pairwise_f64")
         return D
 
     def assemble(self, blocks, tile_rows: Sequence[int], N: int, D=None):
@@ -531,9 +542,11 @@ class Pushed:
 # ---------------------------------------------------------------------------------------------------
 
 def context_for(input, device: Optional[int] = None) -> TreeContext:
-    """Tree context cached on a ``FuncTreeEmduInput``; rebuilt when its dicts change in size or the edge lengths
-    change in sum (a C-speed checksum: 0.3 ms for the full KO tree, against ~10 ms for re-densifying the dicts)."""
-    key = (len(input.basis), len(input.lint), device, sum(input.lint.values()))
+    """Tree context cached on a ``FuncTreeEmduInput``; rebuilt when the parent map or any edge length changes.  The key
+    hashes the value sequences of both dicts (order-sensitive, so swapping two lengths is seen; C speed: ~1 ms for the
+    full KO tree, against ~10 ms for re-densifying the dicts)."""
+    key = (len(input.basis), len(input.lint), device, hash(tuple(input.lint.values())),
+           hash(tuple(input.Tint.values())))
     cached = input.__dict__.get("_fuf_ctx")
     if cached is not None and cached[0] == key and cached[1]._h:
         return cached[1]

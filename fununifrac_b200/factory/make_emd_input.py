@@ -222,8 +222,9 @@ def native_profiles_to_matrix(fun_files, input: FuncTreeEmduInput, abundance_key
                               normalize=True, out: Optional[np.ndarray] = None) -> Tuple[List[str], np.ndarray]:
     """All gather CSVs → dense X[N, n] through the native ingest (``fuf_ingest_gather_csv``, csrc/ingest.cu): a C++
     thread pool that tokenises only the ``name`` and abundance columns of each file.  Row f is bit-for-bit what
-    ``functional_profile_to_vector(pd.read_csv(fun_files[f]), input, abundance_key)`` returns; warnings are printed
-    and errors raised as the reference does, for the first failing file in ``fun_files`` order."""
+    ``functional_profile_to_vector(pd.read_csv(fun_files[f]), input, abundance_key)`` returns (pinned on 800+ number
+    formats, quoting, duplicates, NA); a file the native parser reports as malformed is re-read through that very
+    pandas route, so odd inputs behave — return or raise — exactly as in the reference."""
     import ctypes
 
     from fununifrac_b200 import engine
@@ -251,8 +252,23 @@ def native_profiles_to_matrix(fun_files, input: FuncTreeEmduInput, abundance_key
                                      X.strides[0] // 8 if N else n, status.ctypes.data, messages, stride, warnings, wcap)
         if rc < 0:
             engine._check(rc, "fuf_ingest_gather_csv")
+        # Inputs the native tokeniser rejects or reads differently from pandas (bool / '1_0' / overflowing abundances,
+        # rows with an extra field = pandas' implicit index column, numeric names, an all-NaN profile ...) are rare and
+        # cheap to hand to the reference's own route: whatever pandas + functional_profile_to_vector return or raise
+        # for that file is then, by construction, the reference's behaviour.
+        redo = {f for f in range(N) if status[f] in (1, 2, 3, 4)}
         for line in warnings.value.decode("utf-8", "replace").splitlines():
-            print(f"Warning: {line.split(chr(9), 1)[1]} not found in EMDU index, skipping.")
+            fidx, ko = line.split(chr(9), 1)
+            if int(fidx) not in redo:
+                print(f"Warning: {ko} not found in EMDU index, skipping.")
+        for f in sorted(redo):
+            import pandas as pd
+            P = functional_profile_to_vector(pd.read_csv(fun_files[f]), input, abundance_key=abundance_key,
+                                             normalize=normalize)
+            if unweighted:
+                P[P > 0] = 1
+            X[f, :n] = P
+            status[f] = 0
         for f in range(N):
             if status[f]:
                 msg = messages.raw[f * stride:(f + 1) * stride].split(b"\0", 1)[0].decode("utf-8", "replace")

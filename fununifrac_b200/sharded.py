@@ -58,6 +58,12 @@ def packed_offsets(rows: Sequence[int], N: int):
     return offsets, total
 
 
+def refine_budget(N: int) -> int:
+    """Pairs worth recomputing one by one (0.1 % of all pairs, at least 1,024); more than that and the float64 tile kernel
+    is cheaper."""
+    return max(1024, N * (N - 1) // 2 // 1000)
+
+
 def tiles_of(rows: Sequence[int], N: int) -> int:
     T = (N + TILE - 1) // TILE
     return sum(T - t for t in rows)
@@ -171,7 +177,13 @@ class ShardedAllPairs:
         ops, r, sh = self.ops, self.rank, self.shard
         self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
         if self.rows:
-            ops.refine(self.P64S, self.N, self.mode, stat, self.blocks, self.rows, sh, ops.n * sh, lin)
+            # per-pair recomputation costs ~1 us, the float64 tile kernel ~3 ns per pair: beyond 0.1 % of the pairs
+            # (the count is global, every rank takes the same branch) the float64 kernel redoes this rank's rows —
+            # the same budget rule as the one-GPU paths (engine._refine_or_redo, fuf_all_pairs_host)
+            if self.last_flagged > refine_budget(self.N):
+                ops.pairwise_f64(self.P64S, self.N, self.mode, self.rows, sh, ops.n * sh, self.blocks)
+            else:
+                ops.refine(self.P64S, self.N, self.mode, stat, self.blocks, self.rows, sh, ops.n * sh, lin)
         return True
 
     def step(self, X_local, mark=None):
@@ -335,6 +347,9 @@ class CudaOps:
     def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, lin_stat=None):
         return self.ctx.refine(P64T, N, mode, err_stat, D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride,
                                lin_stat=lin_stat, lin_kappa=2.9e-3)
+
+    def pairwise_f64(self, P64T, N, mode, tile_rows, shard, shard_stride, D):
+        return self.ctx.pairwise_f64(P64T, N, mode, D=D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)
 
     def count_uncertified_into(self, N, mode, err_stat, D, tile_rows, lin_stat, out):
         self.ctx.refine(None, N, mode, err_stat, D, tile_rows=tile_rows, lin_stat=lin_stat, lin_kappa=2.9e-3)

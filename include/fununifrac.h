@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 9
+#define FUF_ABI_VERSION 10
 
 /* error codes */
 #define FUF_OK 0
@@ -190,9 +190,13 @@ int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_flops);
 /* Scale buckets and float64-bypassed node columns of the last fuf_pairwise_gram call. */
 int fuf_gram_last_info(const fuf_ctx *ctx, int32_t *n_buckets, int32_t *n_bypassed);
 
-/* Validation mode: everything in double. Full matrix only. */
-int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int mode, double *D, int64_t ldd,
-                     void *stream);
+/* Validation mode: everything in double, the reference's operation order per entry (subtract, abs / square, add; no
+ * FMA contraction).  Same P64T layouts (single block: ldp; all-gathered shards: shard, shard_stride) and the same
+ * D / tile_rows_h conventions as fuf_pairwise: tile_rows_h == NULL -> full symmetric matrix; otherwise compact
+ * 128-row blocks, upper part only — what the multi-GPU path uses when too many pairs are flagged for per-pair
+ * refinement. */
+int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
+                     int mode, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, void *stream);
 
 /* Float64 refinement of what fuf_pairwise wrote into D (same D / tile_rows_h / shard conventions; P64T laid out
  * like PT): every pair i<j with

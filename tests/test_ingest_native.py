@@ -101,13 +101,50 @@ def test_errors_like_the_reference(toy, tmp_path, data_dir, capsys):
         make_emd_input.native_profiles_to_matrix([good], toy, "no_such_key", False, 1)
     with pytest.raises(KeyError):
         python_rows([good], toy, "no_such_key")
-    with pytest.raises(Exception, match="cannot open"):
+    with pytest.raises(FileNotFoundError):       # re-read through pandas: the reference's own exception
         make_emd_input.native_profiles_to_matrix([str(tmp_path / "missing.csv")], toy, "median_abund", False, 1)
     # NA abundance -> NaN propagates exactly as in the reference (nan sum is not == 0, so no "empty" error)
     na = write_csv(str(tmp_path / "na_gather.csv"), [("ko:d", "3"), ("ko:e", "NA"), ("ko:f", "")])
     want = python_rows([na], toy, "median_abund")
     got = make_emd_input.native_profiles_to_matrix([na], toy, "median_abund", False, 1)[1]
     assert np.isnan(want).all() and np.isnan(got).all()
+    capsys.readouterr()
+
+
+def _outcome(fn):
+    try:
+        return "ok", fn()
+    except Exception as e:  # noqa: BLE001
+        return type(e).__name__, str(e)
+
+
+def test_odd_inputs_behave_like_the_pandas_route(toy, tmp_path, capsys):
+    """Inputs the native tokeniser is stricter on than pandas (all-bool abundances, '1_0', overflowing exponents, an
+    extra field per row = pandas' implicit index column, numeric names): the file is re-read through the reference's
+    route, so the observable outcome — the row, or the exception type and message — is the same."""
+    cases = {
+        "bool": [("ko:d", "True"), ("ko:e", "False")],
+        "underscore": [("ko:d", "1_0"), ("ko:e", "abc")],
+        "overflow": [("ko:d", "1e400"), ("ko:e", "2")],
+        "numeric_names": [("17", "3"), ("42", "2")],
+    }
+    for tag, rows in cases.items():
+        path = write_csv(str(tmp_path / f"{tag}_gather.csv"), rows)
+        kind_py, val_py = _outcome(lambda: python_rows([path], toy, "median_abund"))
+        kind_nat, val_nat = _outcome(lambda: make_emd_input.native_profiles_to_matrix([path], toy, "median_abund", False, 1)[1])
+        assert kind_py == kind_nat, (tag, kind_py, val_py, kind_nat, val_nat)
+        if kind_py == "ok":
+            assert np.array_equal(val_py, val_nat, equal_nan=True), tag
+        else:
+            assert val_py == val_nat, tag
+    # one extra field in every data row: pandas takes the first column as the index
+    path = write_csv(str(tmp_path / "extra_gather.csv"), [("ko:d", "3"), ("ko:e", "2")])
+    lines = open(path).read().splitlines()
+    with open(path, "w") as f:
+        f.write("\n".join([lines[0]] + [ln + ",9" for ln in lines[1:]]) + "\n")
+    kind_py, val_py = _outcome(lambda: python_rows([path], toy, "median_abund"))
+    kind_nat, val_nat = _outcome(lambda: make_emd_input.native_profiles_to_matrix([path], toy, "median_abund", False, 1)[1])
+    assert kind_py == kind_nat and (kind_py != "ok" or np.array_equal(val_py, val_nat, equal_nan=True))
     capsys.readouterr()
 
 

@@ -94,6 +94,10 @@ class OracleOps:
         assert P64T.shape[0] * P64T.shape[2] >= N and err_stat.numel() >= N
         return D
 
+    def pairwise_f64(self, P64T, N, mode, tile_rows, shard, shard_stride, D):
+        self.f64_calls = getattr(self, "f64_calls", 0) + 1
+        return self.pairwise(P64T, N, mode, tile_rows, shard, shard_stride, D)
+
     def assemble(self, blocks, rows, N, D):
         blocks = blocks.reshape(-1, blocks.shape[-1])
         for c, t in enumerate(rows):
