@@ -686,6 +686,82 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-pipe peak for THIS instruction mix (bench.py's roofline denominator, measured instead of assumed): the MMA
+// warp issues the same ten kind::i8 MMAs per 32 basis rows as the tile kernels, back to back, on operands that already
+// sit in shared memory (pseudo-random digits; no TMA, no epilogue, accumulators never read).  CTA_GROUP = 1: M = N = 128
+// per CTA; CTA_GROUP = 2: M = 256 over a CTA pair, N = 128.  Every SM runs one CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int CTA_GROUP>
+__global__ void __launch_bounds__(128, 1)
+i8_mma_peak_kernel(int32_t iters)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr uint32_t B_PLANE = CTA_GROUP == 1 ? PLANE_BYTES : PLANE_B2;
+    constexpr uint32_t OPER_BYTES = NDIG * PLANE_BYTES + NDIG * B_PLANE;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar = base + OPER_BYTES, tmem_slot = bar + 8;
+    unsigned char *oper = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(oper + OPER_BYTES + 8);
+    const int warp = threadIdx.x >> 5;
+    uint32_t rank = 0;
+    if (CTA_GROUP == 2) rank = cluster_ctarank();
+    for (uint32_t i = threadIdx.x; i < OPER_BYTES / 4; i += blockDim.x) {
+        uint32_t h = (i + 977u * blockIdx.x) * 2654435761u;
+        h ^= h >> 15;
+        reinterpret_cast<uint32_t *>(oper)[i] = h * 2246822519u;      // digits in [-128, 127]: any int8 is a valid operand
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        if (CTA_GROUP == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (CTA_GROUP == 2) cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    if (warp == 0 && rank == 0) {
+        const uint32_t a_lo = desc_lo(base), b_lo = a_lo + ((NDIG * PLANE_BYTES) >> 4);
+        for (int32_t it = 0; it < iters; it++) {
+            if (CTA_GROUP == 1) {
+                umma_block10(tmem_base, a_lo, b_lo);
+                umma_block10(tmem_base, a_lo + ((KB * TILE) >> 4), b_lo + ((KB * TILE) >> 4));
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int c = 0; c < NDIG; c++)
+#pragma unroll
+                        for (int x = 0; x <= c; x++)
+                            umma_i8_lo<2, DESC_HI_SW128, DESC_HI_SW64, IDESC2, 1>(
+                                tmem_base + c * TILE, a_lo + ((x * PLANE_BYTES) >> 4) + h * ((KB * TILE) >> 4),
+                                b_lo + (((c - x) * PLANE_B2) >> 4) + h * ((KB * 64) >> 4));
+            }
+        }
+        if (CTA_GROUP == 1) umma_commit(bar); else umma_commit_2sm(bar);
+    }
+    mbar_wait(bar, 0);     // every MMA above has completed
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (CTA_GROUP == 2) cluster_sync_all();
+    if (warp == 0) {
+        if (CTA_GROUP == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 // Per node column (one warp per row): cmax[k] = max_s |PT[k][s]|, nnz[k] = number of non-zero entries,
 // energy[k] = sum_s PT[k][s]^2 (fp32: it only steers the bypass heuristic).  Shard by shard, 16-byte loads, four of
 // them in flight per lane.
@@ -1235,6 +1311,54 @@ extern "C" int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_fl
     FUF_CUDA(cudaSetDevice(ctx->device));
     FUF_CUDA(cudaEventSynchronize(ctx->ev_gram[1]));
     FUF_CUDA(cudaEventElapsedTime(ms, ctx->ev_gram[0], ctx->ev_gram[1]));
+    return FUF_OK;
+}
+
+extern "C" int fuf_i8_mma_peak(fuf_ctx *ctx, int cta_group, int32_t iters, int32_t launches, float *ms,
+                               double *executed_ops, void *stream)
+{
+    using namespace gram;
+    FUF_REQUIRE(ctx && ms && executed_ops, "fuf_i8_mma_peak: null argument");
+    FUF_REQUIRE((cta_group == 1 || cta_group == 2) && iters > 0 && launches > 0, "fuf_i8_mma_peak: bad argument");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->ev_gram[0]) {
+        FUF_CUDA(cudaEventCreate(&ctx->ev_gram[0]));
+        FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
+    }
+    const int grid = cta_group == 1 ? ctx->sm_count : ctx->sm_count / 2 * 2;
+    const uint32_t smem = 200u << 10;   // operands need 48-64 KB; asking for 200 KB keeps it at one CTA (512 TMEM columns) per SM
+    if (cta_group == 1)
+        FUF_CUDA(cudaFuncSetAttribute(i8_mma_peak_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        FUF_CUDA(cudaFuncSetAttribute(i8_mma_peak_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], st));
+    for (int32_t l = 0; l < launches; l++) {
+        if (cta_group == 1) {
+            i8_mma_peak_kernel<1><<<grid, 128, smem, st>>>(iters);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(128);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            FUF_CUDA(cudaLaunchKernelEx(&cfg, i8_mma_peak_kernel<2>, iters));
+        }
+    }
+    FUF_CUDA(cudaGetLastError());
+    FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], st));
+    FUF_CUDA(cudaEventSynchronize(ctx->ev_gram[1]));
+    FUF_CUDA(cudaEventElapsedTime(ms, ctx->ev_gram[0], ctx->ev_gram[1]));
+    ctx->launches += launches;
+    // 20 MMAs per iteration; one MMA = M x N x K multiply-adds = 2 M N K ops (M = 128 per CTA either way)
+    *executed_ops = (double)launches * (double)iters * 20.0 * 2.0 * TILE * TILE * KB * (double)grid;
     return FUF_OK;
 }
 

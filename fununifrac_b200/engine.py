@@ -69,6 +69,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_pairwise_gram.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, vp, vp, vp, i32, vp, i64, vp]
         L.fuf_gram_last_kernel.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
         L.fuf_gram_last_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        L.fuf_i8_mma_peak.argtypes = [vp, ci, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double), vp]
         L.fuf_refine_count.argtypes = [vp, ctypes.POINTER(i64), vp]
         L.fuf_refine_count_device.argtypes = [vp, vp, vp]
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
@@ -92,7 +93,7 @@ def load_library() -> ctypes.CDLL:
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",
                      "fuf_push_up_center", "fuf_center_of_pushed", "fuf_round_pushed", "fuf_refine", "fuf_refine_count", "fuf_refine_count_device",
-                     "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_name_index_create",
+                     "fuf_pairwise_gram", "fuf_gram_last_kernel", "fuf_gram_last_info", "fuf_i8_mma_peak", "fuf_name_index_create",
                      "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
                      "fuf_diffab_gather", "fuf_store_tile_rows_host", "fuf_pack_tile_rows", "fuf_assemble_packed",
@@ -294,6 +295,14 @@ class TreeContext:
         a, b = ctypes.c_int32(), ctypes.c_int32()
         _check(self._lib.fuf_gram_last_info(self.handle, ctypes.byref(a), ctypes.byref(b)), "fuf_gram_last_info")
         return a.value, b.value
+
+    def i8_mma_peak(self, cta_group: int = 2, iters: int = 4096, launches: int = 1) -> Tuple[float, float]:
+        """``fuf_i8_mma_peak``: (milliseconds, executed int8 ops) of ``launches`` launches of the MMA-only kernel."""
+        torch = _torch()
+        ms, ops = ctypes.c_float(), ctypes.c_double()
+        _check(self._lib.fuf_i8_mma_peak(self.handle, cta_group, iters, launches, ctypes.byref(ms), ctypes.byref(ops),
+                                         _stream_ptr(torch)), "fuf_i8_mma_peak")
+        return ms.value, ops.value
 
     def distances_gram(self, job: "Pushed", D=None):
         """--L2 through the Gram kernel + both refinement passes (needs a job pushed with refine=True)."""

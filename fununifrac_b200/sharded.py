@@ -113,6 +113,15 @@ class ShardedAllPairs:
                 self.slot_rows += self.all_rows[r]
                 self.slot_offs += [r * self.max_packed + o for o in packed_offsets(self.all_rows[r], N)[0]]
 
+    def pushup_bytes_per_entry(self, x_itemsize: int) -> int:
+        """HBM bytes the push-up of this job has to move per (sample, node): the profile entry in, the centred fp32
+        entry out, and — when the float64 profiles are kept for the refinement pass — the float64 entry out."""
+        return x_itemsize + 4 + (8 if self.P64S is not None else 0)
+
+    def release_device_matrix(self):
+        """Drop the device-resident result matrix of ``step`` (world == 1); ``step`` allocates it again on demand."""
+        self.D = None
+
     def _pairwise(self, rows, D):
         """Distances of this rank's tile rows (all rows when ``rows`` is None) into D; returns the refinement
         statistics of the refinement scan to run afterwards: (rounding statistic, linear statistic or None)."""
@@ -139,6 +148,8 @@ class ShardedAllPairs:
                         self.stat[r * sh:(r + 1) * sh])
         mark("push_end")
         if self.world == 1:
+            if self.D is None:
+                self.D = ops.empty((N, N), "float64")
             mark("pair_begin")
             stat, lin = self._pairwise(None, self.D)
             mark("pair_end")

@@ -190,6 +190,14 @@ int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_flops);
 /* Scale buckets and float64-bypassed node columns of the last fuf_pairwise_gram call. */
 int fuf_gram_last_info(const fuf_ctx *ctx, int32_t *n_buckets, int32_t *n_bypassed);
 
+/* Measurement aid (no counterpart in the reference): the tensor-pipe rate of the Gram kernels' own instruction mix —
+ * `launches` back-to-back launches in which every SM's MMA warp issues iters x 20 tcgen05.mma kind::i8 (M = 128 per
+ * CTA, N = 128, K = 32; cta_group 1 or 2) on operands resident in shared memory: no TMA, no epilogue.  *ms = device
+ * time of all launches, *executed_ops = 2 x multiply-adds issued.  bench.py uses it as the roofline denominator of
+ * fuf_pairwise_gram (a short call for the burst rate, a seconds-long one for the power-capped sustained rate). */
+int fuf_i8_mma_peak(fuf_ctx *ctx, int cta_group, int32_t iters, int32_t launches, float *ms, double *executed_ops,
+                    void *stream);
+
 /* Validation mode: everything in double, the reference's operation order per entry (subtract, abs / square, add; no
  * FMA contraction).  Same P64T layouts (single block: ldp; all-gathered shards: shard, shard_stride) and the same
  * D / tile_rows_h conventions as fuf_pairwise: tile_rows_h == NULL -> full symmetric matrix; otherwise compact
