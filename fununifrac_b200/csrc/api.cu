@@ -62,14 +62,12 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
 
     int rc;
     if ((rc = ctx->ws_p.reserve((size_t)n * ldp * psz))) return rc;
-    double *P64T = nullptr, *center = nullptr, *stat = nullptr;
+    double *center = nullptr, *stat = nullptr;
     if (!validate) {
-        // centre [n] | error statistic [ldp] | Gram norms [ldp] | Gram error statistic [ldp] | P64T [n][ldp] (if refining)
-        const size_t head = ((size_t)n + 3 * (size_t)ldp) * sizeof(double);
-        if ((rc = ctx->ws_p64.reserve(head + (do_refine ? (size_t)n * ldp * sizeof(double) : 0)))) return rc;
+        // centre [n] | error statistic [ldp] | Gram norms [ldp] | Gram error statistic [ldp]
+        if ((rc = ctx->ws_p64.reserve(((size_t)n + 3 * (size_t)ldp) * sizeof(double)))) return rc;
         center = (double *)ctx->ws_p64.ptr;
         stat = center + n;
-        if (do_refine) P64T = stat + 3 * ldp;
     }
     // The whole X gets a device copy (no staging ring: the copy stream never waits for compute).  Samples are
     // cut into up to 16 bands of whole 128-sample tiles; band b is copied on the copy stream, and as soon as it has
@@ -80,7 +78,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     int nb = (validate || use_gram) ? 1 : (int)std::min<int64_t>(16, std::max<int64_t>(1, tiles_per_dim / 4));
     if (getenv("FUF_HOST_BANDS")) nb = std::max(1, std::min(64, atoi(getenv("FUF_HOST_BANDS"))));
     nb = (int)std::min<int64_t>(nb, tiles_per_dim);
-    if ((rc = ctx->ws_x.reserve((size_t)N * n * esz))) return rc;
+    // device copy of X with a 16-byte aligned row pitch (what the TMA push-up kernel's tensor map needs), whatever n is
+    const int64_t ldx_dev = ((int64_t)n * (int64_t)esz + 15) / 16 * 16 / (int64_t)esz;
+    if ((rc = ctx->ws_x.reserve((size_t)N * ldx_dev * esz))) return rc;
     const bool d_pinned = is_pinned_host(D_h);
     if ((rc = ctx->ws_d.reserve((size_t)N * N * sizeof(double)))) return rc;
     double *D_dev = (double *)ctx->ws_d.ptr;
@@ -105,7 +105,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     for (int b = 0; b < nb; b++) {  // all copies are queued up front
         const int64_t s0 = band_tile[b] * 128, s1 = std::min<int64_t>(N, band_tile[b + 1] * 128);
         if (s1 > s0)
-            FUF_CUDA(cudaMemcpy2DAsync((char *)ctx->ws_x.ptr + (size_t)s0 * n * esz, (size_t)n * esz,
+            FUF_CUDA(cudaMemcpy2DAsync((char *)ctx->ws_x.ptr + (size_t)s0 * ldx_dev * esz, (size_t)ldx_dev * esz,
                                        (const char *)X_h + (size_t)s0 * ldx * esz, (size_t)ldx * esz, (size_t)n * esz,
                                        (size_t)(s1 - s0), cudaMemcpyHostToDevice, sc));
         FUF_CUDA(cudaEventRecord(e_band[b], sc));
@@ -114,16 +114,18 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         const int64_t s0 = band_tile[b] * 128, s1 = std::min<int64_t>(N, band_tile[b + 1] * 128);
         FUF_CUDA(cudaStreamWaitEvent(sk, e_band[b], 0));
         if (s1 <= s0) continue;
-        const char *xb = (const char *)ctx->ws_x.ptr + (size_t)s0 * n * esz;
+        const char *xb = (const char *)ctx->ws_x.ptr + (size_t)s0 * ldx_dev * esz;
         if (validate) {
-            rc = push_up_f64_exact(ctx, (const double *)xb, s1 - s0, n, mode, (double *)ctx->ws_p.ptr, ldp, s0, sk);
+            rc = push_up_f64_exact(ctx, (const double *)xb, s1 - s0, ldx_dev, mode, (double *)ctx->ws_p.ptr, ldp, s0, sk);
         } else {
             if (b == 0) {  // the centre of the whole job: pushed mean of the first few samples
-                rc = push_up_center(ctx, xb, x_dtype, std::min<int64_t>(s1 - s0, FUF_CENTER_SAMPLES), n, mode, center, sk);
+                rc = push_up_center(ctx, xb, x_dtype, std::min<int64_t>(s1 - s0, FUF_CENTER_SAMPLES), ldx_dev, mode, center, sk);
                 if (rc) return rc;
             }
-            rc = push_up_f32(ctx, xb, x_dtype, s1 - s0, n, mode, center, (float *)ctx->ws_p.ptr, ldp, P64T, ldp, stat,
-                             s0, sk);
+            // fp32 operands + statistics only: the float64 profiles are produced further down, and only if some pair
+            // turns out to need them
+            rc = push_up_f32(ctx, xb, x_dtype, s1 - s0, ldx_dev, mode, center, (float *)ctx->ws_p.ptr, ldp, nullptr, 0,
+                             stat, s0, sk);
         }
         if (rc) return rc;
         if (b == 0) FUF_CUDA(cudaEventRecord(e_push, sk));
@@ -133,9 +135,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, 0, 0, stat, qg, eg, nullptr, 0, D_dev, N, sk);
             if (rc) return rc;
             if (do_refine) {
-                // one scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
-                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, 0, N, true,
-                            FUF_CRIT_ROUNDING, qg, 2.9e-3, refine_budget);
+                // one counting scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
+                rc = refine(ctx, nullptr, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, 0, N, true,
+                            FUF_CRIT_ROUNDING, qg, 2.9e-3, 0);
                 if (rc) return rc;
             }
             if (band_d2h) {
@@ -146,9 +148,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, s1, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk,
                               (int32_t)band_tile[b], (int32_t)band_tile[b + 1]);
             if (rc) return rc;
-            if (do_refine) {
-                rc = refine(ctx, P64T, s1, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, s0, s1, b == 0,
-                            FUF_CRIT_ROUNDING, nullptr, 0.0, refine_budget);
+            if (do_refine) {   // counting scan of the band: which pairs can the fp32 operands not certify?
+                rc = refine(ctx, nullptr, s1, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, s0, s1, b == 0,
+                            FUF_CRIT_ROUNDING, nullptr, 0.0, 0);
                 if (rc) return rc;
             }
             if (band_d2h && !use_gram) {
@@ -185,10 +187,25 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         unsigned long long v = 0;
         FUF_CUDA(cudaMemcpy(&v, ctx->d_refined, sizeof(v), cudaMemcpyDeviceToHost));
         ctx->last_refined = (int64_t)v;
-        if ((int64_t)v > refine_budget) {
-            // too many pairs for per-pair recomputation (e.g. --unweighted --L2, or a data set of near-duplicates):
-            // the float64 tile kernel over the float64 profiles gives every pair at validation accuracy
-            rc = pairwise_f64(ctx, P64T, N, ldp, 0, 0, mode, nullptr, 0, D_dev, N, sk);
+        if (v > 0) {
+            // Some pairs (near-duplicate samples) need float64 operands.  Only now are the float64 profiles produced
+            // — one more push-up of the resident X, in the reference's operation order — and the flagged pairs
+            // recomputed; beyond the budget (e.g. --unweighted --L2, or a data set of near-duplicates) the float64 tile
+            // kernel redoes the whole matrix instead.  The finished matrix then crosses PCIe once more.
+            if ((rc = ctx->ws_p64t.reserve((size_t)n * ldp * sizeof(double)))) return rc;
+            double *P64T = (double *)ctx->ws_p64t.ptr;
+            rc = push_up_f32(ctx, ctx->ws_x.ptr, x_dtype, N, ldx_dev, mode, nullptr, nullptr, 0, P64T, ldp, nullptr, 0, sk);
+            if (rc) return rc;
+            if ((int64_t)v > refine_budget) {
+                rc = pairwise_f64(ctx, P64T, N, ldp, 0, 0, mode, nullptr, 0, D_dev, N, sk);
+            } else if (use_gram) {
+                double *qg = stat + ldp, *eg = qg + ldp;
+                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, 0, N, true, FUF_CRIT_ROUNDING,
+                            qg, 2.9e-3, 0);
+            } else {
+                rc = refine(ctx, P64T, N, ldp, 0, 0, mode, stat, 0.0, nullptr, 0, D_dev, N, sk, 0, N, true,
+                            FUF_CRIT_ROUNDING, nullptr, 0.0, 0);
+            }
             if (rc) return rc;
             FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
                                        (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));

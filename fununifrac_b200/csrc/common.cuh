@@ -46,6 +46,18 @@ struct SpanNode {
     int32_t slot_k;      // checkpoint slot with the chunk-local prefix sum up to k (inclusive)
 };
 
+// Per-node record of the TMA push-up kernel (pushup.cu): the weight and the packed plan word in one 16-byte load.
+//   bit 0      leaf-like: the subtree is the node itself, S = x
+//   bit 1      skip: spanning node (written by the span kernel) or padding beyond the tree
+//   bit 2      save the chunk-local prefix after this node (an internal node further on starts right after it)
+//   bits 8-13  b: the subtree starts at chunk-local index b (S = prefix - saved prefix[b - 1]; b = 0: S = prefix)
+//   bits 16-31 checkpoint slot + 1 for the span kernel (0 = none)
+struct PushNode {
+    double w;
+    int32_t meta;
+    int32_t pad;
+};
+
 // Grow-only device buffer owned by a context.
 struct DeviceBuffer {
     void *ptr = nullptr;
@@ -76,6 +88,12 @@ struct TableCache {
     void release();
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda); nullptr if unavailable
+EncodeTiledFn tensor_map_encoder();
+
 template <typename T>
 inline void key_append(std::string &key, const T &v)
 {
@@ -104,6 +122,7 @@ struct fuf_ctx {
     uint8_t *d_is_span = nullptr;       // 1 if node k is a spanning node (written by the fix-up kernel)
     uint8_t *d_has_child = nullptr;     // 1 for internal nodes (the centre is zero on leaves)
     fuf::SpanNode *d_span = nullptr;
+    fuf::PushNode *d_push_node[2] = {nullptr, nullptr};  // [mode][n_chunks * 32] (TMA push-up kernel), null if unusable
     int32_t n_chunks = 0, n_span = 0, n_cp = 0;
 
     // scratch
@@ -117,7 +136,8 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_panel;    // transposed tile panels of fuf_store_tile_rows_host
     fuf::DeviceBuffer ws_gram;     // int8 digit planes + tables of fuf_pairwise_gram
     fuf::DeviceBuffer ws_gram_small;  // column maxima
-    fuf::DeviceBuffer ws_p64;      // P64T + centre + error statistics (fuf_all_pairs_host)
+    fuf::DeviceBuffer ws_p64;      // centre + error statistics (fuf_all_pairs_host)
+    fuf::DeviceBuffer ws_p64t;     // float64 pushed profiles, only when a pair has to be refined (fuf_all_pairs_host)
     unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine
     int64_t last_refined = 0;
     fuf::TableCache tables;        // cached device copies of host-planned tables

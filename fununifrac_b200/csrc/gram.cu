@@ -934,29 +934,9 @@ __global__ void gram_stat_kernel(const double *__restrict__ r2part, const double
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
 static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_rows, const Lay &ws, uint32_t box_samples = TILE)
 {
-    EncodeTiledFn encode = get_encode_fn();
+    EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) {
         set_error("fuf_pairwise_gram: cuTensorMapEncodeTiled is not available from this driver");
         return FUF_ECUDA;

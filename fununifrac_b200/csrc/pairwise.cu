@@ -447,26 +447,6 @@ assemble_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ t
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
                  cudaStream_t stream, int32_t col_tile_begin, int32_t col_tile_end, int32_t n_rows_override,
@@ -480,7 +460,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     FUF_REQUIRE(tiles_per_dim < (1 << 20), "fuf_pairwise: N too large");
 
     // ---- TMA descriptor over PT: dims (sample-in-shard, node, shard) -------------------------
-    EncodeTiledFn encode = get_encode_fn();
+    EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) {
         set_error("fuf_pairwise: cuTensorMapEncodeTiled is not available from this driver");
         return FUF_ECUDA;

@@ -29,6 +29,9 @@
 //
 // Validation path (fuf_push_up_f64): transpose to node-major double, then one thread per sample replays the
 // reference loop verbatim -> bit-identical to the reference's float64 result.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fuf {
@@ -118,6 +121,190 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
     }
     if (T) T[(int64_t)blockIdx.x * ldt + s] = r;
     if (R) R[(int64_t)blockIdx.x * ldt + s] = err;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1t pushup_tma_kernel: the production push-up when only the centred fp32 profiles (+ statistics) are wanted.
+//   * persistent, warp-specialised: warp 8 is the TMA producer, warps 0-7 own 256 samples (one per thread);
+//   * work item = (block of 256 samples, group of 8 consecutive chunks); one pipeline stage = one chunk tile
+//     [256 samples x 32 nodes] of X brought in by cp.async.bulk.tensor.2d with SWIZZLE_128B (64 KB of float64 in two
+//     boxes of 16 nodes, or 32 KB of float32 in one) into a 3-stage ring guarded by full/empty mbarriers; rows and
+//     nodes beyond the matrix are zero-filled by the TMA unit;
+//   * a thread lifts its sample's 32 values with 16-byte shared loads (the swizzle makes a warp's 32 row reads hit
+//     all banks: 4 wavefronts per 512 bytes, the minimum), keeps a running prefix r over the chunk in a register and
+//     gets every subtree sum inside the chunk as S = x (leaf) or S = r - r[start - 1] (internal; the few prefixes
+//     that are needed again are parked in the thread's own row of the stage): no per-node read-modify-write of shared
+//     memory and no dependency chain through it.  The difference of two prefixes of at most 32 same-sign terms is
+//     accurate to ~1e-16 of the chunk's mass — far below the fp32 rounding of the output; the float64 profiles the
+//     refinement pass needs are produced on demand by the chunk kernel above, in the reference's operation order;
+//   * per node one 16-byte uniform load brings the weight and the packed plan word (PushNode); the centre is read for
+//     internal nodes only (it is zero on leaves);
+//   * stores: PT rows, 128 bytes per warp and node; chunk totals T and checkpoints CP for the span kernel; one
+//     rounding-error partial R per (group of 8 chunks, sample) — a fixed grouping, so the statistic does not depend
+//     on the launch geometry.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PT_SAMPLES = 256;                 // samples per tile = consumer threads
+constexpr int PT_GROUP = 8;                     // chunks per work item
+constexpr int PT_STAGES = 3;
+constexpr uint32_t PT_STAGE_BYTES = PT_SAMPLES * KT * sizeof(double);   // 64 KB (float32 input fills half of it)
+constexpr uint32_t PT_SMEM_BYTES = PT_STAGES * PT_STAGE_BYTES + 1024 /* alignment */ + 64 /* barriers */;
+
+struct PushTmaParams {
+    const PushNode *node;      // [n_chunks * 32]
+    const double *center;      // [n] or nullptr
+    float *PT;
+    int64_t ldp, col0, N, ldt;
+    int32_t n_chunks, n_groups, n_items;
+    double *T, *CP, *R;        // chunk totals, checkpoints (nullptr without spanning nodes), error partials (nullptr: none)
+};
+
+__device__ __forceinline__ uint32_t pu_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pu_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();   // a broken pipeline is a CUDA error, not a hung GPU
+    }
+}
+
+template <typename TX, int MODE, bool WANT_ERR>
+__global__ void __launch_bounds__(PT_SAMPLES + 32, 1)
+pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams p)
+{
+    extern __shared__ unsigned char pu_smem[];
+    const uint32_t base = (pu_smem_u32(pu_smem) + 1023u) & ~1023u;      // SWIZZLE_128B atoms sit on 1 KB boundaries
+    const uint32_t full0 = base + PT_STAGES * PT_STAGE_BYTES, empty0 = full0 + 8 * PT_STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < PT_STAGES; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(PT_SAMPLES / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr uint32_t TX_BYTES = PT_SAMPLES * KT * sizeof(TX);
+
+    if (warp == PT_SAMPLES / 32) {
+        // ===================== producer: one lane issues every TMA load =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sb = item / p.n_groups, g = item % p.n_groups;
+                const int c_end = min(p.n_chunks, (g + 1) * PT_GROUP);
+                for (int c = g * PT_GROUP; c < c_end; ++c, ++it) {
+                    const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
+                    pu_mbar_wait(empty0 + 8 * slot, phase ^ 1u);
+                    // the consumers wrote their scratch prefixes into this stage through the generic proxy
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t full = full0 + 8 * slot, dst = base + slot * PT_STAGE_BYTES;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(TX_BYTES) : "memory");
+                    constexpr int BOXES = sizeof(TX) == 8 ? 2 : 1;     // 128-byte inner box: 16 doubles or 32 floats
+#pragma unroll
+                    for (int bx = 0; bx < BOXES; bx++)
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                            ::"r"(dst + bx * (PT_SAMPLES * 128)), "l"(&tmap), "r"(full), "r"(c * KT + bx * 16),
+                            "r"(sb * PT_SAMPLES)
+                            : "memory");
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: thread = sample =====================
+    const uint32_t sw = (uint32_t)(tid & 7) << 4;                  // XOR term of this row's 16-byte units
+    const uint32_t row = (uint32_t)tid * 128u;
+    // parked prefix after chunk-local node q lives in this thread's own row: box q / 16, unit (q % 16) / 2, half q % 2
+    auto park_addr = [&](uint32_t stage, int q) {
+        return stage + (uint32_t)(q >> 4) * (PT_SAMPLES * 128) + row + ((((uint32_t)(q & 15) >> 1) << 4) ^ sw) + (uint32_t)(q & 1) * 8u;
+    };
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int sb = item / p.n_groups, g = item % p.n_groups;
+        const int c_end = min(p.n_chunks, (g + 1) * PT_GROUP);
+        const int64_t s = (int64_t)sb * PT_SAMPLES + tid;
+        const bool live = s < p.N;
+        double err = 0.0;
+        for (int c = g * PT_GROUP; c < c_end; ++c, ++it) {
+            const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
+            const uint32_t stage = base + slot * PT_STAGE_BYTES;
+            pu_mbar_wait(full0 + 8 * slot, phase);
+            double x[KT];
+            if (sizeof(TX) == 8) {
+#pragma unroll
+                for (int bx = 0; bx < 2; bx++)
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        double lo, hi;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                                     : "=d"(lo), "=d"(hi)
+                                     : "r"(stage + bx * (PT_SAMPLES * 128) + row + (((uint32_t)u << 4) ^ sw)));
+                        x[bx * 16 + 2 * u] = lo;
+                        x[bx * 16 + 2 * u + 1] = hi;
+                    }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    float a, b, cc, d;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(a), "=f"(b), "=f"(cc), "=f"(d)
+                                 : "r"(stage + row + (((uint32_t)u << 4) ^ sw)));
+                    x[4 * u] = (double)a, x[4 * u + 1] = (double)b, x[4 * u + 2] = (double)cc, x[4 * u + 3] = (double)d;
+                }
+            }
+            const PushNode *node = p.node + (int64_t)c * KT;
+            const int64_t k0 = (int64_t)c * KT;
+            float *pt = p.PT + k0 * p.ldp + p.col0 + s;
+            double r = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < KT; kk++) {
+                const int4 raw = __ldg(reinterpret_cast<const int4 *>(node + kk));     // uniform: one 16-byte request per warp
+                const double w = __hiloint2double(raw.y, raw.x);
+                const int32_t meta = raw.z;
+                r += x[kk];
+                if (meta & 4) asm volatile("st.shared.f64 [%0], %1;" ::"r"(park_addr(stage, kk)), "d"(r) : "memory");
+                if (!(meta & 2)) {
+                    double v;
+                    if (meta & 1) {
+                        v = w * x[kk];
+                    } else {
+                        const int b = (meta >> 8) & 63;
+                        double S = r;
+                        if (b > 0) {
+                            double parked;
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(parked) : "r"(park_addr(stage, b - 1)) : "memory");
+                            S = r - parked;
+                        }
+                        v = w * S;
+                        if (p.center) v -= __ldg(p.center + k0 + kk);
+                    }
+                    const float f = (float)v;
+                    if (live) pt[(int64_t)kk * p.ldp] = f;
+                    if (WANT_ERR) {
+                        const double e = v - (double)f;
+                        err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
+                    }
+                }
+                const int cp = (int)((uint32_t)meta >> 16);
+                if (cp && live) p.CP[(int64_t)(cp - 1) * p.ldt + s] = r;
+            }
+            if (p.T && live) p.T[(int64_t)c * p.ldt + s] = r;
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
+        }
+        if (WANT_ERR && live) p.R[(int64_t)g * p.ldt + s] = err;
+    }
 }
 
 // err_stat[col0 + s] = sum of the per-chunk error statistics R[c][s] and of the span kernel's per-block partials
@@ -354,11 +541,18 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
     const int64_t ldt = (N + 31) / 32 * 32;
     const bool want_err = (err_stat != nullptr && PT != nullptr);
     const int span_blocks = ctx->n_span > 0 ? min(ctx->n_span, 64) : 0;
+    // The TMA kernel serves the production case (fp32 output only); its X tile is a tensor-map box, which needs a
+    // 16-byte aligned base and row pitch.  Everything else (float64 output wanted, odd pitch) takes the chunk kernel.
+    const size_t esz = x_dtype == FUF_F32 ? 4 : 8;
+    const bool use_tma = PT != nullptr && P64T == nullptr && ctx->d_push_node[mode] != nullptr &&
+                         ((uintptr_t)X & 15) == 0 && ((size_t)ldx * esz) % 16 == 0 && !getenv("FUF_PUSHUP_NO_TMA") &&
+                         tensor_map_encoder() != nullptr;
+    const int32_t n_groups = (ctx->n_chunks + PT_GROUP - 1) / PT_GROUP;
     double *T = nullptr, *CP = nullptr, *R = nullptr, *R2 = nullptr;
     {
         size_t need = 0;
         if (ctx->n_span > 0) need += ((size_t)ctx->n_chunks + (size_t)ctx->n_cp) * (size_t)ldt * sizeof(double);
-        if (want_err) need += ((size_t)ctx->n_chunks + (size_t)span_blocks) * (size_t)ldt * sizeof(double);
+        if (want_err) need += ((size_t)(use_tma ? n_groups : ctx->n_chunks) + (size_t)span_blocks) * (size_t)ldt * sizeof(double);
         if (need) {
             int rc = ctx->ws_push.reserve(need);
             if (rc) return rc;
@@ -370,10 +564,51 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
             }
             if (want_err) {
                 R = base;
-                R2 = R + (size_t)ctx->n_chunks * ldt;
+                R2 = R + (size_t)(use_tma ? n_groups : ctx->n_chunks) * ldt;
             }
         }
     }
+    if (use_tma) {
+        CUtensorMap tmap;
+        const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)N}, gstride[1] = {(cuuint64_t)ldx * esz};
+        const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), PT_SAMPLES}, estr[2] = {1, 1};
+        CUresult cres = tensor_map_encoder()(&tmap, x_dtype == FUF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                             2, const_cast<void *>(X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cres != CUDA_SUCCESS) {
+            set_error("fuf_push_up: cuTensorMapEncodeTiled failed with CUresult %d (N=%lld n=%d ldx=%lld)", (int)cres,
+                      (long long)N, n, (long long)ldx);
+            return FUF_ECUDA;
+        }
+        PushTmaParams p;
+        p.node = ctx->d_push_node[mode];
+        p.center = center;
+        p.PT = PT;
+        p.ldp = ldp;
+        p.col0 = col0;
+        p.N = N;
+        p.ldt = ldt;
+        p.n_chunks = ctx->n_chunks;
+        p.n_groups = n_groups;
+        const int64_t n_sb = (N + PT_SAMPLES - 1) / PT_SAMPLES;
+        FUF_REQUIRE(n_sb * n_groups < ((int64_t)1 << 31), "fuf_push_up: N = %lld too large for one call", (long long)N);
+        p.n_items = (int32_t)(n_sb * n_groups);
+        p.T = T;
+        p.CP = CP;
+        p.R = want_err ? R : nullptr;
+        void (*kern)(const CUtensorMap, const PushTmaParams) = nullptr;
+#define FUF_TMA_KERN(TX)                                                                                             \
+    kern = mode == FUF_MODE_L1 ? (want_err ? pushup_tma_kernel<TX, 0, true> : pushup_tma_kernel<TX, 0, false>)        \
+                               : (want_err ? pushup_tma_kernel<TX, 1, true> : pushup_tma_kernel<TX, 1, false>)
+        if (x_dtype == FUF_F32) FUF_TMA_KERN(float); else FUF_TMA_KERN(double);
+#undef FUF_TMA_KERN
+        FUF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_BYTES));
+        const int grid_t = (int)std::min<int64_t>(p.n_items, ctx->sm_count);
+        kern<<<grid_t, PT_SAMPLES + 32, PT_SMEM_BYTES, stream>>>(tmap, p);
+        FUF_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+    } else {
     FUF_REQUIRE((N + TI - 1) / TI <= 65535, "fuf_push_up: N = %lld too large for one call (max %d)", (long long)N,
                 65535 * TI);
     dim3 grid(ctx->n_chunks, (unsigned)((N + TI - 1) / TI));
@@ -402,6 +637,7 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
 #undef FUF_CHUNK
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    }
     if (ctx->n_span > 0) {
         dim3 g2((unsigned)((N + 127) / 128), (unsigned)span_blocks);
         if (mode == FUF_MODE_L1)
@@ -414,8 +650,8 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
         ctx->launches += 1;
     }
     if (want_err) {
-        pushup_stat_kernel<<<(unsigned)((N + 31) / 32), 256, 0, stream>>>(R, ctx->n_chunks, R2, span_blocks, N, ldt,
-                                                                         err_stat, col0);
+        pushup_stat_kernel<<<(unsigned)((N + 31) / 32), 256, 0, stream>>>(R, use_tma ? n_groups : ctx->n_chunks, R2,
+                                                                         span_blocks, N, ldt, err_stat, col0);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }

@@ -121,6 +121,22 @@ void TableCache::release()
     bytes = 0;
 }
 
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
 template <typename T>
 static int upload(T **dst, const std::vector<T> &src)
 {
@@ -198,9 +214,50 @@ static void build_tree_plan(const int32_t *parent_h, int32_t n, TreePlan &plan)
     plan.n_cp = (int32_t)slot_of_pos.size();
 }
 
+// Plan words of the TMA push-up kernel (see PushNode in common.cuh), padded to whole chunks with "skip".
+static void build_push_meta(const TreePlan &plan, int32_t n, std::vector<int32_t> &meta)
+{
+    const int32_t KT = kPushChunk, padded = (n + KT - 1) / KT * KT;
+    std::vector<uint8_t> need_r(n, 0);
+    for (int32_t k = 0; k < n; k++)   // an internal node whose subtree starts inside its chunk, after node start - 1
+        if (!plan.is_span[k] && plan.start[k] != k && plan.start[k] % KT != 0) need_r[plan.start[k] - 1] = 1;
+    meta.assign(padded, 2);
+    for (int32_t k = 0; k < n; k++) {
+        int32_t m = 0;
+        if (plan.is_span[k])
+            m |= 2;
+        else if (plan.start[k] == k)
+            m |= 1;
+        else
+            m |= (plan.start[k] - (k / KT) * KT) << 8;
+        if (need_r[k]) m |= 4;
+        m |= (plan.cp_after[k] + 1) << 16;
+        meta[k] = m;
+    }
+}
+
 }  // namespace fuf
 
 using namespace fuf;
+
+// Test hook (host only): the per-node plan words of the TMA push-up kernel, n_chunks * 32 entries; *usable = 0 when the
+// tree cannot use that kernel (not a DFS postorder, or more than 65,534 checkpoint slots).
+extern "C" int fuf_debug_push_meta(const int32_t *parent_h, int32_t n, int32_t *meta_out, int32_t *usable)
+{
+    FUF_REQUIRE(parent_h && meta_out && usable, "fuf_debug_push_meta: null argument");
+    FUF_REQUIRE(n >= 1 && parent_h[n - 1] == -1, "fuf_debug_push_meta: root must be last");
+    for (int32_t i = 0; i < n - 1; i++)
+        FUF_REQUIRE(parent_h[i] > i && parent_h[i] < n, "fuf_debug_push_meta: parent[%d] = %d is not a postorder", i,
+                    parent_h[i]);
+    TreePlan plan;
+    build_tree_plan(parent_h, n, plan);
+    *usable = (plan.contiguous && plan.n_cp < 65535) ? 1 : 0;
+    if (!*usable) return FUF_OK;
+    std::vector<int32_t> meta;
+    build_push_meta(plan, n, meta);
+    for (size_t k = 0; k < meta.size(); k++) meta_out[k] = meta[k];
+    return FUF_OK;
+}
 
 // Test hook (host only, no device needed): the push-up plan for a postorder parent array.
 // span_out receives 5 ints per spanning node (k, chunk_first, chunk_last, slot_start, slot_k); capacity n nodes.
@@ -310,6 +367,18 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
     std::vector<uint8_t> &is_span = plan.is_span;
     std::vector<SpanNode> &span = plan.span;
 
+    // per-node records of the TMA push-up kernel (only for DFS postorders whose checkpoint slots fit 16 bits)
+    std::vector<PushNode> push_node[2];
+    if (plan.contiguous && plan.n_cp < 65535) {
+        std::vector<int32_t> meta;
+        build_push_meta(plan, n, meta);
+        for (int mode = 0; mode < 2; mode++) {
+            push_node[mode].assign(meta.size(), PushNode{0.0, 2, 0});
+            for (size_t k = 0; k < meta.size(); k++)
+                push_node[mode][k] = PushNode{k < (size_t)n ? ctx->w[mode][k] : 0.0, meta[k], 0};
+        }
+    }
+
     int rc = FUF_OK;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -320,7 +389,9 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
     if ((rc = upload(&ctx->d_parent, ctx->parent)) || (rc = upload(&ctx->d_w[0], ctx->w[0])) ||
         (rc = upload(&ctx->d_w[1], ctx->w[1])) || (rc = upload(&ctx->d_parent_local, parent_local)) ||
         (rc = upload(&ctx->d_cp_after, cp_after)) || (rc = upload(&ctx->d_is_span, is_span)) ||
-        (rc = upload(&ctx->d_span, span)) || (rc = upload(&ctx->d_has_child, plan.has_child))) {
+        (rc = upload(&ctx->d_span, span)) || (rc = upload(&ctx->d_has_child, plan.has_child)) ||
+        (!push_node[0].empty() && ((rc = upload(&ctx->d_push_node[0], push_node[0])) ||
+                                   (rc = upload(&ctx->d_push_node[1], push_node[1]))))) {
         fuf_tree_destroy(ctx);
         return rc;
     }
@@ -353,6 +424,8 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     cudaFree(ctx->d_is_span);
     cudaFree(ctx->d_span);
     cudaFree(ctx->d_has_child);
+    cudaFree(ctx->d_push_node[0]);
+    cudaFree(ctx->d_push_node[1]);
     cudaFree(ctx->d_refined);
     ctx->ws_center.release();
     ctx->ws_rows.release();
@@ -360,6 +433,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     ctx->ws_gram.release();
     ctx->ws_gram_small.release();
     ctx->ws_p64.release();
+    ctx->ws_p64t.release();
     ctx->ws_push.release();
     ctx->ws_pair.release();
     ctx->ws_x.release();

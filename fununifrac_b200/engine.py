@@ -215,19 +215,35 @@ class TreeContext:
                "fuf_push_up")
         return PT
 
+    def push_up_p64(self, X, mode: int, P64T=None, col0: int = 0):
+        """Float64 pushed profiles only (``fuf_push_up`` without the fp32 output): the operands of the refinement
+        pass, produced when a pair actually needs them."""
+        torch = _torch()
+        N = int(X.shape[0])
+        assert X.dim() == 2 and X.stride(1) == 1 and X.shape[1] >= self.n
+        if P64T is None:
+            P64T = self.new_profile_buffer(N + col0, dtype=torch.float64)
+        assert P64T.dtype == torch.float64 and P64T.stride(1) == 1
+        _check(self._lib.fuf_push_up(self.handle, X.data_ptr(), _dtype_code(X), N, X.stride(0), mode, None, None, 0,
+                                     P64T.data_ptr(), P64T.stride(0), None, col0, _stream_ptr(torch)), "fuf_push_up")
+        return P64T
+
     def push_up_job(self, X, mode: int, refine: bool = True) -> "Pushed":
-        """The production push-up of a whole job: centre from the first samples, centred fp32 profiles, and
-        (``refine``) the float64 profiles + error statistics the refinement pass needs."""
+        """The production push-up of a whole job: centre from the first samples, centred fp32 profiles and their
+        rounding statistics.  With ``refine`` the job remembers X: the float64 profiles the refinement pass needs are
+        pushed up from it on demand (``job.P64T``) — on ordinary data no pair is flagged and they are never written."""
         job = Pushed(self, int(X.shape[0]), refine)
         if job.N:
             job.center = self.push_up_center(X, mode)
-            self.push_up(X, mode, job.PT, 0, job.center, job.P64T, job.err_stat)
+            self.push_up(X, mode, job.PT, 0, job.center, None, job.err_stat)
+            if refine:
+                job.source = (X, mode)
         return job
 
     def round_pushed(self, P64T, N: int, mode: int, refine: bool = True) -> "Pushed":
         """Same as ``push_up_job`` for profiles that are already pushed (node-major float64 P64T)."""
         torch = _torch()
-        job = Pushed(self, N, False)
+        job = Pushed(self, N, refine)
         if N:
             job.center = torch.zeros(self.n, dtype=torch.float64, device=P64T.device)
             st = _stream_ptr(torch)
@@ -242,25 +258,29 @@ class TreeContext:
 
     def distances(self, job: "Pushed", mode: int, D=None, gram: Optional[bool] = None):
         """Full symmetric D of a pushed job: fp32 tile kernel (or, for --L2 from 512 samples on, the tensor-core
-        Gram kernel), then the float64 refinement pass when the job carries float64 profiles."""
+        Gram kernel), then the float64 refinement of whatever pairs the fp32 operands cannot certify."""
         if gram is None:
-            gram = mode == MODE_L2 and job.N >= GRAM_MIN_SAMPLES and job.P64T is not None
+            gram = mode == MODE_L2 and job.N >= GRAM_MIN_SAMPLES and job.can_refine
         if gram:
             return self.distances_gram(job, D=D)
         D = self.pairwise(job.PT, job.N, mode, D=D)
-        if job.P64T is not None and job.N > 1:
+        if job.can_refine and job.N > 1:
             D = self._refine_or_redo(job, mode, job.err_stat, D)
         return D
 
     def _refine_or_redo(self, job: "Pushed", mode: int, err_stat, D, lin_stat=None, lin_kappa: float = 0.0):
-        """Per-pair float64 refinement of up to 0.1 % of the pairs (~1 us each); when more are flagged the float64
-        tile kernel (~3 ns per pair) recomputes the whole matrix instead.  Returns D."""
+        """One counting scan of D against the refinement criteria; if pairs are flagged, the float64 profiles are
+        fetched (pushed up now unless the job already holds them) and either those pairs are recomputed one by one
+        (up to 0.1 % of all pairs, ~1 us each) or the float64 tile kernel (~3 ns per pair) redoes the matrix."""
         budget = max(1024, job.N * (job.N - 1) // 2 // 1000)
-        self.refine(job.P64T, job.N, mode, err_stat, D, lin_stat=lin_stat, lin_kappa=lin_kappa, max_pairs=budget)
+        self.refine(None, job.N, mode, err_stat, D, lin_stat=lin_stat, lin_kappa=lin_kappa)
         self.last_flagged = self.refine_count()
+        if self.last_flagged == 0:
+            return D
+        P64T = job.P64T
         if self.last_flagged > budget:
-            D = self.pairwise_f64(job.P64T, job.N, mode, D=D)
-        return D
+            return self.pairwise_f64(P64T, job.N, mode, D=D)
+        return self.refine(P64T, job.N, mode, err_stat, D, lin_stat=lin_stat, lin_kappa=lin_kappa)
 
     def pairwise_gram(self, PT, N: int, D=None, err_stat=None, tile_rows: Optional[Sequence[int]] = None,
                       shard: int = 0, shard_stride: int = 0):
@@ -306,7 +326,7 @@ class TreeContext:
 
     def distances_gram(self, job: "Pushed", D=None):
         """--L2 through the Gram kernel + both refinement passes (needs a job pushed with refine=True)."""
-        assert job.P64T is not None, "the Gram path needs the float64 profiles for its refinement pass"
+        assert job.can_refine, "the Gram path needs a job that can produce float64 profiles for its refinement pass"
         D, q, err = self.pairwise_gram(job.PT, job.N, D=D, err_stat=job.err_stat)
         self.gram_refined = 0
         if job.N > 1:    # one scan: rounding criterion on err, truncation criterion on the scale statistic h2
@@ -534,16 +554,30 @@ class TreeContext:
 
 
 class Pushed:
-    """Device buffers of one pushed job: centred fp32 profiles ``PT`` [n, ldp], and for the refinement pass the
-    float64 profiles ``P64T`` [n, ldp] and per-sample rounding-error statistics ``err_stat`` [ldp]."""
+    """Device buffers of one pushed job: centred fp32 profiles ``PT`` [n, ldp] and per-sample rounding-error statistics
+    ``err_stat`` [ldp].  ``P64T`` — the float64 profiles [n, ldp] the refinement pass reads — is a property: given by
+    the caller (``round_pushed``) or pushed up from the job's source profiles the first time somebody asks."""
 
     def __init__(self, ctx: TreeContext, N: int, refine: bool = True):
         torch = _torch()
-        self.N = N
+        self.ctx, self.N = ctx, N
         self.PT = ctx.new_profile_buffer(N)
         self.err_stat = torch.zeros(self.PT.shape[1], dtype=torch.float64, device=self.PT.device)
-        self.P64T = ctx.new_profile_buffer(N, dtype=torch.float64) if refine else None
+        self.can_refine = refine
+        self.source = None      # (X, mode): un-pushed profiles to produce P64T from
+        self._p64 = None
         self.center = None
+
+    @property
+    def P64T(self):
+        if self._p64 is None and self.source is not None and self.N:
+            X, mode = self.source
+            self._p64 = self.ctx.push_up_p64(X, mode)
+        return self._p64
+
+    @P64T.setter
+    def P64T(self, value):
+        self._p64 = value
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -92,7 +92,7 @@ class ShardedAllPairs:
             raise ValueError("world > 1 needs a torch.distributed process group")
         n = ops.n
         self.PS = ops.empty((world, n, self.shard), "float32")          # pushed blocks of all ranks (zero-padded)
-        self.P64S = ops.empty((world, n, self.shard), "float64") if refine else None
+        self.P64S = None        # float64 pushed blocks: allocated, computed and exchanged only if a pair is flagged
         self.stat = ops.empty((world * self.shard,), "float64")
         self.center = ops.empty((n,), "float64")
         # full matrix on GPU 0: needed by step(); step_host() with several ranks never touches it (allocated lazily)
@@ -101,8 +101,9 @@ class ShardedAllPairs:
         self.last_flagged = 0
         self._x_stage = None
         self._pending = None
+        self._x_local = None
+        self.flagged = ops.empty((1,), "int64")
         if world > 1:
-            self.flagged = ops.empty((1,), "int64")
             self.blocks = ops.empty((self.max_rows * TILE, N), "float64")
             # what crosses NVLink to rank 0: each rank's row blocks packed to the columns they own (half the volume)
             self.offs, _ = packed_offsets(self.rows, N)
@@ -115,8 +116,8 @@ class ShardedAllPairs:
 
     def pushup_bytes_per_entry(self, x_itemsize: int) -> int:
         """HBM bytes the push-up of this job has to move per (sample, node): the profile entry in, the centred fp32
-        entry out, and — when the float64 profiles are kept for the refinement pass — the float64 entry out."""
-        return x_itemsize + 4 + (8 if self.P64S is not None else 0)
+        entry out (the float64 profiles of the refinement pass are only produced when a pair is flagged)."""
+        return x_itemsize + 4
 
     def release_device_matrix(self):
         """Drop the device-resident result matrix of ``step`` (world == 1); ``step`` allocates it again on demand."""
@@ -143,30 +144,32 @@ class ShardedAllPairs:
         if self.world > 1:
             self.dist.broadcast(self.center, src=0)
         mark("push_begin")      # (after the centre: its kernels and the broadcast)
+        self._x_local = X_local
         if self.hi > self.lo:
-            ops.push_up(X_local, mode, self.PS[r], 0, self.center, self.P64S[r] if self.do_refine else None,
-                        self.stat[r * sh:(r + 1) * sh])
+            ops.push_up(X_local, mode, self.PS[r], 0, self.center, None, self.stat[r * sh:(r + 1) * sh])
         mark("push_end")
+        self._pending = None
         if self.world == 1:
             if self.D is None:
                 self.D = ops.empty((N, N), "float64")
             mark("pair_begin")
             stat, lin = self._pairwise(None, self.D)
             mark("pair_end")
-            if self.do_refine:
-                ops.refine(self.P64S, N, mode, stat, self.D, None, sh, stride, lin)
+            if self.do_refine and N > 1:
+                ops.count_uncertified_into(N, mode, stat, self.D, None, lin, self.flagged)
+                self._pending = (stat, lin)
+            mark("refine_end")
             return
         self.dist.all_gather_into_tensor(self.PS.view(-1), self.PS[r].reshape(-1))
         self.dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
         mark("pair_begin")
         stat, lin = self._pairwise(self.rows, self.blocks) if self.rows else (None, None)
         mark("pair_end")
-        self._pending = None
         if self.do_refine:
-            # The float64 profiles (2x the fp32 volume) cross NVLink only if some rank has a pair to refine.  The count
-            # stays on the device: it is all-reduced in stream order and the caller goes on queueing the collection of
-            # the results; the host looks at the count afterwards (_refine_if_flagged) and, in the rare case, refines
-            # and collects again.
+            # The float64 profiles (2x the fp32 volume) are pushed up and cross NVLink only if some rank has a pair to
+            # refine.  The count stays on the device: it is all-reduced in stream order and the caller goes on queueing
+            # the collection of the results; the host looks at the count afterwards (_refine_if_flagged) and, in the
+            # rare case, refines and collects again.
             if self.rows:
                 ops.count_uncertified_into(N, mode, stat, self.blocks, self.rows, lin, self.flagged)
             else:
@@ -185,16 +188,22 @@ class ShardedAllPairs:
         self.last_flagged = int(self.flagged.item())
         if self.last_flagged == 0:
             return False
-        ops, r, sh = self.ops, self.rank, self.shard
-        self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
-        if self.rows:
+        ops, r, sh, n = self.ops, self.rank, self.shard, self.ops.n
+        if self.P64S is None:
+            self.P64S = ops.empty((self.world, n, sh), "float64")
+        if self.hi > self.lo:
+            ops.push_up_p64(self._x_local, self.mode, self.P64S[r])
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
+        rows, target = (self.rows, self.blocks) if self.world > 1 else (None, self.D)
+        if self.world == 1 or self.rows:
             # per-pair recomputation costs ~1 us, the float64 tile kernel ~3 ns per pair: beyond 0.1 % of the pairs
             # (the count is global, every rank takes the same branch) the float64 kernel redoes this rank's rows —
             # the same budget rule as the one-GPU paths (engine._refine_or_redo, fuf_all_pairs_host)
             if self.last_flagged > refine_budget(self.N):
-                ops.pairwise_f64(self.P64S, self.N, self.mode, self.rows, sh, ops.n * sh, self.blocks)
+                ops.pairwise_f64(self.P64S, self.N, self.mode, rows, sh, n * sh, target)
             else:
-                ops.refine(self.P64S, self.N, self.mode, stat, self.blocks, self.rows, sh, ops.n * sh, lin)
+                ops.refine(self.P64S, self.N, self.mode, stat, target, rows, sh, n * sh, lin)
         return True
 
     def step(self, X_local, mark=None):
@@ -202,7 +211,9 @@ class ShardedAllPairs:
         ``mark(name)`` is called at the phase boundaries (bench.py records CUDA events there)."""
         mark = mark or (lambda name: None)
         self._compute(X_local, mark)
-        if self.world > 1:
+        if self.world == 1:
+            self._refine_if_flagged()
+        else:
             r = self.rank
             if self.packed is None:
                 self.packed = self.ops.empty((self.max_packed,), "float64")
@@ -235,6 +246,7 @@ class ShardedAllPairs:
         X = self.ops.to_device(X_local_host, self._x_stage)
         self._compute(X, mark)
         if self.world == 1:
+            self._refine_if_flagged()
             self.ops.copy_to_host(self.D, D_host.array)
         else:
             for attempt in range(2):
@@ -346,6 +358,9 @@ class CudaOps:
 
     def push_up(self, X, mode, PT, col0, center, P64T, err_stat):
         return self.ctx.push_up(X, mode, PT, col0, center, P64T, err_stat)
+
+    def push_up_p64(self, X, mode, P64T):
+        return self.ctx.push_up_p64(X, mode, P64T)
 
     def pairwise(self, PT, N, mode, tile_rows, shard, shard_stride, D):
         return self.ctx.pairwise(PT, N, mode, D=D, tile_rows=tile_rows, shard=shard, shard_stride=shard_stride)

@@ -130,7 +130,11 @@ int fuf_push_up_center(fuf_ctx *ctx, const void *X, int x_dtype, int64_t m, int6
  *   P64T (device double, node-major, ld ldp64; may be NULL): P64T[k][col0+s] = w_k S_k(s)
  *   err_stat (device double, may be NULL): err_stat[col0+s] = sum_k |rounding error of PT[k][col0+s]|   (L1)
  *                                                             sum_k (rounding error of PT[k][col0+s])^2 (L2)
- * center: device, n doubles, or NULL for no centring. */
+ * center: device, n doubles, or NULL for no centring.
+ * Two kernels serve this call.  P64T == NULL (the production case: the float64 profiles are only needed when a pair
+ * is flagged for refinement, and are then requested by a second call with PT == NULL): a persistent TMA-fed kernel —
+ * it needs X 16-byte aligned with ldx * sizeof(element) a multiple of 16 (pad ldx; fuf_all_pairs_host does).
+ * Otherwise a chunk kernel whose P64T reproduces the reference's additions child by child. */
 int fuf_push_up(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx, int mode, const double *center,
                 float *PT, int64_t ldp, double *P64T, int64_t ldp64, double *err_stat, int64_t col0, void *stream);
 
@@ -311,6 +315,10 @@ int fuf_ingest_gather_csv(const fuf_name_index *index, const char *const *paths,
 int fuf_debug_tree_plan(const int32_t *parent_h, int32_t n, int32_t *parent_local, int32_t *cp_after,
                         uint8_t *is_span, int32_t *span_out, int32_t *n_span, int32_t *n_cp, int32_t *contiguous,
                         int32_t *chunk);
+
+/* Test hook, host only: the per-node plan words of the TMA push-up kernel (see PushNode in csrc/common.cuh),
+ * ceil(n / 32) * 32 entries; *usable = 0 (meta_out untouched) when the tree cannot use that kernel. */
+int fuf_debug_push_meta(const int32_t *parent_h, int32_t n, int32_t *meta_out, int32_t *usable);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,82 @@ def pushup_model(parent, length, X, is_l2, plan=None, x_dtype=np.float64):
     return out
 
 
+def push_meta(parent):
+    """Per-node plan words of the TMA push-up kernel (``fuf_debug_push_meta``), or None when it does not apply."""
+    L = engine.load_library()
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    n = len(parent)
+    meta = np.empty((n + 31) // 32 * 32, np.int32)
+    usable = ctypes.c_int32()
+    L.fuf_debug_push_meta.restype = ctypes.c_int
+    rc = L.fuf_debug_push_meta(parent.ctypes.data_as(ctypes.c_void_p), n, meta.ctypes.data_as(ctypes.c_void_p),
+                               ctypes.byref(usable))
+    if rc != 0:
+        raise RuntimeError(L.fuf_last_error().decode())
+    return meta if usable.value else None
+
+
+def pushup_tma_model(parent, length, X, is_l2, center=None, plan=None):
+    """K1t (pushup_tma_kernel) + K1b on the host: thread = sample; per chunk a running prefix r, S = x for leaf-like
+    nodes, S = r - parked prefix otherwise, spanning nodes from chunk totals and checkpoints.  Returns (float32 [N, n],
+    per-sample rounding statistic)."""
+    parent = np.asarray(parent)
+    n = len(parent)
+    plan = plan or tree_plan(parent)
+    meta = push_meta(parent)
+    assert meta is not None
+    KT = 32
+    w = np.array(length, dtype=np.float64)
+    w[:-1][w[:-1] == 0] = np.finfo(np.float64).eps
+    if is_l2:
+        w = np.sqrt(w)
+    w[-1] = 1.0
+    c = np.zeros(n) if center is None else np.asarray(center, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64)
+    N = X.shape[0]
+    n_chunks = (n + KT - 1) // KT
+    out = np.full((N, n), np.nan, dtype=np.float32)
+    err = np.zeros(N)
+    T = np.zeros((n_chunks, N))
+    CP = np.zeros((max(1, plan["n_cp"]), N))
+
+    def emit(k, v):
+        f = v.astype(np.float32)
+        out[:, k] = f
+        e = v - f.astype(np.float64)
+        return e * e if is_l2 else np.abs(e)
+
+    for ch in range(n_chunks):
+        k0 = ch * KT
+        r = np.zeros(N)
+        parked = {}
+        for kk in range(KT):
+            k = k0 + kk
+            m = int(meta[k])
+            x = X[:, k] if k < n else np.zeros(N)
+            r = r + x
+            if m & 4:
+                parked[kk] = r.copy()
+            if not (m & 2):
+                if m & 1:
+                    v = w[k] * x
+                else:
+                    b = (m >> 8) & 63
+                    S = r - parked[b - 1] if b > 0 else r
+                    v = w[k] * S - c[k]
+                err += emit(k, v)
+            cp = (m >> 16) & 0xFFFF
+            if cp:
+                CP[cp - 1] = r
+        T[ch] = r
+    for k, cf, cl, s_start, s_k in plan["span"]:     # K1b, same-sign form
+        head = T[cf] - (CP[s_start] if s_start >= 0 else 0.0)
+        mid = T[cf + 1:cl].sum(0) if cl > cf + 1 else 0.0
+        err += emit(k, w[k] * ((head + CP[s_k]) + mid) - c[k])
+    assert not np.isnan(out).any()
+    return out, err
+
+
 def pairwise_model(P32, is_l2, flush=256):
     """K2's numerical scheme: fp32 subtraction and accumulation over chunks of `flush` basis entries,
     chunk sums combined in double.  P32: float32 [N, n]."""

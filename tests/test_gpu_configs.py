@@ -200,12 +200,24 @@ def test_cli_diffab_near_duplicates_values_and_nnz(l2, full_tree, tmp_path):
     assert coo.shape == (N, N, n)
     got = coo.todense()
     scale = np.abs(want).max()
-    assert np.all(np.abs(got - want) <= 1e-12 * np.abs(want) + 1e-15 * scale)
-    # non-zero pattern: identical up to entries below the float64 noise of the push-up itself
+    # the production float64 profiles differ from the reference's by at most a few ulp of the entry on the ~2 % of nodes
+    # whose subtree crosses a 32-node chunk (summed chunk-wise instead of child by child), exact elsewhere: a difference
+    # vector entry carries that noise in absolute terms
+    pmax = np.abs(P).max() ** (2 if l2 else 1)
+    noise = 16 * np.finfo(np.float64).eps * pmax
+    assert np.all(np.abs(got - want) <= 1e-12 * np.abs(want) + noise)
+    # non-zero pattern: identical except where the entry itself is below that noise
     diff_pat = (got != 0) != (want != 0)
-    assert not diff_pat.any() or np.abs(want[diff_pat]).max() <= 1e-15 * scale
+    assert diff_pat.mean() < 1e-3 and (not diff_pat.any() or np.maximum(np.abs(want), np.abs(got))[diff_pat].max() <= noise)
     assert not got[0, 6].any() and not got[6, 0].any()                   # identical samples: no entries at all
-    assert got[0, 4].any() and np.abs(got[0, 4]).max() < 1e-8 * scale    # near-duplicates: tiny, but present
+    assert got[0, 4].any() and 0 < np.abs(got[0, 4]).max() < 1e-6 * scale    # near-duplicates: tiny, but present
+    # fp32 operands would have lost them: the largest entry of the near-duplicate row is below one fp32 ulp of the profiles
+    assert np.abs(want[0, 4]).max() < np.finfo(np.float32).eps * np.abs(P[0]).max() ** (2 if l2 else 1)
+    # --validate: float64 kernels in the reference's operation order -> values AND pattern bit-identical to the oracle
+    compute_fununifrac.main(["-e", path, "-fd", str(prof), "-o", out, "-i", "v", "-b", "ko00001", "-a", "median_abund",
+                             "-t", "4", "--diffab", "--validate"] + (["--L2"] if l2 else []))
+    coo_v = sparse_npz.load_npz(os.path.join(out, constant.FUNUNIFRAC_OUT__DIFFAB_FILE_NAME.format("v")) + ".npz")
+    assert np.array_equal(coo_v.todense(), want)
     D = np.load(os.path.join(out, constant.FUNUNIFRAC_OUT__MAIN_FILE_NAME.format("d")))
     Dref = oracle_c.pairwise(P, l2)
     iu = np.triu_indices(N, 1)

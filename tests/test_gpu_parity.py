@@ -160,6 +160,67 @@ def test_full_tree_vs_oracle(l2, full_tree):
     assert rel_err(D, Dref32) < REL
 
 
+@pytest.mark.parametrize("l2", [False, True])
+def test_tma_pushup_kernel_vs_chunk_kernel_and_oracle(l2, full_tree, monkeypatch):
+    """The production push-up (pushup_tma_kernel: TMA boxes of X, prefix differences inside a chunk) against the chunk
+    kernel (child-by-child additions) and the oracle: float64 and float32 input, N that is not a multiple of the 256-sample
+    tile, a column offset, a padded row pitch, and the per-sample rounding statistic."""
+    inp, ctx, leaves = full_tree
+    mode = engine.MODE_L2 if l2 else engine.MODE_L1
+    N, n = 700, ctx.n
+    X = synth.synth_profiles_dense(leaves, n, N, seed=21)
+    X[:, -1] = 1e-3                                   # mass on internal nodes too (root, an upper-level node)
+    X[:, -2] = 2e-3
+    Pref = oracle_c.push_up(inp.parent, inp.edge_length, X, l2)
+    Xd = torch.from_numpy(X).cuda()
+    center = ctx.push_up_center(Xd, mode)
+    cen = center.cpu().numpy()
+    want = Pref - cen[None, :]
+
+    def run(Xin, col0=0):
+        PT = ctx.new_profile_buffer(N + col0)
+        stat = torch.zeros(PT.shape[1], dtype=torch.float64, device="cuda")
+        ctx.push_up(Xin, mode, PT, col0, center, None, stat)
+        return PT[:, col0:col0 + N].t().cpu().numpy(), stat[col0:col0 + N].cpu().numpy()
+
+    launches = ctx.launch_count()
+    P_tma, s_tma = run(Xd)
+    n_tma = ctx.launch_count() - launches
+    monkeypatch.setenv("FUF_PUSHUP_NO_TMA", "1")
+    P_chunk, s_chunk = run(Xd)
+    monkeypatch.delenv("FUF_PUSHUP_NO_TMA")
+    # both round the same float64 value up to ~1e-16 of the chunk's mass: identical except for rare 1-ulp ties
+    assert np.allclose(P_tma, want, rtol=2e-7, atol=1e-7 * np.abs(want).max() * 1e-3)
+    ulp = np.spacing(np.abs(P_chunk).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(P_tma.astype(np.float64) - P_chunk) <= ulp) and (P_tma != P_chunk).mean() < 1e-4
+    resid = want - P_tma.astype(np.float64)
+    stat_true = (resid ** 2).sum(1) if l2 else np.abs(resid).sum(1)
+    assert np.allclose(s_tma, stat_true, rtol=1e-3) and np.allclose(s_tma, s_chunk, rtol=1e-3)
+    assert np.array_equal(P_tma == 0, want.astype(np.float32) == 0)          # exact zeros stay exact zeros
+    # column offset and a padded, 16-byte aligned row pitch (what fuf_all_pairs_host uses for odd n)
+    P_off, s_off = run(Xd, col0=128)
+    assert np.array_equal(P_off, P_tma) and np.array_equal(s_off, s_tma)
+    Xpad = torch.zeros((N, n + 6), dtype=torch.float64, device="cuda")
+    Xpad[:, :n] = Xd
+    P_pad, s_pad = run(Xpad[:, :n])
+    assert np.array_equal(P_pad, P_tma) and np.array_equal(s_pad, s_tma)
+    # an unaligned pitch silently takes the chunk kernel: same values as the chunk kernel
+    Xodd = torch.zeros((N, n + 1), dtype=torch.float64, device="cuda")
+    Xodd[:, :n] = Xd
+    P_odd, _ = run(Xodd[:, :n])
+    assert np.array_equal(P_odd, P_chunk)
+    # float32 input
+    X32 = Xd.float()
+    center32 = ctx.push_up_center(X32, mode)
+    PT32 = ctx.new_profile_buffer(N)
+    ctx.push_up(X32, mode, PT32, 0, center32)
+    want32 = oracle_c.push_up(inp.parent, inp.edge_length, X32.double().cpu().numpy(), l2) - center32.cpu().numpy()[None, :]
+    assert np.allclose(PT32[:, :N].t().cpu().numpy(), want32, rtol=2e-7, atol=1e-10 * np.abs(want32).max())
+    assert n_tma >= 1
+    # the same kernel on the real KO tree (odd n = 25,961: padded pitch) is covered by test_real_tree_golden through
+    # fuf_all_pairs_host
+
+
 def test_unweighted_full_tree(full_tree):
     inp, ctx, leaves = full_tree
     X = synth.synth_profiles_dense(leaves, ctx.n, 40, seed=2)

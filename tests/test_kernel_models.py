@@ -83,6 +83,37 @@ def test_pushup_plan_and_model_random_trees(n, seed):
         assert np.allclose(got, want, rtol=3e-7, atol=1e-30)
 
 
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 0), (7, 1), (32, 3), (33, 4), (257, 6), (1000, 7), (4097, 8)])
+def test_tma_pushup_plan_words_random_trees(n, seed):
+    """The plan the TMA push-up kernel runs on (leaf-like / skip / parked-prefix / checkpoint bits per node): a numpy
+    replay of the kernel's arithmetic from those words reproduces the oracle within fp32 rounding, centred or not, and
+    its statistic is the rounding error it actually made."""
+    rng = np.random.default_rng(seed)
+    parent = _random_postorder_tree(rng, n)
+    length = rng.random(n) * (rng.random(n) > 0.1)
+    X = rng.random((4, n)) * (rng.random((4, n)) > 0.5)
+    meta = km.push_meta(parent)
+    assert meta is not None and len(meta) % 32 == 0 and np.all(meta[n:] == 2)
+    has_child = np.zeros(n, bool)
+    has_child[parent[parent >= 0]] = True
+    assert np.array_equal((meta[:n] & 1).astype(bool) & ~(meta[:n] & 2).astype(bool),
+                          ~has_child & ~(meta[:n] & 2).astype(bool))        # leaf-like = no children
+    for l2 in (False, True):
+        want = oracle_c.push_up(parent, length, X, l2)
+        got, err = km.pushup_tma_model(parent, length, X, l2)
+        assert np.allclose(got, want, rtol=3e-7, atol=1e-30)
+        center = np.where(has_child, want[:2].mean(0), 0.0)
+        got_c, err_c = km.pushup_tma_model(parent, length, X, l2, center=center)
+        resid = (want - center) - got_c.astype(np.float64)
+        stat = (resid ** 2).sum(1) if l2 else np.abs(resid).sum(1)
+        assert np.allclose(got_c, want - center, rtol=3e-7, atol=1e-7 * np.abs(want).max())
+        assert np.allclose(err_c, stat, rtol=1e-6, atol=1e-12 * stat.max() + 1e-300)
+
+
+def test_tma_pushup_plan_unusable_trees():
+    assert km.push_meta(np.array([3, 2, 4, 4, -1], np.int32)) is None         # not a DFS postorder
+
+
 def test_pushup_model_chain_and_star():
     # a path graph (depth n-1: every node spans) and a star (root spans everything)
     n = 300

@@ -67,6 +67,11 @@ class OracleOps:
         e = np.abs(c - f.astype(np.float64))
         err_stat[col0:col0 + N] = torch.from_numpy((e ** 2).sum(1) if self.l2 else e.sum(1))
 
+    def push_up_p64(self, X, mode, P64T):
+        P = self.o.push_up(self.parent, self.length, X.numpy(), self.l2)
+        P64T[:, :P.shape[0]] = torch.from_numpy(P.T.copy())
+        self.p64_calls = getattr(self, "p64_calls", 0) + 1
+
     def _samples(self, PS, N, shard):
         G, n, sh = PS.shape
         return PS.permute(0, 2, 1).reshape(G * sh, n)[:N].double().numpy()
@@ -87,7 +92,7 @@ class OracleOps:
 
     def count_uncertified_into(self, N, mode, err_stat, D, tile_rows, lin_stat, out):
         assert err_stat.numel() >= N
-        out[0] = 1 if 0 in tile_rows else 0        # pretend the rank that owns tile row 0 found one pair
+        out[0] = 1 if tile_rows is None or 0 in tile_rows else 0   # pretend the owner of tile row 0 found one pair
 
     def refine(self, P64T, N, mode, err_stat, D, tile_rows, shard, shard_stride, lin_stat=None):
         self.refine_calls += 1
@@ -170,6 +175,8 @@ def _worker(rank, world, port, N, l2, out_path):
         D = job.step(torch.from_numpy(X[job.lo:job.hi]), marks.append)
         assert marks[0] == "start" and marks[-1] == "end" and "pair_begin" in marks
         assert ops.refine_calls == (1 if job.rows else 0) and job.last_flagged == 1
+        # the float64 profiles were pushed up only because a pair was flagged, by every rank that holds samples
+        assert getattr(ops, "p64_calls", 0) == (1 if job.hi > job.lo else 0)
         if rank == 0:
             from oracle import oracle_c
             ref = oracle_c.pairwise(oracle_c.push_up(parent, length, X, l2), l2)

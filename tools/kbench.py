@@ -33,11 +33,22 @@ def timeit(f, reps=a.reps):
     return min(e[i].elapsed_time(e[i + 1]) for i in range(reps))
 job = engine.Pushed(ctx, N, True)
 job.center = ctx.push_up_center(X, a.mode)
+job.P64T = ctx.new_profile_buffer(N, dtype=torch.float64)
 if "push" in a.what:
     ms = timeit(lambda: ctx.push_up(X, a.mode, job.PT, 0, job.center, job.P64T, job.err_stat))
     print(f"push_up f64->f32+f64+stat N={N}: {ms:.3f} ms  {N*n*20/ms/1e6:.0f} GB/s (20 B/entry)")
     ms = timeit(lambda: ctx.push_up(X, a.mode, job.PT, 0, job.center, None, job.err_stat))
-    print(f"push_up f64->f32+stat     N={N}: {ms:.3f} ms  {N*n*12/ms/1e6:.0f} GB/s (12 B/entry)")
+    print(f"push_up f64->f32+stat     N={N}: {ms:.3f} ms  {N*n*12/ms/1e6:.0f} GB/s (12 B/entry)  [TMA kernel]")
+    os.environ["FUF_PUSHUP_NO_TMA"] = "1"
+    ms = timeit(lambda: ctx.push_up(X, a.mode, job.PT, 0, job.center, None, job.err_stat))
+    print(f"push_up f64->f32+stat     N={N}: {ms:.3f} ms  {N*n*12/ms/1e6:.0f} GB/s (12 B/entry)  [chunk kernel]")
+    del os.environ["FUF_PUSHUP_NO_TMA"]
+    ms = timeit(lambda: ctx.push_up(X, a.mode, job.PT, 0, job.center, None, None))
+    print(f"push_up f64->f32 no stat  N={N}: {ms:.3f} ms  {N*n*12/ms/1e6:.0f} GB/s (12 B/entry)  [TMA kernel]")
+    a_ = torch.empty(N * n * 12 // 16, dtype=torch.float64, device="cuda"); b_ = torch.empty_like(a_)
+    ms = timeit(lambda: b_.copy_(a_))
+    print(f"torch copy of {a_.numel()*8/1e9:.2f} GB (read + write = {a_.numel()*16/1e9:.2f} GB): {ms:.3f} ms  {a_.numel()*16/ms/1e6:.0f} GB/s")
+    del a_, b_
     X32 = X.float()
     ms = timeit(lambda: ctx.push_up(X32, a.mode, job.PT, 0, job.center, None, None))
     print(f"push_up f32->f32          N={N}: {ms:.3f} ms  {N*n*8/ms/1e6:.0f} GB/s (8 B/entry)")
