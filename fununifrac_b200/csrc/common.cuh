@@ -49,9 +49,12 @@ struct SpanNode {
 // Per-node record of the TMA push-up kernel (pushup.cu): the weight and the packed plan word in one 16-byte load.
 //   bit 0      leaf-like: the subtree is the node itself, S = x
 //   bit 1      skip: spanning node (written by the span kernel) or padding beyond the tree
-//   bit 2      save the chunk-local prefix after this node (an internal node further on starts right after it)
-//   bits 8-13  b: the subtree starts at chunk-local index b (S = prefix - saved prefix[b - 1]; b = 0: S = prefix)
+//   bit 3      this node has a checkpoint slot (bits 16-31)
+//   bits 4-7   park slot + 1: keep the chunk-local prefix after this node (an internal node further on starts right after
+//              it); 0 = nothing to keep
+//   bits 8-11  park slot + 1 of the prefix to subtract: S = prefix - parked; 0 = the subtree starts with the chunk, S = prefix
 //   bits 16-31 checkpoint slot + 1 for the span kernel (0 = none)
+constexpr int kPushParkSlots = 12;  // parked prefixes per chunk (24 KB of shared memory per CTA)
 struct PushNode {
     double w;
     int32_t meta;
@@ -132,6 +135,7 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_p;        // PT / P64T (fuf_all_pairs_host)
     fuf::DeviceBuffer ws_d;        // D on device when the host buffer cannot be written in place
     fuf::DeviceBuffer ws_center;   // column mean scratch of fuf_push_up_center
+    fuf::DeviceBuffer ws_rec;      // per-job node records of the TMA push-up kernel
     fuf::DeviceBuffer ws_rows;     // tile-row list of fuf_refine
     fuf::DeviceBuffer ws_panel;    // transposed tile panels of fuf_store_tile_rows_host
     fuf::DeviceBuffer ws_gram;     // int8 digit planes + tables of fuf_pairwise_gram

@@ -38,6 +38,8 @@ namespace fuf {
 
 constexpr int KT = kPushChunk;  // nodes per chunk
 constexpr int TI = 128;         // samples per CTA
+constexpr int PT_SAMPLES = 256;                 // samples per tile = consumer threads
+constexpr int PT_GROUP = 8;                     // chunks per work item
 
 template <typename TX, int MODE, bool HAS_PT, bool HAS_P64>
 __global__ void __launch_bounds__(TI)
@@ -133,29 +135,53 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
 //   * a thread lifts its sample's 32 values with 16-byte shared loads (the swizzle makes a warp's 32 row reads hit
 //     all banks: 4 wavefronts per 512 bytes, the minimum), keeps a running prefix r over the chunk in a register and
 //     gets every subtree sum inside the chunk as S = x (leaf) or S = r - r[start - 1] (internal; the few prefixes
-//     that are needed again are parked in the thread's own row of the stage): no per-node read-modify-write of shared
-//     memory and no dependency chain through it.  The difference of two prefixes of at most 32 same-sign terms is
+//     that are needed again are parked in a [slot][sample] array, at most 12 per chunk): no per-node
+//     read-modify-write of shared memory and no dependency chain through it.  The difference of two prefixes of at most 32 same-sign terms is
 //     accurate to ~1e-16 of the chunk's mass — far below the fp32 rounding of the output; the float64 profiles the
 //     refinement pass needs are produced on demand by the chunk kernel above, in the reference's operation order;
-//   * per node one 16-byte uniform load brings the weight and the packed plan word (PushNode); the centre is read for
-//     internal nodes only (it is zero on leaves);
+//   * the chunk's 32 node records (weight, centre, packed plan word; 1 KB, built per job from the static plan and the
+//     centre) arrive with the tile through one bulk copy; the per-node code is branch-free (selects, predicated
+//     accesses) so that the 32 nodes overlap;
 //   * stores: PT rows, 128 bytes per warp and node; chunk totals T and checkpoints CP for the span kernel; one
 //     rounding-error partial R per (group of 8 chunks, sample) — a fixed grouping, so the statistic does not depend
 //     on the launch geometry.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PT_SAMPLES = 256;                 // samples per tile = consumer threads
-constexpr int PT_GROUP = 8;                     // chunks per work item
 constexpr int PT_STAGES = 3;
 constexpr uint32_t PT_STAGE_BYTES = PT_SAMPLES * KT * sizeof(double);   // 64 KB (float32 input fills half of it)
-constexpr uint32_t PT_SMEM_BYTES = PT_STAGES * PT_STAGE_BYTES + 1024 /* alignment */ + 64 /* barriers */;
+constexpr uint32_t PT_NODE_BYTES = KT * 32;                              // 1 KB of node records (PushRec) per stage
+constexpr uint32_t PT_PARK_BYTES = kPushParkSlots * PT_SAMPLES * sizeof(double);   // 24 KB: [slot][sample]
+constexpr uint32_t PT_SMEM_BYTES = PT_STAGES * (PT_STAGE_BYTES + PT_NODE_BYTES) + PT_PARK_BYTES + 1024 /* alignment */ +
+                                   64 /* barriers */;
+
+// Per-job record of one node: the static plan (PushNode) joined with the job's centre value, 32 bytes, so that one
+// 1 KB bulk copy per chunk brings everything the consumers need besides X.
+struct PushRec {
+    double w, c;
+    int32_t meta, pad[3];
+};
+
+__global__ void __launch_bounds__(256)
+push_records_kernel(const PushNode *__restrict__ node, const double *__restrict__ center, int32_t n, int32_t n_padded,
+                    PushRec *__restrict__ out)
+{
+    const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_padded) return;
+    const PushNode nd = node[k];
+    PushRec r;
+    r.w = nd.w;
+    r.c = (center && k < n && !(nd.meta & 1)) ? center[k] : 0.0;     // leaf-like nodes carry no centre
+    r.meta = nd.meta;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    out[k] = r;
+}
 
 struct PushTmaParams {
-    const PushNode *node;      // [n_chunks * 32]
-    const double *center;      // [n] or nullptr
+    const PushRec *rec;        // [n_chunks * 32]
     float *PT;
     int64_t ldp, col0, N, ldt;
-    int32_t n_chunks, n_groups, n_items;
+    int32_t n, n_chunks, n_groups, n_items;
     double *T, *CP, *R;        // chunk totals, checkpoints (nullptr without spanning nodes), error partials (nullptr: none)
+    double *GT;                // totals of whole groups of PT_GROUP chunks (nullptr without spanning nodes)
 };
 
 __device__ __forceinline__ uint32_t pu_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,7 +206,9 @@ pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams 
 {
     extern __shared__ unsigned char pu_smem[];
     const uint32_t base = (pu_smem_u32(pu_smem) + 1023u) & ~1023u;      // SWIZZLE_128B atoms sit on 1 KB boundaries
-    const uint32_t full0 = base + PT_STAGES * PT_STAGE_BYTES, empty0 = full0 + 8 * PT_STAGES;
+    const uint32_t nodes0 = base + PT_STAGES * PT_STAGE_BYTES;          // per stage: the chunk's 32 plan records
+    const uint32_t park0 = nodes0 + PT_STAGES * PT_NODE_BYTES;
+    const uint32_t full0 = park0 + PT_PARK_BYTES, empty0 = full0 + 8 * PT_STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < PT_STAGES; s++) {
@@ -204,10 +232,12 @@ pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams 
                 for (int c = g * PT_GROUP; c < c_end; ++c, ++it) {
                     const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
                     pu_mbar_wait(empty0 + 8 * slot, phase ^ 1u);
-                    // the consumers wrote their scratch prefixes into this stage through the generic proxy
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     const uint32_t full = full0 + 8 * slot, dst = base + slot * PT_STAGE_BYTES;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(TX_BYTES) : "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(TX_BYTES + PT_NODE_BYTES) : "memory");
+                    // the chunk's plan records ride along (the table is padded to whole chunks)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(nodes0 + slot * PT_NODE_BYTES), "l"(p.rec + (int64_t)c * KT), "r"(PT_NODE_BYTES), "r"(full)
+                                 : "memory");
                     constexpr int BOXES = sizeof(TX) == 8 ? 2 : 1;     // 128-byte inner box: 16 doubles or 32 floats
 #pragma unroll
                     for (int bx = 0; bx < BOXES; bx++)
@@ -223,22 +253,25 @@ pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams 
     }
 
     // ===================== consumers: thread = sample =====================
+    // Everything below is written branch-free per node (selects and predicated accesses): the 32 nodes of a chunk are
+    // independent except for the running prefix, and with two warps per scheduler it is the instruction-level
+    // parallelism across nodes that hides the conversion and shared-memory latencies.
+    unsigned char *gbase = pu_smem + (base - pu_smem_u32(pu_smem));       // generic pointer to the aligned ring
     const uint32_t sw = (uint32_t)(tid & 7) << 4;                  // XOR term of this row's 16-byte units
     const uint32_t row = (uint32_t)tid * 128u;
-    // parked prefix after chunk-local node q lives in this thread's own row: box q / 16, unit (q % 16) / 2, half q % 2
-    auto park_addr = [&](uint32_t stage, int q) {
-        return stage + (uint32_t)(q >> 4) * (PT_SAMPLES * 128) + row + ((((uint32_t)(q & 15) >> 1) << 4) ^ sw) + (uint32_t)(q & 1) * 8u;
-    };
+    // parked prefixes: [slot][sample], each thread its own column (conflict-free, never shared between threads)
+    double *park = reinterpret_cast<double *>(gbase + (park0 - base)) + tid;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int sb = item / p.n_groups, g = item % p.n_groups;
         const int c_end = min(p.n_chunks, (g + 1) * PT_GROUP);
         const int64_t s = (int64_t)sb * PT_SAMPLES + tid;
         const bool live = s < p.N;
-        double err = 0.0;
+        double err = 0.0, group_total = 0.0;
         for (int c = g * PT_GROUP; c < c_end; ++c, ++it) {
             const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
-            const uint32_t stage = base + slot * PT_STAGE_BYTES;
+            unsigned char *stage = gbase + slot * PT_STAGE_BYTES;
+            const PushRec *rec = reinterpret_cast<const PushRec *>(gbase + PT_STAGES * PT_STAGE_BYTES + slot * PT_NODE_BYTES);
             pu_mbar_wait(full0 + 8 * slot, phase);
             double x[KT];
             if (sizeof(TX) == 8) {
@@ -246,63 +279,49 @@ pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams 
                 for (int bx = 0; bx < 2; bx++)
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        double lo, hi;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                                     : "=d"(lo), "=d"(hi)
-                                     : "r"(stage + bx * (PT_SAMPLES * 128) + row + (((uint32_t)u << 4) ^ sw)));
-                        x[bx * 16 + 2 * u] = lo;
-                        x[bx * 16 + 2 * u + 1] = hi;
+                        const double2 v = *reinterpret_cast<const double2 *>(stage + bx * (PT_SAMPLES * 128) + row + (((uint32_t)u << 4) ^ sw));
+                        x[bx * 16 + 2 * u] = v.x;
+                        x[bx * 16 + 2 * u + 1] = v.y;
                     }
             } else {
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
-                    float a, b, cc, d;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(a), "=f"(b), "=f"(cc), "=f"(d)
-                                 : "r"(stage + row + (((uint32_t)u << 4) ^ sw)));
-                    x[4 * u] = (double)a, x[4 * u + 1] = (double)b, x[4 * u + 2] = (double)cc, x[4 * u + 3] = (double)d;
+                    const float4 v = *reinterpret_cast<const float4 *>(stage + row + (((uint32_t)u << 4) ^ sw));
+                    x[4 * u] = (double)v.x, x[4 * u + 1] = (double)v.y, x[4 * u + 2] = (double)v.z, x[4 * u + 3] = (double)v.w;
                 }
             }
-            const PushNode *node = p.node + (int64_t)c * KT;
-            const int64_t k0 = (int64_t)c * KT;
-            float *pt = p.PT + k0 * p.ldp + p.col0 + s;
+            float *pt = p.PT + (int64_t)c * KT * p.ldp + p.col0 + s;
             double r = 0.0;
 #pragma unroll
             for (int kk = 0; kk < KT; kk++) {
-                const int4 raw = __ldg(reinterpret_cast<const int4 *>(node + kk));     // uniform: one 16-byte request per warp
-                const double w = __hiloint2double(raw.y, raw.x);
-                const int32_t meta = raw.z;
+                const double2 wc = *reinterpret_cast<const double2 *>(&rec[kk].w);   // same address in every lane: a broadcast
+                const int32_t meta = rec[kk].meta;
+                const bool leaf = meta & 1, skip = meta & 2;
                 r += x[kk];
-                if (meta & 4) asm volatile("st.shared.f64 [%0], %1;" ::"r"(park_addr(stage, kk)), "d"(r) : "memory");
-                if (!(meta & 2)) {
-                    double v;
-                    if (meta & 1) {
-                        v = w * x[kk];
-                    } else {
-                        const int b = (meta >> 8) & 63;
-                        double S = r;
-                        if (b > 0) {
-                            double parked;
-                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(parked) : "r"(park_addr(stage, b - 1)) : "memory");
-                            S = r - parked;
-                        }
-                        v = w * S;
-                        if (p.center) v -= __ldg(p.center + k0 + kk);
-                    }
-                    const float f = (float)v;
-                    if (live) pt[(int64_t)kk * p.ldp] = f;
-                    if (WANT_ERR) {
-                        const double e = v - (double)f;
-                        err += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
-                    }
+                const int keep = (meta >> 4) & 15, take = (meta >> 8) & 15;
+                if (keep) park[(keep - 1) * PT_SAMPLES] = r;
+                double parked = 0.0;
+                if (take) parked = park[(take - 1) * PT_SAMPLES];       // only internal nodes have one
+                const double S = leaf ? x[kk] : r - parked;
+                const double v = __dsub_rn(__dmul_rn(wc.x, S), wc.y);    // fl(w S) - c like the reference (no FMA); leaf-like: c = 0
+                const float f = (float)v;
+                if (live && !skip) *pt = f;
+                pt += p.ldp;
+                if (WANT_ERR) {
+                    const double e = v - (double)f;
+                    const double a = (MODE == FUF_MODE_L2) ? e * e : fabs(e);
+                    err += skip ? 0.0 : a;
                 }
-                const int cp = (int)((uint32_t)meta >> 16);
-                if (cp && live) p.CP[(int64_t)(cp - 1) * p.ldt + s] = r;
+                if (meta & 8) {                                        // a checkpoint for the span kernel (rare)
+                    if (live) p.CP[(int64_t)(((uint32_t)meta >> 16) - 1) * p.ldt + s] = r;
+                }
             }
             if (p.T && live) p.T[(int64_t)c * p.ldt + s] = r;
+            group_total += r;
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
         }
+        if (p.GT && live) p.GT[(int64_t)g * p.ldt + s] = group_total;
         if (WANT_ERR && live) p.R[(int64_t)g * p.ldt + s] = err;
     }
 }
@@ -338,12 +357,26 @@ pushup_stat_kernel(const double *__restrict__ R, int32_t n_chunks, const double 
     }
 }
 
+// sum of A[c][s] for c in [lo, hi): eight independent loads in flight per round, four accumulators
+__device__ __forceinline__ void span_sum(const double *__restrict__ A, int64_t ldt, int64_t s, int lo, int hi, double (&acc)[4])
+{
+    int c = lo;
+    for (; c + 8 <= hi; c += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = A[(int64_t)(c + u) * ldt + s];
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc[u & 3] += v[u];
+    }
+    for (; c < hi; c++) acc[0] += A[(int64_t)c * ldt + s];
+}
+
 template <int MODE>
 __global__ void pushup_span_kernel(const SpanNode *__restrict__ span, int32_t n_span, const double *__restrict__ w,
                                    const double *__restrict__ center, const double *__restrict__ T,
-                                   const double *__restrict__ CP, int64_t ldt, int64_t N, float *__restrict__ PT,
-                                   int64_t ldp, double *__restrict__ P64T, int64_t ldp64, int64_t col0,
-                                   double *__restrict__ R2)
+                                   const double *__restrict__ GT, const double *__restrict__ CP, int64_t ldt, int64_t N,
+                                   float *__restrict__ PT, int64_t ldp, double *__restrict__ P64T, int64_t ldp64,
+                                   int64_t col0, double *__restrict__ R2)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
@@ -352,16 +385,21 @@ __global__ void pushup_span_kernel(const SpanNode *__restrict__ span, int32_t n_
         SpanNode sn = span[q];
         // subtree sum = tail of the first chunk + whole chunks in between + head of the last chunk: only
         // same-sign terms are added (no difference of long prefix sums), so the result is accurate relative
-        // to the subtree's own mass
+        // to the subtree's own mass.  With group totals GT (one per PT_GROUP consecutive chunks, written by the TMA
+        // kernel) the chunks in between cost at most 2 (PT_GROUP - 1) + (chunks / PT_GROUP) loads: the root's 936 chunk
+        // totals become 130 loads, and the longest dependent-latency chain of the launch shrinks accordingly.
         double head = T[(int64_t)sn.chunk_first * ldt + s];
         if (sn.slot_start >= 0) head -= CP[(int64_t)sn.slot_start * ldt + s];
         double mid[4] = {0.0, 0.0, 0.0, 0.0};
-        int c = sn.chunk_first + 1;
-        for (; c + 4 <= sn.chunk_last; c += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) mid[u] += T[(int64_t)(c + u) * ldt + s];
+        const int lo = sn.chunk_first + 1, hi = sn.chunk_last;
+        if (GT && hi - lo >= 2 * PT_GROUP) {
+            const int g_lo = (lo + PT_GROUP - 1) / PT_GROUP, g_hi = hi / PT_GROUP;     // whole groups [g_lo, g_hi)
+            span_sum(T, ldt, s, lo, g_lo * PT_GROUP, mid);
+            span_sum(GT, ldt, s, g_lo, g_hi, mid);
+            span_sum(T, ldt, s, g_hi * PT_GROUP, hi, mid);
+        } else {
+            span_sum(T, ldt, s, lo, hi, mid);
         }
-        for (; c < sn.chunk_last; c++) mid[0] += T[(int64_t)c * ldt + s];
         const double tail = CP[(int64_t)sn.slot_k * ldt + s];
         const double S = (head + tail) + ((mid[0] + mid[1]) + (mid[2] + mid[3]));
         const double v = w[sn.k] * S;
@@ -548,10 +586,11 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
                          ((uintptr_t)X & 15) == 0 && ((size_t)ldx * esz) % 16 == 0 && !getenv("FUF_PUSHUP_NO_TMA") &&
                          tensor_map_encoder() != nullptr;
     const int32_t n_groups = (ctx->n_chunks + PT_GROUP - 1) / PT_GROUP;
-    double *T = nullptr, *CP = nullptr, *R = nullptr, *R2 = nullptr;
+    double *T = nullptr, *CP = nullptr, *R = nullptr, *R2 = nullptr, *GT = nullptr;
     {
         size_t need = 0;
-        if (ctx->n_span > 0) need += ((size_t)ctx->n_chunks + (size_t)ctx->n_cp) * (size_t)ldt * sizeof(double);
+        if (ctx->n_span > 0)
+            need += ((size_t)ctx->n_chunks + (size_t)ctx->n_cp + (use_tma ? (size_t)n_groups : 0)) * (size_t)ldt * sizeof(double);
         if (want_err) need += ((size_t)(use_tma ? n_groups : ctx->n_chunks) + (size_t)span_blocks) * (size_t)ldt * sizeof(double);
         if (need) {
             int rc = ctx->ws_push.reserve(need);
@@ -561,6 +600,10 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
                 T = base;
                 CP = T + (size_t)ctx->n_chunks * ldt;
                 base = CP + (size_t)ctx->n_cp * ldt;
+                if (use_tma) {
+                    GT = base;
+                    base = GT + (size_t)n_groups * ldt;
+                }
             }
             if (want_err) {
                 R = base;
@@ -581,14 +624,22 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
                       (long long)N, n, (long long)ldx);
             return FUF_ECUDA;
         }
+        // the job's node records: static plan + centre (1 KB per chunk, built by a ~1 us kernel)
+        const int32_t n_padded = ctx->n_chunks * KT;
+        int rc2 = ctx->ws_rec.reserve((size_t)n_padded * sizeof(PushRec));
+        if (rc2) return rc2;
+        PushRec *recs = (PushRec *)ctx->ws_rec.ptr;
+        push_records_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, stream>>>(ctx->d_push_node[mode], center, n, n_padded, recs);
+        FUF_CUDA(cudaGetLastError());
+        ctx->launches += 1;
         PushTmaParams p;
-        p.node = ctx->d_push_node[mode];
-        p.center = center;
+        p.rec = recs;
         p.PT = PT;
         p.ldp = ldp;
         p.col0 = col0;
         p.N = N;
         p.ldt = ldt;
+        p.n = n;
         p.n_chunks = ctx->n_chunks;
         p.n_groups = n_groups;
         const int64_t n_sb = (N + PT_SAMPLES - 1) / PT_SAMPLES;
@@ -597,6 +648,7 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
         p.T = T;
         p.CP = CP;
         p.R = want_err ? R : nullptr;
+        p.GT = GT;
         void (*kern)(const CUtensorMap, const PushTmaParams) = nullptr;
 #define FUF_TMA_KERN(TX)                                                                                             \
     kern = mode == FUF_MODE_L1 ? (want_err ? pushup_tma_kernel<TX, 0, true> : pushup_tma_kernel<TX, 0, false>)        \
@@ -641,10 +693,10 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
     if (ctx->n_span > 0) {
         dim3 g2((unsigned)((N + 127) / 128), (unsigned)span_blocks);
         if (mode == FUF_MODE_L1)
-            pushup_span_kernel<FUF_MODE_L1><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
+            pushup_span_kernel<FUF_MODE_L1><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, GT, CP,
                                                                     ldt, N, PT, ldp, P64T, ldp64, col0, R2);
         else
-            pushup_span_kernel<FUF_MODE_L2><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, CP,
+            pushup_span_kernel<FUF_MODE_L2><<<g2, 128, 0, stream>>>(ctx->d_span, ctx->n_span, ctx->d_w[mode], center, T, GT, CP,
                                                                     ldt, N, PT, ldp, P64T, ldp64, col0, R2);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;

@@ -214,26 +214,36 @@ static void build_tree_plan(const int32_t *parent_h, int32_t n, TreePlan &plan)
     plan.n_cp = (int32_t)slot_of_pos.size();
 }
 
-// Plan words of the TMA push-up kernel (see PushNode in common.cuh), padded to whole chunks with "skip".
-static void build_push_meta(const TreePlan &plan, int32_t n, std::vector<int32_t> &meta)
+// Plan words of the TMA push-up kernel (see PushNode in common.cuh), padded to whole chunks with "skip".  Returns false
+// when a chunk would need more parked prefixes than the kernel has slots for (kPushParkSlots).
+static bool build_push_meta(const TreePlan &plan, int32_t n, std::vector<int32_t> &meta)
 {
     const int32_t KT = kPushChunk, padded = (n + KT - 1) / KT * KT;
-    std::vector<uint8_t> need_r(n, 0);
-    for (int32_t k = 0; k < n; k++)   // an internal node whose subtree starts inside its chunk, after node start - 1
-        if (!plan.is_span[k] && plan.start[k] != k && plan.start[k] % KT != 0) need_r[plan.start[k] - 1] = 1;
+    std::vector<int32_t> park_slot(n, -1);   // slot (within the chunk) that keeps the prefix after node k
     meta.assign(padded, 2);
+    for (int32_t c0 = 0; c0 < n; c0 += KT) {
+        int32_t used = 0;
+        const int32_t c1 = std::min(n, c0 + KT);
+        for (int32_t k = c0; k < c1; k++)   // an internal node whose subtree starts inside its chunk, after node start - 1
+            if (!plan.is_span[k] && plan.start[k] != k && plan.start[k] > c0 && park_slot[plan.start[k] - 1] < 0) {
+                if (used == kPushParkSlots) return false;
+                park_slot[plan.start[k] - 1] = used++;
+            }
+    }
     for (int32_t k = 0; k < n; k++) {
         int32_t m = 0;
         if (plan.is_span[k])
             m |= 2;
         else if (plan.start[k] == k)
             m |= 1;
-        else
-            m |= (plan.start[k] - (k / KT) * KT) << 8;
-        if (need_r[k]) m |= 4;
+        else if (plan.start[k] > (k / KT) * KT)
+            m |= (park_slot[plan.start[k] - 1] + 1) << 8;      // S = prefix - parked prefix; 0: S = prefix
+        if (park_slot[k] >= 0) m |= (park_slot[k] + 1) << 4;
+        if (plan.cp_after[k] >= 0) m |= 8;
         m |= (plan.cp_after[k] + 1) << 16;
         meta[k] = m;
     }
+    return true;
 }
 
 }  // namespace fuf
@@ -251,10 +261,9 @@ extern "C" int fuf_debug_push_meta(const int32_t *parent_h, int32_t n, int32_t *
                     parent_h[i]);
     TreePlan plan;
     build_tree_plan(parent_h, n, plan);
-    *usable = (plan.contiguous && plan.n_cp < 65535) ? 1 : 0;
-    if (!*usable) return FUF_OK;
     std::vector<int32_t> meta;
-    build_push_meta(plan, n, meta);
+    *usable = (plan.contiguous && plan.n_cp < 65535 && build_push_meta(plan, n, meta)) ? 1 : 0;
+    if (!*usable) return FUF_OK;
     for (size_t k = 0; k < meta.size(); k++) meta_out[k] = meta[k];
     return FUF_OK;
 }
@@ -369,9 +378,8 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
 
     // per-node records of the TMA push-up kernel (only for DFS postorders whose checkpoint slots fit 16 bits)
     std::vector<PushNode> push_node[2];
-    if (plan.contiguous && plan.n_cp < 65535) {
-        std::vector<int32_t> meta;
-        build_push_meta(plan, n, meta);
+    std::vector<int32_t> meta;
+    if (plan.contiguous && plan.n_cp < 65535 && build_push_meta(plan, n, meta)) {
         for (int mode = 0; mode < 2; mode++) {
             push_node[mode].assign(meta.size(), PushNode{0.0, 2, 0});
             for (size_t k = 0; k < meta.size(); k++)
@@ -428,6 +436,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     cudaFree(ctx->d_push_node[1]);
     cudaFree(ctx->d_refined);
     ctx->ws_center.release();
+    ctx->ws_rec.release();
     ctx->ws_rows.release();
     ctx->ws_panel.release();
     ctx->ws_gram.release();

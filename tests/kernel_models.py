@@ -134,17 +134,18 @@ def pushup_tma_model(parent, length, X, is_l2, center=None, plan=None):
             m = int(meta[k])
             x = X[:, k] if k < n else np.zeros(N)
             r = r + x
-            if m & 4:
-                parked[kk] = r.copy()
+            keep, take = (m >> 4) & 15, (m >> 8) & 15
+            if keep:
+                parked[keep - 1] = r.copy()
             if not (m & 2):
                 if m & 1:
                     v = w[k] * x
                 else:
-                    b = (m >> 8) & 63
-                    S = r - parked[b - 1] if b > 0 else r
+                    S = r - parked[take - 1] if take else r
                     v = w[k] * S - c[k]
                 err += emit(k, v)
             cp = (m >> 16) & 0xFFFF
+            assert bool(cp) == bool(m & 8)
             if cp:
                 CP[cp - 1] = r
         T[ch] = r

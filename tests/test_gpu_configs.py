@@ -222,7 +222,11 @@ def test_cli_diffab_near_duplicates_values_and_nnz(l2, full_tree, tmp_path):
     Dref = oracle_c.pairwise(P, l2)
     iu = np.triu_indices(N, 1)
     ok = Dref[iu] > 0
-    assert np.all(np.abs(D[iu][ok] - Dref[iu][ok]) <= REL * Dref[iu][ok] + 1e-15 * scale) and D[0, 6] == 0
+    # near-duplicate pairs sit at the float64 noise floor of the push-up itself (the reference's own value there is the
+    # rounding of its additions): agreement to a few ulp of the profile mass, 1e-6 relative everywhere else
+    mass = (P ** 2).sum(1).max() if l2 else np.abs(P).sum(1).max()
+    assert np.all(np.abs(D[iu][ok] - Dref[iu][ok]) <= REL * Dref[iu][ok] + 64 * np.finfo(np.float64).eps * mass)
+    assert D[0, 6] == 0
 
 
 if __name__ == "__main__":
