@@ -230,9 +230,11 @@ def device_profiles(leaves, n, N, seed=1):
     """Random profiles generated on the device: uniform abundances on a random 20 % of the leaves, normalised."""
     import torch
 
+    from fununifrac_b200 import engine
+
     g = torch.Generator(device="cuda").manual_seed(seed)
     lv = torch.from_numpy(leaves).cuda()
-    X = torch.zeros((N, n), dtype=torch.float64, device="cuda")
+    X = engine.profile_matrix(N, n, torch.float64, "cuda")
     for b in range(0, N, 4096):
         e = min(N, b + 4096)
         v = torch.rand((e - b, len(leaves)), generator=g, device="cuda", dtype=torch.float64)
@@ -608,7 +610,9 @@ def run_l1(env, args):
     X_pin = torch.zeros((max(hi - lo, 1), n), dtype=torch.float64, pin_memory=True)
     make_profiles(leaves, n, lo, hi, X_pin.numpy()[:hi - lo])
     X_pin = X_pin[:hi - lo]
-    X_dev = X_pin.to(dev)
+    # HBM-resident copy with 128-byte aligned rows (engine.profile_matrix): the layout the push-up's TMA boxes like
+    X_dev = engine.profile_matrix(hi - lo, n, torch.float64, dev)
+    X_dev.copy_(X_pin)
     pairs = N * (N - 1) // 2
     steps, warmup = args.steps, max(args.warmup, 3)
 

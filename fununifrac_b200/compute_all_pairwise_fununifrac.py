@@ -31,7 +31,7 @@ def _ingest(files, input, abundance_key, unweighted, num_threads, python_ingest)
     n = len(input.basis)
     if not files:
         return np.zeros((0, n))
-    X = engine.pinned_empty((len(files), n), engine._torch().float64)[1]
+    X = engine.profile_matrix(len(files), n, pin_memory=True).numpy()     # rows 128-byte aligned
     if python_ingest:
         # the reference's own route: pandas.read_csv + a process pool (src/factory/make_emd_input.py:58-122)
         results = make_emd_input.parallel_functional_profile_to_vector(num_threads, files, input, abundance_key,

@@ -78,8 +78,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     int nb = (validate || use_gram) ? 1 : (int)std::min<int64_t>(16, std::max<int64_t>(1, tiles_per_dim / 4));
     if (getenv("FUF_HOST_BANDS")) nb = std::max(1, std::min(64, atoi(getenv("FUF_HOST_BANDS"))));
     nb = (int)std::min<int64_t>(nb, tiles_per_dim);
-    // device copy of X with a 16-byte aligned row pitch (what the TMA push-up kernel's tensor map needs), whatever n is
-    const int64_t ldx_dev = ((int64_t)n * (int64_t)esz + 15) / 16 * 16 / (int64_t)esz;
+    // device copy of X with a 128-byte aligned row pitch: the TMA push-up kernel's tensor map needs 16 bytes, and with
+    // 128 every 128-byte box row of a sample is exactly four 32-byte sectors (an odd pitch costs ~10 % more DRAM reads)
+    const int64_t ldx_dev = ((int64_t)n * (int64_t)esz + 127) / 128 * 128 / (int64_t)esz;
     if ((rc = ctx->ws_x.reserve((size_t)N * ldx_dev * esz))) return rc;
     const bool d_pinned = is_pinned_host(D_h);
     if ((rc = ctx->ws_d.reserve((size_t)N * N * sizeof(double)))) return rc;

@@ -127,88 +127,134 @@ pushup_chunk_kernel(const TX *__restrict__ X, int64_t ldx, int64_t N, int32_t n,
 
 // ---------------------------------------------------------------------------------------------------------------
 // K1t pushup_tma_kernel: the production push-up when only the centred fp32 profiles (+ statistics) are wanted.
-//   * persistent, warp-specialised: warp 8 is the TMA producer, warps 0-7 own 256 samples (one per thread);
-//   * work item = (block of 256 samples, group of 8 consecutive chunks); one pipeline stage = one chunk tile
-//     [256 samples x 32 nodes] of X brought in by cp.async.bulk.tensor.2d with SWIZZLE_128B (64 KB of float64 in two
-//     boxes of 16 nodes, or 32 KB of float32 in one) into a 3-stage ring guarded by full/empty mbarriers; rows and
-//     nodes beyond the matrix are zero-filled by the TMA unit;
-//   * a thread lifts its sample's 32 values with 16-byte shared loads (the swizzle makes a warp's 32 row reads hit
-//     all banks: 4 wavefronts per 512 bytes, the minimum), keeps a running prefix r over the chunk in a register and
+//   * persistent, warp-specialised, two CTAs per SM: warp 8 is the TMA producer, warps 0-7 own 256 samples (one per
+//     thread);
+//   * work item = (block of 256 samples, group of 8 consecutive chunks).  One pipeline stage = one TMA box of
+//     256 samples x 128 bytes of X (16 float64 nodes = half a chunk, or 32 float32 nodes = a chunk; 32 KB,
+//     cp.async.bulk.tensor.2d, SWIZZLE_128B) in a 2-stage ring guarded by full/empty mbarriers; rows and nodes beyond
+//     the matrix are zero-filled by the TMA unit.  The stage's node records (weight, centre, plan; 32 bytes per node,
+//     built per job from the static plan and the centre) arrive with it through one bulk copy;
+//   * a thread lifts its sample's values with 16-byte shared loads (the swizzle makes a warp's 32 row reads hit all
+//     banks: 4 wavefronts per 512 bytes, the minimum), keeps a running prefix r over the chunk in a register and
 //     gets every subtree sum inside the chunk as S = x (leaf) or S = r - r[start - 1] (internal; the few prefixes
 //     that are needed again are parked in a [slot][sample] array, at most 12 per chunk): no per-node
-//     read-modify-write of shared memory and no dependency chain through it.  The difference of two prefixes of at most 32 same-sign terms is
-//     accurate to ~1e-16 of the chunk's mass — far below the fp32 rounding of the output; the float64 profiles the
-//     refinement pass needs are produced on demand by the chunk kernel above, in the reference's operation order;
-//   * the chunk's 32 node records (weight, centre, packed plan word; 1 KB, built per job from the static plan and the
-//     centre) arrive with the tile through one bulk copy; the per-node code is branch-free (selects, predicated
-//     accesses) so that the 32 nodes overlap;
-//   * stores: PT rows, 128 bytes per warp and node; chunk totals T and checkpoints CP for the span kernel; one
-//     rounding-error partial R per (group of 8 chunks, sample) — a fixed grouping, so the statistic does not depend
-//     on the launch geometry.
+//     read-modify-write of shared memory and no dependency chain through it.  The difference of two prefixes of at
+//     most 32 same-sign terms is accurate to ~1e-16 of the chunk's mass — far below the fp32 rounding of the output;
+//     the float64 profiles the refinement pass needs are produced on demand by the chunk kernel above, in the
+//     reference's operation order;
+//   * the per-node code is branch-free (selects, predicated accesses; the parked prefixes go through inline PTX that
+//     the compiler knows not to alias the record loads), so the nodes of a stage overlap: with four warps per
+//     scheduler it is this instruction-level parallelism that hides the conversion and shared-memory latencies;
+//   * stores: PT rows, 128 bytes per warp and node; chunk totals T, group totals GT and checkpoints CP for the span
+//     kernel; one rounding-error partial R per (group of 8 chunks, sample) — a fixed grouping, so the statistic does
+//     not depend on the launch geometry.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PT_STAGES = 3;
-constexpr uint32_t PT_STAGE_BYTES = PT_SAMPLES * KT * sizeof(double);   // 64 KB (float32 input fills half of it)
-constexpr uint32_t PT_NODE_BYTES = KT * 32;                              // 1 KB of node records (PushRec) per stage
+constexpr int PT_STAGES = 2;
+constexpr uint32_t PT_STAGE_BYTES = PT_SAMPLES * 128;                     // 32 KB: one 128-byte row per sample
+constexpr uint32_t PT_REC_BYTES = KT * 32;                                // up to 1 KB of node records per stage
 constexpr uint32_t PT_PARK_BYTES = kPushParkSlots * PT_SAMPLES * sizeof(double);   // 24 KB: [slot][sample]
-constexpr uint32_t PT_SMEM_BYTES = PT_STAGES * (PT_STAGE_BYTES + PT_NODE_BYTES) + PT_PARK_BYTES + 1024 /* alignment */ +
-                                   64 /* barriers */;
+constexpr uint32_t pt_smem_bytes(int spt)      // spt = samples per thread (tile = spt x 256 samples)
+{
+    return PT_STAGES * (spt * PT_STAGE_BYTES + PT_REC_BYTES) + spt * PT_PARK_BYTES + 1024 /* alignment */ + 64 /* barriers */;
+}
 
-// Per-job record of one node: the static plan (PushNode) joined with the job's centre value, 32 bytes, so that one
-// 1 KB bulk copy per chunk brings everything the consumers need besides X.
+// Per-job record of one node: the static plan (PushNode) joined with the job's centre value, 32 bytes.
 struct PushRec {
-    double w, c;
-    int32_t meta, pad[3];
+    double w, c;               // weight, centre (both 0 for nodes this kernel does not write: the value and its error vanish)
+    int32_t keep_off;          // byte offset of the park slot that keeps the prefix after this node; < 0: none
+    int32_t take_off;          // byte offset of the parked prefix to subtract; -1: none (S = prefix); -2: leaf-like (S = x)
+    int32_t store;             // -1 (all ones): this kernel writes the node's output; 0: somebody else does / padding
+    int32_t cp_slot;           // checkpoint slot of the span kernel; < 0: none
 };
 
 __global__ void __launch_bounds__(256)
 push_records_kernel(const PushNode *__restrict__ node, const double *__restrict__ center, int32_t n, int32_t n_padded,
-                    PushRec *__restrict__ out)
+                    int32_t slot_bytes, PushRec *__restrict__ out)
 {
     const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_padded) return;
     const PushNode nd = node[k];
+    const int32_t m = nd.meta, keep = (m >> 4) & 15, take = (m >> 8) & 15;
+    const bool leaf = m & 1, skip = m & 2;
     PushRec r;
-    r.w = nd.w;
-    r.c = (center && k < n && !(nd.meta & 1)) ? center[k] : 0.0;     // leaf-like nodes carry no centre
-    r.meta = nd.meta;
-    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    r.w = skip ? 0.0 : nd.w;
+    r.c = (center && k < n && !leaf && !skip) ? center[k] : 0.0;      // leaf-like nodes carry no centre
+    r.keep_off = keep ? (keep - 1) * slot_bytes : -1;
+    r.take_off = leaf ? -2 : (take ? (take - 1) * slot_bytes : -1);
+    r.store = skip ? 0 : -1;
+    r.cp_slot = (int32_t)((uint32_t)m >> 16) - 1;
     out[k] = r;
 }
 
 struct PushTmaParams {
     const PushRec *rec;        // [n_chunks * 32]
     float *PT;
-    int64_t ldp, col0, N, ldt;
+    int64_t col0, N, ldt;
+    uint32_t ldp;
     int32_t n, n_chunks, n_groups, n_items;
     double *T, *CP, *R;        // chunk totals, checkpoints (nullptr without spanning nodes), error partials (nullptr: none)
     double *GT;                // totals of whole groups of PT_GROUP chunks (nullptr without spanning nodes)
 };
 
 __device__ __forceinline__ uint32_t pu_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// try_wait with a suspend-time hint: a waiting warp sleeps in the barrier unit instead of spinning through the issue slots
+// of the warps that have work (the producer waits most of the time); bounded, so a broken pipeline is a CUDA error
 __device__ __forceinline__ void pu_mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
-        if (spin > (1u << 26)) __trap();   // a broken pipeline is a CUDA error, not a hung GPU
+        if (spin > (1u << 22)) __trap();
     }
 }
+// Parked prefixes are touched only through these two (volatile, so they keep their order among themselves; no memory
+// clobber, so the compiler is free to move the record loads across them — the park array aliases nothing it reads).
+__device__ __forceinline__ void park_store(uint32_t park, int32_t off, double r)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\t@p st.shared.f64 [%0], %2;\n\t}" ::"r"(park + (uint32_t)off), "r"(off), "d"(r));
+}
+__device__ __forceinline__ double park_load(uint32_t park, int32_t off)
+{
+    double v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.shared.f64 %0, [%1];\n\t}"
+                 : "=d"(v)
+                 : "r"(park + (uint32_t)off), "r"(off));
+    return v;
+}
 
-template <typename TX, int MODE, bool WANT_ERR>
-__global__ void __launch_bounds__(PT_SAMPLES + 32, 1)
+// the store of a checkpoint is rare (1.5 per chunk): kept out of line so that the node loop pays a compare and a branch
+// for it, not a dozen predicated address instructions
+__device__ __noinline__ void checkpoint_store(double *CP, int64_t ldt, int32_t slot, int64_t s, double r)
+{
+    CP[(int64_t)slot * ldt + s] = r;
+}
+__device__ __forceinline__ void store_if(float *q, float v, int32_t cond)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(q), "f"(v), "r"(cond) : "memory");
+}
+
+template <typename TX, int MODE, bool WANT_ERR, int SPT>
+__global__ void __launch_bounds__(PT_SAMPLES + 32, SPT == 1 ? 2 : 1)
 pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams p)
 {
+    // SPT samples per thread: the plan decoding, record loads and address arithmetic of a node are shared by the SPT
+    // samples a thread owns (rows tid, tid + 256, ... of a tile of SPT x 256 samples); SPT = 2 halves that overhead per
+    // entry and doubles the independent work per thread, at one CTA per SM instead of two.
+    constexpr int NPS = 128 / (int)sizeof(TX);          // nodes per stage: 16 (float64) or 32 (float32)
+    constexpr int SPC = KT / NPS;                        // stages per chunk: 2 or 1
+    constexpr uint32_t STAGE = SPT * PT_STAGE_BYTES;
+    constexpr int TILE_SAMPLES = SPT * PT_SAMPLES;
     extern __shared__ unsigned char pu_smem[];
     const uint32_t base = (pu_smem_u32(pu_smem) + 1023u) & ~1023u;      // SWIZZLE_128B atoms sit on 1 KB boundaries
-    const uint32_t nodes0 = base + PT_STAGES * PT_STAGE_BYTES;          // per stage: the chunk's 32 plan records
-    const uint32_t park0 = nodes0 + PT_STAGES * PT_NODE_BYTES;
-    const uint32_t full0 = park0 + PT_PARK_BYTES, empty0 = full0 + 8 * PT_STAGES;
+    const uint32_t recs0 = base + PT_STAGES * STAGE;                    // per stage: the records of its nodes
+    const uint32_t park0 = recs0 + PT_STAGES * PT_REC_BYTES;
+    const uint32_t full0 = park0 + SPT * PT_PARK_BYTES, empty0 = full0 + 8 * PT_STAGES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < PT_STAGES; s++) {
@@ -219,7 +265,6 @@ pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    constexpr uint32_t TX_BYTES = PT_SAMPLES * KT * sizeof(TX);
 
     if (warp == PT_SAMPLES / 32) {
         // ===================== producer: one lane issues every TMA load =====================
@@ -228,101 +273,118 @@ pushup_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PushTmaParams 
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sb = item / p.n_groups, g = item % p.n_groups;
-                const int c_end = min(p.n_chunks, (g + 1) * PT_GROUP);
-                for (int c = g * PT_GROUP; c < c_end; ++c, ++it) {
+                const int st_end = min(p.n_chunks, (g + 1) * PT_GROUP) * SPC;
+                for (int st = g * PT_GROUP * SPC; st < st_end; ++st, ++it) {
                     const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
                     pu_mbar_wait(empty0 + 8 * slot, phase ^ 1u);
-                    const uint32_t full = full0 + 8 * slot, dst = base + slot * PT_STAGE_BYTES;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(TX_BYTES + PT_NODE_BYTES) : "memory");
-                    // the chunk's plan records ride along (the table is padded to whole chunks)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(nodes0 + slot * PT_NODE_BYTES), "l"(p.rec + (int64_t)c * KT), "r"(PT_NODE_BYTES), "r"(full)
-                                 : "memory");
-                    constexpr int BOXES = sizeof(TX) == 8 ? 2 : 1;     // 128-byte inner box: 16 doubles or 32 floats
+                    const uint32_t full = full0 + 8 * slot;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(STAGE + NPS * 32) : "memory");
 #pragma unroll
-                    for (int bx = 0; bx < BOXES; bx++)
+                    for (int q = 0; q < SPT; q++)      // one box of 256 samples x 128 bytes per owned sample
                         asm volatile(
                             "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                            ::"r"(dst + bx * (PT_SAMPLES * 128)), "l"(&tmap), "r"(full), "r"(c * KT + bx * 16),
-                            "r"(sb * PT_SAMPLES)
+                            ::"r"(base + slot * STAGE + q * PT_STAGE_BYTES), "l"(&tmap), "r"(full), "r"(st * NPS),
+                            "r"(sb * TILE_SAMPLES + q * PT_SAMPLES)
                             : "memory");
+                    // the stage's node records ride along (the table is padded to whole chunks)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(recs0 + slot * PT_REC_BYTES), "l"(p.rec + (int64_t)st * NPS), "r"(NPS * 32), "r"(full)
+                                 : "memory");
                 }
             }
         }
         return;
     }
 
-    // ===================== consumers: thread = sample =====================
-    // Everything below is written branch-free per node (selects and predicated accesses): the 32 nodes of a chunk are
-    // independent except for the running prefix, and with two warps per scheduler it is the instruction-level
-    // parallelism across nodes that hides the conversion and shared-memory latencies.
+    // ===================== consumers =====================
     unsigned char *gbase = pu_smem + (base - pu_smem_u32(pu_smem));       // generic pointer to the aligned ring
-    const uint32_t sw = (uint32_t)(tid & 7) << 4;                  // XOR term of this row's 16-byte units
+    const uint32_t sw = (uint32_t)(tid & 7) << 4;                         // XOR term of this row's 16-byte units
     const uint32_t row = (uint32_t)tid * 128u;
-    // parked prefixes: [slot][sample], each thread its own column (conflict-free, never shared between threads)
-    double *park = reinterpret_cast<double *>(gbase + (park0 - base)) + tid;
+    const uint32_t park = park0 + tid * (uint32_t)sizeof(double);         // [sample of the thread][slot][thread]
+    const uint32_t ldp = p.ldp;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int sb = item / p.n_groups, g = item % p.n_groups;
         const int c_end = min(p.n_chunks, (g + 1) * PT_GROUP);
-        const int64_t s = (int64_t)sb * PT_SAMPLES + tid;
-        const bool live = s < p.N;
-        double err = 0.0, group_total = 0.0;
-        for (int c = g * PT_GROUP; c < c_end; ++c, ++it) {
-            const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
-            unsigned char *stage = gbase + slot * PT_STAGE_BYTES;
-            const PushRec *rec = reinterpret_cast<const PushRec *>(gbase + PT_STAGES * PT_STAGE_BYTES + slot * PT_NODE_BYTES);
-            pu_mbar_wait(full0 + 8 * slot, phase);
-            double x[KT];
-            if (sizeof(TX) == 8) {
+        const int64_t s0 = (int64_t)sb * TILE_SAMPLES + tid;
+        int32_t live_mask[SPT];
+        double err[SPT], group_total[SPT];
 #pragma unroll
-                for (int bx = 0; bx < 2; bx++)
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const double2 v = *reinterpret_cast<const double2 *>(stage + bx * (PT_SAMPLES * 128) + row + (((uint32_t)u << 4) ^ sw));
-                        x[bx * 16 + 2 * u] = v.x;
-                        x[bx * 16 + 2 * u + 1] = v.y;
-                    }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float4 v = *reinterpret_cast<const float4 *>(stage + row + (((uint32_t)u << 4) ^ sw));
-                    x[4 * u] = (double)v.x, x[4 * u + 1] = (double)v.y, x[4 * u + 2] = (double)v.z, x[4 * u + 3] = (double)v.w;
-                }
-            }
-            float *pt = p.PT + (int64_t)c * KT * p.ldp + p.col0 + s;
-            double r = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < KT; kk++) {
-                const double2 wc = *reinterpret_cast<const double2 *>(&rec[kk].w);   // same address in every lane: a broadcast
-                const int32_t meta = rec[kk].meta;
-                const bool leaf = meta & 1, skip = meta & 2;
-                r += x[kk];
-                const int keep = (meta >> 4) & 15, take = (meta >> 8) & 15;
-                if (keep) park[(keep - 1) * PT_SAMPLES] = r;
-                double parked = 0.0;
-                if (take) parked = park[(take - 1) * PT_SAMPLES];       // only internal nodes have one
-                const double S = leaf ? x[kk] : r - parked;
-                const double v = __dsub_rn(__dmul_rn(wc.x, S), wc.y);    // fl(w S) - c like the reference (no FMA); leaf-like: c = 0
-                const float f = (float)v;
-                if (live && !skip) *pt = f;
-                pt += p.ldp;
-                if (WANT_ERR) {
-                    const double e = v - (double)f;
-                    const double a = (MODE == FUF_MODE_L2) ? e * e : fabs(e);
-                    err += skip ? 0.0 : a;
-                }
-                if (meta & 8) {                                        // a checkpoint for the span kernel (rare)
-                    if (live) p.CP[(int64_t)(((uint32_t)meta >> 16) - 1) * p.ldt + s] = r;
-                }
-            }
-            if (p.T && live) p.T[(int64_t)c * p.ldt + s] = r;
-            group_total += r;
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
+        for (int q = 0; q < SPT; q++) {
+            live_mask[q] = (s0 + q * PT_SAMPLES < p.N) ? -1 : 0;
+            err[q] = 0.0;
+            group_total[q] = 0.0;
         }
-        if (p.GT && live) p.GT[(int64_t)g * p.ldt + s] = group_total;
-        if (WANT_ERR && live) p.R[(int64_t)g * p.ldt + s] = err;
+        for (int c = g * PT_GROUP; c < c_end; ++c) {
+            float *pt = p.PT + (int64_t)c * KT * ldp + p.col0 + s0;
+            double r[SPT];
+#pragma unroll
+            for (int q = 0; q < SPT; q++) r[q] = 0.0;
+#pragma unroll
+            for (int h = 0; h < SPC; ++h, ++it) {
+                const uint32_t slot = it % PT_STAGES, phase = (it / PT_STAGES) & 1u;
+                const unsigned char *stage = gbase + slot * STAGE;
+                const PushRec *rec = reinterpret_cast<const PushRec *>(gbase + PT_STAGES * STAGE + slot * PT_REC_BYTES);
+                pu_mbar_wait(full0 + 8 * slot, phase);
+                double x[SPT][NPS];
+#pragma unroll
+                for (int q = 0; q < SPT; q++) {
+                    if (sizeof(TX) == 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const double2 v = *reinterpret_cast<const double2 *>(stage + q * PT_STAGE_BYTES + row + (((uint32_t)u << 4) ^ sw));
+                            x[q][2 * u] = v.x;
+                            x[q][2 * u + 1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const float4 v = *reinterpret_cast<const float4 *>(stage + q * PT_STAGE_BYTES + row + (((uint32_t)u << 4) ^ sw));
+                            x[q][4 * u] = (double)v.x, x[q][4 * u + 1] = (double)v.y, x[q][4 * u + 2] = (double)v.z, x[q][4 * u + 3] = (double)v.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < NPS; kk++) {
+                    // two 16-byte loads, the same address in every lane (broadcasts): weight + centre, plan
+                    const double2 wc = *reinterpret_cast<const double2 *>(&rec[kk].w);
+                    const int4 f = *reinterpret_cast<const int4 *>(&rec[kk].keep_off);
+                    const bool leaf = f.y == -2;
+                    float *row_ptr = pt + (size_t)(h * NPS + kk) * ldp;
+#pragma unroll
+                    for (int q = 0; q < SPT; q++) {
+                        r[q] += x[q][kk];
+                        park_store(park + q * PT_PARK_BYTES, f.x, r[q]);
+                        const double parked = park_load(park + q * PT_PARK_BYTES, f.y);   // 0 unless an internal node has one
+                        const double S = leaf ? x[q][kk] : r[q] - parked;
+                        const double v = fma(wc.x, S, -wc.y);                // w S - c (leaf-like: c = 0, so v = fl(w S))
+                        const float fl = (float)v;
+                        store_if(row_ptr + q * PT_SAMPLES, fl, f.z & live_mask[q]);
+                        if (WANT_ERR) {
+                            const double e = v - (double)fl;                 // nodes written elsewhere: w = c = 0, so e = 0
+                            err[q] += (MODE == FUF_MODE_L2) ? e * e : fabs(e);
+                        }
+                    }
+                    if (f.w >= 0) {                                          // a checkpoint for the span kernel (rare)
+#pragma unroll
+                        for (int q = 0; q < SPT; q++)
+                            if (live_mask[q]) checkpoint_store(p.CP, p.ldt, f.w, s0 + q * PT_SAMPLES, r[q]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
+            }
+#pragma unroll
+            for (int q = 0; q < SPT; q++) {
+                if (p.T && live_mask[q]) p.T[(int64_t)c * p.ldt + s0 + q * PT_SAMPLES] = r[q];
+                group_total[q] += r[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            if (p.GT && live_mask[q]) p.GT[(int64_t)g * p.ldt + s0 + q * PT_SAMPLES] = group_total[q];
+            if (WANT_ERR && live_mask[q]) p.R[(int64_t)g * p.ldt + s0 + q * PT_SAMPLES] = err[q];
+        }
     }
 }
 
@@ -614,7 +676,7 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
     if (use_tma) {
         CUtensorMap tmap;
         const cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)N}, gstride[1] = {(cuuint64_t)ldx * esz};
-        const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), PT_SAMPLES}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), PT_SAMPLES}, estr[2] = {1, 1};   // one 128-byte row per sample
         CUresult cres = tensor_map_encoder()(&tmap, x_dtype == FUF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                                              2, const_cast<void *>(X), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -629,20 +691,26 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
         int rc2 = ctx->ws_rec.reserve((size_t)n_padded * sizeof(PushRec));
         if (rc2) return rc2;
         PushRec *recs = (PushRec *)ctx->ws_rec.ptr;
-        push_records_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, stream>>>(ctx->d_push_node[mode], center, n, n_padded, recs);
+        push_records_kernel<<<(unsigned)((n_padded + 255) / 256), 256, 0, stream>>>(ctx->d_push_node[mode], center, n, n_padded,
+                                                                                   PT_SAMPLES * (int)sizeof(double), recs);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
         PushTmaParams p;
         p.rec = recs;
         p.PT = PT;
-        p.ldp = ldp;
+        FUF_REQUIRE(ldp < ((int64_t)1 << 31), "fuf_push_up: ldp too large");
+        p.ldp = (uint32_t)ldp;
         p.col0 = col0;
         p.N = N;
         p.ldt = ldt;
         p.n = n;
         p.n_chunks = ctx->n_chunks;
         p.n_groups = n_groups;
-        const int64_t n_sb = (N + PT_SAMPLES - 1) / PT_SAMPLES;
+        // One sample per thread, two CTAs per SM.  (FUF_PUSHUP_SPT=2: two samples per thread, one CTA per SM — measured
+        // the same 0.65 ms at N = 10,000: the kernel is at the DRAM roof either way, and smaller tiles suit small N.)
+        const char *spt_env = getenv("FUF_PUSHUP_SPT");
+        const int spt = (spt_env && atoi(spt_env) == 2) ? 2 : 1;
+        const int64_t n_sb = (N + spt * PT_SAMPLES - 1) / (spt * PT_SAMPLES);
         FUF_REQUIRE(n_sb * n_groups < ((int64_t)1 << 31), "fuf_push_up: N = %lld too large for one call", (long long)N);
         p.n_items = (int32_t)(n_sb * n_groups);
         p.T = T;
@@ -650,14 +718,19 @@ int push_up_f32(fuf_ctx *ctx, const void *X, int x_dtype, int64_t N, int64_t ldx
         p.R = want_err ? R : nullptr;
         p.GT = GT;
         void (*kern)(const CUtensorMap, const PushTmaParams) = nullptr;
-#define FUF_TMA_KERN(TX)                                                                                             \
-    kern = mode == FUF_MODE_L1 ? (want_err ? pushup_tma_kernel<TX, 0, true> : pushup_tma_kernel<TX, 0, false>)        \
-                               : (want_err ? pushup_tma_kernel<TX, 1, true> : pushup_tma_kernel<TX, 1, false>)
-        if (x_dtype == FUF_F32) FUF_TMA_KERN(float); else FUF_TMA_KERN(double);
+#define FUF_TMA_KERN(TX, SPT_)                                                                                          \
+    kern = mode == FUF_MODE_L1 ? (want_err ? pushup_tma_kernel<TX, 0, true, SPT_> : pushup_tma_kernel<TX, 0, false, SPT_>) \
+                               : (want_err ? pushup_tma_kernel<TX, 1, true, SPT_> : pushup_tma_kernel<TX, 1, false, SPT_>)
+        if (x_dtype == FUF_F32) {
+            if (spt == 2) FUF_TMA_KERN(float, 2); else FUF_TMA_KERN(float, 1);
+        } else {
+            if (spt == 2) FUF_TMA_KERN(double, 2); else FUF_TMA_KERN(double, 1);
+        }
 #undef FUF_TMA_KERN
-        FUF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_BYTES));
-        const int grid_t = (int)std::min<int64_t>(p.n_items, ctx->sm_count);
-        kern<<<grid_t, PT_SAMPLES + 32, PT_SMEM_BYTES, stream>>>(tmap, p);
+        const uint32_t smem_t = pt_smem_bytes(spt);
+        FUF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        const int grid_t = (int)std::min<int64_t>(p.n_items, (spt == 1 ? 2 : 1) * ctx->sm_count);
+        kern<<<grid_t, PT_SAMPLES + 32, smem_t, stream>>>(tmap, p);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     } else {

@@ -124,6 +124,22 @@ def _stream_ptr(torch) -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def padded_nodes(n: int, itemsize: int = 8) -> int:
+    """Row pitch (in elements) for un-pushed profile matrices X[N, n]: n rounded up so that a row is a whole number of
+    128-byte lines.  The TMA push-up kernel needs 16-byte aligned rows; with 128 its boxes never straddle sectors."""
+    per = 128 // itemsize
+    return (n + per - 1) // per * per
+
+
+def profile_matrix(N: int, n: int, dtype=None, device=None, pin_memory: bool = False):
+    """Zeroed X[N, n] (a view into an [N, padded_nodes(n)] buffer, so rows are 128-byte aligned)."""
+    torch = _torch()
+    dtype = dtype or torch.float64
+    buf = torch.zeros((max(N, 1), padded_nodes(n, torch.empty(0, dtype=dtype).element_size())), dtype=dtype,
+                      device=device, pin_memory=pin_memory)
+    return buf[:N, :n]
+
+
 def padded_samples(N: int) -> int:
     return max(TILE, (N + TILE - 1) // TILE * TILE)
 

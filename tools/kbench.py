@@ -18,7 +18,7 @@ ctx = engine.TreeContext(inp.parent, inp.edge_length)
 n, N = ctx.n, a.N
 leaves = torch.from_numpy(synth.leaves_of(inp.parent)).cuda()
 g = torch.Generator(device="cuda").manual_seed(0)
-X = torch.zeros((N, n), dtype=torch.float64, device="cuda")
+X = engine.profile_matrix(N, n, torch.float64, "cuda") if not os.environ.get("KB_UNPADDED") else torch.zeros((N, n), dtype=torch.float64, device="cuda")
 vals = torch.rand((N, len(leaves)), generator=g, device="cuda", dtype=torch.float64)
 vals = vals * (torch.rand((N, len(leaves)), generator=g, device="cuda") < 0.2)
 X[:, leaves] = vals
@@ -49,7 +49,7 @@ if "push" in a.what:
     ms = timeit(lambda: b_.copy_(a_))
     print(f"torch copy of {a_.numel()*8/1e9:.2f} GB (read + write = {a_.numel()*16/1e9:.2f} GB): {ms:.3f} ms  {a_.numel()*16/ms/1e6:.0f} GB/s")
     del a_, b_
-    X32 = X.float()
+    X32 = engine.profile_matrix(N, n, torch.float32, "cuda"); X32.copy_(X)
     ms = timeit(lambda: ctx.push_up(X32, a.mode, job.PT, 0, job.center, None, None))
     print(f"push_up f32->f32          N={N}: {ms:.3f} ms  {N*n*8/ms/1e6:.0f} GB/s (8 B/entry)")
     del X32
