@@ -168,10 +168,22 @@ int push_up_center(fuf_ctx *ctx, const void *X, int x_dtype, int64_t m, int64_t 
 int push_up_f64_exact(fuf_ctx *ctx, const double *X, int64_t N, int64_t ldx, int mode, double *P64T, int64_t ldp,
                       int64_t col0, cudaStream_t stream);
 // pairwise.cu
+// Explicit tile list of fuf_pairwise_tiles (multi-GPU: operand shards arrive while the kernel runs; results go straight
+// into the full matrix, wherever it lives; refinement flags are evaluated in the tile epilogues).
+struct PairTileList {
+    const int32_t *tiles_h = nullptr;      // (ti, tj, dependency) triples, ti <= tj; dependency = shard flag index or -1
+    int32_t n_tiles = 0;
+    const uint32_t *dep_flags = nullptr;   // device
+    uint32_t epoch = 0;
+    const double *stat = nullptr;          // device: per-sample rounding statistics (all samples)
+    double kappa = 0.0;
+    long long *flag_list = nullptr;        // device: [0] = count, then (i, j) pairs
+    long long list_cap = 0;
+};
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
                  cudaStream_t stream, int32_t col_tile_begin = 0, int32_t col_tile_end = 0, int32_t n_rows_override = 0,
-                 int32_t flush_stages = 0);
+                 int32_t flush_stages = 0, const PairTileList *list = nullptr);
 int pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, cudaStream_t stream);
 int assemble(fuf_ctx *ctx, const double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N, int64_t ldb,

@@ -38,7 +38,8 @@ constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC64_BYTES + 2 * STAGES 
 struct TileDesc {
     int32_t ti, tj;     // tile coordinates (tj >= ti)
     int32_t out_row0;   // first row of this tile row in the output buffer
-    int32_t mirror;     // also write the transposed tile to (tj, ti)
+    int32_t mirror;     // bit 0: also write the transposed tile to (tj, ti); bits 8-31: dependency + 1 (0 = none): the
+                        // operands of this tile are complete once dep_flags[dependency] has reached the launch's epoch
 };
 
 struct PairParams {
@@ -53,7 +54,32 @@ struct PairParams {
     double *D;
     int64_t ldd;
     double *partial;           // [n_items][TILE*TILE] when splits > 1
+    // multi-GPU tiles mode (fuf_pairwise_tiles): operand shards arrive from peer GPUs while the kernel runs
+    const uint32_t *dep_flags; // device flags, one per shard
+    uint32_t epoch;            // value a flag takes once its shard has landed in this launch's step
+    // refinement flags evaluated where the distances are produced (no separate scan of D): pairs i < j with
+    // D < kappa (s_i + s_j) [L2: kappa (sqrt s_i + sqrt s_j)^2] are counted in flag_list[0] and the first list_cap of
+    // them appended as (i, j) to flag_list[1..]
+    const double *stat;
+    double kappa;
+    long long *flag_list;
+    long long list_cap;
 };
+
+// one pair against the refinement criterion of refine.cu (rounding statistics of the fp32 operands)
+template <int MODE>
+__device__ __forceinline__ void flag_pair(const PairParams &p, int64_t gi, int64_t gj, double d, double si, double sj)
+{
+    const double b = (MODE == FUF_MODE_L2) ? sqrt(si) + sqrt(sj) : si + sj;
+    const bool flag = (MODE == FUF_MODE_L2) ? !(d >= p.kappa * b * b) : !(d >= p.kappa * b);
+    if (flag && b != 0.0) {
+        const unsigned long long at = atomicAdd(reinterpret_cast<unsigned long long *>(p.flag_list), 1ull);
+        if ((long long)at < p.list_cap) {
+            p.flag_list[1 + 2 * at] = gi;
+            p.flag_list[2 + 2 * at] = gj;
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers (sm_100a)
@@ -166,6 +192,19 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
                 const int s_begin = split * p.stages_per_split;
                 const int s_end = min(p.stages_total, s_begin + p.stages_per_split);
                 const int ia = td.ti * TILE, ib = td.tj * TILE;
+                if (td.mirror >> 8) {
+                    // this tile reads a shard that a copy engine is still bringing in from a peer GPU: wait for its
+                    // flag (written in stream order behind the copy), then order the TMA reads behind the observation
+                    const uint32_t *flag = p.dep_flags + ((td.mirror >> 8) - 1);
+                    for (uint32_t spin = 0;; ++spin) {
+                        uint32_t seen;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                        if ((int32_t)(seen - p.epoch) >= 0) break;
+                        if (spin > (1u << 24)) __trap();        // ~3 s: a lost copy is a CUDA error, not a hung GPU
+                        __nanosleep(200);
+                    }
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
                 const int a_col = ia % p.shard, a_sh = ia / p.shard;
                 const int b_col = ib % p.shard, b_sh = ib / p.shard;
                 for (int st = s_begin; st < s_end; ++st, ++it) {
@@ -290,13 +329,15 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
         } else {
             const int64_t gi0 = (int64_t)td.ti * TILE, gj0 = (int64_t)td.tj * TILE;
             if (gj0 + col < p.N) {
+                const double sj = p.stat ? p.stat[gj0 + col] : 0.0;
                 for (int r = half; r < TILE; r += 2)
                     if (gi0 + r < p.N) {
                         const double v = acc64[slot_of(r, col)];
                         p.D[((int64_t)td.out_row0 + r) * p.ldd + gj0 + col] = v;
+                        if (p.stat && gi0 + r < gj0 + col) flag_pair<MODE>(p, gi0 + r, gj0 + col, v, p.stat[gi0 + r], sj);
                     }
             }
-            if (td.mirror && gi0 + col < p.N) {
+            if ((td.mirror & 1) && gi0 + col < p.N) {
                 for (int c = half; c < TILE; c += 2)
                     if (gj0 + c < p.N) {
                         const double v = acc64[slot_of(col, c)];
@@ -309,9 +350,10 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
 }
 
 // Sum the k-split partial tiles in fixed order and write D (+ mirror).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restrict__ partial, int splits, int64_t N,
-                       double *__restrict__ D, int64_t ldd)
+                       double *__restrict__ D, int64_t ldd, const PairParams p)
 {
     const TileDesc td = tiles[blockIdx.x];
     const double *src = partial + (size_t)blockIdx.x * splits * (TILE * TILE);
@@ -326,10 +368,13 @@ reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restr
             for (int s = 0; s < splits; s++) v += src[(size_t)s * (TILE * TILE) + (r0 + rr) * TILE + c0 + lx];
             tile[rr][lx] = v;
             const int64_t gi = gi0 + r0 + rr, gj = gj0 + c0 + lx;
-            if (gi < N && gj < N) D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
+            if (gi < N && gj < N) {
+                D[((int64_t)td.out_row0 + r0 + rr) * ldd + gj] = v;
+                if (p.stat && gi < gj) flag_pair<MODE>(p, gi, gj, v, p.stat[gi], p.stat[gj]);
+            }
         }
         __syncthreads();
-        if (td.mirror) {
+        if (td.mirror & 1) {
             for (int cc = ly; cc < 32; cc += 8) {
                 const int64_t gj = gj0 + c0 + cc, gi = gi0 + r0 + lx;
                 if (gi < N && gj < N) D[gj * ldd + gi] = tile[lx][cc];
@@ -450,7 +495,7 @@ assemble_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ t
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
                  cudaStream_t stream, int32_t col_tile_begin, int32_t col_tile_end, int32_t n_rows_override,
-                 int32_t flush_stages)
+                 int32_t flush_stages, const PairTileList *list)
 {
     if (N == 0) return FUF_OK;
     if (flush_stages <= 0) flush_stages = FLUSH_STAGES;
@@ -503,11 +548,20 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     // ---- tile list: built once per (N, rows, column band), kept on the device (ctx->tables) ----------
     const bool full = (tile_rows_h == nullptr);
     const int32_t n_rows = full ? (int32_t)tiles_per_dim : n_tile_rows;
-    const bool band = full && col_tile_end > 0;
+    const bool band = full && col_tile_end > 0 && !list;
     const int32_t cb = band ? std::max(0, col_tile_begin) : 0;
     const int32_t ce = band ? std::min<int32_t>(col_tile_end, (int32_t)tiles_per_dim) : 0;
     int32_t n_tiles = 0;
-    if (band) {
+    if (list) {
+        // explicit (ti, tj, dependency) triples, global addressing: D[i, j] and D[j, i] of the full matrix
+        for (int32_t c = 0; c < list->n_tiles; c++) {
+            const int32_t ti = list->tiles_h[3 * c], tj = list->tiles_h[3 * c + 1], dep = list->tiles_h[3 * c + 2];
+            FUF_REQUIRE(ti >= 0 && ti <= tj && tj < tiles_per_dim, "fuf_pairwise_tiles: tile (%d, %d) outside the upper "
+                        "triangle of %lld tile rows", ti, tj, (long long)tiles_per_dim);
+            FUF_REQUIRE(dep >= -1 && dep < (1 << 20) && (dep < 0 || list->dep_flags), "fuf_pairwise_tiles: bad dependency %d", dep);
+        }
+        n_tiles = list->n_tiles;
+    } else if (band) {
         for (int32_t tj = cb; tj < ce; tj++) n_tiles += tj + 1;
     } else {
         for (int32_t c = 0; c < n_rows; c++) {
@@ -518,17 +572,23 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
         }
     }
     if (n_tiles == 0) return FUF_OK;
-    std::string key("pw");
+    std::string key(list ? "pt" : "pw");
     key_append(key, tiles_per_dim);
     key_append(key, cb);
     key_append(key, ce);
     key_append(key, n_rows);
-    if (!full) key.append((const char *)tile_rows_h, (size_t)n_rows * sizeof(int32_t));
+    if (list) key.append((const char *)list->tiles_h, (size_t)n_tiles * 3 * sizeof(int32_t));
+    else if (!full) key.append((const char *)tile_rows_h, (size_t)n_rows * sizeof(int32_t));
     TileDesc *d_tiles = (TileDesc *)ctx->tables.find(key);
     if (!d_tiles) {
         std::vector<TileDesc> tiles;
         tiles.reserve(n_tiles);
-        if (band) {
+        if (list) {
+            for (int32_t c = 0; c < n_tiles; c++) {
+                const int32_t ti = list->tiles_h[3 * c], tj = list->tiles_h[3 * c + 1], dep = list->tiles_h[3 * c + 2];
+                tiles.push_back(TileDesc{ti, tj, ti * TILE, (tj != ti ? 1 : 0) | ((dep + 1) << 8)});
+            }
+        } else if (band) {
             // column band [cb, ce) of the upper triangle (the host-buffer path computes the matrix band by band
             // while later samples are still in flight over PCIe)
             for (int32_t tj = cb; tj < ce; tj++)
@@ -585,6 +645,13 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     p.D = D;
     p.ldd = ldd;
     p.partial = d_partial;
+    p.dep_flags = list ? list->dep_flags : nullptr;
+    p.epoch = list ? list->epoch : 0;
+    p.stat = list ? list->stat : nullptr;
+    p.kappa = (list && list->kappa > 0) ? list->kappa : (mode == FUF_MODE_L2 ? 1.6e13 : 2e6);
+    p.flag_list = list ? list->flag_list : nullptr;
+    p.list_cap = list ? list->list_cap : 0;
+    if (!p.flag_list) p.stat = nullptr;
 
     const bool packed = !(flags & FUF_PW_SCALAR_MATH);
     void (*kern)(const CUtensorMap, const PairParams) = nullptr;
@@ -598,7 +665,11 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
     if (splits > 1) {
-        reduce_partials_kernel<<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd);
+        PairParams pr = p;
+        if (mode == FUF_MODE_L1)
+            reduce_partials_kernel<FUF_MODE_L1><<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd, pr);
+        else
+            reduce_partials_kernel<FUF_MODE_L2><<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd, pr);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }
@@ -852,7 +923,32 @@ extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ld
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_f32(ctx, PT, N, ldp, shard, shard_stride, mode, tile_rows_h, n_tile_rows, D, ldd, flags,
-                        (cudaStream_t)stream, 0, 0, 0, 0);
+                        (cudaStream_t)stream, 0, 0, 0, 0, nullptr);
+}
+
+extern "C" int fuf_pairwise_tiles(fuf_ctx *ctx, const float *PT, int64_t N, int64_t shard, int64_t shard_stride, int mode,
+                                  const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch,
+                                  double *D, int64_t ldd, const double *err_stat, double kappa, int64_t *flag_list,
+                                  int64_t list_cap, void *stream)
+{
+    FUF_REQUIRE(ctx && PT && D && (tiles_h || n_tiles == 0), "fuf_pairwise_tiles: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_pairwise_tiles: bad mode %d", mode);
+    FUF_REQUIRE(N >= 0 && ldd >= N && n_tiles >= 0, "fuf_pairwise_tiles: bad shape N=%lld ldd=%lld", (long long)N, (long long)ldd);
+    FUF_REQUIRE(shard > 0, "fuf_pairwise_tiles: the operands are the sharded layout [G][n][shard]");
+    FUF_REQUIRE(!flag_list || (err_stat && list_cap >= 0), "fuf_pairwise_tiles: flag_list needs err_stat");
+    if (n_tiles == 0) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    PairTileList list;
+    list.tiles_h = tiles_h;
+    list.n_tiles = n_tiles;
+    list.dep_flags = dep_flags;
+    list.epoch = epoch;
+    list.stat = err_stat;
+    list.kappa = kappa;
+    list.flag_list = (long long *)flag_list;
+    list.list_cap = list_cap;
+    return pairwise_f32(ctx, PT, N, 0, shard, shard_stride, mode, nullptr, 0, D, ldd, 0, (cudaStream_t)stream, 0, 0, 0, 0,
+                        &list);
 }
 
 extern "C" int fuf_pairwise_f64(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp, int64_t shard,

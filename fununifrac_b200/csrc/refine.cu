@@ -138,6 +138,46 @@ refine_kernel(const RefineParams p)
     }
 }
 
+// K6l refine_list_kernel: the pairs a tile epilogue flagged (fuf_pairwise_tiles), one warp per pair, recomputed from the
+// float64 profiles and written to D[i, j] and D[j, i] of the full matrix (which may live on a peer GPU or in mapped
+// host memory: plain stores).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+refine_list_kernel(const long long *__restrict__ list, long long cap, const double *__restrict__ P64T, int64_t ldp64,
+                   int64_t shard, int64_t shard_stride, int32_t n, double *__restrict__ D, int64_t ldd)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long count = min(list[0], cap);
+    const int64_t kstride = shard == 0 ? ldp64 : shard;
+    for (long long q = warp; q < count; q += n_warps) {
+        const int64_t i = list[1 + 2 * q], j = list[2 + 2 * q];
+        const double *a = P64T + (shard == 0 ? i : (i / shard) * shard_stride + i % shard);
+        const double *b = P64T + (shard == 0 ? j : (j / shard) * shard_stride + j % shard);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int32_t k = lane;
+        for (; k + 96 < n; k += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double d = fabs(__dsub_rn(a[(int64_t)(k + 32 * u) * kstride], b[(int64_t)(k + 32 * u) * kstride]));
+                acc[u] = __dadd_rn(acc[u], MODE == FUF_MODE_L2 ? __dmul_rn(d, d) : d);
+            }
+        }
+        for (; k < n; k += 32) {
+            const double d = fabs(__dsub_rn(a[(int64_t)k * kstride], b[(int64_t)k * kstride]));
+            acc[0] = __dadd_rn(acc[0], MODE == FUF_MODE_L2 ? __dmul_rn(d, d) : d);
+        }
+        double v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            D[i * ldd + j] = v;
+            D[j * ldd + i] = v;
+        }
+    }
+}
+
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,
            int64_t ldd, cudaStream_t stream, int64_t j_begin, int64_t j_end, bool reset_counter, int criterion,
@@ -213,6 +253,31 @@ extern "C" int fuf_refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t l
     FUF_CUDA(cudaSetDevice(ctx->device));
     return refine(ctx, P64T, N, ldp64, shard, shard_stride, mode, err_stat, kappa, tile_rows_h, n_tile_rows, D, ldd,
                   (cudaStream_t)stream, 0, N, true, criterion, lin_stat, lin_kappa, max_pairs);
+}
+
+extern "C" int fuf_refine_list(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard,
+                               int64_t shard_stride, int mode, const int64_t *flag_list, int64_t list_cap, double *D,
+                               int64_t ldd, void *stream)
+{
+    FUF_REQUIRE(ctx && P64T && flag_list && D, "fuf_refine_list: null argument");
+    FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_refine_list: bad mode %d", mode);
+    FUF_REQUIRE(N >= 0 && ldd >= N && list_cap >= 0, "fuf_refine_list: bad shape");
+    if (shard == 0)
+        FUF_REQUIRE(ldp64 >= N, "fuf_refine_list: ldp64=%lld < N=%lld", (long long)ldp64, (long long)N);
+    else
+        FUF_REQUIRE(shard > 0 && shard_stride >= shard * (int64_t)ctx->n, "fuf_refine_list: bad shard layout");
+    if (list_cap == 0 || N < 2) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    const int grid = ctx->sm_count * 4;
+    if (mode == FUF_MODE_L1)
+        refine_list_kernel<FUF_MODE_L1><<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)flag_list, list_cap, P64T, ldp64,
+                                                                                 shard, shard_stride, ctx->n, D, ldd);
+    else
+        refine_list_kernel<FUF_MODE_L2><<<grid, 256, 0, (cudaStream_t)stream>>>((const long long *)flag_list, list_cap, P64T, ldp64,
+                                                                                 shard, shard_stride, ctx->n, D, ldd);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
 }
 
 extern "C" int fuf_refine_count(fuf_ctx *ctx, int64_t *refined, void *stream)

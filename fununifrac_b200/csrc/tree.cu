@@ -476,4 +476,107 @@ extern "C" int fuf_tree_get_info(const fuf_ctx *ctx, fuf_tree_info *info)
     return FUF_OK;
 }
 
+// ---- peer memory: one process per GPU on one node shares device buffers through CUDA IPC handles ----------------
+extern "C" int fuf_peer_alloc(fuf_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64])
+{
+    FUF_REQUIRE(ctx && dptr && handle, "fuf_peer_alloc: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    cudaError_t err = cudaMalloc(&p, bytes ? bytes : 1);
+    if (err != cudaSuccess) {
+        set_error("fuf_peer_alloc: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+        cudaGetLastError();
+        return FUF_ENOMEM;
+    }
+    cudaIpcMemHandle_t h;
+    err = cudaIpcGetMemHandle(&h, p);
+    if (err != cudaSuccess) {
+        cudaFree(p);
+        set_error("fuf_peer_alloc: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(err));
+        cudaGetLastError();
+        return FUF_ECUDA;
+    }
+    FUF_CUDA(cudaMemset(p, 0, bytes ? bytes : 1));
+    memcpy(handle, &h, 64);
+    *dptr = p;
+    return FUF_OK;
+}
+
+extern "C" int fuf_peer_open(fuf_ctx *ctx, const unsigned char handle[64], void **dptr)
+{
+    FUF_REQUIRE(ctx && dptr && handle, "fuf_peer_open: null argument");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    *dptr = nullptr;
+    FUF_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FUF_OK;
+}
+
+extern "C" int fuf_peer_close(fuf_ctx *ctx, void *dptr)
+{
+    FUF_REQUIRE(ctx, "fuf_peer_close: null context");
+    if (!dptr) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    FUF_CUDA(cudaIpcCloseMemHandle(dptr));
+    return FUF_OK;
+}
+
+extern "C" int fuf_peer_free(fuf_ctx *ctx, void *dptr)
+{
+    FUF_REQUIRE(ctx, "fuf_peer_free: null context");
+    if (!dptr) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    FUF_CUDA(cudaFree(dptr));
+    return FUF_OK;
+}
+
+// Device-side address of page-locked (cudaHostAlloc / cudaHostRegister) host memory: what a kernel stores through when
+// the result matrix lives in host memory shared by the ranks of a node.
+extern "C" int fuf_host_device_pointer(fuf_ctx *ctx, void *host_ptr, void **dptr)
+{
+    FUF_REQUIRE(ctx && host_ptr && dptr, "fuf_host_device_pointer: null argument");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    FUF_CUDA(cudaHostGetDevicePointer(dptr, host_ptr, 0));
+    return FUF_OK;
+}
+
+// Asynchronous copy between any two device-accessible buffers (own memory, a peer's IPC mapping): the copy engines
+// pull a peer's shard over NVLink while the SMs compute.
+extern "C" int fuf_copy_async(fuf_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream)
+{
+    FUF_REQUIRE(ctx && dst && src, "fuf_copy_async: null argument");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    if (bytes) FUF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return FUF_OK;
+}
+
+// Stream-ordered 32-bit write without an SM (cuStreamWriteValue32): the "shard has landed" flag a running kernel polls.
+extern "C" int fuf_stream_write_u32(fuf_ctx *ctx, uint32_t *dptr, uint32_t value, void *stream)
+{
+    FUF_REQUIRE(ctx && dptr, "fuf_stream_write_u32: null argument");
+    FUF_REQUIRE(((uintptr_t)dptr & 3) == 0, "fuf_stream_write_u32: unaligned address");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    typedef CUresult (*WriteFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WriteFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            set_error("fuf_stream_write_u32: cuStreamWriteValue32 is not available from this driver");
+            return FUF_ECUDA;
+        }
+        fn = (WriteFn)ptr;
+    }
+    CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)dptr, value, 0);
+    if (r != CUDA_SUCCESS) {
+        set_error("fuf_stream_write_u32: cuStreamWriteValue32 failed with CUresult %d", (int)r);
+        return FUF_ECUDA;
+    }
+    return FUF_OK;
+}
+
 extern "C" int64_t fuf_launch_count(const fuf_ctx *ctx) { return ctx ? ctx->launches : 0; }

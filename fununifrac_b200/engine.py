@@ -24,7 +24,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 10
+ABI_VERSION = 11
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -75,6 +75,16 @@ def load_library() -> ctypes.CDLL:
         L.fuf_push_up_f64.argtypes = [vp, vp, i64, i64, ci, vp, i64, i64, vp]
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
+        u32 = ctypes.c_uint32
+        L.fuf_pairwise_tiles.argtypes = [vp, vp, i64, i64, i64, ci, vp, i32, vp, u32, vp, i64, vp, ctypes.c_double, vp, i64, vp]
+        L.fuf_refine_list.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i64, vp, i64, vp]
+        L.fuf_peer_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.fuf_peer_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.fuf_peer_close.argtypes = [vp, vp]
+        L.fuf_peer_free.argtypes = [vp, vp]
+        L.fuf_copy_async.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
+        L.fuf_stream_write_u32.argtypes = [vp, vp, u32, vp]
+        L.fuf_host_device_pointer.argtypes = [vp, vp, ctypes.POINTER(vp)]
         L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, vp]
         L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
         L.fuf_pack_tile_rows.argtypes = [vp, vp, i64, vp, vp, i32, i64, vp, vp]
@@ -97,7 +107,9 @@ def load_library() -> ctypes.CDLL:
                      "fuf_name_index_destroy", "fuf_ingest_gather_csv",
                      "fuf_load_pushed", "fuf_pairwise", "fuf_pairwise_f64", "fuf_assemble", "fuf_diffab_block",
                      "fuf_diffab_gather", "fuf_store_tile_rows_host", "fuf_pack_tile_rows", "fuf_assemble_packed",
-                     "fuf_all_pairs_host", "fuf_last_timing"):
+                     "fuf_all_pairs_host", "fuf_last_timing", "fuf_pairwise_tiles", "fuf_refine_list", "fuf_peer_alloc",
+                     "fuf_peer_open", "fuf_peer_close", "fuf_peer_free", "fuf_copy_async", "fuf_stream_write_u32",
+                     "fuf_host_device_pointer"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
             raise FunUniFracError(f"{LIB_PATH} has ABI version {L.fuf_version()}, this package needs {ABI_VERSION}: "
@@ -432,6 +444,63 @@ class TreeContext:
                                       _stream_ptr(torch)), "fuf_pairwise")
         return D
 
+    # -- several GPUs of one node: peer memory, tiles with arriving operands ------------------------------------
+    def peer_alloc(self, shape, dtype) -> "PeerBuffer":
+        """A zero-filled device buffer other processes of the node can map (``fuf_peer_alloc``)."""
+        return PeerBuffer(self, shape, dtype)
+
+    def peer_open(self, handle: bytes, shape, dtype) -> "PeerBuffer":
+        """Map a peer's buffer from its 64-byte handle (``fuf_peer_open``)."""
+        return PeerBuffer(self, shape, dtype, handle=handle)
+
+    def host_device_pointer(self, host_array: np.ndarray) -> int:
+        """Device-side address of a page-locked host array (``fuf_host_device_pointer``)."""
+        out = ctypes.c_void_p()
+        _check(self._lib.fuf_host_device_pointer(self.handle, host_array.ctypes.data, ctypes.byref(out)),
+               "fuf_host_device_pointer")
+        return int(out.value)
+
+    def copy_async(self, dst, src, stream=None):
+        """dst.copy_(src) through the copy engines on ``stream`` (tensors may be peer mappings)."""
+        torch = _torch()
+        assert dst.is_contiguous() and src.is_contiguous() and dst.numel() * dst.element_size() == src.numel() * src.element_size()
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _check(self._lib.fuf_copy_async(self.handle, dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), st),
+               "fuf_copy_async")
+
+    def stream_write_u32(self, flags, index: int, value: int, stream=None):
+        """flags[index] = value in stream order, without an SM (``fuf_stream_write_u32``)."""
+        torch = _torch()
+        assert flags.dtype == torch.int32 and flags.is_contiguous()
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _check(self._lib.fuf_stream_write_u32(self.handle, flags.data_ptr() + 4 * index, value & 0xFFFFFFFF, st),
+               "fuf_stream_write_u32")
+
+    def pairwise_tiles(self, PS, N: int, mode: int, tiles, dep_flags, epoch: int, D, shard: int, shard_stride: int,
+                       err_stat=None, flag_list=None, list_cap: int = 0, kappa: float = 0.0):
+        """``fuf_pairwise_tiles``: tiles (ti, tj, dependency) of the upper triangle, written in place into the full
+        matrix D (local, peer or mapped host memory; a tensor or a raw pointer) with their mirror."""
+        torch = _torch()
+        if PS.dtype != torch.float32 or PS.stride(-1) != 1:
+            raise TypeError("fuf_pairwise_tiles takes float32 operands [G, n, shard]")
+        tl = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3)
+        dptr, ldd = (D, N) if isinstance(D, int) else (D.data_ptr(), D.stride(0))
+        _check(self._lib.fuf_pairwise_tiles(self.handle, PS.data_ptr(), N, shard, shard_stride, mode, tl.ctypes.data, len(tl),
+                                            None if dep_flags is None else dep_flags.data_ptr(), epoch & 0xFFFFFFFF, dptr,
+                                            ldd, None if err_stat is None else err_stat.data_ptr(), float(kappa),
+                                            None if flag_list is None else flag_list.data_ptr(), int(list_cap),
+                                            _stream_ptr(torch)), "fuf_pairwise_tiles")
+
+    def refine_list(self, P64T, N: int, mode: int, flag_list, list_cap: int, D, shard: int = 0, shard_stride: int = 0):
+        """``fuf_refine_list``: the flagged pairs recomputed in float64 into D[i, j], D[j, i] (tensor or raw pointer)."""
+        torch = _torch()
+        assert P64T.dtype == torch.float64 and flag_list.dtype == torch.int64
+        dptr, ldd = (D, N) if isinstance(D, int) else (D.data_ptr(), D.stride(0))
+        ldp = P64T.stride(0) if shard == 0 else 0
+        _check(self._lib.fuf_refine_list(self.handle, P64T.data_ptr(), N, ldp, shard, shard_stride, mode,
+                                         flag_list.data_ptr(), int(list_cap), dptr, ldd, _stream_ptr(torch)),
+               "fuf_refine_list")
+
     def pairwise_f64(self, P64T, N: int, mode: int, D=None, tile_rows: Optional[Sequence[int]] = None, shard: int = 0,
                      shard_stride: int = 0):
         """``fuf_pairwise_f64``: float64 kernel in the reference's operation order; layouts and ``tile_rows`` as in
@@ -567,6 +636,48 @@ class TreeContext:
         _check(self._lib.fuf_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
                "fuf_last_timing")
         return a.value, b.value, c.value
+
+
+class _CudaArray:
+    """``__cuda_array_interface__`` view of raw device memory, so that torch can wrap it without copying."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerBuffer:
+    """Device memory shared between the processes of one node through a CUDA IPC handle.  ``tensor`` is a torch view of
+    it on this process's device (for a mapping of a peer's buffer: the peer's memory, reached over NVLink)."""
+
+    _TYPESTR = {"float32": "<f4", "float64": "<f8", "int32": "<i4", "int64": "<i8"}
+
+    def __init__(self, ctx: TreeContext, shape, dtype: str, handle: Optional[bytes] = None):
+        torch = _torch()
+        self.ctx, self.owner = ctx, handle is None
+        shape = tuple(int(x) for x in shape)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(self._TYPESTR[dtype]).itemsize
+        ptr = ctypes.c_void_p()
+        if self.owner:
+            buf = ctypes.create_string_buffer(64)
+            _check(ctx._lib.fuf_peer_alloc(ctx.handle, max(nbytes, 1), ctypes.byref(ptr), buf), "fuf_peer_alloc")
+            self.handle = buf.raw
+        else:
+            _check(ctx._lib.fuf_peer_open(ctx.handle, handle, ctypes.byref(ptr)), "fuf_peer_open")
+            self.handle = handle
+        self.ptr = int(ptr.value)
+        self.tensor = torch.as_tensor(_CudaArray(self.ptr, shape, self._TYPESTR[dtype]), device=f"cuda:{ctx.device}")
+
+    def close(self):
+        ptr, self.ptr = getattr(self, "ptr", 0), 0
+        if ptr and self.ctx._h:
+            self.tensor = None
+            if self.owner:
+                self.ctx._lib.fuf_peer_free(self.ctx.handle, ptr)
+            else:
+                self.ctx._lib.fuf_peer_close(self.ctx.handle, ptr)
+
+    __del__ = close
 
 
 class Pushed:

@@ -1,18 +1,25 @@
-"""Multi-GPU all-pairs: one process per GPU, samples and tile rows sharded, two exchanges per job.
+"""Multi-GPU all-pairs: one process per GPU of one node, samples sharded, the distance matrix written in place.
 
 The distance matrix has no cross-pair dependence (every ``dists[i, j]`` of the reference loop,
 ``src/algorithms/emd_unifrac.py:49-54``, needs only rows i and j of the pushed profiles), so the job shards
-without any collective inside the kernels:
+without any collective inside the arithmetic.  Weighted L1 (and the direct --L2 kernel):
 
-1. rank r pushes up its own block of ``shard`` samples              (``fuf_push_up``  → ``[n, shard]`` node-major)
-2. one all-gather of the pushed blocks over NCCL / NVLink            (→ ``[G, n, shard]``, the layout ``fuf_pairwise``
-   reads directly through its ``shard`` / ``shard_stride`` arguments)
-3. rank r computes the 128-row tile rows it owns, upper triangle    (``fuf_pairwise`` with ``tile_rows``)
-4. one gather of the row blocks, packed to the columns each tile   (``fuf_pack_tile_rows``, ``fuf_assemble_packed``)
-   row owns, to rank 0, which mirrors them into the full symmetric matrix (``step``: matrix resident on GPU 0), or — with host buffers, ``step_host`` —
-   every rank stores its tile rows and their mirror straight into ONE host matrix shared by the ranks of the node
-   (``SharedHostMatrix`` + ``fuf_store_tile_rows_host``): the device-to-host traffic then runs over all PCIe links at
-   once and nothing funnels through rank 0.
+1. rank r pushes up its own block of ``shard`` samples              (``fuf_push_up`` -> ``[n, shard]`` node-major, in a
+   buffer its peers have mapped through CUDA IPC)
+2. the per-sample statistics are all-gathered (NCCL, 80 KB)          — which is also the signal that every shard is ready
+3. the tile grid is dealt by SHARD PAIRS (``peer_tile_plan``): rank r owns its diagonal block and the blocks
+   (r, r+1) .. (r, r+G/2) (the last one split with its partner), so it needs only G/2 of the G-1 remote shards.  A copy
+   stream pulls them from the peers' buffers over NVLink, one after the other, and raises a flag behind each copy.
+4. ONE launch of ``fuf_pairwise_tiles`` walks the rank's tiles in arrival order — diagonal block first, which needs
+   nothing remote; a tile whose shard is still in flight makes the kernel's producer warp wait for the flag — and stores
+   every tile, and its mirror, straight into the full matrix: rank 0's device matrix (mapped by every rank), or with
+   host buffers (``step_host``) the page-locked host matrix the ranks share.  Nothing is packed, gathered or assembled.
+   The refinement criterion is evaluated in the tile epilogues; the flagged-pair count is all-reduced (NCCL, 8 bytes:
+   the end-of-step barrier), and only if it is non-zero are the float64 profiles pushed up, exchanged and the listed
+   pairs recomputed (``fuf_refine_list``).
+
+--L2 from 512 samples on (tensor-core Gram kernel) still uses the collective form: all-gather of the pushed blocks, tile
+rows dealt boustrophedon-wise, packed gather to rank 0 (``step``) or per-rank stores into the shared host matrix.
 
 The compute calls are injected (``ops``) so that the partition / exchange logic is testable on CPU with the
 ``gloo`` backend; the product always injects ``engine.TreeContext`` (CUDA).  ``world == 1`` needs no process group.
@@ -58,6 +65,40 @@ def packed_offsets(rows: Sequence[int], N: int):
     return offsets, total
 
 
+def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None):
+    """Tiles of rank ``rank`` when the upper-triangular tile grid is dealt by shard pairs, in processing order, as
+    (ti, tj, dependency) triples, plus the remote shards the rank pulls, in pull order.
+
+    Shard A holds tile indices [A Ts, (A+1) Ts).  Rank r owns the diagonal block (r, r) — no remote operand — then the
+    blocks of shard pair {r, (r + d) mod G} for d = 1 .. G/2: a round-robin tournament, every unordered pair has exactly
+    one owner, except that for even G the pairs at distance G/2 are split by tile rows between their two members.  Every
+    rank gets the same number of tiles (up to the ragged last shard) and pulls only floor(G/2) of the G - 1 remote shards.
+    """
+    shard = shard or shard_size(N, world)
+    Ts, T = shard // TILE, (N + TILE - 1) // TILE
+
+    def tiles_of(A):
+        return range(A * Ts, min((A + 1) * Ts, T))
+
+    own = tiles_of(rank)
+    tiles = [(ti, tj, -1) for ti in own for tj in range(ti, own.stop)]
+    pulls = []
+    for d in range(1, world // 2 + 1):
+        q = (rank + d) % world
+        if q == rank:
+            continue
+        A, B = min(rank, q), max(rank, q)
+        rows = list(tiles_of(A))
+        if 2 * d == world:                       # the pair at distance G/2 is shared: lower rank takes the first half
+            half = (len(rows) + 1) // 2
+            rows = rows[:half] if rank == A else rows[half:]
+        block = [(ti, tj, q) for ti in rows for tj in tiles_of(B)]
+        if block:
+            pulls.append(q)
+            tiles += block
+    return tiles, pulls
+
+
 def refine_budget(N: int) -> int:
     """Pairs worth recomputing one by one (0.1 % of all pairs, at least 1,024); more than that and the float64 tile kernel
     is cheaper."""
@@ -78,7 +119,7 @@ class ShardedAllPairs:
     """
 
     def __init__(self, ops, N: int, mode: int, world: int = 1, rank: int = 0, dist=None, refine: bool = True,
-                 gram: Optional[bool] = None):
+                 gram: Optional[bool] = None, peer: Optional[bool] = None):
         self.ops, self.N, self.mode, self.world, self.rank, self.dist = ops, N, mode, world, rank, dist
         self.do_refine = refine
         # --L2 from 512 samples on: tensor-core Gram kernel (its refinement needs the float64 profiles)
@@ -91,6 +132,12 @@ class ShardedAllPairs:
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs a torch.distributed process group")
         n = ops.n
+        # peer form (weighted L1 and the direct --L2 kernel on several GPUs): shard pairs, NVLink pulls, in-place stores
+        self.use_peer = world > 1 and not self.use_gram and peer is not False
+        self.epoch = 0
+        if self.use_peer:
+            self._init_peer()
+            return
         self.PS = ops.empty((world, n, self.shard), "float32")          # pushed blocks of all ranks (zero-padded)
         self.P64S = None        # float64 pushed blocks: allocated, computed and exchanged only if a pair is flagged
         self.stat = ops.empty((world * self.shard,), "float64")
@@ -206,10 +253,112 @@ class ShardedAllPairs:
                 ops.refine(self.P64S, self.N, self.mode, stat, target, rows, sh, n * sh, lin)
         return True
 
+    # ------------------------------------------------------------------------------------------------------
+    # peer form
+    # ------------------------------------------------------------------------------------------------------
+    def _init_peer(self):
+        ops, N, world, rank, dist, sh, n = self.ops, self.N, self.world, self.rank, self.dist, self.shard, self.ops.n
+        self.tiles, self.pulls = peer_tile_plan(N, world, rank, sh)
+        self.rows = self.tiles                    # (truthy iff this rank computes anything)
+        # every rank's operand buffer [G, n, shard]: slot r is written by its own push-up and read by the peers' copy
+        # engines; the other slots receive the pulled shards
+        self.PS_buf = ops.peer_alloc((world, n, sh), "float32")
+        self.PS = self.PS_buf.tensor
+        self.D_buf = ops.peer_alloc((N, N), "float64") if rank == 0 else None
+        handles = [None] * world
+        dist.all_gather_object(handles, (self.PS_buf.handle, self.D_buf.handle if rank == 0 else None))
+        self.peer_PS = {q: ops.peer_open(handles[q][0], (world, n, sh), "float32") for q in self.pulls}
+        if rank != 0:
+            self.D_buf = ops.peer_open(handles[0][1], (N, N), "float64")
+        self.D = self.D_buf.tensor if rank == 0 else None
+        self.D_target = self.D_buf.tensor         # rank 0's matrix, as seen from this rank
+        self.P64S = None
+        self.stat = ops.empty((world * sh,), "float64")
+        self.center = ops.empty((n,), "float64")
+        self.flags = ops.empty((world,), "int32")                         # arrival flag per shard
+        self.list_cap = refine_budget(N)
+        self.flag_list = ops.empty((1 + 2 * self.list_cap,), "int64")     # [0] = count, then (i, j) pairs
+        self.flagged = ops.empty((1,), "int64")
+        self.copy_stream = ops.new_stream()
+        self.last_flagged = 0
+        self._x_stage = self._pending = self._x_local = None
+        dist.barrier()
+
+    def _compute_peer(self, X_local, D_target, mark):
+        """Steps 1-4 of the module docstring; afterwards the matrix behind ``D_target`` holds this rank's tiles (the
+        refinement decision is pending in ``self.flagged``)."""
+        ops, N, mode, r, sh, n, dist = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n, self.dist
+        self.epoch += 1
+        mark("start")
+        if r == 0:
+            ops.push_up_center(X_local, mode, self.center)
+        dist.broadcast(self.center, src=0)
+        mark("push_begin")
+        self._x_local = X_local
+        if self.hi > self.lo:
+            ops.push_up(X_local, mode, self.PS[r], 0, self.center, None, self.stat[r * sh:(r + 1) * sh])
+        mark("push_end")
+        # the statistics of all samples (the epilogue criterion needs both members of a pair); every rank contributes
+        # after its push-up, so its arrival also says: all shards are ready to be pulled
+        dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
+        ops.zero_(self.flag_list[:1])
+        ready = ops.record_event()
+        ops.stream_wait(self.copy_stream, ready)
+        for q in self.pulls:                      # NVLink pulls, one after the other, a flag behind each
+            ops.copy_async(self.PS[q], self.peer_PS[q].tensor[q], self.copy_stream)
+            ops.stream_write_u32(self.flags, q, self.epoch, self.copy_stream)
+        mark("pair_begin")
+        if self.tiles:
+            ops.pairwise_tiles(self.PS, N, mode, self.tiles, self.flags, self.epoch, D_target, sh, n * sh,
+                               self.stat if self.do_refine else None, self.flag_list if self.do_refine else None,
+                               self.list_cap)
+        mark("pair_end")
+        # the next step's pulls and push-up must not start before everybody is done with this step's: the all-reduce of
+        # the flagged-pair count is that barrier (and tells every rank whether the float64 pass is needed)
+        self.flagged.copy_(self.flag_list[:1])
+        dist.all_reduce(self.flagged)
+        self._pending = True
+        mark("refine_end")
+
+    def _refine_peer(self, D_target) -> None:
+        """The host's half of the refinement decision (one synchronisation per step; the float64 pass itself is rare)."""
+        self.last_flagged = 0
+        if not self._pending:
+            return
+        self._pending = None
+        self.last_flagged = int(self.flagged.item())
+        if self.last_flagged == 0 or not self.do_refine:
+            return
+        ops, r, sh, n, dist = self.ops, self.rank, self.shard, self.ops.n, self.dist
+        if self.P64S is None:
+            self.P64S = ops.empty((self.world, n, sh), "float64")
+        if self.hi > self.lo:
+            ops.push_up_p64(self._x_local, self.mode, self.P64S[r])
+        dist.all_gather_into_tensor(self.P64S.view(-1), self.P64S[r].reshape(-1))
+        counts = ops.empty((self.world,), "int64")
+        dist.all_gather_into_tensor(counts, self.flag_list[:1].clone())
+        if int(counts.max().item()) > self.list_cap:
+            # more flagged pairs than a list holds (a data set of near-duplicates): the float64 tile kernel redoes the
+            # whole matrix on rank 0, which holds every float64 profile now
+            if r == 0:
+                full = self.D if D_target is self.D_target else ops.empty((self.N, self.N), "float64")
+                ops.pairwise_f64(self.P64S, self.N, self.mode, None, sh, n * sh, full)
+                if full is not self.D:
+                    ops.copy_to_target(full, D_target)
+        else:
+            ops.refine_list(self.P64S, self.N, self.mode, self.flag_list, self.list_cap, D_target, sh, n * sh)
+        ops.synchronize()
+        dist.barrier()                            # every rank's corrections have landed
+
     def step(self, X_local, mark=None):
         """X_local: this rank's un-pushed samples [hi - lo, >= n] on the device.  Returns D on rank 0, else None.
         ``mark(name)`` is called at the phase boundaries (bench.py records CUDA events there)."""
         mark = mark or (lambda name: None)
+        if self.use_peer:
+            self._compute_peer(X_local, self.D_target, mark)
+            self._refine_peer(self.D_target)
+            mark("end")
+            return self.D
         self._compute(X_local, mark)
         if self.world == 1:
             self._refine_if_flagged()
@@ -242,8 +391,18 @@ class ShardedAllPairs:
         if D_host.array.shape != (self.N, self.N):
             raise ValueError(f"shared matrix is {D_host.array.shape}, job needs {(self.N, self.N)}")
         if self._x_stage is None:
-            self._x_stage = self.ops.empty((max(self.hi - self.lo, 1), self.ops.n), "float64")
+            self._x_stage = self.ops.profile_matrix(max(self.hi - self.lo, 1))
         X = self.ops.to_device(X_local_host, self._x_stage)
+        if self.use_peer:
+            # the tiles (and their mirror) are stored by the kernel itself into the page-locked host matrix the ranks
+            # share: the device-to-host traffic of all ranks runs over their own PCIe links, under the computation
+            target = self.ops.host_target(D_host)
+            self._compute_peer(X, target, mark)
+            self._refine_peer(target)
+            self.ops.synchronize()
+            self.dist.barrier()
+            mark("end")
+            return D_host.array
         self._compute(X, mark)
         if self.world == 1:
             self._refine_if_flagged()
@@ -358,6 +517,61 @@ class CudaOps:
 
     def push_up(self, X, mode, PT, col0, center, P64T, err_stat):
         return self.ctx.push_up(X, mode, PT, col0, center, P64T, err_stat)
+
+    def profile_matrix(self, rows):
+        from fununifrac_b200 import engine
+        return engine.profile_matrix(rows, self.n, self.torch.float64, self.device)
+
+    def peer_alloc(self, shape, dtype):
+        return self.ctx.peer_alloc(shape, dtype)
+
+    def peer_open(self, handle, shape, dtype):
+        return self.ctx.peer_open(handle, shape, dtype)
+
+    def new_stream(self):
+        return self.torch.cuda.Stream(device=self.device)
+
+    def record_event(self):
+        ev = self.torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def stream_wait(self, stream, event):
+        stream.wait_event(event)
+
+    def zero_(self, t):
+        t.zero_()
+
+    def copy_async(self, dst, src, stream):
+        self.ctx.copy_async(dst, src, stream)
+
+    def stream_write_u32(self, flags, index, value, stream):
+        self.ctx.stream_write_u32(flags, index, value, stream)
+
+    def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap):
+        key = id(tiles)
+        if getattr(self, "_tiles_key", None) != key:      # the plan is fixed for the job: convert it once
+            import numpy as np
+            self._tiles_np, self._tiles_key = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3), key
+        self.ctx.pairwise_tiles(PS, N, mode, self._tiles_np, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap)
+
+    def refine_list(self, P64S, N, mode, flag_list, list_cap, D, shard, shard_stride):
+        self.ctx.refine_list(P64S, N, mode, flag_list, list_cap, D, shard, shard_stride)
+
+    def host_target(self, D_host):
+        """Raw device-side pointer of the shared page-locked host matrix (the kernels store through it)."""
+        if getattr(self, "_host_target_of", None) is not D_host:
+            self._host_target, self._host_target_of = self.ctx.host_device_pointer(D_host.array), D_host
+        return self._host_target
+
+    def copy_to_target(self, D, target):
+        if isinstance(target, int):
+            import ctypes
+            nbytes = D.numel() * 8
+            self.ctx._lib.fuf_copy_async(self.ctx.handle, ctypes.c_void_p(target), D.data_ptr(), nbytes,
+                                         self.torch.cuda.current_stream().cuda_stream)
+        else:
+            target.copy_(D)
 
     def push_up_p64(self, X, mode, P64T):
         return self.ctx.push_up_p64(X, mode, P64T)

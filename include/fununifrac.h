@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 10
+#define FUF_ABI_VERSION 11
 
 /* error codes */
 #define FUF_OK 0
@@ -309,6 +309,39 @@ int fuf_name_index_destroy(fuf_name_index *index);
 int fuf_ingest_gather_csv(const fuf_name_index *index, const char *const *paths, int32_t n_files, const char *abundance_key,
                           int normalize, int unweighted, int n_threads, double *X, int64_t ldx, int32_t *status,
                           char *messages, int64_t message_stride, char *warnings, int64_t warnings_cap);
+
+/* ---- several GPUs of one node, one process each: tiles with arriving operands, results written in place ---------
+ * Replaces, for a sharded job, the same reference loop as fuf_pairwise (src/algorithms/emd_unifrac.py:42-54); the
+ * reference has no multi-device form, so there is no reference interface for the exchange itself.
+ *
+ * fuf_pairwise_tiles: an explicit list of upper-triangle tiles (ti, tj, dependency) on the all-gathered operand layout
+ * [G][n][shard].  Every tile is written straight to its place in the FULL matrix D (D[i, j] and D[j, i]; ldd >= N) —
+ * D may be this device's memory, a peer GPU's (fuf_peer_open) or mapped page-locked host memory: plain stores.
+ * dependency >= 0: the tile reads shard `dependency`, which a copy engine may still be pulling from a peer when the
+ * launch starts; the kernel waits (producer warp, bounded) until dep_flags[dependency] has reached `epoch`
+ * (fuf_stream_write_u32 behind the copy).  List the tiles in the order their shards arrive.
+ * err_stat + flag_list: the refinement criterion of fuf_refine is evaluated in the tile epilogues, where the distances
+ * are produced: flag_list[0] counts the flagged pairs i < j, flag_list[1 + 2q], flag_list[2 + 2q] = (i, j) of the first
+ * list_cap of them (zero flag_list[0] before the launch).  kappa <= 0: the defaults of fuf_refine. */
+int fuf_pairwise_tiles(fuf_ctx *ctx, const float *PT, int64_t N, int64_t shard, int64_t shard_stride, int mode,
+                       const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch, double *D,
+                       int64_t ldd, const double *err_stat, double kappa, int64_t *flag_list, int64_t list_cap, void *stream);
+/* The listed pairs recomputed in float64 from P64T (layouts as in fuf_refine) into D[i, j] and D[j, i] of the full matrix. */
+int fuf_refine_list(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride,
+                    int mode, const int64_t *flag_list, int64_t list_cap, double *D, int64_t ldd, void *stream);
+/* Device buffers shared between the processes of one node (CUDA IPC): the owner allocates (zero-filled) and hands the
+ * 64-byte handle to its peers (any channel: the Python host uses torch.distributed), which map it.  A mapping is an
+ * ordinary device pointer for kernels (loads, stores) and copy engines (fuf_copy_async). */
+int fuf_peer_alloc(fuf_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]);
+int fuf_peer_open(fuf_ctx *ctx, const unsigned char handle[64], void **dptr);
+int fuf_peer_close(fuf_ctx *ctx, void *dptr);
+int fuf_peer_free(fuf_ctx *ctx, void *dptr);
+int fuf_copy_async(fuf_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+/* Device-side address of page-locked host memory (cudaHostAlloc / cudaHostRegister): lets fuf_pairwise_tiles store its
+ * tiles straight into a host matrix (e.g. the one the ranks of a node share and np.save writes). */
+int fuf_host_device_pointer(fuf_ctx *ctx, void *host_ptr, void **dptr);
+/* Stream-ordered 32-bit store that needs no SM (cuStreamWriteValue32): the arrival flag of fuf_pairwise_tiles. */
+int fuf_stream_write_u32(fuf_ctx *ctx, uint32_t *dptr, uint32_t value, void *stream);
 
 /* Test hook, host only (needs no device): the plan of the chunked push-up for a postorder parent array.
  * Arrays of length n; span_out gets 5 ints per spanning node (k, chunk_first, chunk_last, slot_start, slot_k). */

@@ -853,6 +853,22 @@ def test_cli_under_torchrun_two_gpus(l2, tmp_path):
     assert open(tmp_path / "one" / bn).read() == open(tmp_path / "two" / bn).read()
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("N,mode", [(1500, "l1"), (300, "l2"), (700, "l2"), (130, "l1")])
+def test_sharded_job_on_real_gpus(N, mode):
+    """sharded.ShardedAllPairs on every visible GPU (tests/multi_gpu_worker.py under torchrun): peer form for weighted L1
+    and the direct --L2 kernel, collective form for the Gram path (N >= 512), device-resident and host-buffer results,
+    near-duplicate and identical pairs, against the oracle."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = torch.cuda.device_count()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(g), "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(repo, "tests", "multi_gpu_worker.py"), str(N), mode]
+    res = subprocess.run(cmd, cwd=repo, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "MULTI_GPU_OK" in res.stdout, (res.stdout[-2000:], res.stderr[-4000:])
+
+
 # ------------------------------------------------------------------------------------------------------
 # BASELINE.json's full sizes (configs 3 and 4) through size-independent properties
 # ------------------------------------------------------------------------------------------------------

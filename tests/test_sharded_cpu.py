@@ -72,6 +72,92 @@ class OracleOps:
         P64T[:, :P.shape[0]] = torch.from_numpy(P.T.copy())
         self.p64_calls = getattr(self, "p64_calls", 0) + 1
 
+    # ---- peer form: shared-memory stand-ins for CUDA IPC buffers, immediate "streams" -------------------------
+    class _Shm:
+        def __init__(self, shape, dtype, handle=None):
+            import mmap
+            dt = {"float32": np.float32, "float64": np.float64, "int32": np.int32, "int64": np.int64}[dtype]
+            nbytes = max(8, int(np.prod(shape)) * np.dtype(dt).itemsize)
+            if handle is None:
+                self.fd = os.memfd_create("fuf_test_peer")
+                os.ftruncate(self.fd, nbytes)
+                self.handle = (os.getpid(), self.fd)
+            else:
+                self.fd = os.open(f"/proc/{handle[0]}/fd/{handle[1]}", os.O_RDWR)
+                self.handle = handle
+            self.map = mmap.mmap(self.fd, nbytes)
+            self.tensor = torch.from_numpy(np.frombuffer(self.map, dtype=dt, count=int(np.prod(shape))).reshape(shape))
+
+    def peer_alloc(self, shape, dtype):
+        return self._Shm(shape, dtype)
+
+    def peer_open(self, handle, shape, dtype):
+        return self._Shm(shape, dtype, handle)
+
+    def new_stream(self):
+        return None
+
+    def record_event(self):
+        return None
+
+    def stream_wait(self, stream, event):
+        pass
+
+    def zero_(self, t):
+        t.zero_()
+
+    def copy_async(self, dst, src, stream):
+        self.pulled = getattr(self, "pulled", 0) + 1
+        dst.copy_(src)
+
+    def stream_write_u32(self, flags, index, value, stream):
+        flags[index] = value
+
+    def profile_matrix(self, rows):
+        return torch.zeros((rows, self.n), dtype=torch.float64)
+
+    def host_target(self, D_host):
+        return torch.from_numpy(D_host.array)
+
+    def copy_to_target(self, D, target):
+        target.copy_(D)
+
+    def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap):
+        G, n, sh = PS.shape
+        kappa = 1.6e13 if self.l2 else 2e6
+        for ti, tj, dep in tiles:
+            assert dep < 0 or int(flags[dep]) == epoch, "tile scheduled before its shard's flag"
+            i0, i1, j0, j1 = ti * TILE, min(N, (ti + 1) * TILE), tj * TILE, min(N, (tj + 1) * TILE)
+            A = PS[i0 // sh, :, i0 % sh:i0 % sh + (i1 - i0)].T.double().numpy()
+            B = PS[j0 // sh, :, j0 % sh:j0 % sh + (j1 - j0)].T.double().numpy()
+            d = np.abs(A[:, None, :] - B[None, :, :])
+            blk = ((d * d) if self.l2 else d).sum(-1)
+            if ti == tj:
+                np.fill_diagonal(blk, 0.0)
+            D[i0:i1, j0:j1] = torch.from_numpy(blk)
+            D[j0:j1, i0:i1] = torch.from_numpy(blk.T.copy())
+            if flag_list is not None:
+                st = stat.numpy()
+                b = (np.sqrt(st[i0:i1])[:, None] + np.sqrt(st[j0:j1])[None, :]) ** 2 if self.l2 else \
+                    st[i0:i1][:, None] + st[j0:j1][None, :]
+                gi, gj = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), indexing="ij")
+                hit = (blk < kappa * b) & (b != 0) & (gi < gj)
+                for a_, b_ in zip(gi[hit], gj[hit]):
+                    at = int(flag_list[0])
+                    flag_list[0] = at + 1
+                    if at < list_cap:
+                        flag_list[1 + 2 * at], flag_list[2 + 2 * at] = int(a_), int(b_)
+
+    def refine_list(self, P64S, N, mode, flag_list, list_cap, D, shard, shard_stride):
+        self.refine_calls += 1
+        P = self._samples(P64S, N, shard)
+        for q in range(min(int(flag_list[0]), list_cap)):
+            i, j = int(flag_list[1 + 2 * q]), int(flag_list[2 + 2 * q])
+            d = np.abs(P[i] - P[j])
+            v = float((d * d).sum() if self.l2 else d.sum())
+            D[i, j] = v
+            D[j, i] = v
+
     def _samples(self, PS, N, shard):
         G, n, sh = PS.shape
         return PS.permute(0, 2, 1).reshape(G * sh, n)[:N].double().numpy()
@@ -156,7 +242,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, N, l2, out_path):
+def _worker(rank, world, port, N, l2, out_path, peer):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -168,15 +254,25 @@ def _worker(rank, world, port, N, l2, out_path):
         length = rng.random(n) * (rng.random(n) > 0.1)
         X = rng.random((N, n)) * (rng.random((N, n)) < 0.3)
         X[:, -1] = 0
+        if peer and N > 40:                          # a near-duplicate pair across two shards: must be flagged and refined
+            X[N - 3] = X[5] * (1 + 1e-9 * rng.random(n))
         X /= X.sum(1, keepdims=True)
         ops = OracleOps(parent, length, l2)
-        job = sharded.ShardedAllPairs(ops, N, int(l2), world, rank, dist)
+        job = sharded.ShardedAllPairs(ops, N, int(l2), world, rank, dist, peer=peer)
+        assert job.use_peer == bool(peer)
         marks = []
         D = job.step(torch.from_numpy(X[job.lo:job.hi]), marks.append)
         assert marks[0] == "start" and marks[-1] == "end" and "pair_begin" in marks
-        assert ops.refine_calls == (1 if job.rows else 0) and job.last_flagged == 1
-        # the float64 profiles were pushed up only because a pair was flagged, by every rank that holds samples
-        assert getattr(ops, "p64_calls", 0) == (1 if job.hi > job.lo else 0)
+        if peer:
+            # shard pairs: every rank pulled floor(G/2) shards at most, and only those that hold tiles
+            assert getattr(ops, "pulled", 0) == len(job.pulls) <= world // 2
+            want_flag = 1 if N > 40 else 0
+            assert job.last_flagged == want_flag and ops.refine_calls == want_flag
+            assert getattr(ops, "p64_calls", 0) == (want_flag if job.hi > job.lo else 0)
+        else:
+            assert ops.refine_calls == (1 if job.rows else 0) and job.last_flagged == 1
+            # the float64 profiles were pushed up only because a pair was flagged, by every rank that holds samples
+            assert getattr(ops, "p64_calls", 0) == (1 if job.hi > job.lo else 0)
         if rank == 0:
             from oracle import oracle_c
             ref = oracle_c.pairwise(oracle_c.push_up(parent, length, X, l2), l2)
@@ -185,6 +281,8 @@ def _worker(rank, world, port, N, l2, out_path):
             iu = np.triu_indices(N, 1)
             err = np.abs(got[iu] - ref[iu]) / ref[iu]
             assert err.max() < 1e-5, err.max()          # fp32-rounded operands, float64 arithmetic
+            if peer and N > 40:                         # the refined pair is exact to float64 rounding
+                assert abs(got[5, N - 3] - ref[5, N - 3]) <= 1e-12 * ref[5, N - 3] + 1e-18
             assert np.array_equal(got, got.T) and not np.diag(got).any()
             np.save(out_path, got)
         else:
@@ -207,10 +305,34 @@ def _worker(rank, world, port, N, l2, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,N,l2", [(2, 300, False), (3, 700, False), (2, 129, True), (3, 100, False)])
-def test_sharded_exchange_gloo(world, N, l2, tmp_path, monkeypatch):
+@pytest.mark.parametrize("world,N,l2,peer", [(2, 300, False, True), (3, 700, False, True), (4, 400, True, True),
+                                             (3, 100, False, True), (2, 300, False, False), (2, 129, True, False)])
+def test_sharded_exchange_gloo(world, N, l2, peer, tmp_path, monkeypatch):
+    """peer=True: the shard-pair form (NVLink pulls + in-place stores, here over shared memory); peer=False: the
+    collective form (all-gather, tile rows, packed gather) the Gram path still uses."""
     if world == 3:      # once through the named shared-memory file instead of /proc/<pid>/fd
         monkeypatch.setenv("FUF_SHARED_NO_PROCFD", "1")
     out = str(tmp_path / "D.npy")
-    mp.spawn(_worker, args=(world, _free_port(), N, l2, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), N, l2, out, peer), nprocs=world, join=True)
     assert np.load(out).shape == (N, N)
+
+
+def test_peer_tile_plan_covers_the_triangle_once():
+    for N, world in [(10000, 8), (10000, 2), (700, 3), (129, 4), (100, 3), (5000, 5), (128 * 7, 7)]:
+        seen, counts = set(), []
+        for r in range(world):
+            tiles, pulls = sharded.peer_tile_plan(N, world, r)
+            counts.append(len(tiles))
+            assert len(pulls) <= world // 2 and r not in pulls
+            deps = [d for _, _, d in tiles if d >= 0]
+            assert sorted(set(deps), key=deps.index) == pulls            # tiles are listed in pull order
+            assert all(d < 0 for _, _, d in tiles[:len([t for t in tiles if t[2] < 0])])   # diagonal block first
+            sh = sharded.shard_size(N, world) // TILE
+            for ti, tj, d in tiles:
+                assert ti <= tj and (ti, tj) not in seen
+                seen.add((ti, tj))
+                assert {ti // sh, tj // sh} <= {r, d if d >= 0 else r}     # operands: own shard and the dependency
+        T = (N + TILE - 1) // TILE
+        assert len(seen) == T * (T + 1) // 2
+        if N == 10000 and world == 8:
+            assert max(counts) / (sum(counts) / world) < 1.03
