@@ -197,7 +197,7 @@ int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_
 // gram.cu
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
                   const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
-                  double *D, int64_t ldd, cudaStream_t stream);
+                  double *D, int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0);
 // refine.cu
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,

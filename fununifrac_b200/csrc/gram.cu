@@ -109,6 +109,8 @@ struct Params {
     int32_t n_direct;    // node columns kept out of the integer Gram (largest scales): added here in float64
     const double *SUB;   // their values, [n_direct][samples] in layout `sub`
     Lay sub;
+    double *D2;          // optional second destination with the same indexing (the caller's page-locked host matrix)
+    int64_t ldd2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -411,6 +413,10 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         const double v = (gi == gj) ? 0.0 : (qi + p.q[gj]) - 2.0 * acc[e];
                         drow[e] = v;
                         if (mirror) p.D[gj * p.ldd + gi] = v;    // lanes = consecutive gi: one 256-byte store per warp
+                        if (p.D2) {
+                            p.D2[((int64_t)tl.out_row0 + row) * p.ldd2 + gj] = v;
+                            if (mirror) p.D2[gj * p.ldd2 + gi] = v;
+                        }
                     }
                 }
             }
@@ -463,6 +469,8 @@ struct Params2 {
     int32_t mirror, n_direct;
     const double *SUB;
     Lay sub;
+    double *D2;          // optional second destination (page-locked host matrix), same indexing
+    int64_t ldd2;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
@@ -672,6 +680,10 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                         const double v = (gi == gj) ? 0.0 : (p.q[gi] + qj) - 2.0 * acc[e];
                         dcol[(int64_t)e * p.ldd] = v;         // lanes = consecutive gj: one 256-byte store per warp
                         if (mirror) mrow[e] = v;
+                        if (p.D2) {
+                            p.D2[((int64_t)tl.out_row0 + half * 64 + e) * p.ldd2 + gj] = v;
+                            if (mirror) p.D2[gj * p.ldd2 + gi] = v;
+                        }
                     }
                 }
             }
@@ -962,7 +974,7 @@ static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_ro
 
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
                   const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
-                  double *D, int64_t ldd, cudaStream_t stream)
+                  double *D, int64_t ldd, cudaStream_t stream, double *D_second, int64_t ldd_second)
 {
     using namespace gram;
     if (N == 0) return FUF_OK;
@@ -1219,6 +1231,8 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     p.n_direct = n_direct;
     p.SUB = SUB;
     p.sub = sub;
+    p.D2 = D_second;
+    p.ldd2 = ldd_second;
     if (!ctx->ev_gram[0]) {
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[0]));
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
@@ -1257,6 +1271,8 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         p2.n_direct = n_direct;
         p2.SUB = SUB;
         p2.sub = sub;
+        p2.D2 = D_second;
+        p2.ldd2 = ldd_second;
         FUF_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
         const int n_pairs = (int)std::min<int64_t>(p2.n_tiles, ctx->sm_count / 2);
         FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
@@ -1360,5 +1376,5 @@ extern "C" int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise_gram: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_gram(ctx, PT, N, ldp, shard, shard_stride, err_in, h2, err_out, tile_rows_h, n_tile_rows, D, ldd,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, nullptr, 0);
 }

@@ -19,11 +19,67 @@ from fununifrac_b200.factory import make_emd_input, make_tree  # noqa: E402
 from oracle import oracle_c  # noqa: E402
 
 
+class HostStagedDist:
+    """``torch.distributed`` over gloo for CUDA tensors, staged through host memory — lets several ranks share ONE GPU
+    (NCCL refuses that), so that the peer form's CUDA mechanics (IPC mappings, copy-engine pulls, arrival flags, in-place
+    stores) can be exercised on a single-GPU box.  Only the calls sharded.py makes."""
+
+    ReduceOp = dist.ReduceOp
+
+    @staticmethod
+    def _sync():
+        torch.cuda.synchronize()
+
+    def broadcast(self, t, src):
+        self._sync()
+        h = t.cpu()
+        dist.broadcast(h, src=src)
+        t.copy_(h)
+
+    def all_reduce(self, t, op=dist.ReduceOp.SUM):
+        self._sync()
+        h = t.cpu()
+        dist.all_reduce(h, op=op)
+        t.copy_(h)
+
+    def all_gather_into_tensor(self, out, inp):
+        self._sync()
+        h = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(h, inp.cpu().contiguous())
+        out.copy_(h)
+
+    def gather(self, t, gather_list=None, dst=0):
+        self._sync()
+        hs = [torch.empty(t.shape, dtype=t.dtype) for _ in gather_list] if gather_list is not None else None
+        dist.gather(t.cpu(), hs, dst=dst)
+        if gather_list is not None:
+            for g, h in zip(gather_list, hs):
+                g.copy_(h)
+
+    def all_gather_object(self, out, obj):
+        dist.all_gather_object(out, obj)
+
+    def broadcast_object_list(self, objs, src=0):
+        dist.broadcast_object_list(objs, src=src)
+
+    def barrier(self):
+        self._sync()
+        dist.barrier()
+
+
 def main():
     N, l2 = int(sys.argv[1]), sys.argv[2] == "l2"
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    one_gpu = torch.cuda.device_count() < world          # several ranks on device 0: gloo staged through the host
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if one_gpu:
+        dist.init_process_group("gloo")
+        comm = HostStagedDist()
+    else:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        comm = dist
     with tempfile.TemporaryDirectory() as tmp:
         path = synth.synth_ko_tree(os.path.join(tmp, "t.txt"), seed=0)
         inp = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(path), "ko00001")
@@ -36,7 +92,7 @@ def main():
     X[N - 2] /= X[N - 2].sum()
     X[N // 2 + 1] = X[7]                                                 # identical pair
     mode = engine.MODE_L2 if l2 else engine.MODE_L1
-    job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, mode, world, rank, dist)
+    job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, mode, world, rank, comm)
     assert job.use_peer == (not job.use_gram)
     Xl = engine.profile_matrix(job.hi - job.lo, n, torch.float64, f"cuda:{local}")
     Xl.copy_(torch.from_numpy(X[job.lo:job.hi]))
@@ -45,13 +101,14 @@ def main():
         D = job.step(Xl)
         if rank == 0:
             results.append(D.cpu().numpy().copy())
-    shared = sharded.SharedHostMatrix(N, world, rank, dist)
+    shared = sharded.SharedHostMatrix(N, world, rank, comm)
     Xh = engine.profile_matrix(job.hi - job.lo, n, torch.float64, None, pin_memory=True)
     Xh.copy_(torch.from_numpy(X[job.lo:job.hi]))
     Dh = None
     for _ in range(2):
-        shared.array[...] = np.nan if rank == 0 else shared.array
-        dist.barrier()
+        if rank == 0:
+            shared.array[...] = np.nan
+        comm.barrier()
         Dh = job.step_host(Xh, shared)
     if rank == 0:
         ref = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, X, l2), l2)
@@ -70,7 +127,7 @@ def main():
             assert job.last_flagged >= 1                                  # the near-duplicate went through the list path
         print(f"MULTI_GPU_OK world={world} N={N} mode={'l2' if l2 else 'l1'} peer={job.use_peer} flagged={job.last_flagged}",
               flush=True)
-    dist.barrier()
+    comm.barrier()
     shared.close()
     dist.destroy_process_group()
 

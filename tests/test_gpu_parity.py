@@ -853,6 +853,22 @@ def test_cli_under_torchrun_two_gpus(l2, tmp_path):
     assert open(tmp_path / "one" / bn).read() == open(tmp_path / "two" / bn).read()
 
 
+@pytest.mark.parametrize("ranks,N,mode", [(2, 900, "l1"), (3, 700, "l1"), (4, 400, "l2"), (2, 640, "l2")])
+def test_sharded_job_ranks_sharing_one_gpu(ranks, N, mode):
+    """The multi-GPU job with several ranks on ONE device (collectives over gloo, staged through the host): everything
+    CUDA-side of the peer form is real — IPC mappings between the processes, copy-engine pulls, arrival flags polled by
+    the running kernel, tiles stored in place into rank 0's matrix and into the shared host matrix, the float64 list
+    pass — so the form is covered on the driver's single-GPU box too."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr",
+           "127.0.0.1", "--master-port", "29543", os.path.join(repo, "tests", "multi_gpu_worker.py"), str(N), mode]
+    res = subprocess.run(cmd, cwd=repo, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "MULTI_GPU_OK" in res.stdout, (res.stdout[-2000:], res.stderr[-4000:])
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
 @pytest.mark.parametrize("N,mode", [(1500, "l1"), (300, "l2"), (700, "l2"), (130, "l1")])
 def test_sharded_job_on_real_gpus(N, mode):
