@@ -95,7 +95,7 @@ def _main_multi_gpu(args, input, fun_files, is_L2, make_diffab, save_Ppushed, py
             Xall = torch.empty((world * job.shard, ctx.n), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(Xall, Xs)
             keep = torch.cat([torch.arange(r * job.shard, r * job.shard + hi - lo, device=dev)
-                              for r in range(world) for lo, hi in [sharded.sample_range(N, world, r)]])
+                              for r in range(world) for lo, hi in [sharded.sample_range(N, world, r, job.shard)]])
             pushed = ctx.push_up_job(Xall[keep].contiguous(), mode)
             p0, p1 = engine.diffab_pair_range(N, world, rank)
             part = solver.diffab_entries(ctx, pushed.P64T, N, mode, pair_begin=p0, pair_end=p1)

@@ -103,6 +103,15 @@ inline void key_append(std::string &key, const T &v)
     key.append(reinterpret_cast<const char *>(&v), sizeof(T));
 }
 
+// Tables of a sharded Gram job, kept in the context between its phases (fuf_gram_plan .. fuf_gram_tiles)
+struct GramJob {
+    int32_t n_rows = 0, n_direct = 0, n_direct_pad = 0, n_parts = 0, n_groups = 0;
+    int32_t *d_map = nullptr;
+    float *d_scl = nullptr;
+    void *d_groups = nullptr, *d_parts = nullptr;
+    int32_t *d_dn = nullptr;
+};
+
 }  // namespace fuf
 
 struct fuf_ctx {
@@ -140,6 +149,8 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_panel;    // transposed tile panels of fuf_store_tile_rows_host
     fuf::DeviceBuffer ws_gram;     // int8 digit planes + tables of fuf_pairwise_gram
     fuf::DeviceBuffer ws_gram_small;  // column maxima
+    fuf::DeviceBuffer ws_gram_tab;    // plan tables of a sharded Gram job
+    fuf::GramJob gram_job;
     fuf::DeviceBuffer ws_p64;      // centre + error statistics (fuf_all_pairs_host)
     fuf::DeviceBuffer ws_p64t;     // float64 pushed profiles, only when a pair has to be refined (fuf_all_pairs_host)
     unsigned long long *d_refined = nullptr;  // pairs recomputed by the last fuf_refine

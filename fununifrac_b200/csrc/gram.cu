@@ -471,7 +471,28 @@ struct Params2 {
     Lay sub;
     double *D2;          // optional second destination (page-locked host matrix), same indexing
     int64_t ldd2;
+    // sharded jobs (fuf_gram_tiles): digit planes of peer shards arrive while the kernel runs; refinement flags are
+    // evaluated where the distances are produced
+    const uint32_t *dep_flags;   // PairTile::pad = dependency + 1: wait until dep_flags[dependency] reaches `epoch`
+    uint32_t epoch;
+    const double *err;           // per-sample rounding statistic (push-up + quantisation): D < kappa_r (sqrt e_i + sqrt e_j)^2
+    const double *h2;            // per-sample scale statistic: D < kappa_l (h2_i + h2_j)
+    double kappa_r, kappa_l;
+    long long *flag_list;        // [0] = count, then (i, j) pairs; nullptr: no flagging
+    long long list_cap;
 };
+
+__device__ __forceinline__ void gram_wait_shard(const uint32_t *flag, uint32_t epoch)
+{
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t seen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) break;
+        if (spin > (1u << 24)) __trap();        // ~3 s: a lost copy is a CUDA error, not a hung GPU
+        __nanosleep(200);
+    }
+    asm volatile("fence.proxy.async.global;" ::: "memory");     // the TMA reads come after the observation
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -554,6 +575,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 uint32_t it = 0;
                 for (int t = pair; t < p.n_tiles; t += n_pairs) {
                     const PairTile tl = p.tiles[t];
+                    if (tl.pad) gram_wait_shard(p.dep_flags + (tl.pad - 1), p.epoch);   // a peer's shard still in flight
                     const int sa = (2 * tl.b + (int)rank) * TILE;          // first sample of this CTA's column tile
                     const int sb = tl.ti * TILE + 64 * (int)rank;          // its half of the row tile
                     const int ia = sa % p.S, ga = sa / p.S, ib = sb % p.S, gb = sb / p.S;
@@ -671,6 +693,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
             if (gj < p.N) {
                 const double qj = p.q[gj];
+                const double rej = p.flag_list ? sqrt(p.err[gj]) : 0.0, hj = p.flag_list ? p.h2[gj] : 0.0;
                 double *dcol = p.D + ((int64_t)tl.out_row0 + half * 64) * p.ldd + gj;   // walks down the rows
                 double *mrow = p.D + gj * p.ldd + gi0;
 #pragma unroll
@@ -678,6 +701,20 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                     const int64_t gi = gi0 + e;
                     if (gi < p.N) {
                         const double v = (gi == gj) ? 0.0 : (p.q[gi] + qj) - 2.0 * acc[e];
+                        if (p.flag_list && gi < gj) {
+                            // the two criteria of the Gram refinement (refine.cu): rounding of the operands, and the
+                            // dropped digit-product orders measured by the scale statistic
+                            const double b = sqrt(p.err[gi]) + rej;
+                            bool flag = !(v >= p.kappa_r * b * b) && b != 0.0;
+                            flag = flag || !(v >= p.kappa_l * (p.h2[gi] + hj));
+                            if (flag) {
+                                const unsigned long long at = atomicAdd(reinterpret_cast<unsigned long long *>(p.flag_list), 1ull);
+                                if ((long long)at < p.list_cap) {
+                                    p.flag_list[1 + 2 * at] = gi;
+                                    p.flag_list[2 + 2 * at] = gj;
+                                }
+                            }
+                        }
                         dcol[(int64_t)e * p.ldd] = v;         // lanes = consecutive gj: one 256-byte store per warp
                         if (mirror) mrow[e] = v;
                         if (p.D2) {
@@ -970,52 +1007,19 @@ static int make_map(CUtensorMap *map, const int8_t *ptr, int64_t N, int32_t n_ro
     return FUF_OK;
 }
 
-}  // namespace gram
+// The host-side plan of a Gram job from the column statistics (cmax | nnz | energy, n floats each): scale buckets,
+// float64 bypass columns, permuted row map.  Deterministic in its input, so ranks that all-reduce the statistics of
+// their shards arrive at the same plan.
+struct GramPlanHost {
+    std::vector<int32_t> row_map, direct_nodes;
+    std::vector<float> inv_scale;
+    std::vector<Group> groups;
+    std::vector<Part> parts;
+    int32_t n_rows = 0, n_direct = 0, n_direct_pad = 16;
+};
 
-int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
-                  const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
-                  double *D, int64_t ldd, cudaStream_t stream, double *D_second, int64_t ldd_second)
+static int gram_make_plan(fuf_ctx *ctx, const std::vector<float> &cstat, int32_t n, GramPlanHost &plan)
 {
-    using namespace gram;
-    if (N == 0) return FUF_OK;
-    const int32_t n = ctx->n;
-    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
-    FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise_gram: PT must be 16-byte aligned");
-    Lay lay;
-    int64_t n_cols;  // sample slots of the digit planes
-    if (shard == 0) {
-        FUF_REQUIRE(ldp % 4 == 0 && ldp >= N, "fuf_pairwise_gram: ldp=%lld must be a multiple of 4 and >= N=%lld",
-                    (long long)ldp, (long long)N);
-        n_cols = tiles_per_dim * TILE;
-        lay = Lay{ldp, 0, ldp};
-    } else {
-        FUF_REQUIRE(shard % TILE == 0 && shard > 0 && shard_stride >= shard * (int64_t)n && shard_stride % 4 == 0,
-                    "fuf_pairwise_gram: bad shard layout (shard=%lld stride=%lld)", (long long)shard,
-                    (long long)shard_stride);
-        n_cols = (N + shard - 1) / shard * shard;
-        lay = Lay{shard, shard_stride, shard};
-    }
-    std::vector<Tile> tiles;
-    const bool full = (tile_rows_h == nullptr);
-    const int32_t n_trows = full ? (int32_t)tiles_per_dim : n_tile_rows;
-    for (int32_t c = 0; c < n_trows; c++) {
-        const int32_t t = full ? c : tile_rows_h[c];
-        FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise_gram: tile row %d out of range [0,%lld)", t,
-                    (long long)tiles_per_dim);
-        for (int32_t tj = t; tj < tiles_per_dim; tj++) tiles.push_back(Tile{t, tj, full ? t * TILE : c * TILE, 0});
-    }
-    if (tiles.empty()) return FUF_OK;
-
-    // ---- column maxima -> buckets (powers of four), permutation, stage table --------------------------------
-    int rc = ctx->ws_gram_small.reserve(3 * (size_t)n * sizeof(float));
-    if (rc) return rc;
-    float *d_cmax = (float *)ctx->ws_gram_small.ptr;
-    gram_colmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, d_cmax, d_cmax + n, d_cmax + 2 * n);
-    FUF_CUDA(cudaGetLastError());
-    std::vector<float> cstat(3 * (size_t)n);
-    FUF_CUDA(cudaMemcpyAsync(cstat.data(), d_cmax, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    FUF_CUDA(cudaStreamSynchronize(stream));
-    const auto t_plan0 = std::chrono::steady_clock::now();
     const float *cmax = cstat.data(), *nnz = cmax + n, *energy = nnz + n;
     std::vector<std::pair<int32_t, int32_t>> keyed, direct_keyed;  // (bucket exponent, node), all-zero columns dropped
     keyed.reserve(n);
@@ -1113,12 +1117,18 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     }
     const int32_t n_direct = (int32_t)direct_keyed.size();
     const int32_t n_direct_pad = std::max(16, (n_direct + 15) / 16 * 16);
-    std::vector<int32_t> direct_nodes(n_direct_pad, -1);
+    std::vector<int32_t> &direct_nodes = plan.direct_nodes;
+    direct_nodes.assign(n_direct_pad, -1);
     for (int32_t i = 0; i < n_direct; i++) direct_nodes[i] = direct_keyed[i].second;
     ctx->gram_bypassed = n_direct;
-    std::vector<int32_t> row_map;
-    std::vector<float> inv_scale;
-    std::vector<Group> groups;
+    plan.n_direct = n_direct;
+    plan.n_direct_pad = n_direct_pad;
+    std::vector<int32_t> &row_map = plan.row_map;
+    std::vector<float> &inv_scale = plan.inv_scale;
+    std::vector<Group> &groups = plan.groups;
+    row_map.clear();
+    inv_scale.clear();
+    groups.clear();
     for (size_t i = 0; i < keyed.size();) {
         size_t j = i;
         // one bucket; at most 32,768 rows per group so that 4 x 127^2 x rows stays below 2^31 in accumulator 3
@@ -1148,21 +1158,79 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         inv_scale.assign(KC, 0.f);
         groups.push_back(Group{1, 0, 0.0});
     }
+    plan.n_rows = (int32_t)row_map.size();
+    plan.parts.clear();          // <= 512 rows each, never across a bucket boundary
+    {
+        int32_t r0 = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            const int32_t r_end = groups[g].stage_end * KC;
+            for (int32_t r = r0; r < r_end; r += 512) plan.parts.push_back(Part{r, std::min(r_end, r + 512), (int32_t)g, 0});
+            r0 = r_end;
+        }
+    }
+    ctx->gram_groups = (int32_t)groups.size();
+    return FUF_OK;
+}
+
+}  // namespace gram
+
+int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
+                  const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
+                  double *D, int64_t ldd, cudaStream_t stream, double *D_second, int64_t ldd_second)
+{
+    using namespace gram;
+    if (N == 0) return FUF_OK;
+    const int32_t n = ctx->n;
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    FUF_REQUIRE(((uintptr_t)PT & 15) == 0, "fuf_pairwise_gram: PT must be 16-byte aligned");
+    Lay lay;
+    int64_t n_cols;  // sample slots of the digit planes
+    if (shard == 0) {
+        FUF_REQUIRE(ldp % 4 == 0 && ldp >= N, "fuf_pairwise_gram: ldp=%lld must be a multiple of 4 and >= N=%lld",
+                    (long long)ldp, (long long)N);
+        n_cols = tiles_per_dim * TILE;
+        lay = Lay{ldp, 0, ldp};
+    } else {
+        FUF_REQUIRE(shard % TILE == 0 && shard > 0 && shard_stride >= shard * (int64_t)n && shard_stride % 4 == 0,
+                    "fuf_pairwise_gram: bad shard layout (shard=%lld stride=%lld)", (long long)shard,
+                    (long long)shard_stride);
+        n_cols = (N + shard - 1) / shard * shard;
+        lay = Lay{shard, shard_stride, shard};
+    }
+    std::vector<Tile> tiles;
+    const bool full = (tile_rows_h == nullptr);
+    const int32_t n_trows = full ? (int32_t)tiles_per_dim : n_tile_rows;
+    for (int32_t c = 0; c < n_trows; c++) {
+        const int32_t t = full ? c : tile_rows_h[c];
+        FUF_REQUIRE(t >= 0 && t < tiles_per_dim, "fuf_pairwise_gram: tile row %d out of range [0,%lld)", t,
+                    (long long)tiles_per_dim);
+        for (int32_t tj = t; tj < tiles_per_dim; tj++) tiles.push_back(Tile{t, tj, full ? t * TILE : c * TILE, 0});
+    }
+    if (tiles.empty()) return FUF_OK;
+
+    // ---- column maxima -> buckets (powers of four), permutation, stage table --------------------------------
+    int rc = ctx->ws_gram_small.reserve(3 * (size_t)n * sizeof(float));
+    if (rc) return rc;
+    float *d_cmax = (float *)ctx->ws_gram_small.ptr;
+    gram_colmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(PT, lay, N, n, d_cmax, d_cmax + n, d_cmax + 2 * n);
+    FUF_CUDA(cudaGetLastError());
+    std::vector<float> cstat(3 * (size_t)n);
+    FUF_CUDA(cudaMemcpyAsync(cstat.data(), d_cmax, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    FUF_CUDA(cudaStreamSynchronize(stream));
+    const auto t_plan0 = std::chrono::steady_clock::now();
+    GramPlanHost plan;
+    if ((rc = gram_make_plan(ctx, cstat, n, plan))) return rc;
+    std::vector<int32_t> &row_map = plan.row_map, &direct_nodes = plan.direct_nodes;
+    std::vector<float> &inv_scale = plan.inv_scale;
+    std::vector<Group> &groups = plan.groups;
+    const int32_t n_direct = plan.n_direct, n_direct_pad = plan.n_direct_pad;
     const int32_t n_rows = (int32_t)row_map.size();
     Lay ws = shard == 0 ? Lay{n_cols, 0, n_cols} : Lay{shard, (int64_t)n_rows * shard, shard};
 
     // ---- workspace: four digit planes | partial statistics | row map, scales, groups, tiles -----------------
     auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
     const size_t plane = up((size_t)n_rows * n_cols);
-    std::vector<Part> parts;          // <= 512 rows each, never across a bucket boundary
-    {
-        int32_t r0 = 0;
-        for (size_t g = 0; g < groups.size(); g++) {
-            const int32_t r_end = groups[g].stage_end * KC;
-            for (int32_t r = r0; r < r_end; r += 512) parts.push_back(Part{r, std::min(r_end, r + 512), (int32_t)g, 0});
-            r0 = r_end;
-        }
-    }
+    std::vector<Part> &parts = plan.parts;
     const int32_t n_parts = (int32_t)parts.size();
     const size_t part_bytes = up((size_t)n_parts * n_cols * sizeof(double));
     const size_t cself_bytes = up((size_t)n_parts * 4 * n_cols * sizeof(int32_t));
@@ -1273,6 +1341,12 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         p2.sub = sub;
         p2.D2 = D_second;
         p2.ldd2 = ldd_second;
+        p2.dep_flags = nullptr;
+        p2.epoch = 0;
+        p2.err = p2.h2 = nullptr;
+        p2.kappa_r = p2.kappa_l = 0.0;
+        p2.flag_list = nullptr;
+        p2.list_cap = 0;
         FUF_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
         const int n_pairs = (int)std::min<int64_t>(p2.n_tiles, ctx->sm_count / 2);
         FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
@@ -1297,6 +1371,182 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
 }  // namespace fuf
 
 using namespace fuf;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sharded --L2 job (several GPUs of one node): the same computation as fuf_pairwise_gram in phases, so that every rank
+// quantises only its own shard and pulls the digit planes of the shards its tiles need from its peers.
+//   fuf_gram_colstats   column statistics of the own shard                        (all-reduce them: max | sum | sum)
+//   fuf_gram_plan       the plan from the reduced statistics (identical on every rank); keeps its tables in the context
+//   fuf_gram_digits     digit planes, bypass rows and per-sample statistics of the own shard
+//   fuf_gram_tiles      the CTA-pair tile kernel on an explicit list of (row tile, column-tile pair, dependency) items,
+//                       every tile stored in place into the full matrix, refinement flags from the epilogue
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int fuf_gram_colstats(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_t ld, float *stats, void *stream)
+{
+    using namespace gram;
+    FUF_REQUIRE(ctx && PT_shard && stats, "fuf_gram_colstats: null argument");
+    FUF_REQUIRE(n_valid >= 0 && ld >= n_valid && ld % 4 == 0 && ((uintptr_t)PT_shard & 15) == 0, "fuf_gram_colstats: bad shape");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    const int32_t n = ctx->n;
+    gram_colmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(PT_shard, Lay{ld, 0, ld}, n_valid, n, stats,
+                                                                                 stats + n, stats + 2 * n);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return FUF_OK;
+}
+
+extern "C" int fuf_gram_plan(fuf_ctx *ctx, const float *stats, int32_t *n_rows, int32_t *n_direct_pad, void *stream)
+{
+    using namespace gram;
+    FUF_REQUIRE(ctx && stats && n_rows && n_direct_pad, "fuf_gram_plan: null argument");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t n = ctx->n;
+    std::vector<float> cstat(3 * (size_t)n);
+    FUF_CUDA(cudaMemcpyAsync(cstat.data(), stats, cstat.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    FUF_CUDA(cudaStreamSynchronize(st));
+    GramPlanHost plan;
+    int rc = gram_make_plan(ctx, cstat, n, plan);
+    if (rc) return rc;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t map_b = up(plan.row_map.size() * sizeof(int32_t)), scl_b = up(plan.inv_scale.size() * sizeof(float));
+    const size_t grp_b = up(plan.groups.size() * sizeof(Group)), part_b = up(plan.parts.size() * sizeof(Part));
+    const size_t dn_b = up(plan.direct_nodes.size() * sizeof(int32_t));
+    if ((rc = ctx->ws_gram_tab.reserve(map_b + scl_b + grp_b + part_b + dn_b))) return rc;
+    char *w = (char *)ctx->ws_gram_tab.ptr;
+    GramJob &job = ctx->gram_job;
+    job.d_map = (int32_t *)w;
+    job.d_scl = (float *)(w + map_b);
+    job.d_groups = w + map_b + scl_b;
+    job.d_parts = w + map_b + scl_b + grp_b;
+    job.d_dn = (int32_t *)(w + map_b + scl_b + grp_b + part_b);
+    FUF_CUDA(cudaMemcpyAsync(job.d_map, plan.row_map.data(), plan.row_map.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FUF_CUDA(cudaMemcpyAsync(job.d_scl, plan.inv_scale.data(), plan.inv_scale.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    FUF_CUDA(cudaMemcpyAsync(job.d_groups, plan.groups.data(), plan.groups.size() * sizeof(Group), cudaMemcpyHostToDevice, st));
+    FUF_CUDA(cudaMemcpyAsync(job.d_parts, plan.parts.data(), plan.parts.size() * sizeof(Part), cudaMemcpyHostToDevice, st));
+    FUF_CUDA(cudaMemcpyAsync(job.d_dn, plan.direct_nodes.data(), plan.direct_nodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FUF_CUDA(cudaStreamSynchronize(st));   // the host vectors are pageable and die with this call
+    job.n_rows = plan.n_rows;
+    job.n_direct = plan.n_direct;
+    job.n_direct_pad = plan.n_direct_pad;
+    job.n_parts = (int32_t)plan.parts.size();
+    job.n_groups = (int32_t)plan.groups.size();
+    *n_rows = plan.n_rows;
+    *n_direct_pad = plan.n_direct_pad;
+    return FUF_OK;
+}
+
+extern "C" int fuf_gram_digits(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_t shard, int8_t *planes,
+                               int64_t plane_stride, int64_t shard_stride, int32_t shard_index, const double *err_in,
+                               double *q, double *h2, double *err_out, double *SUB, int64_t sub_shard_stride, void *stream)
+{
+    using namespace gram;
+    FUF_REQUIRE(ctx && PT_shard && planes && q && h2 && err_out && SUB, "fuf_gram_digits: null argument");
+    const GramJob &job = ctx->gram_job;
+    FUF_REQUIRE(job.n_rows > 0, "fuf_gram_digits: no plan (call fuf_gram_plan first)");
+    FUF_REQUIRE(shard > 0 && shard % TILE == 0 && n_valid >= 0 && n_valid <= shard && shard_index >= 0, "fuf_gram_digits: bad shape");
+    FUF_REQUIRE(shard_stride >= (int64_t)job.n_rows * shard && plane_stride >= shard_stride &&
+                    sub_shard_stride >= (int64_t)job.n_direct_pad * shard,
+                "fuf_gram_digits: plane / bypass buffers too small for the plan (%d rows, %d bypass rows)", job.n_rows, job.n_direct_pad);
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
+    const size_t part_bytes = up((size_t)job.n_parts * shard * sizeof(double));
+    const size_t cself_bytes = up((size_t)job.n_parts * 4 * shard * sizeof(int32_t));
+    int rc = ctx->ws_gram.reserve(2 * part_bytes + cself_bytes);
+    if (rc) return rc;
+    double *r2part = (double *)ctx->ws_gram.ptr, *h2part = (double *)((char *)r2part + part_bytes);
+    int32_t *cself = (int32_t *)((char *)h2part + part_bytes);
+    const Lay one{shard, 0, shard};
+    int8_t *D0 = planes + (int64_t)shard_index * shard_stride;
+    dim3 g((unsigned)((shard / 4 + 127) / 128), (unsigned)job.n_parts);
+    gram_digits_kernel<<<g, 128, 0, st>>>(PT_shard, one, one, shard, n_valid, (const Part *)job.d_parts, job.d_map, job.d_scl, D0,
+                                          D0 + plane_stride, D0 + 2 * plane_stride, D0 + 3 * plane_stride, r2part, h2part, cself);
+    FUF_CUDA(cudaGetLastError());
+    if (n_valid > 0) {
+        gram_stat_kernel<<<(unsigned)((n_valid + 255) / 256), 256, 0, st>>>(r2part, h2part, cself, (const Part *)job.d_parts, job.n_parts,
+                                                                            (const Group *)job.d_groups, shard, err_in, n_valid, h2,
+                                                                            err_out, q);
+        FUF_CUDA(cudaGetLastError());
+    }
+    dim3 gg((unsigned)((shard + 255) / 256), (unsigned)job.n_direct_pad);
+    gram_gather_kernel<<<gg, 256, 0, st>>>(PT_shard, one, one, shard, n_valid, job.d_dn, SUB + (int64_t)shard_index * sub_shard_stride);
+    FUF_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+    return FUF_OK;
+}
+
+extern "C" int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_stride, int64_t shard_stride, int64_t N,
+                              int64_t shard, const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch,
+                              const double *q, const double *h2, const double *err, const double *SUB,
+                              int64_t sub_shard_stride, double *D, int64_t ldd, int64_t *flag_list, int64_t list_cap,
+                              void *stream)
+{
+    using namespace gram;
+    FUF_REQUIRE(ctx && planes && q && D && (tiles_h || n_tiles == 0), "fuf_gram_tiles: null argument");
+    const GramJob &job = ctx->gram_job;
+    FUF_REQUIRE(job.n_rows > 0, "fuf_gram_tiles: no plan (call fuf_gram_plan first)");
+    FUF_REQUIRE(N > 0 && ldd >= N && shard > 0 && shard % (2 * TILE) == 0, "fuf_gram_tiles: bad shape (shards are multiples of 256)");
+    FUF_REQUIRE(!flag_list || (h2 && err), "fuf_gram_tiles: flag_list needs the statistics");
+    if (n_tiles == 0) return FUF_OK;
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
+    std::vector<PairTile> ptiles((size_t)n_tiles);
+    for (int32_t c = 0; c < n_tiles; c++) {
+        const int32_t ti = tiles_h[3 * c], b = tiles_h[3 * c + 1], dep = tiles_h[3 * c + 2];
+        FUF_REQUIRE(ti >= 0 && ti < tiles_per_dim && b >= ti / 2 && 2 * b < tiles_per_dim, "fuf_gram_tiles: item (%d, %d) outside the upper triangle", ti, b);
+        FUF_REQUIRE(dep >= -1 && (dep < 0 || dep_flags), "fuf_gram_tiles: bad dependency %d", dep);
+        ptiles[c] = PairTile{ti, b, ti * TILE, dep + 1};
+    }
+    PairTile *d_tiles = nullptr;
+    int rc = ctx->tables.get_by_content("gtiles", ptiles.data(), ptiles.size() * sizeof(PairTile), (void **)&d_tiles);
+    if (rc) return rc;
+    const Lay ws{shard, shard_stride, shard};
+    CUtensorMap ma[4], mb[4];
+    for (int pl = 0; pl < 4; pl++)
+        if ((rc = make_map(&ma[pl], planes + pl * plane_stride, N, job.n_rows, ws)) ||
+            (rc = make_map(&mb[pl], planes + pl * plane_stride, N, job.n_rows, ws, 64)))
+            return rc;
+    Params2 p2;
+    p2.tiles = d_tiles;
+    p2.groups = (const Group *)job.d_groups;
+    p2.n_tiles = n_tiles;
+    p2.n_groups = job.n_groups;
+    p2.S = (int32_t)shard;
+    p2.tiles_per_dim = (int32_t)tiles_per_dim;
+    p2.N = N;
+    p2.q = q;
+    p2.D = D;
+    p2.ldd = ldd;
+    p2.mirror = 1;
+    p2.n_direct = job.n_direct;
+    p2.SUB = SUB;
+    p2.sub = Lay{shard, sub_shard_stride, shard};
+    p2.D2 = nullptr;
+    p2.ldd2 = 0;
+    p2.dep_flags = dep_flags;
+    p2.epoch = epoch;
+    p2.err = err;
+    p2.h2 = h2;
+    p2.kappa_r = 1.6e13;
+    p2.kappa_l = 2.9e-3;
+    p2.flag_list = (long long *)flag_list;
+    p2.list_cap = list_cap;
+    if (!ctx->ev_gram[0]) {
+        FUF_CUDA(cudaEventCreate(&ctx->ev_gram[0]));
+        FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
+    }
+    FUF_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
+    const int n_pairs = (int)std::min<int64_t>(n_tiles, ctx->sm_count / 2);
+    FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], st));
+    gram_pair_kernel<<<2 * n_pairs, NTHREADS, SMEM2_BYTES, st>>>(ma[0], ma[1], ma[2], ma[3], mb[0], mb[1], mb[2], mb[3], p2);
+    FUF_CUDA(cudaGetLastError());
+    FUF_CUDA(cudaEventRecord(ctx->ev_gram[1], st));
+    ctx->gram_flops = 10.0 * 2.0 * (2.0 * TILE) * TILE * (double)job.n_rows * (double)n_tiles;
+    ctx->launches += 1;
+    return FUF_OK;
+}
 
 extern "C" int fuf_gram_last_kernel(fuf_ctx *ctx, float *ms, double *executed_flops)
 {

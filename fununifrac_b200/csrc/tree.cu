@@ -441,6 +441,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     ctx->ws_panel.release();
     ctx->ws_gram.release();
     ctx->ws_gram_small.release();
+    ctx->ws_gram_tab.release();
     ctx->ws_p64.release();
     ctx->ws_p64t.release();
     ctx->ws_push.release();

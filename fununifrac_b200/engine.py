@@ -78,6 +78,10 @@ def load_library() -> ctypes.CDLL:
         u32 = ctypes.c_uint32
         L.fuf_pairwise_tiles.argtypes = [vp, vp, i64, i64, i64, ci, vp, i32, vp, u32, vp, i64, vp, ctypes.c_double, vp, i64, vp]
         L.fuf_refine_list.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i64, vp, i64, vp]
+        L.fuf_gram_colstats.argtypes = [vp, vp, i64, i64, vp, vp]
+        L.fuf_gram_plan.argtypes = [vp, vp, ctypes.POINTER(i32), ctypes.POINTER(i32), vp]
+        L.fuf_gram_digits.argtypes = [vp, vp, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp]
+        L.fuf_gram_tiles.argtypes = [vp, vp, i64, i64, i64, i64, vp, i32, vp, u32, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp]
         L.fuf_peer_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
         L.fuf_peer_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.fuf_peer_close.argtypes = [vp, vp]
@@ -109,7 +113,7 @@ def load_library() -> ctypes.CDLL:
                      "fuf_diffab_gather", "fuf_store_tile_rows_host", "fuf_pack_tile_rows", "fuf_assemble_packed",
                      "fuf_all_pairs_host", "fuf_last_timing", "fuf_pairwise_tiles", "fuf_refine_list", "fuf_peer_alloc",
                      "fuf_peer_open", "fuf_peer_close", "fuf_peer_free", "fuf_copy_async", "fuf_stream_write_u32",
-                     "fuf_host_device_pointer"):
+                     "fuf_host_device_pointer", "fuf_gram_colstats", "fuf_gram_plan", "fuf_gram_digits", "fuf_gram_tiles"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
             raise FunUniFracError(f"{LIB_PATH} has ABI version {L.fuf_version()}, this package needs {ABI_VERSION}: "
@@ -491,6 +495,41 @@ class TreeContext:
                                             None if flag_list is None else flag_list.data_ptr(), int(list_cap),
                                             _stream_ptr(torch)), "fuf_pairwise_tiles")
 
+    # the --L2 tensor-core path in phases (sharded jobs)
+    def gram_colstats(self, PT_shard, n_valid: int, stats):
+        torch = _torch()
+        assert PT_shard.dtype == torch.float32 and PT_shard.stride(1) == 1 and stats.dtype == torch.float32
+        _check(self._lib.fuf_gram_colstats(self.handle, PT_shard.data_ptr(), n_valid, PT_shard.stride(0), stats.data_ptr(),
+                                           _stream_ptr(torch)), "fuf_gram_colstats")
+
+    def gram_plan(self, stats) -> Tuple[int, int]:
+        """(digit-plane rows, padded bypass rows) of the plan for the reduced statistics; synchronises."""
+        torch = _torch()
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        _check(self._lib.fuf_gram_plan(self.handle, stats.data_ptr(), ctypes.byref(a), ctypes.byref(b), _stream_ptr(torch)),
+               "fuf_gram_plan")
+        return a.value, b.value
+
+    def gram_digits(self, PT_shard, n_valid: int, planes, shard_index: int, err_in, q, h2, err_out, SUB):
+        """planes: int8 [4, G, rows_cap, shard]; SUB: float64 [G, bypass_cap, shard]; q / h2 / err_out: this shard's slices."""
+        torch = _torch()
+        shard = int(planes.shape[3])
+        _check(self._lib.fuf_gram_digits(self.handle, PT_shard.data_ptr(), n_valid, shard, planes.data_ptr(), planes.stride(0),
+                                         planes.stride(1), shard_index, err_in.data_ptr(), q.data_ptr(), h2.data_ptr(),
+                                         err_out.data_ptr(), SUB.data_ptr(), SUB.stride(0), _stream_ptr(torch)),
+               "fuf_gram_digits")
+
+    def gram_tiles(self, planes, N: int, tiles, dep_flags, epoch: int, q, h2, err, SUB, D, flag_list=None, list_cap: int = 0):
+        torch = _torch()
+        tl = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3)
+        shard = int(planes.shape[3])
+        dptr, ldd = (D, N) if isinstance(D, int) else (D.data_ptr(), D.stride(0))
+        _check(self._lib.fuf_gram_tiles(self.handle, planes.data_ptr(), planes.stride(0), planes.stride(1), N, shard,
+                                        tl.ctypes.data, len(tl), None if dep_flags is None else dep_flags.data_ptr(),
+                                        epoch & 0xFFFFFFFF, q.data_ptr(), h2.data_ptr(), err.data_ptr(), SUB.data_ptr(),
+                                        SUB.stride(0), dptr, ldd, None if flag_list is None else flag_list.data_ptr(),
+                                        int(list_cap), _stream_ptr(torch)), "fuf_gram_tiles")
+
     def refine_list(self, P64T, N: int, mode: int, flag_list, list_cap: int, D, shard: int = 0, shard_stride: int = 0):
         """``fuf_refine_list``: the flagged pairs recomputed in float64 into D[i, j], D[j, i] (tensor or raw pointer)."""
         torch = _torch()
@@ -650,7 +689,7 @@ class PeerBuffer:
     """Device memory shared between the processes of one node through a CUDA IPC handle.  ``tensor`` is a torch view of
     it on this process's device (for a mapping of a peer's buffer: the peer's memory, reached over NVLink)."""
 
-    _TYPESTR = {"float32": "<f4", "float64": "<f8", "int32": "<i4", "int64": "<i8"}
+    _TYPESTR = {"float32": "<f4", "float64": "<f8", "int32": "<i4", "int64": "<i8", "int8": "|i1"}
 
     def __init__(self, ctx: TreeContext, shape, dtype: str, handle: Optional[bytes] = None):
         torch = _torch()

@@ -18,8 +18,12 @@ without any collective inside the arithmetic.  Weighted L1 (and the direct --L2 
    the end-of-step barrier), and only if it is non-zero are the float64 profiles pushed up, exchanged and the listed
    pairs recomputed (``fuf_refine_list``).
 
---L2 from 512 samples on (tensor-core Gram kernel) still uses the collective form: all-gather of the pushed blocks, tile
-rows dealt boustrophedon-wise, packed gather to rank 0 (``step``) or per-rank stores into the shared host matrix.
+--L2 from 512 samples on (tensor-core Gram kernel) takes the same form in phases: column statistics of the own shard,
+all-reduced, so that every rank derives the same plan (``fuf_gram_colstats`` / ``fuf_gram_plan``); int8 digit planes of
+the own shard only (``fuf_gram_digits``); the copy stream pulls the planes — not the fp32 operands — of the G/2 shards
+the rank's tiles touch; one launch of the CTA-pair tile kernel (``fuf_gram_tiles``) with the same arrival flags, in-place
+stores and epilogue flags.  ``peer=False`` keeps the older collective form (all-gather of the pushed blocks, tile rows
+dealt boustrophedon-wise, packed gather to rank 0 or per-rank stores into the shared host matrix).
 
 The compute calls are injected (``ops``) so that the partition / exchange logic is testable on CPU with the
 ``gloo`` backend; the product always injects ``engine.TreeContext`` (CUDA).  ``world == 1`` needs no process group.
@@ -31,15 +35,29 @@ from typing import List, Optional, Sequence  # noqa: F401
 TILE = 128
 
 
-def shard_size(N: int, world: int) -> int:
-    """Samples per rank: ceil(N / world) rounded up to a multiple of the 128-sample tile."""
+def shard_size(N: int, world: int, multiple: int = TILE) -> int:
+    """Samples per rank: ceil(N / world) rounded up to a multiple of the 128-sample tile (256 for the CTA-pair Gram kernel
+    of the peer form, whose work items are pairs of column tiles)."""
     per = (N + world - 1) // world
-    return max(TILE, (per + TILE - 1) // TILE * TILE)
+    return max(multiple, (per + multiple - 1) // multiple * multiple)
 
 
-def sample_range(N: int, world: int, rank: int):
-    s = shard_size(N, world)
+def sample_range(N: int, world: int, rank: int, shard: Optional[int] = None):
+    s = shard or shard_size(N, world)
     return min(N, rank * s), min(N, (rank + 1) * s)
+
+
+def gram_items(tiles):
+    """(ti, tj, dependency) tiles of ``peer_tile_plan`` -> work items (ti, b, dependency) of the CTA-pair Gram kernel: row
+    tile ti against the column-tile pair (2b, 2b + 1), in the same order (shards are multiples of 256, so a pair never
+    straddles two shards)."""
+    items, seen = [], set()
+    for ti, tj, dep in tiles:
+        key = (ti, tj // 2)
+        if key not in seen:
+            seen.add(key)
+            items.append((ti, tj // 2, dep))
+    return items
 
 
 def tile_row_owner(t: int, world: int) -> int:
@@ -124,16 +142,17 @@ class ShardedAllPairs:
         self.do_refine = refine
         # --L2 from 512 samples on: tensor-core Gram kernel (its refinement needs the float64 profiles)
         self.use_gram = (mode == 1 and N >= 512 and refine) if gram is None else bool(gram)
-        self.shard = shard_size(N, world)
-        self.lo, self.hi = sample_range(N, world, rank)
+        # peer form on several GPUs (shard pairs, NVLink pulls, in-place stores): weighted L1, the direct --L2 kernel and the
+        # Gram kernel; peer=False keeps the collective form (all-gather, tile rows, packed gather)
+        self.use_peer = world > 1 and peer is not False
+        self.shard = shard_size(N, world, 2 * TILE if (self.use_peer and self.use_gram) else TILE)
+        self.lo, self.hi = sample_range(N, world, rank, self.shard)
         self.all_rows = [owned_tile_rows(N, world, r) for r in range(world)]
         self.rows = self.all_rows[rank]
         self.max_rows = max(len(r) for r in self.all_rows)
         if world > 1 and dist is None:
             raise ValueError("world > 1 needs a torch.distributed process group")
         n = ops.n
-        # peer form (weighted L1 and the direct --L2 kernel on several GPUs): shard pairs, NVLink pulls, in-place stores
-        self.use_peer = world > 1 and not self.use_gram and peer is not False
         self.epoch = 0
         if self.use_peer:
             self._init_peer()
@@ -262,14 +281,31 @@ class ShardedAllPairs:
         self.rows = self.tiles                    # (truthy iff this rank computes anything)
         # every rank's operand buffer [G, n, shard]: slot r is written by its own push-up and read by the peers' copy
         # engines; the other slots receive the pulled shards
-        self.PS_buf = ops.peer_alloc((world, n, sh), "float32")
-        self.PS = self.PS_buf.tensor
         self.D_buf = ops.peer_alloc((N, N), "float64") if rank == 0 else None
         handles = [None] * world
-        dist.all_gather_object(handles, (self.PS_buf.handle, self.D_buf.handle if rank == 0 else None))
-        self.peer_PS = {q: ops.peer_open(handles[q][0], (world, n, sh), "float32") for q in self.pulls}
+        if self.use_gram:
+            # --L2 on the tensor cores: what crosses NVLink are the int8 digit planes (and the few float64 bypass rows)
+            # of the shards this rank's tiles touch; the fp32 operands never leave their GPU
+            self.items = gram_items(self.tiles)
+            self.rows_cap = (n + 4096 + 63) // 64 * 64            # plan rows: n + padding of the scale buckets
+            self.sub_cap = 256                                    # float64 bypass rows (GRAM_DIRECT_ROWS)
+            self.PT_own = ops.empty((n, sh), "float32")
+            self.planes_buf = ops.peer_alloc((4, world, self.rows_cap, sh), "int8")
+            self.sub_buf = ops.peer_alloc((world, self.sub_cap, sh), "float64")
+            self.planes, self.SUB = self.planes_buf.tensor, self.sub_buf.tensor
+            self.gq, self.gh2, self.gerr = (ops.empty((world * sh,), "float64") for _ in range(3))
+            self.colstats = ops.empty((3 * n,), "float32")
+            dist.all_gather_object(handles, (self.planes_buf.handle, self.sub_buf.handle,
+                                             self.D_buf.handle if rank == 0 else None))
+            self.peer_planes = {q: ops.peer_open(handles[q][0], (4, world, self.rows_cap, sh), "int8") for q in self.pulls}
+            self.peer_sub = {q: ops.peer_open(handles[q][1], (world, self.sub_cap, sh), "float64") for q in self.pulls}
+        else:
+            self.PS_buf = ops.peer_alloc((world, n, sh), "float32")
+            self.PS = self.PS_buf.tensor
+            dist.all_gather_object(handles, (self.PS_buf.handle, self.D_buf.handle if rank == 0 else None))
+            self.peer_PS = {q: ops.peer_open(handles[q][0], (world, n, sh), "float32") for q in self.pulls}
         if rank != 0:
-            self.D_buf = ops.peer_open(handles[0][1], (N, N), "float64")
+            self.D_buf = ops.peer_open(handles[0][-1], (N, N), "float64")
         self.D = self.D_buf.tensor if rank == 0 else None
         self.D_target = self.D_buf.tensor         # rank 0's matrix, as seen from this rank
         self.P64S = None
@@ -284,9 +320,58 @@ class ShardedAllPairs:
         self._x_stage = self._pending = self._x_local = None
         dist.barrier()
 
+    def _compute_peer_gram(self, X_local, D_target, mark):
+        """The peer form of the --L2 tensor-core path: push-up and column statistics of the own shard, all-reduce of the
+        statistics (every rank derives the same plan), digits of the own shard, pulls of the peers' digit planes, one
+        launch of the CTA-pair tile kernel storing in place."""
+        ops, N, mode, r, sh, n, dist = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n, self.dist
+        self.epoch += 1
+        mark("start")
+        if r == 0:
+            ops.push_up_center(X_local, mode, self.center)
+        dist.broadcast(self.center, src=0)
+        mark("push_begin")
+        self._x_local = X_local
+        own = slice(r * sh, (r + 1) * sh)
+        n_valid = self.hi - self.lo
+        if n_valid:
+            ops.push_up(X_local, mode, self.PT_own, 0, self.center, None, self.stat[own])
+        mark("push_end")
+        ops.gram_colstats(self.PT_own, n_valid, self.colstats)
+        dist.all_reduce(self.colstats[:n], op=dist.ReduceOp.MAX)
+        dist.all_reduce(self.colstats[n:])
+        n_rows, n_sub = ops.gram_plan(self.colstats)              # (one host synchronisation: the plan is data-dependent)
+        if n_rows > self.rows_cap or n_sub > self.sub_cap:
+            raise RuntimeError(f"Gram plan needs {n_rows} rows / {n_sub} bypass rows, buffers hold {self.rows_cap} / {self.sub_cap}")
+        ops.gram_digits(self.PT_own, n_valid, self.planes, r, self.stat[own], self.gq[own], self.gh2[own], self.gerr[own],
+                        self.SUB)
+        # per-sample norms and statistics of all samples; the last all-gather also says: every shard's planes are ready
+        dist.all_gather_into_tensor(self.gq, self.gq[own])
+        dist.all_gather_into_tensor(self.gh2, self.gh2[own])
+        dist.all_gather_into_tensor(self.gerr, self.gerr[own])
+        ops.zero_(self.flag_list[:1])
+        ready = ops.record_event()
+        ops.stream_wait(self.copy_stream, ready)
+        for q in self.pulls:
+            for pl in range(4):
+                ops.copy_async(self.planes[pl, q, :n_rows], self.peer_planes[q].tensor[pl, q, :n_rows], self.copy_stream)
+            ops.copy_async(self.SUB[q, :n_sub], self.peer_sub[q].tensor[q, :n_sub], self.copy_stream)
+            ops.stream_write_u32(self.flags, q, self.epoch, self.copy_stream)
+        mark("pair_begin")
+        if self.items:
+            ops.gram_tiles(self.planes, N, self.items, self.flags, self.epoch, self.gq, self.gh2, self.gerr, self.SUB, D_target,
+                           self.flag_list if self.do_refine else None, self.list_cap)
+        mark("pair_end")
+        self.flagged.copy_(self.flag_list[:1])
+        dist.all_reduce(self.flagged)
+        self._pending = True
+        mark("refine_end")
+
     def _compute_peer(self, X_local, D_target, mark):
         """Steps 1-4 of the module docstring; afterwards the matrix behind ``D_target`` holds this rank's tiles (the
         refinement decision is pending in ``self.flagged``)."""
+        if self.use_gram:
+            return self._compute_peer_gram(X_local, D_target, mark)
         ops, N, mode, r, sh, n, dist = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n, self.dist
         self.epoch += 1
         mark("start")
@@ -554,6 +639,22 @@ class CudaOps:
             import numpy as np
             self._tiles_np, self._tiles_key = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3), key
         self.ctx.pairwise_tiles(PS, N, mode, self._tiles_np, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap)
+
+    def gram_colstats(self, PT_shard, n_valid, stats):
+        self.ctx.gram_colstats(PT_shard, n_valid, stats)
+
+    def gram_plan(self, stats):
+        return self.ctx.gram_plan(stats)
+
+    def gram_digits(self, PT_shard, n_valid, planes, shard_index, err_in, q, h2, err_out, SUB):
+        self.ctx.gram_digits(PT_shard, n_valid, planes, shard_index, err_in, q, h2, err_out, SUB)
+
+    def gram_tiles(self, planes, N, items, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap):
+        key = id(items)
+        if getattr(self, "_items_key", None) != key:
+            import numpy as np
+            self._items_np, self._items_key = np.ascontiguousarray(items, dtype=np.int32).reshape(-1, 3), key
+        self.ctx.gram_tiles(planes, N, self._items_np, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap)
 
     def refine_list(self, P64S, N, mode, flag_list, list_cap, D, shard, shard_stride):
         self.ctx.refine_list(P64S, N, mode, flag_list, list_cap, D, shard, shard_stride)

@@ -329,6 +329,32 @@ int fuf_pairwise_tiles(fuf_ctx *ctx, const float *PT, int64_t N, int64_t shard, 
 /* The listed pairs recomputed in float64 from P64T (layouts as in fuf_refine) into D[i, j] and D[j, i] of the full matrix. */
 int fuf_refine_list(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride,
                     int mode, const int64_t *flag_list, int64_t list_cap, double *D, int64_t ldd, void *stream);
+/* The --L2 tensor-core path of a sharded job, in phases (the monolithic fuf_pairwise_gram does the same on one GPU):
+ * every rank quantises only its own shard and pulls the digit planes of the shards its tiles need from its peers.
+ *   fuf_gram_colstats: stats (device, 3 n floats: max |entry| | non-zero count | energy per node) of PT_shard [n][ld], the
+ *                      first n_valid columns.  All-reduce across the ranks (max, sum, sum) before planning.
+ *   fuf_gram_plan:     from the reduced statistics (device), the plan — scale buckets, float64 bypass columns, permuted
+ *                      row map; the same on every rank — kept in the context.  Synchronises the stream.  Returns the
+ *                      number of digit-plane rows and of (padded) bypass rows: the buffers below must hold at least that.
+ *   fuf_gram_digits:   the own shard (index shard_index, n_valid samples) -> its slot of the four int8 digit planes
+ *                      planes[p * plane_stride + shard_index * shard_stride + row * shard + s], of the bypass rows
+ *                      SUB[shard_index * sub_shard_stride + row * shard + s] (double), and the per-sample q (norm of the
+ *                      digit form), h2 (scale statistic), err_out (rounding statistic incl. err_in of the push-up):
+ *                      `shard` doubles each, this shard's slice.
+ *   fuf_gram_tiles:    the CTA-pair tile kernel on items (row tile ti, column-tile pair b = tiles 2b, 2b+1, dependency);
+ *                      q / h2 / err / SUB / planes hold all shards the items touch.  Tiles are stored in place into
+ *                      the full matrix D (and mirrored) as in fuf_pairwise_tiles, dependencies and the flag list work
+ *                      the same way (criteria: D < 1.6e13 (sqrt err_i + sqrt err_j)^2 or D < 2.9e-3 (h2_i + h2_j)). */
+int fuf_gram_colstats(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_t ld, float *stats, void *stream);
+int fuf_gram_plan(fuf_ctx *ctx, const float *stats, int32_t *n_rows, int32_t *n_direct_pad, void *stream);
+int fuf_gram_digits(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_t shard, int8_t *planes, int64_t plane_stride,
+                    int64_t shard_stride, int32_t shard_index, const double *err_in, double *q, double *h2, double *err_out,
+                    double *SUB, int64_t sub_shard_stride, void *stream);
+int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_stride, int64_t shard_stride, int64_t N, int64_t shard,
+                   const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch, const double *q,
+                   const double *h2, const double *err, const double *SUB, int64_t sub_shard_stride, double *D, int64_t ldd,
+                   int64_t *flag_list, int64_t list_cap, void *stream);
+
 /* Device buffers shared between the processes of one node (CUDA IPC): the owner allocates (zero-filled) and hands the
  * 64-byte handle to its peers (any channel: the Python host uses torch.distributed), which map it.  A mapping is an
  * ordinary device pointer for kernels (loads, stores) and copy engines (fuf_copy_async). */

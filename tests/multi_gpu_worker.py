@@ -1,6 +1,6 @@
 """Launched by tests/test_gpu_parity.py under torchrun (one process per GPU): the sharded all-pairs job through
 ``sharded.ShardedAllPairs`` on real GPUs — peer form (shard pairs, NVLink pulls, in-place stores into rank 0's matrix or
-the shared host matrix) for weighted L1 / direct --L2, collective form for the Gram path — against the CPU oracle.
+the shared host matrix) for weighted L1, the direct --L2 kernel and the tensor-core Gram path — against the CPU oracle.
 
     torchrun --nproc-per-node G tests/multi_gpu_worker.py N mode        (mode: l1 | l2)
 Prints ``MULTI_GPU_OK`` on rank 0 when every check passed."""
@@ -93,7 +93,7 @@ def main():
     X[N // 2 + 1] = X[7]                                                 # identical pair
     mode = engine.MODE_L2 if l2 else engine.MODE_L1
     job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, mode, world, rank, comm)
-    assert job.use_peer == (not job.use_gram)
+    assert job.use_peer and job.use_gram == (l2 and N >= 512)
     Xl = engine.profile_matrix(job.hi - job.lo, n, torch.float64, f"cuda:{local}")
     Xl.copy_(torch.from_numpy(X[job.lo:job.hi]))
     results = []
@@ -123,9 +123,8 @@ def main():
             assert got[7, N // 2 + 1] == 0.0
         assert all(np.array_equal(results[0], r) for r in results[1:])    # deterministic from step to step
         assert np.allclose(Dh, results[0], rtol=1e-12, atol=0)
-        if job.use_peer:
-            assert job.last_flagged >= 1                                  # the near-duplicate went through the list path
-        print(f"MULTI_GPU_OK world={world} N={N} mode={'l2' if l2 else 'l1'} peer={job.use_peer} flagged={job.last_flagged}",
+        assert job.last_flagged >= 1                                      # the near-duplicate went through the list path
+        print(f"MULTI_GPU_OK world={world} N={N} mode={'l2' if l2 else 'l1'} gram={job.use_gram} flagged={job.last_flagged}",
               flush=True)
     comm.barrier()
     shared.close()

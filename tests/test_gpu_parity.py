@@ -853,7 +853,7 @@ def test_cli_under_torchrun_two_gpus(l2, tmp_path):
     assert open(tmp_path / "one" / bn).read() == open(tmp_path / "two" / bn).read()
 
 
-@pytest.mark.parametrize("ranks,N,mode", [(2, 900, "l1"), (3, 700, "l1"), (4, 400, "l2"), (2, 640, "l2")])
+@pytest.mark.parametrize("ranks,N,mode", [(2, 900, "l1"), (3, 700, "l1"), (4, 400, "l2"), (2, 640, "l2"), (3, 1100, "l2")])
 def test_sharded_job_ranks_sharing_one_gpu(ranks, N, mode):
     """The multi-GPU job with several ranks on ONE device (collectives over gloo, staged through the host): everything
     CUDA-side of the peer form is real — IPC mappings between the processes, copy-engine pulls, arrival flags polled by

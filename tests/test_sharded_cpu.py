@@ -76,7 +76,7 @@ class OracleOps:
     class _Shm:
         def __init__(self, shape, dtype, handle=None):
             import mmap
-            dt = {"float32": np.float32, "float64": np.float64, "int32": np.int32, "int64": np.int64}[dtype]
+            dt = {"float32": np.float32, "float64": np.float64, "int32": np.int32, "int64": np.int64, "int8": np.int8}[dtype]
             nbytes = max(8, int(np.prod(shape)) * np.dtype(dt).itemsize)
             if handle is None:
                 self.fd = os.memfd_create("fuf_test_peer")
@@ -147,6 +147,41 @@ class OracleOps:
                     flag_list[0] = at + 1
                     if at < list_cap:
                         flag_list[1 + 2 * at], flag_list[2 + 2 * at] = int(a_), int(b_)
+
+    # --L2 tensor-core path in phases: the "digit planes" of this stand-in are the four bytes of the fp32 operand, so the
+    # exchange moves exactly the buffers the CUDA path moves and a tile computed from an un-pulled shard comes out wrong
+    def gram_colstats(self, PT_shard, n_valid, stats):
+        P = PT_shard[:, :n_valid]
+        n = self.n
+        stats[:n] = P.abs().max(1).values if n_valid else 0
+        stats[n:2 * n] = (P != 0).sum(1).float()
+        stats[2 * n:] = (P * P).sum(1)
+
+    def gram_plan(self, stats):
+        assert bool((stats[:self.n] >= 0).all())
+        self.plan_stats = stats.clone()
+        return self.n, 16
+
+    def gram_digits(self, PT_shard, n_valid, planes, shard_index, err_in, q, h2, err_out, SUB):
+        raw = PT_shard.contiguous().numpy().view(np.int8).reshape(self.n, PT_shard.shape[1], 4)
+        for pl in range(4):
+            planes[pl, shard_index, :self.n] = torch.from_numpy(raw[:, :, pl].copy())
+        q[:n_valid] = (PT_shard[:, :n_valid].double() ** 2).sum(0)
+        h2[:n_valid] = 0
+        err_out[:n_valid] = err_in[:n_valid]
+
+    def gram_tiles(self, planes, N, items, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap):
+        G, sh = planes.shape[1], planes.shape[3]
+        raw = np.ascontiguousarray(planes[:, :, :self.n].permute(1, 2, 3, 0).numpy())            # [G, n, shard, 4] bytes
+        PS = torch.from_numpy(raw.view(np.float32).reshape(G, self.n, sh))
+        tiles = []
+        for ti, b, dep in items:
+            for tj in (2 * b, 2 * b + 1):
+                if tj >= ti and tj * TILE < N:
+                    tiles.append((ti, tj, dep))
+        l2, self.l2 = self.l2, True
+        self.pairwise_tiles(PS, N, 1, tiles, flags, epoch, D, sh, self.n * sh, err, flag_list, list_cap)
+        self.l2 = l2
 
     def refine_list(self, P64S, N, mode, flag_list, list_cap, D, shard, shard_stride):
         self.refine_calls += 1
@@ -258,14 +293,16 @@ def _worker(rank, world, port, N, l2, out_path, peer):
             X[N - 3] = X[5] * (1 + 1e-9 * rng.random(n))
         X /= X.sum(1, keepdims=True)
         ops = OracleOps(parent, length, l2)
+        gram = bool(l2 and N >= 512)
         job = sharded.ShardedAllPairs(ops, N, int(l2), world, rank, dist, peer=peer)
-        assert job.use_peer == bool(peer)
+        assert job.use_peer == bool(peer) and (not gram or job.use_gram)
         marks = []
         D = job.step(torch.from_numpy(X[job.lo:job.hi]), marks.append)
         assert marks[0] == "start" and marks[-1] == "end" and "pair_begin" in marks
         if peer:
             # shard pairs: every rank pulled floor(G/2) shards at most, and only those that hold tiles
-            assert getattr(ops, "pulled", 0) == len(job.pulls) <= world // 2
+            # (Gram form: four digit planes + the bypass rows per pulled shard)
+            assert getattr(ops, "pulled", 0) == len(job.pulls) * (5 if job.use_gram else 1) and len(job.pulls) <= world // 2
             want_flag = 1 if N > 40 else 0
             assert job.last_flagged == want_flag and ops.refine_calls == want_flag
             assert getattr(ops, "p64_calls", 0) == (want_flag if job.hi > job.lo else 0)
@@ -306,7 +343,8 @@ def _worker(rank, world, port, N, l2, out_path, peer):
 
 
 @pytest.mark.parametrize("world,N,l2,peer", [(2, 300, False, True), (3, 700, False, True), (4, 400, True, True),
-                                             (3, 100, False, True), (2, 300, False, False), (2, 129, True, False)])
+                                             (3, 100, False, True), (2, 300, False, False), (2, 129, True, False),
+                                             (3, 900, True, True), (2, 520, True, True)])
 def test_sharded_exchange_gloo(world, N, l2, peer, tmp_path, monkeypatch):
     """peer=True: the shard-pair form (NVLink pulls + in-place stores, here over shared memory); peer=False: the
     collective form (all-gather, tile rows, packed gather) the Gram path still uses."""
