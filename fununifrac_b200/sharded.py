@@ -562,16 +562,31 @@ class SharedHostMatrix:
             register = torch.cuda.is_available()
         if register and N:
             import torch
-            rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+            rt = torch.cuda.cudart()
+            base = self.array.ctypes.data
+            rc = rt.cudaHostRegister(base, self.nbytes, 0)
+            self._chunks = [(base, self.nbytes)]
             if int(rc) != 0:
-                raise RuntimeError(f"cudaHostRegister of the shared {N} x {N} matrix failed: {rc}")
+                # some boxes refuse one 20 GB registration but take it in pieces; with unified addressing the pieces
+                # still form one contiguous device-visible range
+                self._chunks, step = [], 1 << 30
+                for off in range(0, self.nbytes, step):
+                    size = min(step, self.nbytes - off)
+                    rc = rt.cudaHostRegister(base + off, size, 0)
+                    if int(rc) != 0:
+                        for b, _ in self._chunks:
+                            rt.cudaHostUnregister(b)
+                        raise RuntimeError(f"cudaHostRegister of the shared {N} x {N} matrix failed at byte {off} of "
+                                           f"{self.nbytes}: CUDA error {int(rc)}")
+                    self._chunks.append((base + off, size))
             self._registered = True
 
     def close(self):
         import os
         if self._registered:
             import torch
-            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            for b, _ in self._chunks:
+                torch.cuda.cudart().cudaHostUnregister(b)
             self._registered = False
         self.array = None
         if self._map is not None:
