@@ -3,6 +3,7 @@
 // Replaces the dict-based tree view of the reference (Tint / lint of tree_to_EMDU_input,
 // src/factory/make_emd_input.py:10-54) with dense postorder arrays on the device, plus the
 // metadata the chunked push-up kernel needs (see pushup.cu).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -530,6 +531,48 @@ extern "C" int fuf_peer_free(fuf_ctx *ctx, void *dptr)
     if (!dptr) return FUF_OK;
     FUF_CUDA(cudaSetDevice(ctx->device));
     FUF_CUDA(cudaFree(dptr));
+    return FUF_OK;
+}
+
+// Page-lock a range of host memory another allocator owns (the result matrix the ranks of a node share).  Some boxes
+// refuse one registration of tens of gigabytes (cudaErrorOperatingSystem) but take it in pieces; with unified addressing
+// the pieces still form one contiguous device-visible range.  *n_pieces receives how many registrations were made.
+extern "C" int fuf_host_register(void *ptr, size_t bytes, int32_t *n_pieces)
+{
+    FUF_REQUIRE(ptr && n_pieces, "fuf_host_register: null argument");
+    *n_pieces = 0;
+    if (bytes == 0) return FUF_OK;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+        *n_pieces = 1;
+        return FUF_OK;
+    }
+    cudaGetLastError();   // not sticky: clear it before trying the pieces
+    const size_t step = (size_t)1 << 30;
+    int32_t done = 0;
+    for (size_t off = 0; off < bytes; off += step, done++) {
+        cudaError_t err = cudaHostRegister((char *)ptr + off, std::min(step, bytes - off), cudaHostRegisterDefault);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            for (int32_t q = 0; q < done; q++) cudaHostUnregister((char *)ptr + (size_t)q * step);
+            cudaGetLastError();
+            set_error("fuf_host_register: cudaHostRegister failed at byte %zu of %zu: %s", off, bytes, cudaGetErrorString(err));
+            return FUF_ECUDA;
+        }
+    }
+    *n_pieces = done;
+    return FUF_OK;
+}
+
+extern "C" int fuf_host_unregister(void *ptr, size_t bytes, int32_t n_pieces)
+{
+    if (!ptr || n_pieces <= 0) return FUF_OK;
+    if (n_pieces == 1) {
+        cudaHostUnregister(ptr);
+    } else {
+        const size_t step = (size_t)1 << 30;
+        for (size_t off = 0; off < bytes; off += step) cudaHostUnregister((char *)ptr + off);
+    }
+    cudaGetLastError();
     return FUF_OK;
 }
 

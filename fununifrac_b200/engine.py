@@ -89,6 +89,8 @@ def load_library() -> ctypes.CDLL:
         L.fuf_copy_async.argtypes = [vp, vp, vp, ctypes.c_size_t, vp]
         L.fuf_stream_write_u32.argtypes = [vp, vp, u32, vp]
         L.fuf_host_device_pointer.argtypes = [vp, vp, ctypes.POINTER(vp)]
+        L.fuf_host_register.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(i32)]
+        L.fuf_host_unregister.argtypes = [vp, ctypes.c_size_t, i32]
         L.fuf_pairwise_f64.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, vp]
         L.fuf_assemble.argtypes = [vp, vp, vp, i32, i64, i64, vp, i64, vp]
         L.fuf_pack_tile_rows.argtypes = [vp, vp, i64, vp, vp, i32, i64, vp, vp]
@@ -113,7 +115,7 @@ def load_library() -> ctypes.CDLL:
                      "fuf_diffab_gather", "fuf_store_tile_rows_host", "fuf_pack_tile_rows", "fuf_assemble_packed",
                      "fuf_all_pairs_host", "fuf_last_timing", "fuf_pairwise_tiles", "fuf_refine_list", "fuf_peer_alloc",
                      "fuf_peer_open", "fuf_peer_close", "fuf_peer_free", "fuf_copy_async", "fuf_stream_write_u32",
-                     "fuf_host_device_pointer", "fuf_gram_colstats", "fuf_gram_plan", "fuf_gram_digits", "fuf_gram_tiles"):
+                     "fuf_host_device_pointer", "fuf_host_register", "fuf_host_unregister", "fuf_gram_colstats", "fuf_gram_plan", "fuf_gram_digits", "fuf_gram_tiles"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
             raise FunUniFracError(f"{LIB_PATH} has ABI version {L.fuf_version()}, this package needs {ABI_VERSION}: "

@@ -562,31 +562,21 @@ class SharedHostMatrix:
             register = torch.cuda.is_available()
         if register and N:
             import torch
-            rt = torch.cuda.cudart()
-            base = self.array.ctypes.data
-            rc = rt.cudaHostRegister(base, self.nbytes, 0)
-            self._chunks = [(base, self.nbytes)]
-            if int(rc) != 0:
-                # some boxes refuse one 20 GB registration but take it in pieces; with unified addressing the pieces
-                # still form one contiguous device-visible range
-                self._chunks, step = [], 1 << 30
-                for off in range(0, self.nbytes, step):
-                    size = min(step, self.nbytes - off)
-                    rc = rt.cudaHostRegister(base + off, size, 0)
-                    if int(rc) != 0:
-                        for b, _ in self._chunks:
-                            rt.cudaHostUnregister(b)
-                        raise RuntimeError(f"cudaHostRegister of the shared {N} x {N} matrix failed at byte {off} of "
-                                           f"{self.nbytes}: CUDA error {int(rc)}")
-                    self._chunks.append((base + off, size))
+            import ctypes
+
+            from fununifrac_b200 import engine
+            torch.cuda.init()
+            pieces = ctypes.c_int32()
+            engine._check(engine.load_library().fuf_host_register(self.array.ctypes.data, self.nbytes, ctypes.byref(pieces)),
+                          "fuf_host_register")
+            self._pieces = pieces.value
             self._registered = True
 
     def close(self):
         import os
         if self._registered:
-            import torch
-            for b, _ in self._chunks:
-                torch.cuda.cudart().cudaHostUnregister(b)
+            from fununifrac_b200 import engine
+            engine.load_library().fuf_host_unregister(self.array.ctypes.data, self.nbytes, self._pieces)
             self._registered = False
         self.array = None
         if self._map is not None:

@@ -363,6 +363,10 @@ int fuf_peer_open(fuf_ctx *ctx, const unsigned char handle[64], void **dptr);
 int fuf_peer_close(fuf_ctx *ctx, void *dptr);
 int fuf_peer_free(fuf_ctx *ctx, void *dptr);
 int fuf_copy_async(fuf_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+/* Page-lock host memory owned by another allocator (e.g. a shared-memory mapping every rank of a node writes its tiles
+ * into) — in 1 GB pieces when one registration of the whole range is refused.  Keep *n_pieces for fuf_host_unregister. */
+int fuf_host_register(void *ptr, size_t bytes, int32_t *n_pieces);
+int fuf_host_unregister(void *ptr, size_t bytes, int32_t n_pieces);
 /* Device-side address of page-locked host memory (cudaHostAlloc / cudaHostRegister): lets fuf_pairwise_tiles store its
  * tiles straight into a host matrix (e.g. the one the ranks of a node share and np.save writes). */
 int fuf_host_device_pointer(fuf_ctx *ctx, void *host_ptr, void **dptr);
