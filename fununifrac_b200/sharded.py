@@ -318,6 +318,18 @@ class ShardedAllPairs:
         self.copy_stream = ops.new_stream()
         self.last_flagged = 0
         self._x_stage = self._pending = self._x_local = None
+        # host-buffer form: the own shard is uploaded in up to 4 bands of whole tiles; band b carries the diagonal-block
+        # tiles whose column tile lies in it (their rows lie in bands <= b)
+        own_tiles = [t for t in self.tiles if t[2] < 0]
+        self.offdiag_tiles = [t for t in self.tiles if t[2] >= 0]
+        Ts_own = (self.hi - self.lo + TILE - 1) // TILE
+        self.diag_bands = []
+        if Ts_own >= 8:
+            t0 = rank * (sh // TILE)
+            for b in range(4):
+                lo_t, hi_t = t0 + Ts_own * b // 4, t0 + Ts_own * (b + 1) // 4
+                s0, s1 = (lo_t - t0) * TILE, min(self.hi - self.lo, (hi_t - t0) * TILE)
+                self.diag_bands.append((s0, s1, [t for t in own_tiles if lo_t <= t[1] < hi_t]))
         dist.barrier()
 
     def _compute_peer_gram(self, X_local, D_target, mark):
@@ -367,35 +379,67 @@ class ShardedAllPairs:
         self._pending = True
         mark("refine_end")
 
-    def _compute_peer(self, X_local, D_target, mark):
+    def _compute_peer(self, X_local, D_target, mark, host_src=None):
         """Steps 1-4 of the module docstring; afterwards the matrix behind ``D_target`` holds this rank's tiles (the
-        refinement decision is pending in ``self.flagged``)."""
+        refinement decision is pending in ``self.flagged``).
+
+        ``host_src``: this rank's un-pushed samples in page-locked host memory (``step_host``).  They are then uploaded
+        into ``X_local`` in a few bands of whole tiles; each band is pushed up as soon as it has landed and followed by the
+        tiles of the rank's DIAGONAL block whose columns it completes — the block that needs no remote shard is computed
+        under the rank's own host-to-device transfer, and the peers' shards are pulled when everybody's upload is done."""
         if self.use_gram:
+            if host_src is not None:
+                self.ops.to_device(host_src, X_local)
             return self._compute_peer_gram(X_local, D_target, mark)
         ops, N, mode, r, sh, n, dist = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n, self.dist
         self.epoch += 1
+        own = slice(r * sh, (r + 1) * sh)
+        stat = self.stat if self.do_refine else None
+        flist = self.flag_list if self.do_refine else None
+        rows_own = self.hi - self.lo
+        ops.zero_(self.flag_list[:1])
         mark("start")
-        if r == 0:
-            ops.push_up_center(X_local, mode, self.center)
-        dist.broadcast(self.center, src=0)
-        mark("push_begin")
+        if host_src is None or rows_own == 0 or not self.diag_bands:
+            if host_src is not None:
+                ops.to_device(host_src, X_local)
+            if r == 0:
+                ops.push_up_center(X_local, mode, self.center)
+            dist.broadcast(self.center, src=0)
+            mark("push_begin")
+            if rows_own:
+                ops.push_up(X_local, mode, self.PS[r], 0, self.center, None, self.stat[own])
+            mark("push_end")
+            rest = self.tiles
+        else:
+            events = []
+            for s0, s1, _ in self.diag_bands:        # all uploads are queued up front on the copy stream
+                ops.to_device(host_src[s0:s1], X_local[s0:s1], self.copy_stream)
+                events.append(ops.record_event(self.copy_stream))
+            ops.stream_wait(None, events[0])
+            if r == 0:
+                ops.push_up_center(X_local[:self.diag_bands[0][1]], mode, self.center)
+            dist.broadcast(self.center, src=0)
+            mark("push_begin")
+            for (s0, s1, band_tiles), ev in zip(self.diag_bands, events):
+                ops.stream_wait(None, ev)
+                ops.push_up(X_local[s0:s1], mode, self.PS[r], s0, self.center, None, self.stat[own])
+                if band_tiles:
+                    ops.pairwise_tiles(self.PS, N, mode, band_tiles, self.flags, self.epoch, D_target, sh, n * sh, stat,
+                                       flist, self.list_cap)
+            mark("push_end")
+            rest = self.offdiag_tiles
         self._x_local = X_local
-        if self.hi > self.lo:
-            ops.push_up(X_local, mode, self.PS[r], 0, self.center, None, self.stat[r * sh:(r + 1) * sh])
-        mark("push_end")
         # the statistics of all samples (the epilogue criterion needs both members of a pair); every rank contributes
         # after its push-up, so its arrival also says: all shards are ready to be pulled
-        dist.all_gather_into_tensor(self.stat, self.stat[r * sh:(r + 1) * sh])
-        ops.zero_(self.flag_list[:1])
+        dist.all_gather_into_tensor(self.stat, self.stat[own])
         ready = ops.record_event()
         ops.stream_wait(self.copy_stream, ready)
         for q in self.pulls:                      # NVLink pulls, one after the other, a flag behind each
             ops.copy_async(self.PS[q], self.peer_PS[q].tensor[q], self.copy_stream)
             ops.stream_write_u32(self.flags, q, self.epoch, self.copy_stream)
         mark("pair_begin")
-        if self.tiles:
-            ops.pairwise_tiles(self.PS, N, mode, self.tiles, self.flags, self.epoch, D_target, sh, n * sh,
-                               self.stat if self.do_refine else None, self.flag_list if self.do_refine else None,
+        if rest:
+            ops.pairwise_tiles(self.PS, N, mode, rest, self.flags, self.epoch, D_target, sh, n * sh, stat, flist,
                                self.list_cap)
         mark("pair_end")
         # the next step's pulls and push-up must not start before everybody is done with this step's: the all-reduce of
@@ -477,17 +521,17 @@ class ShardedAllPairs:
             raise ValueError(f"shared matrix is {D_host.array.shape}, job needs {(self.N, self.N)}")
         if self._x_stage is None:
             self._x_stage = self.ops.profile_matrix(max(self.hi - self.lo, 1))
-        X = self.ops.to_device(X_local_host, self._x_stage)
         if self.use_peer:
             # the tiles (and their mirror) are stored by the kernel itself into the page-locked host matrix the ranks
             # share: the device-to-host traffic of all ranks runs over their own PCIe links, under the computation
             target = self.ops.host_target(D_host)
-            self._compute_peer(X, target, mark)
+            self._compute_peer(self._x_stage[:self.hi - self.lo], target, mark, host_src=X_local_host)
             self._refine_peer(target)
             self.ops.synchronize()
             self.dist.barrier()
             mark("end")
             return D_host.array
+        X = self.ops.to_device(X_local_host, self._x_stage)
         self._compute(X, mark)
         if self.world == 1:
             self._refine_if_flagged()
@@ -621,13 +665,13 @@ class CudaOps:
     def new_stream(self):
         return self.torch.cuda.Stream(device=self.device)
 
-    def record_event(self):
+    def record_event(self, stream=None):
         ev = self.torch.cuda.Event()
-        ev.record()
+        ev.record(stream if stream is not None else self.torch.cuda.current_stream())
         return ev
 
     def stream_wait(self, stream, event):
-        stream.wait_event(event)
+        (stream if stream is not None else self.torch.cuda.current_stream()).wait_event(event)
 
     def zero_(self, t):
         t.zero_()
@@ -639,11 +683,12 @@ class CudaOps:
         self.ctx.stream_write_u32(flags, index, value, stream)
 
     def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap):
-        key = id(tiles)
-        if getattr(self, "_tiles_key", None) != key:      # the plan is fixed for the job: convert it once
+        cache = self.__dict__.setdefault("_tiles_np", {})
+        arr = cache.get(id(tiles))
+        if arr is None or arr[0] is not tiles:             # the plans are fixed for the job: convert each list once
             import numpy as np
-            self._tiles_np, self._tiles_key = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3), key
-        self.ctx.pairwise_tiles(PS, N, mode, self._tiles_np, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap)
+            arr = cache[id(tiles)] = (tiles, np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3))
+        self.ctx.pairwise_tiles(PS, N, mode, arr[1], flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap)
 
     def gram_colstats(self, PT_shard, n_valid, stats):
         self.ctx.gram_colstats(PT_shard, n_valid, stats)
@@ -710,10 +755,15 @@ class CudaOps:
     def assemble_packed(self, packed, rows, offsets, N, D):
         return self.ctx.assemble_packed(packed.view(-1), rows, offsets, N, D=D)
 
-    def to_device(self, X_host, stage):
+    def to_device(self, X_host, stage, stream=None):
+        """Asynchronous host-to-device copy of (page-locked) rows into ``stage`` on ``stream`` (default: current)."""
         src = X_host if self.torch.is_tensor(X_host) else self.torch.from_numpy(X_host)
         out = stage[:src.shape[0]]
-        out.copy_(src, non_blocking=True)
+        if stream is None:
+            out.copy_(src, non_blocking=True)
+        else:
+            with self.torch.cuda.stream(stream):
+                out.copy_(src, non_blocking=True)
         return out
 
     def store_tile_rows_host(self, blocks, rows, N, D_host):

@@ -715,6 +715,25 @@ def test_cli_end_to_end(data_dir, golden_dir, tmp_path):
         compute_fununifrac.main(["-e", edge, "-fd", str(tmp_path), "-o", out])     # no matching files
 
 
+def test_integration_stub_runs(toy, full_tree):
+    """INTEGRATION.md section B shows the ctypes binding a maintainer of the reference would add.  This test executes that
+    very code block (library name replaced by the built library's path) on the toy tree and on the full synthetic tree,
+    for both modes, against the oracle."""
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(repo, "INTEGRATION.md")).read()
+    code = text.split("```python\n# src/algorithms/emd_unifrac_b200.py", 1)[1].split("```", 1)[0]
+    code = code.replace('ctypes.CDLL("libfununifrac.so")', f"ctypes.CDLL({engine.LIB_PATH!r})")
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    inp_toy, _, z = toy
+    inp_full, ctx, leaves = full_tree
+    for inp, X in ((inp_toy, z["l1_median.X"]), (inp_full, synth.synth_profiles_dense(leaves, ctx.n, 300, seed=23))):
+        for l2 in (False, True):
+            D = ns["all_pairs"](inp, list(X), l2)
+            ref = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, X, l2), l2)
+            assert D.shape == ref.shape and rel_err(D, ref) < REL and np.array_equal(D, D.T)
+
+
 def test_combined_table_cli(data_dir, golden_dir, tmp_path):
     """Second caller of the path (reference fununifrac/compute_fununifrac_combined.py): one KO x sample table.
     Expected matrices come from the reference itself, including its L1-push-up-with---L2 quirk."""

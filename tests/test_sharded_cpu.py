@@ -97,7 +97,7 @@ class OracleOps:
     def new_stream(self):
         return None
 
-    def record_event(self):
+    def record_event(self, stream=None):
         return None
 
     def stream_wait(self, stream, event):
@@ -256,8 +256,8 @@ class OracleOps:
         return D
 
     # host-buffer variant (step_host)
-    def to_device(self, X_host, stage):
-        src = X_host if torch.is_tensor(X_host) else torch.from_numpy(X_host)
+    def to_device(self, X_host, stage, stream=None):
+        src = X_host if torch.is_tensor(X_host) else torch.from_numpy(np.ascontiguousarray(X_host))
         stage[:src.shape[0]].copy_(src)
         return stage[:src.shape[0]]
 
@@ -344,7 +344,7 @@ def _worker(rank, world, port, N, l2, out_path, peer):
 
 @pytest.mark.parametrize("world,N,l2,peer", [(2, 300, False, True), (3, 700, False, True), (4, 400, True, True),
                                              (3, 100, False, True), (2, 300, False, False), (2, 129, True, False),
-                                             (3, 900, True, True), (2, 520, True, True)])
+                                             (3, 900, True, True), (2, 520, True, True), (2, 2100, False, True)])
 def test_sharded_exchange_gloo(world, N, l2, peer, tmp_path, monkeypatch):
     """peer=True: the shard-pair form (NVLink pulls + in-place stores, here over shared memory); peer=False: the
     collective form (all-gather, tile rows, packed gather) the Gram path still uses."""
