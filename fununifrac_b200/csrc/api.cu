@@ -7,7 +7,9 @@
 // kernel runs band by band (see below), each band followed by the float64 refinement pass over the few pairs the
 // fp32 operands cannot certify (refine.cu) and by the device-to-host copy of the finished part of D on a
 // third stream.  (Letting the tile epilogues write D straight into pinned host memory was measured: the
-// kernel then stalls for exactly the PCIe time of the matrix, so the DMA engines do it instead.)
+// kernel then stalls for exactly the PCIe time of the matrix, so the DMA engines do it instead.)  --L2 from 512 samples
+// on is ONE launch of the tensor-core Gram kernel; it counts its finished tile rows in completion segments, and the
+// third stream, waiting on those counters, copies the finished rows and mirrored columns while the launch goes on.
 #include <algorithm>
 #include <cstdlib>
 
@@ -100,7 +102,6 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     std::vector<int64_t> band_tile(nb + 1);
     for (int b = 0; b <= nb; b++) band_tile[b] = tiles_per_dim * b / nb;
 
-    bool gram_zero_copy = false;
     StreamDrain drain(ctx);
     FUF_CUDA(cudaEventRecord(e_start, sk));
     FUF_CUDA(cudaStreamWaitEvent(sc, e_start, 0));
@@ -134,22 +135,49 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
         if (use_gram) {
             // --L2 on the tensor cores: the Gram kernel needs every sample (node means), so no banding here
             double *qg = stat + ldp, *eg = qg + ldp;
-            // With a page-locked D_h the tile epilogues store every tile twice: into the device matrix (which the
-            // refinement scan reads) and straight into the caller's matrix.  20 GB at N = 50,000 cannot cross PCIe faster
-            // than the link allows whoever moves it; letting the kernel do it removes the separate device-to-host pass
-            // (the kernel then runs at the link's pace instead of the tensor pipe's: 0.37 s instead of 0.28 + 0.37 s).
-            double *D_zc = nullptr;
-            if (band_d2h && !getenv("FUF_GRAM_NO_ZEROCOPY")) FUF_CUDA(cudaHostGetDevicePointer((void **)&D_zc, D_h, 0));
-            rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, 0, 0, stat, qg, eg, nullptr, 0, D_dev, N, sk, D_zc, ldd);
+            // With a page-locked D_h the matrix leaves while it is being computed: the launch is cut into completion
+            // segments of whole tile rows (same item count each), the kernel counts the finished items of every segment,
+            // and the device-to-host stream waits on each counter in turn (cuStreamWaitValue32) before it copies the
+            // segment's rows right of the diagonal and its mirrored columns below it.  20 GB at N = 50,000 take 0.37 s
+            // over PCIe against 0.26 s of tensor-core work: the copies start ~10 ms into the launch instead of after it.
+            // (Storing the tiles into the mapped host matrix from the kernel was measured first: the epilogue warps then
+            // run at the link's pace — or far below it with narrow stores — and hold the tensor pipe back.)
+            GramSegments segs;
+            if (band_d2h && !getenv("FUF_GRAM_NO_SEGMENTS")) {
+                constexpr size_t max_seg = 4096;
+                if ((rc = ctx->ws_seg.reserve(max_seg * sizeof(uint32_t)))) return rc;
+                segs.seg_done = (uint32_t *)ctx->ws_seg.ptr;
+                segs.n_wanted = (int32_t)std::max<int64_t>(1, std::min<int64_t>(64, tiles_per_dim / 2));
+                if (getenv("FUF_GRAM_SEGMENTS")) segs.n_wanted = std::max(1, std::min(4000, atoi(getenv("FUF_GRAM_SEGMENTS"))));
+                // counters zeroed now; the copy stream may evaluate its waits from here on
+                FUF_CUDA(cudaMemsetAsync(segs.seg_done, 0, max_seg * sizeof(uint32_t), sk));
+                FUF_CUDA(cudaEventRecord(e_band[nb], sk));
+                FUF_CUDA(cudaStreamWaitEvent(sd, e_band[nb], 0));
+            }
+            rc = pairwise_gram(ctx, (const float *)ctx->ws_p.ptr, N, ldp, 0, 0, stat, qg, eg, nullptr, 0, D_dev, N, sk,
+                               segs.seg_done ? &segs : nullptr);
             if (rc) return rc;
-            gram_zero_copy = D_zc != nullptr;
+            int64_t R0 = 0;
+            for (size_t sg = 0; sg < segs.row_end.size(); sg++) {
+                const int64_t R1 = std::min<int64_t>(N, (int64_t)segs.row_end[sg] * 128);
+                if ((rc = stream_wait_u32(segs.seg_done + sg, segs.expected[sg], sd))) return rc;
+                FUF_CUDA(cudaMemcpy2DAsync(D_h + (size_t)R0 * ldd + R0, (size_t)ldd * sizeof(double), D_dev + (size_t)R0 * N + R0,
+                                           (size_t)N * sizeof(double), (size_t)(N - R0) * sizeof(double), (size_t)(R1 - R0),
+                                           cudaMemcpyDeviceToHost, sd));
+                if (R1 < N)
+                    FUF_CUDA(cudaMemcpy2DAsync(D_h + (size_t)R1 * ldd + R0, (size_t)ldd * sizeof(double),
+                                               D_dev + (size_t)R1 * N + R0, (size_t)N * sizeof(double),
+                                               (size_t)(R1 - R0) * sizeof(double), (size_t)(N - R1), cudaMemcpyDeviceToHost, sd));
+                R0 = R1;
+            }
+            const bool gram_segmented = !segs.row_end.empty();
             if (do_refine) {
                 // one counting scan, both criteria: rounding statistic of the operands, and D small against the Gram norms
                 rc = refine(ctx, nullptr, N, ldp, 0, 0, mode, eg, 0.0, nullptr, 0, D_dev, N, sk, 0, N, true,
                             FUF_CRIT_ROUNDING, qg, 2.9e-3, 0);
                 if (rc) return rc;
             }
-            if (band_d2h && !gram_zero_copy) {
+            if (band_d2h && !gram_segmented) {
                 FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
                                            (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
             }

@@ -150,6 +150,7 @@ struct fuf_ctx {
     fuf::DeviceBuffer ws_gram;     // int8 digit planes + tables of fuf_pairwise_gram
     fuf::DeviceBuffer ws_gram_small;  // column maxima
     fuf::DeviceBuffer ws_gram_tab;    // plan tables of a sharded Gram job
+    fuf::DeviceBuffer ws_seg;         // completion counters of the Gram launch of fuf_all_pairs_host
     fuf::GramJob gram_job;
     fuf::DeviceBuffer ws_p64;      // centre + error statistics (fuf_all_pairs_host)
     fuf::DeviceBuffer ws_p64t;     // float64 pushed profiles, only when a pair has to be refined (fuf_all_pairs_host)
@@ -190,6 +191,8 @@ struct PairTileList {
     double kappa = 0.0;
     long long *flag_list = nullptr;        // device: [0] = count, then (i, j) pairs
     long long list_cap = 0;
+    const int32_t *seg_h = nullptr;        // segment of every tile (or -1), n_tiles entries
+    uint32_t *seg_done = nullptr;          // device: completion counters, one per segment (+1 per finished tile)
 };
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
@@ -205,10 +208,20 @@ int assemble_packed(fuf_ctx *ctx, const double *packed, const int32_t *tile_rows
                     int32_t n_blocks, int64_t N, double *D, int64_t ldd, cudaStream_t stream);
 int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_h, int32_t n_blocks, int64_t N,
                          int64_t ldb, double *D_h, int64_t ldd, cudaStream_t stream);
+// tree.cu
+int stream_wait_u32(const uint32_t *dptr, uint32_t value, cudaStream_t stream);
 // gram.cu
+// Completion segments of a full-matrix Gram launch: in — device counters and the number of segments wanted; out — the
+// tile-row boundary of every segment and the counter value that says it is complete (empty: no segments were made).
+struct GramSegments {
+    uint32_t *seg_done = nullptr;
+    int32_t n_wanted = 0;
+    std::vector<int32_t> row_end;
+    std::vector<uint32_t> expected;
+};
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
                   const double *err_in, double *q, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
-                  double *D, int64_t ldd, cudaStream_t stream, double *D2 = nullptr, int64_t ldd2 = 0);
+                  double *D, int64_t ldd, cudaStream_t stream, GramSegments *segs = nullptr);
 // refine.cu
 int refine(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride, int mode,
            const double *err_stat, double kappa, const int32_t *tile_rows_h, int32_t n_tile_rows, double *D,

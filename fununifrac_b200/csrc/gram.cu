@@ -109,8 +109,6 @@ struct Params {
     int32_t n_direct;    // node columns kept out of the integer Gram (largest scales): added here in float64
     const double *SUB;   // their values, [n_direct][samples] in layout `sub`
     Lay sub;
-    double *D2;          // optional second destination with the same indexing (the caller's page-locked host matrix)
-    int64_t ldd2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -413,10 +411,6 @@ gram_tile_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
                         const double v = (gi == gj) ? 0.0 : (qi + p.q[gj]) - 2.0 * acc[e];
                         drow[e] = v;
                         if (mirror) p.D[gj * p.ldd + gi] = v;    // lanes = consecutive gi: one 256-byte store per warp
-                        if (p.D2) {
-                            p.D2[((int64_t)tl.out_row0 + row) * p.ldd2 + gj] = v;
-                            if (mirror) p.D2[gj * p.ldd2 + gi] = v;
-                        }
                     }
                 }
             }
@@ -453,8 +447,10 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                              // shar
 
 struct PairTile {
     int32_t ti, b;       // row tile, column-tile pair (2b, 2b + 1)
-    int32_t out_row0, pad;
+    int32_t out_row0, pad;   // pad: bits 0-11 dependency + 1 (0 = none), bits 12-31 segment + 1 (0 = none)
 };
+constexpr uint32_t GRAM_SEG_UNITS = 2 * NEPI_WARPS;   // a finished item advances its segment counter by this much
+static_assert(GRAM_SEG_UNITS == FUF_GRAM_SEG_UNITS, "include/fununifrac.h documents the count per item");
 
 struct Params2 {
     const PairTile *tiles;
@@ -469,8 +465,6 @@ struct Params2 {
     int32_t mirror, n_direct;
     const double *SUB;
     Lay sub;
-    double *D2;          // optional second destination (page-locked host matrix), same indexing
-    int64_t ldd2;
     // sharded jobs (fuf_gram_tiles): digit planes of peer shards arrive while the kernel runs; refinement flags are
     // evaluated where the distances are produced
     const uint32_t *dep_flags;   // PairTile::pad = dependency + 1: wait until dep_flags[dependency] reaches `epoch`
@@ -480,6 +474,10 @@ struct Params2 {
     double kappa_r, kappa_l;
     long long *flag_list;        // [0] = count, then (i, j) pairs; nullptr: no flagging
     long long list_cap;
+    // completion counters (one per segment of the item list): every epilogue warp of the pair adds 1 once its part of the
+    // item is stored and fenced, so a copy engine waiting on the counter (fuf_stream_wait_u32) can move the finished part
+    // of D to the host while the kernel works on the next segment
+    uint32_t *seg_done;
 };
 
 __device__ __forceinline__ void gram_wait_shard(const uint32_t *flag, uint32_t epoch)
@@ -575,7 +573,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 uint32_t it = 0;
                 for (int t = pair; t < p.n_tiles; t += n_pairs) {
                     const PairTile tl = p.tiles[t];
-                    if (tl.pad) gram_wait_shard(p.dep_flags + (tl.pad - 1), p.epoch);   // a peer's shard still in flight
+                    if (tl.pad & 0xfff) gram_wait_shard(p.dep_flags + ((tl.pad & 0xfff) - 1), p.epoch);   // a peer's shard still in flight
                     const int sa = (2 * tl.b + (int)rank) * TILE;          // first sample of this CTA's column tile
                     const int sb = tl.ti * TILE + 64 * (int)rank;          // its half of the row tile
                     const int ia = sa % p.S, ga = sa / p.S, ib = sb % p.S, gb = sb / p.S;
@@ -677,10 +675,10 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 }
             }
             const int tj = 2 * tl.b + (int)rank;
-            if (tj < tl.ti || tj >= p.tiles_per_dim) continue;   // the lower-triangle / out-of-range half of a pair
+            const bool live = tj >= tl.ti && tj < p.tiles_per_dim;   // else: the lower-triangle / out-of-range half of a pair
             const int64_t gj = (int64_t)tj * TILE + quarter * 32 + lane, gi0 = (int64_t)tl.ti * TILE + half * 64;
             const bool mirror = p.mirror != 0 && tl.ti != tj;
-            if (p.n_direct > 0 && gj < p.N) {
+            if (live && p.n_direct > 0 && gj < p.N) {
                 for (int32_t k = 0; k < p.n_direct; k++) {
                     const double aj = p.SUB[p.sub.at(k, gj)];
                     const double *bi = p.SUB + p.sub.at(k, gi0);
@@ -691,7 +689,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                     }
                 }
             }
-            if (gj < p.N) {
+            if (live && gj < p.N) {
                 const double qj = p.q[gj];
                 const double rej = p.flag_list ? sqrt(p.err[gj]) : 0.0, hj = p.flag_list ? p.h2[gj] : 0.0;
                 double *dcol = p.D + ((int64_t)tl.out_row0 + half * 64) * p.ldd + gj;   // walks down the rows
@@ -701,6 +699,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                     const int64_t gi = gi0 + e;
                     if (gi < p.N) {
                         const double v = (gi == gj) ? 0.0 : (p.q[gi] + qj) - 2.0 * acc[e];
+                        acc[e] = v;
                         if (p.flag_list && gi < gj) {
                             // the two criteria of the Gram refinement (refine.cu): rounding of the operands, and the
                             // dropped digit-product orders measured by the scale statistic
@@ -716,13 +715,29 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                             }
                         }
                         dcol[(int64_t)e * p.ldd] = v;         // lanes = consecutive gj: one 256-byte store per warp
-                        if (mirror) mrow[e] = v;
-                        if (p.D2) {
-                            p.D2[((int64_t)tl.out_row0 + half * 64 + e) * p.ldd2 + gj] = v;
-                            if (mirror) p.D2[gj * p.ldd2 + gi] = v;
-                        }
                     }
                 }
+                if (mirror) {
+                    // the transposed tile: every lane owns 64 consecutive entries of row gj.  32-byte stores (one full
+                    // sector each) when the row segment is aligned — the matrix may live on a peer GPU, where partial
+                    // sectors cost NVLink packets
+                    if ((((uintptr_t)mrow) & 31) == 0 && gi0 + 64 <= p.N) {
+#pragma unroll
+                        for (int e = 0; e < 64; e += 4)
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(mrow + e), "d"(acc[e]), "d"(acc[e + 1]),
+                                         "d"(acc[e + 2]), "d"(acc[e + 3])
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 64; e++)
+                            if (gi0 + e < p.N) mrow[e] = acc[e];
+                    }
+                }
+            }
+            if (p.seg_done && (tl.pad >> 12)) {
+                __threadfence();      // every lane's stores, then the warp's one count
+                __syncwarp();
+                if (lane == 0) atomicAdd(p.seg_done + ((tl.pad >> 12) - 1), 1u);
             }
         }
     }
@@ -1176,9 +1191,10 @@ static int gram_make_plan(fuf_ctx *ctx, const std::vector<float> &cstat, int32_t
 
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
                   const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
-                  double *D, int64_t ldd, cudaStream_t stream, double *D_second, int64_t ldd_second)
+                  double *D, int64_t ldd, cudaStream_t stream, GramSegments *segs)
 {
     using namespace gram;
+    if (segs) segs->row_end.clear(), segs->expected.clear();
     if (N == 0) return FUF_OK;
     const int32_t n = ctx->n;
     const int64_t tiles_per_dim = (N + TILE - 1) / TILE;
@@ -1299,8 +1315,6 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     p.n_direct = n_direct;
     p.SUB = SUB;
     p.sub = sub;
-    p.D2 = D_second;
-    p.ldd2 = ldd_second;
     if (!ctx->ev_gram[0]) {
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[0]));
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
@@ -1313,6 +1327,23 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         for (int32_t c = 0; c < n_trows; c++) {
             const int32_t t = full ? c : tile_rows_h[c];
             for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, full ? t * TILE : c * TILE, 0});
+        }
+        if (segs && segs->seg_done && segs->n_wanted > 0 && full) {
+            // segments of whole tile rows with about the same number of items each: the caller's copy engine moves the
+            // rows (and mirrored columns) of a finished segment to the host while the later ones are computed
+            const int32_t n_seg = (int32_t)std::min<int64_t>(std::min(segs->n_wanted, 4000), n_trows);
+            const size_t per = (ptiles.size() + n_seg - 1) / n_seg;
+            size_t at = 0;
+            uint32_t in_seg = 0;
+            for (int32_t t = 0; t < n_trows; t++) {
+                const int32_t seg = (int32_t)segs->row_end.size();
+                for (; at < ptiles.size() && ptiles[at].ti == t; at++, in_seg++) ptiles[at].pad = (seg + 1) << 12;
+                if (in_seg >= per || t == n_trows - 1) {
+                    segs->row_end.push_back(t + 1);
+                    segs->expected.push_back(in_seg * GRAM_SEG_UNITS);
+                    in_seg = 0;
+                }
+            }
         }
         static_assert(PLANE_BYTES == 8192 && TILE == 128, "umma_block10 hard-codes the plane and accumulator strides");
         static_assert(KC == 2 * KB, "the issue loops are written for two 32-row MMA blocks per stage");
@@ -1339,14 +1370,13 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
         p2.n_direct = n_direct;
         p2.SUB = SUB;
         p2.sub = sub;
-        p2.D2 = D_second;
-        p2.ldd2 = ldd_second;
         p2.dep_flags = nullptr;
         p2.epoch = 0;
         p2.err = p2.h2 = nullptr;
         p2.kappa_r = p2.kappa_l = 0.0;
         p2.flag_list = nullptr;
         p2.list_cap = 0;
+        p2.seg_done = (segs && !segs->row_end.empty()) ? segs->seg_done : nullptr;
         FUF_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
         const int n_pairs = (int)std::min<int64_t>(p2.n_tiles, ctx->sm_count / 2);
         FUF_CUDA(cudaEventRecord(ctx->ev_gram[0], stream));
@@ -1480,7 +1510,7 @@ extern "C" int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_
                               int64_t shard, const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch,
                               const double *q, const double *h2, const double *err, const double *SUB,
                               int64_t sub_shard_stride, double *D, int64_t ldd, int64_t *flag_list, int64_t list_cap,
-                              void *stream)
+                              const int32_t *seg_h, uint32_t *seg_done, void *stream)
 {
     using namespace gram;
     FUF_REQUIRE(ctx && planes && q && D && (tiles_h || n_tiles == 0), "fuf_gram_tiles: null argument");
@@ -1496,8 +1526,10 @@ extern "C" int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_
     for (int32_t c = 0; c < n_tiles; c++) {
         const int32_t ti = tiles_h[3 * c], b = tiles_h[3 * c + 1], dep = tiles_h[3 * c + 2];
         FUF_REQUIRE(ti >= 0 && ti < tiles_per_dim && b >= ti / 2 && 2 * b < tiles_per_dim, "fuf_gram_tiles: item (%d, %d) outside the upper triangle", ti, b);
-        FUF_REQUIRE(dep >= -1 && (dep < 0 || dep_flags), "fuf_gram_tiles: bad dependency %d", dep);
-        ptiles[c] = PairTile{ti, b, ti * TILE, dep + 1};
+        FUF_REQUIRE(dep >= -1 && dep < 4095 && (dep < 0 || dep_flags), "fuf_gram_tiles: bad dependency %d", dep);
+        const int32_t seg = (seg_h && seg_done) ? seg_h[c] : -1;
+        FUF_REQUIRE(seg >= -1 && seg < (1 << 19), "fuf_gram_tiles: bad segment %d", seg);
+        ptiles[c] = PairTile{ti, b, ti * TILE, (dep + 1) | ((seg + 1) << 12)};
     }
     PairTile *d_tiles = nullptr;
     int rc = ctx->tables.get_by_content("gtiles", ptiles.data(), ptiles.size() * sizeof(PairTile), (void **)&d_tiles);
@@ -1523,8 +1555,6 @@ extern "C" int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_
     p2.n_direct = job.n_direct;
     p2.SUB = SUB;
     p2.sub = Lay{shard, sub_shard_stride, shard};
-    p2.D2 = nullptr;
-    p2.ldd2 = 0;
     p2.dep_flags = dep_flags;
     p2.epoch = epoch;
     p2.err = err;
@@ -1533,6 +1563,7 @@ extern "C" int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_
     p2.kappa_l = 2.9e-3;
     p2.flag_list = (long long *)flag_list;
     p2.list_cap = list_cap;
+    p2.seg_done = (seg_h && seg_done) ? seg_done : nullptr;
     if (!ctx->ev_gram[0]) {
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[0]));
         FUF_CUDA(cudaEventCreate(&ctx->ev_gram[1]));
@@ -1626,5 +1657,5 @@ extern "C" int fuf_pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64
     FUF_REQUIRE(tile_rows_h != nullptr || n_tile_rows == 0, "fuf_pairwise_gram: n_tile_rows without tile_rows_h");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return pairwise_gram(ctx, PT, N, ldp, shard, shard_stride, err_in, h2, err_out, tile_rows_h, n_tile_rows, D, ldd,
-                         (cudaStream_t)stream, nullptr, 0);
+                         (cudaStream_t)stream, nullptr);
 }

@@ -38,9 +38,12 @@ constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC64_BYTES + 2 * STAGES 
 struct TileDesc {
     int32_t ti, tj;     // tile coordinates (tj >= ti)
     int32_t out_row0;   // first row of this tile row in the output buffer
-    int32_t mirror;     // bit 0: also write the transposed tile to (tj, ti); bits 8-31: dependency + 1 (0 = none): the
-                        // operands of this tile are complete once dep_flags[dependency] has reached the launch's epoch
+    int32_t mirror;     // bit 0: also write the transposed tile to (tj, ti); bits 8-19: dependency + 1 (0 = none): the
+                        // operands of this tile are complete once dep_flags[dependency] has reached the launch's epoch;
+                        // bits 20-31: segment + 1 (0 = none): seg_done[segment] is incremented once the tile is stored
 };
+__device__ __host__ __forceinline__ int tile_dep(int32_t m) { return (m >> 8) & 0xfff; }
+__device__ __host__ __forceinline__ int tile_seg(int32_t m) { return (m >> 20) & 0xfff; }
 
 struct PairParams {
     const TileDesc *tiles;
@@ -64,6 +67,9 @@ struct PairParams {
     double kappa;
     long long *flag_list;
     long long list_cap;
+    // completion counters: a copy engine waiting on seg_done[s] (fuf_stream_wait_u32) moves a finished part of D while the
+    // kernel is still working on the rest
+    uint32_t *seg_done;
 };
 
 // one pair against the refinement criterion of refine.cu (rounding statistics of the fp32 operands)
@@ -192,10 +198,10 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
                 const int s_begin = split * p.stages_per_split;
                 const int s_end = min(p.stages_total, s_begin + p.stages_per_split);
                 const int ia = td.ti * TILE, ib = td.tj * TILE;
-                if (td.mirror >> 8) {
+                if (tile_dep(td.mirror)) {
                     // this tile reads a shard that a copy engine is still bringing in from a peer GPU: wait for its
                     // flag (written in stream order behind the copy), then order the TMA reads behind the observation
-                    const uint32_t *flag = p.dep_flags + ((td.mirror >> 8) - 1);
+                    const uint32_t *flag = p.dep_flags + (tile_dep(td.mirror) - 1);
                     for (uint32_t spin = 0;; ++spin) {
                         uint32_t seen;
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
@@ -345,7 +351,10 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
                     }
             }
         }
+        const bool count_seg = p.seg_done && p.splits == 1 && tile_seg(td.mirror);
+        if (count_seg) __threadfence();   // this thread's part of the tile is visible before the counter moves
         consumer_bar();  // the next item re-zeroes the accumulators
+        if (count_seg && tid == 0) atomicAdd(p.seg_done + (tile_seg(td.mirror) - 1), 1u);
     }
 }
 
@@ -381,6 +390,11 @@ reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restr
             }
         }
         __syncthreads();
+    }
+    if (p.seg_done && tile_seg(td.mirror)) {   // (with k-splits the tile is finished here, not in the tile kernel)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(p.seg_done + (tile_seg(td.mirror) - 1), 1u);
     }
 }
 
@@ -558,7 +572,9 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
             const int32_t ti = list->tiles_h[3 * c], tj = list->tiles_h[3 * c + 1], dep = list->tiles_h[3 * c + 2];
             FUF_REQUIRE(ti >= 0 && ti <= tj && tj < tiles_per_dim, "fuf_pairwise_tiles: tile (%d, %d) outside the upper "
                         "triangle of %lld tile rows", ti, tj, (long long)tiles_per_dim);
-            FUF_REQUIRE(dep >= -1 && dep < (1 << 20) && (dep < 0 || list->dep_flags), "fuf_pairwise_tiles: bad dependency %d", dep);
+            FUF_REQUIRE(dep >= -1 && dep < 4095 && (dep < 0 || list->dep_flags), "fuf_pairwise_tiles: bad dependency %d", dep);
+            const int32_t seg = list->seg_h ? list->seg_h[c] : -1;
+            FUF_REQUIRE(seg >= -1 && seg < 4095 && (seg < 0 || list->seg_done), "fuf_pairwise_tiles: bad segment %d", seg);
         }
         n_tiles = list->n_tiles;
     } else if (band) {
@@ -578,6 +594,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     key_append(key, ce);
     key_append(key, n_rows);
     if (list) key.append((const char *)list->tiles_h, (size_t)n_tiles * 3 * sizeof(int32_t));
+    if (list && list->seg_h) key.append((const char *)list->seg_h, (size_t)n_tiles * sizeof(int32_t));
     else if (!full) key.append((const char *)tile_rows_h, (size_t)n_rows * sizeof(int32_t));
     TileDesc *d_tiles = (TileDesc *)ctx->tables.find(key);
     if (!d_tiles) {
@@ -586,18 +603,36 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
         if (list) {
             for (int32_t c = 0; c < n_tiles; c++) {
                 const int32_t ti = list->tiles_h[3 * c], tj = list->tiles_h[3 * c + 1], dep = list->tiles_h[3 * c + 2];
-                tiles.push_back(TileDesc{ti, tj, ti * TILE, (tj != ti ? 1 : 0) | ((dep + 1) << 8)});
+                const int32_t seg = list->seg_h ? list->seg_h[c] : -1;
+                tiles.push_back(TileDesc{ti, tj, ti * TILE, (tj != ti ? 1 : 0) | ((dep + 1) << 8) | ((seg + 1) << 20)});
             }
         } else if (band) {
             // column band [cb, ce) of the upper triangle (the host-buffer path computes the matrix band by band
-            // while later samples are still in flight over PCIe)
-            for (int32_t tj = cb; tj < ce; tj++)
-                for (int32_t t = 0; t <= tj; t++) tiles.push_back(TileDesc{t, tj, t * TILE, tj != t ? 1 : 0});
+            // while later samples are still in flight over PCIe), rasterised like the full matrix below: strips of
+            // about sm_count / width tile rows, so that one wave of CTAs reads ~width + sm_count / width panels
+            const int32_t width = ce - cb;
+            const int32_t S = std::max(1, (ctx->sm_count + width - 1) / width);
+            for (int32_t r0 = 0; r0 < ce; r0 += S)
+                for (int32_t tj = std::max(cb, r0); tj < ce; tj++)
+                    for (int32_t t = r0; t < std::min(r0 + S, tj + 1); t++)
+                        tiles.push_back(TileDesc{t, tj, t * TILE, tj != t ? 1 : 0});
+        } else if (full) {
+            // L2 rasterisation.  The CTAs of one wave (items w * grid .. (w + 1) * grid - 1, same cost each) stream their
+            // operand panels [n, 128] front to back at the same pace, so a panel shared by several tiles of the wave
+            // is fetched from DRAM once and found in L2 by the others.  Row-major order puts ~2 tile rows in a wave
+            // (grid / 2 + 2 distinct panels); strips of S = floor(sqrt(grid)) tile rows walked column by column make
+            // every window of `grid` consecutive tiles an S x S block: ~2 S panels (25 instead of 76 on 148 SMs).
+            int32_t S = 1;
+            while ((S + 1) * (S + 1) <= ctx->sm_count) S++;
+            for (int32_t r0 = 0; r0 < tiles_per_dim; r0 += S)
+                for (int32_t tj = r0; tj < tiles_per_dim; tj++)
+                    for (int32_t t = r0; t < std::min<int32_t>(r0 + S, tj + 1); t++)
+                        tiles.push_back(TileDesc{t, tj, t * TILE, tj != t ? 1 : 0});
         } else {
+            // compact row blocks of the listed tile rows (collective multi-GPU form): slot c of the output holds row t
             for (int32_t c = 0; c < n_rows; c++) {
-                const int32_t t = full ? c : tile_rows_h[c];
-                for (int32_t tj = t; tj < tiles_per_dim; tj++)
-                    tiles.push_back(TileDesc{t, tj, full ? t * TILE : c * TILE, (full && tj != t) ? 1 : 0});
+                const int32_t t = tile_rows_h[c];
+                for (int32_t tj = t; tj < tiles_per_dim; tj++) tiles.push_back(TileDesc{t, tj, c * TILE, 0});
             }
         }
         int rc = ctx->tables.put(key, tiles.data(), tiles.size() * sizeof(TileDesc), (void **)&d_tiles);
@@ -652,6 +687,7 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     p.flag_list = list ? list->flag_list : nullptr;
     p.list_cap = list ? list->list_cap : 0;
     if (!p.flag_list) p.stat = nullptr;
+    p.seg_done = list ? list->seg_done : nullptr;
 
     const bool packed = !(flags & FUF_PW_SCALAR_MATH);
     void (*kern)(const CUtensorMap, const PairParams) = nullptr;
@@ -929,7 +965,7 @@ extern "C" int fuf_pairwise(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ld
 extern "C" int fuf_pairwise_tiles(fuf_ctx *ctx, const float *PT, int64_t N, int64_t shard, int64_t shard_stride, int mode,
                                   const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch,
                                   double *D, int64_t ldd, const double *err_stat, double kappa, int64_t *flag_list,
-                                  int64_t list_cap, void *stream)
+                                  int64_t list_cap, const int32_t *seg_h, uint32_t *seg_done, void *stream)
 {
     FUF_REQUIRE(ctx && PT && D && (tiles_h || n_tiles == 0), "fuf_pairwise_tiles: null argument");
     FUF_REQUIRE(mode == FUF_MODE_L1 || mode == FUF_MODE_L2, "fuf_pairwise_tiles: bad mode %d", mode);
@@ -947,6 +983,8 @@ extern "C" int fuf_pairwise_tiles(fuf_ctx *ctx, const float *PT, int64_t N, int6
     list.kappa = kappa;
     list.flag_list = (long long *)flag_list;
     list.list_cap = list_cap;
+    list.seg_h = seg_done ? seg_h : nullptr;
+    list.seg_done = seg_h ? seg_done : nullptr;
     return pairwise_f32(ctx, PT, N, 0, shard, shard_stride, mode, nullptr, 0, D, ldd, 0, (cudaStream_t)stream, 0, 0, 0, 0,
                         &list);
 }

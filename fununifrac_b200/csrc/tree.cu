@@ -443,6 +443,7 @@ extern "C" int fuf_tree_destroy(fuf_ctx *ctx)
     ctx->ws_gram.release();
     ctx->ws_gram_small.release();
     ctx->ws_gram_tab.release();
+    ctx->ws_seg.release();
     ctx->ws_p64.release();
     ctx->ws_p64t.release();
     ctx->ws_push.release();
@@ -620,6 +621,53 @@ extern "C" int fuf_stream_write_u32(fuf_ctx *ctx, uint32_t *dptr, uint32_t value
         set_error("fuf_stream_write_u32: cuStreamWriteValue32 failed with CUresult %d", (int)r);
         return FUF_ECUDA;
     }
+    return FUF_OK;
+}
+
+// Stream-ordered wait until a 32-bit device word has reached a value (cuStreamWaitValue32, >=): the stream's later work
+// — e.g. the copy of a finished segment of D — starts once a running kernel has counted that far.
+namespace fuf {
+int stream_wait_u32(const uint32_t *dptr, uint32_t value, cudaStream_t stream)
+{
+    typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WaitFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            set_error("fuf_stream_wait_u32: cuStreamWaitValue32 is not available from this driver");
+            return FUF_ECUDA;
+        }
+        fn = (WaitFn)ptr;
+    }
+    CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)dptr, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) {
+        set_error("fuf_stream_wait_u32: cuStreamWaitValue32 failed with CUresult %d", (int)r);
+        return FUF_ECUDA;
+    }
+    return FUF_OK;
+}
+}  // namespace fuf
+
+extern "C" int fuf_stream_wait_u32(fuf_ctx *ctx, const uint32_t *dptr, uint32_t value, void *stream)
+{
+    FUF_REQUIRE(ctx && dptr, "fuf_stream_wait_u32: null argument");
+    FUF_REQUIRE(((uintptr_t)dptr & 3) == 0, "fuf_stream_wait_u32: unaligned address");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    return stream_wait_u32(dptr, value, (cudaStream_t)stream);
+}
+
+// Pitched copy (device, peer or page-locked host memory on either side) by a copy engine: `rows` rows of `width` bytes.
+extern "C" int fuf_copy2d_async(fuf_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width,
+                                size_t rows, void *stream)
+{
+    FUF_REQUIRE(ctx && dst && src, "fuf_copy2d_async: null argument");
+    FUF_REQUIRE(dst_pitch >= width && src_pitch >= width, "fuf_copy2d_async: pitch smaller than the row width");
+    FUF_CUDA(cudaSetDevice(ctx->device));
+    if (width && rows)
+        FUF_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDefault, (cudaStream_t)stream));
     return FUF_OK;
 }
 

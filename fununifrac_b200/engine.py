@@ -24,7 +24,8 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 11
+ABI_VERSION = 12
+GRAM_SEG_UNITS = 16     # fuf_gram_tiles: counts per finished item (FUF_GRAM_SEG_UNITS)
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
 _lib = None
@@ -76,12 +77,16 @@ def load_library() -> ctypes.CDLL:
         L.fuf_load_pushed.argtypes = [vp, vp, ci, i64, i64, vp, ci, i64, i64, vp]
         L.fuf_pairwise.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i32, vp, i64, ci, vp]
         u32 = ctypes.c_uint32
-        L.fuf_pairwise_tiles.argtypes = [vp, vp, i64, i64, i64, ci, vp, i32, vp, u32, vp, i64, vp, ctypes.c_double, vp, i64, vp]
+        L.fuf_pairwise_tiles.argtypes = [vp, vp, i64, i64, i64, ci, vp, i32, vp, u32, vp, i64, vp, ctypes.c_double, vp, i64, vp,
+                                         vp, vp]
         L.fuf_refine_list.argtypes = [vp, vp, i64, i64, i64, i64, ci, vp, i64, vp, i64, vp]
         L.fuf_gram_colstats.argtypes = [vp, vp, i64, i64, vp, vp]
         L.fuf_gram_plan.argtypes = [vp, vp, ctypes.POINTER(i32), ctypes.POINTER(i32), vp]
         L.fuf_gram_digits.argtypes = [vp, vp, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp]
-        L.fuf_gram_tiles.argtypes = [vp, vp, i64, i64, i64, i64, vp, i32, vp, u32, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp]
+        L.fuf_gram_tiles.argtypes = [vp, vp, i64, i64, i64, i64, vp, i32, vp, u32, vp, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
+                                     vp]
+        L.fuf_stream_wait_u32.argtypes = [vp, vp, u32, vp]
+        L.fuf_copy2d_async.argtypes = [vp, vp, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp]
         L.fuf_peer_alloc.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
         L.fuf_peer_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.fuf_peer_close.argtypes = [vp, vp]
@@ -115,7 +120,8 @@ def load_library() -> ctypes.CDLL:
                      "fuf_diffab_gather", "fuf_store_tile_rows_host", "fuf_pack_tile_rows", "fuf_assemble_packed",
                      "fuf_all_pairs_host", "fuf_last_timing", "fuf_pairwise_tiles", "fuf_refine_list", "fuf_peer_alloc",
                      "fuf_peer_open", "fuf_peer_close", "fuf_peer_free", "fuf_copy_async", "fuf_stream_write_u32",
-                     "fuf_host_device_pointer", "fuf_host_register", "fuf_host_unregister", "fuf_gram_colstats", "fuf_gram_plan", "fuf_gram_digits", "fuf_gram_tiles"):
+                     "fuf_host_device_pointer", "fuf_host_register", "fuf_host_unregister", "fuf_gram_colstats", "fuf_gram_plan",
+                     "fuf_gram_digits", "fuf_gram_tiles", "fuf_stream_wait_u32", "fuf_copy2d_async"):
             getattr(L, name).restype = ci
         if L.fuf_version() != ABI_VERSION:
             raise FunUniFracError(f"{LIB_PATH} has ABI version {L.fuf_version()}, this package needs {ABI_VERSION}: "
@@ -482,10 +488,32 @@ class TreeContext:
         _check(self._lib.fuf_stream_write_u32(self.handle, flags.data_ptr() + 4 * index, value & 0xFFFFFFFF, st),
                "fuf_stream_write_u32")
 
+    def stream_wait_u32(self, words, index: int, value: int, stream=None):
+        """The stream's later work waits until words[index] >= value (``fuf_stream_wait_u32``)."""
+        torch = _torch()
+        assert words.dtype == torch.int32 and words.is_contiguous()
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _check(self._lib.fuf_stream_wait_u32(self.handle, words.data_ptr() + 4 * index, value & 0xFFFFFFFF, st),
+               "fuf_stream_wait_u32")
+
+    def copy_block_async(self, dst, dst_ld: int, src, rows: Tuple[int, int], cols: Tuple[int, int], stream=None):
+        """dst[r0:r1, c0:c1] = src[r0:r1, c0:c1] for float64 matrices by one pitched copy-engine transfer
+        (``fuf_copy2d_async``).  ``dst`` is a tensor or a raw (device-visible) pointer with row pitch ``dst_ld`` elements."""
+        torch = _torch()
+        (r0, r1), (c0, c1) = rows, cols
+        if r1 <= r0 or c1 <= c0:
+            return
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        dptr = dst if isinstance(dst, int) else dst.data_ptr()
+        off_d, off_s = (r0 * dst_ld + c0) * 8, (r0 * src.stride(0) + c0) * 8
+        _check(self._lib.fuf_copy2d_async(self.handle, dptr + off_d, dst_ld * 8, src.data_ptr() + off_s, src.stride(0) * 8,
+                                          (c1 - c0) * 8, r1 - r0, st), "fuf_copy2d_async")
+
     def pairwise_tiles(self, PS, N: int, mode: int, tiles, dep_flags, epoch: int, D, shard: int, shard_stride: int,
-                       err_stat=None, flag_list=None, list_cap: int = 0, kappa: float = 0.0):
+                       err_stat=None, flag_list=None, list_cap: int = 0, kappa: float = 0.0, segments=None, seg_done=None):
         """``fuf_pairwise_tiles``: tiles (ti, tj, dependency) of the upper triangle, written in place into the full
-        matrix D (local, peer or mapped host memory; a tensor or a raw pointer) with their mirror."""
+        matrix D (local, peer or mapped host memory; a tensor or a raw pointer) with their mirror.  ``segments`` (one
+        int per tile, -1 = none) + ``seg_done`` (int32 device counters): seg_done[s] += 1 per finished tile of segment s."""
         torch = _torch()
         if PS.dtype != torch.float32 or PS.stride(-1) != 1:
             raise TypeError("fuf_pairwise_tiles takes float32 operands [G, n, shard]")
@@ -495,7 +523,18 @@ class TreeContext:
                                             None if dep_flags is None else dep_flags.data_ptr(), epoch & 0xFFFFFFFF, dptr,
                                             ldd, None if err_stat is None else err_stat.data_ptr(), float(kappa),
                                             None if flag_list is None else flag_list.data_ptr(), int(list_cap),
-                                            _stream_ptr(torch)), "fuf_pairwise_tiles")
+                                            *self._segments(segments, seg_done, len(tl)), _stream_ptr(torch)),
+               "fuf_pairwise_tiles")
+
+    @staticmethod
+    def _segments(segments, seg_done, n_items):
+        if segments is None or seg_done is None:
+            return None, None
+        torch = _torch()
+        sg = np.ascontiguousarray(segments, dtype=np.int32)
+        assert sg.shape == (n_items,) and seg_done.dtype == torch.int32 and seg_done.is_contiguous()
+        assert int(sg.max(initial=-1)) < seg_done.numel()
+        return sg.ctypes.data_as(ctypes.c_void_p), seg_done.data_ptr()
 
     # the --L2 tensor-core path in phases (sharded jobs)
     def gram_colstats(self, PT_shard, n_valid: int, stats):
@@ -521,7 +560,10 @@ class TreeContext:
                                          err_out.data_ptr(), SUB.data_ptr(), SUB.stride(0), _stream_ptr(torch)),
                "fuf_gram_digits")
 
-    def gram_tiles(self, planes, N: int, tiles, dep_flags, epoch: int, q, h2, err, SUB, D, flag_list=None, list_cap: int = 0):
+    def gram_tiles(self, planes, N: int, tiles, dep_flags, epoch: int, q, h2, err, SUB, D, flag_list=None, list_cap: int = 0,
+                   segments=None, seg_done=None):
+        """``fuf_gram_tiles``; segments / seg_done as in ``pairwise_tiles``, except that a finished item advances its
+        counter by GRAM_SEG_UNITS (one count per epilogue warp of the CTA pair)."""
         torch = _torch()
         tl = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3)
         shard = int(planes.shape[3])
@@ -530,7 +572,8 @@ class TreeContext:
                                         tl.ctypes.data, len(tl), None if dep_flags is None else dep_flags.data_ptr(),
                                         epoch & 0xFFFFFFFF, q.data_ptr(), h2.data_ptr(), err.data_ptr(), SUB.data_ptr(),
                                         SUB.stride(0), dptr, ldd, None if flag_list is None else flag_list.data_ptr(),
-                                        int(list_cap), _stream_ptr(torch)), "fuf_gram_tiles")
+                                        int(list_cap), *self._segments(segments, seg_done, len(tl)), _stream_ptr(torch)),
+               "fuf_gram_tiles")
 
     def refine_list(self, P64T, N: int, mode: int, flag_list, list_cap: int, D, shard: int = 0, shard_stride: int = 0):
         """``fuf_refine_list``: the flagged pairs recomputed in float64 into D[i, j], D[j, i] (tensor or raw pointer)."""

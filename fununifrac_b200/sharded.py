@@ -33,6 +33,7 @@ from __future__ import annotations
 from typing import List, Optional, Sequence  # noqa: F401
 
 TILE = 128
+STRIP = 12        # tile rows per rasterisation strip: floor(sqrt(148 SMs))
 
 
 def shard_size(N: int, world: int, multiple: int = TILE) -> int:
@@ -47,17 +48,46 @@ def sample_range(N: int, world: int, rank: int, shard: Optional[int] = None):
     return min(N, rank * s), min(N, (rank + 1) * s)
 
 
-def gram_items(tiles):
+def gram_items(tiles, seg=None):
     """(ti, tj, dependency) tiles of ``peer_tile_plan`` -> work items (ti, b, dependency) of the CTA-pair Gram kernel: row
     tile ti against the column-tile pair (2b, 2b + 1), in the same order (shards are multiples of 256, so a pair never
-    straddles two shards)."""
-    items, seen = [], set()
-    for ti, tj, dep in tiles:
+    straddles two shards).  With ``seg`` (the completion segment of every tile) also the segment of every item."""
+    items, item_seg, seen = [], [], set()
+    for c, (ti, tj, dep) in enumerate(tiles):
         key = (ti, tj // 2)
         if key not in seen:
             seen.add(key)
             items.append((ti, tj // 2, dep))
-    return items
+            if seg is not None:
+                item_seg.append(seg[c])
+    return items if seg is None else (items, item_seg)
+
+
+def segment_regions(tiles, seg, N: int):
+    """Rectangles of the full matrix that a completion segment finishes, per segment: [(row0, row1, col0, col1), ...] in
+    samples.  A segment's tiles fill the upper-triangle part of their bounding box of tiles (checked); the kernel stores
+    every tile and its mirror, so the finished entries are the box itself and its transposed image — cut so that the
+    rectangles of one segment do not overlap (strips and column bands of a diagonal block meet the diagonal)."""
+    groups = {}
+    for (ti, tj, _), sg in zip(tiles, seg):
+        groups.setdefault(sg, []).append((ti, tj))
+    assert sorted(groups) == list(range(len(groups))), "segments are numbered 0 .. S-1"
+
+    def rect(a, b, c, d):
+        return (a * TILE, min(N, b * TILE), c * TILE, min(N, d * TILE))
+
+    out = []
+    for sg in range(len(groups)):
+        g = groups[sg]
+        ra, rb = min(t[0] for t in g), max(t[0] for t in g) + 1
+        ca, cb = min(t[1] for t in g), max(t[1] for t in g) + 1
+        want = sum(1 for ti in range(ra, rb) for tj in range(max(ca, ti), cb))
+        assert len(set(g)) == len(g) == want, f"segment {sg} does not fill its box of tiles"
+        regs = [rect(ra, rb, ca, cb),
+                rect(max(ca, ra), min(cb, rb), ra, min(rb, ca)),        # mirror rows inside the box's rows: left of it
+                rect(max(ca, rb), cb, ra, rb)]                          # mirror rows below the box
+        out.append([r for r in regs if r[1] > r[0] and r[3] > r[2]])
+    return out
 
 
 def tile_row_owner(t: int, world: int) -> int:
@@ -83,7 +113,7 @@ def packed_offsets(rows: Sequence[int], N: int):
     return offsets, total
 
 
-def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None):
+def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None, segments: bool = False):
     """Tiles of rank ``rank`` when the upper-triangular tile grid is dealt by shard pairs, in processing order, as
     (ti, tj, dependency) triples, plus the remote shards the rank pulls, in pull order.
 
@@ -91,6 +121,8 @@ def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None):
     blocks of shard pair {r, (r + d) mod G} for d = 1 .. G/2: a round-robin tournament, every unordered pair has exactly
     one owner, except that for even G the pairs at distance G/2 are split by tile rows between their two members.  Every
     rank gets the same number of tiles (up to the ragged last shard) and pulls only floor(G/2) of the G - 1 remote shards.
+    ``segments=True`` adds a third value: the completion segment of every tile — one per rasterisation strip, numbered in
+    processing order (``segment_regions`` gives the part of the matrix each one finishes).
     """
     shard = shard or shard_size(N, world)
     Ts, T = shard // TILE, (N + TILE - 1) // TILE
@@ -98,8 +130,22 @@ def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None):
     def tiles_of(A):
         return range(A * Ts, min((A + 1) * Ts, T))
 
-    own = tiles_of(rank)
-    tiles = [(ti, tj, -1) for ti in own for tj in range(ti, own.stop)]
+    seg = []
+
+    def strips(rows, cols, dep):
+        # L2 rasterisation (see pairwise_f32): strips of STRIP tile rows walked column by column, so that the ~148 tiles
+        # in flight at any time form a compact block sharing ~2 STRIP operand panels
+        out = []
+        for r0 in range(0, len(rows), STRIP):
+            band = rows[r0:r0 + STRIP]
+            part = [(ti, tj, dep) for tj in cols for ti in band if ti <= tj]
+            if part:
+                seg.extend([seg[-1] + 1 if seg else 0] * len(part))
+                out += part
+        return out
+
+    own = list(tiles_of(rank))
+    tiles = strips(own, own, -1)
     pulls = []
     for d in range(1, world // 2 + 1):
         q = (rank + d) % world
@@ -110,11 +156,11 @@ def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None):
         if 2 * d == world:                       # the pair at distance G/2 is shared: lower rank takes the first half
             half = (len(rows) + 1) // 2
             rows = rows[:half] if rank == A else rows[half:]
-        block = [(ti, tj, q) for ti in rows for tj in tiles_of(B)]
+        block = strips(rows, list(tiles_of(B)), q)
         if block:
             pulls.append(q)
             tiles += block
-    return tiles, pulls
+    return (tiles, pulls, seg) if segments else (tiles, pulls)
 
 
 def refine_budget(N: int) -> int:
@@ -277,7 +323,7 @@ class ShardedAllPairs:
     # ------------------------------------------------------------------------------------------------------
     def _init_peer(self):
         ops, N, world, rank, dist, sh, n = self.ops, self.N, self.world, self.rank, self.dist, self.shard, self.ops.n
-        self.tiles, self.pulls = peer_tile_plan(N, world, rank, sh)
+        self.tiles, self.pulls, self.seg = peer_tile_plan(N, world, rank, sh, segments=True)
         self.rows = self.tiles                    # (truthy iff this rank computes anything)
         # every rank's operand buffer [G, n, shard]: slot r is written by its own push-up and read by the peers' copy
         # engines; the other slots receive the pulled shards
@@ -286,7 +332,7 @@ class ShardedAllPairs:
         if self.use_gram:
             # --L2 on the tensor cores: what crosses NVLink are the int8 digit planes (and the few float64 bypass rows)
             # of the shards this rank's tiles touch; the fp32 operands never leave their GPU
-            self.items = gram_items(self.tiles)
+            self.items, self.item_seg = gram_items(self.tiles, self.seg)
             self.rows_cap = (n + 4096 + 63) // 64 * 64            # plan rows: n + padding of the scale buckets
             self.sub_cap = 256                                    # float64 bypass rows (GRAM_DIRECT_ROWS)
             self.PT_own = ops.empty((n, sh), "float32")
@@ -316,21 +362,67 @@ class ShardedAllPairs:
         self.flag_list = ops.empty((1 + 2 * self.list_cap,), "int64")     # [0] = count, then (i, j) pairs
         self.flagged = ops.empty((1,), "int64")
         self.copy_stream = ops.new_stream()
+        self.d2h_stream = ops.new_stream()
         self.last_flagged = 0
         self._x_stage = self._pending = self._x_local = None
-        # host-buffer form: the own shard is uploaded in up to 4 bands of whole tiles; band b carries the diagonal-block
-        # tiles whose column tile lies in it (their rows lie in bands <= b)
+        # A rank whose result matrix lives elsewhere (rank 0's GPU for ranks > 0, the shared host matrix for everybody)
+        # computes into a matrix of its own, D_local, and a copy engine moves every finished completion segment to its
+        # place while the tile kernel works on the next one: the kernel never stores across NVLink or PCIe.
+        self.D_local = None
+        units = self.ops.gram_seg_units if self.use_gram else 1
+        work, work_seg = (self.items, self.item_seg) if self.use_gram else (self.tiles, self.seg)
+        self.plan = _SegmentPlan(work, work_seg, segment_regions(self.tiles, self.seg, N), units)
+        # host-buffer form (weighted L1): the own shard is uploaded in up to 4 bands of whole tiles; band b carries the
+        # diagonal-block tiles whose column tile lies in it (their rows lie in bands <= b) as ONE segment, so the
+        # finished part of the diagonal block leaves for the host while the next band is still coming in
         own_tiles = [t for t in self.tiles if t[2] < 0]
         self.offdiag_tiles = [t for t in self.tiles if t[2] >= 0]
         Ts_own = (self.hi - self.lo + TILE - 1) // TILE
-        self.diag_bands = []
-        if Ts_own >= 8:
+        self.diag_bands, self.plan_banded = [], None
+        if Ts_own >= 8 and not self.use_gram:
             t0 = rank * (sh // TILE)
+            tiles_b, seg_b = [], []
             for b in range(4):
                 lo_t, hi_t = t0 + Ts_own * b // 4, t0 + Ts_own * (b + 1) // 4
                 s0, s1 = (lo_t - t0) * TILE, min(self.hi - self.lo, (hi_t - t0) * TILE)
-                self.diag_bands.append((s0, s1, [t for t in own_tiles if lo_t <= t[1] < hi_t]))
+                band = [t for t in own_tiles if lo_t <= t[1] < hi_t]
+                self.diag_bands.append((s0, s1, len(tiles_b), len(tiles_b) + len(band)))
+                tiles_b += band
+                seg_b += [b] * len(band)
+            first_off = min([sg for t, sg in zip(self.tiles, self.seg) if t[2] >= 0], default=0)
+            self.offdiag_from = len(tiles_b)
+            tiles_b += self.offdiag_tiles
+            seg_b += [4 + sg - first_off for t, sg in zip(self.tiles, self.seg) if t[2] >= 0]
+            self.plan_banded = _SegmentPlan(tiles_b, seg_b, segment_regions(tiles_b, seg_b, N), 1)
+        self.seg_done = ops.empty((max(1, self.plan.n_seg, self.plan_banded.n_seg if self.plan_banded else 0),), "int32")
         dist.barrier()
+
+    def _local_matrix(self, target):
+        """Where the tile kernels store: the target itself when it is this device's memory (rank 0 of ``step``), else the
+        rank's own matrix, from which the copy engine forwards the finished segments."""
+        if target is self.D:
+            return target
+        if self.D_local is None:
+            self.D_local = self.ops.empty((self.N, self.N), "float64")
+        return self.D_local
+
+    def _forward_segments(self, plan, D_comp, target, first_seg=0, last_seg=None):
+        """Queue, on the device-to-host stream, for every completion segment: wait for its counter, then one pitched copy
+        per finished rectangle from the rank's matrix to the target (peer GPU or page-locked host memory)."""
+        ops = self.ops
+        for sg in range(first_seg, plan.n_seg if last_seg is None else last_seg):
+            ops.stream_wait_u32(self.seg_done, sg, plan.expected[sg], self.d2h_stream)
+            for r0, r1, c0, c1 in plan.regions[sg]:
+                ops.copy_block(target, D_comp, (r0, r1), (c0, c1), self.d2h_stream)
+
+    def _begin_segments(self):
+        """Counters to zero in compute-stream order; the copy stream may look at them from here on."""
+        self.ops.zero_(self.seg_done)
+        self.ops.stream_wait(self.d2h_stream, self.ops.record_event())
+
+    def _end_segments(self):
+        """The compute stream (and with it the end-of-step all-reduce) waits for the last forwarded segment."""
+        self.ops.stream_wait(None, self.ops.record_event(self.d2h_stream))
 
     def _compute_peer_gram(self, X_local, D_target, mark):
         """The peer form of the --L2 tensor-core path: push-up and column statistics of the own shard, all-reduce of the
@@ -362,6 +454,10 @@ class ShardedAllPairs:
         dist.all_gather_into_tensor(self.gh2, self.gh2[own])
         dist.all_gather_into_tensor(self.gerr, self.gerr[own])
         ops.zero_(self.flag_list[:1])
+        D_comp = self._local_matrix(D_target)
+        forward = D_comp is not D_target
+        if forward:
+            self._begin_segments()
         ready = ops.record_event()
         ops.stream_wait(self.copy_stream, ready)
         for q in self.pulls:
@@ -371,8 +467,12 @@ class ShardedAllPairs:
             ops.stream_write_u32(self.flags, q, self.epoch, self.copy_stream)
         mark("pair_begin")
         if self.items:
-            ops.gram_tiles(self.planes, N, self.items, self.flags, self.epoch, self.gq, self.gh2, self.gerr, self.SUB, D_target,
-                           self.flag_list if self.do_refine else None, self.list_cap)
+            ops.gram_tiles(self.planes, N, self.items, self.flags, self.epoch, self.gq, self.gh2, self.gerr, self.SUB, D_comp,
+                           self.flag_list if self.do_refine else None, self.list_cap,
+                           self.plan.seg if forward else None, self.seg_done if forward else None)
+            if forward:
+                self._forward_segments(self.plan, D_comp, D_target)
+                self._end_segments()
         mark("pair_end")
         self.flagged.copy_(self.flag_list[:1])
         dist.all_reduce(self.flagged)
@@ -398,8 +498,15 @@ class ShardedAllPairs:
         flist = self.flag_list if self.do_refine else None
         rows_own = self.hi - self.lo
         ops.zero_(self.flag_list[:1])
+        D_comp = self._local_matrix(D_target)
+        forward = D_comp is not D_target
+        banded = not (host_src is None or rows_own == 0 or not self.diag_bands)
+        plan = self.plan_banded if banded else self.plan
+        seg_done = self.seg_done if forward else None
+        if forward:
+            self._begin_segments()
         mark("start")
-        if host_src is None or rows_own == 0 or not self.diag_bands:
+        if not banded:
             if host_src is not None:
                 ops.to_device(host_src, X_local)
             if r == 0:
@@ -409,10 +516,10 @@ class ShardedAllPairs:
             if rows_own:
                 ops.push_up(X_local, mode, self.PS[r], 0, self.center, None, self.stat[own])
             mark("push_end")
-            rest = self.tiles
+            rest, rest_seg, seg_from = plan.work, plan.seg, 0
         else:
             events = []
-            for s0, s1, _ in self.diag_bands:        # all uploads are queued up front on the copy stream
+            for s0, s1, _, _ in self.diag_bands:        # all uploads are queued up front on the copy stream
                 ops.to_device(host_src[s0:s1], X_local[s0:s1], self.copy_stream)
                 events.append(ops.record_event(self.copy_stream))
             ops.stream_wait(None, events[0])
@@ -420,14 +527,16 @@ class ShardedAllPairs:
                 ops.push_up_center(X_local[:self.diag_bands[0][1]], mode, self.center)
             dist.broadcast(self.center, src=0)
             mark("push_begin")
-            for (s0, s1, band_tiles), ev in zip(self.diag_bands, events):
+            for b, ((s0, s1, t0, t1), ev) in enumerate(zip(self.diag_bands, events)):
                 ops.stream_wait(None, ev)
                 ops.push_up(X_local[s0:s1], mode, self.PS[r], s0, self.center, None, self.stat[own])
-                if band_tiles:
-                    ops.pairwise_tiles(self.PS, N, mode, band_tiles, self.flags, self.epoch, D_target, sh, n * sh, stat,
-                                       flist, self.list_cap)
+                if t1 > t0:
+                    ops.pairwise_tiles(self.PS, N, mode, plan.slice(t0, t1), self.flags, self.epoch, D_comp, sh, n * sh, stat,
+                                       flist, self.list_cap, plan.seg_slice(t0, t1) if forward else None, seg_done)
+                    if forward:
+                        self._forward_segments(plan, D_comp, D_target, b, b + 1)
             mark("push_end")
-            rest = self.offdiag_tiles
+            rest, rest_seg, seg_from = plan.slice(self.offdiag_from, None), plan.seg_slice(self.offdiag_from, None), 4
         self._x_local = X_local
         # the statistics of all samples (the epilogue criterion needs both members of a pair); every rank contributes
         # after its push-up, so its arrival also says: all shards are ready to be pulled
@@ -439,8 +548,11 @@ class ShardedAllPairs:
             ops.stream_write_u32(self.flags, q, self.epoch, self.copy_stream)
         mark("pair_begin")
         if rest:
-            ops.pairwise_tiles(self.PS, N, mode, rest, self.flags, self.epoch, D_target, sh, n * sh, stat, flist,
-                               self.list_cap)
+            ops.pairwise_tiles(self.PS, N, mode, rest, self.flags, self.epoch, D_comp, sh, n * sh, stat, flist,
+                               self.list_cap, rest_seg if forward else None, seg_done)
+        if forward:
+            self._forward_segments(plan, D_comp, D_target, seg_from)
+            self._end_segments()
         mark("pair_end")
         # the next step's pulls and push-up must not start before everybody is done with this step's: the all-reduce of
         # the flagged-pair count is that barrier (and tells every rank whether the float64 pass is needed)
@@ -522,8 +634,9 @@ class ShardedAllPairs:
         if self._x_stage is None:
             self._x_stage = self.ops.profile_matrix(max(self.hi - self.lo, 1))
         if self.use_peer:
-            # the tiles (and their mirror) are stored by the kernel itself into the page-locked host matrix the ranks
-            # share: the device-to-host traffic of all ranks runs over their own PCIe links, under the computation
+            # every finished completion segment of the rank's tiles (and their mirror) is copied by a DMA engine into the
+            # page-locked host matrix the ranks share: the device-to-host traffic of all ranks runs over their own
+            # PCIe links, under the computation
             target = self.ops.host_target(D_host)
             self._compute_peer(self._x_stage[:self.hi - self.lo], target, mark, host_src=X_local_host)
             self._refine_peer(target)
@@ -547,6 +660,31 @@ class ShardedAllPairs:
             self.dist.barrier()
         mark("end")
         return D_host.array
+
+
+class _SegmentPlan:
+    """Work list of a rank (tiles, or Gram items) with the completion segment of every entry, the rectangles each segment
+    finishes and the counter value that says so.  Slices are cached so that the ops layer converts each list once."""
+
+    def __init__(self, work, seg, regions, units: int = 1):
+        self.work, self.seg, self.regions = work, seg, regions
+        self.n_seg = len(regions)
+        self.expected = [0] * self.n_seg
+        for sg in seg:
+            self.expected[sg] += units
+        self._slices = {}
+
+    def slice(self, a, b):
+        key = ("w", a, b)
+        if key not in self._slices:
+            self._slices[key] = self.work[a:b]
+        return self._slices[key]
+
+    def seg_slice(self, a, b):
+        key = ("s", a, b)
+        if key not in self._slices:
+            self._slices[key] = self.seg[a:b]
+        return self._slices[key]
 
 
 class SharedHostMatrix:
@@ -682,13 +820,31 @@ class CudaOps:
     def stream_write_u32(self, flags, index, value, stream):
         self.ctx.stream_write_u32(flags, index, value, stream)
 
-    def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap):
-        cache = self.__dict__.setdefault("_tiles_np", {})
-        arr = cache.get(id(tiles))
-        if arr is None or arr[0] is not tiles:             # the plans are fixed for the job: convert each list once
+    gram_seg_units = 16          # engine.GRAM_SEG_UNITS: counts per finished item of fuf_gram_tiles
+
+    def _as_np(self, lst, width):
+        """The plans are fixed for the job: every list is converted to a numpy array once."""
+        cache = self.__dict__.setdefault("_lists_np", {})
+        arr = cache.get(id(lst))
+        if arr is None or arr[0] is not lst:
             import numpy as np
-            arr = cache[id(tiles)] = (tiles, np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3))
-        self.ctx.pairwise_tiles(PS, N, mode, arr[1], flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap)
+            a = np.ascontiguousarray(lst, dtype=np.int32)
+            arr = cache[id(lst)] = (lst, a.reshape(-1, width) if width > 1 else a.reshape(-1))
+        return arr[1]
+
+    def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap,
+                       seg=None, seg_done=None):
+        self.ctx.pairwise_tiles(PS, N, mode, self._as_np(tiles, 3), flags, epoch, D, shard, shard_stride, stat, flag_list,
+                                list_cap, segments=None if seg is None else self._as_np(seg, 1), seg_done=seg_done)
+
+    def stream_wait_u32(self, words, index, value, stream):
+        self.ctx.stream_wait_u32(words, index, value, stream)
+
+    def copy_block(self, target, src, rows, cols, stream):
+        """target[rows, cols] = src[rows, cols]; ``target`` is an N x N tensor (peer mapping) or the raw device-side pointer
+        of the shared host matrix (row pitch N)."""
+        ld = src.shape[1] if isinstance(target, int) else target.stride(0)
+        self.ctx.copy_block_async(target, ld, src, rows, cols, stream)
 
     def gram_colstats(self, PT_shard, n_valid, stats):
         self.ctx.gram_colstats(PT_shard, n_valid, stats)
@@ -699,12 +855,9 @@ class CudaOps:
     def gram_digits(self, PT_shard, n_valid, planes, shard_index, err_in, q, h2, err_out, SUB):
         self.ctx.gram_digits(PT_shard, n_valid, planes, shard_index, err_in, q, h2, err_out, SUB)
 
-    def gram_tiles(self, planes, N, items, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap):
-        key = id(items)
-        if getattr(self, "_items_key", None) != key:
-            import numpy as np
-            self._items_np, self._items_key = np.ascontiguousarray(items, dtype=np.int32).reshape(-1, 3), key
-        self.ctx.gram_tiles(planes, N, self._items_np, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap)
+    def gram_tiles(self, planes, N, items, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap, seg=None, seg_done=None):
+        self.ctx.gram_tiles(planes, N, self._as_np(items, 3), flags, epoch, q, h2, err, SUB, D, flag_list, list_cap,
+                            segments=None if seg is None else self._as_np(seg, 1), seg_done=seg_done)
 
     def refine_list(self, P64S, N, mode, flag_list, list_cap, D, shard, shard_stride):
         self.ctx.refine_list(P64S, N, mode, flag_list, list_cap, D, shard, shard_stride)

@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 11
+#define FUF_ABI_VERSION 12
 
 /* error codes */
 #define FUF_OK 0
@@ -322,10 +322,15 @@ int fuf_ingest_gather_csv(const fuf_name_index *index, const char *const *paths,
  * (fuf_stream_write_u32 behind the copy).  List the tiles in the order their shards arrive.
  * err_stat + flag_list: the refinement criterion of fuf_refine is evaluated in the tile epilogues, where the distances
  * are produced: flag_list[0] counts the flagged pairs i < j, flag_list[1 + 2q], flag_list[2 + 2q] = (i, j) of the first
- * list_cap of them (zero flag_list[0] before the launch).  kappa <= 0: the defaults of fuf_refine. */
+ * list_cap of them (zero flag_list[0] before the launch).  kappa <= 0: the defaults of fuf_refine.
+ * seg_h + seg_done (both or neither): seg_h[c] >= 0 puts tile c into a completion segment; once the tile (and its
+ * mirror) is stored and fenced, the device counter seg_done[seg_h[c]] is incremented by 1 (zero the counters before the
+ * launch).  A copy stream that waits with fuf_stream_wait_u32 for a segment's tile count can move that part of D
+ * (fuf_copy2d_async) while the launch is still computing the rest. */
 int fuf_pairwise_tiles(fuf_ctx *ctx, const float *PT, int64_t N, int64_t shard, int64_t shard_stride, int mode,
                        const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch, double *D,
-                       int64_t ldd, const double *err_stat, double kappa, int64_t *flag_list, int64_t list_cap, void *stream);
+                       int64_t ldd, const double *err_stat, double kappa, int64_t *flag_list, int64_t list_cap,
+                       const int32_t *seg_h, uint32_t *seg_done, void *stream);
 /* The listed pairs recomputed in float64 from P64T (layouts as in fuf_refine) into D[i, j] and D[j, i] of the full matrix. */
 int fuf_refine_list(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, int64_t shard, int64_t shard_stride,
                     int mode, const int64_t *flag_list, int64_t list_cap, double *D, int64_t ldd, void *stream);
@@ -344,7 +349,10 @@ int fuf_refine_list(fuf_ctx *ctx, const double *P64T, int64_t N, int64_t ldp64, 
  *   fuf_gram_tiles:    the CTA-pair tile kernel on items (row tile ti, column-tile pair b = tiles 2b, 2b+1, dependency);
  *                      q / h2 / err / SUB / planes hold all shards the items touch.  Tiles are stored in place into
  *                      the full matrix D (and mirrored) as in fuf_pairwise_tiles, dependencies and the flag list work
- *                      the same way (criteria: D < 1.6e13 (sqrt err_i + sqrt err_j)^2 or D < 2.9e-3 (h2_i + h2_j)). */
+ *                      the same way (criteria: D < 1.6e13 (sqrt err_i + sqrt err_j)^2 or D < 2.9e-3 (h2_i + h2_j)).
+ *                      Completion segments as in fuf_pairwise_tiles, except that a finished item advances its counter
+ *                      by FUF_GRAM_SEG_UNITS (one count per epilogue warp of the CTA pair). */
+#define FUF_GRAM_SEG_UNITS 16
 int fuf_gram_colstats(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_t ld, float *stats, void *stream);
 int fuf_gram_plan(fuf_ctx *ctx, const float *stats, int32_t *n_rows, int32_t *n_direct_pad, void *stream);
 int fuf_gram_digits(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_t shard, int8_t *planes, int64_t plane_stride,
@@ -353,7 +361,7 @@ int fuf_gram_digits(fuf_ctx *ctx, const float *PT_shard, int64_t n_valid, int64_
 int fuf_gram_tiles(fuf_ctx *ctx, const int8_t *planes, int64_t plane_stride, int64_t shard_stride, int64_t N, int64_t shard,
                    const int32_t *tiles_h, int32_t n_tiles, const uint32_t *dep_flags, uint32_t epoch, const double *q,
                    const double *h2, const double *err, const double *SUB, int64_t sub_shard_stride, double *D, int64_t ldd,
-                   int64_t *flag_list, int64_t list_cap, void *stream);
+                   int64_t *flag_list, int64_t list_cap, const int32_t *seg_h, uint32_t *seg_done, void *stream);
 
 /* Device buffers shared between the processes of one node (CUDA IPC): the owner allocates (zero-filled) and hands the
  * 64-byte handle to its peers (any channel: the Python host uses torch.distributed), which map it.  A mapping is an
@@ -372,6 +380,13 @@ int fuf_host_unregister(void *ptr, size_t bytes, int32_t n_pieces);
 int fuf_host_device_pointer(fuf_ctx *ctx, void *host_ptr, void **dptr);
 /* Stream-ordered 32-bit store that needs no SM (cuStreamWriteValue32): the arrival flag of fuf_pairwise_tiles. */
 int fuf_stream_write_u32(fuf_ctx *ctx, uint32_t *dptr, uint32_t value, void *stream);
+/* Stream-ordered wait (cuStreamWaitValue32): the work queued on `stream` after this call starts once *dptr >= value —
+ * a completion counter of fuf_pairwise_tiles / fuf_gram_tiles that a running kernel advances. */
+int fuf_stream_wait_u32(fuf_ctx *ctx, const uint32_t *dptr, uint32_t value, void *stream);
+/* Pitched copy by a copy engine, `rows` rows of `width` bytes; either side may be device, peer or page-locked host
+ * memory (the finished rectangles of D leaving for the caller's matrix). */
+int fuf_copy2d_async(fuf_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows,
+                     void *stream);
 
 /* Test hook, host only (needs no device): the plan of the chunked push-up for a postorder parent array.
  * Arrays of length n; span_out gets 5 ints per spanning node (k, chunk_first, chunk_last, slot_start, slot_k). */

@@ -721,7 +721,7 @@ def test_integration_stub_runs(toy, full_tree):
     for both modes, against the oracle."""
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     text = open(os.path.join(repo, "INTEGRATION.md")).read()
-    code = text.split("```python\n# src/algorithms/emd_unifrac_b200.py", 1)[1].split("```", 1)[0]
+    code = "#" + text.split("```python\n# src/algorithms/emd_unifrac_b200.py", 1)[1].split("```", 1)[0]
     code = code.replace('ctypes.CDLL("libfununifrac.so")', f"ctypes.CDLL({engine.LIB_PATH!r})")
     ns = {}
     exec(compile(code, "INTEGRATION.md", "exec"), ns)
@@ -872,7 +872,8 @@ def test_cli_under_torchrun_two_gpus(l2, tmp_path):
     assert open(tmp_path / "one" / bn).read() == open(tmp_path / "two" / bn).read()
 
 
-@pytest.mark.parametrize("ranks,N,mode", [(2, 900, "l1"), (3, 700, "l1"), (4, 400, "l2"), (2, 640, "l2"), (3, 1100, "l2")])
+@pytest.mark.parametrize("ranks,N,mode", [(2, 900, "l1"), (3, 700, "l1"), (4, 400, "l2"), (2, 640, "l2"), (3, 1100, "l2"),
+                                          (2, 2100, "l1")])      # (the last one: banded upload of the own shard)
 def test_sharded_job_ranks_sharing_one_gpu(ranks, N, mode):
     """The multi-GPU job with several ranks on ONE device (collectives over gloo, staged through the host): everything
     CUDA-side of the peer form is real — IPC mappings between the processes, copy-engine pulls, arrival flags polled by

@@ -29,6 +29,19 @@ def test_library_exports_every_declared_symbol():
     assert L.fuf_padded_samples(1) == 128 and L.fuf_padded_samples(129) == 256
 
 
+def test_integration_stub_compiles_and_binds():
+    """The ctypes block of INTEGRATION.md (executed against the oracle by the GPU test test_integration_stub_runs) is valid
+    Python and every entry point it binds is exported — checked here without a GPU."""
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    code = "#" + text.split("```python\n# src/algorithms/emd_unifrac_b200.py", 1)[1].split("```", 1)[0]
+    code = code.replace('ctypes.CDLL("libfununifrac.so")', f"ctypes.CDLL({engine.LIB_PATH!r})")
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    assert callable(ns["all_pairs"])
+    for name in re.findall(r"_L\.(fuf_[a-z0-9_]+)", code):
+        assert hasattr(ns["_L"], name), name
+
+
 def test_no_gpu_is_a_loud_error():
     import torch
     if torch.cuda.is_available():

@@ -122,10 +122,27 @@ class OracleOps:
     def copy_to_target(self, D, target):
         target.copy_(D)
 
-    def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap):
+    gram_seg_units = 16
+
+    def stream_wait_u32(self, words, index, value, stream):
+        # the stand-in's "kernels" have run by the time the waits are queued: the counter must sit exactly at its target
+        assert int(words[index]) == value, (index, int(words[index]), value)
+        self.waits = getattr(self, "waits", 0) + 1
+
+    def copy_block(self, target, src, rows, cols, stream):
+        (r0, r1), (c0, c1) = rows, cols
+        assert not bool(torch.isnan(src[r0:r1, c0:c1]).any()), "a forwarded rectangle holds entries no tile has written"
+        target[r0:r1, c0:c1] = src[r0:r1, c0:c1]
+        src[r0:r1, c0:c1] = float("nan")        # (forwarded once: the next step must produce it again)
+
+    def pairwise_tiles(self, PS, N, mode, tiles, flags, epoch, D, shard, shard_stride, stat, flag_list, list_cap,
+                       seg=None, seg_done=None, units=1):
         G, n, sh = PS.shape
         kappa = 1.6e13 if self.l2 else 2e6
-        for ti, tj, dep in tiles:
+        assert (seg is None) == (seg_done is None) and (seg is None or len(seg) == len(tiles))
+        for c, (ti, tj, dep) in enumerate(tiles):
+            if seg is not None:
+                seg_done[seg[c]] += units
             assert dep < 0 or int(flags[dep]) == epoch, "tile scheduled before its shard's flag"
             i0, i1, j0, j1 = ti * TILE, min(N, (ti + 1) * TILE), tj * TILE, min(N, (tj + 1) * TILE)
             A = PS[i0 // sh, :, i0 % sh:i0 % sh + (i1 - i0)].T.double().numpy()
@@ -170,12 +187,14 @@ class OracleOps:
         h2[:n_valid] = 0
         err_out[:n_valid] = err_in[:n_valid]
 
-    def gram_tiles(self, planes, N, items, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap):
+    def gram_tiles(self, planes, N, items, flags, epoch, q, h2, err, SUB, D, flag_list, list_cap, seg=None, seg_done=None):
         G, sh = planes.shape[1], planes.shape[3]
         raw = np.ascontiguousarray(planes[:, :, :self.n].permute(1, 2, 3, 0).numpy())            # [G, n, shard, 4] bytes
         PS = torch.from_numpy(raw.view(np.float32).reshape(G, self.n, sh))
         tiles = []
-        for ti, b, dep in items:
+        for c, (ti, b, dep) in enumerate(items):
+            if seg is not None:
+                seg_done[seg[c]] += self.gram_seg_units
             for tj in (2 * b, 2 * b + 1):
                 if tj >= ti and tj * TILE < N:
                     tiles.append((ti, tj, dep))
@@ -374,3 +393,26 @@ def test_peer_tile_plan_covers_the_triangle_once():
         assert len(seen) == T * (T + 1) // 2
         if N == 10000 and world == 8:
             assert max(counts) / (sum(counts) / world) < 1.03
+
+
+def test_completion_segments_tile_the_matrix_once():
+    """The rectangles the completion segments of all ranks forward (sharded.segment_regions) cover every entry of the
+    matrix exactly once, for tiles and for the Gram items derived from them; every item inherits one segment."""
+    for N, world, mult in [(10000, 2, 128), (10000, 8, 128), (700, 3, 128), (129, 4, 128), (50000, 8, 256), (5000, 5, 256),
+                           (2100, 2, 128)]:
+        T = (N + TILE - 1) // TILE
+        cover = np.zeros((N, N), np.int8) if N <= 10000 else None
+        tcover = np.zeros((T, T), np.int32)
+        for r in range(world):
+            sh = sharded.shard_size(N, world, mult)
+            tiles, pulls, seg = sharded.peer_tile_plan(N, world, r, sh, segments=True)
+            assert len(seg) == len(tiles) and seg == sorted(seg)            # numbered in processing order
+            for regs in sharded.segment_regions(tiles, seg, N):
+                for a, b, c, d in regs:
+                    assert 0 <= a < b <= N and 0 <= c < d <= N
+                    tcover[a // TILE:(b + TILE - 1) // TILE, c // TILE:(d + TILE - 1) // TILE] += 1
+                    if cover is not None:
+                        cover[a:b, c:d] += 1
+            items, item_seg = sharded.gram_items(tiles, seg)
+            assert len(items) == len(item_seg) == len(set((i[0], i[1]) for i in items))
+        assert (tcover == 1).all() and (cover is None or (cover == 1).all()), (N, world)
