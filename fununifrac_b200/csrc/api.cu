@@ -108,9 +108,9 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     for (int b = 0; b < nb; b++) {  // all copies are queued up front
         const int64_t s0 = band_tile[b] * 128, s1 = std::min<int64_t>(N, band_tile[b + 1] * 128);
         if (s1 > s0)
-            FUF_CUDA(cudaMemcpy2DAsync((char *)ctx->ws_x.ptr + (size_t)s0 * ldx_dev * esz, (size_t)ldx_dev * esz,
+            FUF_RC(copy2d_async((char *)ctx->ws_x.ptr + (size_t)s0 * ldx_dev * esz, (size_t)ldx_dev * esz,
                                        (const char *)X_h + (size_t)s0 * ldx * esz, (size_t)ldx * esz, (size_t)n * esz,
-                                       (size_t)(s1 - s0), cudaMemcpyHostToDevice, sc));
+                                       (size_t)(s1 - s0), sc));
         FUF_CUDA(cudaEventRecord(e_band[b], sc));
     }
     for (int b = 0; b < nb; b++) {
@@ -136,10 +136,11 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             // --L2 on the tensor cores: the Gram kernel needs every sample (node means), so no banding here
             double *qg = stat + ldp, *eg = qg + ldp;
             // With a page-locked D_h the matrix leaves while it is being computed: the launch is cut into completion
-            // segments of whole tile rows (same item count each), the kernel counts the finished items of every segment,
-            // and the device-to-host stream waits on each counter in turn (cuStreamWaitValue32) before it copies the
-            // segment's rows right of the diagonal and its mirrored columns below it.  20 GB at N = 50,000 take 0.37 s
-            // over PCIe against 0.26 s of tensor-core work: the copies start ~10 ms into the launch instead of after it.
+            // segments of whole tile rows, the kernel counts the finished items of every segment, and the device-to-host
+            // stream waits on each counter in turn (cuStreamWaitValue32) before it copies the segment's rows — final in
+            // every column by then: right of the diagonal from the segment itself, left of it mirrored by the earlier
+            // ones.  20 GB at N = 50,000 take 0.37-0.40 s over PCIe against 0.26 s of tensor-core work: the copies start
+            // ~10 ms into the launch instead of after it (0.88 s -> 0.67 s for the whole call).
             // (Storing the tiles into the mapped host matrix from the kernel was measured first: the epilogue warps then
             // run at the link's pace — or far below it with narrow stores — and hold the tensor pipe back.)
             GramSegments segs;
@@ -147,7 +148,7 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
                 constexpr size_t max_seg = 4096;
                 if ((rc = ctx->ws_seg.reserve(max_seg * sizeof(uint32_t)))) return rc;
                 segs.seg_done = (uint32_t *)ctx->ws_seg.ptr;
-                segs.n_wanted = (int32_t)std::max<int64_t>(1, std::min<int64_t>(64, tiles_per_dim / 2));
+                segs.n_wanted = (int32_t)std::max<int64_t>(1, std::min<int64_t>(32, tiles_per_dim / 2));
                 if (getenv("FUF_GRAM_SEGMENTS")) segs.n_wanted = std::max(1, std::min(4000, atoi(getenv("FUF_GRAM_SEGMENTS"))));
                 // counters zeroed now; the copy stream may evaluate its waits from here on
                 FUF_CUDA(cudaMemsetAsync(segs.seg_done, 0, max_seg * sizeof(uint32_t), sk));
@@ -161,13 +162,8 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
             for (size_t sg = 0; sg < segs.row_end.size(); sg++) {
                 const int64_t R1 = std::min<int64_t>(N, (int64_t)segs.row_end[sg] * 128);
                 if ((rc = stream_wait_u32(segs.seg_done + sg, segs.expected[sg], sd))) return rc;
-                FUF_CUDA(cudaMemcpy2DAsync(D_h + (size_t)R0 * ldd + R0, (size_t)ldd * sizeof(double), D_dev + (size_t)R0 * N + R0,
-                                           (size_t)N * sizeof(double), (size_t)(N - R0) * sizeof(double), (size_t)(R1 - R0),
-                                           cudaMemcpyDeviceToHost, sd));
-                if (R1 < N)
-                    FUF_CUDA(cudaMemcpy2DAsync(D_h + (size_t)R1 * ldd + R0, (size_t)ldd * sizeof(double),
-                                               D_dev + (size_t)R1 * N + R0, (size_t)N * sizeof(double),
-                                               (size_t)(R1 - R0) * sizeof(double), (size_t)(N - R1), cudaMemcpyDeviceToHost, sd));
+                FUF_RC(copy2d_async(D_h + (size_t)R0 * ldd, (size_t)ldd * sizeof(double), D_dev + (size_t)R0 * N,
+                                           (size_t)N * sizeof(double), (size_t)N * sizeof(double), (size_t)(R1 - R0), sd));
                 R0 = R1;
             }
             const bool gram_segmented = !segs.row_end.empty();
@@ -178,8 +174,8 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
                 if (rc) return rc;
             }
             if (band_d2h && !gram_segmented) {
-                FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
-                                           (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
+                FUF_RC(copy2d_async(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
+                                           (size_t)N * sizeof(double), (size_t)N, sk));
             }
         } else if (!validate) {
             rc = pairwise_f32(ctx, (const float *)ctx->ws_p.ptr, s1, ldp, 0, 0, mode, nullptr, 0, D_dev, N, 0, sk,
@@ -194,13 +190,12 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
                 // finished: columns [s0, s1) of rows [0, s1), and (mirror) rows [s0, s1) left of the band
                 FUF_CUDA(cudaEventRecord(e_band[nb + b], sk));
                 FUF_CUDA(cudaStreamWaitEvent(sd, e_band[nb + b], 0));
-                FUF_CUDA(cudaMemcpy2DAsync(D_h + s0, (size_t)ldd * sizeof(double), D_dev + s0, (size_t)N * sizeof(double),
-                                           (size_t)(s1 - s0) * sizeof(double), (size_t)s1, cudaMemcpyDeviceToHost, sd));
+                FUF_RC(copy2d_async(D_h + s0, (size_t)ldd * sizeof(double), D_dev + s0, (size_t)N * sizeof(double),
+                                           (size_t)(s1 - s0) * sizeof(double), (size_t)s1, sd));
                 if (s0 > 0)
-                    FUF_CUDA(cudaMemcpy2DAsync(D_h + (size_t)s0 * ldd, (size_t)ldd * sizeof(double),
+                    FUF_RC(copy2d_async(D_h + (size_t)s0 * ldd, (size_t)ldd * sizeof(double),
                                                D_dev + (size_t)s0 * N, (size_t)N * sizeof(double),
-                                               (size_t)s0 * sizeof(double), (size_t)(s1 - s0), cudaMemcpyDeviceToHost,
-                                               sd));
+                                               (size_t)s0 * sizeof(double), (size_t)(s1 - s0), sd));
             }
         }
     }
@@ -211,8 +206,8 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
     }
     if (rc) return rc;
     if (!band_d2h)
-        FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
-                                   (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
+        FUF_RC(copy2d_async(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
+                                   (size_t)N * sizeof(double), (size_t)N, sk));
     FUF_CUDA(cudaEventRecord(e_end, sk));
     FUF_CUDA(cudaStreamSynchronize(sk));
     FUF_CUDA(cudaStreamSynchronize(sc));
@@ -244,8 +239,8 @@ extern "C" int fuf_all_pairs_host(fuf_ctx *ctx, const void *X_h, int x_dtype, in
                             FUF_CRIT_ROUNDING, nullptr, 0.0, 0);
             }
             if (rc) return rc;
-            FUF_CUDA(cudaMemcpy2DAsync(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
-                                       (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, sk));
+            FUF_RC(copy2d_async(D_h, (size_t)ldd * sizeof(double), D_dev, (size_t)N * sizeof(double),
+                                       (size_t)N * sizeof(double), (size_t)N, sk));
             FUF_CUDA(cudaStreamSynchronize(sk));
         }
     }

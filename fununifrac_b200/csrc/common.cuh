@@ -27,6 +27,13 @@ void set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
+// propagate the error code of a library-internal call (its message is already set)
+#define FUF_RC(call)                                                                           \
+    do {                                                                                       \
+        int rc__ = (call);                                                                     \
+        if (rc__ != FUF_OK) return rc__;                                                       \
+    } while (0)
+
 #define FUF_REQUIRE(cond, ...)                                                                 \
     do {                                                                                       \
         if (!(cond)) {                                                                         \
@@ -210,6 +217,8 @@ int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_
                          int64_t ldb, double *D_h, int64_t ldd, cudaStream_t stream);
 // tree.cu
 int stream_wait_u32(const uint32_t *dptr, uint32_t value, cudaStream_t stream);
+// cudaMemcpy2DAsync (cudaMemcpyDefault), cut at the boundaries of a host range that fuf_host_register page-locked in pieces
+int copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows, cudaStream_t stream);
 // gram.cu
 // Completion segments of a full-matrix Gram launch: in — device counters and the number of segments wanted; out — the
 // tile-row boundary of every segment and the counter value that says it is complete (empty: no segments were made).

@@ -1329,20 +1329,18 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
             for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, full ? t * TILE : c * TILE, 0});
         }
         if (segs && segs->seg_done && segs->n_wanted > 0 && full) {
-            // segments of whole tile rows with about the same number of items each: the caller's copy engine moves the
-            // rows (and mirrored columns) of a finished segment to the host while the later ones are computed
+            // completion segments of equally many tile rows: once segment s (and every earlier one) is counted complete,
+            // rows [row_end[s-1], row_end[s]) x 128 of D are final in ALL columns — right of the diagonal by the segment's
+            // own tiles, left of it by the mirror stores of the earlier segments — and leave as one contiguous copy
             const int32_t n_seg = (int32_t)std::min<int64_t>(std::min(segs->n_wanted, 4000), n_trows);
-            const size_t per = (ptiles.size() + n_seg - 1) / n_seg;
+            const int32_t per = (n_trows + n_seg - 1) / n_seg;
             size_t at = 0;
-            uint32_t in_seg = 0;
-            for (int32_t t = 0; t < n_trows; t++) {
-                const int32_t seg = (int32_t)segs->row_end.size();
-                for (; at < ptiles.size() && ptiles[at].ti == t; at++, in_seg++) ptiles[at].pad = (seg + 1) << 12;
-                if (in_seg >= per || t == n_trows - 1) {
-                    segs->row_end.push_back(t + 1);
-                    segs->expected.push_back(in_seg * GRAM_SEG_UNITS);
-                    in_seg = 0;
-                }
+            for (int32_t t0 = 0; t0 < n_trows; t0 += per) {
+                const int32_t t1 = std::min(n_trows, t0 + per), seg = (int32_t)segs->row_end.size();
+                uint32_t in_seg = 0;
+                for (; at < ptiles.size() && ptiles[at].ti < t1; at++, in_seg++) ptiles[at].pad = (seg + 1) << 12;
+                segs->row_end.push_back(t1);
+                segs->expected.push_back(in_seg * GRAM_SEG_UNITS);
             }
         }
         static_assert(PLANE_BYTES == 8192 && TILE == 128, "umma_block10 hard-codes the plane and accumulator strides");

@@ -933,14 +933,14 @@ int store_tile_rows_host(fuf_ctx *ctx, double *blocks, const int32_t *tile_rows_
         const int64_t row0 = t * TILE, rows = std::min<int64_t>(TILE, N - row0), below = N - row0 - rows;
         // rows [row0, row0 + rows), columns >= row0 (the diagonal tile is symmetric by now)
         if (part != 2)
-        FUF_CUDA(cudaMemcpy2DAsync(D_h + row0 * ldd + row0, (size_t)ldd * sizeof(double),
+        FUF_RC(copy2d_async(D_h + row0 * ldd + row0, (size_t)ldd * sizeof(double),
                                    blocks + (int64_t)c * TILE * ldb + row0, (size_t)ldb * sizeof(double),
-                                   (size_t)(N - row0) * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, stream));
+                                   (size_t)(N - row0) * sizeof(double), (size_t)rows, stream));
         // the mirror: rows below the diagonal tile, columns [row0, row0 + rows)
         if (below > 0 && part != 1)
-            FUF_CUDA(cudaMemcpy2DAsync(D_h + (row0 + rows) * ldd + row0, (size_t)ldd * sizeof(double),
+            FUF_RC(copy2d_async(D_h + (row0 + rows) * ldd + row0, (size_t)ldd * sizeof(double),
                                        panels + slots[c].offset, (size_t)TILE * sizeof(double),
-                                       (size_t)rows * sizeof(double), (size_t)below, cudaMemcpyDeviceToHost, stream));
+                                       (size_t)rows * sizeof(double), (size_t)below, stream));
     }
     return FUF_OK;
 }

@@ -9,6 +9,10 @@
 #include <cstring>
 #include <map>
 
+#include <cstdlib>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace fuf {
@@ -346,6 +350,13 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
     }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    // FUF_SM_LIMIT: size the persistent grids for fewer SMs than the device has — for a device shared with other clients
+    // (the single-GPU emulation of the multi-GPU job runs several ranks on one device, where the "peer" pulls are
+    // same-device copies the driver may run as kernels: they need an SM that no persistent CTA is spinning on)
+    if (const char *lim = getenv("FUF_SM_LIMIT")) {
+        const int v = atoi(lim);
+        if (v >= 2 && v < ctx->sm_count) ctx->sm_count = v;
+    }
     ctx->n = n;
     ctx->parent.assign(parent_h, parent_h + n);
 
@@ -538,17 +549,80 @@ extern "C" int fuf_peer_free(fuf_ctx *ctx, void *dptr)
 // Page-lock a range of host memory another allocator owns (the result matrix the ranks of a node share).  Some boxes
 // refuse one registration of tens of gigabytes (cudaErrorOperatingSystem) but take it in pieces; with unified addressing
 // the pieces still form one contiguous device-visible range.  *n_pieces receives how many registrations were made.
+namespace {
+// Ranges fuf_host_register had to page-lock in pieces.  A copy-engine transfer must lie inside ONE registration, so the
+// pitched copies into such a range are cut at the piece boundaries (fuf::copy2d_async).
+struct PiecedRange {
+    uintptr_t base;
+    size_t bytes, step;
+};
+std::mutex g_pieced_mutex;
+std::vector<PiecedRange> g_pieced;
+
+bool pieced_range_of(const void *p, PiecedRange *out)
+{
+    std::lock_guard<std::mutex> lock(g_pieced_mutex);
+    for (const PiecedRange &r : g_pieced)
+        if ((uintptr_t)p >= r.base && (uintptr_t)p < r.base + r.bytes) {
+            *out = r;
+            return true;
+        }
+    return false;
+}
+}  // namespace
+
+namespace fuf {
+int copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows, cudaStream_t stream)
+{
+    if (!width || !rows) return FUF_OK;
+    PiecedRange r;
+    const bool dst_pieced = pieced_range_of(dst, &r);
+    if (!dst_pieced && !pieced_range_of(src, &r)) {
+        FUF_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDefault, stream));
+        return FUF_OK;
+    }
+    // p walks the side that lives in the pieced range: runs of whole rows inside one piece go as one pitched copy, a row
+    // whose segment straddles a boundary as two plain copies
+    const uintptr_t p0 = (uintptr_t)(dst_pieced ? dst : src);
+    const size_t pitch = dst_pieced ? dst_pitch : src_pitch;
+    size_t i = 0;
+    while (i < rows) {
+        const uintptr_t p = p0 + i * pitch;
+        const uintptr_t piece_end = r.base + ((p - r.base) / r.step + 1) * r.step;
+        char *d = (char *)dst + i * dst_pitch;
+        const char *s = (const char *)src + i * src_pitch;
+        if (p + width <= piece_end) {
+            const size_t fit = pitch ? (piece_end - width - p) / pitch + 1 : rows - i;   // rows i .. i + fit - 1 end inside the piece
+            const size_t run = std::min(rows - i, fit);
+            FUF_CUDA(cudaMemcpy2DAsync(d, dst_pitch, s, src_pitch, width, run, cudaMemcpyDefault, stream));
+            i += run;
+        } else {
+            const size_t head = piece_end - p;
+            FUF_CUDA(cudaMemcpyAsync(d, s, head, cudaMemcpyDefault, stream));
+            FUF_CUDA(cudaMemcpyAsync(d + head, s + head, width - head, cudaMemcpyDefault, stream));
+            i += 1;
+        }
+    }
+    return FUF_OK;
+}
+}  // namespace fuf
+
 extern "C" int fuf_host_register(void *ptr, size_t bytes, int32_t *n_pieces)
 {
     FUF_REQUIRE(ptr && n_pieces, "fuf_host_register: null argument");
     *n_pieces = 0;
     if (bytes == 0) return FUF_OK;
-    if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+    // FUF_REGISTER_STEP (bytes, a multiple of the page size): register in pieces of that size right away — a test hook for
+    // the piece-boundary handling of the pitched copies
+    size_t step = (size_t)1 << 30;
+    const char *forced = getenv("FUF_REGISTER_STEP");
+    if (forced && atoll(forced) >= 4096) {
+        step = (size_t)atoll(forced);
+    } else if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) {
         *n_pieces = 1;
         return FUF_OK;
     }
     cudaGetLastError();   // not sticky: clear it before trying the pieces
-    const size_t step = (size_t)1 << 30;
     int32_t done = 0;
     for (size_t off = 0; off < bytes; off += step, done++) {
         cudaError_t err = cudaHostRegister((char *)ptr + off, std::min(step, bytes - off), cudaHostRegisterDefault);
@@ -561,16 +635,29 @@ extern "C" int fuf_host_register(void *ptr, size_t bytes, int32_t *n_pieces)
         }
     }
     *n_pieces = done;
+    {
+        std::lock_guard<std::mutex> lock(g_pieced_mutex);
+        g_pieced.push_back(PiecedRange{(uintptr_t)ptr, bytes, step});
+    }
     return FUF_OK;
 }
 
 extern "C" int fuf_host_unregister(void *ptr, size_t bytes, int32_t n_pieces)
 {
     if (!ptr || n_pieces <= 0) return FUF_OK;
-    if (n_pieces == 1) {
+    size_t step = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pieced_mutex);
+        for (size_t q = 0; q < g_pieced.size(); q++)
+            if (g_pieced[q].base == (uintptr_t)ptr) {
+                step = g_pieced[q].step;
+                g_pieced.erase(g_pieced.begin() + q);
+                break;
+            }
+    }
+    if (step == 0) {
         cudaHostUnregister(ptr);
     } else {
-        const size_t step = (size_t)1 << 30;
         for (size_t off = 0; off < bytes; off += step) cudaHostUnregister((char *)ptr + off);
     }
     cudaGetLastError();
@@ -666,9 +753,7 @@ extern "C" int fuf_copy2d_async(fuf_ctx *ctx, void *dst, size_t dst_pitch, const
     FUF_REQUIRE(ctx && dst && src, "fuf_copy2d_async: null argument");
     FUF_REQUIRE(dst_pitch >= width && src_pitch >= width, "fuf_copy2d_async: pitch smaller than the row width");
     FUF_CUDA(cudaSetDevice(ctx->device));
-    if (width && rows)
-        FUF_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDefault, (cudaStream_t)stream));
-    return FUF_OK;
+    return copy2d_async(dst, dst_pitch, src, src_pitch, width, rows, (cudaStream_t)stream);
 }
 
 extern "C" int64_t fuf_launch_count(const fuf_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -33,7 +33,9 @@ from __future__ import annotations
 from typing import List, Optional, Sequence  # noqa: F401
 
 TILE = 128
-STRIP = 12        # tile rows per rasterisation strip: floor(sqrt(148 SMs))
+import os as _os
+
+STRIP = int(_os.environ.get("FUF_STRIP", "12"))        # tile rows per rasterisation strip: floor(sqrt(148 SMs))
 
 
 def shard_size(N: int, world: int, multiple: int = TILE) -> int:
@@ -400,7 +402,8 @@ class ShardedAllPairs:
     def _local_matrix(self, target):
         """Where the tile kernels store: the target itself when it is this device's memory (rank 0 of ``step``), else the
         rank's own matrix, from which the copy engine forwards the finished segments."""
-        if target is self.D:
+        import os
+        if target is self.D or os.environ.get("FUF_NO_FORWARD"):      # (debug switch: the kernels store in place everywhere)
             return target
         if self.D_local is None:
             self.D_local = self.ops.empty((self.N, self.N), "float64")

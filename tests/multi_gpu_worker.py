@@ -92,13 +92,37 @@ def main():
     X[N - 2] /= X[N - 2].sum()
     X[N // 2 + 1] = X[7]                                                 # identical pair
     mode = engine.MODE_L2 if l2 else engine.MODE_L1
-    job = sharded.ShardedAllPairs(sharded.CudaOps(ctx), N, mode, world, rank, comm)
+    ops = sharded.CudaOps(ctx)
+    if os.environ.get("FUF_TEST_VERBOSE") == "2":        # debugging aid: synchronise after every ops call, name the one that fails
+        class Traced:
+            def __init__(self, inner):
+                self.__dict__["_inner"] = inner
+
+            def __getattr__(self, name):
+                attr = getattr(self._inner, name)
+                if not callable(attr):
+                    return attr
+
+                def call(*a, **k):
+                    out = attr(*a, **k)
+                    try:
+                        torch.cuda.synchronize()
+                    except Exception:
+                        print(f"rank {rank}: CUDA error surfaced after ops.{name}", flush=True)
+                        raise
+                    return out
+                return call
+        ops = Traced(ops)
+    job = sharded.ShardedAllPairs(ops, N, mode, world, rank, comm)
     assert job.use_peer and job.use_gram == (l2 and N >= 512)
     Xl = engine.profile_matrix(job.hi - job.lo, n, torch.float64, f"cuda:{local}")
     Xl.copy_(torch.from_numpy(X[job.lo:job.hi]))
     results = []
-    for _ in range(3):                                                   # epochs advance, buffers are reused
+    for it in range(3):                                                  # epochs advance, buffers are reused
         D = job.step(Xl)
+        torch.cuda.synchronize()
+        if os.environ.get("FUF_TEST_VERBOSE"):
+            print(f"rank {rank}: step {it} done", flush=True)
         if rank == 0:
             results.append(D.cpu().numpy().copy())
     shared = sharded.SharedHostMatrix(N, world, rank, comm)

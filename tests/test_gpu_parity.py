@@ -715,6 +715,59 @@ def test_cli_end_to_end(data_dir, golden_dir, tmp_path):
         compute_fununifrac.main(["-e", edge, "-fd", str(tmp_path), "-o", out])     # no matching files
 
 
+def test_host_ranges_registered_in_pieces(full_tree, monkeypatch):
+    """Some boxes page-lock a 20 GB result matrix only in pieces (fuf_host_register falls back to 1 GB registrations), and a
+    copy-engine transfer must lie inside one registration: every pitched copy to or from such a range is cut at the piece
+    boundaries.  Forced here with 64 KB pieces (FUF_REGISTER_STEP): rectangles whose rows straddle boundaries, then the
+    whole host-buffer call — both modes, the Gram route with its completion segments — with X and D registered that way."""
+    import ctypes
+    import mmap
+    inp, ctx, leaves = full_tree
+    lib = engine.load_library()
+    monkeypatch.setenv("FUF_REGISTER_STEP", str(64 << 10))
+
+    def pieced(shape):
+        nbytes = int(np.prod(shape)) * 8
+        buf = mmap.mmap(-1, (nbytes + 4095) // 4096 * 4096)
+        arr = np.frombuffer(buf, dtype=np.float64, count=int(np.prod(shape))).reshape(shape)
+        pieces = ctypes.c_int32()
+        engine._check(lib.fuf_host_register(arr.ctypes.data, nbytes, ctypes.byref(pieces)), "fuf_host_register")
+        assert pieces.value == (nbytes + (64 << 10) - 1) // (64 << 10)
+        return buf, arr, pieces
+
+    def release(buf, arr, pieces):
+        lib.fuf_host_unregister(arr.ctypes.data, arr.nbytes, pieces)
+
+    N = 700                                   # a row of D is 5,600 bytes: 64 KB boundaries fall inside rows
+    hb = pieced((N, N))
+    Dh = hb[1]
+    Dh[...] = -1.0
+    src = torch.rand((N, N), dtype=torch.float64, device="cuda")
+    target = ctx.host_device_pointer(Dh)
+    rects = [((0, N), (0, N)), ((3, 400), (17, 650)), ((128, 256), (0, 128)), ((511, 700), (699, 700)), ((5, 6), (0, 700))]
+    want = np.full((N, N), -1.0)
+    for rows, cols in rects[1:]:
+        ctx.copy_block_async(target, N, src, rows, cols)
+        want[rows[0]:rows[1], cols[0]:cols[1]] = src[rows[0]:rows[1], cols[0]:cols[1]].cpu().numpy()
+    torch.cuda.synchronize()
+    assert np.array_equal(Dh, want)
+    ctx.copy_block_async(target, N, src, *rects[0])
+    torch.cuda.synchronize()
+    assert np.array_equal(Dh, src.cpu().numpy())
+    X = synth.synth_profiles_dense(leaves, ctx.n, N, seed=29)
+    hx = pieced(X.shape)
+    hx[1][...] = X
+    try:
+        for l2 in (False, True):
+            Dh[...] = np.nan
+            ctx.all_pairs_host(hx[1], engine.MODE_L2 if l2 else engine.MODE_L1, Dh)
+            ref = oracle_c.pairwise(oracle_c.push_up(inp.parent, inp.edge_length, X, l2), l2)
+            assert rel_err(Dh, ref) < REL and np.array_equal(Dh, Dh.T)
+    finally:
+        release(*hx)
+        release(*hb)
+
+
 def test_integration_stub_runs(toy, full_tree):
     """INTEGRATION.md section B shows the ctypes binding a maintainer of the reference would add.  This test executes that
     very code block (library name replaced by the built library's path) on the toy tree and on the full synthetic tree,
@@ -882,7 +935,10 @@ def test_sharded_job_ranks_sharing_one_gpu(ranks, N, mode):
     import subprocess
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    # FUF_SM_LIMIT: on ONE device the "peer" pulls are same-device copies, which the driver may run as SM kernels; with a
+    # persistent CTA spinning for its shard on every SM such a copy could never start (measured: N = 2,100 deadlocks into
+    # the kernels' bounded-wait trap).  Between real GPUs the pulls are copy-engine transfers and need no SM.
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0], FUF_SM_LIMIT="140")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr",
            "127.0.0.1", "--master-port", "29543", os.path.join(repo, "tests", "multi_gpu_worker.py"), str(N), mode]
     res = subprocess.run(cmd, cwd=repo, env=env, capture_output=True, text=True, timeout=900)

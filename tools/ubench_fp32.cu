@@ -5,7 +5,8 @@
 //   l1_packed : FADD2 d = a.bcast - b2; FADD2 acc2 += |d|   (2 packed per 2 elements)
 //   l2_packed : FADD2 + FFMA2
 //   ffma / ffma2 : plain FMA throughput
-//   l1_minmix : 2/3 of the elements via FADD2 pair, 1/3 via FMNMX (ALU pipe) + FADD
+//   l1_minmix : 3/4 of the elements via FADD2 pair, 1/4 via FMNMX (ALU pipe) + scalar FADD
+//   l1_minpacked_* : 1/2, 3/4 or all of the elements via FMNMX + ONE packed FADD2 per two elements
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_fp32 ubench_fp32.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -75,6 +76,21 @@ __global__ void __launch_bounds__(256) bench(const float *__restrict__ in, float
                 acc[m][6] += fminf(a[m], b[6]);
                 acc[m][7] += fminf(a[m], b[7]);
             }
+        } else if (KIND == 7 || KIND == 8 || KIND == 9) {
+            // packed min form: the FMNMX results of two neighbouring columns land in one register pair and are accumulated
+            // by ONE FADD2 — 1 FMA-pipe lane-op + 1 ALU-pipe lane-op per element instead of 2 FMA-pipe lane-ops.
+            // KIND 7: 2 of 4 column pairs via min (f = 1/2), KIND 8: 3 of 4 (f = 3/4), KIND 9: all four (f = 1)
+            constexpr int NMIN = KIND == 7 ? 2 : (KIND == 8 ? 3 : 4);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+#pragma unroll
+                for (int q = 0; q < 4 - NMIN; q++) acc2[m][q] = add_abs(acc2[m][q], sub_bc(a[m], b2[q]));
+#pragma unroll
+                for (int q = 4 - NMIN; q < 4; q++) {
+                    const uint64_t mn = pk(fminf(a[m], b[2 * q]), fminf(a[m], b[2 * q + 1]));
+                    asm("add.f32x2 %0, %0, %1;" : "+l"(acc2[m][q]) : "l"(mn));
+                }
+            }
         }
         // perturb the operands a little so nothing is loop-invariant (1 FADD per 64 updates for each of 16 regs is noise)
         a[it & 7] += 1.0f;
@@ -127,6 +143,9 @@ int main()
         run<4>("ffma", bps, sms, in, out, cyc);
         run<5>("ffma2", bps, sms, in, out, cyc);
         run<6>("l1_minmix", bps, sms, in, out, cyc);
+        run<7>("l1_minpacked_half", bps, sms, in, out, cyc);
+        run<8>("l1_minpacked_3of4", bps, sms, in, out, cyc);
+        run<9>("l1_minpacked_all", bps, sms, in, out, cyc);
     }
     return 0;
 }
