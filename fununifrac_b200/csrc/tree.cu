@@ -582,7 +582,7 @@ int copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
         return FUF_OK;
     }
     // p walks the side that lives in the pieced range: runs of whole rows inside one piece go as one pitched copy, a row
-    // whose segment straddles a boundary as two plain copies
+    // whose segment straddles a boundary as plain copies of its parts
     const uintptr_t p0 = (uintptr_t)(dst_pieced ? dst : src);
     const size_t pitch = dst_pieced ? dst_pitch : src_pitch;
     size_t i = 0;
@@ -597,9 +597,12 @@ int copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
             FUF_CUDA(cudaMemcpy2DAsync(d, dst_pitch, s, src_pitch, width, run, cudaMemcpyDefault, stream));
             i += run;
         } else {
-            const size_t head = piece_end - p;
-            FUF_CUDA(cudaMemcpyAsync(d, s, head, cudaMemcpyDefault, stream));
-            FUF_CUDA(cudaMemcpyAsync(d + head, s + head, width - head, cudaMemcpyDefault, stream));
+            for (size_t at = 0; at < width;) {   // (a row wider than a piece crosses several boundaries)
+                const uintptr_t q = p + at;
+                const size_t part = std::min<size_t>(width - at, r.base + ((q - r.base) / r.step + 1) * r.step - q);
+                FUF_CUDA(cudaMemcpyAsync(d + at, s + at, part, cudaMemcpyDefault, stream));
+                at += part;
+            }
             i += 1;
         }
     }
