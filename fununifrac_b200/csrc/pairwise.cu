@@ -7,7 +7,9 @@
 // over ALL n basis entries including the unscaled root.
 //
 // K2 pairwise_tile_kernel (production, FP32-pipe bound: 2 FP32 lane-ops per (pair, basis entry)):
-//   * persistent CTAs (one per SM) loop over work items = (128x128 tile of D, k-split);
+//   * persistent CTAs (one per SM) loop over their work items = (128x128 tile of D, range of basis entries): whole tiles
+//     dealt round-robin for the full waves, then the tiles of the last, partial wave cut into equal contiguous spans
+//     of the (tile, basis entry) space, one span per CTA (stream-K tail: no SM idles through a partial wave);
 //   * warp-specialised: warps 0-7 (256 threads, 2 warpgroups) consume, the third warpgroup donates its
 //     registers (setmaxnreg) and one of its lanes is the TMA producer;
 //   * operand tiles A = PT[k0:k0+16][i0:i0+128], B = PT[k0:k0+16][j0:j0+128] are brought in by TMA
@@ -18,9 +20,11 @@
 //   * accuracy: fp32 partial sums are folded into double accumulators (shared memory, one private
 //     column per thread) every 256 basis entries, so each fp32 accumulator sees at most 256 adds;
 //   * epilogue: the double tile is written through shared memory with fully coalesced rows, to
-//     D[i,j] and (mirrored) D[j,i]; with k-splits, to a partial buffer that a second kernel reduces
-//     in fixed order (deterministic, no atomics).
+//     D[i,j] and (mirrored) D[j,i]; a tile shared by several CTAs goes to a partial buffer that a second kernel
+//     reduces in fixed order (deterministic, no atomics).
 // K5 pairwise_f64_kernel: validation mode, everything in double, no FMA contraction.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace fuf {
@@ -45,18 +49,27 @@ struct TileDesc {
 __device__ __host__ __forceinline__ int tile_dep(int32_t m) { return (m >> 8) & 0xfff; }
 __device__ __host__ __forceinline__ int tile_seg(int32_t m) { return (m >> 20) & 0xfff; }
 
+// One work item of a CTA: stages [s_begin, s_end) of a tile.  slot < 0: the item covers every stage and its result goes
+// straight to D; otherwise the tile is shared with other CTAs and the item's sums go to partial slot `slot`.
+struct WorkItem {
+    int32_t tile, s_begin, s_end, slot;
+};
+// A tile assembled from partial slots [first_slot, first_slot + n_slots), in ascending order of the basis entries.
+struct SharedTile {
+    int32_t tile, first_slot, n_slots, pad;
+};
+
 struct PairParams {
     const TileDesc *tiles;
-    int32_t n_items;           // n_tiles * splits
-    int32_t splits;
+    const WorkItem *work;      // all CTAs' items; CTA c owns work[cta_first[c] .. cta_first[c + 1])
+    const int32_t *cta_first;
     int32_t stages_total;      // ceil(n / KC)
-    int32_t stages_per_split;
     int32_t flush_stages;      // fp32 partial sums are folded into double every flush_stages stages
     int32_t shard;             // columns per shard of PT (>= padded N when there is a single block)
     int64_t N;
     double *D;
     int64_t ldd;
-    double *partial;           // [n_items][TILE*TILE] when splits > 1
+    double *partial;           // [n_slots][TILE*TILE]: sums of the items that cover only part of a tile
     // multi-GPU tiles mode (fuf_pairwise_tiles): operand shards arrive from peer GPUs while the kernel runs
     const uint32_t *dep_flags; // device flags, one per shard
     uint32_t epoch;            // value a flag takes once its shard has landed in this launch's step
@@ -192,11 +205,10 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
         if (warp == NCONS / 32 && lane == 0) {  // one elected lane issues all TMA loads
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const TileDesc td = p.tiles[item / p.splits];
-                const int split = item % p.splits;
-                const int s_begin = split * p.stages_per_split;
-                const int s_end = min(p.stages_total, s_begin + p.stages_per_split);
+            for (int w = p.cta_first[blockIdx.x]; w < p.cta_first[blockIdx.x + 1]; ++w) {
+                const WorkItem wi = p.work[w];
+                const TileDesc td = p.tiles[wi.tile];
+                const int s_begin = wi.s_begin, s_end = wi.s_end;
                 const int ia = td.ti * TILE, ib = td.tj * TILE;
                 if (tile_dep(td.mirror)) {
                     // this tile reads a shard that a copy engine is still bringing in from a peer GPU: wait for its
@@ -234,11 +246,10 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
     double *my64 = acc64 + tid;                   // slot (m*8+nn) lives at my64[(m*8+nn)*NCONS]
 
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const TileDesc td = p.tiles[item / p.splits];
-        const int split = item % p.splits;
-        const int s_begin = split * p.stages_per_split;
-        const int s_end = min(p.stages_total, s_begin + p.stages_per_split);
+    for (int w = p.cta_first[blockIdx.x]; w < p.cta_first[blockIdx.x + 1]; ++w) {
+        const WorkItem wi = p.work[w];
+        const TileDesc td = p.tiles[wi.tile];
+        const int s_begin = wi.s_begin, s_end = wi.s_end;
 
         float acc[8][8];
         uint64_t acc2[8][4];
@@ -329,8 +340,8 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
             return (m * 8 + nn) * NCONS + ow * 32 + ol;
         };
         const int half = tid >> 7, col = tid & 127;
-        if (p.splits > 1) {
-            double *dst = p.partial + (size_t)item * (TILE * TILE);
+        if (wi.slot >= 0) {
+            double *dst = p.partial + (size_t)wi.slot * (TILE * TILE);
             for (int r = half; r < TILE; r += 2) dst[r * TILE + col] = acc64[slot_of(r, col)];
         } else {
             const int64_t gi0 = (int64_t)td.ti * TILE, gj0 = (int64_t)td.tj * TILE;
@@ -351,7 +362,7 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
                     }
             }
         }
-        const bool count_seg = p.seg_done && p.splits == 1 && tile_seg(td.mirror);
+        const bool count_seg = p.seg_done && wi.slot < 0 && tile_seg(td.mirror);
         if (count_seg) __threadfence();   // this thread's part of the tile is visible before the counter moves
         consumer_bar();  // the next item re-zeroes the accumulators
         if (count_seg && tid == 0) atomicAdd(p.seg_done + (tile_seg(td.mirror) - 1), 1u);
@@ -361,11 +372,13 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
 // Sum the k-split partial tiles in fixed order and write D (+ mirror).
 template <int MODE>
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restrict__ partial, int splits, int64_t N,
+reduce_partials_kernel(const TileDesc *__restrict__ tiles, const SharedTile *__restrict__ shared, const double *__restrict__ partial, int64_t N,
                        double *__restrict__ D, int64_t ldd, const PairParams p)
 {
-    const TileDesc td = tiles[blockIdx.x];
-    const double *src = partial + (size_t)blockIdx.x * splits * (TILE * TILE);
+    const SharedTile sh = shared[blockIdx.x];
+    const TileDesc td = tiles[sh.tile];
+    const int splits = sh.n_slots;
+    const double *src = partial + (size_t)sh.first_slot * (TILE * TILE);
     const int64_t gi0 = (int64_t)td.ti * TILE, gj0 = (int64_t)td.tj * TILE;
     __shared__ double tile[32][33];
     // 4x4 sub-blocks of 32x32 so that both the direct and the mirrored write are coalesced
@@ -391,7 +404,7 @@ reduce_partials_kernel(const TileDesc *__restrict__ tiles, const double *__restr
         }
         __syncthreads();
     }
-    if (p.seg_done && tile_seg(td.mirror)) {   // (with k-splits the tile is finished here, not in the tile kernel)
+    if (p.seg_done && tile_seg(td.mirror)) {   // (a shared tile is finished here, not in the tile kernel)
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(p.seg_done + (tile_seg(td.mirror) - 1), 1u);
@@ -506,6 +519,84 @@ assemble_kernel(const double *__restrict__ blocks, const int32_t *__restrict__ t
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// Work plan of one launch of the tile kernel.  Tiles cost the same, so the first floor(n_tiles / grid) * grid of them go
+// round-robin as whole tiles — wave w runs tiles w * grid .. (w + 1) * grid - 1, which the rasterised order makes a compact
+// block sharing its operand panels in L2 — and need no second pass.  The remaining R < grid tiles would leave most SMs
+// idle for a whole tile time (N = 10,000: 3,160 tiles = 21.35 waves on 148 SMs; 8 GPUs: 405 = 2.74): their (tile, basis
+// entry) space is cut into equal contiguous spans, one per CTA (stream-K).  Span boundaries fall on fp32 flush
+// boundaries (256 basis entries), so the set of fp32 chunk sums of a pair never depends on the plan — only the order of
+// the last few float64 additions does; a tile cut between CTAs is summed from its partial slots in ascending order by
+// reduce_partials_kernel (fixed order, no atomics).
+struct PairWorkPlan {
+    int32_t grid = 0, n_slots = 0;
+    std::vector<int32_t> cta_first;
+    std::vector<WorkItem> work;
+    std::vector<SharedTile> shared;
+};
+static void plan_pair_work(int32_t n_tiles, int32_t sm_count, int32_t stages_total, int32_t flush_stages, bool stream_k,
+                           PairWorkPlan &plan)
+{
+    constexpr int32_t MIN_UNITS = 4;   // a span is at least 4 flush units (1,024 basis entries) long
+    const int32_t units = (stages_total + flush_stages - 1) / flush_stages;   // flush units per tile
+    const int32_t full_waves = n_tiles / sm_count, rest = n_tiles - full_waves * sm_count;
+    const int64_t rest_units = (int64_t)rest * units;
+    int32_t tail_ctas = 0;
+    if (rest > 0)
+        tail_ctas = stream_k ? (int32_t)std::max<int64_t>(rest, std::min<int64_t>(sm_count, rest_units / MIN_UNITS)) : rest;
+    plan.grid = full_waves > 0 ? sm_count : tail_ctas;
+    std::vector<std::vector<WorkItem>> per(plan.grid);
+    for (int32_t w = 0; w < full_waves; w++)
+        for (int32_t c = 0; c < sm_count; c++) per[c].push_back(WorkItem{w * sm_count + c, 0, stages_total, -1});
+    for (int32_t c = 0; c < tail_ctas; c++) {
+        int64_t lo = rest_units * c / tail_ctas;
+        const int64_t hi = rest_units * (c + 1) / tail_ctas;
+        while (lo < hi) {
+            const int32_t r = (int32_t)(lo / units), u0 = (int32_t)(lo % units);
+            const int32_t u1 = (int32_t)std::min<int64_t>(units, u0 + (hi - lo));
+            const bool whole = u0 == 0 && u1 == units;
+            per[c].push_back(WorkItem{full_waves * sm_count + r, u0 * flush_stages, std::min(stages_total, u1 * flush_stages),
+                                      whole ? -1 : 0});
+            lo += u1 - u0;
+        }
+    }
+    // partial slots in (tile, basis entry) order: CTAs hold ascending spans, so walking them in order numbers the slots
+    plan.cta_first.assign(1, 0);
+    for (int32_t c = 0; c < plan.grid; c++) {
+        for (WorkItem wi : per[c]) {
+            if (wi.slot >= 0 && !(wi.s_begin == 0 && wi.s_end == stages_total)) {
+                wi.slot = plan.n_slots++;
+                if (plan.shared.empty() || plan.shared.back().tile != wi.tile) plan.shared.push_back(SharedTile{wi.tile, wi.slot, 0, 0});
+                plan.shared.back().n_slots++;
+            } else {
+                wi.slot = -1;
+            }
+            plan.work.push_back(wi);
+        }
+        plan.cta_first.push_back((int32_t)plan.work.size());
+    }
+}
+
+// Test hook, host only: the work plan for n_tiles tiles on sm_count SMs as (cta, tile, s_begin, s_end, slot) rows.
+extern "C" int fuf_debug_pair_plan(int32_t n_tiles, int32_t sm_count, int32_t stages_total, int32_t flush_stages,
+                                   int32_t stream_k, int32_t *rows_out, int32_t max_rows, int32_t *n_rows, int32_t *grid)
+{
+    FUF_REQUIRE(n_tiles >= 0 && sm_count > 0 && stages_total > 0 && flush_stages > 0 && n_rows && grid, "fuf_debug_pair_plan: bad argument");
+    PairWorkPlan plan;
+    if (n_tiles > 0) plan_pair_work(n_tiles, sm_count, stages_total, flush_stages, stream_k != 0, plan);
+    *n_rows = (int32_t)plan.work.size();
+    *grid = plan.grid;
+    if (rows_out) {
+        FUF_REQUIRE(max_rows >= *n_rows, "fuf_debug_pair_plan: %d rows needed", *n_rows);
+        for (int32_t c = 0; c < plan.grid; c++)
+            for (int32_t w = plan.cta_first[c]; w < plan.cta_first[c + 1]; w++) {
+                const WorkItem &wi = plan.work[w];
+                int32_t *o = rows_out + 5 * (size_t)w;
+                o[0] = c, o[1] = wi.tile, o[2] = wi.s_begin, o[3] = wi.s_end, o[4] = wi.slot;
+            }
+    }
+    return FUF_OK;
+}
+
 int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride, int mode,
                  const int32_t *tile_rows_h, int32_t n_tile_rows, double *D, int64_t ldd, int flags,
                  cudaStream_t stream, int32_t col_tile_begin, int32_t col_tile_end, int32_t n_rows_override,
@@ -639,41 +730,41 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
         if (rc) return rc;
     }
 
-    // ---- k-splits: minimise the makespan over the SMs ------------------------------------------------
+    // ---- work plan: whole tiles for the full waves, equal spans of the (tile, basis entry) space for the last wave ----
     const int32_t stages_total = (n + KC - 1) / KC;
-    int32_t best_s = 1;
-    {
-        int64_t best_cost = INT64_MAX;
-        const int32_t max_s = std::max(1, std::min(64, stages_total / (2 * flush_stages)));
-        for (int32_t s = 1; s <= max_s; s++) {
-            const int64_t per = (stages_total + s - 1) / s;
-            const int64_t waves = ((int64_t)n_tiles * s + ctx->sm_count - 1) / ctx->sm_count;
-            const int64_t cost = waves * (per + 40);  // +40 stages ~ per-item prologue/epilogue
-            if (cost < best_cost) {
-                best_cost = cost;
-                best_s = s;
-            }
-        }
+    PairWorkPlan plan;
+    plan_pair_work(n_tiles, ctx->sm_count, stages_total, flush_stages, getenv("FUF_PW_NO_STREAMK") == nullptr, plan);
+    std::string wkey("wk");
+    key_append(wkey, n_tiles);
+    key_append(wkey, ctx->sm_count);
+    key_append(wkey, stages_total);
+    key_append(wkey, flush_stages);
+    key_append(wkey, plan.n_slots);
+    const size_t first_bytes = ((size_t)(plan.grid + 1) * sizeof(int32_t) + 15) & ~(size_t)15;
+    const size_t work_bytes = plan.work.size() * sizeof(WorkItem);
+    char *d_plan = (char *)ctx->tables.find(wkey);
+    if (!d_plan) {
+        std::vector<char> blob(first_bytes + work_bytes + plan.shared.size() * sizeof(SharedTile));
+        memcpy(blob.data(), plan.cta_first.data(), (size_t)(plan.grid + 1) * sizeof(int32_t));
+        memcpy(blob.data() + first_bytes, plan.work.data(), work_bytes);
+        if (!plan.shared.empty())
+            memcpy(blob.data() + first_bytes + work_bytes, plan.shared.data(), plan.shared.size() * sizeof(SharedTile));
+        int rc = ctx->tables.put(wkey, blob.data(), blob.size(), (void **)&d_plan);
+        if (rc) return rc;
     }
-    // split boundaries fall on fp32 flush boundaries, so the set of 256-entry fp32 partial sums of a pair does
-    // not depend on the number of splits (only the order of the final double additions does)
-    int32_t per_split = (stages_total + best_s - 1) / best_s;
-    per_split = (per_split + flush_stages - 1) / flush_stages * flush_stages;
-    const int32_t splits = (stages_total + per_split - 1) / per_split;  // no empty split
 
     double *d_partial = nullptr;
-    if (splits > 1) {
-        int rc = ctx->ws_pair.reserve((size_t)n_tiles * splits * TILE * TILE * sizeof(double));
+    if (plan.n_slots > 0) {
+        int rc = ctx->ws_pair.reserve((size_t)plan.n_slots * TILE * TILE * sizeof(double));
         if (rc) return rc;
         d_partial = (double *)ctx->ws_pair.ptr;
     }
 
     PairParams p;
     p.tiles = d_tiles;
-    p.n_items = n_tiles * splits;
-    p.splits = splits;
+    p.cta_first = (const int32_t *)d_plan;
+    p.work = (const WorkItem *)(d_plan + first_bytes);
     p.stages_total = stages_total;
-    p.stages_per_split = per_split;
     p.flush_stages = flush_stages;
     p.shard = shard_cols;
     p.N = N;
@@ -696,16 +787,16 @@ int pairwise_f32(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t 
     else
         kern = packed ? pairwise_tile_kernel<FUF_MODE_L2, true> : pairwise_tile_kernel<FUF_MODE_L2, false>;
     FUF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    const int grid = std::min<int64_t>(p.n_items, ctx->sm_count);
-    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmap, p);
+    kern<<<plan.grid, NTHREADS, SMEM_BYTES, stream>>>(tmap, p);
     FUF_CUDA(cudaGetLastError());
     ctx->launches += 1;
-    if (splits > 1) {
-        PairParams pr = p;
+    if (!plan.shared.empty()) {
+        const SharedTile *d_shared = (const SharedTile *)(d_plan + first_bytes + work_bytes);
+        const unsigned n_shared = (unsigned)plan.shared.size();
         if (mode == FUF_MODE_L1)
-            reduce_partials_kernel<FUF_MODE_L1><<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd, pr);
+            reduce_partials_kernel<FUF_MODE_L1><<<n_shared, 256, 0, stream>>>(d_tiles, d_shared, d_partial, N, D, ldd, p);
         else
-            reduce_partials_kernel<FUF_MODE_L2><<<n_tiles, 256, 0, stream>>>(d_tiles, d_partial, splits, N, D, ldd, pr);
+            reduce_partials_kernel<FUF_MODE_L2><<<n_shared, 256, 0, stream>>>(d_tiles, d_shared, d_partial, N, D, ldd, p);
         FUF_CUDA(cudaGetLastError());
         ctx->launches += 1;
     }

@@ -110,6 +110,8 @@ def load_library() -> ctypes.CDLL:
         L.fuf_name_index_destroy.argtypes = [vp]
         L.fuf_ingest_gather_csv.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), i32, ctypes.c_char_p, ci, ci, ci, vp, i64,
                                             vp, ctypes.c_char_p, i64, ctypes.c_char_p, i64]
+        L.fuf_debug_pair_plan.argtypes = [i32, i32, i32, i32, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        L.fuf_debug_pair_plan.restype = ci
         L.fuf_launch_count.argtypes = [vp]
         L.fuf_launch_count.restype = i64
         for name in ("fuf_tree_create", "fuf_tree_destroy", "fuf_tree_get_info", "fuf_push_up", "fuf_push_up_f64",

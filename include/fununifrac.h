@@ -394,6 +394,13 @@ int fuf_debug_tree_plan(const int32_t *parent_h, int32_t n, int32_t *parent_loca
                         uint8_t *is_span, int32_t *span_out, int32_t *n_span, int32_t *n_cp, int32_t *contiguous,
                         int32_t *chunk);
 
+/* Test hook, host only (needs no device): the work plan of the all-pairs tile kernel for n_tiles tiles on sm_count SMs —
+ * whole tiles round-robin for the full waves, equal spans of the (tile, stage) space for the last partial wave when
+ * stream_k != 0.  rows_out (may be NULL to query *n_rows): 5 ints per work item (cta, tile, s_begin, s_end, slot);
+ * slot < 0: the item covers the whole tile. */
+int fuf_debug_pair_plan(int32_t n_tiles, int32_t sm_count, int32_t stages_total, int32_t flush_stages, int32_t stream_k,
+                        int32_t *rows_out, int32_t max_rows, int32_t *n_rows, int32_t *grid);
+
 /* Test hook, host only: the per-node plan words of the TMA push-up kernel (see PushNode in csrc/common.cuh),
  * ceil(n / 32) * 32 entries; *usable = 0 (meta_out untouched) when the tree cannot use that kernel. */
 int fuf_debug_push_meta(const int32_t *parent_h, int32_t n, int32_t *meta_out, int32_t *usable);

@@ -29,6 +29,44 @@ def test_library_exports_every_declared_symbol():
     assert L.fuf_padded_samples(1) == 128 and L.fuf_padded_samples(129) == 256
 
 
+@pytest.mark.parametrize("n_tiles,sms", [(3160, 148), (405, 148), (36, 148), (1, 148), (148, 148), (149, 148), (295, 148),
+                                         (820, 140), (7, 4)])
+def test_pair_work_plan_covers_every_stage_once(n_tiles, sms):
+    """The work plan of the all-pairs tile kernel (whole tiles for the full waves + a stream-K tail): every (tile, stage)
+    exactly once, span boundaries on fp32 flush boundaries, shared tiles' slots in ascending stage order, and no CTA
+    more than a few flush units above the mean load."""
+    import ctypes
+    L = engine.load_library()
+    stages, flush = 1876, 16
+    for stream_k in (1, 0):
+        nr, grid = ctypes.c_int32(), ctypes.c_int32()
+        assert L.fuf_debug_pair_plan(n_tiles, sms, stages, flush, stream_k, None, 0, ctypes.byref(nr), ctypes.byref(grid)) == 0
+        rows = np.zeros((nr.value, 5), np.int32)
+        assert L.fuf_debug_pair_plan(n_tiles, sms, stages, flush, stream_k, rows.ctypes.data, nr.value, ctypes.byref(nr),
+                                     ctypes.byref(grid)) == 0
+        assert 1 <= grid.value <= sms and rows[:, 0].max() == grid.value - 1
+        cover = np.zeros((n_tiles, stages), np.int32)
+        load = np.zeros(grid.value, np.int64)
+        slots = {}
+        for c, t, s0, s1, slot in rows:
+            assert 0 <= s0 < s1 <= stages and s0 % flush == 0 and (s1 % flush == 0 or s1 == stages)
+            cover[t, s0:s1] += 1
+            load[c] += s1 - s0
+            whole = s0 == 0 and s1 == stages
+            assert (slot < 0) == whole
+            if slot >= 0:
+                slots.setdefault(t, []).append((slot, s0))
+        assert (cover == 1).all()
+        for t, lst in slots.items():            # consecutive slots, ascending stages
+            assert [a for a, _ in lst] == list(range(lst[0][0], lst[0][0] + len(lst))) and [b for _, b in lst] == sorted(b for _, b in lst)
+        assert sorted(a for lst in slots.values() for a, _ in lst) == list(range(sum(len(v) for v in slots.values())))
+        if stream_k:
+            # no CTA more than a minimal span (4 flush units) + rounding above a perfect deal over all SMs
+            assert load.max() <= n_tiles * stages / sms + 5 * flush, (load.max(), n_tiles * stages / sms)
+        else:
+            assert not slots
+
+
 def test_integration_stub_compiles_and_binds():
     """The ctypes block of INTEGRATION.md (executed against the oracle by the GPU test test_integration_stub_runs) is valid
     Python and every entry point it binds is exported — checked here without a GPU."""
