@@ -334,6 +334,34 @@ def host_timed_steps(env, step, steps, warmup):
     return env.max_over_ranks([max(t0.elapsed_time(t1), wall_ms)])[0] / steps, out
 
 
+def measure_host_links(env):
+    """Host-link rates of this box as the job sees them: every rank copies 4 x 256 MiB between pinned host memory and its
+    GPU at the same time (the ranks' links may share PCIe switches and root ports), best of three trials, summed over the
+    ranks.  GB/s, per direction (each direction measured alone)."""
+    torch = env.torch
+    hp = torch.empty(1 << 26, dtype=torch.float32, pin_memory=True)
+    dp = torch.empty(1 << 26, dtype=torch.float32, device=env.dev)
+    out = {}
+    for name, (dst, src) in (("h2d_gbs", (dp, hp)), ("d2h_gbs", (hp, dp))):
+        dst.copy_(src, non_blocking=True)
+        best = 0.0
+        for _ in range(3):
+            env.barrier()
+            e0, e1 = env.event(), env.event()
+            e0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 4 * hp.numel() * 4 / e0.elapsed_time(e1) / 1e6)
+        t = torch.tensor([best], dtype=torch.float64, device=env.dev)
+        if env.dist is not None:
+            env.dist.all_reduce(t)
+        out[name] = float(t[0])
+    out["note"] = "pinned cudaMemcpy, all ranks at once, summed over the ranks"
+    return out
+
+
 def rel_err_block(D, Dref):
     iu = np.triu_indices(Dref.shape[0], 1)
     den = np.where(Dref[iu] > 0, Dref[iu], 1.0)
@@ -513,7 +541,12 @@ def run_l2(env, args, N=50000, steps=None):
     e2e = None
     need = (job.hi - job.lo) * n * 8 + N * N * 8
     import psutil
-    if psutil.virtual_memory().available > need * (1 if world == 1 else 2) + (16 << 30) and not args.no_e2e:
+    fits = psutil.virtual_memory().available > need * (1 if world == 1 else 2) + (16 << 30) and not args.no_e2e
+    if env.dist is not None:        # one decision for all ranks (the leg is full of collectives)
+        ok = torch.tensor([1 if fits else 0], dtype=torch.int32, device=dev)
+        env.dist.all_reduce(ok, op=env.dist.ReduceOp.MIN)
+        fits = bool(int(ok[0]))
+    if fits:
         e2e_steps = max(1, min(steps, 3))
         X_pin = torch.empty((max(job.hi - job.lo, 1), n), dtype=torch.float64, pin_memory=True)[:job.hi - job.lo]
         X_pin.copy_(X)
@@ -536,6 +569,9 @@ def run_l2(env, args, N=50000, steps=None):
                "api": "fuf_all_pairs_host (C ABI, pinned host float64 profiles in, host float64 matrix out)" if world == 1
                else "sharded.ShardedAllPairs.step_host over the C ABI: pinned host shards in on every rank, one shared "
                     "host matrix out (each rank stores its tile rows over its own PCIe link)"}
+        e2e["host_links"] = measure_host_links(env)
+        e2e["transfer_ms_at_link_rate"] = (e2e["h2d_bytes_per_step"] / e2e["host_links"]["h2d_gbs"] +
+                                           e2e["d2h_bytes_per_step"] / e2e["host_links"]["d2h_gbs"]) / 1e6
         if rank == 0:
             e2e["block_vs_device_matrix_max_rel_diff"] = rel_err_block(Dh_out[np.ix_(sub, sub)], D_blk)[0]
             assert e2e["block_vs_device_matrix_max_rel_diff"] < 1e-9
@@ -669,6 +705,10 @@ def run_l1(env, args):
            "api": "fuf_all_pairs_host (C ABI, pinned host float64 profiles in, host float64 matrix out)" if world == 1
            else "sharded.ShardedAllPairs.step_host over the C ABI: pinned host shards in on every rank, one shared "
            "host matrix out (each rank stores its tile rows over its own PCIe link)"}
+
+    e2e["host_links"] = measure_host_links(env)
+    hl = e2e["host_links"]
+    e2e["transfer_ms_at_link_rate"] = (e2e["h2d_bytes_per_step"] / hl["h2d_gbs"] + e2e["d2h_bytes_per_step"] / hl["d2h_gbs"]) / 1e6
 
     line = None
     if rank == 0:
