@@ -30,9 +30,16 @@
 namespace fuf {
 
 constexpr int TILE = FUF_TILE;    // 128
-constexpr int KC = 16;            // basis entries per pipeline stage
-constexpr int STAGES = 4;
-constexpr int FLUSH_STAGES = 16;  // fold fp32 partials into double every 16 stages = 256 basis entries
+#ifndef FUF_KC
+#define FUF_KC 16
+#endif
+#ifndef FUF_STAGES
+#define FUF_STAGES 4
+#endif
+constexpr int KC = FUF_KC;        // basis entries per pipeline stage (a multiple of 16: the inner loop is unrolled by 16)
+constexpr int STAGES = FUF_STAGES;
+constexpr int FLUSH_STAGES = 256 / KC;  // fold fp32 partials into double every 256 basis entries
+static_assert(KC % 16 == 0 && 256 % KC == 0 && KC <= 256, "KC: a multiple of 16 that divides 256");
 constexpr int NCONS = 256;        // consumer threads (8 warps, 16x16 grid of 8x8 register blocks)
 constexpr int NTHREADS = NCONS + 128;  // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg works per warpgroup)
 constexpr uint32_t STAGE_BYTES = 2u * KC * TILE * sizeof(float);                      // 16 KB
@@ -290,8 +297,10 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
             mbar_wait(full0 + 8 * slot, phase);
             const float *As = stage_base + slot * (STAGE_BYTES / 4);
             const float *Bs = As + KC * TILE;
+#pragma unroll 1
+            for (int k0 = 0; k0 < KC; k0 += 16)
 #pragma unroll
-            for (int k = 0; k < KC; k++) {
+            for (int k = k0; k < k0 + 16; k++) {
                 const float4 a0 = *reinterpret_cast<const float4 *>(As + k * TILE + tx * 4);
                 const float4 a1 = *reinterpret_cast<const float4 *>(As + k * TILE + 64 + tx * 4);
                 const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};

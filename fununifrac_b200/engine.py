@@ -14,7 +14,8 @@ from typing import Iterator, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfununifrac.so")
+# FUF_LIB: another build of the library (kernel-variant experiments, tools/build_variant.sh); the product loads the in-tree one
+LIB_PATH = os.environ.get("FUF_LIB") or os.path.join(_HERE, "csrc", "libfununifrac.so")
 
 MODE_L1, MODE_L2 = 0, 1
 F32, F64 = 0, 1
