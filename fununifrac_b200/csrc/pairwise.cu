@@ -12,8 +12,8 @@
 //     of the (tile, basis entry) space, one span per CTA (stream-K tail: no SM idles through a partial wave);
 //   * warp-specialised: warps 0-7 (256 threads, 2 warpgroups) consume, the third warpgroup donates its
 //     registers (setmaxnreg) and one of its lanes is the TMA producer;
-//   * operand tiles A = PT[k0:k0+16][i0:i0+128], B = PT[k0:k0+16][j0:j0+128] are brought in by TMA
-//     (cp.async.bulk.tensor.3d) into a 4-stage shared-memory ring guarded by full/empty mbarriers;
+//   * operand tiles A = PT[k0:k0+32][i0:i0+128], B = PT[k0:k0+32][j0:j0+128] are brought in by TMA
+//     (cp.async.bulk.tensor.3d) into a 2-stage shared-memory ring (32 KB per stage) guarded by full/empty mbarriers;
 //     out-of-range rows/columns are zero-filled by the TMA unit, so no edge cases in the inner loop;
 //   * each consumer thread owns an 8x8 block of the tile: per basis entry 4 LDS.128 feed
 //     32 FADD2 (d = a - b, packed pairs along j) + 32 FADD2 (acc += |d|)  [L2: 32 FFMA2 acc += d*d];
@@ -30,11 +30,16 @@
 namespace fuf {
 
 constexpr int TILE = FUF_TILE;    // 128
+// Pipeline geometry, measured at N = 10,000 (tools/build_variant.sh, K2 ms per launch): 16 entries x 4 stages 91.35;
+// 16 x 4 with the cross-boundary operand prefetch 91.85; 32 x 2 90.57; 32 x 3 90.81; 32 x 2 with the prefetch 89.98.
 #ifndef FUF_KC
-#define FUF_KC 16
+#define FUF_KC 32
 #endif
 #ifndef FUF_STAGES
-#define FUF_STAGES 4
+#define FUF_STAGES 2
+#endif
+#ifndef FUF_PREFETCH
+#define FUF_PREFETCH 1
 #endif
 constexpr int KC = FUF_KC;        // basis entries per pipeline stage (a multiple of 16: the inner loop is unrolled by 16)
 constexpr int STAGES = FUF_STAGES;
@@ -292,6 +297,65 @@ pairwise_tile_kernel(const __grid_constant__ CUtensorMap tmap, const PairParams 
             }
         };
 
+#if FUF_PREFETCH
+        if (PACKED) {
+            // The operands of the next basis entry are fetched before the arithmetic of the current one — also across the
+            // 16-entry unroll blocks and across stage boundaries (the next stage's barrier is awaited during the last
+            // entry of the current stage), so the FMA pipe never waits for a shared-memory round trip at a boundary.
+            float4 na0, na1;
+            ulonglong2 nb0, nb1;
+            {
+                const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
+                mbar_wait(full0 + 8 * slot, phase);
+                const float *As = stage_base + slot * (STAGE_BYTES / 4);
+                const float *Bs = As + KC * TILE;
+                na0 = *reinterpret_cast<const float4 *>(As + tx * 4);
+                na1 = *reinterpret_cast<const float4 *>(As + 64 + tx * 4);
+                nb0 = *reinterpret_cast<const ulonglong2 *>(Bs + ty * 4);
+                nb1 = *reinterpret_cast<const ulonglong2 *>(Bs + 64 + ty * 4);
+            }
+            for (int st = s_begin; st < s_end; ++st, ++it) {
+                const uint32_t slot = it % STAGES;
+                const float *As = stage_base + slot * (STAGE_BYTES / 4);
+                const float *Bs = As + KC * TILE;
+#pragma unroll 1
+                for (int k0 = 0; k0 < KC; k0 += 16)
+#pragma unroll
+                    for (int k = k0; k < k0 + 16; k++) {
+                        const float a[8] = {na0.x, na0.y, na0.z, na0.w, na1.x, na1.y, na1.z, na1.w};
+                        const uint64_t b[4] = {nb0.x, nb0.y, nb1.x, nb1.y};
+                        const float *An = As + (k + 1) * TILE, *Bn = Bs + (k + 1) * TILE;
+                        bool fetch = true;
+                        if (k + 1 == KC) {
+                            fetch = st + 1 < s_end;
+                            if (fetch) {
+                                const uint32_t nslot = (it + 1) % STAGES, nphase = ((it + 1) / STAGES) & 1u;
+                                mbar_wait(full0 + 8 * nslot, nphase);
+                                An = stage_base + nslot * (STAGE_BYTES / 4);
+                                Bn = An + KC * TILE;
+                            }
+                        }
+                        if (fetch) {
+                            na0 = *reinterpret_cast<const float4 *>(An + tx * 4);
+                            na1 = *reinterpret_cast<const float4 *>(An + 64 + tx * 4);
+                            nb0 = *reinterpret_cast<const ulonglong2 *>(Bn + ty * 4);
+                            nb1 = *reinterpret_cast<const ulonglong2 *>(Bn + 64 + ty * 4);
+                        }
+#pragma unroll
+                        for (int m = 0; m < 8; m++) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint64_t d = pk_sub_bcast(a[m], b[q]);
+                                acc2[m][q] = (MODE == FUF_MODE_L1) ? pk_add_abs(acc2[m][q], d) : pk_fma_sq(acc2[m][q], d);
+                            }
+                        }
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+                if ((st - s_begin + 1) % p.flush_stages == 0) flush();
+            }
+        } else
+#endif
         for (int st = s_begin; st < s_end; ++st, ++it) {
             const uint32_t slot = it % STAGES, phase = (it / STAGES) & 1u;
             mbar_wait(full0 + 8 * slot, phase);
