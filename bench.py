@@ -607,7 +607,9 @@ def run_l2(env, args, N=50000, steps=None):
                                                        else "gram_pair_kernel (cta_group::2)")
                                    + " (tcgen05.mma kind::i8, 10 digit products per term)",
                          "achieved": achieved, "peak": i8_peak, "unit": "TOP/s", "frac": achieved / i8_peak if i8_peak else None,
-                         "traffic": None, "ms_per_launch": k_ms,
+                         "traffic": profile_traffic(PROFILE_GRAM) if (world == 1 and N == 50000) else None,
+                         "traffic_source": f"profiles/{PROFILE_GRAM} (ncu --set full, N = 50,000, one GPU)",
+                         "ms_per_launch": k_ms,
                          "peak_source": "measured in this run: fuf_i8_mma_peak, the kernel's own tcgen05.mma kind::i8 "
                                         "(operands resident in shared memory, every SM), "
                                         + ("sustained over 1.5 s (timed region > 1 s, power-capped)" if long_run else "burst"),
@@ -823,6 +825,7 @@ def run_cli(env, args):
 
 PROFILE_PAIRWISE = "r2_ncu_full_pairwise.csv"
 PROFILE_PUSHUP = "r2_ncu_full_pushup.csv"
+PROFILE_GRAM = "r2_ncu_full_gram_pair_N50000.csv"
 
 
 def main():
