@@ -449,6 +449,7 @@ struct PairTile {
     int32_t ti, b;       // row tile, column-tile pair (2b, 2b + 1)
     int32_t out_row0, pad;   // pad: bits 0-11 dependency + 1 (0 = none), bits 12-31 segment + 1 (0 = none)
 };
+constexpr int32_t GRAM_STRIP = 12;                    // tile rows per rasterisation strip (74 CTA pairs ~ 12 rows x 6 column pairs)
 constexpr uint32_t GRAM_SEG_UNITS = 2 * NEPI_WARPS;   // a finished item advances its segment counter by this much
 static_assert(GRAM_SEG_UNITS == FUF_GRAM_SEG_UNITS, "include/fununifrac.h documents the count per item");
 
@@ -1324,23 +1325,41 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     if (use_pairs) {
         // CTA pairs: work item = row tile x two column tiles (2b, 2b+1); the half below the diagonal is computed and dropped
         std::vector<PairTile> ptiles;
-        for (int32_t c = 0; c < n_trows; c++) {
-            const int32_t t = full ? c : tile_rows_h[c];
-            for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, full ? t * TILE : c * TILE, 0});
+        const bool segmented = segs && segs->seg_done && segs->n_wanted > 0 && full;
+        int32_t per = 0;   // tile rows per completion segment
+        if (segmented) {
+            const int32_t n_seg = (int32_t)std::min<int64_t>(std::min(segs->n_wanted, 4000), n_trows);
+            per = (n_trows + n_seg - 1) / n_seg;
         }
-        if (segs && segs->seg_done && segs->n_wanted > 0 && full) {
+        if (full) {
+            // L2 rasterisation (as in pairwise_f32): the 74 CTA pairs in flight stream their digit-plane panels at the
+            // same pace, so a panel shared by several of their items is fetched from DRAM once.  Row-major order put one
+            // tile row and 74 column pairs into a wave — 149 panels of 17 MB, 1.15 TB of DRAM reads per launch at
+            // N = 50,000 (ncu: 4.5 TB/s, L2 hit 38 %) —; strips of ~12 tile rows walked column pair by column pair make it
+            // ~12 rows x 6 pairs = 24 panels.  With completion segments a strip is a whole number of segments.
+            const int32_t S = per > 0 ? per * ((GRAM_STRIP + per - 1) / per) : GRAM_STRIP;
+            for (int32_t r0 = 0; r0 < n_trows; r0 += S)
+                for (int32_t b = r0 / 2; 2 * b < tiles_per_dim; b++)
+                    for (int32_t t = r0; t < std::min(n_trows, r0 + S); t++)
+                        if (b >= t / 2) ptiles.push_back(PairTile{t, b, t * TILE, 0});
+        } else {
+            for (int32_t c = 0; c < n_trows; c++) {
+                const int32_t t = tile_rows_h[c];
+                for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, c * TILE, 0});
+            }
+        }
+        if (segmented) {
             // completion segments of equally many tile rows: once segment s (and every earlier one) is counted complete,
             // rows [row_end[s-1], row_end[s]) x 128 of D are final in ALL columns — right of the diagonal by the segment's
             // own tiles, left of it by the mirror stores of the earlier segments — and leave as one contiguous copy
-            const int32_t n_seg = (int32_t)std::min<int64_t>(std::min(segs->n_wanted, 4000), n_trows);
-            const int32_t per = (n_trows + n_seg - 1) / n_seg;
-            size_t at = 0;
             for (int32_t t0 = 0; t0 < n_trows; t0 += per) {
-                const int32_t t1 = std::min(n_trows, t0 + per), seg = (int32_t)segs->row_end.size();
-                uint32_t in_seg = 0;
-                for (; at < ptiles.size() && ptiles[at].ti < t1; at++, in_seg++) ptiles[at].pad = (seg + 1) << 12;
-                segs->row_end.push_back(t1);
-                segs->expected.push_back(in_seg * GRAM_SEG_UNITS);
+                segs->row_end.push_back(std::min(n_trows, t0 + per));
+                segs->expected.push_back(0);
+            }
+            for (PairTile &pt : ptiles) {
+                const int32_t seg = pt.ti / per;
+                pt.pad = (seg + 1) << 12;
+                segs->expected[seg] += GRAM_SEG_UNITS;
             }
         }
         static_assert(PLANE_BYTES == 8192 && TILE == 128, "umma_block10 hard-codes the plane and accumulator strides");

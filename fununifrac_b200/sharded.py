@@ -11,9 +11,14 @@ without any collective inside the arithmetic.  Weighted L1 (and the direct --L2 
    (r, r+1) .. (r, r+G/2) (the last one split with its partner), so it needs only G/2 of the G-1 remote shards.  A copy
    stream pulls them from the peers' buffers over NVLink, one after the other, and raises a flag behind each copy.
 4. ONE launch of ``fuf_pairwise_tiles`` walks the rank's tiles in arrival order — diagonal block first, which needs
-   nothing remote; a tile whose shard is still in flight makes the kernel's producer warp wait for the flag — and stores
-   every tile, and its mirror, straight into the full matrix: rank 0's device matrix (mapped by every rank), or with
-   host buffers (``step_host``) the page-locked host matrix the ranks share.  Nothing is packed, gathered or assembled.
+   nothing remote; a tile whose shard is still in flight makes the kernel's producer warp wait for the flag.  Rank 0
+   stores every tile, and its mirror, straight into its own matrix.  Every other rank — and every rank when the result
+   goes to host memory (``step_host``) — stores into a matrix of its own, and a copy engine forwards each finished
+   *completion segment* (one rasterisation strip of a shard-pair block: its rectangle and the mirrored one,
+   ``segment_regions``) into rank 0's matrix over NVLink, or into the page-locked host matrix the ranks share over the
+   rank's own PCIe link, while the launch works on the next segment: the kernel counts finished tiles per segment, the
+   copy stream waits on the counter (``fuf_stream_wait_u32``) and issues pitched copies (``fuf_copy2d_async``).
+   Nothing is packed, gathered or assembled, and no kernel stores across NVLink or PCIe.
    The refinement criterion is evaluated in the tile epilogues; the flagged-pair count is all-reduced (NCCL, 8 bytes:
    the end-of-step barrier), and only if it is non-zero are the float64 profiles pushed up, exchanged and the listed
    pairs recomputed (``fuf_refine_list``).
@@ -21,8 +26,8 @@ without any collective inside the arithmetic.  Weighted L1 (and the direct --L2 
 --L2 from 512 samples on (tensor-core Gram kernel) takes the same form in phases: column statistics of the own shard,
 all-reduced, so that every rank derives the same plan (``fuf_gram_colstats`` / ``fuf_gram_plan``); int8 digit planes of
 the own shard only (``fuf_gram_digits``); the copy stream pulls the planes — not the fp32 operands — of the G/2 shards
-the rank's tiles touch; one launch of the CTA-pair tile kernel (``fuf_gram_tiles``) with the same arrival flags, in-place
-stores and epilogue flags.  ``peer=False`` keeps the older collective form (all-gather of the pushed blocks, tile rows
+the rank's tiles touch; one launch of the CTA-pair tile kernel (``fuf_gram_tiles``) with the same arrival flags,
+completion segments and epilogue flags.  ``peer=False`` keeps the older collective form (all-gather of the pushed blocks, tile rows
 dealt boustrophedon-wise, packed gather to rank 0 or per-rank stores into the shared host matrix).
 
 The compute calls are injected (``ops``) so that the partition / exchange logic is testable on CPU with the
@@ -30,12 +35,12 @@ The compute calls are injected (``ops``) so that the partition / exchange logic 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence  # noqa: F401
 
 TILE = 128
-import os as _os
-
-STRIP = int(_os.environ.get("FUF_STRIP", "12"))        # tile rows per rasterisation strip: floor(sqrt(148 SMs))
+# tile rows per rasterisation strip: floor(sqrt(148 SMs)); FUF_STRIP overrides it for experiments (1000 = row-major blocks)
+STRIP = int(os.environ.get("FUF_STRIP", "12"))
 
 
 def shard_size(N: int, world: int, multiple: int = TILE) -> int:
@@ -402,7 +407,6 @@ class ShardedAllPairs:
     def _local_matrix(self, target):
         """Where the tile kernels store: the target itself when it is this device's memory (rank 0 of ``step``), else the
         rank's own matrix, from which the copy engine forwards the finished segments."""
-        import os
         if target is self.D or os.environ.get("FUF_NO_FORWARD"):      # (debug switch: the kernels store in place everywhere)
             return target
         if self.D_local is None:
