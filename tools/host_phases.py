@@ -49,20 +49,19 @@ def main():
     for it in range(3):
         job.step_host(X_pin, shared)
     res = {}
+    D_rows = torch.empty((max(1, N // world), N), dtype=torch.float64, device=f"cuda:{lr}")   # this rank's share of the matrix
+    D_pin = torch.empty(D_rows.shape, dtype=torch.float64, pin_memory=True)
     for it in range(3):
-        res["h2d"] = timed(lambda: stage.copy_(X_pin, non_blocking=True))
-        res["compute"] = timed(lambda: job._compute(stage, lambda name: None))
-        for part in ("0", "1", "2"):
-            os.environ["FUF_STORE_PART"] = part
-            res["store" + part] = timed(lambda: ctx.store_tile_rows_host(job.blocks, job.rows, N, shared.array))
-        os.environ["FUF_STORE_PART"] = "0"
+        res["h2d of the shard"] = timed(lambda: stage.copy_(X_pin, non_blocking=True))
+        res["step (device)"] = timed(lambda: job.step(stage))
+        res["d2h of 1/G of D"] = timed(lambda: D_pin.copy_(D_rows, non_blocking=True))
         res["step_host"] = timed(lambda: job.step_host(X_pin, shared))
     out = torch.tensor([[a, b] for a, b in res.values()], dtype=torch.float64, device=f"cuda:{lr}")
     allr = [torch.zeros_like(out) for _ in range(world)]
     dist.all_gather(allr, out)
     if rank == 0:
         for i, k in enumerate(res):
-            print(f"{k:10s} own ms per rank: " + " ".join(f"{float(a[i, 0]):7.2f}" for a in allr) +
+            print(f"{k:18s} own ms per rank: " + " ".join(f"{float(a[i, 0]):7.2f}" for a in allr) +
                   f"   | to barrier: {max(float(a[i, 1]) for a in allr):7.2f}", flush=True)
     shared.close()
     dist.destroy_process_group()

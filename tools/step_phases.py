@@ -27,9 +27,8 @@ def main():
     X = bench.device_profiles(leaves, len(inp.basis), job.hi - job.lo, seed=1 + rank)
     for _ in range(3):
         job.step(X)
-    names = ["start", "push_begin", "push_end", "pair_begin", "pair_end", "refine_end", "gather_end", "end"]
-    acc = torch.zeros(len(names) - 1, dtype=torch.float64)
-    reps = 5
+    order = ["start", "push_begin", "push_end", "pair_begin", "pair_end", "refine_end", "gather_end", "end"]
+    reps, acc, names = 5, None, None
     for _ in range(reps):
         ev = {}
 
@@ -41,13 +40,14 @@ def main():
         torch.cuda.synchronize()
         job.step(X, mark)
         torch.cuda.synchronize()
-        acc += torch.tensor([ev[a].elapsed_time(ev[b]) for a, b in zip(names, names[1:])], dtype=torch.float64)
+        names = [n for n in order if n in ev]          # (the peer form has no gather phase)
+        t = torch.tensor([ev[a].elapsed_time(ev[b]) for a, b in zip(names, names[1:])], dtype=torch.float64)
+        acc = t if acc is None else acc + t
     acc /= reps
     out = [torch.zeros_like(acc).cuda() for _ in range(world)]
     dist.all_gather(out, acc.cuda())
     if rank == 0:
-        print(f"{what} N={N} world={world}: phase ms per rank (centre+bcast | push-up | all-gathers | pairwise | count/refine | "
-              f"pack+gather | assemble)")
+        print(f"{what} N={N} world={world} peer={job.use_peer}: phase ms per rank: " + " | ".join(f"{a}->{b}" for a, b in zip(names, names[1:])))
         for r, t in enumerate(out):
             print(f"  rank {r}: " + "  ".join(f"{float(v):7.3f}" for v in t) + f"   sum {float(t.sum()):7.3f}")
     dist.destroy_process_group()
