@@ -512,6 +512,18 @@ class TreeContext:
         _check(self._lib.fuf_copy2d_async(self.handle, dptr + off_d, dst_ld * 8, src.data_ptr() + off_s, src.stride(0) * 8,
                                           (c1 - c0) * 8, r1 - r0, st), "fuf_copy2d_async")
 
+    def copy_cols_async(self, dst, src, c0: int, c1: int, stream=None):
+        """dst[:, c0:c1] = src[:, c0:c1] for two 2-D tensors of the same dtype and shape with unit inner stride (device or
+        peer mappings) by one pitched copy-engine transfer (``fuf_copy2d_async``)."""
+        torch = _torch()
+        assert dst.dim() == 2 and dst.shape == src.shape and dst.dtype == src.dtype and dst.stride(1) == 1 and src.stride(1) == 1
+        if c1 <= c0:
+            return
+        es = dst.element_size()
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        _check(self._lib.fuf_copy2d_async(self.handle, dst.data_ptr() + c0 * es, dst.stride(0) * es, src.data_ptr() + c0 * es,
+                                          src.stride(0) * es, (c1 - c0) * es, dst.shape[0], st), "fuf_copy2d_async")
+
     def pairwise_tiles(self, PS, N: int, mode: int, tiles, dep_flags, epoch: int, D, shard: int, shard_stride: int,
                        err_stat=None, flag_list=None, list_cap: int = 0, kappa: float = 0.0, segments=None, seg_done=None):
         """``fuf_pairwise_tiles``: tiles (ti, tj, dependency) of the upper triangle, written in place into the full

@@ -41,6 +41,7 @@ from typing import List, Optional, Sequence  # noqa: F401
 TILE = 128
 # tile rows per rasterisation strip: floor(sqrt(148 SMs)); FUF_STRIP overrides it for experiments (1000 = row-major blocks)
 STRIP = int(os.environ.get("FUF_STRIP", "12"))
+N_PULL_BANDS = 4        # bands per shard of the host-buffer form with band-wise pulls
 
 
 def shard_size(N: int, world: int, multiple: int = TILE) -> int:
@@ -168,6 +169,68 @@ def peer_tile_plan(N: int, world: int, rank: int, shard: Optional[int] = None, s
             pulls.append(q)
             tiles += block
     return (tiles, pulls, seg) if segments else (tiles, pulls)
+
+
+def shard_bands(shard: int, n_bands: int):
+    """Bands of whole tiles of one shard, the same for every rank: [(first tile, end tile)] relative to the shard's first
+    tile.  (The last shard may be ragged: its later bands then hold fewer valid tiles, or none.)"""
+    ts = shard // TILE
+    return [(ts * b // n_bands, ts * (b + 1) // n_bands) for b in range(n_bands)]
+
+
+def banded_pull_plan(N: int, world: int, rank: int, shard: int, n_bands: int):
+    """The rank's tiles of ``peer_tile_plan`` regrouped for a job whose shards arrive band by band (every rank uploads and
+    pushes up its own shard in ``n_bands`` bands and announces each band to the ranks that need it).
+
+    A tile needs one band of the own shard and — off the diagonal block — one band of a remote shard; it joins step
+    max(own band, remote band), the first moment both are in.  Returns (steps, pulls, n_segments): ``steps[s]`` is the launch
+    of step s as (tiles, seg) with tiles = (ti, tj, dependency) and dependency = q * n_bands + remote band (or -1: the
+    diagonal block); ``seg`` numbers the completion segments in launch order, one per box of tiles: the column band of the
+    diagonal block, and per remote shard the boxes {own band s} x {remote bands <= s} and {own bands < s} x {remote band s}."""
+    ts = shard // TILE
+    T = (N + TILE - 1) // TILE
+    bands = shard_bands(shard, n_bands)
+
+    def band_of(t):                      # band of global tile index t inside its shard
+        local = t % ts
+        for b, (lo, hi) in enumerate(bands):
+            if lo <= local < hi:
+                return b
+        raise AssertionError(t)
+
+    tiles, pulls = peer_tile_plan(N, world, rank, shard)
+    steps = [([], []) for _ in range(n_bands)]
+    boxes = {}                           # (step, remote shard or -1, which box) -> tiles
+    for ti, tj, dep in tiles:
+        if dep < 0:
+            boxes.setdefault((band_of(tj), -1, 0), []).append((ti, tj, -1))
+            continue
+        own_t, rem_t = (ti, tj) if ti // ts == rank else (tj, ti)
+        bo, br = band_of(own_t), band_of(rem_t)
+        step = max(bo, br)
+        boxes.setdefault((step, dep, 0 if bo == step else 1), []).append((ti, tj, dep * n_bands + br))
+    n_seg = 0
+    order = [-1] + pulls
+    for s in range(n_bands):
+        for q in order:
+            for which in (0, 1):
+                box = boxes.get((s, q, which))
+                if not box:
+                    continue
+                # rasterise the box like peer_tile_plan does: strips of STRIP tile rows, column by column
+                rows = sorted(set(t[0] for t in box))
+                by = {}
+                for t in box:
+                    by.setdefault((t[0], t[1]), t)
+                cols = sorted(set(t[1] for t in box))
+                for r0 in range(0, len(rows), STRIP):
+                    strip = rows[r0:r0 + STRIP]
+                    part = [by[(ti, tj)] for tj in cols for ti in strip if (ti, tj) in by]
+                    steps[s][0].extend(part)
+                    steps[s][1].extend([n_seg] * len(part))
+                n_seg += 1
+    assert sum(len(st[0]) for st in steps) == len(tiles) and T >= 0
+    return steps, pulls, n_seg
 
 
 def refine_budget(N: int) -> int:
@@ -355,14 +418,22 @@ class ShardedAllPairs:
         else:
             self.PS_buf = ops.peer_alloc((world, n, sh), "float32")
             self.PS = self.PS_buf.tensor
-            dist.all_gather_object(handles, (self.PS_buf.handle, self.D_buf.handle if rank == 0 else None))
+            # band-wise pulls of the host-buffer form: the statistics travel with the bands (peer-readable), and every rank
+            # announces a pushed-up band by a 4-byte copy into the `ready` words of the ranks that pull its shard
+            self.stat_buf = ops.peer_alloc((world * sh,), "float64")
+            self.ready_buf = ops.peer_alloc((world * N_PULL_BANDS,), "int32")
+            dist.all_gather_object(handles, (self.PS_buf.handle, self.stat_buf.handle, self.ready_buf.handle,
+                                             self.D_buf.handle if rank == 0 else None))
             self.peer_PS = {q: ops.peer_open(handles[q][0], (world, n, sh), "float32") for q in self.pulls}
+            self.peer_stat = {q: ops.peer_open(handles[q][1], (world * sh,), "float64") for q in self.pulls}
+            self.consumers = [q for q in range(world) if q != rank and rank in peer_tile_plan(N, world, q, sh)[1]]
+            self.peer_ready = {q: ops.peer_open(handles[q][2], (world * N_PULL_BANDS,), "int32") for q in self.consumers}
         if rank != 0:
             self.D_buf = ops.peer_open(handles[0][-1], (N, N), "float64")
         self.D = self.D_buf.tensor if rank == 0 else None
         self.D_target = self.D_buf.tensor         # rank 0's matrix, as seen from this rank
         self.P64S = None
-        self.stat = ops.empty((world * sh,), "float64")
+        self.stat = ops.empty((world * sh,), "float64") if self.use_gram else self.stat_buf.tensor
         self.center = ops.empty((n,), "float64")
         self.flags = ops.empty((world,), "int32")                         # arrival flag per shard
         self.list_cap = refine_budget(N)
@@ -401,7 +472,28 @@ class ShardedAllPairs:
             tiles_b += self.offdiag_tiles
             seg_b += [4 + sg - first_off for t, sg in zip(self.tiles, self.seg) if t[2] >= 0]
             self.plan_banded = _SegmentPlan(tiles_b, seg_b, segment_regions(tiles_b, seg_b, N), 1)
-        self.seg_done = ops.empty((max(1, self.plan.n_seg, self.plan_banded.n_seg if self.plan_banded else 0),), "int32")
+        # host-buffer form with band-wise pulls (weighted L1, direct --L2): see _compute_peer_band_pulls
+        self.bp = None
+        nb = N_PULL_BANDS
+        if not self.use_gram and sh // TILE >= nb and os.environ.get("FUF_BAND_PULLS", "1") != "0":
+            steps, _, _ = banded_pull_plan(N, world, rank, sh, nb)
+            work = [t for st in steps for t in st[0]]
+            work_seg = [g for st in steps for g in st[1]]
+            plan = _SegmentPlan(work, work_seg, segment_regions(work, work_seg, N), 1)
+            step_range, seg_range, at = [], [], 0
+            for tl, sg in steps:
+                step_range.append((at, at + len(tl)))
+                seg_range.append((sg[0], sg[-1] + 1) if sg else (0, 0))
+                at += len(tl)
+            cols = [(lo * TILE, hi * TILE) for lo, hi in shard_bands(sh, nb)]            # columns of a shard buffer
+            rows_own = self.hi - self.lo
+            self.bp = {"plan": plan, "step_range": step_range, "seg_range": seg_range, "cols": cols,
+                       "own": [(min(rows_own, c0), min(rows_own, c1)) for c0, c1 in cols]}    # rows of the own samples
+            self.ready = self.ready_buf.tensor
+            self.epoch_word = ops.empty((1,), "int32")
+            self.band_flags = ops.empty((world * nb,), "int32")
+        self.seg_done = ops.empty((max(1, self.plan.n_seg, self.plan_banded.n_seg if self.plan_banded else 0,
+                                       self.bp["plan"].n_seg if self.bp else 0),), "int32")
         dist.barrier()
 
     def _local_matrix(self, target):
@@ -418,7 +510,7 @@ class ShardedAllPairs:
         per finished rectangle from the rank's matrix to the target (peer GPU or page-locked host memory)."""
         ops = self.ops
         for sg in range(first_seg, plan.n_seg if last_seg is None else last_seg):
-            ops.stream_wait_u32(self.seg_done, sg, plan.expected[sg], self.d2h_stream)
+            ops.stream_wait_u32(self.seg_done, sg, plan.expected[sg], self.d2h_stream, exact=True)
             for r0, r1, c0, c1 in plan.regions[sg]:
                 ops.copy_block(target, D_comp, (r0, r1), (c0, c1), self.d2h_stream)
 
@@ -498,6 +590,8 @@ class ShardedAllPairs:
             if host_src is not None:
                 self.ops.to_device(host_src, X_local)
             return self._compute_peer_gram(X_local, D_target, mark)
+        if host_src is not None and self.bp is not None:
+            return self._compute_peer_band_pulls(X_local, D_target, mark, host_src)
         ops, N, mode, r, sh, n, dist = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n, self.dist
         self.epoch += 1
         own = slice(r * sh, (r + 1) * sh)
@@ -563,6 +657,78 @@ class ShardedAllPairs:
         mark("pair_end")
         # the next step's pulls and push-up must not start before everybody is done with this step's: the all-reduce of
         # the flagged-pair count is that barrier (and tells every rank whether the float64 pass is needed)
+        self.flagged.copy_(self.flag_list[:1])
+        dist.all_reduce(self.flagged)
+        self._pending = True
+        mark("refine_end")
+
+    def _compute_peer_band_pulls(self, X_local, D_target, mark, host_src):
+        """Host-buffer form of the peer step with BAND-WISE pulls (weighted L1, direct --L2).
+
+        Every rank uploads its shard in N_PULL_BANDS bands of whole tiles.  As soon as band s has landed it is pushed up
+        and announced: a 4-byte copy of the step's epoch into the ``ready`` word (shard, band) of every rank that pulls
+        this shard.  The copy stream of such a rank waits for that word (cuStreamWaitValue32), pulls the band — its columns
+        of the operand buffer and its slice of the statistics — over NVLink and raises the arrival flag the tile kernel
+        polls.  Step s then launches the tiles that became computable with it: the column band s of the diagonal block, and
+        of every shard-pair block the boxes {own band s} x {remote bands <= s} and {own bands < s} x {remote band s}
+        (``banded_pull_plan``).  Off-diagonal tiles therefore run while later bands are still crossing PCIe, instead of
+        after every rank's complete upload; finished boxes leave for the host as completion segments.
+
+        Submission order (it keeps the scheme free of deadlocks even when streams share a hardware queue): per step first
+        the announcement, then the waits and pulls of the copy stream, then the tile launch — no wait is ever queued ahead
+        of work needed to satisfy it, here or (by induction over the steps) on a peer."""
+        ops, N, mode, r, sh, n, dist = self.ops, self.N, self.mode, self.rank, self.shard, self.ops.n, self.dist
+        bp, nb = self.bp, N_PULL_BANDS
+        plan = bp["plan"]
+        self.epoch += 1
+        own = slice(r * sh, (r + 1) * sh)
+        stat = self.stat if self.do_refine else None
+        flist = self.flag_list if self.do_refine else None
+        ops.zero_(self.flag_list[:1])
+        D_comp = self._local_matrix(D_target)
+        forward = D_comp is not D_target
+        if forward:
+            self._begin_segments()
+        ops.fill_(self.epoch_word, self.epoch)
+        mark("start")
+        events = []
+        for s0, s1 in bp["own"]:                   # all uploads are queued up front on the copy stream
+            if s1 > s0:
+                ops.to_device(host_src[s0:s1], X_local[s0:s1], self.copy_stream)
+            events.append(ops.record_event(self.copy_stream))
+        ops.stream_wait(None, events[0])
+        if r == 0:
+            ops.push_up_center(X_local[:bp["own"][0][1]], mode, self.center)
+        dist.broadcast(self.center, src=0)
+        mark("push_begin")
+        for s in range(nb):
+            s0, s1 = bp["own"][s]
+            c0, c1 = bp["cols"][s]
+            ops.stream_wait(None, events[s])
+            if s1 > s0:
+                ops.push_up(X_local[s0:s1], mode, self.PS[r], s0, self.center, None, self.stat[own])
+            for q in self.consumers:               # announce the band (also an empty one: nobody may wait forever)
+                ops.copy_async(self.peer_ready[q].tensor[r * nb + s:r * nb + s + 1], self.epoch_word, None)
+            for q in self.pulls:
+                ops.stream_wait_u32(self.ready, q * nb + s, self.epoch, self.copy_stream)
+                ops.copy_cols(self.PS[q], self.peer_PS[q].tensor[q], c0, c1, self.copy_stream)
+                ops.copy_async(self.stat[q * sh + c0:q * sh + c1], self.peer_stat[q].tensor[q * sh + c0:q * sh + c1],
+                               self.copy_stream)
+                ops.stream_write_u32(self.band_flags, q * nb + s, self.epoch, self.copy_stream)
+            a, b = bp["step_range"][s]
+            if b > a:
+                ops.pairwise_tiles(self.PS, N, mode, plan.slice(a, b), self.band_flags, self.epoch, D_comp, sh, n * sh, stat,
+                                   flist, self.list_cap, plan.seg_slice(a, b) if forward else None,
+                                   self.seg_done if forward else None)
+                if forward:
+                    self._forward_segments(plan, D_comp, D_target, *bp["seg_range"][s])
+        mark("push_end")
+        self._x_local = X_local
+        mark("pair_begin")
+        if forward:
+            self._end_segments()
+        mark("pair_end")
+        # the next step's pulls and push-ups must not start before everybody is done with this step's (see _compute_peer)
         self.flagged.copy_(self.flag_list[:1])
         dist.all_reduce(self.flagged)
         self._pending = True
@@ -844,8 +1010,16 @@ class CudaOps:
         self.ctx.pairwise_tiles(PS, N, mode, self._as_np(tiles, 3), flags, epoch, D, shard, shard_stride, stat, flag_list,
                                 list_cap, segments=None if seg is None else self._as_np(seg, 1), seg_done=seg_done)
 
-    def stream_wait_u32(self, words, index, value, stream):
+    def stream_wait_u32(self, words, index, value, stream, exact=False):
         self.ctx.stream_wait_u32(words, index, value, stream)
+
+    def fill_(self, t, value):
+        t.fill_(value)
+
+    def copy_cols(self, dst, src, c0, c1, stream):
+        """dst[:, c0:c1] = src[:, c0:c1] for two [rows, cols] buffers of the same layout (a band of a shard's operands,
+        pulled from the peer that owns it): one pitched copy-engine transfer."""
+        self.ctx.copy_cols_async(dst, src, c0, c1, stream)
 
     def copy_block(self, target, src, rows, cols, stream):
         """target[rows, cols] = src[rows, cols]; ``target`` is an N x N tensor (peer mapping) or the raw device-side pointer

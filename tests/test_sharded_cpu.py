@@ -124,10 +124,26 @@ class OracleOps:
 
     gram_seg_units = 16
 
-    def stream_wait_u32(self, words, index, value, stream):
-        # the stand-in's "kernels" have run by the time the waits are queued: the counter must sit exactly at its target
-        assert int(words[index]) == value, (index, int(words[index]), value)
+    def stream_wait_u32(self, words, index, value, stream, exact=False):
+        if exact:
+            # completion counters: the stand-in's "kernels" have run by the time the waits are queued, so the counter must
+            # sit exactly at its target
+            assert int(words[index]) == value, (index, int(words[index]), value)
+        else:
+            # band announcements come from another process (shared memory): really wait, bounded
+            import time
+            t0 = time.time()
+            while int(words[index]) - value < 0:
+                assert time.time() - t0 < 120, f"band announcement {index} never arrived"
+                time.sleep(0.001)
         self.waits = getattr(self, "waits", 0) + 1
+
+    def fill_(self, t, value):
+        t.fill_(value)
+
+    def copy_cols(self, dst, src, c0, c1, stream):
+        self.pulled_bands = getattr(self, "pulled_bands", 0) + 1
+        dst[:, c0:c1] = src[:, c0:c1]
 
     def copy_block(self, target, src, rows, cols, stream):
         (r0, r1), (c0, c1) = rows, cols
@@ -348,6 +364,8 @@ def _worker(rank, world, port, N, l2, out_path, peer):
         shared.array.fill(np.nan)
         dist.barrier()
         Dh = job.step_host(X[job.lo:job.hi], shared)
+        if peer and getattr(job, "bp", None) is not None:      # band-wise pulls: every band of every pulled shard, once
+            assert getattr(ops, "pulled_bands", 0) == len(job.pulls) * sharded.N_PULL_BANDS
         want = torch.zeros(1, dtype=torch.float64)
         if rank == 0:
             want[0] = float(np.abs(got).sum())
@@ -363,7 +381,8 @@ def _worker(rank, world, port, N, l2, out_path, peer):
 
 @pytest.mark.parametrize("world,N,l2,peer", [(2, 300, False, True), (3, 700, False, True), (4, 400, True, True),
                                              (3, 100, False, True), (2, 300, False, False), (2, 129, True, False),
-                                             (3, 900, True, True), (2, 520, True, True), (2, 2100, False, True)])
+                                             (3, 900, True, True), (2, 520, True, True), (2, 2100, False, True),
+                                             (4, 2300, False, True), (3, 1600, False, True)])
 def test_sharded_exchange_gloo(world, N, l2, peer, tmp_path, monkeypatch):
     """peer=True: the shard-pair form (NVLink pulls + in-place stores, here over shared memory); peer=False: the
     collective form (all-gather, tile rows, packed gather) the Gram path still uses."""
@@ -416,3 +435,40 @@ def test_completion_segments_tile_the_matrix_once():
             items, item_seg = sharded.gram_items(tiles, seg)
             assert len(items) == len(item_seg) == len(set((i[0], i[1]) for i in items))
         assert (tcover == 1).all() and (cover is None or (cover == 1).all()), (N, world)
+
+
+def test_banded_pull_plan():
+    """Band-wise pulls: every tile of the triangle exactly once over ranks and steps; a tile sits in the step at which both
+    of its bands are in, its dependency names the remote band; the completion segments of all ranks tile the matrix once."""
+    for N, world, nb in [(10000, 2, 4), (10000, 8, 4), (10000, 4, 4), (2100, 2, 4), (5000, 5, 3), (700, 3, 2), (50000, 8, 4),
+                         (1300, 2, 4)]:
+        sh = sharded.shard_size(N, world)
+        ts, T = sh // TILE, (N + TILE - 1) // TILE
+        bands = sharded.shard_bands(sh, nb)
+        assert bands[0][0] == 0 and bands[-1][1] == ts and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+
+        def band_of(t):
+            return [b for b, (lo, hi) in enumerate(bands) if lo <= t % ts < hi][0]
+
+        seen, cover = set(), np.zeros((T, T), np.int32)
+        for r in range(world):
+            steps, pulls, n_seg = sharded.banded_pull_plan(N, world, r, sh, nb)
+            assert pulls == sharded.peer_tile_plan(N, world, r, sh)[1] and len(steps) == nb
+            tiles = [t for st in steps for t in st[0]]
+            seg = [g for st in steps for g in st[1]]
+            assert seg == sorted(seg) and (not seg or seg[-1] == n_seg - 1)
+            for s, (tl, _) in enumerate(steps):
+                for ti, tj, dep in tl:
+                    assert ti <= tj and (ti, tj) not in seen
+                    seen.add((ti, tj))
+                    if dep < 0:
+                        assert ti // ts == r == tj // ts and band_of(tj) == s
+                    else:
+                        q, br = divmod(dep, nb)
+                        own_t, rem_t = (ti, tj) if ti // ts == r else (tj, ti)
+                        assert q in pulls and rem_t // ts == q and own_t // ts == r
+                        assert band_of(rem_t) == br and max(band_of(own_t), br) == s
+            for regs in sharded.segment_regions(tiles, seg, N):
+                for a, b, c, d in regs:
+                    cover[a // TILE:(b + TILE - 1) // TILE, c // TILE:(d + TILE - 1) // TILE] += 1
+        assert len(seen) == T * (T + 1) // 2 and (cover == 1).all(), (N, world)
