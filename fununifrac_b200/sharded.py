@@ -472,10 +472,12 @@ class ShardedAllPairs:
             tiles_b += self.offdiag_tiles
             seg_b += [4 + sg - first_off for t, sg in zip(self.tiles, self.seg) if t[2] >= 0]
             self.plan_banded = _SegmentPlan(tiles_b, seg_b, segment_regions(tiles_b, seg_b, N), 1)
-        # host-buffer form with band-wise pulls (weighted L1, direct --L2): see _compute_peer_band_pulls
+        # host-buffer form with band-wise pulls (weighted L1, direct --L2): see _compute_peer_band_pulls.  EXPERIMENTAL, off
+        # unless FUF_BAND_PULLS=1: green in the gloo emulation (world 2/3/4) and with 2-3 ranks sharing one B200, but on two
+        # real B200s the step ended in a kernel's bounded-wait trap (cause not found within this round's GPU budget).
         self.bp = None
         nb = N_PULL_BANDS
-        if not self.use_gram and sh // TILE >= nb and os.environ.get("FUF_BAND_PULLS", "1") != "0":
+        if not self.use_gram and sh // TILE >= nb and os.environ.get("FUF_BAND_PULLS", "0") == "1":
             steps, _, _ = banded_pull_plan(N, world, rank, sh, nb)
             work = [t for st in steps for t in st[0]]
             work_seg = [g for st in steps for g in st[1]]
@@ -663,7 +665,7 @@ class ShardedAllPairs:
         mark("refine_end")
 
     def _compute_peer_band_pulls(self, X_local, D_target, mark, host_src):
-        """Host-buffer form of the peer step with BAND-WISE pulls (weighted L1, direct --L2).
+        """Host-buffer form of the peer step with BAND-WISE pulls (weighted L1, direct --L2) — experimental, FUF_BAND_PULLS=1.
 
         Every rank uploads its shard in N_PULL_BANDS bands of whole tiles.  As soon as band s has landed it is pushed up
         and announced: a 4-byte copy of the step's epoch into the ``ready`` word (shard, band) of every rank that pulls

@@ -939,6 +939,8 @@ def test_sharded_job_ranks_sharing_one_gpu(ranks, N, mode):
     # persistent CTA spinning for its shard on every SM such a copy could never start (measured: N = 2,100 deadlocks into
     # the kernels' bounded-wait trap).  Between real GPUs the pulls are copy-engine transfers and need no SM.
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0], FUF_SM_LIMIT="140")
+    if N in (2100, 1700):
+        env["FUF_BAND_PULLS"] = "1"        # the experimental band-wise pulls of the host-buffer form (off by default)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr",
            "127.0.0.1", "--master-port", "29543", os.path.join(repo, "tests", "multi_gpu_worker.py"), str(N), mode]
     res = subprocess.run(cmd, cwd=repo, env=env, capture_output=True, text=True, timeout=900)

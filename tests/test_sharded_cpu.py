@@ -388,6 +388,8 @@ def test_sharded_exchange_gloo(world, N, l2, peer, tmp_path, monkeypatch):
     collective form (all-gather, tile rows, packed gather) the Gram path still uses."""
     if world == 3:      # once through the named shared-memory file instead of /proc/<pid>/fd
         monkeypatch.setenv("FUF_SHARED_NO_PROCFD", "1")
+    if N in (2300, 1600):   # the experimental band-wise pulls of the host-buffer form (off by default)
+        monkeypatch.setenv("FUF_BAND_PULLS", "1")
     out = str(tmp_path / "D.npy")
     mp.spawn(_worker, args=(world, _free_port(), N, l2, out, peer), nprocs=world, join=True)
     assert np.load(out).shape == (N, N)
