@@ -123,7 +123,8 @@ struct GramJob {
 
 struct fuf_ctx {
     int device = 0;
-    int sm_count = 0;
+    int sm_count = 0;          // SMs the persistent grids are sized for (fuf_set_sm_limit)
+    int sm_count_default = 0;  // ... at context creation: the device's count, or FUF_SM_LIMIT
     int32_t n = 0;
     int32_t n_leaves = 0, depth = 0, n_zero_len = 0;
     bool contiguous = true;  // every subtree is a contiguous postorder range (true DFS postorder)

@@ -357,6 +357,7 @@ extern "C" int fuf_tree_create(fuf_ctx **out, int device, const int32_t *parent_
         const int v = atoi(lim);
         if (v >= 2 && v < ctx->sm_count) ctx->sm_count = v;
     }
+    ctx->sm_count_default = ctx->sm_count;
     ctx->n = n;
     ctx->parent.assign(parent_h, parent_h + n);
 
@@ -757,6 +758,18 @@ extern "C" int fuf_copy2d_async(fuf_ctx *ctx, void *dst, size_t dst_pitch, const
     FUF_REQUIRE(dst_pitch >= width && src_pitch >= width, "fuf_copy2d_async: pitch smaller than the row width");
     FUF_CUDA(cudaSetDevice(ctx->device));
     return copy2d_async(dst, dst_pitch, src, src_pitch, width, rows, (cudaStream_t)stream);
+}
+
+// Size the persistent grids of this context for `sms` SMs (0: the context's default; < 0: that many fewer than the default).  A caller that makes a running tile
+// kernel wait for a strided peer copy must leave SMs free: the driver may run such a copy as an SM kernel, and with a
+// persistent CTA spinning on every SM it would never start.
+extern "C" int fuf_set_sm_limit(fuf_ctx *ctx, int32_t sms)
+{
+    FUF_REQUIRE(ctx != nullptr, "fuf_set_sm_limit: null context");
+    // never above what the context started with (the device's count, or FUF_SM_LIMIT for a device shared with others)
+    const int want = sms < 0 ? ctx->sm_count_default + sms : sms;
+    ctx->sm_count = (sms != 0 && want >= 2 && want < ctx->sm_count_default) ? want : ctx->sm_count_default;
+    return FUF_OK;
 }
 
 extern "C" int64_t fuf_launch_count(const fuf_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -25,7 +25,7 @@ AP_VALIDATE, AP_NO_REFINE, AP_NO_GRAM = 1, 2, 4
 GRAM_MIN_SAMPLES = 512
 GRAM_KAPPA = 2.9e-3     # dropped digit-product orders: |error| <= 1.44e-9 (h2_i + h2_j) <= 0.5e-6 D
 CENTER_SAMPLES = 32
-ABI_VERSION = 12
+ABI_VERSION = 13
 GRAM_SEG_UNITS = 16     # fuf_gram_tiles: counts per finished item (FUF_GRAM_SEG_UNITS)
 CRIT_ROUNDING, CRIT_LINEAR = 0, 1
 
@@ -111,6 +111,8 @@ def load_library() -> ctypes.CDLL:
         L.fuf_name_index_destroy.argtypes = [vp]
         L.fuf_ingest_gather_csv.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), i32, ctypes.c_char_p, ci, ci, ci, vp, i64,
                                             vp, ctypes.c_char_p, i64, ctypes.c_char_p, i64]
+        L.fuf_set_sm_limit.argtypes = [vp, i32]
+        L.fuf_set_sm_limit.restype = ci
         L.fuf_debug_pair_plan.argtypes = [i32, i32, i32, i32, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.fuf_debug_pair_plan.restype = ci
         L.fuf_launch_count.argtypes = [vp]
@@ -490,6 +492,10 @@ class TreeContext:
         st = (stream or torch.cuda.current_stream()).cuda_stream
         _check(self._lib.fuf_stream_write_u32(self.handle, flags.data_ptr() + 4 * index, value & 0xFFFFFFFF, st),
                "fuf_stream_write_u32")
+
+    def set_sm_limit(self, sms: int = 0):
+        """Size the persistent grids for ``sms`` SMs (0: the whole device) — ``fuf_set_sm_limit``."""
+        _check(self._lib.fuf_set_sm_limit(self.handle, int(sms)), "fuf_set_sm_limit")
 
     def stream_wait_u32(self, words, index: int, value: int, stream=None):
         """The stream's later work waits until words[index] >= value (``fuf_stream_wait_u32``)."""

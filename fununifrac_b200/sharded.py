@@ -692,6 +692,10 @@ class ShardedAllPairs:
         if forward:
             self._begin_segments()
         ops.fill_(self.epoch_word, self.epoch)
+        # the tile launches of this form wait, running, for band pulls — strided peer copies, which the driver may execute
+        # as SM kernels: leave a few SMs without a persistent CTA, or such a copy could never start (seen on two B200s:
+        # the kernels' bounded waits trapped; the whole-shard pulls of the other forms are contiguous copy-engine transfers)
+        ops.set_sm_limit(-8)
         mark("start")
         events = []
         for s0, s1 in bp["own"]:                   # all uploads are queued up front on the copy stream
@@ -724,6 +728,7 @@ class ShardedAllPairs:
                                    self.seg_done if forward else None)
                 if forward:
                     self._forward_segments(plan, D_comp, D_target, *bp["seg_range"][s])
+        ops.set_sm_limit(0)
         mark("push_end")
         self._x_local = X_local
         mark("pair_begin")
@@ -1017,6 +1022,10 @@ class CudaOps:
 
     def fill_(self, t, value):
         t.fill_(value)
+
+    def set_sm_limit(self, sms):
+        """sms > 0: size the persistent grids for that many SMs; sms < 0: leave -sms SMs free; 0: the context's default."""
+        self.ctx.set_sm_limit(sms)
 
     def copy_cols(self, dst, src, c0, c1, stream):
         """dst[:, c0:c1] = src[:, c0:c1] for two [rows, cols] buffers of the same layout (a band of a shard's operands,

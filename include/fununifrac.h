@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define FUF_ABI_VERSION 12
+#define FUF_ABI_VERSION 13
 
 /* error codes */
 #define FUF_OK 0
@@ -393,6 +393,11 @@ int fuf_copy2d_async(fuf_ctx *ctx, void *dst, size_t dst_pitch, const void *src,
 int fuf_debug_tree_plan(const int32_t *parent_h, int32_t n, int32_t *parent_local, int32_t *cp_after,
                         uint8_t *is_span, int32_t *span_out, int32_t *n_span, int32_t *n_cp, int32_t *contiguous,
                         int32_t *chunk);
+
+/* Size the persistent grids of this context for `sms` SMs (0 = the context's default, the whole device unless FUF_SM_LIMIT
+ * is set; < 0 = that many fewer than the default).  For callers that make a running tile kernel wait
+ * for a strided peer copy, which the driver may execute as an SM kernel (it needs an SM no persistent CTA is spinning on). */
+int fuf_set_sm_limit(fuf_ctx *ctx, int32_t sms);
 
 /* Test hook, host only (needs no device): the work plan of the all-pairs tile kernel for n_tiles tiles on sm_count SMs —
  * whole tiles round-robin for the full waves, equal spans of the (tile, stage) space for the last partial wave when

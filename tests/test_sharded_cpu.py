@@ -141,6 +141,9 @@ class OracleOps:
     def fill_(self, t, value):
         t.fill_(value)
 
+    def set_sm_limit(self, sms):
+        self.sm_limit = sms
+
     def copy_cols(self, dst, src, c0, c1, stream):
         self.pulled_bands = getattr(self, "pulled_bands", 0) + 1
         dst[:, c0:c1] = src[:, c0:c1]
