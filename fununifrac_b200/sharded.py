@@ -473,8 +473,8 @@ class ShardedAllPairs:
             seg_b += [4 + sg - first_off for t, sg in zip(self.tiles, self.seg) if t[2] >= 0]
             self.plan_banded = _SegmentPlan(tiles_b, seg_b, segment_regions(tiles_b, seg_b, N), 1)
         # host-buffer form with band-wise pulls (weighted L1, direct --L2): see _compute_peer_band_pulls.  EXPERIMENTAL, off
-        # unless FUF_BAND_PULLS=1: green in the gloo emulation (world 2/3/4) and with 2-3 ranks sharing one B200, but on two
-        # real B200s the step ended in a kernel's bounded-wait trap (cause not found within this round's GPU budget).
+        # unless FUF_BAND_PULLS=1: correct (gloo emulation with world 2/3/4, 2-3 ranks sharing one B200, two real B200s) but
+        # not yet faster — its strided band pulls run as SM kernels on the few SMs left free for them (par. 8).
         self.bp = None
         nb = N_PULL_BANDS
         if not self.use_gram and sh // TILE >= nb and os.environ.get("FUF_BAND_PULLS", "0") == "1":
