@@ -29,12 +29,41 @@
 #include <unordered_map>
 #include <vector>
 
+#include <immintrin.h>
+
 #include "common.cuh"
 
 struct fuf_name_index {
     std::deque<std::string> names;                            // owns the text the views of `map` point into
     std::unordered_map<std::string_view, int32_t> map;        // looked up with views into the file buffer: no copies
     int32_t n = 0;
+    // Names of at most 8 bytes (KO ids are 6: "K01234") also live in a flat open-addressing table keyed by the bytes
+    // themselves packed into one 64-bit word: one multiply, one cache line, no string comparison.  (key 0 = empty slot; a
+    // packed name is never 0 because names are not empty and hold no NUL bytes.)
+    std::vector<uint64_t> flat_key;
+    std::vector<int32_t> flat_val;
+    uint64_t flat_mask = 0;
+    static inline uint64_t pack(const char *p, size_t len)
+    {
+        uint64_t w = 0;
+        memcpy(&w, p, len);            // len <= 8
+        return w | ((uint64_t)len << 60);   // len <= 7: the top byte is free for the length
+    }
+    static inline uint64_t mix(uint64_t w) { return (w * 0x9E3779B97F4A7C15ull) >> 20; }
+    // index of the name, or -1
+    inline int32_t find(const char *p, size_t len) const
+    {
+        if (len <= 7 && len > 0 && flat_mask) {
+            const uint64_t key = pack(p, len);
+            for (uint64_t h = mix(key) & flat_mask;; h = (h + 1) & flat_mask) {
+                if (flat_key[h] == key) return flat_val[h];
+                if (flat_key[h] == 0) break;
+            }
+            return -1;
+        }
+        auto it = map.find(std::string_view(p, len));
+        return it == map.end() ? -1 : it->second;
+    }
 };
 
 namespace fuf {
@@ -152,6 +181,13 @@ static bool is_na(const char *s, size_t len)
 {
     static const char *na[] = {"", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN",
                                "<NA>", "N/A", "NA", "NULL", "NaN", "None", "n/a", "nan", "null"};
+    if (len == 0) return true;
+    // every NA spelling is at most 8 characters long and starts with one of  # - 1 < N n : nearly every real field is
+    // rejected here without a string comparison
+    if (len > 8) return false;
+    const char c = s[0];
+    if (c != '#' && c != '-' && c != '1' && c != '<' && c != 'N' && c != 'n') return false;
+    if (c == '1' && !(len >= 6 && s[1] == '.' && s[2] == '#')) return false;
     for (const char *w : na)
         if (strlen(w) == len && memcmp(w, s, len) == 0) return true;
     return false;
@@ -178,6 +214,11 @@ struct Field {
     size_t len;
     bool quoted;
 };
+
+// Set when a record ended on a '\r' that no '\n' follows (classic Mac line ends).  pandas' C tokenizer has quirks of its
+// own there (with quoted fields it can fail with "Buffer overflow caught" or shift columns), so such a file is handed to
+// the pandas route as a whole: whatever it returns or raises is then the reference's behaviour by construction.
+static thread_local bool t_lone_cr = false;
 
 // First ',', '\n' or '\r' at or after p (end if none): eight bytes at a time.
 static inline const char *skip_plain(const char *p, const char *end)
@@ -276,12 +317,84 @@ static bool tokenize_record(const char *&cur, const char *end, std::deque<std::s
         if (*cur == '\r') {
             cur++;
             if (cur < end && *cur == '\n') cur++;
+            else t_lone_cr = true;
         } else {
             cur++;  // '\n'
         }
         break;
     }
     return true;
+}
+
+// Fast path for the data rows of a gather CSV: a record without any quote character is just its text up to the first
+// '\n' / '\r' split at the commas.  32 bytes at a time (AVX2, checked at run time), the offsets of all commas are
+// collected; the two wanted fields are then read off directly.  Returns false — nothing consumed — when the record
+// holds a quote (pandas' quoting rules live in tokenize_record), has more commas than the buffer, or the CPU has no AVX2.
+constexpr int FAST_MAX_COMMAS = 256;
+struct FastRow {
+    const char *row_end, *next;
+    int n_commas;
+    uint32_t comma[FAST_MAX_COMMAS];
+};
+__attribute__((target("avx2"))) static bool scan_row_avx2(const char *cur, const char *end, FastRow &r)
+{
+    const __m256i vc = _mm256_set1_epi8(','), vn = _mm256_set1_epi8('\n'), vr = _mm256_set1_epi8('\r'), vq = _mm256_set1_epi8('"');
+    const char *p = cur;
+    int nc = 0;
+    const char *row_end = nullptr;
+    while (p + 32 <= end) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+        uint32_t mc = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vc));
+        const uint32_t ml = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(_mm256_cmpeq_epi8(v, vn), _mm256_cmpeq_epi8(v, vr)));
+        uint32_t mq = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vq));
+        if (ml) {
+            const uint32_t first = (uint32_t)__builtin_ctz(ml);
+            const uint32_t keep = first ? (0xFFFFFFFFu >> (32 - first)) : 0u;
+            mc &= keep;
+            mq &= keep;
+            row_end = p + first;
+        }
+        if (mq) return false;
+        if (nc + __builtin_popcount(mc) > FAST_MAX_COMMAS) return false;
+        const uint32_t base = (uint32_t)(p - cur);
+        while (mc) {
+            r.comma[nc++] = base + (uint32_t)__builtin_ctz(mc);
+            mc &= mc - 1;
+        }
+        if (row_end) break;
+        p += 32;
+    }
+    if (!row_end) {
+        for (; p < end; p++) {
+            const char c = *p;
+            if (c == '\n' || c == '\r') break;
+            if (c == '"') return false;
+            if (c == ',') {
+                if (nc >= FAST_MAX_COMMAS) return false;
+                r.comma[nc++] = (uint32_t)(p - cur);
+            }
+        }
+        row_end = p;
+    }
+    r.row_end = row_end;
+    r.n_commas = nc;
+    const char *next = row_end;
+    if (next < end) {
+        if (*next == '\r') {
+            next++;
+            if (next < end && *next == '\n') next++;
+            else t_lone_cr = true;
+        } else {
+            next++;
+        }
+    }
+    r.next = next;
+    return true;
+}
+static inline bool cpu_has_avx2()
+{
+    static const bool has = __builtin_cpu_supports("avx2") && !getenv("FUF_INGEST_NO_AVX2");
+    return has;
 }
 
 // All fields of a record (the header).
@@ -336,6 +449,7 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
     std::vector<Field> fields;
     std::deque<std::string> scratch;   // stable addresses: fields point into its strings
     bool blank = false;
+    t_lone_cr = false;
     // header
     do {
         if (!next_record(cur, end, fields, scratch, &blank)) return set_msg(res, 3, std::string("No columns to parse from file ") + path);
@@ -351,19 +465,34 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
     if (name_col < 0) return set_msg(res, 5, "name");
     long long line = 1;
     const size_t c_name = (size_t)name_col, c_key = (size_t)key_col;
+    const bool fast = cpu_has_avx2();
+    FastRow row;
     for (;;) {
         // data rows: only the two columns the path uses are materialised, the rest is skipped and counted
         Field f_name{nullptr, 0, false}, f_key{nullptr, 0, false};
         bool have_name = false, have_key = false, first_empty = false;
         size_t n_fields = 0;
-        if (!tokenize_record(cur, end, scratch, &n_fields, &first_empty,
-                             [&](size_t i) { return i == c_name || i == c_key; },
-                             [&](size_t i, const Field &f) {
-                                 if (i == c_name) f_name = f, have_name = true;
-                                 if (i == c_key) f_key = f, have_key = true;
-                             }))
+        if (cur >= end) break;
+        if (fast && scan_row_avx2(cur, end, row)) {
+            n_fields = (size_t)row.n_commas + 1;
+            auto field = [&](size_t i) {
+                const char *b = i == 0 ? cur : cur + row.comma[i - 1] + 1;
+                const char *e = i < (size_t)row.n_commas ? cur + row.comma[i] : row.row_end;
+                return Field{b, (size_t)(e - b), false};
+            };
+            first_empty = row.n_commas == 0 ? row.row_end == cur : row.comma[0] == 0;
+            if (c_name < n_fields) f_name = field(c_name), have_name = true;
+            if (c_key < n_fields) f_key = field(c_key), have_key = true;
+            cur = row.next;
+        } else if (!tokenize_record(cur, end, scratch, &n_fields, &first_empty,
+                                    [&](size_t i) { return i == c_name || i == c_key; },
+                                    [&](size_t i, const Field &f) {
+                                        if (i == c_name) f_name = f, have_name = true;
+                                        if (i == c_key) f_key = f, have_key = true;
+                                    }))
             break;
         line++;
+        if (t_lone_cr) return set_msg(res, 3, "carriage-return line ends: left to the pandas route");
         if (n_fields == 1 && first_empty) continue;        // blank line
         if (n_fields > n_cols)
             return set_msg(res, 3, "Error tokenizing data. C error: Expected " + std::to_string(n_cols) + " fields in line " +
@@ -395,12 +524,12 @@ static void parse_file(const fuf_name_index *index, const char *path, const std:
                 break;
             }
         const std::string_view ko(b, (size_t)(e - b));
-        auto it = index->map.find(ko);
-        if (it == index->map.end()) {
+        const int32_t at = index->find(ko.data(), ko.size());
+        if (at < 0) {
             res.warnings.append(ko.data(), ko.size());
             res.warnings.push_back('\n');
         } else {
-            P[it->second] = value;
+            P[at] = value;
         }
     }
     const double total = np_pairwise_sum(P, n);
@@ -430,6 +559,21 @@ extern "C" int fuf_name_index_create(fuf_name_index **out, const char *const *na
     for (int32_t k = 0; k < n; k++) {   // a repeated name keeps its last index (dict semantics)
         ix->names.emplace_back(names[k]);
         ix->map[std::string_view(ix->names.back())] = k;
+    }
+    // flat table over the final (name -> last index) map: names of 1..7 bytes without NUL bytes
+    size_t cap = 64;
+    while (cap < (size_t)n * 4) cap <<= 1;
+    ix->flat_key.assign(cap, 0);
+    ix->flat_val.assign(cap, -1);
+    ix->flat_mask = cap - 1;
+    for (const auto &kv : ix->map) {
+        const std::string_view nm = kv.first;
+        if (nm.empty() || nm.size() > 7 || memchr(nm.data(), 0, nm.size())) continue;
+        const uint64_t key = fuf_name_index::pack(nm.data(), nm.size());
+        uint64_t h = fuf_name_index::mix(key) & ix->flat_mask;
+        while (ix->flat_key[h] != 0) h = (h + 1) & ix->flat_mask;
+        ix->flat_key[h] = key;
+        ix->flat_val[h] = kv.second;
     }
     *out = ix;
     return FUF_OK;

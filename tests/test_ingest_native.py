@@ -169,3 +169,72 @@ def test_many_files_threads_and_order(tmp_path, capsys):
     make_emd_input.native_profiles_to_matrix(files, inp, "f_unique_weighted", True, 4, out=out)
     assert np.array_equal(out[:120, :n], python_rows(files, inp, "f_unique_weighted", True)) and np.all(out[120:] == -1)
     capsys.readouterr()
+
+
+def test_fast_row_scanner_matches_pandas_on_random_layouts(toy, tmp_path, capsys):
+    """The data rows go through a 32-bytes-at-a-time scanner (AVX2) unless a record holds a quote character.  Random
+    layouts exercise what that scanner must get right: records of every length around the 32-byte blocks, '\\n', '\\r\\n' and
+    lone '\\r' terminators, a missing final newline, blank lines, a trailing comma at the end of the input, quoted fields
+    (with commas, doubled quotes) in the wanted and in other columns, files shorter than one block — against pandas + the
+    Python mirror, bit for bit; the same files once more with the scanner switched off (subprocess) must give the same rows."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(5)
+    nodes = ["d", "e", "f", "g", "b", "c"]
+    files = []
+    for t in range(60):
+        width = int(rng.integers(2, 40))                    # columns: name, median_abund and filler columns
+        pos = rng.choice(width, 2, replace=False)
+        cols = [f"c{i}" for i in range(width)]
+        cols[pos[0]], cols[pos[1]] = "name", "median_abund"
+        nl = ["\n", "\r\n", "\r"][t % 3] if t % 7 else "\n"
+        lines = [",".join(cols)]
+        for r in range(int(rng.integers(1, 12))):
+            rec = []
+            for c in cols:
+                if c == "name":
+                    nm = f"ko:{nodes[int(rng.integers(len(nodes)))]}"
+                    style = int(rng.integers(5))
+                    rec.append([nm, f"x|{nm}", f'"{nm}"', f'"pre, with comma|{nm}"', f'"say ""hi""|{nm}"'][style])
+                elif c == "median_abund":
+                    rec.append(["3", "2.5", "1e-3", "", "NA", "0.125", "17.0"][int(rng.integers(7))])
+                else:
+                    k = int(rng.integers(0, 14))
+                    filler = "".join(rng.choice(list("abcxyz0123456789. "), k))
+                    rec.append(f'"{filler},q"' if rng.random() < 0.05 else filler)
+            lines.append(",".join(rec))
+            if rng.random() < 0.15:
+                lines.append("")                             # blank line
+        text = nl.join(lines)
+        if t % 4:
+            text += nl                                       # (else: no final newline)
+        if t % 11 == 0 and nl == "\n":
+            text += ",".join([""] * width)                   # last record: only delimiters, ends on a comma at end of input
+        path = str(tmp_path / f"r{t:02d}_gather.csv")
+        with open(path, "w", newline="") as f:
+            f.write(text)
+        files.append(path)
+    good, want = [], []
+    for path in files:
+        try:
+            row = python_rows([path], toy, "median_abund")
+        except Exception:
+            # the pandas route rejects the file (e.g. an all-NA profile): the native route must refuse it too
+            with pytest.raises(Exception):
+                make_emd_input.native_profiles_to_matrix([path], toy, "median_abund", False, 1)
+            continue
+        good.append(path)
+        want.append(row[0])
+    capsys.readouterr()
+    assert len(good) >= 30
+    got = make_emd_input.native_profiles_to_matrix(good, toy, "median_abund", False, 2)[1]
+    assert np.array_equal(got, np.stack(want), equal_nan=True)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from fununifrac_b200.factory import make_emd_input, make_tree; "
+            "inp = make_emd_input.tree_to_EMDU_input(make_tree.import_graph(%r), 'ko00001'); "
+            "X = make_emd_input.native_profiles_to_matrix(%r, inp, 'median_abund', False, 1)[1]; np.save(%r, X)")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    edge = os.path.join(repo, "tests", "golden", "data", "small_edge_list_with_lengths.txt")
+    out = str(tmp_path / "slow.npy")
+    subprocess.run([sys.executable, "-c", code % (repo, edge, good, out)], check=True, capture_output=True,
+                   env=dict(os.environ, FUF_INGEST_NO_AVX2="1"))
+    assert np.array_equal(np.load(out), got, equal_nan=True)
