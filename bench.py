@@ -829,10 +829,6 @@ PROFILE_GRAM = "r2_ncu_full_gram_pair_N50000.csv"
 
 
 def main():
-    # more hardware work queues than the default 8: the multi-GPU step keeps a compute, an upload/pull and a forwarding
-    # stream busy next to NCCL's own; streams that share a queue serialise behind each other's waits (must be set before
-    # the CUDA context exists)
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

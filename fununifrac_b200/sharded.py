@@ -418,22 +418,26 @@ class ShardedAllPairs:
         else:
             self.PS_buf = ops.peer_alloc((world, n, sh), "float32")
             self.PS = self.PS_buf.tensor
-            # band-wise pulls of the host-buffer form: the statistics travel with the bands (peer-readable), and every rank
-            # announces a pushed-up band by a 4-byte copy into the `ready` words of the ranks that pull its shard
-            self.stat_buf = ops.peer_alloc((world * sh,), "float64")
-            self.ready_buf = ops.peer_alloc((world * N_PULL_BANDS,), "int32")
-            dist.all_gather_object(handles, (self.PS_buf.handle, self.stat_buf.handle, self.ready_buf.handle,
+            # experimental band-wise pulls of the host-buffer form (FUF_BAND_PULLS=1): the statistics travel with the bands
+            # (peer-readable), and every rank announces a pushed-up band by a 4-byte copy into the `ready` words of the
+            # ranks that pull its shard
+            self.band_pulls = os.environ.get("FUF_BAND_PULLS", "0") == "1" and sh // TILE >= N_PULL_BANDS
+            self.stat_buf = ops.peer_alloc((world * sh,), "float64") if self.band_pulls else None
+            self.ready_buf = ops.peer_alloc((world * N_PULL_BANDS,), "int32") if self.band_pulls else None
+            dist.all_gather_object(handles, (self.PS_buf.handle, self.stat_buf.handle if self.band_pulls else None,
+                                             self.ready_buf.handle if self.band_pulls else None,
                                              self.D_buf.handle if rank == 0 else None))
             self.peer_PS = {q: ops.peer_open(handles[q][0], (world, n, sh), "float32") for q in self.pulls}
-            self.peer_stat = {q: ops.peer_open(handles[q][1], (world * sh,), "float64") for q in self.pulls}
-            self.consumers = [q for q in range(world) if q != rank and rank in peer_tile_plan(N, world, q, sh)[1]]
-            self.peer_ready = {q: ops.peer_open(handles[q][2], (world * N_PULL_BANDS,), "int32") for q in self.consumers}
+            if self.band_pulls:
+                self.peer_stat = {q: ops.peer_open(handles[q][1], (world * sh,), "float64") for q in self.pulls}
+                self.consumers = [q for q in range(world) if q != rank and rank in peer_tile_plan(N, world, q, sh)[1]]
+                self.peer_ready = {q: ops.peer_open(handles[q][2], (world * N_PULL_BANDS,), "int32") for q in self.consumers}
         if rank != 0:
             self.D_buf = ops.peer_open(handles[0][-1], (N, N), "float64")
         self.D = self.D_buf.tensor if rank == 0 else None
         self.D_target = self.D_buf.tensor         # rank 0's matrix, as seen from this rank
         self.P64S = None
-        self.stat = ops.empty((world * sh,), "float64") if self.use_gram else self.stat_buf.tensor
+        self.stat = self.stat_buf.tensor if (not self.use_gram and self.band_pulls) else ops.empty((world * sh,), "float64")
         self.center = ops.empty((n,), "float64")
         self.flags = ops.empty((world,), "int32")                         # arrival flag per shard
         self.list_cap = refine_budget(N)
@@ -477,7 +481,7 @@ class ShardedAllPairs:
         # not yet faster — its strided band pulls run as SM kernels on the few SMs left free for them (par. 8).
         self.bp = None
         nb = N_PULL_BANDS
-        if not self.use_gram and sh // TILE >= nb and os.environ.get("FUF_BAND_PULLS", "0") == "1":
+        if not self.use_gram and self.band_pulls:
             steps, _, _ = banded_pull_plan(N, world, rank, sh, nb)
             work = [t for st in steps for t in st[0]]
             work_seg = [g for st in steps for g in st[1]]
