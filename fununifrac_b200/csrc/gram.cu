@@ -1190,6 +1190,78 @@ static int gram_make_plan(fuf_ctx *ctx, const std::vector<float> &cstat, int32_t
 
 }  // namespace gram
 
+// Items (row tile x column-tile pair) of one launch of the CTA-pair kernel, in processing order, and — when n_seg_wanted
+// > 0 (full matrix only) — their completion segments: equally many tile rows each; `segs` receives the row boundary and
+// the counter target of every segment.
+//
+// L2 rasterisation (as in pairwise_f32): the 74 CTA pairs in flight stream their digit-plane panels at the same pace, so
+// a panel shared by several of their items is fetched from DRAM once.  Row-major order put one tile row and 74 column
+// pairs into a wave — 149 panels of 17 MB, 1.15 TB of DRAM reads per launch at N = 50,000 (ncu: 4.5 TB/s, L2 hit 38 %) —;
+// strips of ~12 tile rows walked column pair by column pair make it ~12 rows x 6 pairs = 24 panels.  With completion
+// segments a strip is a whole number of segments.
+static void plan_gram_items(int32_t tiles_per_dim, const int32_t *tile_rows_h, int32_t n_trows, int32_t n_seg_wanted,
+                            std::vector<gram::PairTile> &ptiles, GramSegments *segs)
+{
+    using namespace gram;
+    const bool full = tile_rows_h == nullptr;
+    int32_t per = 0;   // tile rows per completion segment
+    if (n_seg_wanted > 0 && full) {
+        const int32_t n_seg = std::min(std::min(n_seg_wanted, 4000), n_trows);
+        per = (n_trows + n_seg - 1) / n_seg;
+    }
+    if (full) {
+        const int32_t S = per > 0 ? per * ((GRAM_STRIP + per - 1) / per) : GRAM_STRIP;
+        for (int32_t r0 = 0; r0 < n_trows; r0 += S)
+            for (int32_t b = r0 / 2; 2 * b < tiles_per_dim; b++)
+                for (int32_t t = r0; t < std::min(n_trows, r0 + S); t++)
+                    if (b >= t / 2) ptiles.push_back(PairTile{t, b, t * TILE, 0});
+    } else {
+        for (int32_t c = 0; c < n_trows; c++) {
+            const int32_t t = tile_rows_h[c];
+            for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, c * TILE, 0});
+        }
+    }
+    if (per > 0 && segs) {
+        // once segment s (and every earlier one) is counted complete, rows [row_end[s-1], row_end[s]) x 128 of D are final
+        // in ALL columns — right of the diagonal by the segment's own tiles, left of it by the mirror stores of the earlier
+        // segments — and leave as one contiguous copy
+        for (int32_t t0 = 0; t0 < n_trows; t0 += per) {
+            segs->row_end.push_back(std::min(n_trows, t0 + per));
+            segs->expected.push_back(0);
+        }
+        for (PairTile &pt : ptiles) {
+            const int32_t seg = pt.ti / per;
+            pt.pad = (seg + 1) << 12;
+            segs->expected[seg] += GRAM_SEG_UNITS;
+        }
+    }
+}
+
+// Test hook, host only: the items of a full-matrix launch for `tiles_per_dim` tile rows as (ti, b, segment) rows.
+extern "C" int fuf_debug_gram_items(int32_t tiles_per_dim, int32_t n_seg_wanted, int32_t *rows_out, int32_t max_rows,
+                                    int32_t *n_rows, int32_t *seg_row_end, int32_t *seg_expected, int32_t max_seg, int32_t *n_seg)
+{
+    FUF_REQUIRE(tiles_per_dim > 0 && n_rows && n_seg, "fuf_debug_gram_items: bad argument");
+    std::vector<gram::PairTile> ptiles;
+    GramSegments segs;
+    plan_gram_items(tiles_per_dim, nullptr, tiles_per_dim, n_seg_wanted, ptiles, &segs);
+    *n_rows = (int32_t)ptiles.size();
+    *n_seg = (int32_t)segs.row_end.size();
+    if (rows_out) {
+        FUF_REQUIRE(max_rows >= *n_rows && max_seg >= *n_seg, "fuf_debug_gram_items: %d rows, %d segments needed", *n_rows, *n_seg);
+        for (size_t i = 0; i < ptiles.size(); i++) {
+            rows_out[3 * i] = ptiles[i].ti;
+            rows_out[3 * i + 1] = ptiles[i].b;
+            rows_out[3 * i + 2] = (ptiles[i].pad >> 12) - 1;
+        }
+        for (int32_t q = 0; q < *n_seg; q++) {
+            if (seg_row_end) seg_row_end[q] = segs.row_end[q];
+            if (seg_expected) seg_expected[q] = (int32_t)segs.expected[q];
+        }
+    }
+    return FUF_OK;
+}
+
 int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t shard, int64_t shard_stride,
                   const double *err_in, double *h2, double *err_out, const int32_t *tile_rows_h, int32_t n_tile_rows,
                   double *D, int64_t ldd, cudaStream_t stream, GramSegments *segs)
@@ -1325,43 +1397,8 @@ int pairwise_gram(fuf_ctx *ctx, const float *PT, int64_t N, int64_t ldp, int64_t
     if (use_pairs) {
         // CTA pairs: work item = row tile x two column tiles (2b, 2b+1); the half below the diagonal is computed and dropped
         std::vector<PairTile> ptiles;
-        const bool segmented = segs && segs->seg_done && segs->n_wanted > 0 && full;
-        int32_t per = 0;   // tile rows per completion segment
-        if (segmented) {
-            const int32_t n_seg = (int32_t)std::min<int64_t>(std::min(segs->n_wanted, 4000), n_trows);
-            per = (n_trows + n_seg - 1) / n_seg;
-        }
-        if (full) {
-            // L2 rasterisation (as in pairwise_f32): the 74 CTA pairs in flight stream their digit-plane panels at the
-            // same pace, so a panel shared by several of their items is fetched from DRAM once.  Row-major order put one
-            // tile row and 74 column pairs into a wave — 149 panels of 17 MB, 1.15 TB of DRAM reads per launch at
-            // N = 50,000 (ncu: 4.5 TB/s, L2 hit 38 %) —; strips of ~12 tile rows walked column pair by column pair make it
-            // ~12 rows x 6 pairs = 24 panels.  With completion segments a strip is a whole number of segments.
-            const int32_t S = per > 0 ? per * ((GRAM_STRIP + per - 1) / per) : GRAM_STRIP;
-            for (int32_t r0 = 0; r0 < n_trows; r0 += S)
-                for (int32_t b = r0 / 2; 2 * b < tiles_per_dim; b++)
-                    for (int32_t t = r0; t < std::min(n_trows, r0 + S); t++)
-                        if (b >= t / 2) ptiles.push_back(PairTile{t, b, t * TILE, 0});
-        } else {
-            for (int32_t c = 0; c < n_trows; c++) {
-                const int32_t t = tile_rows_h[c];
-                for (int32_t b = t / 2; 2 * b < tiles_per_dim; b++) ptiles.push_back(PairTile{t, b, c * TILE, 0});
-            }
-        }
-        if (segmented) {
-            // completion segments of equally many tile rows: once segment s (and every earlier one) is counted complete,
-            // rows [row_end[s-1], row_end[s]) x 128 of D are final in ALL columns — right of the diagonal by the segment's
-            // own tiles, left of it by the mirror stores of the earlier segments — and leave as one contiguous copy
-            for (int32_t t0 = 0; t0 < n_trows; t0 += per) {
-                segs->row_end.push_back(std::min(n_trows, t0 + per));
-                segs->expected.push_back(0);
-            }
-            for (PairTile &pt : ptiles) {
-                const int32_t seg = pt.ti / per;
-                pt.pad = (seg + 1) << 12;
-                segs->expected[seg] += GRAM_SEG_UNITS;
-            }
-        }
+        plan_gram_items((int32_t)tiles_per_dim, full ? nullptr : tile_rows_h, n_trows,
+                        (segs && segs->seg_done && full) ? segs->n_wanted : 0, ptiles, segs);
         static_assert(PLANE_BYTES == 8192 && TILE == 128, "umma_block10 hard-codes the plane and accumulator strides");
         static_assert(KC == 2 * KB, "the issue loops are written for two 32-row MMA blocks per stage");
         static_assert(sizeof(PairTile) == sizeof(Tile), "the pair tiles reuse the tile table's room");

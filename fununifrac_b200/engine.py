@@ -111,6 +111,8 @@ def load_library() -> ctypes.CDLL:
         L.fuf_name_index_destroy.argtypes = [vp]
         L.fuf_ingest_gather_csv.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), i32, ctypes.c_char_p, ci, ci, ci, vp, i64,
                                             vp, ctypes.c_char_p, i64, ctypes.c_char_p, i64]
+        L.fuf_debug_gram_items.argtypes = [i32, i32, vp, i32, ctypes.POINTER(i32), vp, vp, i32, ctypes.POINTER(i32)]
+        L.fuf_debug_gram_items.restype = ci
         L.fuf_set_sm_limit.argtypes = [vp, i32]
         L.fuf_set_sm_limit.restype = ci
         L.fuf_debug_pair_plan.argtypes = [i32, i32, i32, i32, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]

@@ -406,6 +406,12 @@ int fuf_set_sm_limit(fuf_ctx *ctx, int32_t sms);
 int fuf_debug_pair_plan(int32_t n_tiles, int32_t sm_count, int32_t stages_total, int32_t flush_stages, int32_t stream_k,
                         int32_t *rows_out, int32_t max_rows, int32_t *n_rows, int32_t *grid);
 
+/* Test hook, host only: the work items (row tile ti, column-tile pair b, completion segment or -1) of a full-matrix launch
+ * of the CTA-pair Gram kernel for tiles_per_dim tile rows, in processing order; seg_row_end / seg_expected (may be NULL):
+ * the tile-row boundary and the counter target of every segment.  rows_out may be NULL to query the counts. */
+int fuf_debug_gram_items(int32_t tiles_per_dim, int32_t n_seg_wanted, int32_t *rows_out, int32_t max_rows, int32_t *n_rows,
+                         int32_t *seg_row_end, int32_t *seg_expected, int32_t max_seg, int32_t *n_seg);
+
 /* Test hook, host only: the per-node plan words of the TMA push-up kernel (see PushNode in csrc/common.cuh),
  * ceil(n / 32) * 32 entries; *usable = 0 (meta_out untouched) when the tree cannot use that kernel. */
 int fuf_debug_push_meta(const int32_t *parent_h, int32_t n, int32_t *meta_out, int32_t *usable);

@@ -67,6 +67,42 @@ def test_pair_work_plan_covers_every_stage_once(n_tiles, sms):
             assert not slots
 
 
+@pytest.mark.parametrize("T,n_seg", [(391, 32), (391, 0), (64, 32), (5, 3), (1, 1), (129, 16), (40, 64)])
+def test_gram_item_order_and_segments(T, n_seg):
+    """Items of a full-matrix launch of the CTA-pair Gram kernel: every (row tile, column-tile pair) of the upper triangle
+    exactly once; rasterised in strips that are a whole number of completion segments; a segment's counter target is its
+    item count x 16; any 74 consecutive items (the CTA pairs in flight) touch few distinct panels."""
+    import ctypes
+    L = engine.load_library()
+    nr, ns = ctypes.c_int32(), ctypes.c_int32()
+    assert L.fuf_debug_gram_items(T, n_seg, None, 0, ctypes.byref(nr), None, None, 0, ctypes.byref(ns)) == 0
+    rows = np.zeros((nr.value, 3), np.int32)
+    row_end, expected = np.zeros(max(1, ns.value), np.int32), np.zeros(max(1, ns.value), np.int32)
+    assert L.fuf_debug_gram_items(T, n_seg, rows.ctypes.data, nr.value, ctypes.byref(nr), row_end.ctypes.data,
+                                  expected.ctypes.data, len(row_end), ctypes.byref(ns)) == 0
+    want = {(t, b) for t in range(T) for b in range(t // 2, (T + 1) // 2)}
+    assert len(rows) == len(want) and {(int(t), int(b)) for t, b, _ in rows} == want
+    if n_seg == 0:
+        assert ns.value == 0 and (rows[:, 2] == -1).all()
+    else:
+        assert 1 <= ns.value <= min(n_seg, T) and row_end[ns.value - 1] == T and (np.diff(row_end[:ns.value]) > 0).all()
+        per = int(row_end[0])
+        assert (rows[:, 2] == rows[:, 0] // per).all()
+        counts = np.bincount(rows[:, 2], minlength=ns.value)
+        assert (expected[:ns.value] == counts * engine.GRAM_SEG_UNITS).all()
+        first = [int(np.argmax(rows[:, 2] == s)) for s in range(ns.value)]
+        last = [len(rows) - 1 - int(np.argmax(rows[::-1, 2] == s)) for s in range(ns.value)]
+        assert last == sorted(last)                                  # segments complete in order
+        strip = per * -(-12 // per)
+        assert all(first[s] > last[s - strip // per] for s in range(strip // per, ns.value))   # ... strip by strip
+    if T >= 128:                                                     # locality of the 74 item pairs in flight
+        worst = 0
+        for at in range(0, len(rows) - 74, 997):
+            win = rows[at:at + 74]
+            worst = max(worst, len(set(win[:, 0])) + 2 * len(set(win[:, 1])))
+        assert worst <= 64, worst                                    # (a window that straddles two strips; row-major: 149)
+
+
 def test_integration_stub_compiles_and_binds():
     """The ctypes block of INTEGRATION.md (executed against the oracle by the GPU test test_integration_stub_runs) is valid
     Python and every entry point it binds is exported — checked here without a GPU."""
